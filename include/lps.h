@@ -1,0 +1,202 @@
+/*
+ * lps.h — C ABI of the B200-native read-to-variant hot path of LongPhase-S.
+ *
+ * This is the drop-in boundary.  The reference has no FFI; its seams are
+ * C++ member functions inside one binary.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  All functions return
+ * LPS_OK (0) or a negative lps_status; none of them ever calls exit().  lps_last_error()
+ * returns a human readable message for the last failure on that context.
+ *
+ * Threading: one context per (GPU, host thread).  A context is thread-compatible, not
+ * thread-safe.  All pointers in the argument structs are HOST pointers (pageable or pinned)
+ * unless the struct says otherwise; the library copies what it needs before returning unless
+ * the function is documented as asynchronous.
+ *
+ * There is no CPU fallback: every compute entry point runs hand-written sm_100a kernels and
+ * fails with LPS_E_CUDA when no device is usable.
+ */
+#ifndef LPS_H
+#define LPS_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lps_ctx lps_ctx;
+
+typedef enum {
+    LPS_OK = 0,
+    LPS_E_ARG = -1,       /* bad argument (null pointer, unsorted positions, ...)            */
+    LPS_E_CUDA = -2,      /* CUDA runtime failure; message has the cudaError string          */
+    LPS_E_STATE = -3,     /* call order violated (e.g. build_edges before call_alleles)      */
+    LPS_E_CIGAR = -4,     /* unsupported CIGAR op (reference: exit(1), ParsingBam.cpp:1625)  */
+    LPS_E_NOMEM = -5
+} lps_status;
+
+/* ---- variant table of one contig ------------------------------------------------------- *
+ * Replaces the per-contig std::map<int,RefAlt> copy made in BamParser::BamParser
+ * (src/phase/ParsingBam.cpp:1207-1235) and the std::map<int,MultiGenomeVar> of the tag family
+ * (src/haplotag/HaplotagType.h:110-162).  SoA, strictly ascending by pos (0-based).        */
+typedef struct {
+    int32_t n;
+    const int32_t *pos;       /* 0-based position (rec->pos)                                  */
+    const uint8_t *ref0;      /* first character of REF (ASCII, case preserved)               */
+    const uint8_t *alt0;      /* first character of ALT                                       */
+    const uint16_t *ref_len;  /* strlen(REF), saturated at 65535                              */
+    const uint16_t *alt_len;  /* strlen(ALT)                                                  */
+    /* --- tag-family only; may be NULL for `phase` ------------------------------------------ */
+    const uint8_t *hp1_is_alt; /* 1 when HP1 carries ALT (GT 1|0), 0 when HP1 carries REF (0|1) */
+    const int32_t *ps;         /* phase-set id of the NORMAL record (PS), 0 = none              */
+    const uint8_t *gt_kind;    /* GenomeType: 1 PHASED_HETERO, 2 UNPHASED_HETERO, 3 UNPHASED_HOMO */
+} lps_variants;
+
+/* ---- a batch of decoded alignments of ONE contig, in BAM (coordinate) order ------------- *
+ * Replaces the bam1_t handed to BamParser::get_snp (src/phase/ParsingBam.cpp:1303) and to
+ * ChromosomeProcessor::processRead (src/haplotag/HaplotagParsingBam.h:360-367).            */
+typedef struct {
+    int32_t n_reads;
+    const int32_t *ref_start;   /* core.pos                                                   */
+    const int32_t *l_qseq;      /* core.l_qseq                                                */
+    const uint32_t *n_cigar;    /* core.n_cigar                                               */
+    const uint64_t *cigar_off;  /* first op of read r in cigar[], in uint32 units             */
+    const uint64_t *seq_off;    /* first byte of read r in seq4[] (BAM 4-bit packing, 2/byte) */
+    const uint64_t *qual_off;   /* first byte of read r in qual[]                             */
+    const uint16_t *flag;       /* core.flag                                                  */
+    const uint8_t *mapq;        /* core.qual                                                  */
+    const int32_t *name_rank;   /* rank of the read NAME in lexicographic (std::string <) order
+                                   among the names of this batch; alignments sharing a name share
+                                   a rank.  Needed because the reference folds float edge weights
+                                   in std::map<std::string,...> order (PhasingGraph.cpp:697,848) */
+    const uint32_t *cigar;      /* BAM encoding len<<4|op                                     */
+    uint64_t cigar_len;         /* total uint32 in cigar[]                                    */
+    const uint8_t *seq4;
+    uint64_t seq_bytes;
+    const uint8_t *qual;
+    uint64_t qual_bytes;
+} lps_read_batch;
+
+/* one allele call: replaces struct Variant (src/shared/Util.h:63-75)                        */
+typedef struct {
+    int32_t var;      /* index into the contig's variant table                                */
+    int16_t quality;  /* base quality, or -4 indel / -5 danger indel (ParsingBam.cpp:1485-1490) */
+    int8_t allele;    /* 0 REF, 1 ALT                                                          */
+    int8_t origin;    /* 0 = called inside an M/=/X op, 1 = called by the D-op rule            */
+} lps_call;
+
+typedef struct {
+    int32_t mapping_quality;   /* -q, default 1 (Phasing.cpp:105)                              */
+    int32_t is_ont;            /* --ont: enables SnpParser::filterSNP (ParsingBam.cpp:837-912) */
+    int32_t have_reference;    /* ref_string != "" (ParsingBam.cpp:1544)                       */
+    int32_t connect_adjacent;  /* -a, default 35                                               */
+    int32_t base_quality;      /* -x? baseQuality default 12                                   */
+    int32_t distance;          /* -d default 300000                                            */
+    double edge_weight;        /* default 0.1                                                  */
+    double edge_threshold;     /* default 0.7                                                  */
+    double overlap_threshold;  /* default 0.2                                                  */
+    double read_confidence;    /* default 0.65                                                 */
+    double snp_confidence;     /* default 0.75                                                 */
+} lps_phase_params;
+
+/* read status codes written to lps_calls.read_status                                         */
+enum { LPS_READ_OK = 0, LPS_READ_ABORTED = 1, LPS_READ_FILTERED = 2 };
+
+/* result of lps_phase_call_alleles; arrays are owned by the context and stay valid until the
+ * next lps_batch_submit / lps_ctx_destroy.                                                   */
+typedef struct {
+    int32_t n_reads;
+    uint64_t n_calls;
+    const uint64_t *call_off;     /* [n_reads+1] CSR offsets into calls[]                      */
+    const lps_call *calls;        /* calls of read r = calls[call_off[r] .. call_off[r+1])     */
+    const uint8_t *read_status;   /* [n_reads]                                                 */
+    int32_t n_clips;              /* distinct clip positions                                   */
+    const int32_t *clip_pos;      /* ascending                                                 */
+    const int32_t *clip_front;    /* clipCount[pos][FRONT]                                     */
+    const int32_t *clip_back;     /* clipCount[pos][BACK]                                      */
+} lps_calls;
+
+/* per-variant annotation computed on the device from the reference string                    */
+typedef struct {
+    int32_t n;
+    const uint8_t *homopolymer;   /* homopolymerLength(pos) (Util.cpp:21-54), 1..10+            */
+    const uint8_t *is_danger;     /* tandem-repeat indel flag (ParsingBam.cpp:378-417)         */
+    const uint8_t *filtered;      /* erased by SnpParser::filterSNP (ONT only)                 */
+} lps_variant_notes;
+
+/* result of lps_phase_build_edges                                                             */
+typedef struct {
+    int32_t n_nodes;              /* variants with >=1 surviving call (totalVariantInfo keys)  */
+    const int32_t *node_var;      /* [n_nodes] variant index of node k (ascending)             */
+    const uint8_t *node_type;     /* [n_nodes] 0 SNP, 3 indel, 4 danger indel                  */
+    int32_t window;               /* = connect_adjacent                                        */
+    const float *weights;         /* [n_nodes][window][4] rr, ra, ar, aa between node k and k+1+d */
+    uint64_t n_contrib;           /* pair contributions folded into the table                  */
+    uint64_t n_contrib_far;       /* contributions to pairs farther than `window` nodes apart:
+                                     written by the reference but never read by its sweep      */
+} lps_edges;
+
+/* result of the whole per-contig phase pipeline                                               */
+typedef struct {
+    int32_t n_variants;
+    const int32_t *ps;            /* [n_variants] phase set (block start + 1) or 0 = unphased   */
+    const int8_t *hap_ref;        /* [n_variants] haplotype of the REF allele (0/1), -1 unphased */
+    int32_t n_reads;
+    const int8_t *read_hp;        /* [n_reads] 0/1 haplotype, -1 untagged, -2 read not used     */
+    const int32_t *hp_counts;     /* [n_variants][4] hp0_ref, hp0_alt, hp1_ref, hp1_alt         */
+} lps_phase_result;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int lps_ctx_create(int device, lps_ctx **out);
+void lps_ctx_destroy(lps_ctx *ctx);
+const char *lps_last_error(const lps_ctx *ctx);
+const char *lps_version(void);
+
+/* ---- per-contig static data -------------------------------------------------------------- */
+/* FastaParser::chrString (ParsingBam.cpp:17-59) as used by homopolymerLength (Util.cpp:21-54),
+ * getVariants_markindel (ParsingBam.cpp:378-417) and getWindowsDiffRef (SomaticVarCaller.cpp:627). */
+int lps_contig_set_reference(lps_ctx *ctx, const char *ref_ascii, int64_t len);
+/* BamParser::BamParser variant copy + mark-indel (ParsingBam.cpp:1207-1235, 378-417) and, when
+ * is_ont, the variant side of SnpParser::filterSNP (ParsingBam.cpp:866-888).                  */
+int lps_contig_set_variants(lps_ctx *ctx, const lps_variants *v, int is_ont);
+int lps_contig_get_notes(lps_ctx *ctx, lps_variant_notes *out);
+
+/* ---- reads -------------------------------------------------------------------------------- */
+/* Copies the batch to the device (asynchronously on the context's stream when the host buffers
+ * are pinned).  The host buffers must stay valid until the next lps_* call on this context
+ * returns.                                                                                     */
+int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b);
+/* Same, for buffers that already live in device memory (used for kernel-resident timing).      */
+int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b_dev);
+
+/* ---- phase -------------------------------------------------------------------------------- */
+/* BamParser::direct_detect_alleles read filter + BamParser::get_snp + getClip
+ * (ParsingBam.cpp:1243-1301, 1303-1634, 1636-1645) and the call-erasing half of
+ * SnpParser::filterSNP (ParsingBam.cpp:891-911).  want_host!=0 copies the result to the host. */
+int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_calls *out);
+/* VairiantGraph::addEdge (PhasingGraph.cpp:694-889): overlap filter and CNV filter on the host,
+ * merge by read name, fan-out and the ordered float fold of SubEdge::addSubEdge (:25-70).      */
+int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_edges *out);
+/* VairiantGraph::phasingProcess + exportResult (PhasingGraph.cpp:286-474, 891-1029, 1049-1077) */
+int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
+/* all of the above for one contig (the body of the loop at PhasingProcess.cpp:113-173)         */
+int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
+
+/* ---- timing / accounting ------------------------------------------------------------------ */
+typedef struct {
+    float ms_call_alleles;   /* device time of the allele-calling kernels of the last call      */
+    float ms_build_edges;
+    float ms_read_correction;
+    float ms_h2d;
+    float ms_d2h;
+    uint64_t kernel_launches; /* kernels launched by this context since creation                 */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} lps_stats;
+int lps_get_stats(lps_ctx *ctx, lps_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPS_H */

@@ -1,0 +1,129 @@
+"""ctypes mirror of include/lps.h (the C ABI).  Plain pointers and sizes only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblps_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+i8p = C.POINTER(C.c_int8)
+u16p = C.POINTER(C.c_uint16)
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f32p = C.POINTER(C.c_float)
+
+
+class LpsVariants(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", i32p), ("ref0", u8p), ("alt0", u8p), ("ref_len", u16p), ("alt_len", u16p),
+                ("hp1_is_alt", u8p), ("ps", i32p), ("gt_kind", u8p)]
+
+
+class LpsReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("ref_start", i32p), ("l_qseq", i32p), ("n_cigar", u32p),
+                ("cigar_off", u64p), ("seq_off", u64p), ("qual_off", u64p), ("flag", u16p), ("mapq", u8p),
+                ("name_rank", i32p), ("cigar", u32p), ("cigar_len", C.c_uint64), ("seq4", u8p),
+                ("seq_bytes", C.c_uint64), ("qual", u8p), ("qual_bytes", C.c_uint64)]
+
+
+class LpsCall(C.Structure):
+    _fields_ = [("var", C.c_int32), ("quality", C.c_int16), ("allele", C.c_int8), ("origin", C.c_int8)]
+
+
+CALL_DTYPE = np.dtype([("var", "<i4"), ("quality", "<i2"), ("allele", "i1"), ("origin", "i1")])
+
+
+class LpsPhaseParams(C.Structure):
+    _fields_ = [("mapping_quality", C.c_int32), ("is_ont", C.c_int32), ("have_reference", C.c_int32),
+                ("connect_adjacent", C.c_int32), ("base_quality", C.c_int32), ("distance", C.c_int32),
+                ("edge_weight", C.c_double), ("edge_threshold", C.c_double), ("overlap_threshold", C.c_double),
+                ("read_confidence", C.c_double), ("snp_confidence", C.c_double)]
+
+
+def default_phase_params(is_ont=True):
+    """Defaults of `longphase-s phase` (reference src/phase/Phasing.cpp:88-116)."""
+    return LpsPhaseParams(mapping_quality=1, is_ont=int(is_ont), have_reference=1, connect_adjacent=35,
+                          base_quality=12, distance=300000, edge_weight=0.1, edge_threshold=0.7,
+                          overlap_threshold=0.2, read_confidence=0.65, snp_confidence=0.75)
+
+
+class LpsCalls(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall)),
+                ("read_status", u8p), ("n_clips", C.c_int32), ("clip_pos", i32p), ("clip_front", i32p),
+                ("clip_back", i32p)]
+
+
+class LpsVariantNotes(C.Structure):
+    _fields_ = [("n", C.c_int32), ("homopolymer", u8p), ("is_danger", u8p), ("filtered", u8p)]
+
+
+class LpsEdges(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_var", i32p), ("node_type", u8p), ("window", C.c_int32),
+                ("weights", f32p), ("n_contrib", C.c_uint64), ("n_contrib_far", C.c_uint64)]
+
+
+class LpsPhaseResult(C.Structure):
+    _fields_ = [("n_variants", C.c_int32), ("ps", i32p), ("hap_ref", i8p), ("n_reads", C.c_int32),
+                ("read_hp", i8p), ("hp_counts", i32p)]
+
+
+class LpsStats(C.Structure):
+    _fields_ = [("ms_call_alleles", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+# every symbol include/lps.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "lps_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "lps_ctx_destroy": (None, [C.c_void_p]),
+    "lps_last_error": (C.c_char_p, [C.c_void_p]),
+    "lps_version": (C.c_char_p, []),
+    "lps_contig_set_reference": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "lps_contig_set_variants": (C.c_int, [C.c_void_p, C.POINTER(LpsVariants), C.c_int]),
+    "lps_contig_get_notes": (C.c_int, [C.c_void_p, C.POINTER(LpsVariantNotes)]),
+    "lps_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
+    "lps_batch_submit_device": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
+    "lps_phase_call_alleles": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsCalls)]),
+    "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
+    "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
+    "lps_phase_contig": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
+    "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load liblps_b200.so.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU fallback for the hot path")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(a, typ):
+    """numpy array -> typed pointer (None -> NULL)."""
+    if a is None:
+        return C.cast(None, typ)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(typ)
+
+
+def as_np(p, n, dtype):
+    """typed pointer -> numpy copy of n elements."""
+    n = int(n)
+    if n == 0 or not p:
+        return np.zeros(0, dtype=dtype)
+    buf = C.cast(p, C.POINTER(C.c_uint8 * (n * np.dtype(dtype).itemsize))).contents
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()

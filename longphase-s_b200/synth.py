@@ -1,0 +1,132 @@
+"""ctypes wrapper of synth/synth.c: deterministic ONT-like synthetic contigs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _ffi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "synth", "synth.c")
+LIB = os.path.join(HERE, "synth", "libsynth.so")
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("contig_len", C.c_int64), ("variant_rate", C.c_double),
+                ("indel_frac", C.c_double), ("danger_frac", C.c_double), ("homopolymer_frac", C.c_double),
+                ("depth", C.c_double), ("mean_len", C.c_double), ("sigma", C.c_double), ("sub_rate", C.c_double),
+                ("ins_rate", C.c_double), ("del_rate", C.c_double), ("clip_frac", C.c_double),
+                ("supp_frac", C.c_double), ("sec_frac", C.c_double), ("dup_frac", C.c_double),
+                ("noseq_frac", C.c_double), ("lowq_mapq_frac", C.c_double), ("zero_mapq_frac", C.c_double),
+                ("tumor", C.c_int32)]
+
+
+class SynthOut(C.Structure):
+    _fields_ = [("ref_len", C.c_int64), ("ref", C.POINTER(C.c_char)), ("n_var", C.c_int32), ("var_pos", _ffi.i32p),
+                ("var_ref0", _ffi.u8p), ("var_alt0", _ffi.u8p), ("var_ref_len", _ffi.u16p), ("var_alt_len", _ffi.u16p),
+                ("var_hp1_is_alt", _ffi.u8p), ("var_str_off", _ffi.u32p), ("var_str", C.POINTER(C.c_char)),
+                ("n_reads", C.c_int32), ("ref_start", _ffi.i32p), ("l_qseq", _ffi.i32p), ("n_cigar", _ffi.u32p),
+                ("cigar_off", _ffi.u64p), ("seq_off", _ffi.u64p), ("qual_off", _ffi.u64p), ("flag", _ffi.u16p),
+                ("mapq", _ffi.u8p), ("name_rank", _ffi.i32p), ("hap", _ffi.u8p), ("cigar", _ffi.u32p),
+                ("cigar_len", C.c_uint64), ("seq4", _ffi.u8p), ("seq_bytes", C.c_uint64), ("qual", _ffi.u8p),
+                ("qual_bytes", C.c_uint64), ("names", C.POINTER(C.c_char))]
+
+
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"])
+    return LIB
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.synth_generate.argtypes = [C.POINTER(SynthParams), C.POINTER(SynthOut)]
+        _lib.synth_generate.restype = C.c_int
+        _lib.synth_default_params.argtypes = [C.POINTER(SynthParams)]
+        _lib.synth_free.argtypes = [C.POINTER(SynthOut)]
+    return _lib
+
+
+class Contig:
+    """One synthetic contig: reference, variant table, read batch (all numpy, host memory)."""
+
+    NAME_STRIDE = 40
+
+    def __init__(self, **kw):
+        lib = _load()
+        p = SynthParams()
+        lib.synth_default_params(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown synth parameter {k}")
+            setattr(p, k, v)
+        self.params = p
+        o = SynthOut()
+        rc = lib.synth_generate(C.byref(p), C.byref(o))
+        if rc != 0:
+            raise RuntimeError("synth_generate failed")
+        try:
+            g = _ffi.as_np
+            self.ref = C.string_at(o.ref, o.ref_len)
+            nv, nr = o.n_var, o.n_reads
+            self.n_var, self.n_reads = nv, nr
+            self.var_pos = g(o.var_pos, nv, np.int32)
+            self.var_ref0 = g(o.var_ref0, nv, np.uint8)
+            self.var_alt0 = g(o.var_alt0, nv, np.uint8)
+            self.var_ref_len = g(o.var_ref_len, nv, np.uint16)
+            self.var_alt_len = g(o.var_alt_len, nv, np.uint16)
+            self.var_hp1_is_alt = g(o.var_hp1_is_alt, nv, np.uint8)
+            self.var_str_off = g(o.var_str_off, nv + 1, np.uint32)
+            self.var_str = C.string_at(o.var_str, int(self.var_str_off[-1]) if nv else 0)
+            self.ref_start = g(o.ref_start, nr, np.int32)
+            self.l_qseq = g(o.l_qseq, nr, np.int32)
+            self.n_cigar = g(o.n_cigar, nr, np.uint32)
+            self.cigar_off = g(o.cigar_off, nr, np.uint64)
+            self.seq_off = g(o.seq_off, nr, np.uint64)
+            self.qual_off = g(o.qual_off, nr, np.uint64)
+            self.flag = g(o.flag, nr, np.uint16)
+            self.mapq = g(o.mapq, nr, np.uint8)
+            self.name_rank = g(o.name_rank, nr, np.int32)
+            self.hap = g(o.hap, nr, np.uint8)
+            self.cigar = g(o.cigar, o.cigar_len, np.uint32)
+            self.seq4 = g(o.seq4, o.seq_bytes, np.uint8)
+            self.qual = g(o.qual, o.qual_bytes, np.uint8)
+            self.names = C.string_at(o.names, nr * self.NAME_STRIDE)
+        finally:
+            lib.synth_free(C.byref(o))
+
+    # ---- views in the C ABI layout -------------------------------------------------------
+    def variants_struct(self):
+        P = _ffi.ptr
+        return _ffi.LpsVariants(n=self.n_var, pos=P(self.var_pos, _ffi.i32p), ref0=P(self.var_ref0, _ffi.u8p),
+                                alt0=P(self.var_alt0, _ffi.u8p), ref_len=P(self.var_ref_len, _ffi.u16p),
+                                alt_len=P(self.var_alt_len, _ffi.u16p), hp1_is_alt=P(self.var_hp1_is_alt, _ffi.u8p),
+                                ps=P(None, _ffi.i32p), gt_kind=P(None, _ffi.u8p))
+
+    def batch_struct(self):
+        P = _ffi.ptr
+        return _ffi.LpsReadBatch(n_reads=self.n_reads, ref_start=P(self.ref_start, _ffi.i32p),
+                                 l_qseq=P(self.l_qseq, _ffi.i32p), n_cigar=P(self.n_cigar, _ffi.u32p),
+                                 cigar_off=P(self.cigar_off, _ffi.u64p), seq_off=P(self.seq_off, _ffi.u64p),
+                                 qual_off=P(self.qual_off, _ffi.u64p), flag=P(self.flag, _ffi.u16p),
+                                 mapq=P(self.mapq, _ffi.u8p), name_rank=P(self.name_rank, _ffi.i32p),
+                                 cigar=P(self.cigar, _ffi.u32p), cigar_len=len(self.cigar),
+                                 seq4=P(self.seq4, _ffi.u8p), seq_bytes=len(self.seq4), qual=P(self.qual, _ffi.u8p),
+                                 qual_bytes=len(self.qual))
+
+    def name(self, i):
+        s = self.names[i * self.NAME_STRIDE:(i + 1) * self.NAME_STRIDE]
+        return s[:s.index(b"\0")].decode()
+
+    def variant_strings(self, i):
+        o = int(self.var_str_off[i])
+        rl = int(self.var_ref_len[i])
+        al = int(self.var_alt_len[i])
+        return self.var_str[o:o + rl].decode(), self.var_str[o + rl + 1:o + rl + 1 + al].decode()

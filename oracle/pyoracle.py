@@ -1,0 +1,231 @@
+"""ctypes wrappers of the oracle (liboracle.so) and of the reference tap (oracle/_ref/libref_tap.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Never imported by the product package.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+import __graft_entry__ as _entry  # noqa: E402
+
+_pkg = _entry.load_package()
+_ffi = _pkg._ffi
+
+ORACLE_LIB = os.path.join(HERE, "liboracle.so")
+TAP_LIB = os.path.join(HERE, "_ref", "libref_tap.so")
+REF_BIN = os.path.join(HERE, "_ref", "longphase-s")
+
+i32p, u8p, i8p, u64p, f32p = _ffi.i32p, _ffi.u8p, _ffi.i8p, _ffi.u64p, _ffi.f32p
+callp = C.POINTER(_ffi.LpsCall)
+
+
+class OrcCalls(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", callp),
+                ("read_status", u8p), ("n_clips", C.c_int32), ("clip_pos", i32p), ("clip_front", i32p),
+                ("clip_back", i32p)]
+
+
+class OrcGraph(C.Structure):
+    _fields_ = [("n_aln", C.c_int32), ("aln_read", i32p), ("aln_off", u64p), ("aln_calls", callp),
+                ("n_cnv", C.c_int32), ("cnv_start", i32p), ("cnv_end", i32p), ("n_nodes", C.c_int32),
+                ("node_var", i32p), ("node_type", u8p), ("window", C.c_int32), ("weights", f32p),
+                ("n_contrib", C.c_uint64), ("n_contrib_far", C.c_uint64), ("n_far_cells", C.c_uint64)]
+
+
+class OrcSolution(C.Structure):
+    _fields_ = [("n_variants", C.c_int32), ("ps_sweep", i32p), ("hap_ref_sweep", i8p), ("ps", i32p),
+                ("hap_ref", i8p), ("n_aln", C.c_int32), ("read_hp", i8p), ("hp_counts", i32p)]
+
+
+class TapIn(C.Structure):
+    _fields_ = [("chr", C.c_char_p), ("ref", C.c_char_p), ("ref_len", C.c_int64), ("n_var", C.c_int32),
+                ("var_pos", i32p), ("var_str_off", _ffi.u32p), ("var_str", C.c_char_p),
+                ("batch", _ffi.LpsReadBatch), ("names", C.c_char_p), ("name_stride", C.c_int32),
+                ("stop_after_calls", C.c_int32), ("p", _ffi.LpsPhaseParams)]
+
+
+class TapCalls(C.Structure):
+    _fields_ = [("n_aln", C.c_int32), ("read_idx", i32p), ("off", u64p), ("pos", i32p), ("allele", i32p),
+                ("quality", i32p)]
+
+
+class TapNodes(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", i32p), ("type", i32p), ("ps", i32p), ("hap_ref", i32p),
+                ("hap_alt", i32p)]
+
+
+class TapOut(C.Structure):
+    _fields_ = [("stage_a", TapCalls), ("stage_b", TapCalls), ("stage_c", TapCalls), ("n_clips", C.c_int32),
+                ("clip_pos", i32p), ("clip_front", i32p), ("clip_back", i32p), ("n_cnv", C.c_int32),
+                ("cnv_start", i32p), ("cnv_end", i32p), ("n_empty_after_filter", C.c_int32),
+                ("n_edge_nodes", C.c_int32), ("n_cells", C.c_int64), ("n_contrib", C.c_uint64),
+                ("cell_a", i32p), ("cell_b", i32p), ("cell_which", u8p), ("cell_val", f32p),
+                ("nodes_sweep", TapNodes), ("nodes_final", TapNodes), ("read_hp", i32p),
+                ("n_result", C.c_int32), ("res_pos", i32p), ("res_block", i32p), ("res_hap_ref", i32p),
+                ("res_hap_alt", i32p), ("t_get_snp", C.c_double), ("t_filter_snp", C.c_double),
+                ("t_clip", C.c_double), ("t_add_edge", C.c_double), ("t_sweep", C.c_double),
+                ("t_read_correction", C.c_double)]
+
+
+_orc = None
+_tap = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        lib = C.CDLL(ORACLE_LIB)
+        lib.orc_annotate.argtypes = [C.c_char_p, C.c_int64, C.POINTER(_ffi.LpsVariants), C.c_int, u8p, u8p, u8p]
+        lib.orc_call_alleles.argtypes = [C.POINTER(_ffi.LpsReadBatch), C.POINTER(_ffi.LpsVariants), u8p, u8p, u8p,
+                                         C.c_int, C.POINTER(_ffi.LpsPhaseParams), C.POINTER(OrcCalls)]
+        lib.orc_calls_free.argtypes = [C.POINTER(OrcCalls)]
+        lib.orc_build_graph.argtypes = [C.POINTER(_ffi.LpsReadBatch), C.POINTER(_ffi.LpsVariants), u8p,
+                                        C.POINTER(OrcCalls), C.POINTER(_ffi.LpsPhaseParams), C.POINTER(OrcGraph)]
+        lib.orc_graph_free.argtypes = [C.POINTER(OrcGraph)]
+        lib.orc_solve.argtypes = [C.POINTER(_ffi.LpsVariants), C.POINTER(OrcGraph), C.POINTER(_ffi.LpsPhaseParams),
+                                  C.POINTER(OrcSolution)]
+        lib.orc_solution_free.argtypes = [C.POINTER(OrcSolution)]
+        _orc = lib
+    return _orc
+
+
+def tap_available():
+    return os.path.exists(TAP_LIB)
+
+
+def tap_lib():
+    global _tap
+    if _tap is None:
+        lib = C.CDLL(TAP_LIB)
+        lib.ref_tap_phase.argtypes = [C.POINTER(TapIn), C.POINTER(TapOut)]
+        lib.ref_tap_phase.restype = C.c_int
+        lib.ref_tap_phase_free.argtypes = [C.POINTER(TapOut)]
+        lib.ref_tap_homopolymer.argtypes = [C.c_char_p, C.c_int64, C.c_int]
+        _tap = lib
+    return _tap
+
+
+g = _ffi.as_np
+
+
+class Notes:
+    def __init__(self, contig, is_ont):
+        n = contig.n_var
+        self.hom = np.zeros(n, np.uint8)
+        self.danger = np.zeros(n, np.uint8)
+        self.filtered = np.zeros(n, np.uint8)
+        vs = contig.variants_struct()
+        P = _ffi.ptr
+        oracle_lib().orc_annotate(contig.ref, len(contig.ref), C.byref(vs), int(is_ont), P(self.hom, u8p),
+                                  P(self.danger, u8p), P(self.filtered, u8p))
+
+
+class OraclePhase:
+    """Runs the oracle stage by stage on a synth.Contig; results are numpy copies."""
+
+    def __init__(self, contig, params, apply_filter=True, stages=3):
+        lib = oracle_lib()
+        P = _ffi.ptr
+        self.contig = contig
+        self.notes = Notes(contig, params.is_ont)
+        vs, bs = contig.variants_struct(), contig.batch_struct()
+        oc = OrcCalls()
+        rc = lib.orc_call_alleles(C.byref(bs), C.byref(vs), P(self.notes.hom, u8p), P(self.notes.danger, u8p),
+                                  P(self.notes.filtered, u8p), int(apply_filter and params.is_ont), C.byref(params),
+                                  C.byref(oc))
+        self.rc = rc
+        nr = oc.n_reads
+        self.call_off = g(oc.call_off, nr + 1, np.uint64)
+        self.calls = g(oc.calls, oc.n_calls, _ffi.CALL_DTYPE)
+        self.read_status = g(oc.read_status, nr, np.uint8)
+        self.clip_pos = g(oc.clip_pos, oc.n_clips, np.int32)
+        self.clip_front = g(oc.clip_front, oc.n_clips, np.int32)
+        self.clip_back = g(oc.clip_back, oc.n_clips, np.int32)
+        if stages >= 2 and rc == 0:
+            og = OrcGraph()
+            lib.orc_build_graph(C.byref(bs), C.byref(vs), P(self.notes.danger, u8p), C.byref(oc), C.byref(params),
+                                C.byref(og))
+            self.n_aln = og.n_aln
+            self.aln_read = g(og.aln_read, og.n_aln, np.int32)
+            self.aln_off = g(og.aln_off, og.n_aln + 1, np.uint64)
+            self.aln_calls = g(og.aln_calls, int(self.aln_off[-1]) if og.n_aln else 0, _ffi.CALL_DTYPE)
+            self.cnv = np.stack([g(og.cnv_start, og.n_cnv, np.int32), g(og.cnv_end, og.n_cnv, np.int32)], 1)
+            self.n_nodes = og.n_nodes
+            self.node_var = g(og.node_var, og.n_nodes, np.int32)
+            self.node_type = g(og.node_type, og.n_nodes, np.uint8)
+            self.window = og.window
+            self.weights = g(og.weights, og.n_nodes * og.window * 4, np.float32).reshape(og.n_nodes, og.window, 4)
+            self.n_contrib, self.n_contrib_far, self.n_far_cells = og.n_contrib, og.n_contrib_far, og.n_far_cells
+            if stages >= 3:
+                so = OrcSolution()
+                lib.orc_solve(C.byref(vs), C.byref(og), C.byref(params), C.byref(so))
+                nv = so.n_variants
+                self.ps_sweep = g(so.ps_sweep, nv, np.int32)
+                self.hap_ref_sweep = g(so.hap_ref_sweep, nv, np.int8)
+                self.ps = g(so.ps, nv, np.int32)
+                self.hap_ref = g(so.hap_ref, nv, np.int8)
+                self.read_hp = g(so.read_hp, so.n_aln, np.int8)
+                self.hp_counts = g(so.hp_counts, nv * 4, np.int32).reshape(nv, 4)
+                lib.orc_solution_free(C.byref(so))
+            lib.orc_graph_free(C.byref(og))
+        lib.orc_calls_free(C.byref(oc))
+
+
+def _tap_calls(tc):
+    n = tc.n_aln
+    off = g(tc.off, n + 1, np.uint64)
+    m = int(off[-1]) if n else 0
+    return dict(read_idx=g(tc.read_idx, n, np.int32), off=off, pos=g(tc.pos, m, np.int32),
+                allele=g(tc.allele, m, np.int32), quality=g(tc.quality, m, np.int32))
+
+
+def _tap_nodes(tn):
+    n = tn.n
+    return dict(pos=g(tn.pos, n, np.int32), type=g(tn.type, n, np.int32), ps=g(tn.ps, n, np.int32),
+                hap_ref=g(tn.hap_ref, n, np.int32), hap_alt=g(tn.hap_alt, n, np.int32))
+
+
+class ReferencePhase:
+    """Runs the UNMODIFIED reference (oracle/_ref/libref_tap.so) on a synth.Contig."""
+
+    def __init__(self, contig, params, stop_after_calls=False, chr_name="chrS"):
+        lib = tap_lib()
+        tin = TapIn(chr=chr_name.encode(), ref=contig.ref, ref_len=len(contig.ref), n_var=contig.n_var,
+                    var_pos=_ffi.ptr(contig.var_pos, i32p), var_str_off=_ffi.ptr(contig.var_str_off, _ffi.u32p),
+                    var_str=contig.var_str, batch=contig.batch_struct(), names=contig.names,
+                    name_stride=contig.NAME_STRIDE, stop_after_calls=int(stop_after_calls), p=params)
+        out = TapOut()
+        self.rc = lib.ref_tap_phase(C.byref(tin), C.byref(out))
+        try:
+            self.stage_a = _tap_calls(out.stage_a)
+            self.stage_b = _tap_calls(out.stage_b)
+            self.clip_pos = g(out.clip_pos, out.n_clips, np.int32)
+            self.clip_front = g(out.clip_front, out.n_clips, np.int32)
+            self.clip_back = g(out.clip_back, out.n_clips, np.int32)
+            self.times = dict(get_snp=out.t_get_snp, filter_snp=out.t_filter_snp, clip=out.t_clip,
+                              add_edge=out.t_add_edge, sweep=out.t_sweep, read_correction=out.t_read_correction)
+            self.n_empty_after_filter = out.n_empty_after_filter
+            self.complete = False
+            if self.rc == 0 and not stop_after_calls and out.stage_c.off:
+                self.complete = True
+                self.stage_c = _tap_calls(out.stage_c)
+                self.cnv = np.stack([g(out.cnv_start, out.n_cnv, np.int32), g(out.cnv_end, out.n_cnv, np.int32)], 1)
+                self.n_edge_nodes, self.n_cells, self.n_contrib = out.n_edge_nodes, out.n_cells, out.n_contrib
+                self.cell_a = g(out.cell_a, out.n_cells, np.int32)
+                self.cell_b = g(out.cell_b, out.n_cells, np.int32)
+                self.cell_which = g(out.cell_which, out.n_cells, np.uint8)
+                self.cell_val = g(out.cell_val, out.n_cells, np.float32)
+                self.nodes_sweep = _tap_nodes(out.nodes_sweep)
+                self.nodes_final = _tap_nodes(out.nodes_final)
+                self.read_hp = g(out.read_hp, out.stage_c.n_aln, np.int32)
+                n = out.n_result
+                self.res_pos, self.res_block = g(out.res_pos, n, np.int32), g(out.res_block, n, np.int32)
+                self.res_hap_ref, self.res_hap_alt = g(out.res_hap_ref, n, np.int32), g(out.res_hap_alt, n, np.int32)
+        finally:
+            lib.ref_tap_phase_free(C.byref(out))

@@ -1,0 +1,72 @@
+/* ref_tap.h — C view of the reference tap library (TEST INFRASTRUCTURE ONLY, see ref_tap.cpp). */
+#ifndef REF_TAP_H
+#define REF_TAP_H
+#include <stdint.h>
+#include "../include/lps.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    const char *chr;
+    const char *ref;
+    int64_t ref_len;
+    int32_t n_var;
+    const int32_t *var_pos;
+    const uint32_t *var_str_off;   /* REF '\0' ALT '\0' per variant                       */
+    const char *var_str;
+    lps_read_batch batch;
+    const char *names;             /* NUL-terminated, one per read, name_stride apart      */
+    int32_t name_stride;
+    int32_t stop_after_calls;      /* 1: only get_snp + filterSNP                          */
+    lps_phase_params p;
+} tap_phase_in;
+
+/* a std::vector<ReadVariant> flattened: alignment k holds calls [off[k], off[k+1]) */
+typedef struct {
+    int32_t n_aln;
+    int32_t *read_idx;             /* index of the alignment in the input batch            */
+    uint64_t *off;
+    int32_t *pos, *allele, *quality;
+} tap_calls;
+
+/* one entry per key of VairiantGraph::totalVariantInfo */
+typedef struct {
+    int32_t n;
+    int32_t *pos, *type;
+    int32_t *ps;                   /* bkResult[(pos,1)] or 0                               */
+    int32_t *hap_ref, *hap_alt;    /* subNodeHP[(pos,1)], [(pos,2)], -1 when absent        */
+} tap_nodes;
+
+typedef struct {
+    tap_calls stage_a;             /* after get_snp                                        */
+    tap_calls stage_b;             /* after SnpParser::filterSNP                           */
+    tap_calls stage_c;             /* after the filters at the head of addEdge             */
+    int32_t n_clips;
+    int32_t *clip_pos, *clip_front, *clip_back;
+    int32_t n_cnv;
+    int32_t *cnv_start, *cnv_end;
+    int32_t n_empty_after_filter;  /* alignments whose calls were all erased by filterSNP  */
+    int32_t n_edge_nodes;
+    int64_t n_cells;
+    uint64_t n_contrib;            /* sum of SubEdge::readCount                            */
+    int32_t *cell_a, *cell_b;      /* positions                                            */
+    uint8_t *cell_which;           /* 0 rr, 1 ra, 2 ar, 3 aa                               */
+    float *cell_val;
+    tap_nodes nodes_sweep;         /* after edgeConnectResult                              */
+    tap_nodes nodes_final;         /* after readCorrection                                 */
+    int32_t *read_hp;              /* per stage_c alignment: readHpMap[name]               */
+    int32_t n_result;              /* exportResult                                         */
+    int32_t *res_pos, *res_block, *res_hap_ref, *res_hap_alt;
+    double t_get_snp, t_filter_snp, t_clip, t_add_edge, t_sweep, t_read_correction;
+} tap_phase_out;
+
+int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out);
+void ref_tap_phase_free(tap_phase_out *out);
+int ref_tap_homopolymer(const char *ref, int64_t len, int pos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
