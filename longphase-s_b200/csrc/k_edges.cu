@@ -1,0 +1,374 @@
+// k_edges.cu — KERNEL 2: graph construction of VairiantGraph::addEdge (reference
+// src/phase/PhasingGraph.cpp:795-888) and the ordered float fold of SubEdge::addSubEdge (:25-70).
+//
+// The reference folds `float` edge weights read by read in std::map<std::string,...> (lexicographic
+// read NAME) order: `x++` for a high-quality pair, `x = x + 0.1(double)` otherwise.  The result
+// depends on the order, so an unordered atomic add cannot be bit-exact.  Instead of sorting the
+// ~35x larger stream of pair contributions, the device
+//   1. lays the surviving calls out as "merged reads" M in name-rank order (alignments of one name
+//      concatenated, sorted by position) — 4 bytes per call: node << 2 | allele << 1 | q_hi;
+//   2. builds, with ONE stable radix sort of the calls by node, the list of calls at each node in
+//      name-rank order;
+//   3. runs one warp per node `a`: it walks that list sequentially (the fold order) and, for each
+//      call, the lanes handle the next <= connectAdjacent calls of the same merged read in parallel,
+//      updating a [window][4] float tile kept in shared memory.  Distinct lanes hit distinct cells
+//      (positions inside a merged read are distinct, duplicates are serialised), so the per-cell
+//      order is exactly the reference's.  The tile is written once, coalesced.
+// Cell (a, b) is indexed by node distance d = b - a - 1 < window, nodes being the variants with at
+// least one surviving call (the keys of totalVariantInfo): that is the only part of the table the
+// sweep ever reads (:360-417); contributions to farther pairs are only counted.
+#include <cub/cub.cuh>
+#include "lps_ctx.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// per read: alive call count, node marking (last writer decides the node type, :803-832)
+__global__ void k_mark_nodes(int n_reads, const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
+                             const uint8_t *__restrict__ read_dead, const uint8_t *__restrict__ call_erased,
+                             const int32_t *__restrict__ name_rank, unsigned long long *__restrict__ var_lastw,
+                             uint32_t *__restrict__ alive_cnt, uint64_t *__restrict__ aln_keys) {
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n_reads) return;
+    int r = (int)wid;
+    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
+    int alive = 0;
+    if (!read_dead[r]) {
+        for (uint64_t c = c0 + lane; c < c1; c += 32) {
+            if (call_erased && call_erased[c]) continue;
+            lps_call cl = calls[c];
+            unsigned type = cl.quality == -4 ? 3u : (cl.quality == -5 ? 4u : 0u);
+            atomicMax(&var_lastw[cl.var], ((unsigned long long)(r + 1) << 3) | type);
+            alive++;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) alive += __shfl_xor_sync(FULL, alive, d);
+    if (lane == 0) {
+        alive_cnt[r] = (uint32_t)alive;
+        aln_keys[r] = alive ? (((uint64_t)(uint32_t)name_rank[r] << 32) | (uint32_t)r) : ~0ull;
+    }
+}
+
+__global__ void k_node_flags(int nv, const unsigned long long *__restrict__ var_lastw, int32_t *__restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nv) flag[i] = var_lastw[i] != 0;
+}
+
+__global__ void k_fill_nodes(int nv, const unsigned long long *__restrict__ var_lastw, int32_t *__restrict__ node_of_var,
+                             int32_t *__restrict__ node_var, uint8_t *__restrict__ node_type) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    if (var_lastw[i] != 0) {
+        int k = node_of_var[i];
+        node_var[k] = i;
+        node_type[k] = (uint8_t)(var_lastw[i] & 7ull);
+    } else node_of_var[i] = -1;
+}
+
+__global__ void k_sorted_counts(int n, const uint64_t *__restrict__ keys_sorted, const uint32_t *__restrict__ alive_cnt,
+                                uint64_t *__restrict__ cnt_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint64_t k = i < n ? keys_sorted[i] : ~0ull;
+    cnt_out[i] = (k == ~0ull) ? 0 : alive_cnt[(uint32_t)k];
+}
+
+// one warp per sorted alignment: append its alive calls to M
+__global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
+                              const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
+                              const uint8_t *__restrict__ call_erased, const int32_t *__restrict__ node_of_var, int base_quality,
+                              uint32_t *__restrict__ M, uint32_t *__restrict__ M_gend, uint32_t *__restrict__ node_cnt) {
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n_aln) return;
+    int i = (int)wid;
+    uint64_t key = keys_sorted[i];
+    uint32_t rank = (uint32_t)(key >> 32);
+    int r = (int)(uint32_t)key;
+    // end of the merged group: first later alignment with another name
+    int j = i + 1;
+    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
+    uint32_t gend = (uint32_t)grp_off[j];
+    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
+    uint64_t w = grp_off[i];
+    for (uint64_t cb = c0; cb < c1; cb += 32) {
+        uint64_t c = cb + lane;
+        bool ok = c < c1 && !(call_erased && call_erased[c]);
+        unsigned m = __ballot_sync(FULL, ok);
+        if (ok) {
+            lps_call cl = calls[c];
+            int q = cl.quality < 0 ? 60 : cl.quality;                       // -4/-5 -> 60 (:820-828)
+            int node = node_of_var[cl.var];
+            uint64_t dst = w + __popc(m & ((1u << lane) - 1u));
+            M[dst] = ((uint32_t)node << 2) | ((uint32_t)cl.allele << 1) | (q >= base_quality ? 1u : 0u);
+            M_gend[dst] = gend;
+            atomicAdd(&node_cnt[node], 1u);
+        }
+        w += __popc(m);
+    }
+}
+
+// merged reads made of several alignments: order by position (== node index).  The runs are already
+// sorted, so an in-place insertion sort moves little.  Equal positions keep their concatenation order,
+// which is what std::sort's insertion-sort branch (n <= 16) does; larger groups with ties are flagged
+// for the host, which replays the same std::sort as the reference (ReadVariant::sort, Util.cpp:3-5).
+__global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
+                                    uint32_t *__restrict__ M, uint32_t *__restrict__ tie_groups, uint32_t tie_cap,
+                                    unsigned int *__restrict__ n_tie) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_aln) return;
+    uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
+    if (i > 0 && (uint32_t)(keys_sorted[i - 1] >> 32) == rank) return;          // not a group head
+    int j = i + 1;
+    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
+    if (j == i + 1) return;                                                      // single alignment
+    uint64_t g0 = grp_off[i], g1 = grp_off[j];
+    bool tie = false;
+    for (uint64_t a = g0 + 1; a < g1; a++) {
+        uint32_t v = M[a];
+        uint64_t b = a;
+        while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
+        if (b > g0 && (M[b - 1] >> 2) == (v >> 2)) tie = true;
+        M[b] = v;
+    }
+    if (tie && g1 - g0 > 16) {
+        unsigned k = atomicAdd(n_tie, 1u);
+        if (k < tie_cap) tie_groups[k] = (uint32_t)i;
+    }
+}
+
+__global__ void k_split_merged(uint64_t n, const uint32_t *__restrict__ M, uint32_t *__restrict__ node, uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { node[i] = M[i] >> 2; idx[i] = (uint32_t)i; }
+}
+
+__global__ void k_widen_u32b(int n, const uint32_t *__restrict__ in, uint64_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i < n ? in[i] : 0;
+}
+
+// the fold: one warp per node
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, double edge_weight,
+                                                          const uint64_t *__restrict__ node_off,
+                                                          const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
+                                                          const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
+                                                          unsigned long long *__restrict__ counters) {
+    extern __shared__ float s_acc[];                       // [WARPS][W*4]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * WARPS + wib;
+    if (wid >= n_nodes) return;
+    const int a = (int)wid;
+    float *acc = s_acc + (size_t)wib * W * 4;
+    for (int i = lane; i < W * 4; i += 32) acc[i] = 0.0f;
+    __syncwarp();
+    const uint64_t l0 = node_off[a], l1 = node_off[a + 1];
+    unsigned long long contrib = 0, far = 0;
+    uint32_t m_next = l0 < l1 ? list[l0] : 0;
+    for (uint64_t t = l0; t < l1; t++) {
+        const uint32_t m = m_next;
+        if (t + 1 < l1) m_next = list[t + 1];
+        const uint32_t ea = M[m];
+        const uint32_t gend = M_gend[m];
+        const unsigned al_a = (ea >> 1) & 1u, hi_a = ea & 1u;
+        for (int j0 = 0; j0 < W; j0 += 32) {
+            const int j = j0 + lane;
+            const uint64_t idx = (uint64_t)m + 1 + (uint64_t)j;
+            const bool active = j < W && idx < gend;
+            const uint32_t eb = active ? M[idx] : 0xffffffffu;
+            const int nb = (int)(eb >> 2);
+            const uint32_t nb_prev = __shfl_up_sync(FULL, eb >> 2, 1);
+            const bool dup = active && lane > 0 && nb_prev == (uint32_t)nb;
+            const bool any_dup = __any_sync(FULL, dup);
+            const int d = nb - a - 1;
+            const bool dense = active && d >= 0 && d < W;
+            if (active) { if (dense) contrib++; else far++; }
+            float *cell = dense ? &acc[d * 4 + (int)(al_a * 2u + ((eb >> 1) & 1u))] : nullptr;
+            const bool high = hi_a && (eb & 1u);
+            if (!any_dup) {
+                if (dense) {
+                    float x = *cell;
+                    x = high ? x + 1.0f : (float)((double)x + edge_weight);      // SubEdge::addSubEdge :40-43, :62-65
+                    *cell = x;
+                }
+            } else {
+                // two calls of one merged read at the same position: keep the read's own order
+                for (int l = 0; l < 32; l++) {
+                    if (lane == l && dense) {
+                        float x = *cell;
+                        x = high ? x + 1.0f : (float)((double)x + edge_weight);
+                        *cell = x;
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (!__any_sync(FULL, active)) break;
+        }
+    }
+    __syncwarp();
+    float *out = weights + (size_t)a * W * 4;
+    for (int i = lane; i < W * 4; i += 32) out[i] = acc[i];
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) {
+        contrib += __shfl_xor_sync(FULL, contrib, dd);
+        far += __shfl_xor_sync(FULL, far, dd);
+    }
+    if (lane == 0) {
+        if (contrib) atomicAdd(&counters[0], contrib);
+        if (far) atomicAdd(&counters[1], far);
+    }
+}
+
+int bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < (uint64_t)n + 1) b++; return b; }
+
+}  // namespace
+
+// host fix-up of merged reads with tied positions and more than 16 calls (see k_sort_multi_groups)
+int lps_host_fix_tie_groups(lps_ctx *ctx, const std::vector<uint32_t> &heads, const std::vector<uint64_t> &keys_sorted,
+                            const std::vector<uint64_t> &grp_off, int base_quality);
+
+int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->batch.n_reads, nv = ctx->var.n, W = p->connect_adjacent;
+    const int tb = 256;
+    if (W < 1 || W > 256) return ctx->fail(LPS_E_ARG, "connect_adjacent must be in [1,256]");
+    LPS_CUDA(ctx, ctx->d_var_lastw.reserve((size_t)nv + 1));
+    LPS_CUDA(ctx, ctx->d_alive_cnt.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, ctx->d_aln_keys.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, ctx->d_aln_keys_sorted.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, ctx->d_node_of_var.reserve((size_t)nv + 2));
+    LPS_CUDA(ctx, ctx->d_node_var.reserve((size_t)nv + 1));
+    LPS_CUDA(ctx, ctx->d_node_type.reserve((size_t)nv + 1));
+    LPS_CUDA(ctx, ctx->d_grp_off.reserve((size_t)n + 2));
+    LPS_CUDA(ctx, ctx->d_edge_counters.reserve(4));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_var_lastw.p, 0, 8 * ((size_t)nv + 1), st));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_edge_counters.p, 0, 32, st));
+    const uint8_t *erased = ctx->have_erased ? ctx->d_call_erased.p : nullptr;
+
+    // 1. alive calls per read, node marking, alignment keys
+    if (n > 0) {
+        k_mark_nodes<<<(unsigned)(((long long)n * 32 + tb - 1) / tb), tb, 0, st>>>(
+            n, ctx->d_call_off.p, ctx->d_calls.p, ctx->d_read_dead.p, erased, ctx->batch.name_rank,
+            (unsigned long long *)ctx->d_var_lastw.p, ctx->d_alive_cnt.p, ctx->d_aln_keys.p);
+        ctx->stats.kernel_launches++;
+    }
+    // 2. node numbering
+    size_t cub_bytes = 0, need = 0;
+    k_node_flags<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->d_node_of_var.p);
+    cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_node_of_var.p, ctx->d_node_of_var.p, nv + 1, st);
+    cub_bytes = need;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 0, 64, st);
+    if (need > cub_bytes) cub_bytes = need;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_grp_off.p, ctx->d_grp_off.p, n + 1, st);
+    if (need > cub_bytes) cub_bytes = need;
+    LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(cub_bytes + 256));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_of_var.p + nv, 0, 4, st));
+    cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_node_of_var.p, ctx->d_node_of_var.p, nv + 1, st);
+    int32_t n_nodes = 0;
+    LPS_CUDA(ctx, cudaMemcpyAsync(&n_nodes, ctx->d_node_of_var.p + nv, 4, cudaMemcpyDeviceToHost, st));
+    k_fill_nodes<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->d_node_of_var.p,
+                                                ctx->d_node_var.p, ctx->d_node_type.p);
+    ctx->stats.kernel_launches += 3;
+    // 3. alignments in (name rank, BAM order); offsets of their calls inside M
+    int rank_bits = 32 + 32;
+    cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, cub_bytes, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 0, rank_bits, st);
+    k_sorted_counts<<<(n + 1 + tb) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_alive_cnt.p, ctx->d_grp_off.p);
+    cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_grp_off.p, ctx->d_grp_off.p, n + 1, st);
+    ctx->stats.kernel_launches += 3;
+    uint64_t n_merged = 0;
+    LPS_CUDA(ctx, cudaMemcpyAsync(&n_merged, ctx->d_grp_off.p + n, 8, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_nodes = n_nodes; ctx->window = W; ctx->n_merged = n_merged;
+    // number of alive alignments = sorted keys that are not the sentinel: they are a prefix; count via grp_off on host is
+    // avoidable: dead entries own zero calls, the kernels below simply skip them (their key is ~0).
+    LPS_CUDA(ctx, ctx->d_M.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_M_gend.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_M_node.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_M_node_sorted.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_M_idx.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_M_idx_sorted.reserve((size_t)n_merged + 1));
+    LPS_CUDA(ctx, ctx->d_node_cnt.reserve((size_t)n_nodes + 2));
+    LPS_CUDA(ctx, ctx->d_node_off.reserve((size_t)n_nodes + 2));
+    LPS_CUDA(ctx, ctx->d_weights.reserve((size_t)n_nodes * (size_t)W * 4 + 4));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_cnt.p, 0, 4 * ((size_t)n_nodes + 2), st));
+
+    // alive alignments: keys != ~0 are a prefix of the sorted array
+    int n_aln = 0;
+    {
+        // binary search on the device array would need a kernel; the host already knows which reads have calls:
+        // count = reads that are not dead and have >= 1 surviving call == entries with alive_cnt > 0.
+        std::vector<uint32_t> cnt((size_t)n);
+        LPS_CUDA(ctx, cudaMemcpy(cnt.data(), ctx->d_alive_cnt.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += 4ull * (uint64_t)n;
+        for (int r = 0; r < n; r++) if (cnt[r]) n_aln++;
+    }
+    if (n_aln > 0 && n_merged > 0) {
+        k_fill_merged<<<(unsigned)(((long long)n_aln * 32 + tb - 1) / tb), tb, 0, st>>>(
+            n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_call_off.p, ctx->d_calls.p, erased, ctx->d_node_of_var.p,
+            p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
+        // multi-alignment merged reads
+        DevBuf<uint32_t> tie_groups;
+        DevBuf<unsigned int> n_tie;
+        const uint32_t tie_cap = 1u << 16;
+        LPS_CUDA(ctx, tie_groups.reserve(tie_cap));
+        LPS_CUDA(ctx, n_tie.reserve(1));
+        LPS_CUDA(ctx, cudaMemsetAsync(n_tie.p, 0, 4, st));
+        k_sort_multi_groups<<<(n_aln + tb - 1) / tb, tb, 0, st>>>(n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p,
+                                                                  tie_groups.p, tie_cap, n_tie.p);
+        ctx->stats.kernel_launches += 2;
+        unsigned int h_tie = 0;
+        LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, n_tie.p, 4, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_tie > tie_cap) return ctx->fail(LPS_E_NOMEM, "too many tied merged reads");
+        if (h_tie) {
+            std::vector<uint32_t> heads(h_tie);
+            std::vector<uint64_t> keys((size_t)n_aln), goff((size_t)n_aln + 1);
+            LPS_CUDA(ctx, cudaMemcpy(heads.data(), tie_groups.p, 4 * (size_t)h_tie, cudaMemcpyDeviceToHost));
+            LPS_CUDA(ctx, cudaMemcpy(keys.data(), ctx->d_aln_keys_sorted.p, 8 * (size_t)n_aln, cudaMemcpyDeviceToHost));
+            LPS_CUDA(ctx, cudaMemcpy(goff.data(), ctx->d_grp_off.p, 8 * ((size_t)n_aln + 1), cudaMemcpyDeviceToHost));
+            int rc = lps_host_fix_tie_groups(ctx, heads, keys, goff, p->base_quality);
+            if (rc) return rc;
+        }
+        tie_groups.release(); n_tie.release();
+
+        // 4. per-node call lists in merged (= name rank) order: one stable radix sort by node
+        k_split_merged<<<(unsigned)((n_merged + tb - 1) / tb), tb, 0, st>>>(n_merged, ctx->d_M.p, ctx->d_M_node.p, ctx->d_M_idx.p);
+        size_t sort_bytes = 0;
+        const int nb = bits_for((uint32_t)n_nodes);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p,
+                                        ctx->d_M_idx_sorted.p, (int)n_merged, 0, nb, st);
+        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(sort_bytes + 256));
+        cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, sort_bytes, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p,
+                                        ctx->d_M_idx_sorted.p, (int)n_merged, 0, nb, st);
+        k_widen_u32b<<<(n_nodes + 1 + tb) / tb, tb, 0, st>>>(n_nodes, ctx->d_node_cnt.p, ctx->d_node_off.p);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_node_off.p, ctx->d_node_off.p, n_nodes + 1, st);
+        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(scan_bytes + 256));
+        cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, scan_bytes, ctx->d_node_off.p, ctx->d_node_off.p, n_nodes + 1, st);
+        ctx->stats.kernel_launches += 4;
+    }
+    // 5. the fold
+    if (n_nodes > 0) {
+        if (n_merged == 0) {
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_weights.p, 0, 4 * (size_t)n_nodes * W * 4, st));
+        } else {
+            constexpr int WARPS = 8;
+            size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
+            k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
+                n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
+                (unsigned long long *)ctx->d_edge_counters.p);
+            ctx->stats.kernel_launches++;
+        }
+    }
+    LPS_CUDA(ctx, cudaGetLastError());
+    unsigned long long hc[2] = {0, 0};
+    LPS_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_edge_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_contrib = hc[0]; ctx->n_contrib_far = hc[1];
+    ctx->have_graph = true;
+    return LPS_OK;
+}

@@ -1,0 +1,343 @@
+// lps_api.cu — the extern "C" boundary declared in include/lps.h.
+#include "lps_ctx.cuh"
+
+namespace {
+
+template <typename T> int h2d(lps_ctx *ctx, DevBuf<T> &dst, const T *src, size_t n, size_t pad = 0) {
+    LPS_CUDA(ctx, dst.reserve(n + pad + 1));
+    if (n) LPS_CUDA(ctx, cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(T);
+    return LPS_OK;
+}
+template <typename T> int d2h(lps_ctx *ctx, std::vector<T> &dst, const T *src, size_t n) {
+    dst.resize(n);
+    if (n) LPS_CUDA(ctx, cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * sizeof(T);
+    return LPS_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != LPS_OK) return rc__; } while (0)
+
+// first / last called position of every read (what the overlap filter looks at)
+__global__ void k_first_last(int n, const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
+                             const int32_t *__restrict__ vpos, int32_t *__restrict__ first_pos, int32_t *__restrict__ last_pos) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
+    first_pos[r] = c1 > c0 ? vpos[calls[c0].var] : -1;
+    last_pos[r] = c1 > c0 ? vpos[calls[c1 - 1].var] : -1;
+}
+
+int fetch_host_calls(lps_ctx *ctx) {
+    if (ctx->host_calls_valid) return LPS_OK;
+    const size_t n = (size_t)ctx->batch.n_reads;
+    TRY(d2h(ctx, ctx->h_call_off, ctx->d_call_off.p, n + 1));
+    TRY(d2h(ctx, ctx->h_calls, ctx->d_calls.p, (size_t)ctx->n_calls));
+    TRY(d2h(ctx, ctx->h_status, ctx->d_status.p, n));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->host_calls_valid = true;
+    return LPS_OK;
+}
+
+float elapsed(lps_ctx *ctx, int a, int b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+    return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lps_version(void) { return "longphase-s_b200 0.1 (sm_100a)"; }
+
+int lps_ctx_create(int device, lps_ctx **out) {
+    if (!out) return LPS_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return LPS_E_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
+    lps_ctx *ctx = new lps_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return LPS_OK;
+}
+
+void lps_ctx_destroy(lps_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    // DevBuf members are plain structs; release the big ones explicitly
+    ctx->d_ref.release(); ctx->d_vpos.release(); ctx->d_vref0.release(); ctx->d_valt0.release(); ctx->d_vhom.release();
+    ctx->d_vdanger.release(); ctx->d_vfiltered.release(); ctx->d_vref_len.release(); ctx->d_valt_len.release();
+    ctx->d_ref_start.release(); ctx->d_l_qseq.release(); ctx->d_name_rank.release(); ctx->d_n_cigar.release();
+    ctx->d_cigar.release(); ctx->d_cigar_off.release(); ctx->d_seq_off.release(); ctx->d_qual_off.release();
+    ctx->d_flag.release(); ctx->d_mapq.release(); ctx->d_seq4.release(); ctx->d_qual.release();
+    ctx->d_calls_tmp.release(); ctx->d_calls.release(); ctx->d_tmp_start.release(); ctx->d_call_off.release();
+    ctx->d_ncalls.release(); ctx->d_status.release(); ctx->d_clip_keys.release(); ctx->d_clip_keys_sorted.release();
+    ctx->d_clip_unique.release(); ctx->d_clip_counts.release(); ctx->d_num_runs.release(); ctx->d_counters.release();
+    ctx->d_overflow_reads.release(); ctx->d_overflow_cand.release(); ctx->d_overflow_off.release(); ctx->d_cub_tmp.release();
+    ctx->d_read_dead.release(); ctx->d_call_erased.release(); ctx->d_var_lastw.release(); ctx->d_node_of_var.release();
+    ctx->d_node_var.release(); ctx->d_node_type.release(); ctx->d_aln_keys.release(); ctx->d_aln_keys_sorted.release();
+    ctx->d_alive_cnt.release(); ctx->d_grp_off.release(); ctx->d_M.release(); ctx->d_M_node.release();
+    ctx->d_M_node_sorted.release(); ctx->d_M_idx.release(); ctx->d_M_idx_sorted.release(); ctx->d_M_gend.release();
+    ctx->d_node_cnt.release(); ctx->d_node_off.release(); ctx->d_weights.release(); ctx->d_edge_counters.release();
+    ctx->d_ps.release(); ctx->d_hp_counts.release(); ctx->d_hap_ref.release(); ctx->d_read_hp.release();
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *lps_last_error(const lps_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int lps_contig_set_reference(lps_ctx *ctx, const char *ref_ascii, int64_t len) {
+    if (!ctx || (len > 0 && !ref_ascii) || len < 0) return LPS_E_ARG;
+    cudaSetDevice(ctx->device);
+    TRY(h2d(ctx, ctx->d_ref, ref_ascii, (size_t)len));
+    ctx->ref_len = len;
+    ctx->have_variants = false;
+    return LPS_OK;
+}
+
+int lps_contig_set_variants(lps_ctx *ctx, const lps_variants *v, int is_ont) {
+    if (!ctx || !v || v->n < 0) return LPS_E_ARG;
+    if (v->n && (!v->pos || !v->ref0 || !v->alt0 || !v->ref_len || !v->alt_len)) return ctx->fail(LPS_E_ARG, "null variant array");
+    for (int i = 1; i < v->n; i++)
+        if (v->pos[i] <= v->pos[i - 1]) return ctx->fail(LPS_E_ARG, "variant positions must be strictly ascending");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)v->n;
+    TRY(h2d(ctx, ctx->d_vpos, v->pos, n));
+    TRY(h2d(ctx, ctx->d_vref0, v->ref0, n));
+    TRY(h2d(ctx, ctx->d_valt0, v->alt0, n));
+    TRY(h2d(ctx, ctx->d_vref_len, v->ref_len, n));
+    TRY(h2d(ctx, ctx->d_valt_len, v->alt_len, n));
+    LPS_CUDA(ctx, ctx->d_vhom.reserve(n + 1));
+    LPS_CUDA(ctx, ctx->d_vdanger.reserve(n + 1));
+    LPS_CUDA(ctx, ctx->d_vfiltered.reserve(n + 1));
+    ctx->h_vpos.assign(v->pos, v->pos + n);
+    ctx->var.n = v->n;
+    ctx->var.pos = ctx->d_vpos.p; ctx->var.ref0 = ctx->d_vref0.p; ctx->var.alt0 = ctx->d_valt0.p;
+    ctx->var.ref_len = ctx->d_vref_len.p; ctx->var.alt_len = ctx->d_valt_len.p;
+    ctx->var.hom = ctx->d_vhom.p; ctx->var.danger = ctx->d_vdanger.p; ctx->var.filtered = ctx->d_vfiltered.p;
+    ctx->is_ont = is_ont;
+    TRY(lps_launch_annotate(ctx));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_variants = true;
+    ctx->have_calls = false; ctx->have_graph = false;
+    return LPS_OK;
+}
+
+int lps_contig_get_notes(lps_ctx *ctx, lps_variant_notes *out) {
+    if (!ctx || !out) return LPS_E_ARG;
+    if (!ctx->have_variants) return ctx->fail(LPS_E_STATE, "lps_contig_set_variants has not been called");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->var.n;
+    TRY(d2h(ctx, ctx->h_vhom, ctx->d_vhom.p, n));
+    TRY(d2h(ctx, ctx->h_vdanger, ctx->d_vdanger.p, n));
+    TRY(d2h(ctx, ctx->h_vfiltered, ctx->d_vfiltered.p, n));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->n = ctx->var.n;
+    out->homopolymer = ctx->h_vhom.data(); out->is_danger = ctx->h_vdanger.data(); out->filtered = ctx->h_vfiltered.data();
+    return LPS_OK;
+}
+
+int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
+    if (!ctx || !b || b->n_reads < 0) return LPS_E_ARG;
+    const size_t n = (size_t)b->n_reads;
+    if (n && (!b->ref_start || !b->l_qseq || !b->n_cigar || !b->cigar_off || !b->seq_off || !b->qual_off || !b->flag || !b->mapq ||
+              !b->name_rank))
+        return ctx->fail(LPS_E_ARG, "null read array");
+    cudaSetDevice(ctx->device);
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    TRY(h2d(ctx, ctx->d_ref_start, b->ref_start, n));
+    TRY(h2d(ctx, ctx->d_l_qseq, b->l_qseq, n));
+    TRY(h2d(ctx, ctx->d_n_cigar, b->n_cigar, n));
+    TRY(h2d(ctx, ctx->d_cigar_off, b->cigar_off, n));
+    TRY(h2d(ctx, ctx->d_seq_off, b->seq_off, n));
+    TRY(h2d(ctx, ctx->d_qual_off, b->qual_off, n));
+    TRY(h2d(ctx, ctx->d_flag, b->flag, n));
+    TRY(h2d(ctx, ctx->d_mapq, b->mapq, n));
+    TRY(h2d(ctx, ctx->d_name_rank, b->name_rank, n));
+    TRY(h2d(ctx, ctx->d_cigar, b->cigar, (size_t)b->cigar_len, 64));
+    TRY(h2d(ctx, ctx->d_seq4, b->seq4, (size_t)b->seq_bytes, 16));
+    TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->h_name_rank.assign(b->name_rank, b->name_rank + n);
+    uint64_t s = 0;
+    for (size_t i = 0; i < n; i++) s += (uint64_t)(b->l_qseq[i] > 0 ? b->l_qseq[i] : 0);
+    ctx->sum_l_qseq = s;
+    DevBatch &d = ctx->batch;
+    d.n_reads = b->n_reads;
+    d.ref_start = ctx->d_ref_start.p; d.l_qseq = ctx->d_l_qseq.p; d.n_cigar = ctx->d_n_cigar.p;
+    d.cigar_off = ctx->d_cigar_off.p; d.seq_off = ctx->d_seq_off.p; d.qual_off = ctx->d_qual_off.p;
+    d.flag = ctx->d_flag.p; d.mapq = ctx->d_mapq.p; d.name_rank = ctx->d_name_rank.p;
+    d.cigar = ctx->d_cigar.p; d.cigar_len = b->cigar_len; d.seq4 = ctx->d_seq4.p; d.seq_bytes = b->seq_bytes;
+    d.qual = ctx->d_qual.p; d.qual_bytes = b->qual_bytes;
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.ms_h2d = elapsed(ctx, 0, 1);
+    ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
+    return LPS_OK;
+}
+
+int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
+    if (!ctx || !b || b->n_reads < 0) return LPS_E_ARG;
+    cudaSetDevice(ctx->device);
+    DevBatch &d = ctx->batch;
+    d.n_reads = b->n_reads;
+    d.ref_start = b->ref_start; d.l_qseq = b->l_qseq; d.n_cigar = b->n_cigar; d.cigar_off = b->cigar_off;
+    d.seq_off = b->seq_off; d.qual_off = b->qual_off; d.flag = b->flag; d.mapq = b->mapq; d.name_rank = b->name_rank;
+    d.cigar = b->cigar; d.cigar_len = b->cigar_len; d.seq4 = b->seq4; d.seq_bytes = b->seq_bytes;
+    d.qual = b->qual; d.qual_bytes = b->qual_bytes;
+    TRY(d2h(ctx, ctx->h_name_rank, b->name_rank, (size_t)b->n_reads));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->sum_l_qseq = b->qual_bytes;
+    ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
+    return LPS_OK;
+}
+
+int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_calls *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
+    cudaSetDevice(ctx->device);
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    TRY(lps_launch_call_alleles(ctx, p));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.ms_call_alleles = elapsed(ctx, 2, 3);
+    ctx->have_graph = false;
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->n_reads = ctx->batch.n_reads;
+        out->n_calls = ctx->n_calls;
+        out->n_clips = (int32_t)ctx->h_clip_pos.size();
+        out->clip_pos = ctx->h_clip_pos.data(); out->clip_front = ctx->h_clip_front.data(); out->clip_back = ctx->h_clip_back.data();
+        if (want_host) {
+            cudaEventRecord(ctx->ev[4], ctx->stream);
+            TRY(fetch_host_calls(ctx));
+            cudaEventRecord(ctx->ev[5], ctx->stream);
+            LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->stats.ms_d2h = elapsed(ctx, 4, 5);
+            out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data(); out->read_status = ctx->h_status.data();
+        }
+    }
+    return LPS_OK;
+}
+
+int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_edges *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_calls) return ctx->fail(LPS_E_STATE, "lps_phase_call_alleles must run first");
+    cudaSetDevice(ctx->device);
+    const int n = ctx->batch.n_reads;
+    cudaStream_t st = ctx->stream;
+    // ---- host filters at the head of addEdge (PhasingGraph.cpp:707-791) ----
+    std::vector<int32_t> first_pos, last_pos;
+    std::vector<uint32_t> ncalls;
+    {
+        DevBuf<int32_t> d_first, d_last;
+        LPS_CUDA(ctx, d_first.reserve((size_t)n + 1));
+        LPS_CUDA(ctx, d_last.reserve((size_t)n + 1));
+        if (n > 0) {
+            k_first_last<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->d_call_off.p, ctx->d_calls.p, ctx->var.pos, d_first.p, d_last.p);
+            ctx->stats.kernel_launches++;
+        }
+        TRY(d2h(ctx, first_pos, d_first.p, (size_t)n));
+        TRY(d2h(ctx, last_pos, d_last.p, (size_t)n));
+        TRY(d2h(ctx, ncalls, ctx->d_ncalls.p, (size_t)n));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        d_first.release(); d_last.release();
+    }
+    TRY(lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls));
+    TRY(h2d(ctx, ctx->d_read_dead, ctx->h_read_dead.data(), (size_t)n));
+    ctx->h_cnv_start.clear(); ctx->h_cnv_end.clear();
+    lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
+    lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
+    ctx->have_erased = false;
+    if (!ctx->h_cnv_start.empty()) {
+        TRY(fetch_host_calls(ctx));
+        std::vector<uint8_t> erased;
+        TRY(lps_host_cnv_filter(ctx, erased));
+        bool any = false;
+        for (uint8_t e : erased) if (e) { any = true; break; }
+        if (any) {
+            TRY(h2d(ctx, ctx->d_call_erased, erased.data(), erased.size()));
+            ctx->have_erased = true;
+        }
+    }
+    ctx->h_aln_read.clear();
+    for (int r = 0; r < n; r++) if (ncalls[(size_t)r] && !ctx->h_read_dead[(size_t)r]) ctx->h_aln_read.push_back(r);
+    // ---- device: merge by name, fan out, ordered fold ----
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_build_edges(ctx, p));
+    cudaEventRecord(ctx->ev[3], st);
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_build_edges = elapsed(ctx, 2, 3);
+    const size_t nn = (size_t)ctx->n_nodes;
+    TRY(d2h(ctx, ctx->h_node_var, ctx->d_node_var.p, nn));
+    TRY(d2h(ctx, ctx->h_node_type, ctx->d_node_type.p, nn));
+    ctx->h_weights.clear();
+    if (want_host) TRY(d2h(ctx, ctx->h_weights, ctx->d_weights.p, nn * (size_t)ctx->window * 4));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->n_nodes = ctx->n_nodes; out->window = ctx->window;
+        out->node_var = ctx->h_node_var.data(); out->node_type = ctx->h_node_type.data();
+        out->weights = want_host ? ctx->h_weights.data() : nullptr;
+        out->n_contrib = ctx->n_contrib; out->n_contrib_far = ctx->n_contrib_far;
+    }
+    return LPS_OK;
+}
+
+int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_graph) return ctx->fail(LPS_E_STATE, "lps_phase_build_edges must run first");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
+    if (ctx->h_weights.size() != nn * (size_t)ctx->window * 4) {
+        TRY(d2h(ctx, ctx->h_weights, ctx->d_weights.p, nn * (size_t)ctx->window * 4));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    // ---- host sweep (edgeConnectResult) ----
+    std::vector<int32_t> node_pos(nn), node_ps(nn);
+    std::vector<int8_t> node_hap(nn);
+    for (size_t k = 0; k < nn; k++) node_pos[k] = ctx->h_vpos[(size_t)ctx->h_node_var[k]];
+    lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->h_weights.data(), node_ps.data(),
+                   node_hap.data());
+    ctx->h_ps.assign(nv, 0);
+    ctx->h_hap_ref.assign(nv, -1);
+    for (size_t k = 0; k < nn; k++) { ctx->h_ps[(size_t)ctx->h_node_var[k]] = node_ps[k]; ctx->h_hap_ref[(size_t)ctx->h_node_var[k]] = node_hap[k]; }
+    TRY(h2d(ctx, ctx->d_ps, ctx->h_ps.data(), nv));
+    TRY(h2d(ctx, ctx->d_hap_ref, ctx->h_hap_ref.data(), nv));
+    // ---- device: read correction ----
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_read_correction(ctx, p));
+    cudaEventRecord(ctx->ev[3], st);
+    TRY(d2h(ctx, ctx->h_ps, ctx->d_ps.p, nv));
+    TRY(d2h(ctx, ctx->h_hap_ref, ctx->d_hap_ref.p, nv));
+    TRY(d2h(ctx, ctx->h_read_hp, ctx->d_read_hp.p, n));
+    TRY(d2h(ctx, ctx->h_hp_counts, ctx->d_hp_counts.p, nv * 4));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_read_correction = elapsed(ctx, 2, 3);
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->n_variants = ctx->var.n; out->ps = ctx->h_ps.data(); out->hap_ref = ctx->h_hap_ref.data();
+        out->n_reads = ctx->batch.n_reads; out->read_hp = ctx->h_read_hp.data(); out->hp_counts = ctx->h_hp_counts.data();
+    }
+    return LPS_OK;
+}
+
+int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
+    TRY(lps_phase_call_alleles(ctx, p, 0, nullptr));
+    TRY(lps_phase_build_edges(ctx, p, 1, nullptr));
+    return lps_phase_solve(ctx, p, out);
+}
+
+int lps_get_stats(lps_ctx *ctx, lps_stats *out) {
+    if (!ctx || !out) return LPS_E_ARG;
+    *out = ctx->stats;
+    return LPS_OK;
+}
+
+}  // extern "C"

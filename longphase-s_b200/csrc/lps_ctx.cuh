@@ -1,0 +1,191 @@
+// lps_ctx.cuh — context, device buffers and error plumbing of liblps_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/lps.h"
+
+#define LPS_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->fail(LPS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+            return LPS_E_CUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+// growable device buffer; never shrinks, so steady-state batches do no cudaMalloc
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// pinned host staging buffer
+template <typename T> struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// device view of a read batch (pointers are DEVICE pointers)
+struct DevBatch {
+    int32_t n_reads = 0;
+    const int32_t *ref_start = nullptr, *l_qseq = nullptr;
+    const uint32_t *n_cigar = nullptr;
+    const uint64_t *cigar_off = nullptr, *seq_off = nullptr, *qual_off = nullptr;
+    const uint16_t *flag = nullptr;
+    const uint8_t *mapq = nullptr;
+    const int32_t *name_rank = nullptr;
+    const uint32_t *cigar = nullptr;
+    uint64_t cigar_len = 0;
+    const uint8_t *seq4 = nullptr;
+    uint64_t seq_bytes = 0;
+    const uint8_t *qual = nullptr;
+    uint64_t qual_bytes = 0;
+};
+
+// device view of the variant table
+struct DevVariants {
+    int32_t n = 0;
+    const int32_t *pos = nullptr;
+    const uint8_t *ref0 = nullptr, *alt0 = nullptr;
+    const uint16_t *ref_len = nullptr, *alt_len = nullptr;
+    const uint8_t *hom = nullptr, *danger = nullptr, *filtered = nullptr;
+};
+
+// counters written by the allele-calling kernel (one small struct, copied back once per call)
+struct CallCounters {
+    unsigned long long tmp_calls;      // slots requested in the scratch call pool
+    unsigned long long clips;          // clip events appended
+    unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
+    unsigned int overflow_reads;
+    unsigned int bad_cigar;            // reads with an unsupported CIGAR op
+};
+
+struct lps_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    int err_code = 0;
+    lps_stats stats = {};
+
+    // ---- contig ----
+    DevBuf<char> d_ref;
+    int64_t ref_len = 0;
+    DevBuf<int32_t> d_vpos;
+    DevBuf<uint8_t> d_vref0, d_valt0, d_vhom, d_vdanger, d_vfiltered;
+    DevBuf<uint16_t> d_vref_len, d_valt_len;
+    std::vector<int32_t> h_vpos;
+    std::vector<uint8_t> h_vhom, h_vdanger, h_vfiltered;
+    DevVariants var;
+    bool have_variants = false;
+    int is_ont = 0;
+
+    // ---- batch ----
+    DevBuf<int32_t> d_ref_start, d_l_qseq, d_name_rank;
+    DevBuf<uint32_t> d_n_cigar, d_cigar;
+    DevBuf<uint64_t> d_cigar_off, d_seq_off, d_qual_off;
+    DevBuf<uint16_t> d_flag;
+    DevBuf<uint8_t> d_mapq, d_seq4, d_qual;
+    DevBatch batch;
+    std::vector<int32_t> h_name_rank;
+    uint64_t sum_l_qseq = 0;
+    bool have_batch = false;
+
+    // ---- allele calls ----
+    DevBuf<lps_call> d_calls_tmp, d_calls;          // scratch pool (allocation order) and final CSR
+    DevBuf<uint64_t> d_tmp_start, d_call_off;       // per read
+    DevBuf<uint32_t> d_ncalls;
+    DevBuf<uint8_t> d_status;
+    DevBuf<uint32_t> d_clip_keys, d_clip_keys_sorted, d_clip_unique, d_clip_counts;
+    DevBuf<int32_t> d_num_runs;
+    DevBuf<CallCounters> d_counters;
+    DevBuf<uint32_t> d_overflow_reads;
+    DevBuf<uint64_t> d_overflow_cand, d_overflow_off;
+    DevBuf<uint8_t> d_cub_tmp;
+    uint64_t n_calls = 0;
+    bool have_calls = false;
+    std::vector<uint64_t> h_call_off;
+    std::vector<lps_call> h_calls;
+    std::vector<uint8_t> h_status;
+    std::vector<int32_t> h_clip_pos, h_clip_front, h_clip_back;
+    bool host_calls_valid = false;
+
+    // ---- graph ----
+    std::vector<int32_t> h_aln_read;                // stage-C alignments (batch index), BAM order
+    std::vector<uint8_t> h_read_dead;               // per read: removed by the overlap filter
+    std::vector<int32_t> h_cnv_start, h_cnv_end;
+    DevBuf<uint8_t> d_read_dead, d_call_erased;
+    bool have_erased = false;
+    DevBuf<uint64_t> d_var_lastw;                   // per variant: (read_idx+1) << 3 | type of the last writer
+    DevBuf<int32_t> d_node_of_var, d_node_var;
+    DevBuf<uint8_t> d_node_type;
+    DevBuf<uint64_t> d_aln_keys, d_aln_keys_sorted; // (rank << 32 | read) of alive alignments
+    DevBuf<uint32_t> d_alive_cnt;                   // alive calls per read
+    DevBuf<uint64_t> d_grp_off;                     // offset of each sorted alignment inside M
+    DevBuf<uint32_t> d_M;                           // merged calls: node << 2 | allele << 1 | q_hi
+    DevBuf<uint32_t> d_M_node, d_M_node_sorted, d_M_idx, d_M_idx_sorted;
+    DevBuf<uint32_t> d_M_gend;                      // end (exclusive) of the merged group that owns entry m
+    DevBuf<uint32_t> d_node_cnt;
+    DevBuf<uint64_t> d_node_off;
+    DevBuf<float> d_weights;
+    DevBuf<unsigned long long> d_edge_counters;     // [0] contrib, [1] far
+    int32_t n_nodes = 0;
+    int32_t window = 0;
+    uint64_t n_merged = 0;
+    bool have_graph = false;
+    std::vector<int32_t> h_node_var;
+    std::vector<uint8_t> h_node_type;
+    std::vector<float> h_weights;
+    uint64_t n_contrib = 0, n_contrib_far = 0;
+
+    // ---- solution ----
+    DevBuf<int32_t> d_ps, d_hp_counts;
+    DevBuf<int8_t> d_hap_ref, d_read_hp;
+    std::vector<int32_t> h_ps, h_hp_counts;
+    std::vector<int8_t> h_hap_ref, h_read_hp;
+
+    int fail(int code, const std::string &msg) {
+        err_code = code;
+        err = msg;
+        return code;
+    }
+};
+
+// kernels (k_*.cu)
+int lps_launch_annotate(lps_ctx *ctx);
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p);
+int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p);
+int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p);
+// host restatements that sit between the kernels (host_phase.cpp)
+int lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
+                            const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls);
+void lps_host_cnv_intervals(const std::vector<int32_t> &pos, const std::vector<int32_t> &front,
+                            const std::vector<int32_t> &back, std::vector<int32_t> &cs, std::vector<int32_t> &ce);
+int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);
+void lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos,
+                    const uint8_t *node_type, const float *weights, int32_t *node_ps, int8_t *node_hap_ref);

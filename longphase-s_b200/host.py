@@ -1,0 +1,150 @@
+"""Host-side mirror of the reference's phase interface over the C ABI (include/lps.h).
+
+The names follow the reference seams this path replaces:
+  BamParser.direct_detect_alleles  <- src/phase/ParsingBam.h:209
+  VairiantGraph.addEdge / phasingProcess / exportResult  <- src/phase/PhasingGraph.h:187-192
+Everything here is ctypes plumbing: the compute is in liblps_b200.so (CUDA, sm_100a) and there is no
+CPU fallback — constructing a context without a usable GPU raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class LpsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lps error {code}: {msg}")
+        self.code = code
+
+
+class Context:
+    """One context per (GPU, host thread) — lps_ctx_create / lps_ctx_destroy."""
+
+    def __init__(self, device=0):
+        self.lib = _ffi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.lps_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise LpsError(rc, "lps_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.lps_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LpsError(rc, self.lib.lps_last_error(self.h).decode())
+
+    # ---- per-contig static data ----
+    def set_reference(self, ref_bytes):
+        self._check(self.lib.lps_contig_set_reference(self.h, ref_bytes, len(ref_bytes)))
+
+    def set_variants(self, variants_struct, is_ont):
+        self._check(self.lib.lps_contig_set_variants(self.h, C.byref(variants_struct), int(is_ont)))
+
+    def notes(self):
+        o = _ffi.LpsVariantNotes()
+        self._check(self.lib.lps_contig_get_notes(self.h, C.byref(o)))
+        g = _ffi.as_np
+        return dict(homopolymer=g(o.homopolymer, o.n, np.uint8), is_danger=g(o.is_danger, o.n, np.uint8),
+                    filtered=g(o.filtered, o.n, np.uint8))
+
+    def submit(self, batch_struct):
+        self._check(self.lib.lps_batch_submit(self.h, C.byref(batch_struct)))
+
+    def submit_device(self, batch_struct):
+        self._check(self.lib.lps_batch_submit_device(self.h, C.byref(batch_struct)))
+
+    # ---- phase ----
+    def call_alleles(self, params, want_host=True):
+        o = _ffi.LpsCalls()
+        self._check(self.lib.lps_phase_call_alleles(self.h, C.byref(params), int(want_host), C.byref(o)))
+        g = _ffi.as_np
+        res = dict(n_reads=o.n_reads, n_calls=int(o.n_calls), clip_pos=g(o.clip_pos, o.n_clips, np.int32),
+                   clip_front=g(o.clip_front, o.n_clips, np.int32), clip_back=g(o.clip_back, o.n_clips, np.int32))
+        if want_host:
+            res.update(call_off=g(o.call_off, o.n_reads + 1, np.uint64), calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE),
+                       read_status=g(o.read_status, o.n_reads, np.uint8))
+        return res
+
+    def build_edges(self, params, want_host=True):
+        o = _ffi.LpsEdges()
+        self._check(self.lib.lps_phase_build_edges(self.h, C.byref(params), int(want_host), C.byref(o)))
+        g = _ffi.as_np
+        res = dict(n_nodes=o.n_nodes, window=o.window, node_var=g(o.node_var, o.n_nodes, np.int32),
+                   node_type=g(o.node_type, o.n_nodes, np.uint8), n_contrib=int(o.n_contrib),
+                   n_contrib_far=int(o.n_contrib_far))
+        if want_host:
+            res["weights"] = g(o.weights, o.n_nodes * o.window * 4, np.float32).reshape(o.n_nodes, o.window, 4)
+        return res
+
+    def _result(self, o):
+        g = _ffi.as_np
+        return dict(ps=g(o.ps, o.n_variants, np.int32), hap_ref=g(o.hap_ref, o.n_variants, np.int8),
+                    read_hp=g(o.read_hp, o.n_reads, np.int8),
+                    hp_counts=g(o.hp_counts, o.n_variants * 4, np.int32).reshape(o.n_variants, 4))
+
+    def solve(self, params):
+        o = _ffi.LpsPhaseResult()
+        self._check(self.lib.lps_phase_solve(self.h, C.byref(params), C.byref(o)))
+        return self._result(o)
+
+    def phase_contig(self, params):
+        o = _ffi.LpsPhaseResult()
+        self._check(self.lib.lps_phase_contig(self.h, C.byref(params), C.byref(o)))
+        return self._result(o)
+
+    def stats(self):
+        s = _ffi.LpsStats()
+        self._check(self.lib.lps_get_stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+
+class BamParser:
+    """Mirror of reference BamParser (src/phase/ParsingBam.h:187-210) for one contig: the constructor takes
+    the contig's variant table and reference string, direct_detect_alleles takes the decoded alignments."""
+
+    def __init__(self, ctx, contig, params):
+        self.ctx, self.params = ctx, params
+        ctx.set_reference(contig.ref if params.have_reference else b"")
+        self._vs = contig.variants_struct()
+        ctx.set_variants(self._vs, params.is_ont)
+
+    def direct_detect_alleles(self, contig, want_host=True):
+        self._bs = contig.batch_struct()
+        self.ctx.submit(self._bs)
+        return self.ctx.call_alleles(self.params, want_host)
+
+
+class VairiantGraph:
+    """Mirror of reference VairiantGraph (src/phase/PhasingGraph.h:128-197); the misspelling is the reference's."""
+
+    def __init__(self, ctx, params):
+        self.ctx, self.params = ctx, params
+
+    def addEdge(self, want_host=True):
+        return self.ctx.build_edges(self.params, want_host)
+
+    def phasingProcess(self):
+        self.result = self.ctx.solve(self.params)
+        return self.result
+
+    def exportResult(self, contig):
+        """-> list of (pos0, 'a|b', PS) like PhasingResult (src/phase/PhasingGraph.cpp:1049-1077)."""
+        r = self.result
+        out = []
+        for i in np.nonzero(r["ps"])[0]:
+            h = int(r["hap_ref"][i])
+            out.append((int(contig.var_pos[i]), f"{h}|{1 - h}", int(r["ps"][i])))
+        return out
