@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the LongPhase-S `phase` read-to-variant hot path on B200.
+
+One "step" = one pass of the whole hot path (allele calling -> host filters -> edge fold -> host sweep
+-> read correction) over one synthetic contig per GPU (BASELINE.json config C2, contig-sharded).
+  value : reads/s with the read batch already resident in HBM (lps_batch_submit_device)
+  e2e   : reads/s through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region
+  roofline : the dominant kernel (k_call_alleles) against the measured HBM copy peak
+  cpu_baseline / --impl reference : the unmodified reference (oracle/_ref) on the host cores
+Launch: `python bench.py --gpus 1` or torchrun for N > 1 (one rank per GPU, contigs are independent:
+no collective on the data path; NCCL is only used for the barrier and the max-over-ranks of the time).
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+WORKLOAD = ("C2 shard: phase SNP+indel, one {mb} Mb contig per GPU, 30x ONT-like 20 kb reads, "
+            "1 het variant/kb (10% indels), ONT error model")
+
+
+def synth_kwargs(args, seed):
+    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000), indel_frac=0.1, depth=30.0, mean_len=20000.0)
+
+
+def algorithmic_bytes_k1(contig, status, n_calls):
+    """B1 = sum_reads (16 + 4 n_cigar) + 18 n_calls; reads rejected by the flag/MAPQ filter
+    are never walked, so only their 16-byte record counts."""
+    walked = status != 2
+    return int(16 * contig.n_reads + 4 * int(contig.n_cigar[walked].sum()) + 18 * n_calls)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.stop_flag, self.th = device, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def run_reference_cpu(args, n_threads, sample_mb):
+    """The UNMODIFIED reference (oracle/_ref/libref_tap.so: get_snp, filterSNP, Clip, addEdge, edgeConnectResult,
+    readCorrection, exportResult) on one bounded sample contig, every host thread running its own replica —
+    the reference parallelises over contigs the same way (PhasingProcess.cpp:113)."""
+    from oracle import pyoracle as po
+    synth = importlib.import_module("longphase_s_b200.synth")
+    ffi = importlib.import_module("longphase_s_b200._ffi")
+    kw = synth_kwargs(args, 1000)
+    kw["contig_len"] = int(sample_mb * 1_000_000)
+    contig = synth.Contig(**kw)
+    params = ffi.default_phase_params(True)
+    if not po.tap_available():
+        kind = "port"
+        runner = lambda: po.OraclePhase(contig, params)  # noqa: E731
+    else:
+        kind = "reference"
+        runner = lambda: po.ReferencePhase(contig, params)  # noqa: E731
+    calls = []
+
+    def work():
+        r = runner()
+        if kind == "reference":
+            calls.append(int(r.stage_a["off"][-1]))
+        else:
+            calls.append(len(r.calls))
+
+    def one_round():
+        ths = [threading.Thread(target=work) for _ in range(n_threads)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+    times = []
+    for _ in range(args.warmup):
+        one_round()
+    for _ in range(args.steps):
+        times.append(one_round())
+    dt = float(np.mean(times))
+    reads = contig.n_reads * n_threads
+    return dict(value=reads / dt, unit="reads/s", cores=n_threads, kind=kind,
+                sample=f"{n_threads} replicas of one {sample_mb} Mb contig ({contig.n_reads} reads each), "
+                       f"{dt:.2f} s per round, {args.steps} rounds",
+                allele_calls_per_s=(calls[0] * n_threads / dt) if calls else None, ms_per_step=dt * 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contig-mb", type=float, default=64.0)
+    ap.add_argument("--cpu-sample-mb", type=float, default=8.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    entry.load_package()
+    ncores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        os.environ["OMP_NUM_THREADS"] = str(ncores)
+        res = run_reference_cpu(args, ncores, args.cpu_sample_mb)
+        line = {"impl": "reference", "metric": "phase_hot_path_reads_per_s", "value": res["value"], "unit": "reads/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
+                "allele_calls_per_s": res["allele_calls_per_s"],
+                "config": {"workload": WORKLOAD.format(mb=args.contig_mb), "sample": res["sample"]},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    synth_mod = importlib.import_module("longphase_s_b200.synth")
+    host = importlib.import_module("longphase_s_b200.host")
+    ffi = importlib.import_module("longphase_s_b200._ffi")
+    os.environ["OMP_NUM_THREADS"] = str(max(1, ncores // world))
+
+    t_gen = time.time()
+    contig = synth_mod.Contig(**synth_kwargs(args, 100 + rank))
+    t_gen = time.time() - t_gen
+    params = ffi.default_phase_params(True)
+    ctx = host.Context(local_rank)
+    ctx.set_reference(contig.ref)
+    vs = contig.variants_struct()
+    ctx.set_variants(vs, True)
+
+    # ---- device-resident copy of the batch (torch owns the memory) ----
+    def dev(a):
+        view = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}.get(a.dtype)
+        return torch.from_numpy(a.view(view) if view else a).cuda()
+
+    names = ["ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"]
+    dtens = {k: dev(getattr(contig, k)) for k in names}
+    ptypes = dict(ref_start=ffi.i32p, l_qseq=ffi.i32p, n_cigar=ffi.u32p, cigar_off=ffi.u64p, seq_off=ffi.u64p, qual_off=ffi.u64p,
+                  flag=ffi.u16p, mapq=ffi.u8p, name_rank=ffi.i32p, cigar=ffi.u32p, seq4=ffi.u8p, qual=ffi.u8p)
+
+    def batch_from(ptr_of):
+        return ffi.LpsReadBatch(n_reads=contig.n_reads, cigar_len=len(contig.cigar), seq_bytes=len(contig.seq4),
+                                qual_bytes=len(contig.qual), **{k: C.cast(ptr_of(k), ptypes[k]) for k in names})
+
+    dev_batch = batch_from(lambda k: dtens[k].data_ptr())
+    # ---- pinned host copy for the end-to-end leg ----
+    ptens = {k: torch.from_numpy(getattr(contig, k).view(np.uint8).reshape(-1)).pin_memory() for k in names}
+    pin_batch = batch_from(lambda k: ptens[k].data_ptr())
+    h2d_bytes = int(sum(t.numel() for t in ptens.values()))
+    input_bytes = h2d_bytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def step_resident():
+        ctx.submit_device(dev_batch)
+        return ctx.phase_contig(params)
+
+    def step_e2e():
+        ctx.submit(pin_batch)
+        return ctx.phase_contig(params)
+
+    # ---- kernel-resident leg ----
+    for _ in range(args.warmup):
+        res = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    s0 = ctx.stats()
+    k1_ms, fold_ms, call_ms, edge_ms, rc_ms = [], [], [], [], []
+    wall = {k: [] for k in ("ms_wall_call_alleles", "ms_wall_build_edges", "ms_wall_solve", "ms_host_filters", "ms_host_sweep")}
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_resident()
+        st = ctx.stats()
+        k1_ms.append(st["ms_kernel_call_alleles"]); fold_ms.append(st["ms_kernel_fold_edges"])
+        call_ms.append(st["ms_call_alleles"]); edge_ms.append(st["ms_build_edges"]); rc_ms.append(st["ms_read_correction"])
+        for k in wall:
+            wall[k].append(st[k])
+    ctx.event_record(1)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    s1 = ctx.stats()
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(dev_ms / args.steps)
+    launches = int(s1["kernel_launches"] - s0["kernel_launches"])
+
+    # per-launch accounting of the dominant kernel (host copy of the calls for the byte count)
+    ctx.submit_device(dev_batch)
+    calls = ctx.call_alleles(params, want_host=True)
+    n_calls = calls["n_calls"]
+    b1 = algorithmic_bytes_k1(contig, calls["read_status"], n_calls)
+    k1 = float(np.mean(k1_ms))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = b1 / (k1 * 1e-3) / 1e9 if k1 > 0 else 0.0
+
+    # ---- end-to-end leg: pinned host buffers through the C ABI ----
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    s2 = ctx.stats()
+    ctx.event_record(2)
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    ctx.event_record(3)
+    barrier()
+    e2e_ms = max_over_ranks(ctx.event_elapsed_ms(2, 3) / args.steps)
+    s3 = ctx.stats()
+    d2h_step = int((s3["d2h_bytes"] - s2["d2h_bytes"]) / args.steps)
+    for k in ("ps", "hap_ref", "read_hp"):
+        assert np.array_equal(res[k], res_e2e[k]), "resident and end-to-end legs disagree"
+
+    total_reads = sum_over_ranks(float(contig.n_reads))
+    total_calls = sum_over_ranks(float(n_calls))
+    line = {
+        "metric": "phase_hot_path_reads_per_s", "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
+        "allele_calls_per_s": total_calls / (ms_step * 1e-3),
+        "config": {"workload": WORKLOAD.format(mb=args.contig_mb), "reads_per_gpu": contig.n_reads, "variants_per_gpu": contig.n_var,
+                   "allele_calls_per_gpu": n_calls, "cigar_ops_per_read": float(contig.n_cigar.mean()),
+                   "input_bytes_per_gpu": input_bytes, "l2": "inputs (%.1f GB) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
+                   "parallelism": f"contig-sharded x{world}, no collective", "timing": "CUDA events on the library stream, max over ranks",
+                   "wall_ms_per_step_rank0": wall_ms / args.steps, "synth_seconds": t_gen},
+        "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_step,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1, "peak_source": peak_src},
+        "stage_ms": {"call_alleles": float(np.mean(call_ms)), "k_call_alleles": k1, "build_edges": float(np.mean(edge_ms)),
+                     "k_fold_edges": float(np.mean(fold_ms)), "read_correction": float(np.mean(rc_ms)),
+                     **{k[3:]: float(np.mean(v)) for k, v in wall.items()}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = run_reference_cpu(args, min(ncores, 64), args.cpu_sample_mb)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -190,11 +190,22 @@ typedef struct {
     float ms_read_correction;
     float ms_h2d;
     float ms_d2h;
+    float ms_kernel_call_alleles; /* the k_call_alleles launch alone (CUDA events on the launching stream) */
+    float ms_kernel_fold_edges;   /* the k_fold_edges launch alone                                          */
+    float ms_wall_call_alleles;   /* host wall clock of the last lps_phase_call_alleles              */
+    float ms_wall_build_edges;    /* ... lps_phase_build_edges                                        */
+    float ms_wall_solve;          /* ... lps_phase_solve                                              */
+    float ms_host_filters;        /* overlap filter + CNV intervals/filter on the host                */
+    float ms_host_sweep;          /* edgeConnectResult on the host (0 when the device sweep ran)      */
     uint64_t kernel_launches; /* kernels launched by this context since creation                 */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
 } lps_stats;
 int lps_get_stats(lps_ctx *ctx, lps_stats *out);
+/* CUDA events on the context's stream (the stream every kernel of this library is launched on), so a
+ * caller can time a region on the device: slots 0..3.                                                */
+int lps_event_record(lps_ctx *ctx, int slot);
+int lps_event_elapsed_ms(lps_ctx *ctx, int slot_a, int slot_b, float *ms);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,10 @@ class LpsPhaseResult(C.Structure):
 
 class LpsStats(C.Structure):
     _fields_ = [("ms_call_alleles", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("kernel_launches", C.c_uint64),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_kernel_call_alleles", C.c_float),
+                ("ms_kernel_fold_edges", C.c_float), ("ms_wall_call_alleles", C.c_float),
+                ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
+                ("ms_host_sweep", C.c_float), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -91,6 +94,8 @@ SYMBOLS = {
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_phase_contig": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
+    "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

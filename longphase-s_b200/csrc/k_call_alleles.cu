@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int CAND_CAP = 192;        // candidates buffered per warp in shared memory
+constexpr int CAND_CAP = 128;        // candidates buffered per warp in shared memory
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t PAD_OP = 1u;     // zero-length insertion: advances nothing
 
@@ -78,17 +78,27 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ pos,
     return lo + __popc(__ballot_sync(FULL, pred));
 }
 
+// K consecutive ops of this lane, starting at global index g0 (a multiple of 4 -> 128-bit loads).
+// `edge` (warp-uniform) is set for the first / last chunk of a read and for the tail of the array:
+// only there can ops fall outside [lo, hi); they become "I, len 0" (no effect, not a clip).
 template <int K>
 __device__ __forceinline__ void load_ops(const uint32_t *__restrict__ cig, uint64_t total, int64_t g0, int64_t lo, int64_t hi,
-                                         uint32_t (&ops)[K]) {
-    // g0: global index of this lane's first op (multiple of 4).  Ops outside [lo, hi) become "I, len 0"
-    // (no effect on either cursor, not a clip).
-    if (g0 + K <= lo || g0 >= hi) {
+                                         bool edge, uint32_t (&ops)[K]) {
+    if (!edge) {
+#pragma unroll
+        for (int j = 0; j < K; j += 4) {
+            uint4 t = __ldg(reinterpret_cast<const uint4 *>(cig + g0 + j));
+            ops[j] = t.x; ops[j + 1] = t.y; ops[j + 2] = t.z; ops[j + 3] = t.w;
+        }
+        return;
+    }
+    const int rel = (int)(g0 - lo), n = (int)(hi - lo);     // index of ops[0] inside the read
+    if (rel + K <= 0 || rel >= n) {
 #pragma unroll
         for (int j = 0; j < K; j++) ops[j] = PAD_OP;
         return;
     }
-    if ((uint64_t)(g0 + K) <= total && g0 >= 0) {
+    if ((uint64_t)(g0 + K) <= total) {
 #pragma unroll
         for (int j = 0; j < K; j += 4) {
             uint4 t = __ldg(reinterpret_cast<const uint4 *>(cig + g0 + j));
@@ -96,25 +106,40 @@ __device__ __forceinline__ void load_ops(const uint32_t *__restrict__ cig, uint6
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < K; j++) ops[j] = (g0 + j >= 0 && (uint64_t)(g0 + j) < total) ? cig[g0 + j] : PAD_OP;
+        for (int j = 0; j < K; j++) ops[j] = ((uint64_t)(g0 + j) < total) ? cig[g0 + j] : PAD_OP;
     }
 #pragma unroll
-    for (int j = 0; j < K; j++) if (g0 + j < lo || g0 + j >= hi) ops[j] = PAD_OP;
+    for (int j = 0; j < K; j++) if ((unsigned)(rel + j) >= (unsigned)n) ops[j] = PAD_OP;
 }
 
+// per-op advance bits, two bits per op code: bit0 = consumes the reference (M D N = X),
+// bit1 = consumes the query (M I S = X)
+constexpr uint32_t ADV_LUT = (3u << 0) | (2u << 2) | (1u << 4) | (1u << 6) | (2u << 8) | (3u << 14) | (3u << 16);
+// op codes that need the slow path: S, H (clips), P, and the unsupported codes 9..15
+constexpr uint32_t RARE_OPS = 0xFE70u;
+
 template <int K>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_call_alleles(K1Args a) {
-    __shared__ Cand s_cand[WARPS_PER_CTA][CAND_CAP];
+struct WarpScratch {
+    int r[32 * K + 4];        // reference position at which op j of the chunk starts
+    int q[32 * K + 4];        // query position at which op j of the chunk starts
+    uint32_t op[32 * K + 4];  // the op word itself
+    Cand cand[CAND_CAP];
+};
+
+template <int K>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a) {
+    __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
     const bool overflow_pass = a.overflow_reads != nullptr;
+    WarpScratch<K> &S = s_all[wib];
     int r;
     Cand *cand;
     int cand_cap;
     if (!overflow_pass) {
         if (wid >= a.b.n_reads) return;
         r = (int)wid;
-        cand = s_cand[wib];
+        cand = S.cand;
         cand_cap = CAND_CAP;
     } else {
         if (wid >= a.overflow_list_cap) return;
@@ -133,127 +158,171 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_call_alleles(K1Args a) {
         return;
     }
     const int32_t *__restrict__ vpos = a.v.pos;
+    // window of 32 variant positions, one per lane; `cur` is the first pending variant
     int cur = warp_lower_bound(vpos, nv, ref_start, lane);
-    int prev_vp = cur > 0 ? vpos[cur - 1] : INT_MIN;
     int win_base = cur;
     int vwin = (win_base + lane < nv) ? vpos[win_base + lane] : INT_MAX;
+    int win_prev = cur > 0 ? vpos[cur - 1] : INT_MIN;      // position of variant win_base - 1
 
     const int64_t lo = (int64_t)a.b.cigar_off[r], hi = lo + ncig;
     const int64_t abase = lo & ~(int64_t)3;
     constexpr int CH = 32 * K;
     const uint32_t *__restrict__ cig = a.b.cigar;
+    const uint64_t total = a.b.cigar_len;
 
     int ref_pos = ref_start, qpos = 0;
     int ncand = 0;
     bool aborted = false, bad = false;
 
     uint32_t nxt_ops[K];
-    load_ops<K>(cig, a.b.cigar_len, abase + (int64_t)lane * K, lo, hi, nxt_ops);
+    load_ops<K>(cig, total, abase + (int64_t)lane * K, lo, hi, true, nxt_ops);
     for (int64_t cb = abase; cb < hi; cb += CH) {
         uint32_t ops[K];
 #pragma unroll
         for (int j = 0; j < K; j++) ops[j] = nxt_ops[j];
-        if (cb + CH < hi) load_ops<K>(cig, a.b.cigar_len, cb + CH + (int64_t)lane * K, lo, hi, nxt_ops);
-        // per-lane advances
+        if (cb + CH < hi) {
+            const bool edge = (cb + 2 * CH > hi) || ((uint64_t)(cb + 2 * CH) > total);
+            load_ops<K>(cig, total, cb + CH + (int64_t)lane * K, lo, hi, edge, nxt_ops);
+        }
+        // ---- per-lane advances ----
         int rs = 0, qs = 0;
-        unsigned opmask = 0;
+        unsigned rare = 0;
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            unsigned op = ops[j] & 15u;
-            int len = (int)(ops[j] >> 4);
-            rs += ((0x18Du >> op) & 1u) ? len : 0;   // M D N = X consume the reference
-            qs += ((0x193u >> op) & 1u) ? len : 0;   // M I S = X consume the query
-            opmask |= 1u << op;
+            const unsigned c = ops[j];
+            const unsigned t = ADV_LUT >> ((c << 1) & 30u);
+            const int len = (int)(c >> 4);
+            rs += (t & 1u) ? len : 0;
+            qs += (t & 2u) ? len : 0;
+            rare |= RARE_OPS >> (c & 15u);
         }
-        int ri = rs, qi = qs;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(FULL, ri, d);
-            int u = __shfl_up_sync(FULL, qi, d);
-            if (lane >= d) { ri += t; qi += u; }
-        }
-        const int rtot = __shfl_sync(FULL, ri, 31), qtot = __shfl_sync(FULL, qi, 31);
-        const int r0 = ref_pos + ri - rs, q0 = qpos + qi - qs;   // this lane's first op starts here
+        const int rtot = (int)__reduce_add_sync(FULL, (unsigned)rs);
         const int chunk_end = ref_pos + rtot;
         int abort_op = INT_MAX;
 
-        // ---- variants whose position falls inside this chunk ----
-        while (true) {
-            if (cur - win_base >= 32) {
-                win_base = cur;
-                vwin = (win_base + lane < nv) ? vpos[win_base + lane] : INT_MAX;
+        // ---- variants inside this chunk: every lane takes the variant in its own window slot ----
+        int first_pending = __shfl_sync(FULL, vwin, cur - win_base);
+        if (first_pending < chunk_end) {
+            // exclusive scans of both cursors, then publish the per-op start positions
+            int ri = rs, qi = qs;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(FULL, ri, d);
+                int u = __shfl_up_sync(FULL, qi, d);
+                if (lane >= d) { ri += t; qi += u; }
             }
-            const int vp = __shfl_sync(FULL, vwin, cur - win_base);
-            if (vp >= chunk_end) break;     // also covers cur == nv (INT_MAX)
-            // owner lane: the one whose ops span vp
-            const unsigned own = __ballot_sync(FULL, vp >= r0 && vp < r0 + rs);
-            if (own == 0) { prev_vp = vp; cur++; continue; }   // cannot happen: the lanes tile [ref_pos, chunk_end)
-            const int ol = __ffs(own) - 1;
-            int o_op = 0, o_len = 0, o_r = 0, o_q = 0, o_idx = 0;
-            if (lane == ol) {
-                int rr = r0, qq = q0;
+            {
+                int rr = ref_pos + ri - rs, qq = qpos + qi - qs;
 #pragma unroll
                 for (int j = 0; j < K; j++) {
-                    unsigned op = ops[j] & 15u;
-                    int len = (int)(ops[j] >> 4);
-                    int radv = ((0x18Du >> op) & 1u) ? len : 0;
-                    if (vp >= rr && vp < rr + radv) { o_op = (int)op; o_len = len; o_r = rr; o_q = qq; o_idx = j; }
-                    rr += radv;
-                    qq += ((0x193u >> op) & 1u) ? len : 0;
+                    const unsigned c = ops[j];
+                    const unsigned t = ADV_LUT >> ((c << 1) & 30u);
+                    const int len = (int)(c >> 4);
+                    S.r[lane * K + j] = rr; S.q[lane * K + j] = qq; S.op[lane * K + j] = c;
+                    rr += (t & 1u) ? len : 0;
+                    qq += (t & 2u) ? len : 0;
                 }
             }
-            o_op = __shfl_sync(FULL, o_op, ol); o_len = __shfl_sync(FULL, o_len, ol);
-            o_r = __shfl_sync(FULL, o_r, ol);   o_q = __shfl_sync(FULL, o_q, ol);
-            o_idx = __shfl_sync(FULL, o_idx, ol);
-            const int64_t gidx = cb + (int64_t)ol * K + o_idx;   // global index of the covering op
-            const int opi = (int)(gidx - lo);                     // CIGAR index inside the read
-
-            if (o_op == 0 || o_op == 7 || o_op == 8) {
-                const int off = vp - o_r;
-                if (o_q + off + 1 > lq) { aborted = true; abort_op = opi; break; }            // :1453-1455
-                const int rl = a.v.ref_len[cur], al = a.v.alt_len[cur];
-                if (rl == 1 && al == 1) {
-                    if (lane == 0 && ncand < cand_cap) { cand[ncand].var = cur; cand[ncand].x = (uint32_t)(o_q + off); }
-                    ncand++;
-                } else if ((rl == 1) != (al == 1)) {
-                    if (opi + 1 < ncig) {                                                       // :1470, :1495
-                        const unsigned nop = cig[gidx + 1] & 15u;
-                        const unsigned want = (rl == 1) ? 1u : 2u;                             // I for an insertion, D for a deletion
-                        const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
-                        if (lane == 0 && ncand < cand_cap) {
-                            cand[ncand].var = cur;
-                            cand[ncand].x = (2u << 30) | ((unsigned)allele << 1) | (unsigned)a.v.danger[cur];
+            __syncwarp();
+            while (true) {
+                const int e = lane - (cur - win_base);                 // this lane's variant is cur + e
+                const int vp = vwin;
+                const bool mine = e >= 0 && vp < chunk_end;
+                const unsigned mmask = __ballot_sync(FULL, mine);
+                if (mmask == 0) break;
+                int cand_var = -1; uint32_t cand_x = 0;
+                bool ab = false, in_del = false;
+                int my_op_index = 0, my_j = 0;
+                if (mine) {
+                    // covering op: the last op of the chunk that starts at or before vp
+                    int lo_j = 0, hi_j = CH;                            // answer in [lo_j, hi_j)
+#pragma unroll
+                    for (int step = CH / 2; step >= 1; step >>= 1) {
+                        const int mid = lo_j + step;
+                        if (mid < hi_j && S.r[mid] <= vp) lo_j = mid;
+                    }
+                    const int j = lo_j;
+                    my_j = j;
+                    const unsigned c = S.op[j];
+                    const int o_op = (int)(c & 15u), o_len = (int)(c >> 4), o_r = S.r[j], o_q = S.q[j];
+                    const int vi = win_base + lane;
+                    const int64_t gidx = cb + j;
+                    const int opi = (int)(gidx - lo);
+                    my_op_index = opi;
+                    if (o_op == 0 || o_op == 7 || o_op == 8) {
+                        const int off = vp - o_r;
+                        if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
+                        else {
+                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                            if (rl == 1 && al == 1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                            else if ((rl == 1) != (al == 1)) {
+                                if (opi + 1 < ncig) {                                                   // :1470, :1495
+                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
+                                    const unsigned want = (rl == 1) ? 1u : 2u;                          // I after an insertion anchor, D after a deletion anchor
+                                    const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
+                                    cand_var = vi;
+                                    cand_x = (2u << 30) | ((unsigned)allele << 1) | (unsigned)a.v.danger[vi];
+                                }
+                            }
                         }
-                        ncand++;
+                    } else if (o_op == 2) in_del = true;   // decided below, after the neighbour exchange
+                }
+                // D-op rule (:1539-1607): only the FIRST pending variant of the op (previous variant lies before the op)
+                const int prev_pos = __shfl_up_sync(FULL, vwin, 1);
+                if (in_del) {
+                    const int o_r = S.r[my_j], o_q = S.q[my_j];
+                    const int vi = win_base + lane;
+                    const int pv = lane > 0 ? prev_pos : win_prev;
+                    if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
+                        if (o_q + 1 > lq) ab = true;                                                    // :1559-1561
+                        else {
+                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                            if (rl == 1 && al == 1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                            else if (rl != 1 && al == 1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
+                        }
                     }
                 }
-            } else if (o_op == 2) {
-                // D-op rule (:1539-1607): only the first pending variant of the op, homopolymer >= 3
-                if (a.have_reference && prev_vp < o_r && a.v.hom[cur] >= 3) {
-                    if (o_q + 1 > lq) { aborted = true; abort_op = opi; break; }               // :1559-1561
-                    const int rl = a.v.ref_len[cur], al = a.v.alt_len[cur];
-                    if (rl == 1 && al == 1) {
-                        if (lane == 0 && ncand < cand_cap) { cand[ncand].var = cur; cand[ncand].x = (1u << 30) | (uint32_t)o_q; }
-                        ncand++;
-                    } else if (rl != 1 && al == 1) {
-                        if (lane == 0 && ncand < cand_cap) { cand[ncand].var = cur; cand[ncand].x = (2u << 30) | (1u << 2) | (1u << 1); }
-                        ncand++;
-                    }
+                // the first aborting variant (in order) drops the read; nothing after it matters
+                const unsigned abmask = __ballot_sync(FULL, ab);
+                unsigned keep = __ballot_sync(FULL, cand_var >= 0);
+                if (abmask) {
+                    const int fl = __ffs(abmask) - 1;
+                    abort_op = __shfl_sync(FULL, my_op_index, fl);
+                    aborted = true;
+                    keep &= (1u << fl) - 1u;
                 }
+                if (cand_var >= 0 && ((keep >> lane) & 1u)) {
+                    const int dst = ncand + __popc(keep & ((1u << lane) - 1u));
+                    if (dst < cand_cap) { cand[dst].var = cand_var; cand[dst].x = cand_x; }
+                }
+                ncand += __popc(keep);
+                if (aborted) break;
+                // advance the cursor past everything handled; slide the window when it is exhausted
+                const int handled = __popc(mmask);
+                cur += handled;
+                if (cur - win_base >= 32) {
+                    win_prev = __shfl_sync(FULL, vwin, 31);
+                    win_base = cur;
+                    vwin = (win_base + lane < nv) ? vpos[win_base + lane] : INT_MAX;
+                } else break;   // the window still holds a variant >= chunk_end (or the sentinel)
             }
-            // N ops and variants deeper inside a D op are skipped by the reference's catch-up loop
-            prev_vp = vp;
-            cur++;
+            __syncwarp();
         }
 
         // ---- clips (S/H longer than 5) and unsupported ops ----
-        if (__any_sync(FULL, (opmask & ~0x18Fu) != 0)) {
-            int rr = r0;
+        if (__any_sync(FULL, (rare & 1u) != 0)) {
+            int ri = rs;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(FULL, ri, d);
+                if (lane >= d) ri += t;
+            }
+            int rr = ref_pos + ri - rs;
 #pragma unroll
             for (int j = 0; j < K; j++) {
-                unsigned op = ops[j] & 15u;
-                int len = (int)(ops[j] >> 4);
-                int64_t g = cb + (int64_t)lane * K + j;
+                const unsigned op = ops[j] & 15u;
+                const int len = (int)(ops[j] >> 4);
+                const int64_t g = cb + (int64_t)lane * K + j;
                 if ((op == 4 || op == 5) && len > 5 && (int)(g - lo) < abort_op) {
                     unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
                     if (slot < a.clip_cap) a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
@@ -263,7 +332,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_call_alleles(K1Args a) {
             }
         }
         if (aborted) break;
-        ref_pos += rtot; qpos += qtot;
+        ref_pos = chunk_end;
+        qpos += (int)__reduce_add_sync(FULL, (unsigned)qs);
     }
     bad = __any_sync(FULL, bad);
     if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar, 1u);
@@ -315,7 +385,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_call_alleles(K1Args a) {
             }
             if (valid && a.apply_filter && a.v.filtered[cd.var]) valid = false;
         }
-        // compact inside the shared buffer (reuse it as the staging area for the final write)
+        // compact inside the candidate buffer (reused as the staging area of the final write)
         const unsigned m = __ballot_sync(FULL, valid);
         __syncwarp();
         if (valid) {
@@ -323,7 +393,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_call_alleles(K1Args a) {
             Cand packed;
             packed.var = out.var;
             packed.x = ((uint32_t)(uint16_t)out.quality) | ((uint32_t)(uint8_t)out.allele << 16) | ((uint32_t)(uint8_t)out.origin << 24);
-            cand[dst] = packed;   // dst <= c, and all reads of this round happened before the __syncwarp
+            cand[dst] = packed;   // dst <= c, and every read of this round happened before the __syncwarp
         }
         nvalid += __popc(m);
         __syncwarp();
@@ -407,12 +477,15 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
         a.overflow_list_cap = ovf_cap;
         const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > 0) {
+            cudaEventRecord(ctx->kev[0], st);
             k_call_alleles<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+            cudaEventRecord(ctx->kev[1], st);
             ctx->stats.kernel_launches++;
         }
         LPS_CUDA(ctx, cudaGetLastError());
         LPS_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (grid > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_call_alleles, ctx->kev[0], ctx->kev[1]);
         if (hc.bad_cigar) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
         if (hc.overflow_reads > ovf_cap) return ctx->fail(LPS_E_NOMEM, "too many reads overflow the candidate buffer");
         if (hc.overflow_reads) {

@@ -358,9 +358,11 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
         } else {
             constexpr int WARPS = 8;
             size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
+            cudaEventRecord(ctx->kev[2], st);
             k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
                 n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
                 (unsigned long long *)ctx->d_edge_counters.p);
+            cudaEventRecord(ctx->kev[3], st);
             ctx->stats.kernel_launches++;
         }
     }
@@ -368,6 +370,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     unsigned long long hc[2] = {0, 0};
     LPS_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_edge_counters.p, 16, cudaMemcpyDeviceToHost, st));
     LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_nodes > 0 && n_merged > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_fold_edges, ctx->kev[2], ctx->kev[3]);
     ctx->n_contrib = hc[0]; ctx->n_contrib_far = hc[1];
     ctx->have_graph = true;
     return LPS_OK;

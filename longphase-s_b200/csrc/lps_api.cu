@@ -1,4 +1,5 @@
 // lps_api.cu — the extern "C" boundary declared in include/lps.h.
+#include <chrono>
 #include "lps_ctx.cuh"
 
 namespace {
@@ -38,6 +39,11 @@ int fetch_host_calls(lps_ctx *ctx) {
     return LPS_OK;
 }
 
+struct WallTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 float elapsed(lps_ctx *ctx, int a, int b) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
@@ -61,6 +67,8 @@ int lps_ctx_create(int device, lps_ctx **out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto &ev : ctx->user_ev) cudaEventCreate(&ev);
+    for (auto &ev : ctx->kev) cudaEventCreate(&ev);
     *out = ctx;
     return LPS_OK;
 }
@@ -86,6 +94,8 @@ void lps_ctx_destroy(lps_ctx *ctx) {
     ctx->d_node_cnt.release(); ctx->d_node_off.release(); ctx->d_weights.release(); ctx->d_edge_counters.release();
     ctx->d_ps.release(); ctx->d_hp_counts.release(); ctx->d_hap_ref.release(); ctx->d_read_hp.release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->user_ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->kev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -201,6 +211,7 @@ int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_hos
     if (!ctx || !p) return LPS_E_ARG;
     if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
     cudaSetDevice(ctx->device);
+    WallTimer wt;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     TRY(lps_launch_call_alleles(ctx, p));
     cudaEventRecord(ctx->ev[3], ctx->stream);
@@ -222,6 +233,7 @@ int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_hos
             out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data(); out->read_status = ctx->h_status.data();
         }
     }
+    ctx->stats.ms_wall_call_alleles = wt.ms();
     return LPS_OK;
 }
 
@@ -231,6 +243,7 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
     cudaSetDevice(ctx->device);
     const int n = ctx->batch.n_reads;
     cudaStream_t st = ctx->stream;
+    WallTimer wt;
     // ---- host filters at the head of addEdge (PhasingGraph.cpp:707-791) ----
     std::vector<int32_t> first_pos, last_pos;
     std::vector<uint32_t> ncalls;
@@ -248,6 +261,7 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
         d_first.release(); d_last.release();
     }
+    WallTimer wf;
     TRY(lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls));
     TRY(h2d(ctx, ctx->d_read_dead, ctx->h_read_dead.data(), (size_t)n));
     ctx->h_cnv_start.clear(); ctx->h_cnv_end.clear();
@@ -267,6 +281,7 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
     }
     ctx->h_aln_read.clear();
     for (int r = 0; r < n; r++) if (ncalls[(size_t)r] && !ctx->h_read_dead[(size_t)r]) ctx->h_aln_read.push_back(r);
+    ctx->stats.ms_host_filters = wf.ms();
     // ---- device: merge by name, fan out, ordered fold ----
     cudaEventRecord(ctx->ev[2], st);
     TRY(lps_launch_build_edges(ctx, p));
@@ -286,6 +301,7 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
         out->weights = want_host ? ctx->h_weights.data() : nullptr;
         out->n_contrib = ctx->n_contrib; out->n_contrib_far = ctx->n_contrib_far;
     }
+    ctx->stats.ms_wall_build_edges = wt.ms();
     return LPS_OK;
 }
 
@@ -295,6 +311,7 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     cudaSetDevice(ctx->device);
     cudaStream_t st = ctx->stream;
     const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
+    WallTimer wt;
     if (ctx->h_weights.size() != nn * (size_t)ctx->window * 4) {
         TRY(d2h(ctx, ctx->h_weights, ctx->d_weights.p, nn * (size_t)ctx->window * 4));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -303,8 +320,10 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     std::vector<int32_t> node_pos(nn), node_ps(nn);
     std::vector<int8_t> node_hap(nn);
     for (size_t k = 0; k < nn; k++) node_pos[k] = ctx->h_vpos[(size_t)ctx->h_node_var[k]];
+    WallTimer ws;
     lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->h_weights.data(), node_ps.data(),
                    node_hap.data());
+    ctx->stats.ms_host_sweep = ws.ms();
     ctx->h_ps.assign(nv, 0);
     ctx->h_hap_ref.assign(nv, -1);
     for (size_t k = 0; k < nn; k++) { ctx->h_ps[(size_t)ctx->h_node_var[k]] = node_ps[k]; ctx->h_hap_ref[(size_t)ctx->h_node_var[k]] = node_hap[k]; }
@@ -325,6 +344,7 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
         out->n_variants = ctx->var.n; out->ps = ctx->h_ps.data(); out->hap_ref = ctx->h_hap_ref.data();
         out->n_reads = ctx->batch.n_reads; out->read_hp = ctx->h_read_hp.data(); out->hp_counts = ctx->h_hp_counts.data();
     }
+    ctx->stats.ms_wall_solve = wt.ms();
     return LPS_OK;
 }
 
@@ -332,6 +352,21 @@ int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *
     TRY(lps_phase_call_alleles(ctx, p, 0, nullptr));
     TRY(lps_phase_build_edges(ctx, p, 1, nullptr));
     return lps_phase_solve(ctx, p, out);
+}
+
+int lps_event_record(lps_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 4) return LPS_E_ARG;
+    cudaSetDevice(ctx->device);
+    LPS_CUDA(ctx, cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+    return LPS_OK;
+}
+
+int lps_event_elapsed_ms(lps_ctx *ctx, int slot_a, int slot_b, float *ms) {
+    if (!ctx || !ms || slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4) return LPS_E_ARG;
+    cudaSetDevice(ctx->device);
+    LPS_CUDA(ctx, cudaEventSynchronize(ctx->user_ev[slot_b]));
+    LPS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->user_ev[slot_a], ctx->user_ev[slot_b]));
+    return LPS_OK;
 }
 
 int lps_get_stats(lps_ctx *ctx, lps_stats *out) {

@@ -89,6 +89,8 @@ struct lps_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t user_ev[4] = {};
+    cudaEvent_t kev[4] = {};   // around the two hot kernels
     std::string err;
     int err_code = 0;
     lps_stats stats = {};

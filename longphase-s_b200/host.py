@@ -105,6 +105,14 @@ class Context:
         self._check(self.lib.lps_phase_contig(self.h, C.byref(params), C.byref(o)))
         return self._result(o)
 
+    def event_record(self, slot):
+        self._check(self.lib.lps_event_record(self.h, int(slot)))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self.lib.lps_event_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value
+
     def stats(self):
         s = _ffi.LpsStats()
         self._check(self.lib.lps_get_stats(self.h, C.byref(s)))
