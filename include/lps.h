@@ -145,6 +145,8 @@ typedef struct {
     int32_t n_reads;
     const int8_t *read_hp;        /* [n_reads] 0/1 haplotype, -1 untagged, -2 read not used     */
     const int32_t *hp_counts;     /* [n_variants][4] hp0_ref, hp0_alt, hp1_ref, hp1_alt         */
+    const int32_t *ps_sweep;      /* [n_variants] phase set after edgeConnectResult, before readCorrection */
+    const int8_t *hap_ref_sweep;  /* [n_variants] REF-allele haplotype after the sweep, -1 outside blocks  */
 } lps_phase_result;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -196,7 +198,7 @@ typedef struct {
     float ms_wall_build_edges;    /* ... lps_phase_build_edges                                        */
     float ms_wall_solve;          /* ... lps_phase_solve                                              */
     float ms_host_filters;        /* overlap filter + CNV intervals/filter on the host                */
-    float ms_host_sweep;          /* edgeConnectResult on the host (0 when the device sweep ran)      */
+    float ms_host_sweep;          /* edgeConnectResult chain on the host, over the one-byte votes     */
     uint64_t kernel_launches; /* kernels launched by this context since creation                 */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;

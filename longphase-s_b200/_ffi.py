@@ -66,7 +66,7 @@ class LpsEdges(C.Structure):
 
 class LpsPhaseResult(C.Structure):
     _fields_ = [("n_variants", C.c_int32), ("ps", i32p), ("hap_ref", i8p), ("n_reads", C.c_int32),
-                ("read_hp", i8p), ("hp_counts", i32p)]
+                ("read_hp", i8p), ("hp_counts", i32p), ("ps_sweep", i32p), ("hap_ref_sweep", i8p)]
 
 
 class LpsStats(C.Structure):

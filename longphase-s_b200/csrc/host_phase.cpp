@@ -5,11 +5,14 @@
 // must be bit-exact because kernel 2 consumes the filters and kernel 3a consumes the sweep:
 //   * overlap filter among the alignments of one read name   reference PhasingGraph.cpp:707-781
 //   * Clip::getCNVInterval (run twice) + CNV mismatch filter  reference PhasingGraph.cpp:520-692, 1103-1227
-//   * edgeConnectResult / findBestEdgePair / Onelongcase       reference PhasingGraph.cpp:166-228, 251-283, 286-474
-//   * std::sort replay for merged reads with tied positions    reference Util.cpp:3-5
+//   * edgeConnectResult / Onelongcase (the chain itself)        reference PhasingGraph.cpp:251-283, 286-474
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "lps_ctx.cuh"
 
 // --------------------------------------------------------------------------------------------
@@ -222,141 +225,144 @@ int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased) {
 }
 
 // --------------------------------------------------------------------------------------------
-// the sweep: every node receives weighted votes from up to `window` predecessors and, in turn, votes
-// on its `window` successors.  Votes for node t can only come from nodes t-window..t-1, so a ring of
-// window+1 slots holds all live vote lists.
+// the sweep (edgeConnectResult).  It is a left-to-right chain — node k's haplotype comes from the
+// weighted votes of its <= W predecessors, then k votes on its W successors — so it runs on the
+// host; but nothing about a vote except its DIRECTION depends on the chain, and k_fold_edges' epilogue
+// already reduced every (node, successor) cell to one byte (findBestEdgePair, :166-228):
+//   bits 0-1 link (1 same haplotype, 2 opposite, 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1,
+//   bit 4 edgeSimilarRatio < 0.2.
+// Only those W bytes per node cross PCIe, never the [nodes][W][4] float table.
+//   * hpCountMap2 is a float sum in voter order (weights 1, 20, 0.1f): successors receive their votes
+//     one voter at a time in ascending voter order, exactly like the reference;
+//   * Onelongcase's sums only ever add 1 or 20, so they are kept as integers;
+//   * inside a block the REF-allele haplotype telescopes to hp[k]-1 (the first member of a block
+//     always has hp 1) and PS = position(block start)+1; single-member blocks are dropped (:425).
 // --------------------------------------------------------------------------------------------
 namespace {
-struct Vote { int voter; float para, cross, weight; int hap; double esr; };
+
+// Accumulators of every node (hpCountMap2 and Onelongcase's sums), SoA inside ONE allocation.  The five
+// arrays are staggered by a few cache lines so that w1[d], w2[d], ... never share their low 12 address
+// bits (4K aliasing would serialise the loads behind the stores).
+struct SweepAcc {
+    std::vector<char> mem;
+    float *w1, *w2;
+    int *s1, *s2, *singles;
+    explicit SweepAcc(size_t len) {
+        const size_t bytes = (len * 4 + 4095) & ~(size_t)4095;
+        mem.assign(5 * bytes + 5 * 832 + 64, 0);
+        char *b = mem.data();
+        b += (64 - ((uintptr_t)b & 63)) & 63;
+        w1 = (float *)(b);
+        w2 = (float *)(b + 1 * (bytes + 832));
+        s1 = (int *)(b + 2 * (bytes + 832));
+        s2 = (int *)(b + 3 * (bytes + 832));
+        singles = (int *)(b + 4 * (bytes + 832));
+    }
+};
+
+inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t as_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+// node k votes on its successors t0 .. t0+dmax-1.  Mask arithmetic instead of branches: the vote directions are
+// data, not control flow (adding +0.0f is exact and the accumulators are never -0.0).  Returns the last d with a link.
+int cast_votes_scalar(const uint8_t *row, int dmax, int hp, unsigned type, const SweepAcc &A, size_t t0) {
+    const uint32_t wtab[2] = {as_bits(type == 4u ? (float)0.1 : 1.f), as_bits(type == 4u ? (float)0.1 : 20.f)};   // :367-369
+    const uint32_t itab[2] = {1u, 20u};
+    const unsigned same = hp == 1 ? 1u : 2u, other = 3u - same;       // link code that sends the vote to haplotype 1
+    const uint32_t type_ok = (type != 3u && type != 4u) ? ~0u : 0u;  // Onelongcase: weight >= 1, voter not an indel (:265)
+    int last = -1;
+    for (int d = 0; d < dmax; d++) {
+        const unsigned info = row[d];
+        const unsigned link = info & 3u;
+        const uint32_t mA = 0u - (uint32_t)(link == same), mB = 0u - (uint32_t)(link == other);
+        const uint32_t wb = wtab[(info >> 2) & 1u];
+        A.w1[t0 + d] += as_float(wb & mA);
+        A.w2[t0 + d] += as_float(wb & mB);
+        const uint32_t single = 0u - ((info >> 3) & 1u);
+        A.singles[t0 + d] += (int)((mA | mB) & single & 1u);
+        const uint32_t qual = ~single & (0u - ((info >> 4) & 1u)) & type_ok;
+        const uint32_t wi = itab[(info >> 2) & 1u];
+        A.s1[t0 + d] += (int)(wi & qual & mA);
+        A.s2[t0 + d] += (int)(wi & qual & mB);
+        const int md = (int)(mA | mB);
+        last = (d & md) | (last & ~md);
+    }
+    return last;
 }
+
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+int cast_votes_avx2(const uint8_t *row, int dmax, int hp, unsigned type, const SweepAcc &A, size_t t0) {
+    const __m256 w_lo = _mm256_set1_ps(type == 4u ? (float)0.1 : 1.f), w_hi = _mm256_set1_ps(type == 4u ? (float)0.1 : 20.f);
+    const __m256i same = _mm256_set1_epi32(hp == 1 ? 1 : 2), other = _mm256_set1_epi32(hp == 1 ? 2 : 1);
+    const __m256i type_ok = _mm256_set1_epi32((type != 3u && type != 4u) ? -1 : 0);
+    const __m256i iota = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m256i c1 = _mm256_set1_epi32(1), c3 = _mm256_set1_epi32(3), c4 = _mm256_set1_epi32(4), c8 = _mm256_set1_epi32(8),
+                  c16 = _mm256_set1_epi32(16), c20 = _mm256_set1_epi32(20);
+    int last = -1;
+    for (int d = 0; d < dmax; d += 8) {
+        // 8 vote bytes (the read may run into the next row / the padding; those lanes are masked off)
+        const __m256i info = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(row + d)));
+        const __m256i valid = _mm256_cmpgt_epi32(_mm256_set1_epi32(dmax - d), iota);
+        const __m256i link = _mm256_and_si256(info, c3);
+        const __m256i mA = _mm256_and_si256(_mm256_cmpeq_epi32(link, same), valid);
+        const __m256i mB = _mm256_and_si256(_mm256_cmpeq_epi32(link, other), valid);
+        const __m256i heavy = _mm256_cmpeq_epi32(_mm256_and_si256(info, c4), c4);
+        const __m256 wb = _mm256_blendv_ps(w_lo, w_hi, _mm256_castsi256_ps(heavy));
+        float *p1 = A.w1 + t0 + d, *p2 = A.w2 + t0 + d;
+        _mm256_storeu_ps(p1, _mm256_add_ps(_mm256_loadu_ps(p1), _mm256_and_ps(wb, _mm256_castsi256_ps(mA))));
+        _mm256_storeu_ps(p2, _mm256_add_ps(_mm256_loadu_ps(p2), _mm256_and_ps(wb, _mm256_castsi256_ps(mB))));
+        const __m256i act = _mm256_or_si256(mA, mB);
+        const __m256i single = _mm256_cmpeq_epi32(_mm256_and_si256(info, c8), c8);
+        __m256i *ps = (__m256i *)(A.singles + t0 + d), *q1 = (__m256i *)(A.s1 + t0 + d), *q2 = (__m256i *)(A.s2 + t0 + d);
+        _mm256_storeu_si256(ps, _mm256_add_epi32(_mm256_loadu_si256(ps), _mm256_and_si256(_mm256_and_si256(act, single), c1)));
+        const __m256i qual = _mm256_and_si256(_mm256_andnot_si256(single, _mm256_cmpeq_epi32(_mm256_and_si256(info, c16), c16)), type_ok);
+        const __m256i wi = _mm256_blendv_epi8(c1, c20, heavy);
+        _mm256_storeu_si256(q1, _mm256_add_epi32(_mm256_loadu_si256(q1), _mm256_and_si256(wi, _mm256_and_si256(qual, mA))));
+        _mm256_storeu_si256(q2, _mm256_add_epi32(_mm256_loadu_si256(q2), _mm256_and_si256(wi, _mm256_and_si256(qual, mB))));
+        const unsigned bits = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(act));
+        if (bits) last = d + 31 - __builtin_clz(bits);
+    }
+    return last;
+}
+#endif
+
+}  // namespace
 
 void lps_host_sweep(const lps_phase_params *p, int32_t N, int32_t W, const int32_t *node_pos, const uint8_t *node_type,
-                    const float *weights, int32_t *node_ps, int8_t *node_hap_ref) {
+                    const uint8_t *vote_info, int32_t *node_ps, int8_t *node_hap_ref) {
     for (int k = 0; k < N; k++) { node_ps[k] = 0; node_hap_ref[k] = -1; }
     if (N < 2) return;
-    const int R = W + 1;
-    std::vector<std::vector<Vote>> ring((size_t)R);
-    std::vector<float> w1((size_t)R, 0.0f), w2((size_t)R, 0.0f);   // hpCountMap2[node][1|2]
-    std::vector<int8_t> hp((size_t)N, 0);                           // hpResult
-    std::vector<int32_t> block_of((size_t)N, -2);                   // -2: never entered a block
-    int block_start = -1, last_connect = -1;
+    SweepAcc A((size_t)N + (size_t)W + 16);
+#if defined(__x86_64__)
+    const bool use_avx2 = __builtin_cpu_supports("avx2");
+#else
+    const bool use_avx2 = false;
+#endif
+    int block_start = -1, block_size = 0, block_ps = 0, last_connect = -1;
     for (int k = 0; k + 1 < N; k++) {
-        const int slot = k % R;
-        std::vector<Vote> &my_votes = ring[(size_t)slot];
-        float h1 = w1[(size_t)slot], h2 = w2[(size_t)slot];
-        const bool skip = std::abs(node_pos[k + 1] - node_pos[k]) > p->distance;   // :318-320
-        bool enter = !skip;
-        if (enter) {
-            // Onelongcase (:251-283): many single-read votes -> trust only consistent multi-read non-indel ones
-            int singles = 0;
-            float s1 = 0, s2 = 0;
-            for (const Vote &v : my_votes) {
-                if ((v.para + v.cross) <= 1) singles++;
-                else if (v.esr < 0.2 && v.weight >= 1 && node_type[v.voter] != 3) {
-                    if (v.hap == 1) s1 += v.weight; else if (v.hap == 2) s2 += v.weight;
-                }
-            }
-            if (!(singles <= 3 || (s1 == 0 && s2 == 0))) { h1 = s1; h2 = s2; }
-            if (h1 == h2) {
-                if (last_connect >= 0 && node_pos[k] < node_pos[last_connect]) enter = false;   // :340-342
-                else { block_start = k; block_of[(size_t)k] = k; hp[(size_t)k] = 1; }
-            } else {
-                hp[(size_t)k] = h1 > h2 ? 1 : 2;
-                block_of[(size_t)k] = block_start;
-            }
-        }
-        if (enter) {
-            const float *row = weights + (size_t)k * (size_t)W * 4;
-            for (int d = 0; d < W && k + 1 + d < N; d++) {
-                const int t = k + 1 + d;
-                const float rr = row[d * 4 + 0], ra = row[d * 4 + 1], ar = row[d * 4 + 2], aa = row[d * 4 + 3];
-                // findBestEdgePair (:166-228)
-                const float para = rr + aa, cross = ar + ra;
-                const double esr = (double)std::min(para, cross) / (double)std::max(para, cross);
-                int link = 0;                            // 1: same haplotype, 2: opposite, 0: no connection
-                if (rr + aa > ra + ar) link = 1; else if (rr + aa < ra + ar) link = 2;
-                if (esr > p->edge_threshold) link = 0;
-                Vote v;
-                v.voter = k; v.weight = 1; v.hap = 0;
-                if ((esr <= 0.1 && (rr + aa + ra + ar) >= 1) || ((rr + aa) < 1 && (ra + ar) >= 1) || ((rr + aa) >= 1 && (ra + ar) < 1))
-                    v.weight = 20;
-                v.para = rr + aa; v.cross = ra + ar; v.esr = esr;
-                if (node_type[k] == 4) v.weight = (float)0.1;                   // danger indel voter (:367-369)
-                if (link) {
-                    const bool to_h1 = (hp[(size_t)k] == 1) == (link == 1);
-                    const int ts = t % R;
-                    if (to_h1) { w1[(size_t)ts] += v.weight; v.hap = 1; } else { w2[(size_t)ts] += v.weight; v.hap = 2; }
-                    ring[(size_t)ts].push_back(v);
-                    last_connect = t;
-                }
-            }
-        }
-        // slot k is recycled for node k + R
-        my_votes.clear(); w1[(size_t)slot] = 0.0f; w2[(size_t)slot] = 0.0f;
+        if (std::abs(node_pos[k + 1] - node_pos[k]) > p->distance) continue;                   // :318-320
+        float h1 = A.w1[k], h2 = A.w2[k];
+        const int a1 = A.s1[k], a2 = A.s2[k], sg = A.singles[k];
+        if (!(sg <= 3 || (a1 == 0 && a2 == 0))) { h1 = (float)a1; h2 = (float)a2; }           // Onelongcase :276-281
+        int hp;
+        if (h1 == h2) {
+            if (last_connect >= 0 && k < last_connect) continue;                                // :340-342
+            if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
+            block_start = k; block_size = 0; block_ps = node_pos[k] + 1; hp = 1;
+        } else hp = h1 > h2 ? 1 : 2;
+        block_size++;
+        node_ps[k] = block_ps;
+        node_hap_ref[k] = (int8_t)(hp - 1);
+        const int dmax = std::min(W, N - 1 - k);
+        const uint8_t *row = vote_info + (size_t)k * (size_t)W;
+        int last;
+#if defined(__x86_64__)
+        if (use_avx2) last = cast_votes_avx2(row, dmax, hp, node_type[k], A, (size_t)k + 1);
+        else
+#endif
+            last = cast_votes_scalar(row, dmax, hp, node_type[k], A, (size_t)k + 1);
+        if (last >= 0) last_connect = k + 1 + last;
     }
-    // blocks -> PS and haplotype of the REF allele (:423-467); one-node blocks are dropped
-    int prev = -1, prev_block = -3;
-    for (int k = 0; k < N; k++) {
-        const int b = block_of[(size_t)k];
-        if (b == -2) continue;
-        if (b != prev_block) { prev_block = b; prev = k; continue; }
-        const int ps = node_pos[b] + 1;
-        if (node_ps[prev] == 0) { node_ps[prev] = ps; if (node_hap_ref[prev] < 0) node_hap_ref[prev] = 0; }
-        node_ps[k] = ps;
-        node_hap_ref[k] = (int8_t)(hp[(size_t)prev] == hp[(size_t)k] ? node_hap_ref[prev] : 1 - node_hap_ref[prev]);
-        prev = k;
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// merged reads with tied positions and > 16 calls: replay std::sort like ReadVariant::sort()
-// --------------------------------------------------------------------------------------------
-namespace {
-struct SortRec { int position; uint32_t packed; };
-struct ByPosition { bool operator()(const SortRec &a, const SortRec &b) const { return a.position < b.position; } };
-}
-
-int lps_host_fix_tie_groups(lps_ctx *ctx, const std::vector<uint32_t> &heads, const std::vector<uint64_t> &keys_sorted,
-                            const std::vector<uint64_t> &grp_off, int base_quality) {
-    const int n = ctx->batch.n_reads, nv = ctx->var.n;
-    // host copies of what the groups are made of
-    std::vector<uint64_t> off((size_t)n + 1);
-    LPS_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_call_off.p, 8 * ((size_t)n + 1), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> node_of((size_t)nv);
-    LPS_CUDA(ctx, cudaMemcpy(node_of.data(), ctx->d_node_of_var.p, 4 * (size_t)nv, cudaMemcpyDeviceToHost));
-    std::vector<uint8_t> erased;
-    if (ctx->have_erased) {
-        erased.resize((size_t)ctx->n_calls);
-        LPS_CUDA(ctx, cudaMemcpy(erased.data(), ctx->d_call_erased.p, (size_t)ctx->n_calls, cudaMemcpyDeviceToHost));
-    }
-    const int n_aln = (int)keys_sorted.size();
-    std::vector<lps_call> buf;
-    std::vector<SortRec> recs;
-    for (uint32_t head : heads) {
-        const uint32_t rank = (uint32_t)(keys_sorted[head] >> 32);
-        int j = (int)head;
-        recs.clear();
-        for (; j < n_aln && (uint32_t)(keys_sorted[(size_t)j] >> 32) == rank; j++) {
-            const int r = (int)(uint32_t)keys_sorted[(size_t)j];
-            const uint64_t c0 = off[(size_t)r], c1 = off[(size_t)r + 1];
-            buf.resize((size_t)(c1 - c0));
-            if (c1 > c0) LPS_CUDA(ctx, cudaMemcpy(buf.data(), ctx->d_calls.p + c0, sizeof(lps_call) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost));
-            for (uint64_t c = c0; c < c1; c++) {
-                if (!erased.empty() && erased[(size_t)c]) continue;
-                const lps_call &cl = buf[(size_t)(c - c0)];
-                const int q = cl.quality < 0 ? 60 : cl.quality;
-                SortRec s;
-                s.position = ctx->h_vpos[(size_t)cl.var];
-                s.packed = ((uint32_t)node_of[(size_t)cl.var] << 2) | ((uint32_t)cl.allele << 1) | (q >= base_quality ? 1u : 0u);
-                recs.push_back(s);
-            }
-        }
-        std::sort(recs.begin(), recs.end(), ByPosition());
-        const uint64_t g0 = grp_off[head], g1 = grp_off[(size_t)j];
-        if (recs.size() != (size_t)(g1 - g0)) return ctx->fail(LPS_E_STATE, "merged group size mismatch in tie fix-up");
-        std::vector<uint32_t> packed(recs.size());
-        for (size_t i = 0; i < recs.size(); i++) packed[i] = recs[i].packed;
-        LPS_CUDA(ctx, cudaMemcpy(ctx->d_M.p + g0, packed.data(), 4 * packed.size(), cudaMemcpyHostToDevice));
-    }
-    return LPS_OK;
+    if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
 }

@@ -17,6 +17,7 @@
 // Cell (a, b) is indexed by node distance d = b - a - 1 < window, nodes being the variants with at
 // least one surviving call (the keys of totalVariantInfo): that is the only part of the table the
 // sweep ever reads (:360-417); contributions to farther pairs are only counted.
+#include <algorithm>
 #include <cub/cub.cuh>
 #include "lps_ctx.cuh"
 
@@ -57,13 +58,15 @@ __global__ void k_node_flags(int nv, const unsigned long long *__restrict__ var_
     if (i < nv) flag[i] = var_lastw[i] != 0;
 }
 
-__global__ void k_fill_nodes(int nv, const unsigned long long *__restrict__ var_lastw, int32_t *__restrict__ node_of_var,
-                             int32_t *__restrict__ node_var, uint8_t *__restrict__ node_type) {
+__global__ void k_fill_nodes(int nv, const unsigned long long *__restrict__ var_lastw, const int32_t *__restrict__ vpos,
+                             int32_t *__restrict__ node_of_var, int32_t *__restrict__ node_var, int32_t *__restrict__ node_pos,
+                             uint8_t *__restrict__ node_type) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
     if (var_lastw[i] != 0) {
         int k = node_of_var[i];
         node_var[k] = i;
+        node_pos[k] = vpos[i];
         node_type[k] = (uint8_t)(var_lastw[i] & 7ull);
     } else node_of_var[i] = -1;
 }
@@ -116,8 +119,8 @@ __global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorte
 // which is what std::sort's insertion-sort branch (n <= 16) does; larger groups with ties are flagged
 // for the host, which replays the same std::sort as the reference (ReadVariant::sort, Util.cpp:3-5).
 __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
-                                    uint32_t *__restrict__ M, uint32_t *__restrict__ tie_groups, uint32_t tie_cap,
-                                    unsigned int *__restrict__ n_tie) {
+                                    uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted, uint2 *__restrict__ tie_groups,
+                                    uint32_t tie_cap, unsigned int *__restrict__ n_tie) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_aln) return;
     uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
@@ -126,6 +129,7 @@ __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys
     while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
     if (j == i + 1) return;                                                      // single alignment
     uint64_t g0 = grp_off[i], g1 = grp_off[j];
+    for (uint64_t a = g0; a < g1; a++) M_unsorted[a] = M[a];                     // concatenation order, for the host replay
     bool tie = false;
     for (uint64_t a = g0 + 1; a < g1; a++) {
         uint32_t v = M[a];
@@ -136,7 +140,20 @@ __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys
     }
     if (tie && g1 - g0 > 16) {
         unsigned k = atomicAdd(n_tie, 1u);
-        if (k < tie_cap) tie_groups[k] = (uint32_t)i;
+        if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
+    }
+}
+
+// staging of the tied groups for the host std::sort replay: one warp per group
+__global__ void k_tie_copy(int n_groups, const uint2 *__restrict__ groups, const uint32_t *__restrict__ stage_off,
+                           uint32_t *__restrict__ M, uint32_t *__restrict__ stage, int to_stage) {
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n_groups) return;
+    uint2 g = groups[wid];
+    uint32_t o = stage_off[wid];
+    for (uint32_t a = g.x + lane; a < g.y; a += 32) {
+        if (to_stage) stage[o + (a - g.x)] = M[a]; else M[a] = stage[o + (a - g.x)];
     }
 }
 
@@ -156,6 +173,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
                                                           const uint64_t *__restrict__ node_off,
                                                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
                                                           const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
+                                                          double edge_threshold, uint8_t *__restrict__ vote_info,
                                                           unsigned long long *__restrict__ counters) {
     extern __shared__ float s_acc[];                       // [WARPS][W*4]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -212,6 +230,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
     __syncwarp();
     float *out = weights + (size_t)a * W * 4;
     for (int i = lane; i < W * 4; i += 32) out[i] = acc[i];
+    // epilogue: everything VariantEdge::findBestEdgePair (:166-228) derives from a cell, one byte per successor:
+    //   bits 0-1 link (1 same haplotype, 2 opposite, 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1,
+    //   bit 4 edgeSimilarRatio < 0.2.  The sweep (k_sweep.cu) only reads these bytes.
+    for (int d = lane; d < W; d += 32) {
+        const float rr = acc[d * 4 + 0], ra = acc[d * 4 + 1], ar = acc[d * 4 + 2], aa = acc[d * 4 + 3];
+        const float para = rr + aa, cross = ar + ra;
+        const double esr = (double)fminf(para, cross) / (double)fmaxf(para, cross);
+        unsigned link = 0;
+        if (rr + aa > ra + ar) link = 1; else if (rr + aa < ra + ar) link = 2;
+        if (esr > edge_threshold) link = 0;
+        unsigned info = link;
+        if ((esr <= 0.1 && (rr + aa + ra + ar) >= 1) || ((rr + aa) < 1 && (ra + ar) >= 1) || ((rr + aa) >= 1 && (ra + ar) < 1)) info |= 4u;
+        if ((para + cross) <= 1) info |= 8u;
+        if (esr < 0.2) info |= 16u;
+        vote_info[(size_t)a * W + d] = (uint8_t)info;
+    }
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) {
         contrib += __shfl_xor_sync(FULL, contrib, dd);
@@ -228,8 +262,46 @@ int bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < (uint64_t)n
 }  // namespace
 
 // host fix-up of merged reads with tied positions and more than 16 calls (see k_sort_multi_groups)
-int lps_host_fix_tie_groups(lps_ctx *ctx, const std::vector<uint32_t> &heads, const std::vector<uint64_t> &keys_sorted,
-                            const std::vector<uint64_t> &grp_off, int base_quality);
+int lps_host_fix_tie_groups(lps_ctx *ctx, int n_groups);
+
+// Merged reads with tied positions and more than 16 calls: libstdc++'s std::sort is not stable there, so the
+// reference's order of the tied calls is whatever its introsort leaves (ReadVariant::sort, Util.cpp:3-5).  The groups
+// (in concatenation order, saved by k_sort_multi_groups) are staged to the host in one copy, sorted with the very same
+// std::sort and comparator (position order == node order), and written back.
+namespace {
+struct SortRec { int position; uint32_t packed; };
+struct ByPosition { bool operator()(const SortRec &a, const SortRec &b) const { return a.position < b.position; } };
+}
+int lps_host_fix_tie_groups(lps_ctx *ctx, int n_groups) {
+    cudaStream_t st = ctx->stream;
+    std::vector<uint2> groups((size_t)n_groups);
+    LPS_CUDA(ctx, cudaMemcpy(groups.data(), ctx->d_tie_groups.p, sizeof(uint2) * (size_t)n_groups, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> off((size_t)n_groups + 1, 0);
+    for (int k = 0; k < n_groups; k++) off[(size_t)k + 1] = off[(size_t)k] + (groups[(size_t)k].y - groups[(size_t)k].x);
+    const size_t total = off[(size_t)n_groups];
+    LPS_CUDA(ctx, ctx->d_tie_off.reserve((size_t)n_groups + 1));
+    LPS_CUDA(ctx, ctx->d_tie_stage.reserve(total + 1));
+    LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tie_off.p, off.data(), 4 * ((size_t)n_groups + 1), cudaMemcpyHostToDevice, st));
+    const int tb = 256;
+    const unsigned grid = (unsigned)(((long long)n_groups * 32 + tb - 1) / tb);
+    k_tie_copy<<<grid, tb, 0, st>>>(n_groups, ctx->d_tie_groups.p, ctx->d_tie_off.p, ctx->d_M_unsorted.p, ctx->d_tie_stage.p, 1);
+    std::vector<uint32_t> stage(total);
+    LPS_CUDA(ctx, cudaMemcpyAsync(stage.data(), ctx->d_tie_stage.p, 4 * total, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<SortRec> recs;
+    for (int k = 0; k < n_groups; k++) {
+        const size_t o = off[(size_t)k], m = off[(size_t)k + 1] - o;
+        recs.resize(m);
+        for (size_t i = 0; i < m; i++) { recs[i].position = (int)(stage[o + i] >> 2); recs[i].packed = stage[o + i]; }
+        std::sort(recs.begin(), recs.end(), ByPosition());
+        for (size_t i = 0; i < m; i++) stage[o + i] = recs[i].packed;
+    }
+    LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tie_stage.p, stage.data(), 4 * total, cudaMemcpyHostToDevice, st));
+    k_tie_copy<<<grid, tb, 0, st>>>(n_groups, ctx->d_tie_groups.p, ctx->d_tie_off.p, ctx->d_M.p, ctx->d_tie_stage.p, 0);
+    ctx->stats.kernel_launches += 2;
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    return LPS_OK;
+}
 
 int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     cudaStream_t st = ctx->stream;
@@ -243,6 +315,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_node_of_var.reserve((size_t)nv + 2));
     LPS_CUDA(ctx, ctx->d_node_var.reserve((size_t)nv + 1));
     LPS_CUDA(ctx, ctx->d_node_type.reserve((size_t)nv + 1));
+    LPS_CUDA(ctx, ctx->d_node_pos.reserve((size_t)nv + 66));
     LPS_CUDA(ctx, ctx->d_grp_off.reserve((size_t)n + 2));
     LPS_CUDA(ctx, ctx->d_edge_counters.reserve(4));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_var_lastw.p, 0, 8 * ((size_t)nv + 1), st));
@@ -270,8 +343,8 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_node_of_var.p, ctx->d_node_of_var.p, nv + 1, st);
     int32_t n_nodes = 0;
     LPS_CUDA(ctx, cudaMemcpyAsync(&n_nodes, ctx->d_node_of_var.p + nv, 4, cudaMemcpyDeviceToHost, st));
-    k_fill_nodes<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->d_node_of_var.p,
-                                                ctx->d_node_var.p, ctx->d_node_type.p);
+    k_fill_nodes<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->var.pos, ctx->d_node_of_var.p,
+                                                ctx->d_node_var.p, ctx->d_node_pos.p, ctx->d_node_type.p);
     ctx->stats.kernel_launches += 3;
     // 3. alignments in (name rank, BAM order); offsets of their calls inside M
     int rank_bits = 32 + 32;
@@ -294,6 +367,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_node_cnt.reserve((size_t)n_nodes + 2));
     LPS_CUDA(ctx, ctx->d_node_off.reserve((size_t)n_nodes + 2));
     LPS_CUDA(ctx, ctx->d_weights.reserve((size_t)n_nodes * (size_t)W * 4 + 4));
+    LPS_CUDA(ctx, ctx->d_vote_info.reserve(((size_t)n_nodes + 130) * (size_t)W + 64));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_cnt.p, 0, 4 * ((size_t)n_nodes + 2), st));
 
     // alive alignments: keys != ~0 are a prefix of the sorted array
@@ -311,29 +385,24 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
             n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_call_off.p, ctx->d_calls.p, erased, ctx->d_node_of_var.p,
             p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
         // multi-alignment merged reads
-        DevBuf<uint32_t> tie_groups;
-        DevBuf<unsigned int> n_tie;
-        const uint32_t tie_cap = 1u << 16;
+        DevBuf<uint2> &tie_groups = ctx->d_tie_groups;
+        DevBuf<unsigned int> &n_tie = ctx->d_n_tie;
+        const uint32_t tie_cap = 1u << 18;
         LPS_CUDA(ctx, tie_groups.reserve(tie_cap));
         LPS_CUDA(ctx, n_tie.reserve(1));
+        LPS_CUDA(ctx, ctx->d_M_unsorted.reserve((size_t)n_merged + 1));
         LPS_CUDA(ctx, cudaMemsetAsync(n_tie.p, 0, 4, st));
         k_sort_multi_groups<<<(n_aln + tb - 1) / tb, tb, 0, st>>>(n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p,
-                                                                  tie_groups.p, tie_cap, n_tie.p);
+                                                                  ctx->d_M_unsorted.p, tie_groups.p, tie_cap, n_tie.p);
         ctx->stats.kernel_launches += 2;
         unsigned int h_tie = 0;
         LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, n_tie.p, 4, cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
         if (h_tie > tie_cap) return ctx->fail(LPS_E_NOMEM, "too many tied merged reads");
         if (h_tie) {
-            std::vector<uint32_t> heads(h_tie);
-            std::vector<uint64_t> keys((size_t)n_aln), goff((size_t)n_aln + 1);
-            LPS_CUDA(ctx, cudaMemcpy(heads.data(), tie_groups.p, 4 * (size_t)h_tie, cudaMemcpyDeviceToHost));
-            LPS_CUDA(ctx, cudaMemcpy(keys.data(), ctx->d_aln_keys_sorted.p, 8 * (size_t)n_aln, cudaMemcpyDeviceToHost));
-            LPS_CUDA(ctx, cudaMemcpy(goff.data(), ctx->d_grp_off.p, 8 * ((size_t)n_aln + 1), cudaMemcpyDeviceToHost));
-            int rc = lps_host_fix_tie_groups(ctx, heads, keys, goff, p->base_quality);
+            int rc = lps_host_fix_tie_groups(ctx, (int)h_tie);
             if (rc) return rc;
         }
-        tie_groups.release(); n_tie.release();
 
         // 4. per-node call lists in merged (= name rank) order: one stable radix sort by node
         k_split_merged<<<(unsigned)((n_merged + tb - 1) / tb), tb, 0, st>>>(n_merged, ctx->d_M.p, ctx->d_M_node.p, ctx->d_M_idx.p);
@@ -355,13 +424,14 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     if (n_nodes > 0) {
         if (n_merged == 0) {
             LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_weights.p, 0, 4 * (size_t)n_nodes * W * 4, st));
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_vote_info.p, 0, (size_t)n_nodes * W, st));
         } else {
             constexpr int WARPS = 8;
             size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
             cudaEventRecord(ctx->kev[2], st);
             k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
                 n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
-                (unsigned long long *)ctx->d_edge_counters.p);
+                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p);
             cudaEventRecord(ctx->kev[3], st);
             ctx->stats.kernel_launches++;
         }

@@ -70,8 +70,8 @@ int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_hp_counts.reserve((size_t)nv * 4 + 4));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_hp_counts.p, 0, 16 * (size_t)nv + 16, st));
     const uint8_t *erased = ctx->have_erased ? ctx->d_call_erased.p : nullptr;
-    DevBuf<int32_t> ps_final;
-    DevBuf<int8_t> hap_final;
+    DevBuf<int32_t> &ps_final = ctx->d_ps_final;
+    DevBuf<int8_t> &hap_final = ctx->d_hap_final;
     LPS_CUDA(ctx, ps_final.reserve((size_t)nv + 1));
     LPS_CUDA(ctx, hap_final.reserve((size_t)nv + 1));
     if (n > 0) {
@@ -89,6 +89,5 @@ int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p) {
     }
     LPS_CUDA(ctx, cudaGetLastError());
     LPS_CUDA(ctx, cudaStreamSynchronize(st));
-    ps_final.release(); hap_final.release();
     return LPS_OK;
 }

@@ -248,7 +248,7 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
     std::vector<int32_t> first_pos, last_pos;
     std::vector<uint32_t> ncalls;
     {
-        DevBuf<int32_t> d_first, d_last;
+        DevBuf<int32_t> &d_first = ctx->d_first_pos, &d_last = ctx->d_last_pos;
         LPS_CUDA(ctx, d_first.reserve((size_t)n + 1));
         LPS_CUDA(ctx, d_last.reserve((size_t)n + 1));
         if (n > 0) {
@@ -259,7 +259,6 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
         TRY(d2h(ctx, last_pos, d_last.p, (size_t)n));
         TRY(d2h(ctx, ncalls, ctx->d_ncalls.p, (size_t)n));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
-        d_first.release(); d_last.release();
     }
     WallTimer wf;
     TRY(lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls));
@@ -312,23 +311,27 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     cudaStream_t st = ctx->stream;
     const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
     WallTimer wt;
-    if (ctx->h_weights.size() != nn * (size_t)ctx->window * 4) {
-        TRY(d2h(ctx, ctx->h_weights, ctx->d_weights.p, nn * (size_t)ctx->window * 4));
-        LPS_CUDA(ctx, cudaStreamSynchronize(st));
-    }
-    // ---- host sweep (edgeConnectResult) ----
+    // ---- sweep (edgeConnectResult) on the host over the one-byte votes computed by the fold epilogue ----
+    const size_t W = (size_t)ctx->window;
+    LPS_CUDA(ctx, ctx->p_vote_info.reserve(nn * W + 16));
+    if (nn) LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_vote_info.p, ctx->d_vote_info.p, nn * W, cudaMemcpyDeviceToHost, st));
+    ctx->stats.d2h_bytes += nn * W;
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    WallTimer ws;
     std::vector<int32_t> node_pos(nn), node_ps(nn);
     std::vector<int8_t> node_hap(nn);
     for (size_t k = 0; k < nn; k++) node_pos[k] = ctx->h_vpos[(size_t)ctx->h_node_var[k]];
-    WallTimer ws;
-    lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->h_weights.data(), node_ps.data(),
+    lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->p_vote_info.p, node_ps.data(),
                    node_hap.data());
+    ctx->h_ps_sweep.assign(nv, 0);
+    ctx->h_hap_sweep.assign(nv, -1);
+    for (size_t k = 0; k < nn; k++) {
+        ctx->h_ps_sweep[(size_t)ctx->h_node_var[k]] = node_ps[k];
+        ctx->h_hap_sweep[(size_t)ctx->h_node_var[k]] = node_hap[k];
+    }
     ctx->stats.ms_host_sweep = ws.ms();
-    ctx->h_ps.assign(nv, 0);
-    ctx->h_hap_ref.assign(nv, -1);
-    for (size_t k = 0; k < nn; k++) { ctx->h_ps[(size_t)ctx->h_node_var[k]] = node_ps[k]; ctx->h_hap_ref[(size_t)ctx->h_node_var[k]] = node_hap[k]; }
-    TRY(h2d(ctx, ctx->d_ps, ctx->h_ps.data(), nv));
-    TRY(h2d(ctx, ctx->d_hap_ref, ctx->h_hap_ref.data(), nv));
+    TRY(h2d(ctx, ctx->d_ps, ctx->h_ps_sweep.data(), nv));
+    TRY(h2d(ctx, ctx->d_hap_ref, ctx->h_hap_sweep.data(), nv));
     // ---- device: read correction ----
     cudaEventRecord(ctx->ev[2], st);
     TRY(lps_launch_read_correction(ctx, p));
@@ -343,6 +346,7 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
         memset(out, 0, sizeof(*out));
         out->n_variants = ctx->var.n; out->ps = ctx->h_ps.data(); out->hap_ref = ctx->h_hap_ref.data();
         out->n_reads = ctx->batch.n_reads; out->read_hp = ctx->h_read_hp.data(); out->hp_counts = ctx->h_hp_counts.data();
+        out->ps_sweep = ctx->h_ps_sweep.data(); out->hap_ref_sweep = ctx->h_hap_sweep.data();
     }
     ctx->stats.ms_wall_solve = wt.ms();
     return LPS_OK;
@@ -350,7 +354,7 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
 
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
     TRY(lps_phase_call_alleles(ctx, p, 0, nullptr));
-    TRY(lps_phase_build_edges(ctx, p, 1, nullptr));
+    TRY(lps_phase_build_edges(ctx, p, 0, nullptr));
     return lps_phase_solve(ctx, p, out);
 }
 

@@ -90,7 +90,7 @@ struct lps_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t user_ev[4] = {};
-    cudaEvent_t kev[4] = {};   // around the two hot kernels
+    cudaEvent_t kev[6] = {};   // around the hot kernels
     std::string err;
     int err_code = 0;
     lps_stats stats = {};
@@ -155,7 +155,15 @@ struct lps_ctx {
     DevBuf<uint32_t> d_node_cnt;
     DevBuf<uint64_t> d_node_off;
     DevBuf<float> d_weights;
+    DevBuf<uint8_t> d_vote_info;                    // [n_nodes][window] one byte per (node, successor): see k_sweep.cu
+    DevBuf<int32_t> d_node_pos;
+    PinBuf<uint8_t> p_vote_info;                    // pinned staging of the vote bytes for the host sweep
     DevBuf<unsigned long long> d_edge_counters;     // [0] contrib, [1] far
+    DevBuf<uint2> d_tie_groups;
+    DevBuf<uint32_t> d_M_unsorted, d_tie_off, d_tie_stage;
+    DevBuf<unsigned int> d_n_tie;
+    DevBuf<int32_t> d_first_pos, d_last_pos, d_ps_final;
+    DevBuf<int8_t> d_hap_final;
     int32_t n_nodes = 0;
     int32_t window = 0;
     uint64_t n_merged = 0;
@@ -169,7 +177,8 @@ struct lps_ctx {
     DevBuf<int32_t> d_ps, d_hp_counts;
     DevBuf<int8_t> d_hap_ref, d_read_hp;
     std::vector<int32_t> h_ps, h_hp_counts;
-    std::vector<int8_t> h_hap_ref, h_read_hp;
+    std::vector<int8_t> h_hap_ref, h_read_hp, h_hap_sweep;
+    std::vector<int32_t> h_ps_sweep;
 
     int fail(int code, const std::string &msg) {
         err_code = code;
@@ -189,5 +198,5 @@ int lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::
 void lps_host_cnv_intervals(const std::vector<int32_t> &pos, const std::vector<int32_t> &front,
                             const std::vector<int32_t> &back, std::vector<int32_t> &cs, std::vector<int32_t> &ce);
 int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);
-void lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos,
-                    const uint8_t *node_type, const float *weights, int32_t *node_ps, int8_t *node_hap_ref);
+void lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
+                    const uint8_t *vote_info, int32_t *node_ps, int8_t *node_hap_ref);

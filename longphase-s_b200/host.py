@@ -93,7 +93,8 @@ class Context:
         g = _ffi.as_np
         return dict(ps=g(o.ps, o.n_variants, np.int32), hap_ref=g(o.hap_ref, o.n_variants, np.int8),
                     read_hp=g(o.read_hp, o.n_reads, np.int8),
-                    hp_counts=g(o.hp_counts, o.n_variants * 4, np.int32).reshape(o.n_variants, 4))
+                    hp_counts=g(o.hp_counts, o.n_variants * 4, np.int32).reshape(o.n_variants, 4),
+                    ps_sweep=g(o.ps_sweep, o.n_variants, np.int32), hap_ref_sweep=g(o.hap_ref_sweep, o.n_variants, np.int8))
 
     def solve(self, params):
         o = _ffi.LpsPhaseResult()

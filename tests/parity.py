@@ -38,6 +38,8 @@ def check_phase(contig, params, ctx=None, verbose=False):
         assert edges["weights"].tobytes() == orc.weights.tobytes(), "edge weights differ (bit pattern)"
         assert edges["n_contrib"] == orc.n_contrib and edges["n_contrib_far"] == orc.n_contrib_far, "contribution counts differ"
         res = g.phasingProcess()
+        assert np.array_equal(res["ps_sweep"], orc.ps_sweep), "sweep phase sets differ"
+        assert np.array_equal(res["hap_ref_sweep"], orc.hap_ref_sweep), "sweep haplotypes differ"
         assert np.array_equal(res["ps"], orc.ps), "phase sets differ"
         m = orc.ps != 0
         assert np.array_equal(res["hap_ref"][m], orc.hap_ref[m]), "haplotypes differ"
