@@ -185,9 +185,49 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
 /* all of the above for one contig (the body of the loop at PhasingProcess.cpp:113-173)         */
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
 
+/* ---- haplotag (germline tag dialect) -------------------------------------------------------- */
+/* dispatch category of every alignment, in the order of ChromosomeProcessor::processSingleChrom
+ * (src/haplotag/HaplotagParsingBam.cpp:457-486); only PROCESSED alignments reach processRead          */
+enum { LPS_TAG_PROCESSED = 0, LPS_TAG_LOW_MAPQ = 1, LPS_TAG_UNMAPPED = 2, LPS_TAG_SECONDARY = 3,
+       LPS_TAG_SUPPLEMENTARY = 4, LPS_TAG_EMPTY_VARIANTS = 5, LPS_TAG_OTHER = 6 };
+
+typedef struct {
+    int32_t mapping_quality;      /* -q qualityThreshold, default 1 (src/haplotag/Haplotag.cpp:60-72)      */
+    int32_t mapq_filter;          /* ParsingBamControl::mappingQualityFilter (true for `haplotag`)         */
+    int32_t tag_supplementary;    /* --tagSupplementary                                                    */
+    int32_t have_reference;       /* ref_string != "" (HaplotagStrategy.cpp:159)                           */
+    double percentage_threshold;  /* -p, default 0.6                                                       */
+} lps_tag_params;
+
+/* result of lps_tag_reads: one entry per alignment of the batch, arrays owned by the context              */
+typedef struct {
+    int32_t n_reads;
+    const uint8_t *category;      /* LPS_TAG_*                                                             */
+    const int8_t *hp;             /* ReadHP: 0 unTag, 1 H1, 2 H2 -> HP:i (HaplotagProcess.cpp:357-361)     */
+    const int32_t *ps;            /* PS:i (smallest phase set seen, HaplotagStrategy.cpp:295-298), 0 if untagged */
+    const int32_t *pq;            /* PQ:i (HaplotagStrategy.cpp:279-288)                                   */
+    const int32_t *h1, *h2;       /* hpCount[GERMLINE_H1], hpCount[GERMLINE_H2]                            */
+    /* optional (want_calls): the variants that touched countPS, CSR per alignment; lps_call.allele is the
+     * variantsHP value (0 = HP1, 1 = HP2, -1 = only counted towards countPS), lps_call.origin 0 SNP in an M op,
+     * 1 SNP by the D-op rule, 2 indel                                                                      */
+    uint64_t n_calls;
+    const uint64_t *call_off;
+    const lps_call *calls;
+    /* ReadStatistics (src/haplotag/HaplotagProcess.h:21-45) reduced over the batch                         */
+    int64_t total_alignment, total_supplementary, total_secondary, total_unmapped, total_tag, total_untag,
+            total_lower_quality, total_other_case, total_empty_variant, total_high_similarity,
+            total_without_variant, total_hp1, total_hp2, total_hp0;
+} lps_tag_result;
+
+/* GermlineHaplotagChrProcessor::processRead for every alignment of the batch: CigarParser::parsingCigar
+ * (HaplotagParsingBam.cpp:541-647) + GermlineHaplotagStrategy::judgeSnpHap / judgeDeletionHap / judgeReadHap
+ * (HaplotagStrategy.cpp:20-300).  The variant table must carry hp1_is_alt and ps (lps_contig_set_variants). */
+int lps_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_tag_result *out);
+
 /* ---- timing / accounting ------------------------------------------------------------------ */
 typedef struct {
     float ms_call_alleles;   /* device time of the allele-calling kernels of the last call      */
+    float ms_tag_reads;      /* device time of the last lps_tag_reads                            */
     float ms_build_edges;
     float ms_read_correction;
     float ms_h2d;

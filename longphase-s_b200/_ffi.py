@@ -69,8 +69,28 @@ class LpsPhaseResult(C.Structure):
                 ("read_hp", i8p), ("hp_counts", i32p), ("ps_sweep", i32p), ("hap_ref_sweep", i8p)]
 
 
+class LpsTagParams(C.Structure):
+    _fields_ = [("mapping_quality", C.c_int32), ("mapq_filter", C.c_int32), ("tag_supplementary", C.c_int32),
+                ("have_reference", C.c_int32), ("percentage_threshold", C.c_double)]
+
+
+def default_tag_params():
+    """Defaults of `longphase-s haplotag` (reference src/haplotag/Haplotag.cpp:60-72)."""
+    return LpsTagParams(mapping_quality=1, mapq_filter=1, tag_supplementary=0, have_reference=1, percentage_threshold=0.6)
+
+
+TAG_COUNTERS = ["total_alignment", "total_supplementary", "total_secondary", "total_unmapped", "total_tag", "total_untag",
+                "total_lower_quality", "total_other_case", "total_empty_variant", "total_high_similarity",
+                "total_without_variant", "total_hp1", "total_hp2", "total_hp0"]
+
+
+class LpsTagResult(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("category", u8p), ("hp", i8p), ("ps", i32p), ("pq", i32p), ("h1", i32p), ("h2", i32p),
+                ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))] + [(k, C.c_int64) for k in TAG_COUNTERS]
+
+
 class LpsStats(C.Structure):
-    _fields_ = [("ms_call_alleles", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
+    _fields_ = [("ms_call_alleles", C.c_float), ("ms_tag_reads", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_kernel_call_alleles", C.c_float),
                 ("ms_kernel_fold_edges", C.c_float), ("ms_wall_call_alleles", C.c_float),
                 ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
@@ -93,6 +113,7 @@ SYMBOLS = {
     "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_phase_contig": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
+    "lps_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsTagResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -58,6 +58,17 @@ struct K1Args {
     uint32_t *overflow_list_out;      // main pass: list of reads that overflowed
     uint64_t *overflow_need_out;      // main pass: candidates they need
     uint32_t overflow_list_cap;
+    // ---- tag dialect (CigarParser::parsingCigar + GermlineHaplotagStrategy) ----
+    const uint8_t *hp1_is_alt;        // per variant: HP1 carries ALT (GT 1|0)
+    const int32_t *var_ps;            // per variant: phase set
+    int mapq_filter;                  // ParsingBamControl::mappingQualityFilter
+    int tag_supplementary;            // ParsingBamConfig::tagSupplementary
+    int want_calls;                   // also emit the per-read (variant, haplotype) list
+    double percentage;                // ParsingBamConfig::percentageThreshold
+    const int8_t *pq_lut;             // [256][256] PQ by (min, max), built on the host with the host libm
+    int8_t *tag_hp;                   // ReadHP: 0 unTag, 1 H1, 2 H2
+    int32_t *tag_ps, *tag_pq, *tag_h1, *tag_h2;
+    uint8_t *tag_cat;                 // dispatch category, see LPS_TAG_* in lps.h
 };
 
 __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ pos, int n, int key, int lane) {
@@ -126,7 +137,7 @@ struct WarpScratch {
     Cand cand[CAND_CAP];
 };
 
-template <int K>
+template <int K, bool TAG>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a) {
     __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -152,10 +163,29 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
     const int lq = a.b.l_qseq[r];
     const int ncig = (int)a.b.n_cigar[r];
     const int flag = a.b.flag[r];
-    // iterator region "chr:1-lastSNP" (ParsingBam.cpp:1273) + read filter (:1282-1291)
-    if (ref_start >= a.last_var_pos || (int)a.b.mapq[r] < a.mapping_quality || (flag & (0x4 | 0x100 | 0x400))) {
-        if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED; }
-        return;
+    if (!TAG) {
+        // iterator region "chr:1-lastSNP" (ParsingBam.cpp:1273) + read filter (:1282-1291)
+        if (ref_start >= a.last_var_pos || (int)a.b.mapq[r] < a.mapping_quality || (flag & (0x4 | 0x100 | 0x400))) {
+            if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED; }
+            return;
+        }
+    } else {
+        // dispatch of ChromosomeProcessor::processSingleChrom (HaplotagParsingBam.cpp:457-486), in its order
+        int cat = LPS_TAG_PROCESSED;
+        if ((int)a.b.mapq[r] < a.mapping_quality && a.mapq_filter) cat = LPS_TAG_LOW_MAPQ;
+        else if (flag & 0x4) cat = LPS_TAG_UNMAPPED;
+        else if (flag & 0x100) cat = LPS_TAG_SECONDARY;
+        else if ((flag & 0x800) && !a.tag_supplementary) cat = LPS_TAG_SUPPLEMENTARY;
+        else if (nv == 0) cat = LPS_TAG_EMPTY_VARIANTS;
+        else if (!(ref_start <= a.last_var_pos)) cat = LPS_TAG_OTHER;
+        if (lane == 0 && !overflow_pass) a.tag_cat[r] = (uint8_t)cat;
+        if (cat != LPS_TAG_PROCESSED) {
+            if (lane == 0) {
+                a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED;
+                a.tag_hp[r] = 0; a.tag_ps[r] = 0; a.tag_pq[r] = 0; a.tag_h1[r] = 0; a.tag_h2[r] = 0;
+            }
+            return;
+        }
     }
     const int32_t *__restrict__ vpos = a.v.pos;
     // window of 32 variant positions, one per lane; `cur` is the first pending variant
@@ -249,6 +279,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                     const int64_t gidx = cb + j;
                     const int opi = (int)(gidx - lo);
                     my_op_index = opi;
+                    if (TAG) {
+                        // CigarParser::parsingCigar M branch (HaplotagParsingBam.cpp:585-614) + judgeSnpHap (HaplotagStrategy.cpp:20-130)
+                        if (o_op == 0 || o_op == 7 || o_op == 8) {
+                            const int off = vp - o_r;
+                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                            if (rl == 1 && al == 1) {
+                                // the reference reads seq[query_pos+offset] without a bounds check; past l_qseq that is
+                                // memory of the BAM record (undefined) — such a hit is dropped here
+                                if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                            } else if ((rl == 1) != (al == 1)) {
+                                if (opi + 1 < ncig) {
+                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
+                                    const unsigned want = (rl == 1) ? 1u : 2u;
+                                    const bool has = (o_r + o_len - 1 == vp && nop == want);
+                                    const bool h1alt = a.hp1_is_alt[vi] != 0;
+                                    const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;       // lengths of the HP1 / HP2 allele strings
+                                    // read shows the indel: the haplotype whose allele string is not 1 long gets the vote, else the other
+                                    int hpbit = -1;
+                                    if (l1 != 1 && l2 == 1) hpbit = has ? 0 : 1;
+                                    else if (l1 == 1 && l2 != 1) hpbit = has ? 1 : 0;
+                                    cand_var = vi;
+                                    cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
+                                }
+                            }
+                        } else if (o_op == 2) in_del = true;
+                    } else
                     if (o_op == 0 || o_op == 7 || o_op == 8) {
                         const int off = vp - o_r;
                         if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
@@ -269,6 +325,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                 }
                 // D-op rule (:1539-1607): only the FIRST pending variant of the op (previous variant lies before the op)
                 const int prev_pos = __shfl_up_sync(FULL, vwin, 1);
+                if (TAG && in_del) {
+                    // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
+                    // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
+                    const int o_r = S.r[my_j], o_q = S.q[my_j];
+                    const int vi = win_base + lane;
+                    const int pv = lane > 0 ? prev_pos : win_prev;
+                    if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
+                        const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                        if (rl == 1 && al == 1) {
+                            if (o_q < lq) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                        } else if (rl != 1 && al == 1) {
+                            const bool h1alt = a.hp1_is_alt[vi] != 0;
+                            const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;
+                            int hpbit = -1;
+                            if (l1 != 1 && l2 == 1) hpbit = 0; else if (l1 == 1 && l2 != 1) hpbit = 1;
+                            cand_var = vi;
+                            cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
+                        }
+                    }
+                } else
                 if (in_del) {
                     const int o_r = S.r[my_j], o_q = S.q[my_j];
                     const int vi = win_base + lane;
@@ -323,7 +399,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                 const unsigned op = ops[j] & 15u;
                 const int len = (int)(ops[j] >> 4);
                 const int64_t g = cb + (int64_t)lane * K + j;
-                if ((op == 4 || op == 5) && len > 5 && (int)(g - lo) < abort_op) {
+                if (!TAG && (op == 4 || op == 5) && len > 5 && (int)(g - lo) < abort_op) {
                     unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
                     if (slot < a.clip_cap) a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
                 }
@@ -353,6 +429,83 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
         return;
     }
     __syncwarp();
+
+    if (TAG) {
+        // ---- resolve: per candidate the haplotype bit and the "counts towards countPS" flag, then judgeReadHap ----
+        const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
+        int h1 = 0, h2 = 0, ps_min = INT_MAX, ps_max = INT_MIN, nout = 0;
+        for (int c0 = 0; c0 < ncand; c0 += 32) {
+            const int c = c0 + lane;
+            int hpbit = -1; bool ps_counted = false; int var = -1; unsigned kind = 0;
+            if (c < ncand) {
+                const Cand cd = cand[c];
+                kind = cd.x >> 30; var = cd.var;
+                if (kind == 2) { ps_counted = true; if (cd.x & 2u) hpbit = (int)(cd.x & 1u); }
+                else {
+                    const int qi = (int)(cd.x & 0x3fffffffu);
+                    const unsigned code = (seq[qi >> 1] >> ((~qi & 1) << 2)) & 0xfu;
+                    const char base = "=ACMGRSVTWYHKDBN"[code];
+                    const char rb = (char)a.v.ref0[var], ab = (char)a.v.alt0[var];
+                    const bool h1alt = a.hp1_is_alt[var] != 0;
+                    const char hp1 = h1alt ? ab : rb, hp2 = h1alt ? rb : ab;
+                    // M op: only a REF/ALT base counts at all (HaplotagStrategy.cpp:39); D-op rule: countPS unconditionally (:186)
+                    if (kind == 1 || base == rb || base == ab) {
+                        ps_counted = true;
+                        if (base == hp1) hpbit = 0;
+                        if (base == hp2) hpbit = 1;     // HP2 assigned last, as in the reference (:52-59)
+                    }
+                }
+            }
+            if (ps_counted) { const int ps = a.var_ps[var]; ps_min = min(ps_min, ps); ps_max = max(ps_max, ps); }
+            if (hpbit == 0) h1++; else if (hpbit == 1) h2++;
+            // a base equal to both HP1 and HP2 cannot happen for a het; H1 and H2 counts are therefore exclusive
+            if (a.want_calls) {
+                const unsigned m = __ballot_sync(FULL, ps_counted);
+                __syncwarp();
+                if (ps_counted) {
+                    const int dst = nout + __popc(m & ((1u << lane) - 1u));
+                    Cand packed;
+                    packed.var = var;
+                    packed.x = ((uint32_t)(uint16_t)(int16_t)1) | ((uint32_t)(uint8_t)(int8_t)hpbit << 16) | ((uint32_t)kind << 24);
+                    cand[dst] = packed;
+                }
+                nout += __popc(m);
+                __syncwarp();
+            }
+        }
+        h1 = (int)__reduce_add_sync(FULL, (unsigned)h1);
+        h2 = (int)__reduce_add_sync(FULL, (unsigned)h2);
+        ps_min = __reduce_min_sync(FULL, ps_min);
+        ps_max = __reduce_max_sync(FULL, ps_max);
+        if (lane == 0) {
+            // GermlineHaplotagStrategy::judgeReadHap (HaplotagStrategy.cpp:243-300)
+            const double mx = (double)(h1 > h2 ? h1 : h2), mn = (double)(h1 > h2 ? h2 : h1);
+            int hp = 0;
+            if (!(mx / (mx + mn) < a.percentage)) { if (h1 > h2) hp = 1; if (h1 < h2) hp = 2; }
+            if (ps_min != INT_MAX && ps_min != ps_max) hp = 0;                  // countPS.size() > 1: crosses two blocks
+            const int imx = h1 > h2 ? h1 : h2, imn = h1 > h2 ? h2 : h1;
+            int pq;
+            if (imx == 0) pq = 0; else if (imn == 0) pq = 40;
+            else pq = (imx < 256) ? (int)a.pq_lut[imn * 256 + imx] : -1;         // -1: the host fills it in with its libm
+            a.tag_hp[r] = (int8_t)hp; a.tag_ps[r] = hp ? ps_min : 0; a.tag_pq[r] = pq; a.tag_h1[r] = h1; a.tag_h2[r] = h2;
+        }
+        unsigned long long start = 0;
+        if (lane == 0 && nout) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nout);
+        start = __shfl_sync(FULL, start, 0);
+        if (lane == 0) { a.ncalls[r] = (uint32_t)nout; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
+        if (start + nout <= a.calls_cap) {
+            for (int c = lane; c < nout; c += 32) {
+                const Cand cd = cand[c];
+                lps_call out;
+                out.var = cd.var;
+                out.quality = (int16_t)(cd.x & 0xffffu);
+                out.allele = (int8_t)((cd.x >> 16) & 0xffu);
+                out.origin = (int8_t)((cd.x >> 24) & 0xffu);
+                a.calls_tmp[start + c] = out;
+            }
+        }
+        return;
+    }
 
     // ---- resolve candidates: gather base + quality, decide the allele, drop filterSNP variants ----
     const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
@@ -438,7 +591,8 @@ __global__ void k_widen_u32(int n, const uint32_t *__restrict__ in, uint64_t *__
 
 static_assert(sizeof(lps_call) == 8, "lps_call must be 8 bytes");
 
-int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls) {
+    const bool tag = t != nullptr;
     const int n = ctx->batch.n_reads;
     const int nv = ctx->var.n;
     cudaStream_t st = ctx->stream;
@@ -447,6 +601,11 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_ncalls.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_status.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_counters.reserve(1));
+    if (tag) {
+        LPS_CUDA(ctx, ctx->d_tag_hp.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_ps.reserve((size_t)n + 1));
+        LPS_CUDA(ctx, ctx->d_tag_pq.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_h1.reserve((size_t)n + 1));
+        LPS_CUDA(ctx, ctx->d_tag_h2.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_cat.reserve((size_t)n + 1));
+    }
     // scratch pool capacity from the variant density of the contig; re-run on overflow
     double density = 0.0;
     if (nv > 1) density = (double)nv / ((double)ctx->h_vpos[nv - 1] - (double)ctx->h_vpos[0] + 1.0);
@@ -466,8 +625,17 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
         K1Args a;
         memset(&a, 0, sizeof(a));
         a.b = ctx->batch; a.v = ctx->var;
-        a.mapping_quality = p->mapping_quality; a.have_reference = p->have_reference && ctx->ref_len > 0;
-        a.apply_filter = p->is_ont;
+        if (!tag) {
+            a.mapping_quality = p->mapping_quality; a.have_reference = p->have_reference && ctx->ref_len > 0;
+            a.apply_filter = p->is_ont;
+        } else {
+            a.mapping_quality = t->mapping_quality; a.have_reference = t->have_reference && ctx->ref_len > 0;
+            a.mapq_filter = t->mapq_filter; a.tag_supplementary = t->tag_supplementary; a.want_calls = want_calls;
+            a.percentage = t->percentage_threshold;
+            a.hp1_is_alt = ctx->d_vhp1_is_alt.p; a.var_ps = ctx->d_vps.p; a.pq_lut = ctx->d_pq_lut.p;
+            a.tag_hp = ctx->d_tag_hp.p; a.tag_ps = ctx->d_tag_ps.p; a.tag_pq = ctx->d_tag_pq.p;
+            a.tag_h1 = ctx->d_tag_h1.p; a.tag_h2 = ctx->d_tag_h2.p; a.tag_cat = ctx->d_tag_cat.p;
+        }
         a.last_var_pos = nv ? ctx->h_vpos[nv - 1] : -1;
         a.calls_tmp = ctx->d_calls_tmp.p; a.calls_cap = ctx->d_calls_tmp.cap;
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
@@ -478,7 +646,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
         const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > 0) {
             cudaEventRecord(ctx->kev[0], st);
-            k_call_alleles<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+            if (tag) k_call_alleles<8, true><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a); else k_call_alleles<8, false><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
             cudaEventRecord(ctx->kev[1], st);
             ctx->stats.kernel_launches++;
         }
@@ -508,7 +676,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
             LPS_CUDA(ctx, cudaMemcpyAsync(scratch.p, ctx->d_counters.p, sizeof(CallCounters), cudaMemcpyDeviceToDevice, st));
             b2.counters = scratch.p;
             const int g2 = ((int)hc.overflow_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-            k_call_alleles<8><<<g2, WARPS_PER_CTA * 32, 0, st>>>(b2);
+            if (tag) k_call_alleles<8, true><<<g2, WARPS_PER_CTA * 32, 0, st>>>(b2); else k_call_alleles<8, false><<<g2, WARPS_PER_CTA * 32, 0, st>>>(b2);
             ctx->stats.kernel_launches++;
             LPS_CUDA(ctx, cudaGetLastError());
             CallCounters h2;
@@ -575,7 +743,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p) {
             if (keys[i] & 1u) ctx->h_clip_back.back() += (int32_t)cnts[i]; else ctx->h_clip_front.back() += (int32_t)cnts[i];
         }
     }
-    ctx->have_calls = true;
+    ctx->have_calls = !tag;
     ctx->host_calls_valid = false;
     return LPS_OK;
 }

@@ -1,5 +1,6 @@
 // lps_api.cu — the extern "C" boundary declared in include/lps.h.
 #include <chrono>
+#include <cmath>
 #include "lps_ctx.cuh"
 
 namespace {
@@ -69,6 +70,18 @@ int lps_ctx_create(int device, lps_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->user_ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->kev) cudaEventCreate(&ev);
+    {
+        // PQ = (int)(-10*log10(min/(max+min))) (HaplotagStrategy.cpp:287) tabulated with the HOST libm, so that the
+        // truncation to int agrees with the reference on the same machine; the kernel only looks it up
+        std::vector<int8_t> lut(256 * 256, 0);
+        for (int mn = 1; mn < 256; mn++)
+            for (int mx = mn; mx < 256; mx++) {
+                int pq = -10 * (std::log10((double)mn / double(mx + mn)));
+                lut[(size_t)mn * 256 + mx] = (int8_t)pq;
+            }
+        if (ctx->d_pq_lut.reserve(lut.size()) != cudaSuccess ||
+            cudaMemcpy(ctx->d_pq_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
+    }
     *out = ctx;
     return LPS_OK;
 }
@@ -132,6 +145,12 @@ int lps_contig_set_variants(lps_ctx *ctx, const lps_variants *v, int is_ont) {
     ctx->var.ref_len = ctx->d_vref_len.p; ctx->var.alt_len = ctx->d_valt_len.p;
     ctx->var.hom = ctx->d_vhom.p; ctx->var.danger = ctx->d_vdanger.p; ctx->var.filtered = ctx->d_vfiltered.p;
     ctx->is_ont = is_ont;
+    ctx->have_tag_variants = false;
+    if (v->hp1_is_alt && v->ps) {
+        TRY(h2d(ctx, ctx->d_vhp1_is_alt, v->hp1_is_alt, n));
+        TRY(h2d(ctx, ctx->d_vps, v->ps, n));
+        ctx->have_tag_variants = true;
+    }
     TRY(lps_launch_annotate(ctx));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_variants = true;
@@ -175,6 +194,7 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->h_name_rank.assign(b->name_rank, b->name_rank + n);
+    ctx->h_flag.assign(b->flag, b->flag + n);
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)(b->l_qseq[i] > 0 ? b->l_qseq[i] : 0);
     ctx->sum_l_qseq = s;
@@ -201,6 +221,7 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     d.cigar = b->cigar; d.cigar_len = b->cigar_len; d.seq4 = b->seq4; d.seq_bytes = b->seq_bytes;
     d.qual = b->qual; d.qual_bytes = b->qual_bytes;
     TRY(d2h(ctx, ctx->h_name_rank, b->name_rank, (size_t)b->n_reads));
+    TRY(d2h(ctx, ctx->h_flag, b->flag, (size_t)b->n_reads));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->sum_l_qseq = b->qual_bytes;
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
@@ -234,6 +255,67 @@ int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_hos
         }
     }
     ctx->stats.ms_wall_call_alleles = wt.ms();
+    return LPS_OK;
+}
+
+int lps_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_tag_result *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
+    if (!ctx->have_tag_variants) return ctx->fail(LPS_E_STATE, "the variant table lacks hp1_is_alt / ps (phased VCF fields)");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)ctx->batch.n_reads;
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_call_alleles(ctx, nullptr, p, want_calls));
+    cudaEventRecord(ctx->ev[3], st);
+    TRY(d2h(ctx, ctx->h_tag_cat, ctx->d_tag_cat.p, n));
+    TRY(d2h(ctx, ctx->h_tag_hp, ctx->d_tag_hp.p, n));
+    TRY(d2h(ctx, ctx->h_tag_ps, ctx->d_tag_ps.p, n));
+    TRY(d2h(ctx, ctx->h_tag_pq, ctx->d_tag_pq.p, n));
+    TRY(d2h(ctx, ctx->h_tag_h1, ctx->d_tag_h1.p, n));
+    TRY(d2h(ctx, ctx->h_tag_h2, ctx->d_tag_h2.p, n));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_tag_reads = elapsed(ctx, 2, 3);
+    ctx->have_calls = false; ctx->have_graph = false; ctx->host_calls_valid = false;
+    if (want_calls) {
+        TRY(d2h(ctx, ctx->h_call_off, ctx->d_call_off.p, n + 1));
+        TRY(d2h(ctx, ctx->h_calls, ctx->d_calls.p, (size_t)ctx->n_calls));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (out) memset(out, 0, sizeof(*out));
+    // ReadStatistics (HaplotagProcess.cpp:282-354) and the PQ values beyond the device table
+    lps_tag_result acc;
+    memset(&acc, 0, sizeof(acc));
+    for (size_t r = 0; r < n; r++) {
+        acc.total_alignment++;
+        const int cat = ctx->h_tag_cat[r];
+        if (cat == LPS_TAG_PROCESSED) {
+            if (ctx->h_flag[r] & 0x800) acc.total_supplementary++;
+            const int h1 = ctx->h_tag_h1[r], h2 = ctx->h_tag_h2[r];
+            const double mx = h1 > h2 ? h1 : h2, mn = h1 > h2 ? h2 : h1;
+            if (ctx->h_tag_pq[r] < 0) ctx->h_tag_pq[r] = -10 * (std::log10((double)mn / double(mx + mn)));
+            if (mx / (mx + mn) < p->percentage_threshold) acc.total_high_similarity++;
+            if (mx == 0) acc.total_without_variant++;
+            const int hp = ctx->h_tag_hp[r];
+            if (hp == 0) { acc.total_hp0++; acc.total_untag++; }
+            else { if (hp == 1) acc.total_hp1++; else acc.total_hp2++; acc.total_tag++; }
+        } else {
+            acc.total_untag++;
+            if (cat == LPS_TAG_LOW_MAPQ) acc.total_lower_quality++;
+            else if (cat == LPS_TAG_UNMAPPED) acc.total_unmapped++;
+            else if (cat == LPS_TAG_SECONDARY) acc.total_secondary++;
+            else if (cat == LPS_TAG_SUPPLEMENTARY) acc.total_supplementary++;
+            else if (cat == LPS_TAG_EMPTY_VARIANTS) acc.total_empty_variant++;
+            else acc.total_other_case++;
+        }
+    }
+    if (out) {
+        *out = acc;
+        out->n_reads = ctx->batch.n_reads;
+        out->category = ctx->h_tag_cat.data(); out->hp = ctx->h_tag_hp.data(); out->ps = ctx->h_tag_ps.data();
+        out->pq = ctx->h_tag_pq.data(); out->h1 = ctx->h_tag_h1.data(); out->h2 = ctx->h_tag_h2.data();
+        if (want_calls) { out->n_calls = ctx->n_calls; out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data(); }
+    }
     return LPS_OK;
 }
 

@@ -104,6 +104,10 @@ struct lps_ctx {
     std::vector<int32_t> h_vpos;
     std::vector<uint8_t> h_vhom, h_vdanger, h_vfiltered;
     DevVariants var;
+    DevBuf<uint8_t> d_vhp1_is_alt;
+    DevBuf<int32_t> d_vps;
+    bool have_tag_variants = false;
+    DevBuf<int8_t> d_pq_lut;
     bool have_variants = false;
     int is_ont = 0;
 
@@ -136,6 +140,15 @@ struct lps_ctx {
     std::vector<uint8_t> h_status;
     std::vector<int32_t> h_clip_pos, h_clip_front, h_clip_back;
     bool host_calls_valid = false;
+
+    // ---- haplotag ----
+    DevBuf<int8_t> d_tag_hp;
+    DevBuf<int32_t> d_tag_ps, d_tag_pq, d_tag_h1, d_tag_h2;
+    DevBuf<uint8_t> d_tag_cat;
+    std::vector<int8_t> h_tag_hp;
+    std::vector<int32_t> h_tag_ps, h_tag_pq, h_tag_h1, h_tag_h2;
+    std::vector<uint8_t> h_tag_cat;
+    std::vector<uint16_t> h_flag;
 
     // ---- graph ----
     std::vector<int32_t> h_aln_read;                // stage-C alignments (batch index), BAM order
@@ -189,7 +202,7 @@ struct lps_ctx {
 
 // kernels (k_*.cu)
 int lps_launch_annotate(lps_ctx *ctx);
-int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p);
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t = nullptr, int want_calls = 0);
 int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p);
 int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p);
 // host restatements that sit between the kernels (host_phase.cpp)

@@ -114,6 +114,18 @@ class Context:
         self._check(self.lib.lps_event_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
         return ms.value
 
+    # ---- haplotag ----
+    def tag_reads(self, tparams, want_calls=True):
+        o = _ffi.LpsTagResult()
+        self._check(self.lib.lps_tag_reads(self.h, C.byref(tparams), int(want_calls), C.byref(o)))
+        g = _ffi.as_np
+        n = o.n_reads
+        res = dict(category=g(o.category, n, np.uint8), hp=g(o.hp, n, np.int8), ps=g(o.ps, n, np.int32), pq=g(o.pq, n, np.int32),
+                   h1=g(o.h1, n, np.int32), h2=g(o.h2, n, np.int32), stats={k: getattr(o, k) for k in _ffi.TAG_COUNTERS})
+        if want_calls:
+            res.update(call_off=g(o.call_off, n + 1, np.uint64), calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE))
+        return res
+
     def stats(self):
         s = _ffi.LpsStats()
         self._check(self.lib.lps_get_stats(self.h, C.byref(s)))
@@ -157,3 +169,19 @@ class VairiantGraph:
             h = int(r["hap_ref"][i])
             out.append((int(contig.var_pos[i]), f"{h}|{1 - h}", int(r["ps"][i])))
         return out
+
+
+class GermlineHaplotagChrProcessor:
+    """Mirror of reference GermlineHaplotagChrProcessor (src/haplotag/HaplotagProcess.h:98-152): processSingleChrom's
+    dispatch plus processRead (judgeHaplotype -> HP/PS/PQ) for every alignment of one contig."""
+
+    def __init__(self, ctx, contig, tparams):
+        self.ctx, self.tparams = ctx, tparams
+        ctx.set_reference(contig.ref if tparams.have_reference else b"")
+        self._vs = contig.variants_struct()
+        ctx.set_variants(self._vs, 0)
+
+    def processSingleChrom(self, contig, want_calls=True):
+        self._bs = contig.batch_struct()
+        self.ctx.submit(self._bs)
+        return self.ctx.tag_reads(self.tparams, want_calls)

@@ -105,10 +105,33 @@ class Contig:
     # ---- views in the C ABI layout -------------------------------------------------------
     def variants_struct(self):
         P = _ffi.ptr
+        ps = getattr(self, "var_ps", None)
+        gt = getattr(self, "var_gt_kind", None)
         return _ffi.LpsVariants(n=self.n_var, pos=P(self.var_pos, _ffi.i32p), ref0=P(self.var_ref0, _ffi.u8p),
                                 alt0=P(self.var_alt0, _ffi.u8p), ref_len=P(self.var_ref_len, _ffi.u16p),
                                 alt_len=P(self.var_alt_len, _ffi.u16p), hp1_is_alt=P(self.var_hp1_is_alt, _ffi.u8p),
-                                ps=P(None, _ffi.i32p), gt_kind=P(None, _ffi.u8p))
+                                ps=P(ps, _ffi.i32p), gt_kind=P(gt, _ffi.u8p))
+
+    def phased(self, ps, hp1_is_alt=None):
+        """The contig as `haplotag` sees it after `phase`: only variants with a phase set (ps != 0) remain, each with
+        its PS and the haplotype that carries ALT (GT 1|0 -> hp1_is_alt).  Reads are shared with self."""
+        import copy
+        keep = np.nonzero(np.asarray(ps) != 0)[0]
+        c = copy.copy(self)
+        c.n_var = len(keep)
+        for k in ("var_pos", "var_ref0", "var_alt0", "var_ref_len", "var_alt_len"):
+            setattr(c, k, np.ascontiguousarray(getattr(self, k)[keep]))
+        h = self.var_hp1_is_alt if hp1_is_alt is None else np.asarray(hp1_is_alt)
+        c.var_hp1_is_alt = np.ascontiguousarray(h[keep].astype(np.uint8))
+        c.var_ps = np.ascontiguousarray(np.asarray(ps)[keep].astype(np.int32))
+        c.var_gt_kind = np.ones(len(keep), np.uint8)
+        blob, off = b"", [0]
+        for i in keep:
+            o, e = int(self.var_str_off[i]), int(self.var_str_off[i + 1])
+            blob += self.var_str[o:e]
+            off.append(len(blob))
+        c.var_str, c.var_str_off = blob, np.array(off, np.uint32)
+        return c
 
     def batch_struct(self):
         P = _ffi.ptr

@@ -85,6 +85,19 @@ typedef struct {
 int orc_solve(const lps_variants *v, const orc_graph *g, const lps_phase_params *p, orc_solution *out);
 void orc_solution_free(orc_solution *s);
 
+/* germline haplotag: dispatch + CigarParser::parsingCigar + GermlineHaplotagStrategy (see oracle_tag.c) */
+typedef struct {
+    int32_t n_reads;
+    uint8_t *category;
+    int8_t *hp;
+    int32_t *ps, *pq, *h1, *h2;
+    uint64_t n_calls;
+    uint64_t *call_off;
+    lps_call *calls;       /* variants that touched countPS: allele = variantsHP (0/1) or -1, origin 0 M-SNP, 1 D-SNP, 2 indel */
+} orc_tags;
+int orc_tag_reads(const lps_read_batch *b, const lps_variants *v, const uint8_t *hom, const lps_tag_params *p, orc_tags *out);
+void orc_tags_free(orc_tags *t);
+
 /* std::sort with the reference's comparator (src/shared/Util.h:100-106, Util.cpp:3-5): the order of
  * equal positions inside a merged read is whatever libstdc++'s introsort leaves, so the oracle calls
  * the same std::sort.  perm[] is permuted alongside pos[].                                        */

@@ -73,6 +73,24 @@ class TapOut(C.Structure):
                 ("t_read_correction", C.c_double)]
 
 
+class OrcTags(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("category", u8p), ("hp", i8p), ("ps", i32p), ("pq", i32p), ("h1", i32p), ("h2", i32p),
+                ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", callp)]
+
+
+class TapTagIn(C.Structure):
+    _fields_ = [("chr", C.c_char_p), ("ref", C.c_char_p), ("ref_len", C.c_int64), ("n_var", C.c_int32),
+                ("var_pos", i32p), ("var_str_off", _ffi.u32p), ("var_str", C.c_char_p), ("var_hp1_is_alt", u8p),
+                ("var_ps", i32p), ("batch", _ffi.LpsReadBatch), ("names", C.c_char_p), ("name_stride", C.c_int32),
+                ("p", _ffi.LpsTagParams)]
+
+
+class TapTagOut(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("category", u8p), ("hp", i32p), ("ps", i32p), ("pq", i32p), ("h1", i32p), ("h2", i32p),
+                ("n_ps", i32p), ("var_off", u64p), ("var_pos", i32p), ("var_hp", i32p), ("ps_off", u64p), ("ps_id", i32p),
+                ("ps_count", i32p), ("stats", C.c_int64 * 14), ("t_total", C.c_double)]
+
+
 _orc = None
 _tap = None
 
@@ -91,6 +109,9 @@ def oracle_lib():
         lib.orc_solve.argtypes = [C.POINTER(_ffi.LpsVariants), C.POINTER(OrcGraph), C.POINTER(_ffi.LpsPhaseParams),
                                   C.POINTER(OrcSolution)]
         lib.orc_solution_free.argtypes = [C.POINTER(OrcSolution)]
+        lib.orc_tag_reads.argtypes = [C.POINTER(_ffi.LpsReadBatch), C.POINTER(_ffi.LpsVariants), u8p, C.POINTER(_ffi.LpsTagParams),
+                                      C.POINTER(OrcTags)]
+        lib.orc_tags_free.argtypes = [C.POINTER(OrcTags)]
         _orc = lib
     return _orc
 
@@ -107,6 +128,9 @@ def tap_lib():
         lib.ref_tap_phase.restype = C.c_int
         lib.ref_tap_phase_free.argtypes = [C.POINTER(TapOut)]
         lib.ref_tap_homopolymer.argtypes = [C.c_char_p, C.c_int64, C.c_int]
+        lib.ref_tap_tag.argtypes = [C.POINTER(TapTagIn), C.POINTER(TapTagOut)]
+        lib.ref_tap_tag.restype = C.c_int
+        lib.ref_tap_tag_free.argtypes = [C.POINTER(TapTagOut)]
         _tap = lib
     return _tap
 
@@ -229,3 +253,49 @@ class ReferencePhase:
                 self.res_hap_ref, self.res_hap_alt = g(out.res_hap_ref, n, np.int32), g(out.res_hap_alt, n, np.int32)
         finally:
             lib.ref_tap_phase_free(C.byref(out))
+
+
+class OracleTag:
+    """Germline haplotag oracle on a phased synth.Contig (contig.phased(...))."""
+
+    def __init__(self, contig, tparams):
+        lib = oracle_lib()
+        self.notes = Notes(contig, False)
+        vs, bs = contig.variants_struct(), contig.batch_struct()
+        o = OrcTags()
+        self.rc = lib.orc_tag_reads(C.byref(bs), C.byref(vs), _ffi.ptr(self.notes.hom, u8p), C.byref(tparams), C.byref(o))
+        n = o.n_reads
+        self.category = g(o.category, n, np.uint8)
+        self.hp = g(o.hp, n, np.int8)
+        self.ps, self.pq = g(o.ps, n, np.int32), g(o.pq, n, np.int32)
+        self.h1, self.h2 = g(o.h1, n, np.int32), g(o.h2, n, np.int32)
+        self.call_off = g(o.call_off, n + 1, np.uint64)
+        self.calls = g(o.calls, o.n_calls, _ffi.CALL_DTYPE)
+        lib.orc_tags_free(C.byref(o))
+
+
+class ReferenceTag:
+    """The UNMODIFIED reference's germline haplotag objects on a phased synth.Contig (oracle/ref_tap_tag.cpp)."""
+
+    def __init__(self, contig, tparams, chr_name="chrS"):
+        lib = tap_lib()
+        tin = TapTagIn(chr=chr_name.encode(), ref=contig.ref, ref_len=len(contig.ref), n_var=contig.n_var,
+                       var_pos=_ffi.ptr(contig.var_pos, i32p), var_str_off=_ffi.ptr(contig.var_str_off, _ffi.u32p),
+                       var_str=contig.var_str, var_hp1_is_alt=_ffi.ptr(contig.var_hp1_is_alt, u8p),
+                       var_ps=_ffi.ptr(contig.var_ps, i32p), batch=contig.batch_struct(), names=contig.names,
+                       name_stride=contig.NAME_STRIDE, p=tparams)
+        out = TapTagOut()
+        self.rc = lib.ref_tap_tag(C.byref(tin), C.byref(out))
+        n = out.n_reads
+        self.category = g(out.category, n, np.uint8)
+        for k in ("hp", "ps", "pq", "h1", "h2", "n_ps"):
+            setattr(self, k, g(getattr(out, k), n, np.int32))
+        self.var_off = g(out.var_off, n + 1, np.uint64)
+        m = int(self.var_off[-1]) if n else 0
+        self.var_pos, self.var_hp = g(out.var_pos, m, np.int32), g(out.var_hp, m, np.int32)
+        self.ps_off = g(out.ps_off, n + 1, np.uint64)
+        m = int(self.ps_off[-1]) if n else 0
+        self.ps_id, self.ps_count = g(out.ps_id, m, np.int32), g(out.ps_count, m, np.int32)
+        self.stats = dict(zip(_ffi.TAG_COUNTERS, list(out.stats)))
+        self.t_total = out.t_total
+        lib.ref_tap_tag_free(C.byref(out))

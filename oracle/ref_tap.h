@@ -62,6 +62,38 @@ typedef struct {
     double t_get_snp, t_filter_snp, t_clip, t_add_edge, t_sweep, t_read_correction;
 } tap_phase_out;
 
+/* ---- germline haplotag tap (ref_tap_tag.cpp) ---- */
+typedef struct {
+    const char *chr;
+    const char *ref;
+    int64_t ref_len;
+    int32_t n_var;
+    const int32_t *var_pos;
+    const uint32_t *var_str_off;
+    const char *var_str;
+    const uint8_t *var_hp1_is_alt;
+    const int32_t *var_ps;
+    lps_read_batch batch;
+    const char *names;
+    int32_t name_stride;
+    lps_tag_params p;
+} tap_tag_in;
+
+typedef struct {
+    int32_t n_reads;
+    uint8_t *category;
+    int32_t *hp, *ps, *pq, *h1, *h2, *n_ps;   /* per read: judgeHaplotype result and hpCount / countPS.size() */
+    uint64_t *var_off;                        /* per read CSR over variantsHP: (position, 0|1) */
+    int32_t *var_pos, *var_hp;
+    uint64_t *ps_off;                         /* per read CSR over countPS: (PS id, count) */
+    int32_t *ps_id, *ps_count;
+    int64_t stats[14];                        /* ReadStatistics in the order of lps_tag_result's counters */
+    double t_total;
+} tap_tag_out;
+
+int ref_tap_tag(const tap_tag_in *in, tap_tag_out *out);
+void ref_tap_tag_free(tap_tag_out *out);
+
 int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out);
 void ref_tap_phase_free(tap_phase_out *out);
 int ref_tap_homopolymer(const char *ref, int64_t len, int pos);

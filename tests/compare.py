@@ -56,3 +56,36 @@ def name_level_hp(read_hp, aln_read, name_rank):
     for hp, r in zip(read_hp, aln_read):
         last[int(name_rank[r])] = int(hp)
     return np.array([last[int(name_rank[r])] for r in aln_read], np.int32)
+
+
+def well_formed_reads(contig):
+    """Reads whose SEQ covers the query span of their CIGAR.  For the others (SEQ '*', l_qseq = 0) the reference's
+    tag-family parser reads bases past the end of SEQ without a bounds check (HaplotagParsingBam.cpp:595-596), which is
+    undefined; they are excluded from tag-family comparisons with the reference."""
+    ok = np.ones(contig.n_reads, bool)
+    consumes_q = np.array([1, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0], bool)
+    for r in range(contig.n_reads):
+        c = contig.cigar[int(contig.cigar_off[r]):int(contig.cigar_off[r]) + int(contig.n_cigar[r])]
+        qlen = int((c >> 4)[consumes_q[c & 15]].sum())
+        ok[r] = qlen <= int(contig.l_qseq[r])
+    return ok
+
+
+def assert_tag_matches_reference(orc, ref, contig):
+    """orc: po.OracleTag (or anything with the same fields), ref: po.ReferenceTag."""
+    ok = well_formed_reads(contig)
+    assert np.array_equal(orc.category, ref.category), "dispatch categories differ"
+    for k in ("hp", "ps", "pq", "h1", "h2"):
+        a, b = np.asarray(getattr(orc, k)).astype(np.int64), np.asarray(getattr(ref, k)).astype(np.int64)
+        bad = np.nonzero((a != b) & ok)[0]
+        assert len(bad) == 0, f"{k} differs at reads {bad[:5]}: {a[bad[:5]]} vs {b[bad[:5]]}"
+    off = orc.call_off.astype(np.int64)
+    for r in np.nonzero(ok)[0]:
+        oc = orc.calls[off[r]:off[r + 1]]
+        sel = oc["allele"] >= 0
+        s = slice(int(ref.var_off[r]), int(ref.var_off[r + 1]))
+        assert np.array_equal(contig.var_pos[oc["var"][sel]], ref.var_pos[s]) and np.array_equal(oc["allele"][sel].astype(np.int32), ref.var_hp[s]), f"variantsHP of read {r}"
+        s = slice(int(ref.ps_off[r]), int(ref.ps_off[r + 1]))
+        u, cnt = np.unique(contig.var_ps[oc["var"]], return_counts=True)
+        assert np.array_equal(u, ref.ps_id[s]) and np.array_equal(cnt, ref.ps_count[s]), f"countPS of read {r}"
+    return int(ok.sum())
