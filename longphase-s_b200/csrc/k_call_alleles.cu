@@ -26,7 +26,7 @@
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int CAND_CAP = 128;        // candidates buffered per warp in shared memory
+constexpr int CAND_CAP = 256;        // candidates buffered per warp in shared memory
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t PAD_OP = 1u;     // zero-length insertion: advances nothing
 
@@ -64,6 +64,7 @@ struct K1Args {
     int mapq_filter;                  // ParsingBamControl::mappingQualityFilter
     int tag_supplementary;            // ParsingBamConfig::tagSupplementary
     int want_calls;                   // also emit the per-read (variant, haplotype) list
+    int count_gathers;                // SEQ/QUAL live in pinned host memory: count the gathered sectors
     double percentage;                // ParsingBamConfig::percentageThreshold
     const int8_t *pq_lut;             // [256][256] PQ by (min, max), built on the host with the host libm
     int8_t *tag_hp;                   // ReadHP: 0 unTag, 1 H1, 2 H2
@@ -138,7 +139,7 @@ struct WarpScratch {
 };
 
 template <int K, bool TAG>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a) {
     __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
             const bool edge = (cb + 2 * CH > hi) || ((uint64_t)(cb + 2 * CH) > total);
             load_ops<K>(cig, total, cb + CH + (int64_t)lane * K, lo, hi, edge, nxt_ops);
         }
-        // ---- per-lane advances ----
+        // ---- per-lane advances; rl/ql = lane-local position of each op start ----
+        int rl[K], ql[K];
         int rs = 0, qs = 0;
         unsigned rare = 0;
 #pragma unroll
@@ -222,35 +224,50 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
             const unsigned c = ops[j];
             const unsigned t = ADV_LUT >> ((c << 1) & 30u);
             const int len = (int)(c >> 4);
-            rs += (t & 1u) ? len : 0;
-            qs += (t & 2u) ? len : 0;
-            rare |= RARE_OPS >> (c & 15u);
+            rl[j] = rs; ql[j] = qs;
+            rs += (int)(t & 1u) * len;
+            qs += (int)((t >> 1) & 1u) * len;
+            rare |= c;                                // op code bits 2..3 set <=> some op code >= 4 (S H P = X or unsupported)
         }
         const int rtot = (int)__reduce_add_sync(FULL, (unsigned)rs);
+        const int qtot = (int)__reduce_add_sync(FULL, (unsigned)qs);
         const int chunk_end = ref_pos + rtot;
         int abort_op = INT_MAX;
 
         // ---- variants inside this chunk: every lane takes the variant in its own window slot ----
         int first_pending = __shfl_sync(FULL, vwin, cur - win_base);
         if (first_pending < chunk_end) {
-            // exclusive scans of both cursors, then publish the per-op start positions
-            int ri = rs, qi = qs;
+            // exclusive scan of both cursors (one packed scan when both chunk totals fit 16 bits), then publish the
+            // per-op start positions with 128-bit shared stores
+            int r0, q0;
+            if (((unsigned)rtot | (unsigned)qtot) < 65536u) {
+                unsigned pk = (unsigned)rs | ((unsigned)qs << 16);
+                unsigned inc = pk;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(FULL, ri, d);
-                int u = __shfl_up_sync(FULL, qi, d);
-                if (lane >= d) { ri += t; qi += u; }
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned t = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                const unsigned exc = inc - pk;
+                r0 = ref_pos + (int)(exc & 0xffffu); q0 = qpos + (int)(exc >> 16);
+            } else {
+                int ri = rs, qi = qs;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(FULL, ri, d);
+                    int u = __shfl_up_sync(FULL, qi, d);
+                    if (lane >= d) { ri += t; qi += u; }
+                }
+                r0 = ref_pos + ri - rs; q0 = qpos + qi - qs;
             }
             {
-                int rr = ref_pos + ri - rs, qq = qpos + qi - qs;
+                int4 *dr = reinterpret_cast<int4 *>(S.r + lane * K), *dq = reinterpret_cast<int4 *>(S.q + lane * K);
+                uint4 *dop = reinterpret_cast<uint4 *>(S.op + lane * K);
 #pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const unsigned c = ops[j];
-                    const unsigned t = ADV_LUT >> ((c << 1) & 30u);
-                    const int len = (int)(c >> 4);
-                    S.r[lane * K + j] = rr; S.q[lane * K + j] = qq; S.op[lane * K + j] = c;
-                    rr += (t & 1u) ? len : 0;
-                    qq += (t & 2u) ? len : 0;
+                for (int j = 0; j < K; j += 4) {
+                    dr[j / 4] = make_int4(r0 + rl[j], r0 + rl[j + 1], r0 + rl[j + 2], r0 + rl[j + 3]);
+                    dq[j / 4] = make_int4(q0 + ql[j], q0 + ql[j + 1], q0 + ql[j + 2], q0 + ql[j + 3]);
+                    dop[j / 4] = make_uint4(ops[j], ops[j + 1], ops[j + 2], ops[j + 3]);
                 }
             }
             __syncwarp();
@@ -386,7 +403,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
         }
 
         // ---- clips (S/H longer than 5) and unsupported ops ----
-        if (__any_sync(FULL, (rare & 1u) != 0)) {
+        if (__any_sync(FULL, (rare & 0xCu) != 0)) {
             int ri = rs;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -409,7 +426,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
         }
         if (aborted) break;
         ref_pos = chunk_end;
-        qpos += (int)__reduce_add_sync(FULL, (unsigned)qs);
+        qpos += qtot;
     }
     bad = __any_sync(FULL, bad);
     if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar, 1u);
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
     if (TAG) {
         // ---- resolve: per candidate the haplotype bit and the "counts towards countPS" flag, then judgeReadHap ----
         const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
-        int h1 = 0, h2 = 0, ps_min = INT_MAX, ps_max = INT_MIN, nout = 0;
+        int h1 = 0, h2 = 0, ps_min = INT_MAX, ps_max = INT_MIN, nout = 0, ngather = 0;
         for (int c0 = 0; c0 < ncand; c0 += 32) {
             const int c = c0 + lane;
             int hpbit = -1; bool ps_counted = false; int var = -1; unsigned kind = 0;
@@ -442,6 +459,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                 kind = cd.x >> 30; var = cd.var;
                 if (kind == 2) { ps_counted = true; if (cd.x & 2u) hpbit = (int)(cd.x & 1u); }
                 else {
+                    ngather++;
                     const int qi = (int)(cd.x & 0x3fffffffu);
                     const unsigned code = (seq[qi >> 1] >> ((~qi & 1) << 2)) & 0xfu;
                     const char base = "=ACMGRSVTWYHKDBN"[code];
@@ -472,6 +490,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                 nout += __popc(m);
                 __syncwarp();
             }
+        }
+        if (a.count_gathers) {
+            ngather = (int)__reduce_add_sync(FULL, (unsigned)ngather);
+            if (lane == 0 && ngather) atomicAdd(&a.counters->gathers, (unsigned long long)ngather);
         }
         h1 = (int)__reduce_add_sync(FULL, (unsigned)h1);
         h2 = (int)__reduce_add_sync(FULL, (unsigned)h2);
@@ -510,7 +532,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
     // ---- resolve candidates: gather base + quality, decide the allele, drop filterSNP variants ----
     const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
     const uint8_t *__restrict__ qual = a.b.qual + a.b.qual_off[r];
-    int nvalid = 0;
+    int nvalid = 0, ngather = 0;
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         const int c = c0 + lane;
         bool valid = false;
@@ -526,6 +548,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
                 out.quality = (cd.x & 1u) ? -5 : -4;
                 valid = true;
             } else {
+                ngather++;
                 const int qi = (int)(cd.x & 0x3fffffffu);
                 const unsigned byte = seq[qi >> 1];
                 const unsigned code = (byte >> ((~qi & 1) << 2)) & 0xfu;            // bam_seqi
@@ -550,6 +573,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_call_alleles(K1Args a
         }
         nvalid += __popc(m);
         __syncwarp();
+    }
+    if (a.count_gathers) {
+        ngather = (int)__reduce_add_sync(FULL, (unsigned)ngather);
+        if (lane == 0 && ngather) atomicAdd(&a.counters->gathers, (unsigned long long)ngather);
     }
     unsigned long long start = 0;
     if (lane == 0 && nvalid) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nvalid);
@@ -641,6 +668,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
         a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap;
         a.counters = ctx->d_counters.p;
+        a.count_gathers = ctx->zero_copy ? 1 : 0;
         a.overflow_list_out = ctx->d_overflow_reads.p; a.overflow_need_out = ctx->d_overflow_cand.p;
         a.overflow_list_cap = ovf_cap;
         const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -654,6 +682,8 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
         if (grid > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_call_alleles, ctx->kev[0], ctx->kev[1]);
+        // zero-copy accounting: one 32-byte sector of SEQ (phase: and one of QUAL) crosses PCIe per gathered candidate
+        if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers * (tag ? 32ull : 64ull);
         if (hc.bad_cigar) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
         if (hc.overflow_reads > ovf_cap) return ctx->fail(LPS_E_NOMEM, "too many reads overflow the candidate buffer");
         if (hc.overflow_reads) {

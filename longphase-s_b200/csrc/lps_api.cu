@@ -190,8 +190,27 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_mapq, b->mapq, n));
     TRY(h2d(ctx, ctx->d_name_rank, b->name_rank, n));
     TRY(h2d(ctx, ctx->d_cigar, b->cigar, (size_t)b->cigar_len, 64));
-    TRY(h2d(ctx, ctx->d_seq4, b->seq4, (size_t)b->seq_bytes, 16));
-    TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
+    // SEQ and QUAL are 85 % of a batch but the kernels touch ~2 bytes per allele call of them.  When the caller's
+    // buffers are pinned (cudaHostAlloc / cudaHostRegister) they stay on the host and the resolve phase of the kernel
+    // gathers the few sectors it needs straight over PCIe (UVA zero-copy); pageable buffers are copied as before.
+    const uint8_t *seq_dev = nullptr, *qual_dev = nullptr;
+    bool zero_copy = false;
+    {
+        const char *env = getenv("LPS_ZERO_COPY");
+        cudaPointerAttributes as, aq;
+        if (!(env && env[0] == '0') && b->seq_bytes && b->qual_bytes &&
+            cudaPointerGetAttributes(&as, b->seq4) == cudaSuccess && cudaPointerGetAttributes(&aq, b->qual) == cudaSuccess &&
+            as.type == cudaMemoryTypeHost && aq.type == cudaMemoryTypeHost && as.devicePointer && aq.devicePointer) {
+            seq_dev = (const uint8_t *)as.devicePointer; qual_dev = (const uint8_t *)aq.devicePointer; zero_copy = true;
+        }
+        cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers
+    }
+    if (!zero_copy) {
+        TRY(h2d(ctx, ctx->d_seq4, b->seq4, (size_t)b->seq_bytes, 16));
+        TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
+        seq_dev = ctx->d_seq4.p; qual_dev = ctx->d_qual.p;
+    }
+    ctx->zero_copy = zero_copy;
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->h_name_rank.assign(b->name_rank, b->name_rank + n);
     ctx->h_flag.assign(b->flag, b->flag + n);
@@ -203,8 +222,8 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     d.ref_start = ctx->d_ref_start.p; d.l_qseq = ctx->d_l_qseq.p; d.n_cigar = ctx->d_n_cigar.p;
     d.cigar_off = ctx->d_cigar_off.p; d.seq_off = ctx->d_seq_off.p; d.qual_off = ctx->d_qual_off.p;
     d.flag = ctx->d_flag.p; d.mapq = ctx->d_mapq.p; d.name_rank = ctx->d_name_rank.p;
-    d.cigar = ctx->d_cigar.p; d.cigar_len = b->cigar_len; d.seq4 = ctx->d_seq4.p; d.seq_bytes = b->seq_bytes;
-    d.qual = ctx->d_qual.p; d.qual_bytes = b->qual_bytes;
+    d.cigar = ctx->d_cigar.p; d.cigar_len = b->cigar_len; d.seq4 = seq_dev; d.seq_bytes = b->seq_bytes;
+    d.qual = qual_dev; d.qual_bytes = b->qual_bytes;
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.ms_h2d = elapsed(ctx, 0, 1);
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;

@@ -81,6 +81,7 @@ struct CallCounters {
     unsigned long long tmp_calls;      // slots requested in the scratch call pool
     unsigned long long clips;          // clip events appended
     unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
+    unsigned long long gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
     unsigned int overflow_reads;
     unsigned int bad_cigar;            // reads with an unsupported CIGAR op
 };
@@ -121,6 +122,7 @@ struct lps_ctx {
     std::vector<int32_t> h_name_rank;
     uint64_t sum_l_qseq = 0;
     bool have_batch = false;
+    bool zero_copy = false;                         // SEQ/QUAL stayed in pinned host memory (gathered over PCIe)
 
     // ---- allele calls ----
     DevBuf<lps_call> d_calls_tmp, d_calls;          // scratch pool (allocation order) and final CSR
