@@ -224,14 +224,14 @@ def main():
         return float(t.item())
 
     def step_resident():
-        ctx.submit_device(dev_batch)
-        return ctx.phase_contig(params)
+        return ctx.phase_contig(params)      # the batch was registered once with lps_batch_submit_device (no copy)
 
     def step_e2e():
         ctx.submit(pin_batch)
         return ctx.phase_contig(params)
 
     # ---- kernel-resident leg ----
+    ctx.submit_device(dev_batch)
     for _ in range(args.warmup):
         res = step_resident()
     sampler = ClockSampler(local_rank)

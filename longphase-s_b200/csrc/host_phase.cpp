@@ -16,37 +16,48 @@
 #include "lps_ctx.cuh"
 
 // --------------------------------------------------------------------------------------------
-// overlap filter.  Works on alignments that produced >= 1 call (after filterSNP); only names that
-// own more than one such alignment can be affected, so the state machine runs on those alone.
-// Sets ctx->h_read_dead.
+// overlap filter.  Only read names that own more than one alignment in the batch can be affected, so the
+// batch is indexed once at submit time (lps_host_index_names) and the state machine runs on those groups
+// alone, on (first called position, last called position, #calls) of just their alignments.
 // --------------------------------------------------------------------------------------------
-int lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
-                            const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls) {
-    const int n = (int)ncalls.size();
-    ctx->h_read_dead.assign((size_t)n, 0);
+void lps_host_index_names(lps_ctx *ctx) {
     const std::vector<int32_t> &rank = ctx->h_name_rank;
+    const int n = (int)rank.size();
+    ctx->h_multi_members.clear(); ctx->h_multi_group_off.assign(1, 0);
     int max_rank = -1;
-    for (int r = 0; r < n; r++) if (ncalls[r] && rank[r] > max_rank) max_rank = rank[r];
-    if (max_rank < 0) return LPS_OK;
-    // bucket the alignments with calls by name rank, BAM order preserved inside a bucket
-    std::vector<int32_t> bucket_off((size_t)max_rank + 2, 0);
-    for (int r = 0; r < n; r++) if (ncalls[r]) bucket_off[(size_t)rank[r] + 1]++;
-    for (int k = 0; k <= max_rank; k++) bucket_off[(size_t)k + 1] += bucket_off[(size_t)k];
-    std::vector<int32_t> members((size_t)bucket_off[(size_t)max_rank + 1]);
-    {
-        std::vector<int32_t> cursor(bucket_off.begin(), bucket_off.end() - 1);
-        for (int r = 0; r < n; r++) if (ncalls[r]) members[(size_t)cursor[(size_t)rank[r]]++] = r;
+    for (int r = 0; r < n; r++) if (rank[r] > max_rank) max_rank = rank[r];
+    if (max_rank < 0) return;
+    std::vector<int32_t> count((size_t)max_rank + 1, 0);
+    for (int r = 0; r < n; r++) count[(size_t)rank[r]]++;
+    // slot of every multi-alignment name, in order of first appearance; members keep BAM order
+    std::vector<int32_t> slot((size_t)max_rank + 1, -1);
+    std::vector<std::vector<int32_t>> groups;
+    for (int r = 0; r < n; r++) {
+        const int k = rank[r];
+        if (count[(size_t)k] < 2) continue;
+        if (slot[(size_t)k] < 0) { slot[(size_t)k] = (int32_t)groups.size(); groups.emplace_back(); }
+        groups[(size_t)slot[(size_t)k]].push_back(r);
     }
-    std::vector<int32_t> kept;   // readIdxVec[name]
-    for (int k = 0; k <= max_rank; k++) {
-        const int b0 = bucket_off[(size_t)k], b1 = bucket_off[(size_t)k + 1];
-        if (b1 - b0 < 2) continue;
+    for (const auto &g : groups) {
+        ctx->h_multi_members.insert(ctx->h_multi_members.end(), g.begin(), g.end());
+        ctx->h_multi_group_off.push_back((int32_t)ctx->h_multi_members.size());
+    }
+}
+
+// first_pos / last_pos / ncalls are indexed like ctx->h_multi_members; returns the batch indices of deleted alignments
+void lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
+                             const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls, std::vector<int32_t> &dead) {
+    dead.clear();
+    std::vector<int32_t> kept;   // readIdxVec[name] (indices into the member arrays)
+    const size_t ngroups = ctx->h_multi_group_off.size() - 1;
+    for (size_t g = 0; g < ngroups; g++) {
+        const int b0 = ctx->h_multi_group_off[g], b1 = ctx->h_multi_group_off[g + 1];
         kept.clear();
         // alignRange[name]: inserted as {0,0} before the find(), so .first is always 0 (:712-716)
         int range_end = 0;
         for (int m = b0; m < b1; m++) {
-            const int cur = members[(size_t)m];
-            const int first = first_pos[(size_t)cur], last = last_pos[(size_t)cur];
+            if (!ncalls[(size_t)m]) continue;   // alignments without calls never reach addEdge
+            const int first = first_pos[(size_t)m], last = last_pos[(size_t)m];
             bool drop_cur = false;
             while (0 <= first && first <= range_end) {
                 if (last < range_end) { drop_cur = true; break; }
@@ -60,17 +71,16 @@ int lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::
                 if (ov_len / span >= p->overlap_threshold) {
                     const int len_prev = prev_end - prev_start + 1, len_cur = last - first + 1;
                     if (len_cur <= len_prev) { drop_cur = true; break; }
-                    ctx->h_read_dead[(size_t)prev] = 1;
+                    dead.push_back(ctx->h_multi_members[(size_t)prev]);
                     kept.pop_back();
                     range_end = kept.empty() ? first : last_pos[(size_t)kept.back()];
                 } else break;
             }
             range_end = last;
-            if (drop_cur) ctx->h_read_dead[(size_t)cur] = 1;
-            else kept.push_back(cur);
+            if (drop_cur) dead.push_back(ctx->h_multi_members[(size_t)m]);
+            else kept.push_back(m);
         }
     }
-    return LPS_OK;
 }
 
 // --------------------------------------------------------------------------------------------

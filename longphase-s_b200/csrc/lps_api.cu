@@ -19,14 +19,22 @@ template <typename T> int d2h(lps_ctx *ctx, std::vector<T> &dst, const T *src, s
 }
 #define TRY(x) do { int rc__ = (x); if (rc__ != LPS_OK) return rc__; } while (0)
 
-// first / last called position of every read (what the overlap filter looks at)
-__global__ void k_first_last(int n, const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
-                             const int32_t *__restrict__ vpos, int32_t *__restrict__ first_pos, int32_t *__restrict__ last_pos) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
+// first / last called position of the listed reads (what the overlap filter looks at)
+__global__ void k_first_last(int m, const int32_t *__restrict__ reads, const uint64_t *__restrict__ call_off,
+                             const lps_call *__restrict__ calls, const int32_t *__restrict__ vpos, int32_t *__restrict__ first_pos,
+                             int32_t *__restrict__ last_pos, uint32_t *__restrict__ ncalls) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int r = reads[i];
     uint64_t c0 = call_off[r], c1 = call_off[r + 1];
-    first_pos[r] = c1 > c0 ? vpos[calls[c0].var] : -1;
-    last_pos[r] = c1 > c0 ? vpos[calls[c1 - 1].var] : -1;
+    first_pos[i] = c1 > c0 ? vpos[calls[c0].var] : -1;
+    last_pos[i] = c1 > c0 ? vpos[calls[c1 - 1].var] : -1;
+    ncalls[i] = (uint32_t)(c1 - c0);
+}
+
+__global__ void k_mark_dead(int m, const int32_t *__restrict__ reads, uint8_t *__restrict__ dead) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) dead[reads[i]] = 1;
 }
 
 int fetch_host_calls(lps_ctx *ctx) {
@@ -214,6 +222,8 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     cudaEventRecord(ctx->ev[1], ctx->stream);
     ctx->h_name_rank.assign(b->name_rank, b->name_rank + n);
     ctx->h_flag.assign(b->flag, b->flag + n);
+    lps_host_index_names(ctx);
+    TRY(h2d(ctx, ctx->d_multi_members, ctx->h_multi_members.data(), ctx->h_multi_members.size()));
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)(b->l_qseq[i] > 0 ? b->l_qseq[i] : 0);
     ctx->sum_l_qseq = s;
@@ -242,6 +252,8 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(d2h(ctx, ctx->h_name_rank, b->name_rank, (size_t)b->n_reads));
     TRY(d2h(ctx, ctx->h_flag, b->flag, (size_t)b->n_reads));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lps_host_index_names(ctx);
+    TRY(h2d(ctx, ctx->d_multi_members, ctx->h_multi_members.data(), ctx->h_multi_members.size()));
     ctx->sum_l_qseq = b->qual_bytes;
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
     return LPS_OK;
@@ -346,24 +358,33 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
     cudaStream_t st = ctx->stream;
     WallTimer wt;
     // ---- host filters at the head of addEdge (PhasingGraph.cpp:707-791) ----
-    std::vector<int32_t> first_pos, last_pos;
+    std::vector<int32_t> first_pos, last_pos, dead;
     std::vector<uint32_t> ncalls;
-    {
+    const int m = (int)ctx->h_multi_members.size();
+    LPS_CUDA(ctx, ctx->d_read_dead.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_read_dead.p, 0, (size_t)n + 1, st));
+    WallTimer wf;
+    ctx->h_read_dead.assign((size_t)n, 0);
+    if (m > 0) {
         DevBuf<int32_t> &d_first = ctx->d_first_pos, &d_last = ctx->d_last_pos;
-        LPS_CUDA(ctx, d_first.reserve((size_t)n + 1));
-        LPS_CUDA(ctx, d_last.reserve((size_t)n + 1));
-        if (n > 0) {
-            k_first_last<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->d_call_off.p, ctx->d_calls.p, ctx->var.pos, d_first.p, d_last.p);
+        LPS_CUDA(ctx, d_first.reserve((size_t)m + 1));
+        LPS_CUDA(ctx, d_last.reserve((size_t)m + 1));
+        LPS_CUDA(ctx, ctx->d_multi_ncalls.reserve((size_t)m + 1));
+        k_first_last<<<(m + 255) / 256, 256, 0, st>>>(m, ctx->d_multi_members.p, ctx->d_call_off.p, ctx->d_calls.p, ctx->var.pos,
+                                                      d_first.p, d_last.p, ctx->d_multi_ncalls.p);
+        ctx->stats.kernel_launches++;
+        TRY(d2h(ctx, first_pos, d_first.p, (size_t)m));
+        TRY(d2h(ctx, last_pos, d_last.p, (size_t)m));
+        TRY(d2h(ctx, ncalls, ctx->d_multi_ncalls.p, (size_t)m));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls, dead);
+        if (!dead.empty()) {
+            for (int32_t r : dead) ctx->h_read_dead[(size_t)r] = 1;
+            TRY(h2d(ctx, ctx->d_dead_list, dead.data(), dead.size()));
+            k_mark_dead<<<((int)dead.size() + 255) / 256, 256, 0, st>>>((int)dead.size(), ctx->d_dead_list.p, ctx->d_read_dead.p);
             ctx->stats.kernel_launches++;
         }
-        TRY(d2h(ctx, first_pos, d_first.p, (size_t)n));
-        TRY(d2h(ctx, last_pos, d_last.p, (size_t)n));
-        TRY(d2h(ctx, ncalls, ctx->d_ncalls.p, (size_t)n));
-        LPS_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    WallTimer wf;
-    TRY(lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls));
-    TRY(h2d(ctx, ctx->d_read_dead, ctx->h_read_dead.data(), (size_t)n));
     ctx->h_cnv_start.clear(); ctx->h_cnv_end.clear();
     lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
     lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
@@ -379,8 +400,6 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
             ctx->have_erased = true;
         }
     }
-    ctx->h_aln_read.clear();
-    for (int r = 0; r < n; r++) if (ncalls[(size_t)r] && !ctx->h_read_dead[(size_t)r]) ctx->h_aln_read.push_back(r);
     ctx->stats.ms_host_filters = wf.ms();
     // ---- device: merge by name, fan out, ordered fold ----
     cudaEventRecord(ctx->ev[2], st);

@@ -120,6 +120,9 @@ struct lps_ctx {
     DevBuf<uint8_t> d_mapq, d_seq4, d_qual;
     DevBatch batch;
     std::vector<int32_t> h_name_rank;
+    std::vector<int32_t> h_multi_members, h_multi_group_off;   // alignments of names that occur more than once, grouped by name
+    DevBuf<int32_t> d_multi_members, d_dead_list;
+    DevBuf<uint32_t> d_multi_ncalls;
     uint64_t sum_l_qseq = 0;
     bool have_batch = false;
     bool zero_copy = false;                         // SEQ/QUAL stayed in pinned host memory (gathered over PCIe)
@@ -208,8 +211,9 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
 int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p);
 int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p);
 // host restatements that sit between the kernels (host_phase.cpp)
-int lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
-                            const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls);
+void lps_host_index_names(lps_ctx *ctx);
+void lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
+                             const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls, std::vector<int32_t> &dead);
 void lps_host_cnv_intervals(const std::vector<int32_t> &pos, const std::vector<int32_t> &front,
                             const std::vector<int32_t> &back, std::vector<int32_t> &cs, std::vector<int32_t> &ce);
 int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);
