@@ -224,16 +224,114 @@ typedef struct {
  * (HaplotagStrategy.cpp:20-300).  The variant table must carry hp1_is_alt and ps (lps_contig_set_variants). */
 int lps_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_tag_result *out);
 
+/* ---- somatic family: union variant map, the two extract passes, somatic tagging ------------------------------ */
+/* TUMOR side of the union map std::map<int, MultiGenomeVar> (src/haplotag/HaplotagType.h:146-162).  All arrays are
+ * parallel to the table given to lps_contig_set_variants (same n, same ascending positions), which carries the NORMAL
+ * records; a position may hold a NORMAL record, a TUMOR record, or both.  Tumor-present positions are numbered
+ * 0..n_tum-1 in ascending order ("tumor slots"); every per-position product of this family is indexed by slot.     */
+typedef struct {
+    int32_t n;
+    const uint8_t *nor_present;   /* MultiGenomeVar::isExists(NORMAL); NULL = present everywhere                 */
+    const uint8_t *tum_present;   /* MultiGenomeVar::isExists(TUMOR)                                             */
+    const uint8_t *ref0, *alt0;   /* first characters of the tumor record's REF / ALT                            */
+    const uint16_t *ref_len, *alt_len;
+    const uint8_t *gt_kind;       /* GenomeType of the tumor record (1 phased het, 2 unphased het, 3 unphased hom) */
+    const uint8_t *hp1_is_alt;    /* phased tumor records only (unused by the passes below, kept for the logs)   */
+    const int32_t *ps;            /* PhasedSet of a phased tumor record (must not be -1, HaplotagStrategy.cpp:337) */
+    const uint8_t *is_somatic;    /* MultiGenomeVar::isSomaticVariant (set by SomaticVarCaller::getSomaticFlag)  */
+    const int8_t *derive_hp;      /* MultiGenomeVar::somaticReadDeriveByHP: 0 none, 1 GERMLINE_H1, 2 GERMLINE_H2 */
+} lps_tumor_variants;
+int lps_contig_set_tumor_variants(lps_ctx *ctx, const lps_tumor_variants *t);
+
+/* PosBase counters (src/haplotag/HaplotagType.h:165-224), in this order                                          */
+enum { LPS_PB_ALT = 0, LPS_PB_A, LPS_PB_C, LPS_PB_G, LPS_PB_T, LPS_PB_UNKNOWN, LPS_PB_DEPTH, LPS_PB_DEL,
+       LPS_PB_MPQ_ALT, LPS_PB_MPQ_A, LPS_PB_MPQ_C, LPS_PB_MPQ_G, LPS_PB_MPQ_T, LPS_PB_MPQ_UNKNOWN, LPS_PB_MPQ_DEPTH,
+       LPS_PB_FIELDS };
+/* read-case counters of SomaticData (HaplotagType.h:226-233), filled by classifyReadsByCase                      */
+enum { LPS_CASE_CLEAN_HP3 = 0, LPS_CASE_PURE_H1_1, LPS_CASE_PURE_H2_1, LPS_CASE_PURE_H3, LPS_CASE_MIXED, LPS_CASE_UNTAG,
+       LPS_CASE_FIELDS };
+enum { LPS_READHP_FIELDS = 9 };   /* ReadHP: unTag 0, H1, H2, H3, H4, H1_1, H1_2, H2_1, H2_2 (HaplotagType.h:97-108)  */
+enum { LPS_WINDOW = 100, LPS_WINDOW_BINS = 2 * LPS_WINDOW + 1 };   /* getWindowsDiffRef windowSize, offsets -100..100 */
+
+/* per-alignment products shared by the three passes; arrays owned by the context                                 */
+typedef struct {
+    int32_t n_reads;
+    const uint8_t *category;      /* LPS_TAG_* dispatch category                                                 */
+    const int8_t *read_hp;        /* ReadHP of processed alignments, 0 otherwise                                 */
+    const int32_t *ps;            /* somatic tagging: PS:i value, -1 = VarData::NONE_PHASED_SET (no PS tag), 0 untagged */
+    const int32_t *pq;
+    const int32_t *h1, *h2, *h3;  /* hpCount[1..3]; hpCount[4] is never incremented by the reference             */
+    const uint8_t *n_ps;          /* min(norCountPS.size(), 2)                                                   */
+    const int32_t *end_pos;       /* ref_pos after parsingCigar (ReadVarHpCount::endPos)                          */
+    const int32_t *read_len;      /* query_pos after parsingCigar (ReadVarHpCount::readLength)                    */
+} lps_read_tags;
+
+typedef struct {
+    int32_t n_tum;
+    const int32_t *tum_var;        /* [n_tum] variant index of each tumor slot                                    */
+    const int32_t *pos_base;       /* [n_tum][LPS_PB_FIELDS]                                                      */
+    const int32_t *read_hp_count;  /* [n_tum][9] PosBase::ReadHpCount[ReadHP]                                     */
+    lps_read_tags reads;
+    /* ---- tumor pass only (NULL / 0 after lps_extract_normal) ---- */
+    const int32_t *somatic_read_hp_count; /* [n_tum][9] SomaticData::somaticReadHpCount                          */
+    const int32_t *case_count;     /* [n_tum][LPS_CASE_FIELDS]                                                    */
+    const int32_t *allele_count;   /* [n_tum][2] SomaticData::alleleCount                                         */
+    const int32_t *window_hist;    /* [n_tum][2][LPS_WINDOW_BINS] entries of PosSomaticOffsetBase[allele] per offset
+                                      (bin = offset + 100): all the DenseAlt filter reads (SomaticVarCaller.cpp:1160) */
+    uint64_t n_window_items;       /* (alignment, tumor position) pairs whose window was scanned                  */
+    /* per alignment, CSR: every variant that entered variantsHP or tumorSnpPosVec.  lps_call.allele = variantsHP
+     * (SnpHP 1 H1, 2 H2, 3 H3, 0 none), lps_call.quality bit0 = in tumorSnpPosVec, bit1 = in tumorAllelePosVec
+     * (ReadVarHpCount::posHpPairs, tumorPosReadCorrBaseHP; SomaticVarCaller.cpp:407-459)                         */
+    uint64_t n_calls;
+    const uint64_t *call_off;
+    const lps_call *calls;
+} lps_extract_result;
+
+/* pass A of SomaticVarCaller::extractSomaticData over the NORMAL BAM: ExtractNorDataChrProcessor::processRead with the
+ * ExtractNorDataCigarParser hooks and countBaseNucleotide (src/somatic_haplotag/SomaticVarCaller.cpp:123-293,
+ * src/haplotag/HaplotagParsingBam.cpp:682-730).  postProcess' ratios (:176-210) are left to the host.            */
+int lps_extract_normal(lps_ctx *ctx, const lps_tag_params *p, lps_extract_result *out);
+/* pass B over the TUMOR BAM: ExtractTumDataChrProcessor::processRead / classifyReadsByCase, the ExtractTumDataCigarParser
+ * hooks, judgeSomaticSnpHap / judgeSomaticReadHap and getWindowsDiffRef (SomaticVarCaller.cpp:334-759,
+ * HaplotagStrategy.cpp:315-602, 617-638).  postProcess' ratios (:520-603) are left to the host.                   */
+int lps_extract_tumor(lps_ctx *ctx, const lps_tag_params *p, lps_extract_result *out);
+
+typedef struct {
+    lps_read_tags reads;           /* read_hp = ReadHP after inheritHaplotype -> HP:Z, ps -> PS:i, pq -> PQ:i      */
+    const int8_t *hp_before;       /* [n_reads] ReadHP before inheritHaplotype                                    */
+    const float *derive_similarity;/* [n_reads] deriveByHpSimilarity (SomaticHaplotagProcess.cpp:493)              */
+    int32_t n_tum;
+    const int32_t *tum_var;
+    const int32_t *hp_before_count;   /* [n_tum][9] chrReadHpResult readHpCounter before inheritance (somatic positions) */
+    const int32_t *hp_after_count;    /* [n_tum][9] ... after inheritance                                          */
+    const int32_t *h3_before_count;   /* [n_tum][9] somaticBaseReadHpCounter before inheritance                    */
+    const int32_t *h3_after_count;    /* [n_tum][9] ... after                                                      */
+    const int32_t *cover_start, *cover_end; /* [n_tum] recordAlignCoverRegion (INT_MAX / INT_MIN when untouched)  */
+    uint64_t n_calls;              /* per alignment CSR of variantsHP (lps_call.allele = SnpHP, quality bit2 = somatic variant) */
+    const uint64_t *call_off;
+    const lps_call *calls;
+    /* ReadStatistics (HaplotagProcess.h:21-45)                                                                   */
+    int64_t total_alignment, total_supplementary, total_secondary, total_unmapped, total_tag, total_untag,
+            total_lower_quality, total_other_case, total_empty_variant, total_high_similarity, total_cross_two_block,
+            total_without_variant, total_read_only_h3, total_hp[LPS_READHP_FIELDS];
+} lps_somatic_tag_result;
+
+/* SomaticHaplotagChrProcessor::judgeHaplotype for every alignment of the TUMOR batch: SomaticHaplotagCigarParser hooks,
+ * SomaticHaplotagStrategy::judgeTumorOnlySnpHap, judgeSomaticReadHap, inheritHaplotype and the PS rule
+ * (src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-579, src/haplotag/HaplotagStrategy.cpp:452-668).          */
+int lps_somatic_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_somatic_tag_result *out);
+
 /* ---- timing / accounting ------------------------------------------------------------------ */
 typedef struct {
     float ms_call_alleles;   /* device time of the allele-calling kernels of the last call      */
-    float ms_tag_reads;      /* device time of the last lps_tag_reads                            */
+    float ms_tag_reads;      /* device time of the last lps_tag_reads / lps_extract_* / lps_somatic_tag_reads */
     float ms_build_edges;
     float ms_read_correction;
     float ms_h2d;
     float ms_d2h;
     float ms_kernel_call_alleles; /* the k_call_alleles launch alone (CUDA events on the launching stream) */
     float ms_kernel_fold_edges;   /* the k_fold_edges launch alone                                          */
+    float ms_kernel_window_diff;  /* the k_window_diff launch alone (lps_extract_tumor)                     */
     float ms_wall_call_alleles;   /* host wall clock of the last lps_phase_call_alleles              */
     float ms_wall_build_edges;    /* ... lps_phase_build_edges                                        */
     float ms_wall_solve;          /* ... lps_phase_solve                                              */

@@ -89,10 +89,46 @@ class LpsTagResult(C.Structure):
                 ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))] + [(k, C.c_int64) for k in TAG_COUNTERS]
 
 
+class LpsTumorVariants(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nor_present", u8p), ("tum_present", u8p), ("ref0", u8p), ("alt0", u8p), ("ref_len", u16p),
+                ("alt_len", u16p), ("gt_kind", u8p), ("hp1_is_alt", u8p), ("ps", i32p), ("is_somatic", u8p), ("derive_hp", i8p)]
+
+
+PB_FIELDS = ["alt", "A", "C", "G", "T", "unknown", "depth", "del", "mpq_alt", "mpq_A", "mpq_C", "mpq_G", "mpq_T", "mpq_unknown",
+             "mpq_depth"]
+
+
+class LpsReadTags(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("category", u8p), ("read_hp", i8p), ("ps", i32p), ("pq", i32p), ("h1", i32p), ("h2", i32p),
+                ("h3", i32p), ("n_ps", u8p), ("end_pos", i32p), ("read_len", i32p)]
+
+
+CASE_FIELDS = ["clean_hp3", "pure_h1_1", "pure_h2_1", "pure_h3", "mixed", "untag"]
+WINDOW_BINS = 201
+
+
+class LpsExtractResult(C.Structure):
+    _fields_ = [("n_tum", C.c_int32), ("tum_var", i32p), ("pos_base", i32p), ("read_hp_count", i32p), ("reads", LpsReadTags),
+                ("somatic_read_hp_count", i32p), ("case_count", i32p), ("allele_count", i32p), ("window_hist", i32p),
+                ("n_window_items", C.c_uint64), ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))]
+
+
+SOMATIC_COUNTERS = ["total_alignment", "total_supplementary", "total_secondary", "total_unmapped", "total_tag", "total_untag",
+                    "total_lower_quality", "total_other_case", "total_empty_variant", "total_high_similarity", "total_cross_two_block",
+                    "total_without_variant", "total_read_only_h3"]
+
+
+class LpsSomaticTagResult(C.Structure):
+    _fields_ = [("reads", LpsReadTags), ("hp_before", i8p), ("derive_similarity", f32p), ("n_tum", C.c_int32), ("tum_var", i32p),
+                ("hp_before_count", i32p), ("hp_after_count", i32p), ("h3_before_count", i32p), ("h3_after_count", i32p),
+                ("cover_start", i32p), ("cover_end", i32p), ("n_calls", C.c_uint64), ("call_off", u64p),
+                ("calls", C.POINTER(LpsCall))] + [(k, C.c_int64) for k in SOMATIC_COUNTERS] + [("total_hp", C.c_int64 * 9)]
+
+
 class LpsStats(C.Structure):
     _fields_ = [("ms_call_alleles", C.c_float), ("ms_tag_reads", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_kernel_call_alleles", C.c_float),
-                ("ms_kernel_fold_edges", C.c_float), ("ms_wall_call_alleles", C.c_float),
+                ("ms_kernel_fold_edges", C.c_float), ("ms_kernel_window_diff", C.c_float), ("ms_wall_call_alleles", C.c_float),
                 ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
                 ("ms_host_sweep", C.c_float), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -114,6 +150,10 @@ SYMBOLS = {
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_phase_contig": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsTagResult)]),
+    "lps_contig_set_tumor_variants": (C.c_int, [C.c_void_p, C.POINTER(LpsTumorVariants)]),
+    "lps_extract_normal": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
+    "lps_extract_tumor": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
+    "lps_somatic_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsSomaticTagResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -70,6 +70,14 @@ struct K1Args {
     int8_t *tag_hp;                   // ReadHP: 0 unTag, 1 H1, 2 H2
     int32_t *tag_ps, *tag_pq, *tag_h1, *tag_h2;
     uint8_t *tag_cat;                 // dispatch category, see LPS_TAG_* in lps.h
+    // ---- somatic family (extract-normal, extract-tumor, somatic tagging) ----
+    DevSomatic som;
+    WdItem *wd_items;                 // tumor pass: window-diff work list
+    unsigned long long wd_cap;
+    int32_t *tag_h3, *tag_end, *tag_len;
+    uint8_t *tag_nps;
+    int8_t *tag_hpb;
+    float *tag_sim;
 };
 
 __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ pos, int n, int key, int lane) {
@@ -138,8 +146,260 @@ struct WarpScratch {
     Cand cand[CAND_CAP];
 };
 
-template <int K, bool TAG>
+// HaplotagVariantType (HaplotagType.h:76-85): 1 SNP, 2 INSERTION, 3 DELETION, 4 MNP, 0 = setVariantType would throw
+__device__ __forceinline__ int hvt(int rl, int al) {
+    if (rl == 1) return al == 1 ? 1 : (al > 1 ? 2 : 0);
+    if (rl > 1) return al == 1 ? 3 : (al == rl ? 4 : 0);
+    return 0;
+}
+
+// CigarParser::countBaseNucleotide (HaplotagParsingBam.cpp:682-720)
+__device__ __forceinline__ void count_base(int32_t *pb, char base, bool mpq_ok, bool is_alt, int ttype) {
+    const int k = base == 'A' ? 0 : base == 'C' ? 1 : base == 'G' ? 2 : base == 'T' ? 3 : 4;
+    if (mpq_ok) { atomicAdd(pb + LPS_PB_MPQ_A + k, 1); if (is_alt) atomicAdd(pb + LPS_PB_MPQ_ALT, 1); atomicAdd(pb + LPS_PB_MPQ_DEPTH, 1); }
+    atomicAdd(pb + LPS_PB_A + k, 1);
+    if (is_alt) { if (ttype == 3) atomicAdd(pb + LPS_PB_DEL, 1); atomicAdd(pb + LPS_PB_ALT, 1); }
+    atomicAdd(pb + LPS_PB_DEPTH, 1);
+}
+
+// The hooks of the three somatic parsers over the raw candidates of one read, the per-read decision, and the per-position
+// counters.  Pass 1 (32 candidates at a time): hooks + votes; warp reduction; decision (all lanes, uniform); pass 2: counters
+// that depend on the read's haplotype, and the per-read variant list.
+//   extract-normal  ExtractNorDataCigarParser + ExtractNorDataChrProcessor::processRead   SomaticVarCaller.cpp:123-293
+//   extract-tumor   ExtractTumDataCigarParser + ExtractTumDataChrProcessor::processRead   SomaticVarCaller.cpp:334-518, 712-759
+//   somatic tagging SomaticHaplotagCigarParser + SomaticHaplotagChrProcessor::judgeHaplotype  SomaticHaplotagProcess.cpp:310-579
+template <int MODE>
+__device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane, uint4 *cand4, int ncand, int ref_start, int ref_end,
+                                                int q_end, int lq) {
+    constexpr bool XNOR = MODE == LPS_MODE_EXTRACT_NORMAL, XTUM = MODE == LPS_MODE_EXTRACT_TUMOR, STAG = MODE == LPS_MODE_SOMATIC_TAG;
+    const DevSomatic &s = a.som;
+    const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
+    const bool mpq_ok = (int)a.b.mapq[r] >= a.mapping_quality;
+    int h1 = 0, h2 = 0, h3 = 0, ps_min = INT_MAX, ps_max = INT_MIN, d1 = 0, d2 = 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int c = c0 + lane;
+        int var = -1, vhp = 0; unsigned flags = 0; bool ps_counted = false;
+        if (c < ncand) {
+            const uint4 cd = cand4[c];
+            var = (int)cd.x;
+            const int qidx = (int)cd.y;
+            const unsigned fl = cd.w >> 28;
+            const bool N = s.nor_present ? s.nor_present[var] != 0 : true, T = s.tum_present[var] != 0;
+            const bool nphased = N && (s.nor_gt ? s.nor_gt[var] == 1 : true);          // NORMAL record is PHASED_HETERO
+            const int slot = s.slot_of_var[var];
+            const int nrl = a.v.ref_len[var], nal = a.v.alt_len[var];
+            const int trl = T ? s.t_ref_len[var] : 0, tal = T ? s.t_alt_len[var] : 0;
+            const int nty = N ? hvt(nrl, nal) : 0, tty = T ? hvt(trl, tal) : 0;
+            const char nrb = (char)a.v.ref0[var], nab = (char)a.v.alt0[var];
+            const char trb = T ? (char)s.t_ref0[var] : 0, tab = T ? (char)s.t_alt0[var] : 0;
+            const bool h1alt = N && a.hp1_is_alt[var] != 0;
+            if (!(fl & 8u)) {
+                // ---- processMatchOperation ----
+                const char base = "=ACMGRSVTWYHKDBN"[(seq[qidx >> 1] >> ((~qidx & 1) << 2)) & 0xfu];
+                // IsAltIndel (HaplotagParsingBam.cpp:650-670) on the NORMAL record when there is one, else on the TUMOR record
+                const int sty = N ? nty : tty;
+                const bool is_alt = sty == 1 ? base == (N ? nab : tab) : sty == 2 ? (fl & 2u) != 0 : sty == 3 ? (fl & 4u) != 0 : false;
+                if (XNOR) {
+                    if (T && tty >= 1 && tty <= 3) { flags |= 1u; count_base(s.pos_base + (size_t)slot * LPS_PB_FIELDS, base, mpq_ok, is_alt, tty); }
+                    if (mpq_ok && nphased) {
+                        // GermlineHaplotagStrategy::judgeSnpHap (HaplotagStrategy.cpp:20-130)
+                        if (nty == 1) {
+                            if (base == nrb || base == nab) {
+                                ps_counted = true;
+                                if (base == (h1alt ? nab : nrb)) h1++;
+                                if (base == (h1alt ? nrb : nab)) h2++;
+                            }
+                        } else if ((nty == 2 || nty == 3) && (fl & 1u)) {
+                            const bool has = nty == 2 ? (fl & 2u) != 0 : (fl & 4u) != 0;
+                            const int l1 = h1alt ? nal : nrl, l2 = h1alt ? nrl : nal;
+                            if (l1 != 1 && l2 == 1) { if (has) h1++; else h2++; }
+                            else if (l1 == 1 && l2 != 1) { if (has) h2++; else h1++; }
+                            ps_counted = true;
+                        }
+                    }
+                } else {
+                    if (STAG || mpq_ok) {
+                        // SomaticJudgeHapStrategy::judgeSomaticSnpHap (HaplotagStrategy.cpp:315-389)
+                        if (N) {
+                            if (nphased) {
+                                if (nty == 2 || nty == 3) {          // base := whole ALT / REF string, compared with HP1 / HP2
+                                    if (is_alt == h1alt) { h1++; vhp = 1; } else { h2++; vhp = 2; }
+                                    ps_counted = true;
+                                } else if (nty == 1 && (base == nrb || base == nab)) {
+                                    if (base == (h1alt ? nab : nrb)) { h1++; vhp = 1; }
+                                    if (base == (h1alt ? nrb : nab)) { h2++; vhp = 2; }
+                                    ps_counted = true;
+                                }
+                            }
+                        } else if (T) {
+                            const int gt = s.t_gt[var];
+                            const bool indel = tty == 2 || tty == 3;
+                            if (gt >= 1 && gt <= 3 && (indel || (tty == 1 && (base == trb || base == tab)))) {
+                                const bool base_is_alt = indel ? is_alt : base == tab;
+                                // judgeTumorOnlySnpHap: extract (:617-638) counts every ALT, tagging (:653-668) only somatic variants
+                                if (base_is_alt && (XTUM || s.is_somatic[var])) { h3++; vhp = 3; if (XTUM) flags |= 2u; }
+                            }
+                        }
+                        if (XTUM && T) flags |= 1u;               // tumorSnpPosVec
+                    }
+                    if (XTUM && T && tty >= 1 && tty <= 3) {
+                        if (tty != 1 || base == trb || base == tab) {
+                            atomicAdd(s.allele_count + (size_t)slot * 2 + (is_alt ? 1 : 0), 1);
+                            const unsigned long long k = atomicAdd(&a.counters->wd_items, 1ull);
+                            if (k < a.wd_cap) {
+                                WdItem it;
+                                it.read = (uint32_t)r; it.slot2 = (uint32_t)slot * 2u + (is_alt ? 1u : 0u); it.opi = cd.z; it.qidx = cd.y;
+                                it.off = cd.w & 0x0fffffffu;
+                                a.wd_items[k] = it;
+                            }
+                        }
+                        count_base(s.pos_base + (size_t)slot * LPS_PB_FIELDS, base, mpq_ok, is_alt, tty);
+                    }
+                    if (STAG && s.is_somatic[var]) flags |= 4u;     // somaticVarDeriveHP entry
+                }
+            } else if (XNOR || XTUM) {
+                // ---- processDeletionOperation ----
+                if (T) {
+                    int32_t *pb = s.pos_base + (size_t)slot * LPS_PB_FIELDS;
+                    if (XNOR) flags |= 1u;
+                    if (tty == 1) { atomicAdd(pb + LPS_PB_DEL, 1); atomicAdd(pb + LPS_PB_DEPTH, 1); }
+                    else if (tty == 3) { atomicAdd(pb + LPS_PB_ALT, 1); atomicAdd(pb + LPS_PB_DEL, 1); atomicAdd(pb + LPS_PB_DEPTH, 1); }
+                }
+                // first phased-het NORMAL variant of the D op only (alreadyJudgeDel); judgeDeletionHap (HaplotagStrategy.cpp:147-209)
+                if (XNOR && mpq_ok && nphased && s.prev_nor[var] < (int)cd.z && a.have_reference && a.v.hom[var] >= 3) {
+                    if (nty == 1) {
+                        if (qidx < lq) {
+                            const char base = "=ACMGRSVTWYHKDBN"[(seq[qidx >> 1] >> ((~qidx & 1) << 2)) & 0xfu];
+                            if (base == (h1alt ? nab : nrb)) h1++;
+                            if (base == (h1alt ? nrb : nab)) h2++;
+                            ps_counted = true;
+                        }
+                    } else if (nty == 3) {
+                        const int l1 = h1alt ? nal : nrl, l2 = h1alt ? nrl : nal;
+                        if (l1 != 1 && l2 == 1) h1++; else if (l1 == 1 && l2 != 1) h2++;
+                        ps_counted = true;
+                    }
+                }
+            }
+            if (ps_counted) { const int ps = a.var_ps[var]; ps_min = min(ps_min, ps); ps_max = max(ps_max, ps); }
+            if (STAG && (flags & 4u) && vhp == 3) { const int d = s.derive_hp[var]; d1 += d == 1; d2 += d == 2; }
+        }
+        __syncwarp();
+        if (c < ncand) cand4[c] = make_uint4((unsigned)var, (unsigned)vhp | (flags << 8), 0u, 0u);
+    }
+    h1 = (int)__reduce_add_sync(FULL, (unsigned)h1); h2 = (int)__reduce_add_sync(FULL, (unsigned)h2);
+    h3 = (int)__reduce_add_sync(FULL, (unsigned)h3);
+    ps_min = __reduce_min_sync(FULL, ps_min); ps_max = __reduce_max_sync(FULL, ps_max);
+    const bool ps_seen = ps_min != INT_MAX, ps_multi = ps_seen && ps_min != ps_max;
+    const int imx = h1 > h2 ? h1 : h2, imn = h1 > h2 ? h2 : h1;
+    int hp = 0, hp_before = 0, pq;
+    float sim = 0.f;
+    // PQ from the germline counts (HaplotagStrategy.cpp:279-288, :589-597); -1: beyond the table, the host fills it in
+    if (imx == 0) pq = 0; else if (imn == 0) pq = 40; else pq = imx < 256 ? (int)a.pq_lut[imn * 256 + imx] : -1;
+    if (XNOR) {
+        // GermlineHaplotagStrategy::judgeReadHap (HaplotagStrategy.cpp:243-300)
+        const double mx = (double)imx, mn = (double)imn;
+        if (!(mx / (mx + mn) < a.percentage)) { if (h1 > h2) hp = 1; if (h1 < h2) hp = 2; }
+        if (ps_multi) hp = 0;
+    } else {
+        // SomaticJudgeHapStrategy::judgeSomaticReadHap (HaplotagStrategy.cpp:452-602); hpCount[4] stays 0, so the tumor
+        // similarity is 1 whenever hpCount[3] != 0, and on a tie the normal maximum is H2
+        const int max_n = h1 > h2 ? 1 : 2;
+        const double nsim = imx == 0 ? 0.0 : (double)imx / ((double)imx + (double)imn);
+        if (h3 != 0) {
+            if (1.0 >= a.percentage) hp = nsim >= a.percentage ? (max_n == 1 ? 5 : 7) : 3;   // H1_1 / H2_1 / H3
+            pq = 40;
+        } else if (imx != 0) {
+            if (nsim >= a.percentage) hp = max_n;
+        }
+        if (ps_multi) hp = 0;
+        hp_before = hp;
+        if (STAG && hp == 3) {
+            // inheritHaplotype (SomaticHaplotagProcess.cpp:461-527), similarity in float
+            d1 = (int)__reduce_add_sync(FULL, (unsigned)d1); d2 = (int)__reduce_add_sync(FULL, (unsigned)d2);
+            const int mx = d1 > d2 ? d1 : d2, mn = d1 > d2 ? d2 : d1;
+            sim = mx == 0 ? 0.0f : (float)mx / ((float)mx + (float)mn);
+            if ((double)sim >= a.percentage) hp = d1 > d2 ? 5 : 7;
+        }
+    }
+    if (lane == 0) {
+        a.tag_hp[r] = (int8_t)hp; a.tag_pq[r] = pq; a.tag_h1[r] = h1; a.tag_h2[r] = h2; a.tag_h3[r] = h3;
+        a.tag_ps[r] = XNOR ? (hp ? ps_min : 0) : (hp ? (ps_seen ? ps_min : -1) : 0);       // PS rule (SomaticHaplotagProcess.cpp:409-430)
+        a.tag_nps[r] = (uint8_t)(ps_multi ? 2 : (ps_seen ? 1 : 0));
+        a.tag_end[r] = ref_end; a.tag_len[r] = q_end; a.tag_hpb[r] = (int8_t)hp_before; a.tag_sim[r] = sim;
+    }
+    __syncwarp();
+    // ---- pass 2: counters keyed by the read's haplotype; the per-read variant list ----
+    const bool record = !ps_multi, clean = h1 == 0 || h2 == 0;
+    int nout = 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int c = c0 + lane;
+        bool emit = false;
+        uint4 cd = make_uint4(0u, 0u, 0u, 0u);
+        if (c < ncand) {
+            cd = cand4[c];
+            const int var = (int)cd.x, vhp = (int)(cd.y & 0xffu);
+            const unsigned flags = cd.y >> 8;
+            const size_t sl = (size_t)max(s.slot_of_var[var], 0);
+            if (XNOR) {
+                if (flags & 1u) atomicAdd(s.read_hp_count + sl * 9 + hp, 1);
+            } else if (XTUM) {
+                if (flags & 2u) {
+                    // classifyReadsByCase (SomaticVarCaller.cpp:462-518) + somaticReadHpCount (:395-404)
+                    int32_t *cc = s.case_count + sl * LPS_CASE_FIELDS;
+                    if (!record) atomicAdd(cc + LPS_CASE_UNTAG, 1);
+                    else if (clean) {
+                        atomicAdd(cc + LPS_CASE_CLEAN_HP3, 1);
+                        if (h1 == 0 && h2 == 0) atomicAdd(cc + LPS_CASE_PURE_H3, 1);
+                        else if (h1 != 0) atomicAdd(cc + LPS_CASE_PURE_H1_1, 1);
+                        else atomicAdd(cc + LPS_CASE_PURE_H2_1, 1);
+                    } else atomicAdd(cc + LPS_CASE_MIXED, 1);
+                    if (hp == 5 || hp == 7 || hp == 3 || hp == 0) atomicAdd(s.somatic_read_hp_count + sl * 9 + hp, 1);
+                }
+                if (flags & 1u) atomicAdd(s.read_hp_count + sl * 9 + hp, 1);
+                emit = vhp != 0 || (flags & 1u);
+            } else {
+                if (flags & 4u) {
+                    // chrReadHpResult::recordReadHp / recordAlignCoverRegion (HaplotagLogging.cpp:13-72)
+                    atomicAdd(s.hp_before_count + sl * 9 + hp_before, 1);
+                    if (hp_before != 0 && vhp == 3) atomicAdd(s.h3_before_count + sl * 9 + hp_before, 1);
+                    atomicAdd(s.hp_after_count + sl * 9 + hp, 1);
+                    if (hp != 0 && vhp == 3) atomicAdd(s.h3_after_count + sl * 9 + hp, 1);
+                    if (hp != 0) { atomicMin(s.cover_start + sl, ref_start + 1); atomicMax(s.cover_end + sl, ref_end); }
+                }
+                emit = vhp != 0;
+            }
+        }
+        if (a.want_calls) {
+            const unsigned m = __ballot_sync(FULL, emit);
+            __syncwarp();
+            if (emit) {
+                const int dst = nout + __popc(m & ((1u << lane) - 1u));
+                const unsigned q = XTUM ? ((cd.y >> 8) & 3u) : ((cd.y >> 8) & 4u);
+                cand4[dst] = make_uint4(cd.x, q | ((cd.y & 0xffu) << 16), 0u, 0u);   // dst <= c
+            }
+            nout += __popc(m);
+            __syncwarp();
+        }
+    }
+    unsigned long long start = 0;
+    if (lane == 0 && nout) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nout);
+    start = __shfl_sync(FULL, start, 0);
+    if (lane == 0) { a.ncalls[r] = (uint32_t)nout; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
+    if (start + nout <= a.calls_cap) {
+        for (int c = lane; c < nout; c += 32) {
+            const uint4 cd = cand4[c];
+            lps_call out;
+            out.var = (int32_t)cd.x; out.quality = (int16_t)(cd.y & 0xffffu); out.allele = (int8_t)((cd.y >> 16) & 0xffu); out.origin = 0;
+            a.calls_tmp[start + c] = out;
+        }
+    }
+}
+
+template <int K, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a) {
+    constexpr bool TAG = MODE != LPS_MODE_PHASE;        // CigarParser::parsingCigar instead of BamParser::get_snp
+    constexpr bool SOM = MODE >= LPS_MODE_EXTRACT_NORMAL; // raw 16-byte candidates, resolved by resolve_somatic
     __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
@@ -159,6 +419,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
         cand = a.overflow_buf + a.overflow_off[wid];
         cand_cap = (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]);
     }
+    if (SOM) cand_cap >>= 1;                            // 16-byte candidates
+    uint4 *cand4 = reinterpret_cast<uint4 *>(cand);
     const int nv = a.v.n;
     const int ref_start = a.b.ref_start[r];
     const int lq = a.b.l_qseq[r];
@@ -184,6 +446,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
             if (lane == 0) {
                 a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED;
                 a.tag_hp[r] = 0; a.tag_ps[r] = 0; a.tag_pq[r] = 0; a.tag_h1[r] = 0; a.tag_h2[r] = 0;
+                if (SOM) { a.tag_h3[r] = 0; a.tag_end[r] = 0; a.tag_len[r] = 0; a.tag_nps[r] = 0; a.tag_hpb[r] = 0; a.tag_sim[r] = 0.f; }
             }
             return;
         }
@@ -278,6 +541,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
                 const unsigned mmask = __ballot_sync(FULL, mine);
                 if (mmask == 0) break;
                 int cand_var = -1; uint32_t cand_x = 0;
+                uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
                 bool ab = false, in_del = false;
                 int my_op_index = 0, my_j = 0;
                 if (mine) {
@@ -296,7 +560,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
                     const int64_t gidx = cb + j;
                     const int opi = (int)(gidx - lo);
                     my_op_index = opi;
-                    if (TAG) {
+                    if (SOM) {
+                        // union map: every variant inside an M/=/X op (HaplotagParsingBam.cpp:585-614) or a D op (:623-631) becomes a
+                        // raw candidate {variant, query index, op index | op start, offset | flags}; the hooks run in resolve_somatic
+                        if (o_op == 0 || o_op == 7 || o_op == 8) {
+                            const int off = vp - o_r;
+                            if (o_q + off < lq) {                      // beyond SEQ the reference reads undefined memory: dropped
+                                unsigned fl = 0;
+                                if (opi + 1 < ncig) {
+                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
+                                    fl = 1u;                           // i + 1 < n_cigar
+                                    if (o_r + o_len - 1 == vp) fl |= (nop == 1u ? 2u : 0u) | (nop == 2u ? 4u : 0u);
+                                }
+                                cand_var = vi;
+                                c4 = make_uint4((unsigned)vi, (unsigned)(o_q + off), (unsigned)opi, (unsigned)off | (fl << 28));
+                            }
+                        } else if (o_op == 2) {
+                            cand_var = vi;
+                            c4 = make_uint4((unsigned)vi, (unsigned)o_q, (unsigned)o_r, 8u << 28);
+                        }
+                    } else if (TAG) {
                         // CigarParser::parsingCigar M branch (HaplotagParsingBam.cpp:585-614) + judgeSnpHap (HaplotagStrategy.cpp:20-130)
                         if (o_op == 0 || o_op == 7 || o_op == 8) {
                             const int off = vp - o_r;
@@ -342,7 +625,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
                 }
                 // D-op rule (:1539-1607): only the FIRST pending variant of the op (previous variant lies before the op)
                 const int prev_pos = __shfl_up_sync(FULL, vwin, 1);
-                if (TAG && in_del) {
+                if (TAG && !SOM && in_del) {
                     // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
                     // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
                     const int o_r = S.r[my_j], o_q = S.q[my_j];
@@ -386,7 +669,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
                 }
                 if (cand_var >= 0 && ((keep >> lane) & 1u)) {
                     const int dst = ncand + __popc(keep & ((1u << lane) - 1u));
-                    if (dst < cand_cap) { cand[dst].var = cand_var; cand[dst].x = cand_x; }
+                    if (dst < cand_cap) {
+                        if (SOM) cand4[dst] = c4;
+                        else { cand[dst].var = cand_var; cand[dst].x = cand_x; }
+                    }
                 }
                 ncand += __popc(keep);
                 if (aborted) break;
@@ -447,6 +733,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
     }
     __syncwarp();
 
+    if (SOM) {
+        resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq);
+        return;
+    }
     if (TAG) {
         // ---- resolve: per candidate the haplotype bit and the "counts towards countPS" flag, then judgeReadHap ----
         const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
@@ -618,8 +908,23 @@ __global__ void k_widen_u32(int n, const uint32_t *__restrict__ in, uint64_t *__
 
 static_assert(sizeof(lps_call) == 8, "lps_call must be 8 bytes");
 
-int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls) {
+namespace {
+void launch_k1(int mode, int grid, cudaStream_t st, const K1Args &a) {
+    const int tb = WARPS_PER_CTA * 32;
+    switch (mode) {
+        case LPS_MODE_PHASE: k_call_alleles<8, LPS_MODE_PHASE><<<grid, tb, 0, st>>>(a); break;
+        case LPS_MODE_GERMLINE: k_call_alleles<8, LPS_MODE_GERMLINE><<<grid, tb, 0, st>>>(a); break;
+        case LPS_MODE_EXTRACT_NORMAL: k_call_alleles<8, LPS_MODE_EXTRACT_NORMAL><<<grid, tb, 0, st>>>(a); break;
+        case LPS_MODE_EXTRACT_TUMOR: k_call_alleles<8, LPS_MODE_EXTRACT_TUMOR><<<grid, tb, 0, st>>>(a); break;
+        default: k_call_alleles<8, LPS_MODE_SOMATIC_TAG><<<grid, tb, 0, st>>>(a); break;
+    }
+}
+}  // namespace
+
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls, int mode) {
     const bool tag = t != nullptr;
+    if (mode < 0) mode = tag ? LPS_MODE_GERMLINE : LPS_MODE_PHASE;
+    const bool som = mode >= LPS_MODE_EXTRACT_NORMAL;
     const int n = ctx->batch.n_reads;
     const int nv = ctx->var.n;
     cudaStream_t st = ctx->stream;
@@ -632,6 +937,19 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, ctx->d_tag_hp.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_ps.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_pq.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_h1.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_h2.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_cat.reserve((size_t)n + 1));
+    }
+    if (som) {
+        LPS_CUDA(ctx, ctx->d_tag_h3.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_end.reserve((size_t)n + 1));
+        LPS_CUDA(ctx, ctx->d_tag_len.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_nps.reserve((size_t)n + 1));
+        LPS_CUDA(ctx, ctx->d_tag_hpb.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_sim.reserve((size_t)n + 1));
+    }
+    // tumor pass: one window-diff work item per (alignment, covered tumor position); sized from the tumor density, re-run on overflow
+    size_t wd_cap = 0;
+    if (mode == LPS_MODE_EXTRACT_TUMOR) {
+        double tden = 0.0;
+        if (nv > 1) tden = (double)ctx->som.n_tum / ((double)ctx->h_vpos[nv - 1] - (double)ctx->h_vpos[0] + 1.0);
+        wd_cap = (size_t)((double)ctx->sum_l_qseq * tden * 1.5) + (size_t)n + 4096;
+        if (wd_cap < ctx->d_wd_items.cap) wd_cap = ctx->d_wd_items.cap;
     }
     // scratch pool capacity from the variant density of the contig; re-run on overflow
     double density = 0.0;
@@ -649,6 +967,17 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, ctx->d_calls_tmp.reserve(cap));
         LPS_CUDA(ctx, ctx->d_clip_keys.reserve(clip_cap));
         LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(CallCounters), st));
+        if (som) {
+            // per-slot counters start from zero on every attempt (a re-run after a pool overflow must not count twice)
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_som_counters.p, 0, ctx->som_counter_words * sizeof(int32_t), st));
+            if (ctx->som.n_tum) {
+                std::vector<int32_t> init((size_t)ctx->som.n_tum * 2, INT_MIN);
+                std::fill(init.begin(), init.begin() + ctx->som.n_tum, INT_MAX);
+                LPS_CUDA(ctx, cudaMemcpyAsync(ctx->som.cover_start, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                LPS_CUDA(ctx, cudaStreamSynchronize(st));
+            }
+            if (wd_cap) LPS_CUDA(ctx, ctx->d_wd_items.reserve(wd_cap));
+        }
         K1Args a;
         memset(&a, 0, sizeof(a));
         a.b = ctx->batch; a.v = ctx->var;
@@ -663,6 +992,12 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             a.tag_hp = ctx->d_tag_hp.p; a.tag_ps = ctx->d_tag_ps.p; a.tag_pq = ctx->d_tag_pq.p;
             a.tag_h1 = ctx->d_tag_h1.p; a.tag_h2 = ctx->d_tag_h2.p; a.tag_cat = ctx->d_tag_cat.p;
         }
+        if (som) {
+            a.som = ctx->som;
+            a.wd_items = ctx->d_wd_items.p; a.wd_cap = mode == LPS_MODE_EXTRACT_TUMOR ? ctx->d_wd_items.cap : 0;
+            a.tag_h3 = ctx->d_tag_h3.p; a.tag_end = ctx->d_tag_end.p; a.tag_len = ctx->d_tag_len.p; a.tag_nps = ctx->d_tag_nps.p;
+            a.tag_hpb = ctx->d_tag_hpb.p; a.tag_sim = ctx->d_tag_sim.p;
+        }
         a.last_var_pos = nv ? ctx->h_vpos[nv - 1] : -1;
         a.calls_tmp = ctx->d_calls_tmp.p; a.calls_cap = ctx->d_calls_tmp.cap;
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
@@ -674,7 +1009,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (grid > 0) {
             cudaEventRecord(ctx->kev[0], st);
-            if (tag) k_call_alleles<8, true><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a); else k_call_alleles<8, false><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+            launch_k1(mode, grid, st, a);
             cudaEventRecord(ctx->kev[1], st);
             ctx->stats.kernel_launches++;
         }
@@ -691,7 +1026,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             // candidate lists in global memory sized from the first pass
             std::vector<uint64_t> need(hc.overflow_reads), off(hc.overflow_reads + 1, 0);
             LPS_CUDA(ctx, cudaMemcpy(need.data(), ctx->d_overflow_cand.p, 8 * (size_t)hc.overflow_reads, cudaMemcpyDeviceToHost));
-            for (uint32_t i = 0; i < hc.overflow_reads; i++) off[i + 1] = off[i] + need[i];
+            for (uint32_t i = 0; i < hc.overflow_reads; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
             LPS_CUDA(ctx, ctx->d_overflow_off.reserve(off.size()));
             LPS_CUDA(ctx, cudaMemcpy(ctx->d_overflow_off.p, off.data(), 8 * off.size(), cudaMemcpyHostToDevice));
             DevBuf<Cand> ovf;
@@ -706,18 +1041,20 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             LPS_CUDA(ctx, cudaMemcpyAsync(scratch.p, ctx->d_counters.p, sizeof(CallCounters), cudaMemcpyDeviceToDevice, st));
             b2.counters = scratch.p;
             const int g2 = ((int)hc.overflow_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-            if (tag) k_call_alleles<8, true><<<g2, WARPS_PER_CTA * 32, 0, st>>>(b2); else k_call_alleles<8, false><<<g2, WARPS_PER_CTA * 32, 0, st>>>(b2);
+            launch_k1(mode, g2, st, b2);
             ctx->stats.kernel_launches++;
             LPS_CUDA(ctx, cudaGetLastError());
             CallCounters h2;
             LPS_CUDA(ctx, cudaMemcpyAsync(&h2, scratch.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
             LPS_CUDA(ctx, cudaStreamSynchronize(st));
-            hc.tmp_calls = h2.tmp_calls;
+            hc.tmp_calls = h2.tmp_calls; hc.wd_items = h2.wd_items;
             ovf.release(); scratch.release();
         }
-        if (hc.tmp_calls <= ctx->d_calls_tmp.cap && hc.clips <= ctx->d_clip_keys.cap) break;
+        ctx->n_wd_items = hc.wd_items;
+        if (hc.tmp_calls <= ctx->d_calls_tmp.cap && hc.clips <= ctx->d_clip_keys.cap && hc.wd_items <= ctx->d_wd_items.cap) break;
         cap = (size_t)hc.tmp_calls + 1024;
         clip_cap = (size_t)hc.clips + 1024;
+        if (wd_cap) wd_cap = (size_t)hc.wd_items + 1024;
         if (attempt == 2) return ctx->fail(LPS_E_NOMEM, "call pool sizing did not converge");
     }
 

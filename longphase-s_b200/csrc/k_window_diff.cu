@@ -1,0 +1,99 @@
+// k_window_diff.cu — the +-100 window comparison of a read with the reference around every covered tumor position:
+// getWindowsDiffRef / getOrderWindowsDiffRef / processCigarOperation (reference src/somatic_haplotag/SomaticVarCaller.cpp:627-710),
+// the hottest function of the tumor extract pass on the CPU (47 % of its non-I/O samples).
+//
+// The reference appends (offset, read_base) pairs to PosSomaticOffsetBase[allele]; its only consumer, the DenseAlt filter
+// (:1160-1203), counts entries per offset.  The kernel therefore bins straight into window_hist[slot][allele][offset + 100].
+//
+// Mapping: ONE THREAD PER (alignment, tumor position) work item emitted by k_call_alleles' tumor dialect.  The scan is a
+// sequential state machine with the reference's quirks (the budget is decremented BEFORE each step and the hop to the
+// neighbouring CIGAR op happens at 0 or -1, so the backward scan skips the first base of every op; N / P / X ops consume
+// iterations without moving; offsets are iteration indices, not base distances), so it is replayed step by step per thread;
+// work items of one read are adjacent in the list, which keeps the CIGAR / SEQ / reference lines they share in L1.
+#include "lps_ctx.cuh"
+
+namespace {
+
+struct WdArgs {
+    DevBatch b;
+    const WdItem *items;
+    unsigned long long n_items;
+    const int32_t *vpos;        // variant positions
+    const int32_t *tum_var;     // slot -> variant
+    const char *ref;
+    long long ref_len;          // 0 when the reference string is empty
+    int32_t *window_hist;       // [n_tum][2][LPS_WINDOW_BINS]
+};
+
+// processCigarOperation (:627-654)
+__device__ __forceinline__ bool next_op(const uint32_t *__restrict__ cig, int &ci, int ci_end, int dir, int &remaining, int &read_pos, int &ref_pos,
+                                        int &op) {
+    ci += dir;
+    while (ci < ci_end && ci >= 0) {
+        const uint32_t c = cig[ci];
+        op = (int)(c & 15u);
+        const int len = (int)(c >> 4);
+        if (op == 0 || op == 3 || op == 6 || op == 7 || op == 8) { remaining += len; return true; }
+        else if (op == 1) read_pos += len * dir;
+        else if (op == 2) ref_pos += len * dir;
+        else return false;
+        ci += dir;
+    }
+    return false;
+}
+
+// getOrderWindowsDiffRef (:655-686)
+__device__ __forceinline__ void scan(const WdArgs &a, const uint32_t *__restrict__ cig, int ci, int ncig, const uint8_t *__restrict__ seq, int lq,
+                                     int read_pos, int remaining, int ref_pos, int dir, int32_t *__restrict__ hist) {
+    int op = (int)(cig[ci] & 15u);
+    for (int i = 1; i <= LPS_WINDOW; i++) {
+        remaining--;
+        if (remaining == 0 || remaining == -1)
+            if (!next_op(cig, ci, ncig, dir, remaining, read_pos, ref_pos, op)) return;
+        if (op == 2 || op == 1 || op == 3 || op == 6 || op == 8) continue;
+        read_pos += dir; ref_pos += dir;
+        if (read_pos > lq || (long long)ref_pos > a.ref_len || read_pos < 0 || ref_pos < 0) return;
+        if (read_pos == lq) return;                                        // one past SEQ: undefined in the reference
+        const char rb = "=ACMGRSVTWYHKDBN"[(seq[read_pos >> 1] >> ((~read_pos & 1) << 2)) & 0xfu];
+        const char fb = (long long)ref_pos == a.ref_len ? '\0' : a.ref[ref_pos];   // std::string::operator[](size())
+        if (rb != fb) atomicAdd(hist + i * dir + LPS_WINDOW, 1);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_window_diff(WdArgs a) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_items) return;
+    const WdItem it = a.items[t];
+    const int r = (int)it.read;
+    const uint32_t *__restrict__ cig = a.b.cigar + a.b.cigar_off[r];
+    const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
+    const int ncig = (int)a.b.n_cigar[r], lq = a.b.l_qseq[r];
+    const int ci = (int)it.opi, off = (int)it.off;
+    const int var_pos = a.vpos[a.tum_var[it.slot2 >> 1]];
+    int32_t *hist = a.window_hist + (size_t)it.slot2 * LPS_WINDOW_BINS;
+    // getWindowsDiffRef (:688-710): the op is an M/=/X op, never an insertion
+    const int oplen = (int)(cig[ci] >> 4);
+    const int fwd = oplen - off > 0 ? oplen - off : 0, rev = off > 0 ? off : 0;
+    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, rev, var_pos, -1, hist);
+    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, fwd, var_pos, 1, hist);
+}
+
+}  // namespace
+
+int lps_launch_window_diff(lps_ctx *ctx, int have_reference) {
+    const unsigned long long n = ctx->n_wd_items;
+    ctx->stats.ms_kernel_window_diff = 0.f;
+    if (n == 0) return LPS_OK;
+    WdArgs a;
+    a.b = ctx->batch; a.items = ctx->d_wd_items.p; a.n_items = n; a.vpos = ctx->var.pos; a.tum_var = ctx->som.tum_var;
+    a.ref = ctx->d_ref.p; a.ref_len = have_reference ? (long long)ctx->ref_len : 0; a.window_hist = ctx->som.window_hist;
+    const int tb = 128;
+    cudaEventRecord(ctx->kev[4], ctx->stream);
+    k_window_diff<<<(unsigned)((n + tb - 1) / tb), tb, 0, ctx->stream>>>(a);
+    cudaEventRecord(ctx->kev[5], ctx->stream);
+    ctx->stats.kernel_launches++;
+    LPS_CUDA(ctx, cudaGetLastError());
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.ms_kernel_window_diff, ctx->kev[4], ctx->kev[5]);
+    return LPS_OK;
+}

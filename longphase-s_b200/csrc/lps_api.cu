@@ -1,5 +1,6 @@
 // lps_api.cu — the extern "C" boundary declared in include/lps.h.
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include "lps_ctx.cuh"
 
@@ -154,6 +155,9 @@ int lps_contig_set_variants(lps_ctx *ctx, const lps_variants *v, int is_ont) {
     ctx->var.hom = ctx->d_vhom.p; ctx->var.danger = ctx->d_vdanger.p; ctx->var.filtered = ctx->d_vfiltered.p;
     ctx->is_ont = is_ont;
     ctx->have_tag_variants = false;
+    ctx->have_tumor_variants = false;
+    ctx->som = DevSomatic();
+    if (v->gt_kind) { TRY(h2d(ctx, ctx->d_nor_gt, v->gt_kind, n)); ctx->som.nor_gt = ctx->d_nor_gt.p; }
     if (v->hp1_is_alt && v->ps) {
         TRY(h2d(ctx, ctx->d_vhp1_is_alt, v->hp1_is_alt, n));
         TRY(h2d(ctx, ctx->d_vps, v->ps, n));
@@ -346,6 +350,193 @@ int lps_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_tag
         out->category = ctx->h_tag_cat.data(); out->hp = ctx->h_tag_hp.data(); out->ps = ctx->h_tag_ps.data();
         out->pq = ctx->h_tag_pq.data(); out->h1 = ctx->h_tag_h1.data(); out->h2 = ctx->h_tag_h2.data();
         if (want_calls) { out->n_calls = ctx->n_calls; out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data(); }
+    }
+    return LPS_OK;
+}
+
+int lps_contig_set_tumor_variants(lps_ctx *ctx, const lps_tumor_variants *t) {
+    if (!ctx || !t) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_tag_variants)
+        return ctx->fail(LPS_E_STATE, "lps_contig_set_variants (with hp1_is_alt / ps) must be called first");
+    if (t->n != ctx->var.n) return ctx->fail(LPS_E_ARG, "the tumor arrays must be parallel to the variant table");
+    const size_t n = (size_t)t->n;
+    if (n && (!t->tum_present || !t->ref0 || !t->alt0 || !t->ref_len || !t->alt_len || !t->gt_kind || !t->ps || !t->is_somatic || !t->derive_hp))
+        return ctx->fail(LPS_E_ARG, "null tumor variant array");
+    cudaSetDevice(ctx->device);
+    std::vector<uint8_t> nor_gt;
+    if (ctx->som.nor_gt) { TRY(d2h(ctx, nor_gt, ctx->som.nor_gt, n)); LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    std::vector<int32_t> slot(n, -1), prev_nor(n, INT_MIN);
+    ctx->h_tum_var.clear();
+    int32_t last_nor = INT_MIN;
+    for (size_t i = 0; i < n; i++) {
+        const bool N = t->nor_present ? t->nor_present[i] != 0 : true, T = t->tum_present[i] != 0;
+        if (!N && !T) return ctx->fail(LPS_E_ARG, "a position of the union map holds neither a NORMAL nor a TUMOR record");
+        if (T) {
+            if (t->gt_kind[i] == 1 && t->ps[i] == -1) return ctx->fail(LPS_E_ARG, "phased tumor record without a phase set (HaplotagStrategy.cpp:337)");
+            slot[i] = (int32_t)ctx->h_tum_var.size();
+            ctx->h_tum_var.push_back((int32_t)i);
+        } else if (t->is_somatic[i]) return ctx->fail(LPS_E_ARG, "is_somatic set on a position without a TUMOR record");
+        if (t->derive_hp[i] < 0 || t->derive_hp[i] > 2) return ctx->fail(LPS_E_ARG, "derive_hp must be 0, 1 or 2 (HaplotagLogging.cpp:41)");
+        prev_nor[i] = last_nor;
+        if (N && (nor_gt.empty() || nor_gt[i] == 1)) last_nor = ctx->h_vpos[i];
+    }
+    const size_t nt = ctx->h_tum_var.size();
+    DevSomatic &s = ctx->som;
+    if (t->nor_present) { TRY(h2d(ctx, ctx->d_nor_present, t->nor_present, n)); s.nor_present = ctx->d_nor_present.p; } else s.nor_present = nullptr;
+    TRY(h2d(ctx, ctx->d_tum_present, t->tum_present, n)); s.tum_present = ctx->d_tum_present.p;
+    TRY(h2d(ctx, ctx->d_t_ref0, t->ref0, n)); s.t_ref0 = ctx->d_t_ref0.p;
+    TRY(h2d(ctx, ctx->d_t_alt0, t->alt0, n)); s.t_alt0 = ctx->d_t_alt0.p;
+    TRY(h2d(ctx, ctx->d_t_ref_len, t->ref_len, n)); s.t_ref_len = ctx->d_t_ref_len.p;
+    TRY(h2d(ctx, ctx->d_t_alt_len, t->alt_len, n)); s.t_alt_len = ctx->d_t_alt_len.p;
+    TRY(h2d(ctx, ctx->d_t_gt, t->gt_kind, n)); s.t_gt = ctx->d_t_gt.p;
+    TRY(h2d(ctx, ctx->d_is_somatic, t->is_somatic, n)); s.is_somatic = ctx->d_is_somatic.p;
+    TRY(h2d(ctx, ctx->d_derive_hp, t->derive_hp, n)); s.derive_hp = ctx->d_derive_hp.p;
+    TRY(h2d(ctx, ctx->d_slot_of_var, slot.data(), n)); s.slot_of_var = ctx->d_slot_of_var.p;
+    TRY(h2d(ctx, ctx->d_prev_nor, prev_nor.data(), n)); s.prev_nor = ctx->d_prev_nor.p;
+    TRY(h2d(ctx, ctx->d_tum_var, ctx->h_tum_var.data(), nt)); s.tum_var = ctx->d_tum_var.p;
+    s.n_tum = (int32_t)nt;
+    // one block of per-slot counters; cover_start / cover_end are adjacent (initialised together by the launcher)
+    const size_t words[] = {LPS_PB_FIELDS, 9, 9, LPS_CASE_FIELDS, 2, 9, 9, 9, 9, 1, 1, 2 * LPS_WINDOW_BINS};
+    size_t total = 0;
+    for (size_t w : words) total += w * nt;
+    LPS_CUDA(ctx, ctx->d_som_counters.reserve(total + 1));
+    ctx->som_counter_words = total;
+    int32_t *q = ctx->d_som_counters.p;
+    int32_t **dst[] = {&s.pos_base, &s.read_hp_count, &s.somatic_read_hp_count, &s.case_count, &s.allele_count, &s.hp_before_count,
+                       &s.hp_after_count, &s.h3_before_count, &s.h3_after_count, &s.cover_start, &s.cover_end, &s.window_hist};
+    for (size_t k = 0; k < sizeof(words) / sizeof(words[0]); k++) { *dst[k] = q; q += words[k] * nt; }
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_tumor_variants = true;
+    return LPS_OK;
+}
+
+namespace {
+
+// per-alignment products of the somatic family -> host; PQ values beyond the device table use the host libm
+int fetch_read_tags(lps_ctx *ctx, bool somatic_pq, lps_read_tags *out) {
+    const size_t n = (size_t)ctx->batch.n_reads;
+    TRY(d2h(ctx, ctx->h_tag_cat, ctx->d_tag_cat.p, n));
+    TRY(d2h(ctx, ctx->h_tag_hp, ctx->d_tag_hp.p, n));
+    TRY(d2h(ctx, ctx->h_tag_ps, ctx->d_tag_ps.p, n));
+    TRY(d2h(ctx, ctx->h_tag_pq, ctx->d_tag_pq.p, n));
+    TRY(d2h(ctx, ctx->h_tag_h1, ctx->d_tag_h1.p, n));
+    TRY(d2h(ctx, ctx->h_tag_h2, ctx->d_tag_h2.p, n));
+    TRY(d2h(ctx, ctx->h_tag_h3, ctx->d_tag_h3.p, n));
+    TRY(d2h(ctx, ctx->h_tag_nps, ctx->d_tag_nps.p, n));
+    TRY(d2h(ctx, ctx->h_tag_end, ctx->d_tag_end.p, n));
+    TRY(d2h(ctx, ctx->h_tag_len, ctx->d_tag_len.p, n));
+    TRY(d2h(ctx, ctx->h_tag_hpb, ctx->d_tag_hpb.p, n));
+    TRY(d2h(ctx, ctx->h_tag_sim, ctx->d_tag_sim.p, n));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t r = 0; r < n; r++)
+        if (ctx->h_tag_pq[r] < 0) {
+            const int h1 = ctx->h_tag_h1[r], h2 = ctx->h_tag_h2[r];
+            const double mx = h1 > h2 ? h1 : h2, mn = h1 > h2 ? h2 : h1;
+            ctx->h_tag_pq[r] = -10 * (std::log10((double)mn / double(mx + mn)));
+        }
+    (void)somatic_pq;
+    out->n_reads = ctx->batch.n_reads;
+    out->category = ctx->h_tag_cat.data(); out->read_hp = ctx->h_tag_hp.data(); out->ps = ctx->h_tag_ps.data(); out->pq = ctx->h_tag_pq.data();
+    out->h1 = ctx->h_tag_h1.data(); out->h2 = ctx->h_tag_h2.data(); out->h3 = ctx->h_tag_h3.data(); out->n_ps = ctx->h_tag_nps.data();
+    out->end_pos = ctx->h_tag_end.data(); out->read_len = ctx->h_tag_len.data();
+    return LPS_OK;
+}
+
+int run_extract(lps_ctx *ctx, const lps_tag_params *p, int mode, lps_extract_result *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
+    if (!ctx->have_tumor_variants) return ctx->fail(LPS_E_STATE, "lps_contig_set_tumor_variants has not been called");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const bool tumor = mode == LPS_MODE_EXTRACT_TUMOR;
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_call_alleles(ctx, nullptr, p, tumor ? 1 : 0, mode));
+    if (tumor) TRY(lps_launch_window_diff(ctx, p->have_reference));
+    cudaEventRecord(ctx->ev[3], st);
+    TRY(d2h(ctx, ctx->h_som_counters, ctx->d_som_counters.p, ctx->som_counter_words));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_tag_reads = elapsed(ctx, 2, 3);
+    ctx->have_calls = false; ctx->have_graph = false; ctx->host_calls_valid = false;
+    if (!out) return LPS_OK;
+    memset(out, 0, sizeof(*out));
+    TRY(fetch_read_tags(ctx, tumor, &out->reads));
+    const DevSomatic &s = ctx->som;
+    const int32_t *h = ctx->h_som_counters.data(), *d = ctx->d_som_counters.p;
+    out->n_tum = s.n_tum; out->tum_var = ctx->h_tum_var.data();
+    out->pos_base = h + (s.pos_base - d); out->read_hp_count = h + (s.read_hp_count - d);
+    if (tumor) {
+        out->somatic_read_hp_count = h + (s.somatic_read_hp_count - d); out->case_count = h + (s.case_count - d);
+        out->allele_count = h + (s.allele_count - d); out->window_hist = h + (s.window_hist - d);
+        out->n_window_items = ctx->n_wd_items;
+        const size_t n = (size_t)ctx->batch.n_reads;
+        TRY(d2h(ctx, ctx->h_call_off, ctx->d_call_off.p, n + 1));
+        TRY(d2h(ctx, ctx->h_calls, ctx->d_calls.p, (size_t)ctx->n_calls));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        out->n_calls = ctx->n_calls; out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data();
+    }
+    return LPS_OK;
+}
+
+}  // namespace
+
+int lps_extract_normal(lps_ctx *ctx, const lps_tag_params *p, lps_extract_result *out) { return run_extract(ctx, p, LPS_MODE_EXTRACT_NORMAL, out); }
+int lps_extract_tumor(lps_ctx *ctx, const lps_tag_params *p, lps_extract_result *out) { return run_extract(ctx, p, LPS_MODE_EXTRACT_TUMOR, out); }
+
+int lps_somatic_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_somatic_tag_result *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
+    if (!ctx->have_tumor_variants) return ctx->fail(LPS_E_STATE, "lps_contig_set_tumor_variants has not been called");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)ctx->batch.n_reads;
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_call_alleles(ctx, nullptr, p, want_calls, LPS_MODE_SOMATIC_TAG));
+    cudaEventRecord(ctx->ev[3], st);
+    TRY(d2h(ctx, ctx->h_som_counters, ctx->d_som_counters.p, ctx->som_counter_words));
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_tag_reads = elapsed(ctx, 2, 3);
+    ctx->have_calls = false; ctx->have_graph = false; ctx->host_calls_valid = false;
+    if (!out) return LPS_OK;
+    memset(out, 0, sizeof(*out));
+    TRY(fetch_read_tags(ctx, true, &out->reads));
+    out->hp_before = ctx->h_tag_hpb.data(); out->derive_similarity = ctx->h_tag_sim.data();
+    const DevSomatic &s = ctx->som;
+    const int32_t *h = ctx->h_som_counters.data(), *d = ctx->d_som_counters.p;
+    out->n_tum = s.n_tum; out->tum_var = ctx->h_tum_var.data();
+    out->hp_before_count = h + (s.hp_before_count - d); out->hp_after_count = h + (s.hp_after_count - d);
+    out->h3_before_count = h + (s.h3_before_count - d); out->h3_after_count = h + (s.h3_after_count - d);
+    out->cover_start = h + (s.cover_start - d); out->cover_end = h + (s.cover_end - d);
+    if (want_calls) {
+        TRY(d2h(ctx, ctx->h_call_off, ctx->d_call_off.p, n + 1));
+        TRY(d2h(ctx, ctx->h_calls, ctx->d_calls.p, (size_t)ctx->n_calls));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        out->n_calls = ctx->n_calls; out->call_off = ctx->h_call_off.data(); out->calls = ctx->h_calls.data();
+    }
+    // ReadStatistics (HaplotagProcess.cpp:282-354; SomaticHaplotagProcess.cpp:352, 398-402; HaplotagStrategy.cpp:452-602)
+    for (size_t r = 0; r < n; r++) {
+        out->total_alignment++;
+        const int cat = ctx->h_tag_cat[r];
+        if (cat != LPS_TAG_PROCESSED) {
+            out->total_untag++;
+            if (cat == LPS_TAG_LOW_MAPQ) out->total_lower_quality++;
+            else if (cat == LPS_TAG_UNMAPPED) out->total_unmapped++;
+            else if (cat == LPS_TAG_SECONDARY) out->total_secondary++;
+            else if (cat == LPS_TAG_SUPPLEMENTARY) out->total_supplementary++;
+            else if (cat == LPS_TAG_EMPTY_VARIANTS) out->total_empty_variant++;
+            else out->total_other_case++;
+            continue;
+        }
+        if (ctx->h_flag[r] & 0x800) out->total_supplementary++;
+        const int h1 = ctx->h_tag_h1[r], h2 = ctx->h_tag_h2[r], h3 = ctx->h_tag_h3[r], hp = ctx->h_tag_hp[r];
+        const double mx = h1 > h2 ? h1 : h2, mn = h1 > h2 ? h2 : h1;
+        const double nsim = mx == 0 ? 0.0 : mx / (mx + mn);
+        if (h3 != 0) { if (!(1.0 >= p->percentage_threshold)) out->total_high_similarity++; }
+        else if (mx != 0 && !(nsim >= p->percentage_threshold)) out->total_high_similarity++;
+        if (ctx->h_tag_nps[r] > 1) out->total_cross_two_block++;
+        if (mx == 0 && h3 == 0) out->total_without_variant++;
+        if (h1 == 0 && h2 == 0 && h3 != 0 && hp == 3) out->total_read_only_h3++;
+        out->total_hp[hp]++;
+        if (hp != 0) out->total_tag++; else out->total_untag++;
     }
     return LPS_OK;
 }

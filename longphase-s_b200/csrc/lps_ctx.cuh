@@ -76,12 +76,34 @@ struct DevVariants {
     const uint8_t *hom = nullptr, *danger = nullptr, *filtered = nullptr;
 };
 
+// TUMOR side of the union variant map + per-slot counter block of the somatic family (see lps.h); DEVICE pointers
+struct DevSomatic {
+    const uint8_t *nor_present = nullptr, *nor_gt = nullptr, *tum_present = nullptr;
+    const uint8_t *t_ref0 = nullptr, *t_alt0 = nullptr, *t_gt = nullptr, *is_somatic = nullptr;
+    const uint16_t *t_ref_len = nullptr, *t_alt_len = nullptr;
+    const int8_t *derive_hp = nullptr;
+    const int32_t *slot_of_var = nullptr;   // tumor slot of a variant, -1 when it has no TUMOR record
+    const int32_t *tum_var = nullptr;       // [n_tum]
+    const int32_t *prev_nor = nullptr;      // position of the last earlier variant with a phased-het NORMAL record, INT_MIN if none
+    int32_t n_tum = 0;
+    // per-slot counters, every array [n_tum][k]
+    int32_t *pos_base = nullptr, *read_hp_count = nullptr, *somatic_read_hp_count = nullptr, *case_count = nullptr, *allele_count = nullptr;
+    int32_t *hp_before_count = nullptr, *hp_after_count = nullptr, *h3_before_count = nullptr, *h3_after_count = nullptr;
+    int32_t *cover_start = nullptr, *cover_end = nullptr, *window_hist = nullptr;
+};
+
+// one (alignment, tumor position) pair whose +-100 window is compared with the reference by k_window_diff
+struct WdItem { uint32_t read, slot2, opi, qidx, off; };
+
+enum { LPS_MODE_PHASE = 0, LPS_MODE_GERMLINE = 1, LPS_MODE_EXTRACT_NORMAL = 2, LPS_MODE_EXTRACT_TUMOR = 3, LPS_MODE_SOMATIC_TAG = 4 };
+
 // counters written by the allele-calling kernel (one small struct, copied back once per call)
 struct CallCounters {
     unsigned long long tmp_calls;      // slots requested in the scratch call pool
     unsigned long long clips;          // clip events appended
     unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
     unsigned long long gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
+    unsigned long long wd_items;       // window-diff work items appended (tumor extract pass)
     unsigned int overflow_reads;
     unsigned int bad_cigar;            // reads with an unsupported CIGAR op
 };
@@ -155,6 +177,26 @@ struct lps_ctx {
     std::vector<uint8_t> h_tag_cat;
     std::vector<uint16_t> h_flag;
 
+    // ---- somatic family ----
+    DevBuf<uint8_t> d_nor_present, d_nor_gt, d_tum_present, d_t_ref0, d_t_alt0, d_t_gt, d_is_somatic;
+    DevBuf<uint16_t> d_t_ref_len, d_t_alt_len;
+    DevBuf<int8_t> d_derive_hp;
+    DevBuf<int32_t> d_slot_of_var, d_tum_var, d_prev_nor, d_som_counters;
+    DevBuf<WdItem> d_wd_items;
+    DevSomatic som;
+    size_t som_counter_words = 0;
+    bool have_tumor_variants = false;
+    std::vector<int32_t> h_tum_var, h_som_counters;
+    DevBuf<int32_t> d_tag_h3, d_tag_end, d_tag_len;
+    DevBuf<uint8_t> d_tag_nps;
+    DevBuf<int8_t> d_tag_hpb;
+    DevBuf<float> d_tag_sim;
+    std::vector<int32_t> h_tag_h3, h_tag_end, h_tag_len;
+    std::vector<uint8_t> h_tag_nps;
+    std::vector<int8_t> h_tag_hpb;
+    std::vector<float> h_tag_sim;
+    uint64_t n_wd_items = 0;
+
     // ---- graph ----
     std::vector<int32_t> h_aln_read;                // stage-C alignments (batch index), BAM order
     std::vector<uint8_t> h_read_dead;               // per read: removed by the overlap filter
@@ -207,7 +249,9 @@ struct lps_ctx {
 
 // kernels (k_*.cu)
 int lps_launch_annotate(lps_ctx *ctx);
-int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t = nullptr, int want_calls = 0);
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t = nullptr, int want_calls = 0,
+                            int mode = -1 /* LPS_MODE_*; -1: PHASE when t is null, GERMLINE otherwise */);
+int lps_launch_window_diff(lps_ctx *ctx, int have_reference);
 int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p);
 int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p);
 // host restatements that sit between the kernels (host_phase.cpp)

@@ -126,6 +126,56 @@ class Context:
             res.update(call_off=g(o.call_off, n + 1, np.uint64), calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE))
         return res
 
+    # ---- somatic family ----
+    def set_tumor_variants(self, tumor_struct):
+        self._check(self.lib.lps_contig_set_tumor_variants(self.h, C.byref(tumor_struct)))
+
+    @staticmethod
+    def _read_tags(t):
+        g = _ffi.as_np
+        n = t.n_reads
+        return dict(category=g(t.category, n, np.uint8), read_hp=g(t.read_hp, n, np.int8), ps=g(t.ps, n, np.int32), pq=g(t.pq, n, np.int32),
+                    h1=g(t.h1, n, np.int32), h2=g(t.h2, n, np.int32), h3=g(t.h3, n, np.int32), n_ps=g(t.n_ps, n, np.uint8),
+                    end_pos=g(t.end_pos, n, np.int32), read_len=g(t.read_len, n, np.int32))
+
+    def _extract(self, fn, tparams, tumor):
+        o = _ffi.LpsExtractResult()
+        self._check(fn(self.h, C.byref(tparams), C.byref(o)))
+        g = _ffi.as_np
+        nt = o.n_tum
+        res = self._read_tags(o.reads)
+        res.update(n_tum=nt, tum_var=g(o.tum_var, nt, np.int32), pos_base=g(o.pos_base, nt * 15, np.int32).reshape(nt, 15),
+                   read_hp_count=g(o.read_hp_count, nt * 9, np.int32).reshape(nt, 9))
+        if tumor:
+            res.update(somatic_read_hp_count=g(o.somatic_read_hp_count, nt * 9, np.int32).reshape(nt, 9),
+                       case_count=g(o.case_count, nt * 6, np.int32).reshape(nt, 6),
+                       allele_count=g(o.allele_count, nt * 2, np.int32).reshape(nt, 2),
+                       window_hist=g(o.window_hist, nt * 2 * _ffi.WINDOW_BINS, np.int32).reshape(nt, 2, _ffi.WINDOW_BINS),
+                       n_window_items=int(o.n_window_items), call_off=g(o.call_off, o.reads.n_reads + 1, np.uint64),
+                       calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE))
+        return res
+
+    def extract_normal(self, tparams):
+        return self._extract(self.lib.lps_extract_normal, tparams, False)
+
+    def extract_tumor(self, tparams):
+        return self._extract(self.lib.lps_extract_tumor, tparams, True)
+
+    def somatic_tag_reads(self, tparams, want_calls=True):
+        o = _ffi.LpsSomaticTagResult()
+        self._check(self.lib.lps_somatic_tag_reads(self.h, C.byref(tparams), int(want_calls), C.byref(o)))
+        g = _ffi.as_np
+        n, nt = o.reads.n_reads, o.n_tum
+        res = self._read_tags(o.reads)
+        res.update(hp_before=g(o.hp_before, n, np.int8), derive_similarity=g(o.derive_similarity, n, np.float32), n_tum=nt,
+                   tum_var=g(o.tum_var, nt, np.int32), cover_start=g(o.cover_start, nt, np.int32), cover_end=g(o.cover_end, nt, np.int32),
+                   stats={**{k: getattr(o, k) for k in _ffi.SOMATIC_COUNTERS}, **{f"hp{k}": o.total_hp[k] for k in range(9)}})
+        for k in ("hp_before_count", "hp_after_count", "h3_before_count", "h3_after_count"):
+            res[k] = g(getattr(o, k), nt * 9, np.int32).reshape(nt, 9)
+        if want_calls:
+            res.update(call_off=g(o.call_off, n + 1, np.uint64), calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE))
+        return res
+
     def stats(self):
         s = _ffi.LpsStats()
         self._check(self.lib.lps_get_stats(self.h, C.byref(s)))
@@ -185,3 +235,44 @@ class GermlineHaplotagChrProcessor:
         self._bs = contig.batch_struct()
         self.ctx.submit(self._bs)
         return self.ctx.tag_reads(self.tparams, want_calls)
+
+
+class _SomaticChrProcessor:
+    """Shared set-up of the three somatic processors: reference string, union variant map (NORMAL + TUMOR records)."""
+
+    def __init__(self, ctx, contig, tparams):
+        self.ctx, self.tparams = ctx, tparams
+        ctx.set_reference(contig.ref if tparams.have_reference else b"")
+        self._vs, self._ts = contig.variants_struct(), contig.tumor_struct()
+        ctx.set_variants(self._vs, 0)
+        ctx.set_tumor_variants(self._ts)
+
+    def _submit(self, contig):
+        self._bs = contig.batch_struct()
+        self.ctx.submit(self._bs)
+
+
+class ExtractNorDataChrProcessor(_SomaticChrProcessor):
+    """Mirror of reference ExtractNorDataChrProcessor (src/somatic_haplotag/SomaticVarCaller.h:235-259): processSingleChrom
+    over the NORMAL BAM's alignments of one contig -> PosBase counters per tumor position."""
+
+    def processSingleChrom(self, contig):
+        self._submit(contig)
+        return self.ctx.extract_normal(self.tparams)
+
+
+class ExtractTumDataChrProcessor(_SomaticChrProcessor):
+    """Mirror of reference ExtractTumDataChrProcessor (SomaticVarCaller.h:332-373) over the TUMOR BAM's alignments."""
+
+    def processSingleChrom(self, contig):
+        self._submit(contig)
+        return self.ctx.extract_tumor(self.tparams)
+
+
+class SomaticHaplotagChrProcessor(_SomaticChrProcessor):
+    """Mirror of reference SomaticHaplotagChrProcessor (src/somatic_haplotag/SomaticHaplotagProcess.h:67-122): HP:Z / PS:i / PQ:i
+    of every TUMOR alignment plus the per-position haplotype distributions before / after inheritance."""
+
+    def processSingleChrom(self, contig, want_calls=True):
+        self._submit(contig)
+        return self.ctx.somatic_tag_reads(self.tparams, want_calls)

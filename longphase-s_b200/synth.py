@@ -19,13 +19,13 @@ class SynthParams(C.Structure):
                 ("ins_rate", C.c_double), ("del_rate", C.c_double), ("clip_frac", C.c_double),
                 ("supp_frac", C.c_double), ("sec_frac", C.c_double), ("dup_frac", C.c_double),
                 ("noseq_frac", C.c_double), ("lowq_mapq_frac", C.c_double), ("zero_mapq_frac", C.c_double),
-                ("tumor", C.c_int32)]
+                ("tumor", C.c_int32), ("somatic_rate", C.c_double), ("purity", C.c_double), ("read_seed", C.c_uint64)]
 
 
 class SynthOut(C.Structure):
     _fields_ = [("ref_len", C.c_int64), ("ref", C.POINTER(C.c_char)), ("n_var", C.c_int32), ("var_pos", _ffi.i32p),
                 ("var_ref0", _ffi.u8p), ("var_alt0", _ffi.u8p), ("var_ref_len", _ffi.u16p), ("var_alt_len", _ffi.u16p),
-                ("var_hp1_is_alt", _ffi.u8p), ("var_str_off", _ffi.u32p), ("var_str", C.POINTER(C.c_char)),
+                ("var_hp1_is_alt", _ffi.u8p), ("var_is_somatic", _ffi.u8p), ("var_str_off", _ffi.u32p), ("var_str", C.POINTER(C.c_char)),
                 ("n_reads", C.c_int32), ("ref_start", _ffi.i32p), ("l_qseq", _ffi.i32p), ("n_cigar", _ffi.u32p),
                 ("cigar_off", _ffi.u64p), ("seq_off", _ffi.u64p), ("qual_off", _ffi.u64p), ("flag", _ffi.u16p),
                 ("mapq", _ffi.u8p), ("name_rank", _ffi.i32p), ("hap", _ffi.u8p), ("cigar", _ffi.u32p),
@@ -83,6 +83,7 @@ class Contig:
             self.var_ref_len = g(o.var_ref_len, nv, np.uint16)
             self.var_alt_len = g(o.var_alt_len, nv, np.uint16)
             self.var_hp1_is_alt = g(o.var_hp1_is_alt, nv, np.uint8)
+            self.var_is_somatic = g(o.var_is_somatic, nv, np.uint8)
             self.var_str_off = g(o.var_str_off, nv + 1, np.uint32)
             self.var_str = C.string_at(o.var_str, int(self.var_str_off[-1]) if nv else 0)
             self.ref_start = g(o.ref_start, nr, np.int32)
@@ -131,6 +132,79 @@ class Contig:
             blob += self.var_str[o:e]
             off.append(len(blob))
         c.var_str, c.var_str_off = blob, np.array(off, np.uint32)
+        return c
+
+    def somatic_union(self, seed=1, block=50, nor_frac=0.9, germ_in_tumor=0.15):
+        """The contig as `somatic_haplotag` sees it: a union variant table (std::map<int, MultiGenomeVar>) built from the
+        generator's truth.  NORMAL records = phased germline variants (true phase, artificial phase sets of `block`
+        variants); TUMOR records = every somatic variant plus a share of the germline ones, with mixed genotypes.  Positions
+        that end up in neither VCF are dropped.  Reads are shared with self."""
+        import copy
+        rng = np.random.default_rng(seed)
+        n = self.n_var
+        som = self.var_is_somatic != 0
+        nor = (~som) & (rng.random(n) < nor_frac)
+        tum = som | ((~som) & (rng.random(n) < germ_in_tumor))
+        keep = np.nonzero(nor | tum)[0]
+        c = copy.copy(self)
+        c.n_var = len(keep)
+        for k in ("var_pos", "var_ref0", "var_alt0", "var_ref_len", "var_alt_len", "var_hp1_is_alt", "var_is_somatic"):
+            setattr(c, k, np.ascontiguousarray(getattr(self, k)[keep]))
+        blk = (np.arange(c.n_var) // block) * block
+        c.var_ps = np.ascontiguousarray((c.var_pos[blk] + 1).astype(np.int32))
+        c.var_gt_kind = np.ones(c.n_var, np.uint8)
+        blob, off = b"", [0]
+        for i in keep:
+            o, e = int(self.var_str_off[i]), int(self.var_str_off[i + 1])
+            blob += self.var_str[o:e]
+            off.append(len(blob))
+        c.var_str, c.var_str_off = blob, np.array(off, np.uint32)
+        c.nor_present = np.ascontiguousarray(nor[keep].astype(np.uint8))
+        c.tum_present = np.ascontiguousarray(tum[keep].astype(np.uint8))
+        m = c.n_var
+        ksom = c.var_is_somatic != 0
+        u = rng.random(m)
+        c.tum_gt = np.where(ksom, np.where(u < 0.7, 2, np.where(u < 0.8, 3, 1)), 1 + (u * 3).astype(np.int64)).astype(np.uint8)
+        c.tum_gt[c.tum_present == 0] = 0
+        c.tum_hp1_is_alt = np.ascontiguousarray(c.var_hp1_is_alt.copy())
+        c.tum_ps = np.where(c.tum_gt == 1, c.var_ps, -1).astype(np.int32)
+        c.tum_ref0, c.tum_alt0 = c.var_ref0.copy(), c.var_alt0.copy()
+        c.tum_ref_len, c.tum_alt_len = c.var_ref_len.copy(), c.var_alt_len.copy()
+        # a few positions where the tumor VCF reports another ALT base than the normal VCF
+        snp = (c.var_ref_len == 1) & (c.var_alt_len == 1) & (c.tum_present != 0) & (c.nor_present != 0) & (rng.random(m) < 0.1)
+        tblob, toff = b"", [0]
+        for i in range(m):
+            o, e = int(c.var_str_off[i]), int(c.var_str_off[i + 1])
+            rec = c.var_str[o:e]
+            if snp[i]:
+                alt = next(x for x in b"ACGT" if x != c.var_ref0[i] and x != c.var_alt0[i])
+                c.tum_alt0[i] = alt
+                rec = bytes([c.var_ref0[i], 0, alt, 0])
+            tblob += rec
+            toff.append(len(tblob))
+        c.tum_str, c.tum_str_off = tblob, np.array(toff, np.uint32)
+        # the caller's verdict (SomaticVarCaller::getSomaticFlag): most true somatic positions, a few germline tumor-only ones
+        c.is_somatic = (((ksom & (rng.random(m) < 0.85)) | (~ksom & (c.nor_present == 0) & (rng.random(m) < 0.05)))
+                        & (c.tum_present != 0)).astype(np.uint8)
+        c.derive_hp = np.where(c.is_somatic != 0, rng.integers(0, 3, m), 0).astype(np.int8)
+        return c
+
+    def tumor_struct(self):
+        P = _ffi.ptr
+        return _ffi.LpsTumorVariants(n=self.n_var, nor_present=P(self.nor_present, _ffi.u8p), tum_present=P(self.tum_present, _ffi.u8p),
+                                     ref0=P(self.tum_ref0, _ffi.u8p), alt0=P(self.tum_alt0, _ffi.u8p),
+                                     ref_len=P(self.tum_ref_len, _ffi.u16p), alt_len=P(self.tum_alt_len, _ffi.u16p),
+                                     gt_kind=P(self.tum_gt, _ffi.u8p), hp1_is_alt=P(self.tum_hp1_is_alt, _ffi.u8p),
+                                     ps=P(self.tum_ps, _ffi.i32p), is_somatic=P(self.is_somatic, _ffi.u8p),
+                                     derive_hp=P(self.derive_hp, _ffi.i8p))
+
+    def with_reads_of(self, other):
+        """Same variant tables, the read batch of `other` (a contig generated with the same seed and another read_seed)."""
+        import copy
+        c = copy.copy(self)
+        for k in ("n_reads", "ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "hap",
+                  "cigar", "seq4", "qual", "names"):
+            setattr(c, k, getattr(other, k))
         return c
 
     def batch_struct(self):

@@ -40,6 +40,9 @@ typedef struct {
     double lowq_mapq_frac; /* MAPQ 1-59                                                   */
     double zero_mapq_frac; /* MAPQ 0                                                      */
     int32_t tumor;         /* 0: germline reads only                                      */
+    double somatic_rate;   /* somatic variants per bp (tumor-only, on one haplotype)      */
+    double purity;         /* fraction of reads that come from tumor cells               */
+    uint64_t read_seed;    /* seed of the read streams (0: same as seed); reference and variants depend on `seed` only */
 } synth_params;
 
 typedef struct {
@@ -52,6 +55,7 @@ typedef struct {
     uint8_t *var_ref0, *var_alt0;
     uint16_t *var_ref_len, *var_alt_len;
     uint8_t *var_hp1_is_alt;    /* phase: haplotype 0 carries ALT                         */
+    uint8_t *var_is_somatic;    /* 1: tumor-only variant, present on haplotype (hp1_is_alt ? 0 : 1) of tumor cells */
     uint32_t *var_str_off;      /* [n_var+1] offsets into var_str: REF '\0' ALT '\0'       */
     char *var_str;
     /* reads */
@@ -150,7 +154,7 @@ static inline char other_base(rng_t *r, char c) {
 }
 
 /* walk the reference from `start` for `span` bases on haplotype `hap`, appending M/I/D ops */
-static void gen_aligned(const synth_params *p, const synth_out *o, rng_t *r, rbuf *b, int64_t start, int64_t span, int hap) {
+static void gen_aligned(const synth_params *p, const synth_out *o, rng_t *r, rbuf *b, int64_t start, int64_t span, int hap, int tumor_cell) {
     int64_t end = start + span;
     if (end > o->ref_len) end = o->ref_len;
     /* first variant >= start */
@@ -185,6 +189,7 @@ static void gen_aligned(const synth_params *p, const synth_out *o, rng_t *r, rbu
         }
         if (pos == next_var) {
             int carries_alt = (o->var_hp1_is_alt[vi] != 0) == (hap == 0);
+            if (o->var_is_somatic[vi] && !tumor_cell) carries_alt = 0;
             int rl = o->var_ref_len[vi], al = o->var_alt_len[vi];
             const char *rs = o->var_str + o->var_str_off[vi];
             const char *as = rs + rl + 1;
@@ -234,7 +239,7 @@ static void gen_aligned(const synth_params *p, const synth_out *o, rng_t *r, rbu
 
 typedef struct {
     int64_t start; int64_t span; int hap; uint16_t flag; uint8_t mapq; int clip_front, clip_back; int hard; int noseq;
-    uint64_t name_id; uint64_t stream;
+    uint64_t name_id; uint64_t stream; int tumor_cell;
 } aln_plan;
 
 static int cmp_plan(const void *a, const void *b) {
@@ -264,7 +269,7 @@ void synth_default_params(synth_params *p) {
 
 void synth_free(synth_out *o) {
     free(o->ref); free(o->var_pos); free(o->var_ref0); free(o->var_alt0); free(o->var_ref_len); free(o->var_alt_len);
-    free(o->var_hp1_is_alt); free(o->var_str_off); free(o->var_str);
+    free(o->var_hp1_is_alt); free(o->var_is_somatic); free(o->var_str_off); free(o->var_str);
     free(o->ref_start); free(o->l_qseq); free(o->n_cigar); free(o->cigar_off); free(o->seq_off); free(o->qual_off);
     free(o->flag); free(o->mapq); free(o->name_rank); free(o->hap); free(o->cigar); free(o->seq4); free(o->qual); free(o->names);
     memset(o, 0, sizeof(*o));
@@ -297,22 +302,25 @@ int synth_generate(const synth_params *p, synth_out *o) {
     /* ---- variants (stream 2) ---- */
     rng_seed(&r, p->seed, 2);
     {
-        int cap = (int)(L * p->variant_rate * 1.3) + 64;
+        int cap = (int)(L * (p->variant_rate + p->somatic_rate) * 1.3) + 64;
+        const double total_rate = p->variant_rate + p->somatic_rate;
         o->var_pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
         o->var_ref0 = (uint8_t *)malloc((size_t)cap); o->var_alt0 = (uint8_t *)malloc((size_t)cap);
         o->var_ref_len = (uint16_t *)malloc(2 * (size_t)cap); o->var_alt_len = (uint16_t *)malloc(2 * (size_t)cap);
         o->var_hp1_is_alt = (uint8_t *)malloc((size_t)cap);
+        o->var_is_somatic = (uint8_t *)calloc((size_t)cap, 1);
         o->var_str_off = (uint32_t *)malloc(4 * ((size_t)cap + 1));
         o->var_str = (char *)malloc((size_t)cap * 16);
         uint32_t so = 0;
         int n = 0;
         int64_t pos = 50, last_end = 0;
         while (n + 1 < cap) {
-            pos += (int64_t)(-log(1.0 - rng_u(&r)) / p->variant_rate) + 1;
+            pos += (int64_t)(-log(1.0 - rng_u(&r)) / total_rate) + 1;
             if (pos + 40 >= L) break;
             int is_indel = rng_u(&r) < p->indel_frac;
             o->var_pos[n] = (int32_t)pos;
             o->var_hp1_is_alt[n] = (uint8_t)(rng_next(&r) >> 63);
+            o->var_is_somatic[n] = (uint8_t)(p->somatic_rate > 0 && rng_u(&r) < p->somatic_rate / total_rate);
             o->var_str_off[n] = so;
             if (!is_indel) {
                 char rc = o->ref[pos], ac = other_base(&r, rc);
@@ -377,7 +385,8 @@ int synth_generate(const synth_params *p, synth_out *o) {
         o->n_var = n;
     }
     /* ---- alignment plan (stream 3) ---- */
-    rng_seed(&r, p->seed, 3);
+    const uint64_t rseed = p->read_seed ? p->read_seed : p->seed;
+    rng_seed(&r, rseed, 3);
     double mu = log(p->mean_len) - 0.5 * p->sigma * p->sigma;
     int64_t n_primary = (int64_t)(p->depth * (double)L / p->mean_len);
     if (n_primary < 1) n_primary = 1;
@@ -392,6 +401,7 @@ int synth_generate(const synth_params *p, synth_out *o) {
         a.span = (int64_t)len;
         a.start = (int64_t)(rng_u(&r) * (double)(L - a.span));
         a.hap = (int)(rng_next(&r) >> 63);
+        a.tumor_cell = p->purity > 0 && rng_u(&r) < p->purity;
         double u = rng_u(&r);
         a.mapq = u < p->zero_mapq_frac ? 0 : (u < p->zero_mapq_frac + p->lowq_mapq_frac ? (uint8_t)(1 + rng_below(&r, 59)) : 60);
         a.flag = (rng_next(&r) >> 63) ? 16 : 0;
@@ -437,14 +447,14 @@ int synth_generate(const synth_params *p, synth_out *o) {
 #pragma omp parallel for schedule(dynamic, 64)
     for (int32_t i = 0; i < n; i++) {
         const aln_plan *a = &plan[i];
-        rng_t rr; rng_seed(&rr, p->seed, a->stream);
+        rng_t rr; rng_seed(&rr, rseed, a->stream);
         rbuf *b = &bufs[i];
         int clip_op = a->hard ? 5 : 4;
         if (a->clip_front) {
             rb_op(b, clip_op, a->clip_front);
             if (!a->hard) for (int k = 0; k < a->clip_front; k++) rb_base(b, &rr, ACGT[rng_below(&rr, 4)]);
         }
-        gen_aligned(p, o, &rr, b, a->start, a->span, a->hap);
+        gen_aligned(p, o, &rr, b, a->start, a->span, a->hap, a->tumor_cell);
         if (a->clip_back) {
             rb_op(b, clip_op, a->clip_back);
             if (!a->hard) for (int k = 0; k < a->clip_back; k++) rb_base(b, &rr, ACGT[rng_below(&rr, 4)]);
@@ -469,7 +479,7 @@ int synth_generate(const synth_params *p, synth_out *o) {
         uint8_t *s = o->seq4 + o->seq_off[i];
         for (int k = 0; k + 1 < b->nq; k += 2) s[k >> 1] = (uint8_t)((b->bases[k] << 4) | b->bases[k + 1]);
         if (b->nq & 1) s[b->nq >> 1] = (uint8_t)(b->bases[b->nq - 1] << 4);
-        make_name(p->seed, a->name_id, o->names + (size_t)i * 40);
+        make_name(rseed, a->name_id, o->names + (size_t)i * 40);
         free(b->cig); free(b->bases); free(b->quals);
     }
     free(bufs);

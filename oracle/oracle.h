@@ -98,6 +98,29 @@ typedef struct {
 int orc_tag_reads(const lps_read_batch *b, const lps_variants *v, const uint8_t *hom, const lps_tag_params *p, orc_tags *out);
 void orc_tags_free(orc_tags *t);
 
+/* somatic family (oracle_somatic.c): the two extract passes of SomaticVarCaller::extractSomaticData and somatic tagging.
+ * Per-position arrays are indexed by tumor slot (ascending tumor-present variants), as in include/lps.h.            */
+enum { ORC_SOM_EXTRACT_NORMAL = 0, ORC_SOM_EXTRACT_TUMOR = 1, ORC_SOM_TAG = 2 };
+typedef struct {
+    int32_t n_reads, n_tum;
+    int32_t *tum_var;
+    uint8_t *category;
+    int8_t *read_hp, *hp_before;
+    int32_t *ps, *pq, *h1, *h2, *h3;
+    uint8_t *n_ps;
+    int32_t *end_pos, *read_len;
+    float *derive_similarity;
+    int32_t *pos_base, *read_hp_count, *somatic_read_hp_count, *case_count, *allele_count, *window_hist;
+    int32_t *hp_before_count, *hp_after_count, *h3_before_count, *h3_after_count, *cover_start, *cover_end;
+    uint64_t n_window_items;
+    uint64_t n_calls;
+    uint64_t *call_off;
+    lps_call *calls;
+} orc_somatic_out;
+int orc_somatic(int mode, const lps_read_batch *b, const lps_variants *v, const lps_tumor_variants *t, const uint8_t *hom,
+                const char *ref, int64_t ref_len, const lps_tag_params *p, orc_somatic_out *out);
+void orc_somatic_free(orc_somatic_out *o);
+
 /* std::sort with the reference's comparator (src/shared/Util.h:100-106, Util.cpp:3-5): the order of
  * equal positions inside a merged read is whatever libstdc++'s introsort leaves, so the oracle calls
  * the same std::sort.  perm[] is permuted alongside pos[].                                        */

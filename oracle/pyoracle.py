@@ -91,6 +91,26 @@ class TapTagOut(C.Structure):
                 ("ps_count", i32p), ("stats", C.c_int64 * 14), ("t_total", C.c_double)]
 
 
+class OrcSomaticOut(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_tum", C.c_int32), ("tum_var", i32p), ("category", u8p), ("read_hp", i8p), ("hp_before", i8p),
+                ("ps", i32p), ("pq", i32p), ("h1", i32p), ("h2", i32p), ("h3", i32p), ("n_ps", u8p), ("end_pos", i32p),
+                ("read_len", i32p), ("derive_similarity", f32p), ("pos_base", i32p), ("read_hp_count", i32p),
+                ("somatic_read_hp_count", i32p), ("case_count", i32p), ("allele_count", i32p), ("window_hist", i32p),
+                ("hp_before_count", i32p), ("hp_after_count", i32p), ("h3_before_count", i32p), ("h3_after_count", i32p),
+                ("cover_start", i32p), ("cover_end", i32p), ("n_window_items", C.c_uint64), ("n_calls", C.c_uint64),
+                ("call_off", u64p), ("calls", callp)]
+
+
+class TapSomIn(C.Structure):
+    _fields_ = [("chr", C.c_char_p), ("ref", C.c_char_p), ("ref_len", C.c_int64), ("n_var", C.c_int32), ("var_pos", i32p),
+                ("var_str_off", _ffi.u32p), ("var_str", C.c_char_p), ("var_hp1_is_alt", u8p), ("var_ps", i32p), ("nor_gt", u8p),
+                ("nor_present", u8p), ("tum_present", u8p), ("tum_str_off", _ffi.u32p), ("tum_str", C.c_char_p), ("tum_gt", u8p),
+                ("tum_hp1_is_alt", u8p), ("tum_ps", i32p), ("is_somatic", u8p), ("derive_hp", i8p), ("batch", _ffi.LpsReadBatch),
+                ("names", C.c_char_p), ("name_stride", C.c_int32), ("p", _ffi.LpsTagParams), ("stats_out", C.POINTER(C.c_int64))]
+
+
+SOM_MODES = {"extract_normal": 0, "extract_tumor": 1, "somatic_tag": 2}
+
 _orc = None
 _tap = None
 
@@ -112,6 +132,9 @@ def oracle_lib():
         lib.orc_tag_reads.argtypes = [C.POINTER(_ffi.LpsReadBatch), C.POINTER(_ffi.LpsVariants), u8p, C.POINTER(_ffi.LpsTagParams),
                                       C.POINTER(OrcTags)]
         lib.orc_tags_free.argtypes = [C.POINTER(OrcTags)]
+        lib.orc_somatic.argtypes = [C.c_int, C.POINTER(_ffi.LpsReadBatch), C.POINTER(_ffi.LpsVariants), C.POINTER(_ffi.LpsTumorVariants),
+                                    u8p, C.c_char_p, C.c_int64, C.POINTER(_ffi.LpsTagParams), C.POINTER(OrcSomaticOut)]
+        lib.orc_somatic_free.argtypes = [C.POINTER(OrcSomaticOut)]
         _orc = lib
     return _orc
 
@@ -131,6 +154,9 @@ def tap_lib():
         lib.ref_tap_tag.argtypes = [C.POINTER(TapTagIn), C.POINTER(TapTagOut)]
         lib.ref_tap_tag.restype = C.c_int
         lib.ref_tap_tag_free.argtypes = [C.POINTER(TapTagOut)]
+        lib.ref_tap_somatic.argtypes = [C.c_int, C.POINTER(TapSomIn), C.POINTER(OrcSomaticOut)]
+        lib.ref_tap_somatic.restype = C.c_int
+        lib.ref_tap_somatic_free.argtypes = [C.POINTER(OrcSomaticOut)]
         _tap = lib
     return _tap
 
@@ -299,3 +325,62 @@ class ReferenceTag:
         self.stats = dict(zip(_ffi.TAG_COUNTERS, list(out.stats)))
         self.t_total = out.t_total
         lib.ref_tap_tag_free(C.byref(out))
+
+
+def _somatic_fields(self, o):
+    n, nt = o.n_reads, o.n_tum
+    self.n_reads, self.n_tum = n, nt
+    self.tum_var = g(o.tum_var, nt, np.int32)
+    self.category = g(o.category, n, np.uint8)
+    self.read_hp, self.hp_before = g(o.read_hp, n, np.int8), g(o.hp_before, n, np.int8)
+    for k in ("ps", "pq", "h1", "h2", "h3", "end_pos", "read_len"):
+        setattr(self, k, g(getattr(o, k), n, np.int32))
+    self.n_ps = g(o.n_ps, n, np.uint8)
+    self.derive_similarity = g(o.derive_similarity, n, np.float32)
+    self.pos_base = g(o.pos_base, nt * 15, np.int32).reshape(nt, 15)
+    for k in ("read_hp_count", "somatic_read_hp_count", "hp_before_count", "hp_after_count", "h3_before_count", "h3_after_count"):
+        setattr(self, k, g(getattr(o, k), nt * 9, np.int32).reshape(nt, 9))
+    self.case_count = g(o.case_count, nt * 6, np.int32).reshape(nt, 6)
+    self.allele_count = g(o.allele_count, nt * 2, np.int32).reshape(nt, 2)
+    self.window_hist = g(o.window_hist, nt * 2 * 201, np.int32).reshape(nt, 2, 201)
+    self.cover_start, self.cover_end = g(o.cover_start, nt, np.int32), g(o.cover_end, nt, np.int32)
+    self.n_window_items = int(o.n_window_items)
+    self.call_off = g(o.call_off, n + 1, np.uint64)
+    self.calls = g(o.calls, o.n_calls, _ffi.CALL_DTYPE)
+
+
+class OracleSomatic:
+    """oracle_somatic.c on a union contig (synth.Contig.somatic_union): mode in SOM_MODES."""
+
+    def __init__(self, contig, tparams, mode):
+        lib = oracle_lib()
+        self.notes = Notes(contig, False)
+        vs, bs, ts = contig.variants_struct(), contig.batch_struct(), contig.tumor_struct()
+        o = OrcSomaticOut()
+        self.rc = lib.orc_somatic(SOM_MODES[mode], C.byref(bs), C.byref(vs), C.byref(ts), _ffi.ptr(self.notes.hom, u8p), contig.ref,
+                                  len(contig.ref), C.byref(tparams), C.byref(o))
+        _somatic_fields(self, o)
+        lib.orc_somatic_free(C.byref(o))
+
+
+class ReferenceSomatic:
+    """The UNMODIFIED reference's extract / somatic-tagging objects on a union contig (oracle/ref_tap_somatic.cpp).
+    Per-read values the reference keeps in locals come back as -1 (h1/h2/h3/end_pos/read_len), 255 (n_ps)."""
+
+    def __init__(self, contig, tparams, mode, chr_name="chrS"):
+        lib = tap_lib()
+        P = _ffi.ptr
+        stats = (C.c_int64 * 22)()
+        tin = TapSomIn(chr=chr_name.encode(), ref=contig.ref, ref_len=len(contig.ref), n_var=contig.n_var, var_pos=P(contig.var_pos, i32p),
+                       var_str_off=P(contig.var_str_off, _ffi.u32p), var_str=contig.var_str, var_hp1_is_alt=P(contig.var_hp1_is_alt, u8p),
+                       var_ps=P(contig.var_ps, i32p), nor_gt=P(contig.var_gt_kind, u8p), nor_present=P(contig.nor_present, u8p),
+                       tum_present=P(contig.tum_present, u8p), tum_str_off=P(contig.tum_str_off, _ffi.u32p), tum_str=contig.tum_str,
+                       tum_gt=P(contig.tum_gt, u8p), tum_hp1_is_alt=P(contig.tum_hp1_is_alt, u8p), tum_ps=P(contig.tum_ps, i32p),
+                       is_somatic=P(contig.is_somatic, u8p), derive_hp=P(contig.derive_hp, i8p), batch=contig.batch_struct(),
+                       names=contig.names, name_stride=contig.NAME_STRIDE, p=tparams,
+                       stats_out=C.cast(stats, C.POINTER(C.c_int64)))
+        o = OrcSomaticOut()
+        self.rc = lib.ref_tap_somatic(SOM_MODES[mode], C.byref(tin), C.byref(o))
+        _somatic_fields(self, o)
+        self.stats = dict(zip(_ffi.SOMATIC_COUNTERS + [f"hp{k}" for k in range(9)], list(stats)))
+        lib.ref_tap_somatic_free(C.byref(o))

@@ -94,6 +94,34 @@ typedef struct {
 int ref_tap_tag(const tap_tag_in *in, tap_tag_out *out);
 void ref_tap_tag_free(tap_tag_out *out);
 
+/* ---- somatic family tap (ref_tap_somatic.cpp); the output is oracle.h's orc_somatic_out ---- */
+#define TAP_SOM_STATS 22   /* the 13 ReadStatistics counters of lps_somatic_tag_result followed by totalHpCount[0..8] */
+typedef struct {
+    const char *chr;
+    const char *ref;
+    int64_t ref_len;
+    int32_t n_var;
+    const int32_t *var_pos;
+    const uint32_t *var_str_off;     /* NORMAL record: REF '\0' ALT '\0' */
+    const char *var_str;
+    const uint8_t *var_hp1_is_alt;
+    const int32_t *var_ps;
+    const uint8_t *nor_gt;           /* NULL: every NORMAL record is PHASED_HETERO */
+    const uint8_t *nor_present;      /* NULL: everywhere */
+    const uint8_t *tum_present;
+    const uint32_t *tum_str_off;     /* TUMOR record strings, same layout */
+    const char *tum_str;
+    const uint8_t *tum_gt, *tum_hp1_is_alt;
+    const int32_t *tum_ps;
+    const uint8_t *is_somatic;
+    const int8_t *derive_hp;
+    lps_read_batch batch;
+    const char *names;
+    int32_t name_stride;
+    lps_tag_params p;
+    int64_t *stats_out;              /* [TAP_SOM_STATS], written in mode 2 */
+} tap_som_in;
+
 int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out);
 void ref_tap_phase_free(tap_phase_out *out);
 int ref_tap_homopolymer(const char *ref, int64_t len, int pos);
