@@ -49,6 +49,9 @@ struct K1Args {
     uint32_t *ncalls;
     uint8_t *status;
     uint32_t *clip_keys;
+    uint2 *clip_meta;                 // (read, CIGAR index) of every clip event
+    int32_t *abort_of_read;           // CIGAR index at which get_snp dropped the read, INT_MAX otherwise
+    const int32_t *first_var;         // per read: lower_bound of its start in the variant positions
     unsigned long long clip_cap;
     CallCounters *counters;
     // overflow pass
@@ -138,11 +141,11 @@ constexpr uint32_t ADV_LUT = (3u << 0) | (2u << 2) | (1u << 4) | (1u << 6) | (2u
 // op codes that need the slow path: S, H (clips), P, and the unsupported codes 9..15
 constexpr uint32_t RARE_OPS = 0xFE70u;
 
+constexpr int GROUPS_CAP = 384;     // K-op groups indexed per super-chunk (3072 ops); longer reads are walked in several super-chunks
+
 template <int K>
 struct WarpScratch {
-    int r[32 * K + 4];        // reference position at which op j of the chunk starts
-    int q[32 * K + 4];        // query position at which op j of the chunk starts
-    uint32_t op[32 * K + 4];  // the op word itself
+    int2 grp[GROUPS_CAP];     // (reference, query) position at which each group of K consecutive ops starts
     Cand cand[CAND_CAP];
 };
 
@@ -396,40 +399,31 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
     }
 }
 
+// One read, one warp.
+//   phase 1 (streaming): the CIGAR goes through registers in chunks of 32*K ops; per chunk only the per-lane advance sums and
+//     one warp exclusive scan are computed, and the (ref, query) position at which each lane's group of K ops starts is
+//     written to a shared-memory index.  No per-op positions are materialised.
+//   phase 2 (once per super-chunk, i.e. once per read for reads up to 3072 ops): every lane takes one pending variant,
+//     finds its group by binary search in the index, and re-walks the <= K ops of that group (L1/L2 hits: the lines were
+//     streamed moments ago) to get the covering op, its start positions and the op that follows it.
 template <int K, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a) {
-    constexpr bool TAG = MODE != LPS_MODE_PHASE;        // CigarParser::parsingCigar instead of BamParser::get_snp
+__device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S, const int r, Cand *cand, int cand_cap, const int lane,
+                                             const bool overflow_pass) {
+    constexpr bool TAG = MODE != LPS_MODE_PHASE;          // CigarParser::parsingCigar instead of BamParser::get_snp
     constexpr bool SOM = MODE >= LPS_MODE_EXTRACT_NORMAL; // raw 16-byte candidates, resolved by resolve_somatic
-    __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
-    const bool overflow_pass = a.overflow_reads != nullptr;
-    WarpScratch<K> &S = s_all[wib];
-    int r;
-    Cand *cand;
-    int cand_cap;
-    if (!overflow_pass) {
-        if (wid >= a.b.n_reads) return;
-        r = (int)wid;
-        cand = S.cand;
-        cand_cap = CAND_CAP;
-    } else {
-        if (wid >= a.overflow_list_cap) return;
-        r = (int)a.overflow_reads[wid];
-        cand = a.overflow_buf + a.overflow_off[wid];
-        cand_cap = (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]);
-    }
-    if (SOM) cand_cap >>= 1;                            // 16-byte candidates
+    if (SOM) cand_cap >>= 1;                              // 16-byte candidates
     uint4 *cand4 = reinterpret_cast<uint4 *>(cand);
     const int nv = a.v.n;
     const int ref_start = a.b.ref_start[r];
     const int lq = a.b.l_qseq[r];
     const int ncig = (int)a.b.n_cigar[r];
     const int flag = a.b.flag[r];
+    int cur = a.first_var[r];                              // lower_bound(variants, ref_start), from k_first_var
+    const int64_t lo = (int64_t)a.b.cigar_off[r];
     if (!TAG) {
         // iterator region "chr:1-lastSNP" (ParsingBam.cpp:1273) + read filter (:1282-1291)
         if (ref_start >= a.last_var_pos || (int)a.b.mapq[r] < a.mapping_quality || (flag & (0x4 | 0x100 | 0x400))) {
-            if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED; }
+            if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED; a.abort_of_read[r] = INT_MAX; }
             return;
         }
     } else {
@@ -452,13 +446,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
         }
     }
     const int32_t *__restrict__ vpos = a.v.pos;
-    // window of 32 variant positions, one per lane; `cur` is the first pending variant
-    int cur = warp_lower_bound(vpos, nv, ref_start, lane);
-    int win_base = cur;
-    int vwin = (win_base + lane < nv) ? vpos[win_base + lane] : INT_MAX;
-    int win_prev = cur > 0 ? vpos[cur - 1] : INT_MIN;      // position of variant win_base - 1
-
-    const int64_t lo = (int64_t)a.b.cigar_off[r], hi = lo + ncig;
+    const int64_t hi = lo + ncig;
     const int64_t abase = lo & ~(int64_t)3;
     constexpr int CH = 32 * K;
     const uint32_t *__restrict__ cig = a.b.cigar;
@@ -466,173 +454,195 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
 
     int ref_pos = ref_start, qpos = 0;
     int ncand = 0;
-    bool aborted = false, bad = false;
+    bool aborted = false;
+    int abort_op = INT_MAX, bad_op = INT_MAX;
 
     uint32_t nxt_ops[K];
     load_ops<K>(cig, total, abase + (int64_t)lane * K, lo, hi, true, nxt_ops);
-    for (int64_t cb = abase; cb < hi; cb += CH) {
-        uint32_t ops[K];
+    int64_t cb = abase;
+    while (cb < hi) {
+        // ================= phase 1: stream one super-chunk, index the group starts =================
+        const int64_t sc_cb = cb;
+        int k = 0;
+        for (; k < GROUPS_CAP / 32 && cb < hi; k++, cb += CH) {
+            uint32_t ops[K];
 #pragma unroll
-        for (int j = 0; j < K; j++) ops[j] = nxt_ops[j];
-        if (cb + CH < hi) {
-            const bool edge = (cb + 2 * CH > hi) || ((uint64_t)(cb + 2 * CH) > total);
-            load_ops<K>(cig, total, cb + CH + (int64_t)lane * K, lo, hi, edge, nxt_ops);
-        }
-        // ---- per-lane advances; rl/ql = lane-local position of each op start ----
-        int rl[K], ql[K];
-        int rs = 0, qs = 0;
-        unsigned rare = 0;
+            for (int j = 0; j < K; j++) ops[j] = nxt_ops[j];
+            if (cb + CH < hi) {
+                const bool edge = (cb + 2 * CH > hi) || ((uint64_t)(cb + 2 * CH) > total);
+                load_ops<K>(cig, total, cb + CH + (int64_t)lane * K, lo, hi, edge, nxt_ops);
+            }
+            int rs = 0, qs = 0;
+            unsigned rare = 0;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            const unsigned c = ops[j];
-            const unsigned t = ADV_LUT >> ((c << 1) & 30u);
-            const int len = (int)(c >> 4);
-            rl[j] = rs; ql[j] = qs;
-            rs += (int)(t & 1u) * len;
-            qs += (int)((t >> 1) & 1u) * len;
-            rare |= c;                                // op code bits 2..3 set <=> some op code >= 4 (S H P = X or unsupported)
-        }
-        const int rtot = (int)__reduce_add_sync(FULL, (unsigned)rs);
-        const int qtot = (int)__reduce_add_sync(FULL, (unsigned)qs);
-        const int chunk_end = ref_pos + rtot;
-        int abort_op = INT_MAX;
-
-        // ---- variants inside this chunk: every lane takes the variant in its own window slot ----
-        int first_pending = __shfl_sync(FULL, vwin, cur - win_base);
-        if (first_pending < chunk_end) {
-            // exclusive scan of both cursors (one packed scan when both chunk totals fit 16 bits), then publish the
-            // per-op start positions with 128-bit shared stores
-            int r0, q0;
-            if (((unsigned)rtot | (unsigned)qtot) < 65536u) {
-                unsigned pk = (unsigned)rs | ((unsigned)qs << 16);
+            for (int j = 0; j < K; j++) {
+                const unsigned c = ops[j];
+                const unsigned t = ADV_LUT >> ((c << 1) & 30u);
+                const int len = (int)(c >> 4);
+                rs += (int)(t & 1u) * len;
+                qs += (int)((t >> 1) & 1u) * len;
+                rare |= c;                                // op code bits 2..3 set <=> some op code >= 4 (S H P = X or unsupported)
+            }
+            // exclusive scan of both cursors: one packed scan when every lane sum fits 11 bits (so the totals fit 16)
+            int er, eq, rtot, qtot;
+            if (!__any_sync(FULL, (unsigned)(rs | qs) >= 2048u)) {
+                const unsigned pk = (unsigned)rs | ((unsigned)qs << 16);
                 unsigned inc = pk;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    unsigned t = __shfl_up_sync(FULL, inc, d);
+                    const unsigned t = __shfl_up_sync(FULL, inc, d);
                     if (lane >= d) inc += t;
                 }
-                const unsigned exc = inc - pk;
-                r0 = ref_pos + (int)(exc & 0xffffu); q0 = qpos + (int)(exc >> 16);
+                const unsigned exc = inc - pk, tot = __shfl_sync(FULL, inc, 31);
+                er = (int)(exc & 0xffffu); eq = (int)(exc >> 16);
+                rtot = (int)(tot & 0xffffu); qtot = (int)(tot >> 16);
             } else {
                 int ri = rs, qi = qs;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    int t = __shfl_up_sync(FULL, ri, d);
-                    int u = __shfl_up_sync(FULL, qi, d);
+                    const int t = __shfl_up_sync(FULL, ri, d);
+                    const int u = __shfl_up_sync(FULL, qi, d);
                     if (lane >= d) { ri += t; qi += u; }
                 }
-                r0 = ref_pos + ri - rs; q0 = qpos + qi - qs;
+                er = ri - rs; eq = qi - qs;
+                rtot = __shfl_sync(FULL, ri, 31); qtot = __shfl_sync(FULL, qi, 31);
             }
-            {
-                int4 *dr = reinterpret_cast<int4 *>(S.r + lane * K), *dq = reinterpret_cast<int4 *>(S.q + lane * K);
-                uint4 *dop = reinterpret_cast<uint4 *>(S.op + lane * K);
+            S.grp[k * 32 + lane] = make_int2(ref_pos + er, qpos + eq);
+            // ---- clips (S/H longer than 5) and unsupported ops: first / last chunk of a read, normally ----
+            if (__any_sync(FULL, (rare & 0xCu) != 0)) {
+                int rr = ref_pos + er;
 #pragma unroll
-                for (int j = 0; j < K; j += 4) {
-                    dr[j / 4] = make_int4(r0 + rl[j], r0 + rl[j + 1], r0 + rl[j + 2], r0 + rl[j + 3]);
-                    dq[j / 4] = make_int4(q0 + ql[j], q0 + ql[j + 1], q0 + ql[j + 2], q0 + ql[j + 3]);
-                    dop[j / 4] = make_uint4(ops[j], ops[j + 1], ops[j + 2], ops[j + 3]);
+                for (int j = 0; j < K; j++) {
+                    const unsigned op = ops[j] & 15u;
+                    const int len = (int)(ops[j] >> 4);
+                    const int64_t g = cb + (int64_t)lane * K + j;
+                    if (!TAG && (op == 4 || op == 5) && len > 5) {
+                        // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
+                        const unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
+                        if (slot < a.clip_cap) {
+                            a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
+                            a.clip_meta[slot] = make_uint2((unsigned)r, (unsigned)(g - lo));
+                        }
+                    }
+                    if (op > 8) bad_op = min(bad_op, (int)(g - lo));
+                    rr += ((0x18Du >> op) & 1u) ? len : 0;
                 }
             }
-            __syncwarp();
-            while (true) {
-                const int e = lane - (cur - win_base);                 // this lane's variant is cur + e
-                const int vp = vwin;
-                const bool mine = e >= 0 && vp < chunk_end;
-                const unsigned mmask = __ballot_sync(FULL, mine);
-                if (mmask == 0) break;
-                int cand_var = -1; uint32_t cand_x = 0;
-                uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
-                bool ab = false, in_del = false;
-                int my_op_index = 0, my_j = 0;
-                if (mine) {
-                    // covering op: the last op of the chunk that starts at or before vp
-                    int lo_j = 0, hi_j = CH;                            // answer in [lo_j, hi_j)
+            ref_pos += rtot; qpos += qtot;
+        }
+        const int ng = k * 32;
+        __syncwarp();
+
+        // ================= phase 2: every pending variant below ref_pos, one per lane =================
+        while (true) {
+            const int vi = cur + lane;
+            const int vp = vi < nv ? vpos[vi] : INT_MAX;
+            const bool mine = vp < ref_pos;
+            const unsigned mmask = __ballot_sync(FULL, mine);
+            if (mmask == 0) break;
+            int cand_var = -1; uint32_t cand_x = 0;
+            uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+            bool ab = false, in_del = false;
+            int o_r = 0, o_q = 0, opi = 0;
+            if (mine) {
+                // group: the last one that starts at or before vp
+                int g = 0;
 #pragma unroll
-                    for (int step = CH / 2; step >= 1; step >>= 1) {
-                        const int mid = lo_j + step;
-                        if (mid < hi_j && S.r[mid] <= vp) lo_j = mid;
-                    }
-                    const int j = lo_j;
-                    my_j = j;
-                    const unsigned c = S.op[j];
-                    const int o_op = (int)(c & 15u), o_len = (int)(c >> 4), o_r = S.r[j], o_q = S.q[j];
-                    const int vi = win_base + lane;
-                    const int64_t gidx = cb + j;
-                    const int opi = (int)(gidx - lo);
-                    my_op_index = opi;
-                    if (SOM) {
-                        // union map: every variant inside an M/=/X op (HaplotagParsingBam.cpp:585-614) or a D op (:623-631) becomes a
-                        // raw candidate {variant, query index, op index | op start, offset | flags}; the hooks run in resolve_somatic
-                        if (o_op == 0 || o_op == 7 || o_op == 8) {
-                            const int off = vp - o_r;
-                            if (o_q + off < lq) {                      // beyond SEQ the reference reads undefined memory: dropped
-                                unsigned fl = 0;
-                                if (opi + 1 < ncig) {
-                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
-                                    fl = 1u;                           // i + 1 < n_cigar
-                                    if (o_r + o_len - 1 == vp) fl |= (nop == 1u ? 2u : 0u) | (nop == 2u ? 4u : 0u);
-                                }
-                                cand_var = vi;
-                                c4 = make_uint4((unsigned)vi, (unsigned)(o_q + off), (unsigned)opi, (unsigned)off | (fl << 28));
-                            }
-                        } else if (o_op == 2) {
-                            cand_var = vi;
-                            c4 = make_uint4((unsigned)vi, (unsigned)o_q, (unsigned)o_r, 8u << 28);
-                        }
-                    } else if (TAG) {
-                        // CigarParser::parsingCigar M branch (HaplotagParsingBam.cpp:585-614) + judgeSnpHap (HaplotagStrategy.cpp:20-130)
-                        if (o_op == 0 || o_op == 7 || o_op == 8) {
-                            const int off = vp - o_r;
-                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
-                            if (rl == 1 && al == 1) {
-                                // the reference reads seq[query_pos+offset] without a bounds check; past l_qseq that is
-                                // memory of the BAM record (undefined) — such a hit is dropped here
-                                if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
-                            } else if ((rl == 1) != (al == 1)) {
-                                if (opi + 1 < ncig) {
-                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
-                                    const unsigned want = (rl == 1) ? 1u : 2u;
-                                    const bool has = (o_r + o_len - 1 == vp && nop == want);
-                                    const bool h1alt = a.hp1_is_alt[vi] != 0;
-                                    const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;       // lengths of the HP1 / HP2 allele strings
-                                    // read shows the indel: the haplotype whose allele string is not 1 long gets the vote, else the other
-                                    int hpbit = -1;
-                                    if (l1 != 1 && l2 == 1) hpbit = has ? 0 : 1;
-                                    else if (l1 == 1 && l2 != 1) hpbit = has ? 1 : 0;
-                                    cand_var = vi;
-                                    cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
-                                }
-                            }
-                        } else if (o_op == 2) in_del = true;
-                    } else
+                for (int step = 256; step >= 1; step >>= 1) {
+                    const int mid = g + step;
+                    if (mid < ng && S.grp[mid].x <= vp) g = mid;
+                }
+                const int2 gs = S.grp[g];
+                // covering op: the last op of the group that starts at or before vp
+                int wr = gs.x, wq = gs.y;
+                unsigned c = PAD_OP;
+                const int64_t g0 = sc_cb + (int64_t)g * K;
+                int64_t gidx = g0;
+#pragma unroll 1
+                for (int j = 0; j < K; j++) {
+                    const int64_t idx = g0 + j;
+                    if (idx >= hi) break;
+                    if (idx < lo) continue;
+                    const unsigned cc = cig[idx];
+                    if (wr > vp) break;
+                    c = cc; o_r = wr; o_q = wq; gidx = idx;
+                    const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
+                    const int len = (int)(cc >> 4);
+                    wr += (int)(t & 1u) * len;
+                    wq += (int)((t >> 1) & 1u) * len;
+                }
+                const int o_op = (int)(c & 15u), o_len = (int)(c >> 4);
+                opi = (int)(gidx - lo);
+                if (SOM) {
+                    // union map: every variant inside an M/=/X op (HaplotagParsingBam.cpp:585-614) or a D op (:623-631) becomes a
+                    // raw candidate {variant, query index, op index | op start, offset | flags}; the hooks run in resolve_somatic
                     if (o_op == 0 || o_op == 7 || o_op == 8) {
                         const int off = vp - o_r;
-                        if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
-                        else {
-                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
-                            if (rl == 1 && al == 1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
-                            else if ((rl == 1) != (al == 1)) {
-                                if (opi + 1 < ncig) {                                                   // :1470, :1495
-                                    const unsigned nop = (j + 1 < CH ? S.op[j + 1] : cig[gidx + 1]) & 15u;
-                                    const unsigned want = (rl == 1) ? 1u : 2u;                          // I after an insertion anchor, D after a deletion anchor
-                                    const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
-                                    cand_var = vi;
-                                    cand_x = (2u << 30) | ((unsigned)allele << 1) | (unsigned)a.v.danger[vi];
-                                }
+                        if (o_q + off < lq) {                      // beyond SEQ the reference reads undefined memory: dropped
+                            unsigned fl = 0;
+                            if (opi + 1 < ncig) {
+                                const unsigned nop = cig[gidx + 1] & 15u;
+                                fl = 1u;                           // i + 1 < n_cigar
+                                if (o_r + o_len - 1 == vp) fl |= (nop == 1u ? 2u : 0u) | (nop == 2u ? 4u : 0u);
+                            }
+                            cand_var = vi;
+                            c4 = make_uint4((unsigned)vi, (unsigned)(o_q + off), (unsigned)opi, (unsigned)off | (fl << 28));
+                        }
+                    } else if (o_op == 2) {
+                        cand_var = vi;
+                        c4 = make_uint4((unsigned)vi, (unsigned)o_q, (unsigned)o_r, 8u << 28);
+                    }
+                } else if (TAG) {
+                    // CigarParser::parsingCigar M branch (HaplotagParsingBam.cpp:585-614) + judgeSnpHap (HaplotagStrategy.cpp:20-130)
+                    if (o_op == 0 || o_op == 7 || o_op == 8) {
+                        const int off = vp - o_r;
+                        const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                        if (rl == 1 && al == 1) {
+                            // the reference reads seq[query_pos+offset] without a bounds check; past l_qseq that is
+                            // memory of the BAM record (undefined) — such a hit is dropped here
+                            if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                        } else if ((rl == 1) != (al == 1)) {
+                            if (opi + 1 < ncig) {
+                                const unsigned nop = cig[gidx + 1] & 15u;
+                                const unsigned want = (rl == 1) ? 1u : 2u;
+                                const bool has = (o_r + o_len - 1 == vp && nop == want);
+                                const bool h1alt = a.hp1_is_alt[vi] != 0;
+                                const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;       // lengths of the HP1 / HP2 allele strings
+                                // read shows the indel: the haplotype whose allele string is not 1 long gets the vote, else the other
+                                int hpbit = -1;
+                                if (l1 != 1 && l2 == 1) hpbit = has ? 0 : 1;
+                                else if (l1 == 1 && l2 != 1) hpbit = has ? 1 : 0;
+                                cand_var = vi;
+                                cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
                             }
                         }
-                    } else if (o_op == 2) in_del = true;   // decided below, after the neighbour exchange
-                }
-                // D-op rule (:1539-1607): only the FIRST pending variant of the op (previous variant lies before the op)
-                const int prev_pos = __shfl_up_sync(FULL, vwin, 1);
-                if (TAG && !SOM && in_del) {
-                    // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
-                    // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
-                    const int o_r = S.r[my_j], o_q = S.q[my_j];
-                    const int vi = win_base + lane;
-                    const int pv = lane > 0 ? prev_pos : win_prev;
-                    if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
+                    } else if (o_op == 2) in_del = true;
+                } else if (o_op == 0 || o_op == 7 || o_op == 8) {
+                    const int off = vp - o_r;
+                    if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
+                    else {
                         const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                        if (rl == 1 && al == 1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                        else if ((rl == 1) != (al == 1)) {
+                            if (opi + 1 < ncig) {                                                   // :1470, :1495
+                                const unsigned nop = cig[gidx + 1] & 15u;
+                                const unsigned want = (rl == 1) ? 1u : 2u;                          // I after an insertion anchor, D after a deletion anchor
+                                const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
+                                cand_var = vi;
+                                cand_x = (2u << 30) | ((unsigned)allele << 1) | (unsigned)a.v.danger[vi];
+                            }
+                        }
+                    }
+                } else if (o_op == 2) in_del = true;   // decided below, with the position of the previous variant
+            }
+            // D-op rule: only the FIRST pending variant of the op (the previous variant lies before the op)
+            if (!SOM && in_del) {
+                const int pv = vi > 0 ? vpos[vi - 1] : INT_MIN;
+                if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
+                    const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                    if (TAG) {
+                        // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
+                        // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
                         if (rl == 1 && al == 1) {
                             if (o_q < lq) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
                         } else if (rl != 1 && al == 1) {
@@ -643,79 +653,45 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
                             cand_var = vi;
                             cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
                         }
-                    }
-                } else
-                if (in_del) {
-                    const int o_r = S.r[my_j], o_q = S.q[my_j];
-                    const int vi = win_base + lane;
-                    const int pv = lane > 0 ? prev_pos : win_prev;
-                    if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
-                        if (o_q + 1 > lq) ab = true;                                                    // :1559-1561
-                        else {
-                            const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
-                            if (rl == 1 && al == 1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
-                            else if (rl != 1 && al == 1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
-                        }
+                    } else {
+                        // get_snp D branch (:1539-1607)
+                        if (o_q + 1 > lq) ab = true;                                                // :1559-1561
+                        else if (rl == 1 && al == 1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                        else if (rl != 1 && al == 1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
                     }
                 }
-                // the first aborting variant (in order) drops the read; nothing after it matters
-                const unsigned abmask = __ballot_sync(FULL, ab);
-                unsigned keep = __ballot_sync(FULL, cand_var >= 0);
-                if (abmask) {
-                    const int fl = __ffs(abmask) - 1;
-                    abort_op = __shfl_sync(FULL, my_op_index, fl);
-                    aborted = true;
-                    keep &= (1u << fl) - 1u;
-                }
-                if (cand_var >= 0 && ((keep >> lane) & 1u)) {
-                    const int dst = ncand + __popc(keep & ((1u << lane) - 1u));
-                    if (dst < cand_cap) {
-                        if (SOM) cand4[dst] = c4;
-                        else { cand[dst].var = cand_var; cand[dst].x = cand_x; }
-                    }
-                }
-                ncand += __popc(keep);
-                if (aborted) break;
-                // advance the cursor past everything handled; slide the window when it is exhausted
-                const int handled = __popc(mmask);
-                cur += handled;
-                if (cur - win_base >= 32) {
-                    win_prev = __shfl_sync(FULL, vwin, 31);
-                    win_base = cur;
-                    vwin = (win_base + lane < nv) ? vpos[win_base + lane] : INT_MAX;
-                } else break;   // the window still holds a variant >= chunk_end (or the sentinel)
             }
-            __syncwarp();
-        }
-
-        // ---- clips (S/H longer than 5) and unsupported ops ----
-        if (__any_sync(FULL, (rare & 0xCu) != 0)) {
-            int ri = rs;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(FULL, ri, d);
-                if (lane >= d) ri += t;
+            // the first aborting variant (in order) drops the read; nothing after it matters
+            const unsigned abmask = __ballot_sync(FULL, ab);
+            unsigned keep = __ballot_sync(FULL, cand_var >= 0);
+            if (abmask) {
+                const int fl = __ffs(abmask) - 1;
+                abort_op = __shfl_sync(FULL, opi, fl);
+                aborted = true;
+                keep &= (1u << fl) - 1u;
             }
-            int rr = ref_pos + ri - rs;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                const unsigned op = ops[j] & 15u;
-                const int len = (int)(ops[j] >> 4);
-                const int64_t g = cb + (int64_t)lane * K + j;
-                if (!TAG && (op == 4 || op == 5) && len > 5 && (int)(g - lo) < abort_op) {
-                    unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
-                    if (slot < a.clip_cap) a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
+            if (cand_var >= 0 && ((keep >> lane) & 1u)) {
+                const int dst = ncand + __popc(keep & ((1u << lane) - 1u));
+                if (dst < cand_cap) {
+                    if (SOM) cand4[dst] = c4;
+                    else { cand[dst].var = cand_var; cand[dst].x = cand_x; }
                 }
-                if (op > 8 && (int)(g - lo) < abort_op) bad = true;
-                rr += ((0x18Du >> op) & 1u) ? len : 0;
             }
+            ncand += __popc(keep);
+            if (aborted) break;
+            const int handled = __popc(mmask);
+            cur += handled;
+            if (handled < 32) break;
         }
         if (aborted) break;
-        ref_pos = chunk_end;
-        qpos += qtot;
+        __syncwarp();   // the next super-chunk overwrites the index
     }
-    bad = __any_sync(FULL, bad);
+    const bool bad = __any_sync(FULL, bad_op < abort_op);
     if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar, 1u);
+    if (!TAG && lane == 0) {
+        a.abort_of_read[r] = aborted ? abort_op : INT_MAX;
+        if (aborted) atomicAdd(&a.counters->aborted_reads, 1u);
+    }
 
     if (aborted || bad) {
         if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_ABORTED; }
@@ -885,6 +861,54 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a
     }
 }
 
+// Persistent launch: every warp fetches the next read from a global counter until the batch is exhausted, so a CTA is never
+// held hostage by its longest read (read lengths are log-normal).  The overflow pass walks its list one read per warp.
+template <int K, int MODE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a) {
+    __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpScratch<K> &S = s_all[wib];
+    if (a.overflow_reads != nullptr) {
+        const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
+        if (wid >= a.overflow_list_cap) return;
+        process_read<K, MODE>(a, S, (int)a.overflow_reads[wid], a.overflow_buf + a.overflow_off[wid],
+                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true);
+        return;
+    }
+    while (true) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(&a.counters->next_read, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= (unsigned)a.b.n_reads) break;
+        process_read<K, MODE>(a, S, (int)t, S.cand, CAND_CAP, lane, false);
+        __syncwarp();
+    }
+}
+
+// lower_bound of every read start in the variant positions (the reference's stateful firstVariantIter, ParsingBam.cpp:1318-1319,
+// HaplotagParsingBam.cpp:555-563, equals it for a coordinate-sorted batch); one thread per read
+__global__ void k_first_var(int n_reads, const int32_t *__restrict__ ref_start, int nv, const int32_t *__restrict__ vpos,
+                            int32_t *__restrict__ first_var) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int key = ref_start[r];
+    int lo = 0, hi = nv;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (vpos[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    first_var[r] = lo;
+}
+
+// clip events of aborted reads: the reference stops walking at the aborting op, so events at or after it never happened
+__global__ void k_clip_filter(unsigned long long n, uint32_t *__restrict__ keys, const uint2 *__restrict__ meta,
+                              const int32_t *__restrict__ abort_of_read) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 m = meta[i];
+    if ((int)m.y >= abort_of_read[m.x]) keys[i] = 0xFFFFFFFFu;
+}
+
 // scratch pool (allocation order) -> CSR in read order; one warp per read
 __global__ void k_gather_calls(int n_reads, const uint64_t *__restrict__ tmp_start, const uint32_t *__restrict__ ncalls,
                                const uint64_t *__restrict__ call_off, const lps_call *__restrict__ tmp,
@@ -933,6 +957,12 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, ctx->d_ncalls.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_status.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_counters.reserve(1));
+    LPS_CUDA(ctx, ctx->d_first_var.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, ctx->d_abort_of_read.reserve((size_t)n + 1));
+    if (n > 0) {
+        k_first_var<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->batch.ref_start, nv, ctx->var.pos, ctx->d_first_var.p);
+        ctx->stats.kernel_launches++;
+    }
     if (tag) {
         LPS_CUDA(ctx, ctx->d_tag_hp.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_ps.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_pq.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_h1.reserve((size_t)n + 1));
@@ -966,6 +996,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     for (int attempt = 0; attempt < 3; attempt++) {
         LPS_CUDA(ctx, ctx->d_calls_tmp.reserve(cap));
         LPS_CUDA(ctx, ctx->d_clip_keys.reserve(clip_cap));
+        LPS_CUDA(ctx, ctx->d_clip_meta.reserve(ctx->d_clip_keys.cap));
         LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(CallCounters), st));
         if (som) {
             // per-slot counters start from zero on every attempt (a re-run after a pool overflow must not count twice)
@@ -1001,12 +1032,14 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         a.last_var_pos = nv ? ctx->h_vpos[nv - 1] : -1;
         a.calls_tmp = ctx->d_calls_tmp.p; a.calls_cap = ctx->d_calls_tmp.cap;
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
-        a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap;
+        a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap; a.clip_meta = ctx->d_clip_meta.p;
+        a.abort_of_read = ctx->d_abort_of_read.p; a.first_var = ctx->d_first_var.p;
         a.counters = ctx->d_counters.p;
         a.count_gathers = ctx->zero_copy ? 1 : 0;
         a.overflow_list_out = ctx->d_overflow_reads.p; a.overflow_need_out = ctx->d_overflow_cand.p;
         a.overflow_list_cap = ovf_cap;
-        const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if (grid > ctx->persistent_ctas) grid = ctx->persistent_ctas;   // 4 resident CTAs per SM, reads fetched dynamically
         if (grid > 0) {
             cudaEventRecord(ctx->kev[0], st);
             launch_k1(mode, grid, st, a);
@@ -1047,7 +1080,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             CallCounters h2;
             LPS_CUDA(ctx, cudaMemcpyAsync(&h2, scratch.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
             LPS_CUDA(ctx, cudaStreamSynchronize(st));
-            hc.tmp_calls = h2.tmp_calls; hc.wd_items = h2.wd_items;
+            hc.tmp_calls = h2.tmp_calls; hc.wd_items = h2.wd_items; hc.aborted_reads = h2.aborted_reads;
             ovf.release(); scratch.release();
         }
         ctx->n_wd_items = hc.wd_items;
@@ -1080,6 +1113,10 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
 
     // clipCount map: sort the (pos << 1 | side) keys, run-length encode
     const int nclip = (int)hc.clips;
+    if (nclip > 0 && hc.aborted_reads) {
+        k_clip_filter<<<(nclip + 255) / 256, 256, 0, st>>>((unsigned long long)nclip, ctx->d_clip_keys.p, ctx->d_clip_meta.p, ctx->d_abort_of_read.p);
+        ctx->stats.kernel_launches++;
+    }
     ctx->h_clip_pos.clear(); ctx->h_clip_front.clear(); ctx->h_clip_back.clear();
     if (nclip > 0) {
         LPS_CUDA(ctx, ctx->d_clip_keys_sorted.reserve((size_t)nclip));
@@ -1103,6 +1140,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, cudaMemcpy(cnts.data(), ctx->d_clip_counts.p, 4 * (size_t)runs, cudaMemcpyDeviceToHost));
         ctx->stats.d2h_bytes += 8ull * (uint64_t)runs;
         for (int i = 0; i < runs; i++) {
+            if (keys[i] == 0xFFFFFFFFu) continue;   // cancelled by k_clip_filter
             int32_t pos = (int32_t)(keys[i] >> 1);
             if (ctx->h_clip_pos.empty() || ctx->h_clip_pos.back() != pos) {
                 ctx->h_clip_pos.push_back(pos); ctx->h_clip_front.push_back(0); ctx->h_clip_back.push_back(0);

@@ -75,6 +75,10 @@ int lps_ctx_create(int device, lps_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
     lps_ctx *ctx = new lps_ctx();
     ctx->device = device;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->persistent_ctas = sms * 4;
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->user_ev) cudaEventCreate(&ev);

@@ -104,6 +104,8 @@ struct CallCounters {
     unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
     unsigned long long gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
     unsigned long long wd_items;       // window-diff work items appended (tumor extract pass)
+    unsigned int next_read;            // dynamic read fetch of the persistent k_call_alleles launch
+    unsigned int aborted_reads;        // reads dropped by get_snp's bounds check (their later clip events are cancelled)
     unsigned int overflow_reads;
     unsigned int bad_cigar;            // reads with an unsupported CIGAR op
 };
@@ -155,6 +157,9 @@ struct lps_ctx {
     DevBuf<uint32_t> d_ncalls;
     DevBuf<uint8_t> d_status;
     DevBuf<uint32_t> d_clip_keys, d_clip_keys_sorted, d_clip_unique, d_clip_counts;
+    DevBuf<uint2> d_clip_meta;
+    DevBuf<int32_t> d_first_var, d_abort_of_read;
+    int persistent_ctas = 592;
     DevBuf<int32_t> d_num_runs;
     DevBuf<CallCounters> d_counters;
     DevBuf<uint32_t> d_overflow_reads;
