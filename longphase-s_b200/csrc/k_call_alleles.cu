@@ -25,7 +25,26 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
+constexpr int WARPS_PER_CTA = 32;   // one CTA of 32 warps per SM: its 160 KB of (dynamic) shared memory pin the L1 / shared split,
+                                     // so residency does not depend on the driver's carve-out heuristics
+#ifndef LPS_DECODE
+#define LPS_DECODE 2      // 0: two sums with selects, 1: packed multiply-add, multiplier from a shared-memory table, 2: ..., from the LUT word
+#endif
+#ifndef LPS_WALK_VEC
+#define LPS_WALK_VEC 1
+#endif
+#ifndef LPS_FETCH
+#define LPS_FETCH 2
+#endif
+constexpr int FETCH = LPS_FETCH;              // work items claimed per atomic by a warp
+#ifndef LPS_KOPS
+#define LPS_KOPS 8
+#endif
+#ifndef LPS_CTAS_PER_SM
+#define LPS_CTAS_PER_SM 1
+#endif
+constexpr int KOPS = LPS_KOPS;                 // CIGAR ops per lane and chunk (32 * KOPS ops per chunk)
+constexpr int CTAS_PER_SM = LPS_CTAS_PER_SM;   // resident CTAs per SM the register budget is sized for
 constexpr int CAND_CAP = 256;        // candidates buffered per warp in shared memory
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t PAD_OP = 1u;     // zero-length insertion: advances nothing
@@ -52,6 +71,9 @@ struct K1Args {
     uint2 *clip_meta;                 // (read, CIGAR index) of every clip event
     int32_t *abort_of_read;           // CIGAR index at which get_snp dropped the read, INT_MAX otherwise
     const int32_t *first_var;         // per read: lower_bound of its start in the variant positions
+    const uint32_t *long_list;        // [3][n_reads] reads with many CIGAR ops, longest tier first: they are started first
+    const uint32_t *long_count;       // [3] entries per tier (device memory, written by k_first_var)
+    uint32_t long_thr;                // n_cigar above which a read is in a tier (and skipped by the in-order pass)
     unsigned long long clip_cap;
     CallCounters *counters;
     // overflow pass
@@ -101,38 +123,36 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ pos,
     return lo + __popc(__ballot_sync(FULL, pred));
 }
 
-// K consecutive ops of this lane, starting at global index g0 (a multiple of 4 -> 128-bit loads).
-// `edge` (warp-uniform) is set for the first / last chunk of a read and for the tail of the array:
-// only there can ops fall outside [lo, hi); they become "I, len 0" (no effect, not a clip).
+// K consecutive ops of this lane, starting at index g0 of `rc` (the read's CIGAR, rebased to a 16-byte boundary; g0 is a
+// multiple of 4 -> 128-bit loads).  The read owns [lo, hi); `edge` (warp-uniform) is set for the first / last chunk of a read
+// and near the end of the whole array (tot): only there can ops fall outside [lo, hi); they become "I, len 0" (no effect).
 template <int K>
-__device__ __forceinline__ void load_ops(const uint32_t *__restrict__ cig, uint64_t total, int64_t g0, int64_t lo, int64_t hi,
-                                         bool edge, uint32_t (&ops)[K]) {
+__device__ __forceinline__ void load_ops(const uint32_t *__restrict__ rc, int tot, int g0, int lo, int hi, bool edge, uint32_t (&ops)[K]) {
     if (!edge) {
 #pragma unroll
         for (int j = 0; j < K; j += 4) {
-            uint4 t = __ldg(reinterpret_cast<const uint4 *>(cig + g0 + j));
+            uint4 t = __ldg(reinterpret_cast<const uint4 *>(rc + g0 + j));
             ops[j] = t.x; ops[j + 1] = t.y; ops[j + 2] = t.z; ops[j + 3] = t.w;
         }
         return;
     }
-    const int rel = (int)(g0 - lo), n = (int)(hi - lo);     // index of ops[0] inside the read
-    if (rel + K <= 0 || rel >= n) {
+    if (g0 + K <= lo || g0 >= hi) {
 #pragma unroll
         for (int j = 0; j < K; j++) ops[j] = PAD_OP;
         return;
     }
-    if ((uint64_t)(g0 + K) <= total) {
+    if (g0 + K <= tot) {
 #pragma unroll
         for (int j = 0; j < K; j += 4) {
-            uint4 t = __ldg(reinterpret_cast<const uint4 *>(cig + g0 + j));
+            uint4 t = __ldg(reinterpret_cast<const uint4 *>(rc + g0 + j));
             ops[j] = t.x; ops[j + 1] = t.y; ops[j + 2] = t.z; ops[j + 3] = t.w;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < K; j++) ops[j] = ((uint64_t)(g0 + j) < total) ? cig[g0 + j] : PAD_OP;
+        for (int j = 0; j < K; j++) ops[j] = (g0 + j < tot) ? rc[g0 + j] : PAD_OP;
     }
 #pragma unroll
-    for (int j = 0; j < K; j++) if ((unsigned)(rel + j) >= (unsigned)n) ops[j] = PAD_OP;
+    for (int j = 0; j < K; j++) if ((unsigned)(g0 + j - lo) >= (unsigned)(hi - lo)) ops[j] = PAD_OP;
 }
 
 // per-op advance bits, two bits per op code: bit0 = consumes the reference (M D N = X),
@@ -141,7 +161,10 @@ constexpr uint32_t ADV_LUT = (3u << 0) | (2u << 2) | (1u << 4) | (1u << 6) | (2u
 // op codes that need the slow path: S, H (clips), P, and the unsupported codes 9..15
 constexpr uint32_t RARE_OPS = 0xFE70u;
 
-constexpr int GROUPS_CAP = 384;     // K-op groups indexed per super-chunk (3072 ops); longer reads are walked in several super-chunks
+#ifndef LPS_GROUPS_CAP
+#define LPS_GROUPS_CAP 384
+#endif
+constexpr int GROUPS_CAP = LPS_GROUPS_CAP;     // K-op groups indexed per super-chunk (3072 ops); longer reads are walked in several super-chunks
 
 template <int K>
 struct WarpScratch {
@@ -171,9 +194,12 @@ __device__ __forceinline__ void count_base(int32_t *pb, char base, bool mpq_ok, 
 //   extract-normal  ExtractNorDataCigarParser + ExtractNorDataChrProcessor::processRead   SomaticVarCaller.cpp:123-293
 //   extract-tumor   ExtractTumDataCigarParser + ExtractTumDataChrProcessor::processRead   SomaticVarCaller.cpp:334-518, 712-759
 //   somatic tagging SomaticHaplotagCigarParser + SomaticHaplotagChrProcessor::judgeHaplotype  SomaticHaplotagProcess.cpp:310-579
+struct PoolCursor;
+__device__ __forceinline__ unsigned long long pool_alloc(const K1Args &a, PoolCursor &pc, int n, int lane);
+
 template <int MODE>
 __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane, uint4 *cand4, int ncand, int ref_start, int ref_end,
-                                                int q_end, int lq) {
+                                                int q_end, int lq, PoolCursor &pc) {
     constexpr bool XNOR = MODE == LPS_MODE_EXTRACT_NORMAL, XTUM = MODE == LPS_MODE_EXTRACT_TUMOR, STAG = MODE == LPS_MODE_SOMATIC_TAG;
     const DevSomatic &s = a.som;
     const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
@@ -385,9 +411,7 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
             __syncwarp();
         }
     }
-    unsigned long long start = 0;
-    if (lane == 0 && nout) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nout);
-    start = __shfl_sync(FULL, start, 0);
+    const unsigned long long start = pool_alloc(a, pc, nout, lane);
     if (lane == 0) { a.ncalls[r] = (uint32_t)nout; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
     if (start + nout <= a.calls_cap) {
         for (int c = lane; c < nout; c += 32) {
@@ -406,9 +430,29 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
 //   phase 2 (once per super-chunk, i.e. once per read for reads up to 3072 ops): every lane takes one pending variant,
 //     finds its group by binary search in the index, and re-walks the <= K ops of that group (L1/L2 hits: the lines were
 //     streamed moments ago) to get the covering op, its start positions and the op that follows it.
+// Slots of the scratch call pool are handed out in blocks of POOL_BLOCK per warp (one global atomic per ~50 reads instead of
+// one per read on the critical path); the unused tail of a block stays empty, k_gather_calls compacts the pool anyway.
+constexpr unsigned POOL_BLOCK = 1024;
+struct PoolCursor { unsigned long long next, end; };
+
+__device__ __forceinline__ unsigned long long pool_alloc(const K1Args &a, PoolCursor &pc, int n, int lane) {
+    if (n == 0) return 0ull;
+    if (pc.next + (unsigned)n > pc.end) {
+        const unsigned long long want = (unsigned)n > POOL_BLOCK ? (unsigned long long)n : (unsigned long long)POOL_BLOCK;
+        unsigned long long s = 0;
+        if (lane == 0) s = atomicAdd(&a.counters->tmp_calls, want);
+        s = __shfl_sync(FULL, s, 0);
+        pc.next = s; pc.end = s + want;
+    }
+    const unsigned long long start = pc.next;
+    pc.next += (unsigned)n;
+    if (lane == 0) atomicAdd(&a.counters->n_calls, (unsigned long long)n);   // no return value: a fire-and-forget RED
+    return start;
+}
+
 template <int K, int MODE>
-__device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S, const int r, Cand *cand, int cand_cap, const int lane,
-                                             const bool overflow_pass) {
+__device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S, const uint32_t *__restrict__ s_mult, const int r, Cand *cand,
+                                             int cand_cap, const int lane, const bool overflow_pass, PoolCursor &pc) {
     constexpr bool TAG = MODE != LPS_MODE_PHASE;          // CigarParser::parsingCigar instead of BamParser::get_snp
     constexpr bool SOM = MODE >= LPS_MODE_EXTRACT_NORMAL; // raw 16-byte candidates, resolved by resolve_somatic
     if (SOM) cand_cap >>= 1;                              // 16-byte candidates
@@ -419,7 +463,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     const int ncig = (int)a.b.n_cigar[r];
     const int flag = a.b.flag[r];
     int cur = a.first_var[r];                              // lower_bound(variants, ref_start), from k_first_var
-    const int64_t lo = (int64_t)a.b.cigar_off[r];
+    const int64_t lo64 = (int64_t)a.b.cigar_off[r];
     if (!TAG) {
         // iterator region "chr:1-lastSNP" (ParsingBam.cpp:1273) + read filter (:1282-1291)
         if (ref_start >= a.last_var_pos || (int)a.b.mapq[r] < a.mapping_quality || (flag & (0x4 | 0x100 | 0x400))) {
@@ -446,11 +490,13 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
         }
     }
     const int32_t *__restrict__ vpos = a.v.pos;
-    const int64_t hi = lo + ncig;
-    const int64_t abase = lo & ~(int64_t)3;
+    // the read's CIGAR rebased to a 16-byte boundary: 32-bit indices from here on; the read owns [lo, hi) of rc
+    const int64_t abase = lo64 & ~(int64_t)3;
+    const uint32_t *__restrict__ rc = a.b.cigar + abase;
+    const int lo = (int)(lo64 - abase), hi = lo + ncig;
+    const int64_t left = (int64_t)a.b.cigar_len - abase;
+    const int tot = left > (int64_t)INT_MAX ? INT_MAX : (int)left;
     constexpr int CH = 32 * K;
-    const uint32_t *__restrict__ cig = a.b.cigar;
-    const uint64_t total = a.b.cigar_len;
 
     int ref_pos = ref_start, qpos = 0;
     int ncand = 0;
@@ -458,44 +504,61 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     int abort_op = INT_MAX, bad_op = INT_MAX;
 
     uint32_t nxt_ops[K];
-    load_ops<K>(cig, total, abase + (int64_t)lane * K, lo, hi, true, nxt_ops);
-    int64_t cb = abase;
+    load_ops<K>(rc, tot, lane * K, lo, hi, true, nxt_ops);
+    int cb = 0;
     while (cb < hi) {
         // ================= phase 1: stream one super-chunk, index the group starts =================
-        const int64_t sc_cb = cb;
+        const int sc_cb = cb;
         int k = 0;
         for (; k < GROUPS_CAP / 32 && cb < hi; k++, cb += CH) {
             uint32_t ops[K];
 #pragma unroll
             for (int j = 0; j < K; j++) ops[j] = nxt_ops[j];
             if (cb + CH < hi) {
-                const bool edge = (cb + 2 * CH > hi) || ((uint64_t)(cb + 2 * CH) > total);
-                load_ops<K>(cig, total, cb + CH + (int64_t)lane * K, lo, hi, edge, nxt_ops);
+                const bool edge = (cb + 2 * CH > hi) || (cb + 2 * CH > tot);
+                load_ops<K>(rc, tot, cb + CH + lane * K, lo, hi, edge, nxt_ops);
             }
-            int rs = 0, qs = 0;
-            unsigned rare = 0;
+            // per-lane advance sums.  Fast path: both sums in one register (ref in bits 0..15, query in bits 16..31), one
+            // multiply-add per op with the multiplier 0 / 1 / 0x10000 / 0x10001 looked up by op code; exact while every op of
+            // the warp's chunk is shorter than 2048 (8 ops * 2047 < 2^16, no carry between the halves)
+            unsigned pk = 0, rare = 0;
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const unsigned c = ops[j];
+#if LPS_DECODE == 1
+                pk = (c >> 4) * s_mult[c & 15u] + pk;
+#elif LPS_DECODE == 2
                 const unsigned t = ADV_LUT >> ((c << 1) & 30u);
-                const int len = (int)(c >> 4);
-                rs += (int)(t & 1u) * len;
-                qs += (int)((t >> 1) & 1u) * len;
+                pk = (c >> 4) * ((t & 1u) | ((t & 2u) << 15)) + pk;
+#endif
                 rare |= c;                                // op code bits 2..3 set <=> some op code >= 4 (S H P = X or unsupported)
+            }
+            int rs, qs;
+            if (LPS_DECODE != 0 && !__any_sync(FULL, rare >= (2048u << 4))) { rs = (int)(pk & 0xffffu); qs = (int)(pk >> 16); }
+            else {
+                rs = 0; qs = 0;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const unsigned c = ops[j];
+                    const unsigned t = ADV_LUT >> ((c << 1) & 30u);
+                    const int len = (int)(c >> 4);
+                    rs += (int)(t & 1u) * len;
+                    qs += (int)((t >> 1) & 1u) * len;
+                }
             }
             // exclusive scan of both cursors: one packed scan when every lane sum fits 11 bits (so the totals fit 16)
             int er, eq, rtot, qtot;
             if (!__any_sync(FULL, (unsigned)(rs | qs) >= 2048u)) {
-                const unsigned pk = (unsigned)rs | ((unsigned)qs << 16);
-                unsigned inc = pk;
+                const unsigned pk2 = (unsigned)rs | ((unsigned)qs << 16);
+                unsigned inc = pk2;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const unsigned t = __shfl_up_sync(FULL, inc, d);
                     if (lane >= d) inc += t;
                 }
-                const unsigned exc = inc - pk, tot = __shfl_sync(FULL, inc, 31);
+                const unsigned exc = inc - pk2, tt = __shfl_sync(FULL, inc, 31);
                 er = (int)(exc & 0xffffu); eq = (int)(exc >> 16);
-                rtot = (int)(tot & 0xffffu); qtot = (int)(tot >> 16);
+                rtot = (int)(tt & 0xffffu); qtot = (int)(tt >> 16);
             } else {
                 int ri = rs, qi = qs;
 #pragma unroll
@@ -515,7 +578,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                 for (int j = 0; j < K; j++) {
                     const unsigned op = ops[j] & 15u;
                     const int len = (int)(ops[j] >> 4);
-                    const int64_t g = cb + (int64_t)lane * K + j;
+                    const int g = cb + lane * K + j;
                     if (!TAG && (op == 4 || op == 5) && len > 5) {
                         // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
                         const unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
@@ -553,17 +616,33 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     if (mid < ng && S.grp[mid].x <= vp) g = mid;
                 }
                 const int2 gs = S.grp[g];
-                // covering op: the last op of the group that starts at or before vp
+                const int g0 = sc_cb + g * K;
                 int wr = gs.x, wq = gs.y;
                 unsigned c = PAD_OP;
-                const int64_t g0 = sc_cb + (int64_t)g * K;
-                int64_t gidx = g0;
+#if LPS_WALK_VEC
+                // covering op: the last op of the group that starts at or before vp (two 128-bit loads, walked in registers)
+                uint32_t gops[K];
+                load_ops<K>(rc, tot, g0, lo, hi, true, gops);
+                int jsel = 0;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const unsigned cc = gops[j];
+                    if (wr <= vp) { c = cc; o_r = wr; o_q = wq; jsel = j; }
+                    const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
+                    const int len = (int)(cc >> 4);
+                    wr += (int)(t & 1u) * len;
+                    wq += (int)((t >> 1) & 1u) * len;
+                }
+                const int gidx = g0 + jsel;
+#else
+                // covering op: the last op of the group that starts at or before vp
+                int gidx = g0;
 #pragma unroll 1
                 for (int j = 0; j < K; j++) {
-                    const int64_t idx = g0 + j;
+                    const int idx = g0 + j;
                     if (idx >= hi) break;
                     if (idx < lo) continue;
-                    const unsigned cc = cig[idx];
+                    const unsigned cc = rc[idx];
                     if (wr > vp) break;
                     c = cc; o_r = wr; o_q = wq; gidx = idx;
                     const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
@@ -571,6 +650,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     wr += (int)(t & 1u) * len;
                     wq += (int)((t >> 1) & 1u) * len;
                 }
+#endif
                 const int o_op = (int)(c & 15u), o_len = (int)(c >> 4);
                 opi = (int)(gidx - lo);
                 if (SOM) {
@@ -581,7 +661,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                         if (o_q + off < lq) {                      // beyond SEQ the reference reads undefined memory: dropped
                             unsigned fl = 0;
                             if (opi + 1 < ncig) {
-                                const unsigned nop = cig[gidx + 1] & 15u;
+                                const unsigned nop = rc[gidx + 1] & 15u;
                                 fl = 1u;                           // i + 1 < n_cigar
                                 if (o_r + o_len - 1 == vp) fl |= (nop == 1u ? 2u : 0u) | (nop == 2u ? 4u : 0u);
                             }
@@ -603,7 +683,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                             if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
                         } else if ((rl == 1) != (al == 1)) {
                             if (opi + 1 < ncig) {
-                                const unsigned nop = cig[gidx + 1] & 15u;
+                                const unsigned nop = rc[gidx + 1] & 15u;
                                 const unsigned want = (rl == 1) ? 1u : 2u;
                                 const bool has = (o_r + o_len - 1 == vp && nop == want);
                                 const bool h1alt = a.hp1_is_alt[vi] != 0;
@@ -625,7 +705,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                         if (rl == 1 && al == 1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
                         else if ((rl == 1) != (al == 1)) {
                             if (opi + 1 < ncig) {                                                   // :1470, :1495
-                                const unsigned nop = cig[gidx + 1] & 15u;
+                                const unsigned nop = rc[gidx + 1] & 15u;
                                 const unsigned want = (rl == 1) ? 1u : 2u;                          // I after an insertion anchor, D after a deletion anchor
                                 const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
                                 cand_var = vi;
@@ -710,7 +790,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     __syncwarp();
 
     if (SOM) {
-        resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq);
+        resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq, pc);
         return;
     }
     if (TAG) {
@@ -777,9 +857,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
             else pq = (imx < 256) ? (int)a.pq_lut[imn * 256 + imx] : -1;         // -1: the host fills it in with its libm
             a.tag_hp[r] = (int8_t)hp; a.tag_ps[r] = hp ? ps_min : 0; a.tag_pq[r] = pq; a.tag_h1[r] = h1; a.tag_h2[r] = h2;
         }
-        unsigned long long start = 0;
-        if (lane == 0 && nout) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nout);
-        start = __shfl_sync(FULL, start, 0);
+        const unsigned long long start = pool_alloc(a, pc, nout, lane);
         if (lane == 0) { a.ncalls[r] = (uint32_t)nout; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
         if (start + nout <= a.calls_cap) {
             for (int c = lane; c < nout; c += 32) {
@@ -844,9 +922,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
         ngather = (int)__reduce_add_sync(FULL, (unsigned)ngather);
         if (lane == 0 && ngather) atomicAdd(&a.counters->gathers, (unsigned long long)ngather);
     }
-    unsigned long long start = 0;
-    if (lane == 0 && nvalid) start = atomicAdd(&a.counters->tmp_calls, (unsigned long long)nvalid);
-    start = __shfl_sync(FULL, start, 0);
+    const unsigned long long start = pool_alloc(a, pc, nvalid, lane);
     if (lane == 0) { a.ncalls[r] = (uint32_t)nvalid; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
     if (start + nvalid <= a.calls_cap) {
         for (int c = lane; c < nvalid; c += 32) {
@@ -864,33 +940,59 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
 // Persistent launch: every warp fetches the next read from a global counter until the batch is exhausted, so a CTA is never
 // held hostage by its longest read (read lengths are log-normal).  The overflow pass walks its list one read per warp.
 template <int K, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) k_call_alleles(K1Args a) {
-    __shared__ __align__(16) WarpScratch<K> s_all[WARPS_PER_CTA];
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) k_call_alleles(K1Args a) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    WarpScratch<K> *s_all = reinterpret_cast<WarpScratch<K> *>(s_dyn);
+    __shared__ uint32_t s_mult[16];   // per op code: (consumes reference) | (consumes query) << 16; M I D N S H P = X, 0 for the rest
+    if (threadIdx.x < 16) s_mult[threadIdx.x] = ((ADV_LUT >> (2 * threadIdx.x)) & 1u) | (((ADV_LUT >> (2 * threadIdx.x + 1)) & 1u) << 16);
+    __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch<K> &S = s_all[wib];
+    PoolCursor pc;
+    pc.next = 0; pc.end = 0;
     if (a.overflow_reads != nullptr) {
         const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
         if (wid >= a.overflow_list_cap) return;
-        process_read<K, MODE>(a, S, (int)a.overflow_reads[wid], a.overflow_buf + a.overflow_off[wid],
-                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true);
+        process_read<K, MODE>(a, S, s_mult, (int)a.overflow_reads[wid], a.overflow_buf + a.overflow_off[wid],
+                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true, pc);
         return;
     }
+    // Work items: first the long-read tiers (longest first), then every read in batch order (reads already taken from a tier are
+    // skipped).  FETCH items are claimed per atomic, and the NEXT claim is issued before the current one is processed, so neither
+    // the round trip nor the same-address atomic rate of the counter is on the critical path.
+    const unsigned n0 = a.long_count[0], n1 = n0 + a.long_count[1], n2 = n1 + a.long_count[2];
+    const unsigned n_items = n2 + (unsigned)a.b.n_reads;
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&a.counters->next_read, (unsigned)FETCH);
     while (true) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(&a.counters->next_read, 1u);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= (unsigned)a.b.n_reads) break;
-        process_read<K, MODE>(a, S, (int)t, S.cand, CAND_CAP, lane, false);
-        __syncwarp();
+        const unsigned t0 = __shfl_sync(FULL, nxt, 0);
+        if (t0 >= n_items) break;
+        if (lane == 0) nxt = atomicAdd(&a.counters->next_read, (unsigned)FETCH);
+#pragma unroll 1
+        for (unsigned t = t0; t < t0 + FETCH && t < n_items; t++) {
+            unsigned r;
+            if (t < n2) r = a.long_list[(size_t)(t < n0 ? 0 : t < n1 ? 1 : 2) * a.b.n_reads + (t < n0 ? t : t < n1 ? t - n0 : t - n1)];
+            else { r = t - n2; if (a.b.n_cigar[r] > a.long_thr) continue; }
+            process_read<K, MODE>(a, S, s_mult, (int)r, S.cand, CAND_CAP, lane, false, pc);
+            __syncwarp();
+        }
     }
 }
 
 // lower_bound of every read start in the variant positions (the reference's stateful firstVariantIter, ParsingBam.cpp:1318-1319,
 // HaplotagParsingBam.cpp:555-563, equals it for a coordinate-sorted batch); one thread per read
+// Also sorts the reads with many CIGAR ops into three tiers (> 4x, > 2.5x, > 1.6x the mean): the persistent kernel starts
+// those first, so that the longest reads do not form its tail.
 __global__ void k_first_var(int n_reads, const int32_t *__restrict__ ref_start, int nv, const int32_t *__restrict__ vpos,
-                            int32_t *__restrict__ first_var) {
+                            int32_t *__restrict__ first_var, const uint32_t *__restrict__ n_cigar, uint32_t thr0, uint32_t thr1, uint32_t thr2,
+                            uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
+    {
+        const uint32_t nc = n_cigar[r];
+        const int tier = nc > thr0 ? 0 : nc > thr1 ? 1 : nc > thr2 ? 2 : -1;
+        if (tier >= 0) long_list[(size_t)tier * n_reads + atomicAdd(long_count + tier, 1u)] = (uint32_t)r;
+    }
     const int key = ref_start[r];
     int lo = 0, hi = nv;
     while (lo < hi) {
@@ -933,14 +1035,32 @@ __global__ void k_widen_u32(int n, const uint32_t *__restrict__ in, uint64_t *__
 static_assert(sizeof(lps_call) == 8, "lps_call must be 8 bytes");
 
 namespace {
+constexpr size_t K1_SMEM = sizeof(WarpScratch<KOPS>) * WARPS_PER_CTA;
+
+template <int MODE> void prepare_k1() {
+    cudaFuncSetAttribute(k_call_alleles<KOPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM);
+    cudaFuncSetAttribute(k_call_alleles<KOPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("LPS_DEBUG_OCC")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_call_alleles<KOPS, MODE>, WARPS_PER_CTA * 32, K1_SMEM);
+        fprintf(stderr, "k_call_alleles<%d,%d>: %d resident CTAs per SM\n", KOPS, MODE, nb);
+    }
+}
+
 void launch_k1(int mode, int grid, cudaStream_t st, const K1Args &a) {
     const int tb = WARPS_PER_CTA * 32;
+    static bool prepared = false;
+    if (!prepared) {
+        prepare_k1<LPS_MODE_PHASE>(); prepare_k1<LPS_MODE_GERMLINE>(); prepare_k1<LPS_MODE_EXTRACT_NORMAL>();
+        prepare_k1<LPS_MODE_EXTRACT_TUMOR>(); prepare_k1<LPS_MODE_SOMATIC_TAG>();
+        prepared = true;
+    }
     switch (mode) {
-        case LPS_MODE_PHASE: k_call_alleles<8, LPS_MODE_PHASE><<<grid, tb, 0, st>>>(a); break;
-        case LPS_MODE_GERMLINE: k_call_alleles<8, LPS_MODE_GERMLINE><<<grid, tb, 0, st>>>(a); break;
-        case LPS_MODE_EXTRACT_NORMAL: k_call_alleles<8, LPS_MODE_EXTRACT_NORMAL><<<grid, tb, 0, st>>>(a); break;
-        case LPS_MODE_EXTRACT_TUMOR: k_call_alleles<8, LPS_MODE_EXTRACT_TUMOR><<<grid, tb, 0, st>>>(a); break;
-        default: k_call_alleles<8, LPS_MODE_SOMATIC_TAG><<<grid, tb, 0, st>>>(a); break;
+        case LPS_MODE_PHASE: k_call_alleles<KOPS, LPS_MODE_PHASE><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_GERMLINE: k_call_alleles<KOPS, LPS_MODE_GERMLINE><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_EXTRACT_NORMAL: k_call_alleles<KOPS, LPS_MODE_EXTRACT_NORMAL><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_EXTRACT_TUMOR: k_call_alleles<KOPS, LPS_MODE_EXTRACT_TUMOR><<<grid, tb, K1_SMEM, st>>>(a); break;
+        default: k_call_alleles<KOPS, LPS_MODE_SOMATIC_TAG><<<grid, tb, K1_SMEM, st>>>(a); break;
     }
 }
 }  // namespace
@@ -959,8 +1079,17 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, ctx->d_counters.reserve(1));
     LPS_CUDA(ctx, ctx->d_first_var.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_abort_of_read.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, ctx->d_long_list.reserve(3 * (size_t)n + 4));
+    LPS_CUDA(ctx, ctx->d_long_count.reserve(4));
+    const double mean_ops = n > 0 ? (double)ctx->batch.cigar_len / (double)n : 0.0;
+    const char *lpt_env = getenv("LPS_LPT");
+    const bool lpt = !(lpt_env && lpt_env[0] == '0');
+    const uint32_t thr0 = lpt ? (uint32_t)(4.0 * mean_ops) + 64 : 0xFFFFFFFFu, thr1 = lpt ? (uint32_t)(2.5 * mean_ops) + 64 : 0xFFFFFFFFu,
+                   thr2 = lpt ? (uint32_t)(1.6 * mean_ops) + 64 : 0xFFFFFFFFu;
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_long_count.p, 0, 4 * sizeof(uint32_t), st));
     if (n > 0) {
-        k_first_var<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->batch.ref_start, nv, ctx->var.pos, ctx->d_first_var.p);
+        k_first_var<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->batch.ref_start, nv, ctx->var.pos, ctx->d_first_var.p, ctx->batch.n_cigar, thr0, thr1,
+                                                     thr2, ctx->d_long_list.p, ctx->d_long_count.p);
         ctx->stats.kernel_launches++;
     }
     if (tag) {
@@ -984,7 +1113,8 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     // scratch pool capacity from the variant density of the contig; re-run on overflow
     double density = 0.0;
     if (nv > 1) density = (double)nv / ((double)ctx->h_vpos[nv - 1] - (double)ctx->h_vpos[0] + 1.0);
-    size_t cap = (size_t)((double)ctx->sum_l_qseq * density * 1.5) + (size_t)n * 4 + 4096;
+    size_t cap = (size_t)((double)ctx->sum_l_qseq * density * 1.5) + (size_t)n * 4 + 4096 +
+                 (size_t)ctx->sm_count * CTAS_PER_SM * WARPS_PER_CTA * POOL_BLOCK;   // every warp may leave one block partly unused
     if (cap < ctx->d_calls_tmp.cap) cap = ctx->d_calls_tmp.cap;
     size_t clip_cap = (size_t)n * 2 + 1024;
     if (clip_cap < ctx->d_clip_keys.cap) clip_cap = ctx->d_clip_keys.cap;
@@ -1034,12 +1164,13 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
         a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap; a.clip_meta = ctx->d_clip_meta.p;
         a.abort_of_read = ctx->d_abort_of_read.p; a.first_var = ctx->d_first_var.p;
+        a.long_list = ctx->d_long_list.p; a.long_count = ctx->d_long_count.p; a.long_thr = thr2;
         a.counters = ctx->d_counters.p;
         a.count_gathers = ctx->zero_copy ? 1 : 0;
         a.overflow_list_out = ctx->d_overflow_reads.p; a.overflow_need_out = ctx->d_overflow_cand.p;
         a.overflow_list_cap = ovf_cap;
         int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        if (grid > ctx->persistent_ctas) grid = ctx->persistent_ctas;   // 4 resident CTAs per SM, reads fetched dynamically
+        if (grid > ctx->sm_count * CTAS_PER_SM) grid = ctx->sm_count * CTAS_PER_SM;   // resident CTAs only, reads fetched dynamically
         if (grid > 0) {
             cudaEventRecord(ctx->kev[0], st);
             launch_k1(mode, grid, st, a);
@@ -1050,6 +1181,9 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
         if (grid > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_call_alleles, ctx->kev[0], ctx->kev[1]);
+        if (getenv("LPS_DEBUG_K1"))
+            fprintf(stderr, "k1 mode=%d attempt=%d grid=%d ms=%.4f pool=%llu/%zu calls=%llu clips=%llu overflow_reads=%u aborted=%u\n", mode, attempt, grid,
+                    ctx->stats.ms_kernel_call_alleles, hc.tmp_calls, ctx->d_calls_tmp.cap, hc.n_calls, hc.clips, hc.overflow_reads, hc.aborted_reads);
         // zero-copy accounting: one 32-byte sector of SEQ (phase: and one of QUAL) crosses PCIe per gathered candidate
         if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers * (tag ? 32ull : 64ull);
         if (hc.bad_cigar) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
@@ -1080,12 +1214,12 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             CallCounters h2;
             LPS_CUDA(ctx, cudaMemcpyAsync(&h2, scratch.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
             LPS_CUDA(ctx, cudaStreamSynchronize(st));
-            hc.tmp_calls = h2.tmp_calls; hc.wd_items = h2.wd_items; hc.aborted_reads = h2.aborted_reads;
+            hc.tmp_calls = h2.tmp_calls; hc.n_calls = h2.n_calls; hc.wd_items = h2.wd_items; hc.aborted_reads = h2.aborted_reads;
             ovf.release(); scratch.release();
         }
         ctx->n_wd_items = hc.wd_items;
         if (hc.tmp_calls <= ctx->d_calls_tmp.cap && hc.clips <= ctx->d_clip_keys.cap && hc.wd_items <= ctx->d_wd_items.cap) break;
-        cap = (size_t)hc.tmp_calls + 1024;
+        cap = (size_t)hc.tmp_calls + (size_t)hc.tmp_calls / 8 + 65536;   // the block hand-out is not deterministic: leave slack
         clip_cap = (size_t)hc.clips + 1024;
         if (wd_cap) wd_cap = (size_t)hc.wd_items + 1024;
         if (attempt == 2) return ctx->fail(LPS_E_NOMEM, "call pool sizing did not converge");
@@ -1101,7 +1235,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_call_off.p + n, 0, 8, st));
     cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, tmp_bytes, ctx->d_call_off.p, ctx->d_call_off.p, n + 1, st);
     ctx->stats.kernel_launches++;
-    ctx->n_calls = hc.tmp_calls;
+    ctx->n_calls = hc.n_calls;
     LPS_CUDA(ctx, ctx->d_calls.reserve((size_t)ctx->n_calls + 1));
     if (n > 0) {
         const long long threads = (long long)n * 32;

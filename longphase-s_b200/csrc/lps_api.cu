@@ -73,11 +73,17 @@ int lps_ctx_create(int device, lps_ctx **out) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || device < 0 || device >= count) return LPS_E_CUDA;   // no CPU fallback
     if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
+    {
+        // the SEQ / QUAL gathers touch one byte per 32-byte sector: ask L2 not to fetch the neighbouring sector along with it
+        const char *env = getenv("LPS_L2_FETCH");
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, env ? (size_t)atoi(env) : 32);
+        cudaGetLastError();
+    }
     lps_ctx *ctx = new lps_ctx();
     ctx->device = device;
     {
         int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->persistent_ctas = sms * 4;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);

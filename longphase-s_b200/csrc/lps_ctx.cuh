@@ -99,7 +99,8 @@ enum { LPS_MODE_PHASE = 0, LPS_MODE_GERMLINE = 1, LPS_MODE_EXTRACT_NORMAL = 2, L
 
 // counters written by the allele-calling kernel (one small struct, copied back once per call)
 struct CallCounters {
-    unsigned long long tmp_calls;      // slots requested in the scratch call pool
+    unsigned long long tmp_calls;      // slots handed out from the scratch call pool (in per-warp blocks)
+    unsigned long long n_calls;        // calls actually written
     unsigned long long clips;          // clip events appended
     unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
     unsigned long long gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
@@ -159,7 +160,8 @@ struct lps_ctx {
     DevBuf<uint32_t> d_clip_keys, d_clip_keys_sorted, d_clip_unique, d_clip_counts;
     DevBuf<uint2> d_clip_meta;
     DevBuf<int32_t> d_first_var, d_abort_of_read;
-    int persistent_ctas = 592;
+    DevBuf<uint32_t> d_long_list, d_long_count;
+    int sm_count = 148;
     DevBuf<int32_t> d_num_runs;
     DevBuf<CallCounters> d_counters;
     DevBuf<uint32_t> d_overflow_reads;
