@@ -2,7 +2,8 @@
 """bench.py — throughput of the LongPhase-S `phase` read-to-variant hot path on B200.
 
 One "step" = one pass of the whole hot path (allele calling -> host filters -> edge fold -> host sweep
--> read correction) over one synthetic contig per GPU (BASELINE.json config C2, contig-sharded).
+-> read correction) over the synthetic contigs of this GPU (BASELINE.json config C2, contig-sharded; by default 4 x 64 Mb
+per GPU, in flight concurrently on one lps_ctx + host thread each, like the reference's omp-parallel contig loop).
   value : reads/s with the read batch already resident in HBM (lps_batch_submit_device)
   e2e   : reads/s through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region
   roofline : the dominant kernel (k_call_alleles) against the measured HBM copy peak
@@ -26,8 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-WORKLOAD = ("C2 shard: phase SNP+indel, one {mb} Mb contig per GPU, 30x ONT-like 20 kb reads, "
-            "1 het variant/kb (10% indels), ONT error model")
+WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb, a chr1-sized share of the genome), 30x ONT-like "
+            "20 kb reads, 1 het variant/kb (10% indels), ONT error model")
 
 
 def synth_kwargs(args, seed):
@@ -135,8 +136,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contig-mb", type=float, default=64.0)
+    ap.add_argument("--contigs-per-gpu", type=int, default=4)
     ap.add_argument("--cpu-sample-mb", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-paths", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -155,7 +158,8 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
                 "allele_calls_per_s": res["allele_calls_per_s"],
-                "config": {"workload": WORKLOAD.format(mb=args.contig_mb), "sample": res["sample"]},
+                "config": {"workload": WORKLOAD.format(n=args.contigs_per_gpu, mb=args.contig_mb, tot=args.contigs_per_gpu * args.contig_mb),
+                           "sample": res["sample"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -173,35 +177,44 @@ def main():
     ffi = importlib.import_module("longphase_s_b200._ffi")
     os.environ["OMP_NUM_THREADS"] = str(max(1, ncores // world))
 
+    from concurrent.futures import ThreadPoolExecutor
+    C_ = args.contigs_per_gpu
     t_gen = time.time()
-    contig = synth_mod.Contig(**synth_kwargs(args, 100 + rank))
+    contigs = [synth_mod.Contig(**synth_kwargs(args, 100 + 16 * rank + i)) for i in range(C_)]
     t_gen = time.time() - t_gen
     params = ffi.default_phase_params(True)
-    ctx = host.Context(local_rank)
-    ctx.set_reference(contig.ref)
-    vs = contig.variants_struct()
-    ctx.set_variants(vs, True)
+    # one context (own stream, own scratch) per contig in flight, driven by its own host thread: the reference runs its contig
+    # loop the same way (`#pragma omp parallel for`, PhasingProcess.cpp:113), and the host parts of one contig (overlap filter,
+    # edgeConnectResult chain) overlap the kernels of the others
+    ctxs = [host.Context(local_rank) for _ in range(C_)]
+    keep = []
+    for ctx, contig in zip(ctxs, contigs):
+        ctx.set_reference(contig.ref)
+        vs = contig.variants_struct()
+        keep.append(vs)
+        ctx.set_variants(vs, True)
 
-    # ---- device-resident copy of the batch (torch owns the memory) ----
+    # ---- device-resident copy of every batch (torch owns the memory) ----
     def dev(a):
         view = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}.get(a.dtype)
         return torch.from_numpy(a.view(view) if view else a).cuda()
 
     names = ["ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"]
-    dtens = {k: dev(getattr(contig, k)) for k in names}
     ptypes = dict(ref_start=ffi.i32p, l_qseq=ffi.i32p, n_cigar=ffi.u32p, cigar_off=ffi.u64p, seq_off=ffi.u64p, qual_off=ffi.u64p,
                   flag=ffi.u16p, mapq=ffi.u8p, name_rank=ffi.i32p, cigar=ffi.u32p, seq4=ffi.u8p, qual=ffi.u8p)
 
-    def batch_from(ptr_of):
+    def batch_from(contig, ptr_of):
         return ffi.LpsReadBatch(n_reads=contig.n_reads, cigar_len=len(contig.cigar), seq_bytes=len(contig.seq4),
                                 qual_bytes=len(contig.qual), **{k: C.cast(ptr_of(k), ptypes[k]) for k in names})
 
-    dev_batch = batch_from(lambda k: dtens[k].data_ptr())
-    # ---- pinned host copy for the end-to-end leg ----
-    ptens = {k: torch.from_numpy(getattr(contig, k).view(np.uint8).reshape(-1)).pin_memory() for k in names}
-    pin_batch = batch_from(lambda k: ptens[k].data_ptr())
-    h2d_bytes = int(sum(t.numel() for t in ptens.values()))
-    input_bytes = h2d_bytes
+    dtens = [{k: dev(getattr(c, k)) for k in names} for c in contigs]
+    dev_batches = [batch_from(c, lambda k, d=d: d[k].data_ptr()) for c, d in zip(contigs, dtens)]
+    # ---- pinned host copies for the end-to-end leg ----
+    ptens = [{k: torch.from_numpy(getattr(c, k).view(np.uint8).reshape(-1)).pin_memory() for k in names} for c in contigs]
+    pin_batches = [batch_from(c, lambda k, d=d: d[k].data_ptr()) for c, d in zip(contigs, ptens)]
+    host_bytes = int(sum(t.numel() for d in ptens for t in d.values()))
+    input_bytes = host_bytes
+    n_reads_gpu = int(sum(c.n_reads for c in contigs))
 
     def barrier():
         torch.cuda.synchronize()
@@ -209,109 +222,172 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MAX if world > 1 else None)  # noqa: E731
+    sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM if world > 1 else None)  # noqa: E731
 
-    def step_resident():
-        return ctx.phase_contig(params)      # the batch was registered once with lps_batch_submit_device (no copy)
+    pool = ThreadPoolExecutor(max_workers=C_)
 
-    def step_e2e():
-        ctx.submit(pin_batch)
-        return ctx.phase_contig(params)
+    def run_all(fn):
+        return [f.result() for f in [pool.submit(fn, i) for i in range(C_)]]
+
+    def step_resident(i):
+        return ctxs[i].phase_contig(params)      # the batch was registered once with lps_batch_submit_device (no copy)
+
+    def step_e2e(i):
+        ctxs[i].submit(pin_batches[i])
+        return ctxs[i].phase_contig(params)
+
+    def timed(fn, steps, slot):
+        """`steps` passes over all contigs of this GPU; device time between the events of every context's stream, max over them."""
+        barrier()
+        for ctx in ctxs:
+            ctx.event_record(slot)
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(steps):
+            out = run_all(fn)
+        for ctx in ctxs:
+            ctx.event_record(slot + 1)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(ctx.event_elapsed_ms(slot, slot + 1) for ctx in ctxs) / steps, wall / steps, out
 
     # ---- kernel-resident leg ----
-    ctx.submit_device(dev_batch)
+    for i in range(C_):
+        ctxs[i].submit_device(dev_batches[i])
     for _ in range(args.warmup):
-        res = step_resident()
+        run_all(step_resident)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
-    s0 = ctx.stats()
-    k1_ms, fold_ms, call_ms, edge_ms, rc_ms = [], [], [], [], []
-    wall = {k: [] for k in ("ms_wall_call_alleles", "ms_wall_build_edges", "ms_wall_solve", "ms_host_filters", "ms_host_sweep")}
-    ctx.event_record(0)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = step_resident()
-        st = ctx.stats()
-        k1_ms.append(st["ms_kernel_call_alleles"]); fold_ms.append(st["ms_kernel_fold_edges"])
-        call_ms.append(st["ms_call_alleles"]); edge_ms.append(st["ms_build_edges"]); rc_ms.append(st["ms_read_correction"])
-        for k in wall:
-            wall[k].append(st[k])
-    ctx.event_record(1)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    dev_ms = ctx.event_elapsed_ms(0, 1)
-    s1 = ctx.stats()
+    s0 = [ctx.stats() for ctx in ctxs]
+    dev_ms, wall_ms, res = timed(step_resident, args.steps, 0)
+    s1 = [ctx.stats() for ctx in ctxs]
     clocks = sampler.stop()
-    ms_step = max_over_ranks(dev_ms / args.steps)
-    launches = int(s1["kernel_launches"] - s0["kernel_launches"])
+    ms_step = max_over_ranks(dev_ms)
+    launches = int(sum(b_["kernel_launches"] - a_["kernel_launches"] for a_, b_ in zip(s0, s1)))
+    stage_keys = ("ms_call_alleles", "ms_build_edges", "ms_read_correction", "ms_wall_call_alleles", "ms_wall_build_edges", "ms_wall_solve",
+                  "ms_host_filters", "ms_host_sweep", "ms_kernel_fold_edges")
+    stage = {k[3:]: float(np.mean([st[k] for st in s1])) for k in stage_keys}
 
-    # per-launch accounting of the dominant kernel (host copy of the calls for the byte count)
-    ctx.submit_device(dev_batch)
-    calls = ctx.call_alleles(params, want_host=True)
-    n_calls = calls["n_calls"]
-    b1 = algorithmic_bytes_k1(contig, calls["read_status"], n_calls)
+    # ---- the dominant kernel timed alone (one context, nothing else on the GPU): roofline ----
+    ctx0, contig0 = ctxs[0], contigs[0]
+    calls = ctx0.call_alleles(params, want_host=True)
+    n_calls0 = calls["n_calls"]
+    b1 = algorithmic_bytes_k1(contig0, calls["read_status"], n_calls0)
+    k1_ms = []
+    for _ in range(max(args.steps, 5)):
+        ctx0.call_alleles(params, want_host=False)
+        k1_ms.append(ctx0.stats()["ms_kernel_call_alleles"])
     k1 = float(np.mean(k1_ms))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy; the kernel is timed alone)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = b1 / (k1 * 1e-3) / 1e9 if k1 > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("contig_mb") == args.contig_mb and tj.get("reads") == contig0.n_reads:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
 
     # ---- end-to-end leg: pinned host buffers through the C ABI ----
     for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    s2 = ctx.stats()
-    ctx.event_record(2)
-    for _ in range(args.steps):
-        res_e2e = step_e2e()
-    ctx.event_record(3)
-    barrier()
-    e2e_ms = max_over_ranks(ctx.event_elapsed_ms(2, 3) / args.steps)
-    s3 = ctx.stats()
-    d2h_step = int((s3["d2h_bytes"] - s2["d2h_bytes"]) / args.steps)
-    h2d_step = int((s3["h2d_bytes"] - s2["h2d_bytes"]) / args.steps)
-    for k in ("ps", "hap_ref", "read_hp"):
-        assert np.array_equal(res[k], res_e2e[k]), "resident and end-to-end legs disagree"
+        run_all(step_e2e)
+    s2 = [ctx.stats() for ctx in ctxs]
+    e2e_dev_ms, e2e_wall_ms, res_e2e = timed(step_e2e, args.steps, 2)
+    e2e_ms = max_over_ranks(e2e_dev_ms)
+    s3 = [ctx.stats() for ctx in ctxs]
+    d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+    h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+    for ra, rb in zip(res, res_e2e):
+        for k in ("ps", "hap_ref", "read_hp"):
+            assert np.array_equal(ra[k], rb[k]), "resident and end-to-end legs disagree"
+    # allele calls of every contig (one extra pass, outside the timed regions)
+    calls_gpu = 0
+    for i in range(C_):
+        ctxs[i].submit_device(dev_batches[i])
+        calls_gpu += int(ctxs[i].call_alleles(params, want_host=False)["n_calls"])
 
-    total_reads = sum_over_ranks(float(contig.n_reads))
-    total_calls = sum_over_ranks(float(n_calls))
+    total_reads = sum_over_ranks(float(n_reads_gpu))
+    total_calls = sum_over_ranks(float(calls_gpu))
     line = {
         "metric": "phase_hot_path_reads_per_s", "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
         "allele_calls_per_s": total_calls / (ms_step * 1e-3),
-        "config": {"workload": WORKLOAD.format(mb=args.contig_mb), "reads_per_gpu": contig.n_reads, "variants_per_gpu": contig.n_var,
-                   "allele_calls_per_gpu": n_calls, "cigar_ops_per_read": float(contig.n_cigar.mean()),
-                   "input_bytes_per_gpu": input_bytes, "l2": "inputs (%.1f GB) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
-                   "parallelism": f"contig-sharded x{world}, no collective", "timing": "CUDA events on the library stream, max over ranks",
-                   "wall_ms_per_step_rank0": wall_ms / args.steps, "synth_seconds": t_gen},
+        "config": {"workload": WORKLOAD.format(n=C_, mb=args.contig_mb, tot=C_ * args.contig_mb), "contigs_per_gpu": C_,
+                   "reads_per_gpu": n_reads_gpu, "variants_per_gpu": int(sum(c.n_var for c in contigs)), "allele_calls_per_gpu": calls_gpu,
+                   "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "input_bytes_per_gpu": input_bytes,
+                   "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
+                   "parallelism": f"contig-sharded x{world} GPUs, {C_} contigs in flight per GPU (one lps_ctx + host thread each), no collective",
+                   "timing": "CUDA events on every context's stream (the streams the kernels run on), max over contexts and ranks",
+                   "wall_ms_per_step_rank0": wall_ms, "synth_seconds": t_gen},
         "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                "ms_per_step": e2e_ms, "host_buffer_bytes": h2d_bytes,
+                "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes,
                 "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
                         "CIGAR and per-read records are copied; h2d bytes are the library's own count"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1, "peak_source": peak_src},
-        "stage_ms": {"call_alleles": float(np.mean(call_ms)), "k_call_alleles": k1, "build_edges": float(np.mean(edge_ms)),
-                     "k_fold_edges": float(np.mean(fold_ms)), "read_correction": float(np.mean(rc_ms)),
-                     **{k[3:]: float(np.mean(v)) for k, v in wall.items()}},
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1,
+                     "peak_source": peak_src, "launch": f"one {args.contig_mb} Mb contig ({contig0.n_reads} reads), timed alone"},
+        "stage_ms": dict(k_call_alleles_alone=k1, **stage),
     }
+    if rank == 0 and world == 1 and not args.no_other_paths:
+        # ---- the other dialects of the hot path (BASELINE configs C3 / C4), kernel-resident device time of one call each ----
+        other = {}
+        try:
+            tp = ffi.default_tag_params()
+            phased = contig0.phased(res[0]["ps"], res[0]["hap_ref"] == 1)
+            pv = phased.variants_struct()
+            ctx0.set_variants(pv, 0)
+            ctx0.submit_device(dev_batches[0])
+            ms = []
+            for _ in range(args.warmup + args.steps):
+                r_tag = ctx0.tag_reads(tp, want_calls=False)
+                ms.append(ctx0.stats()["ms_tag_reads"])
+            ms = float(np.mean(ms[args.warmup:]))
+            other["haplotag"] = {"config": "C3: germline haplotag of one %.0f Mb contig with the phase set of this run" % args.contig_mb,
+                                 "reads_per_s": contig0.n_reads / (ms * 1e-3), "device_ms": ms, "alignments": contig0.n_reads,
+                                 "tagged": int((r_tag["hp"] != 0).sum())}
+            kw = synth_kwargs(args, 900)
+            kw.update(contig_len=int(min(args.contig_mb, 32.0) * 1_000_000), somatic_rate=3000.0 / 64e6, indel_frac=0.1)
+            kn, kt = dict(kw), dict(kw)
+            kn.update(depth=25.0, purity=0.0, read_seed=901)
+            kt.update(depth=50.0, purity=0.6, read_seed=902)
+            cn, ct = synth_mod.Contig(**kn), synth_mod.Contig(**kt)
+            un = cn.somatic_union(seed=9)
+            ut = un.with_reads_of(ct)
+            sp = ffi.LpsTagParams(mapping_quality=20, mapq_filter=0, tag_supplementary=1, have_reference=1, percentage_threshold=0.6)
+            for name, c, cls in (("extract_normal", un, host.ExtractNorDataChrProcessor), ("extract_tumor", ut, host.ExtractTumDataChrProcessor),
+                                 ("somatic_tag", ut, host.SomaticHaplotagChrProcessor)):
+                proc = cls(ctx0, c, sp)
+                ms, wd = [], []
+                for _ in range(args.warmup + args.steps):
+                    r_s = proc.processSingleChrom(c)
+                    st = ctx0.stats()
+                    ms.append(st["ms_tag_reads"]); wd.append(st["ms_kernel_window_diff"])
+                ms = float(np.mean(ms[args.warmup:]))
+                other[name] = {"reads_per_s": c.n_reads / (ms * 1e-3), "device_ms": ms, "alignments": c.n_reads, "tumor_positions": int(r_s["n_tum"])}
+                if name == "extract_tumor":
+                    wdm = float(np.mean(wd[args.warmup:]))
+                    # SURVEY §8d: 250 B of SEQ / reference / CIGAR + 8 B of histogram update per (tumor position, alignment) pair
+                    other[name].update(window_items=r_s["n_window_items"], k_window_diff_ms=wdm,
+                                       k_window_diff_gbs=258.0 * r_s["n_window_items"] / (wdm * 1e-3) / 1e9 if wdm > 0 else None)
+            other["somatic_config"] = "C4 shard: tumor 50x (purity 0.6) / normal 25x pair of one %.0f Mb contig, ~%d somatic SNV+indel, union map of %d positions" % (
+                kw["contig_len"] / 1e6, int(un.var_is_somatic.sum()), un.n_var)
+        except Exception as e:  # secondary numbers: never fail the headline line
+            other["error"] = repr(e)
+        line["other_paths"] = other
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cb = run_reference_cpu(args, min(ncores, 64), args.cpu_sample_mb)
@@ -320,7 +396,9 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
+    pool.shutdown()
+    for ctx in ctxs:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
