@@ -146,14 +146,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1; the synthetic generator (OpenMP) gets this rank's share of the host cores.  Must be
+    # set before libgomp is loaded (torch pulls it in).
+    os.environ["OMP_NUM_THREADS"] = str(max(1, ncores // world))
+    # stdout carries exactly ONE line (the JSON); anything libraries print there (NCCL's version banner) goes to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     entry.load_package()
-    ncores = os.cpu_count() or 1
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         os.environ["OMP_NUM_THREADS"] = str(ncores)
-        res = run_reference_cpu(args, ncores, args.cpu_sample_mb)
+        res = run_reference_cpu(args, min(ncores, 64), args.cpu_sample_mb)
         line = {"impl": "reference", "metric": "phase_hot_path_reads_per_s", "value": res["value"], "unit": "reads/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
@@ -162,7 +168,8 @@ def main():
                            "sample": res["sample"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return 0
 
     import torch
@@ -175,10 +182,10 @@ def main():
     synth_mod = importlib.import_module("longphase_s_b200.synth")
     host = importlib.import_module("longphase_s_b200.host")
     ffi = importlib.import_module("longphase_s_b200._ffi")
-    os.environ["OMP_NUM_THREADS"] = str(max(1, ncores // world))
 
     from concurrent.futures import ThreadPoolExecutor
-    C_ = args.contigs_per_gpu
+    # contigs in flight per GPU: each needs a host thread, so never more than this rank's share of the host cores
+    C_ = max(1, min(args.contigs_per_gpu, ncores // world))
     t_gen = time.time()
     contigs = [synth_mod.Contig(**synth_kwargs(args, 100 + 16 * rank + i)) for i in range(C_)]
     t_gen = time.time() - t_gen
@@ -395,7 +402,8 @@ def main():
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     pool.shutdown()
     for ctx in ctxs:
         ctx.close()
