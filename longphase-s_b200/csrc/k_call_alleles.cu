@@ -20,6 +20,7 @@
 // op start; only the FIRST pending variant of a D op is examined (homopolymer >= 3 rule); a variant
 // whose query index is beyond l_qseq drops the whole read but keeps the clips seen before it; indel
 // alleles look at the op that follows the M op; clips are FRONT iff the CIGAR index is 0.
+#include <algorithm>
 #include <cub/cub.cuh>
 #include "lps_ctx.cuh"
 
@@ -74,6 +75,7 @@ struct K1Args {
     const uint32_t *long_list;        // [3][n_reads] reads with many CIGAR ops, longest tier first: they are started first
     const uint32_t *long_count;       // [3] entries per tier (device memory, written by k_first_var)
     uint32_t long_thr;                // n_cigar above which a read is in a tier (and skipped by the in-order pass)
+    unsigned long long *dbg_times;    // LPS_DEBUG_K1: per warp {globaltimer at start, at end, reads processed, SM id}
     unsigned long long clip_cap;
     CallCounters *counters;
     // overflow pass
@@ -274,7 +276,7 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
                     if (XTUM && T && tty >= 1 && tty <= 3) {
                         if (tty != 1 || base == trb || base == tab) {
                             atomicAdd(s.allele_count + (size_t)slot * 2 + (is_alt ? 1 : 0), 1);
-                            const unsigned long long k = atomicAdd(&a.counters->wd_items, 1ull);
+                            const unsigned long long k = atomicAdd(&a.counters->wd_items.v, 1ull);
                             if (k < a.wd_cap) {
                                 WdItem it;
                                 it.read = (uint32_t)r; it.slot2 = (uint32_t)slot * 2u + (is_alt ? 1u : 0u); it.opi = cd.z; it.qidx = cd.y;
@@ -433,26 +435,26 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
 // Slots of the scratch call pool are handed out in blocks of POOL_BLOCK per warp (one global atomic per ~50 reads instead of
 // one per read on the critical path); the unused tail of a block stays empty, k_gather_calls compacts the pool anyway.
 constexpr unsigned POOL_BLOCK = 1024;
-struct PoolCursor { unsigned long long next, end; };
+struct PoolCursor { unsigned long long next, end, used; };
 
 __device__ __forceinline__ unsigned long long pool_alloc(const K1Args &a, PoolCursor &pc, int n, int lane) {
     if (n == 0) return 0ull;
     if (pc.next + (unsigned)n > pc.end) {
         const unsigned long long want = (unsigned)n > POOL_BLOCK ? (unsigned long long)n : (unsigned long long)POOL_BLOCK;
         unsigned long long s = 0;
-        if (lane == 0) s = atomicAdd(&a.counters->tmp_calls, want);
+        if (lane == 0) s = atomicAdd(&a.counters->tmp_calls.v, want);
         s = __shfl_sync(FULL, s, 0);
         pc.next = s; pc.end = s + want;
     }
     const unsigned long long start = pc.next;
     pc.next += (unsigned)n;
-    if (lane == 0) atomicAdd(&a.counters->n_calls, (unsigned long long)n);   // no return value: a fire-and-forget RED
+    pc.used += (unsigned)n;
     return start;
 }
 
 template <int K, int MODE>
 __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S, const uint32_t *__restrict__ s_mult, const int r, Cand *cand,
-                                             int cand_cap, const int lane, const bool overflow_pass, PoolCursor &pc) {
+                                             int cand_cap, const int lane, const bool overflow_pass, PoolCursor &pc, unsigned &nxt, bool &claimed) {
     constexpr bool TAG = MODE != LPS_MODE_PHASE;          // CigarParser::parsingCigar instead of BamParser::get_snp
     constexpr bool SOM = MODE >= LPS_MODE_EXTRACT_NORMAL; // raw 16-byte candidates, resolved by resolve_somatic
     if (SOM) cand_cap >>= 1;                              // 16-byte candidates
@@ -581,7 +583,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     const int g = cb + lane * K + j;
                     if (!TAG && (op == 4 || op == 5) && len > 5) {
                         // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
-                        const unsigned long long slot = atomicAdd(&a.counters->clips, 1ull);
+                        const unsigned long long slot = atomicAdd(&a.counters->clips.v, 1ull);
                         if (slot < a.clip_cap) {
                             a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
                             a.clip_meta[slot] = make_uint2((unsigned)r, (unsigned)(g - lo));
@@ -594,6 +596,11 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
             ref_pos += rtot; qpos += qtot;
         }
         const int ng = k * 32;
+        // claim the NEXT work item now: the streaming registers are dead, and phase 2 + the gathers hide the atomic's round trip
+        if (!claimed) {
+            if (lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);
+            claimed = true;
+        }
         __syncwarp();
 
         // ================= phase 2: every pending variant below ref_pos, one per lane =================
@@ -767,10 +774,10 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
         __syncwarp();   // the next super-chunk overwrites the index
     }
     const bool bad = __any_sync(FULL, bad_op < abort_op);
-    if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar, 1u);
+    if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar.v, 1ull);
     if (!TAG && lane == 0) {
         a.abort_of_read[r] = aborted ? abort_op : INT_MAX;
-        if (aborted) atomicAdd(&a.counters->aborted_reads, 1u);
+        if (aborted) atomicAdd(&a.counters->aborted_reads.v, 1ull);
     }
 
     if (aborted || bad) {
@@ -780,8 +787,8 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     if (ncand > cand_cap) {
         // rare: more candidates than the shared buffer holds — redo this read in the overflow pass
         if (lane == 0) {
-            unsigned k = atomicAdd(&a.counters->overflow_reads, 1u);
-            atomicAdd(&a.counters->overflow_cands, (unsigned long long)ncand);
+            unsigned k = (unsigned)atomicAdd(&a.counters->overflow_reads.v, 1ull);
+            atomicAdd(&a.counters->overflow_cands.v, (unsigned long long)ncand);
             if (k < a.overflow_list_cap) { a.overflow_list_out[k] = (uint32_t)r; a.overflow_need_out[k] = (uint64_t)ncand; }
             a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_OK;
         }
@@ -839,7 +846,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
         }
         if (a.count_gathers) {
             ngather = (int)__reduce_add_sync(FULL, (unsigned)ngather);
-            if (lane == 0 && ngather) atomicAdd(&a.counters->gathers, (unsigned long long)ngather);
+            if (lane == 0 && ngather) atomicAdd(&a.counters->gathers.v, (unsigned long long)ngather);
         }
         h1 = (int)__reduce_add_sync(FULL, (unsigned)h1);
         h2 = (int)__reduce_add_sync(FULL, (unsigned)h2);
@@ -920,7 +927,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     }
     if (a.count_gathers) {
         ngather = (int)__reduce_add_sync(FULL, (unsigned)ngather);
-        if (lane == 0 && ngather) atomicAdd(&a.counters->gathers, (unsigned long long)ngather);
+        if (lane == 0 && ngather) atomicAdd(&a.counters->gathers.v, (unsigned long long)ngather);
     }
     const unsigned long long start = pool_alloc(a, pc, nvalid, lane);
     if (lane == 0) { a.ncalls[r] = (uint32_t)nvalid; a.tmp_start[r] = start; a.status[r] = LPS_READ_OK; }
@@ -949,33 +956,46 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) k_call_allele
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpScratch<K> &S = s_all[wib];
     PoolCursor pc;
-    pc.next = 0; pc.end = 0;
+    pc.next = 0; pc.end = 0; pc.used = 0;
+    unsigned long long dbg_t0 = 0, dbg_n = 0;
+    if (a.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     if (a.overflow_reads != nullptr) {
         const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
         if (wid >= a.overflow_list_cap) return;
+        unsigned none = 0;
+        bool claimed = true;
         process_read<K, MODE>(a, S, s_mult, (int)a.overflow_reads[wid], a.overflow_buf + a.overflow_off[wid],
-                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true, pc);
+                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true, pc, none, claimed);
+        if (lane == 0 && pc.used) atomicAdd(&a.counters->n_calls.v, pc.used);
         return;
     }
     // Work items: first the long-read tiers (longest first), then every read in batch order (reads already taken from a tier are
-    // skipped).  FETCH items are claimed per atomic, and the NEXT claim is issued before the current one is processed, so neither
-    // the round trip nor the same-address atomic rate of the counter is on the critical path.
+    // skipped).  The NEXT item is claimed while the current read is between its two phases, so the atomic's round trip is hidden
+    // (claiming at the top of the loop made the compiler spill the pending result, i.e. wait for it at once).
     const unsigned n0 = a.long_count[0], n1 = n0 + a.long_count[1], n2 = n1 + a.long_count[2];
     const unsigned n_items = n2 + (unsigned)a.b.n_reads;
     unsigned nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&a.counters->next_read, (unsigned)FETCH);
+    if (lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);
     while (true) {
-        const unsigned t0 = __shfl_sync(FULL, nxt, 0);
-        if (t0 >= n_items) break;
-        if (lane == 0) nxt = atomicAdd(&a.counters->next_read, (unsigned)FETCH);
-#pragma unroll 1
-        for (unsigned t = t0; t < t0 + FETCH && t < n_items; t++) {
-            unsigned r;
-            if (t < n2) r = a.long_list[(size_t)(t < n0 ? 0 : t < n1 ? 1 : 2) * a.b.n_reads + (t < n0 ? t : t < n1 ? t - n0 : t - n1)];
-            else { r = t - n2; if (a.b.n_cigar[r] > a.long_thr) continue; }
-            process_read<K, MODE>(a, S, s_mult, (int)r, S.cand, CAND_CAP, lane, false, pc);
-            __syncwarp();
-        }
+        const unsigned t = __shfl_sync(FULL, nxt, 0);
+        if (t >= n_items) break;
+        bool claimed = false;
+        unsigned r;
+        bool skip = false;
+        if (t < n2) r = a.long_list[(size_t)(t < n0 ? 0 : t < n1 ? 1 : 2) * a.b.n_reads + (t < n0 ? t : t < n1 ? t - n0 : t - n1)];
+        else { r = t - n2; skip = a.b.n_cigar[r] > a.long_thr; }
+        if (!skip) process_read<K, MODE>(a, S, s_mult, (int)r, S.cand, CAND_CAP, lane, false, pc, nxt, claimed);
+        if (!claimed && lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);   // filtered / skipped reads never reach the claim point
+        __syncwarp();
+        dbg_n++;
+    }
+    if (lane == 0 && pc.used) atomicAdd(&a.counters->n_calls.v, pc.used);
+    if (a.dbg_times && lane == 0) {
+        unsigned long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *d = a.dbg_times + 4ull * ((unsigned long long)blockIdx.x * WARPS_PER_CTA + wib);
+        d[0] = dbg_t0; d[1] = t1; d[2] = dbg_n; d[3] = smid;
     }
 }
 
@@ -1165,6 +1185,11 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap; a.clip_meta = ctx->d_clip_meta.p;
         a.abort_of_read = ctx->d_abort_of_read.p; a.first_var = ctx->d_first_var.p;
         a.long_list = ctx->d_long_list.p; a.long_count = ctx->d_long_count.p; a.long_thr = thr2;
+        if (getenv("LPS_DEBUG_K1")) {
+            LPS_CUDA(ctx, ctx->d_dbg_times.reserve(4 * (size_t)ctx->sm_count * CTAS_PER_SM * WARPS_PER_CTA + 64));
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_times.p, 0, 8 * ctx->d_dbg_times.cap, st));
+            a.dbg_times = ctx->d_dbg_times.p;
+        }
         a.counters = ctx->d_counters.p;
         a.count_gathers = ctx->zero_copy ? 1 : 0;
         a.overflow_list_out = ctx->d_overflow_reads.p; a.overflow_need_out = ctx->d_overflow_cand.p;
@@ -1181,47 +1206,60 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->d_counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaStreamSynchronize(st));
         if (grid > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_call_alleles, ctx->kev[0], ctx->kev[1]);
+        if (getenv("LPS_DEBUG_K1") && a.dbg_times) {
+            const size_t nw = (size_t)grid * WARPS_PER_CTA;
+            std::vector<unsigned long long> h(4 * nw);
+            cudaMemcpy(h.data(), a.dbg_times, 32 * nw, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull, t1 = 0;
+            for (size_t w = 0; w < nw; w++) { if (h[4 * w] && h[4 * w] < t0) t0 = h[4 * w]; if (h[4 * w + 1] > t1) t1 = h[4 * w + 1]; }
+            std::vector<double> st, en, cnt;
+            for (size_t w = 0; w < nw; w++) { st.push_back((double)(h[4 * w] - t0) / 1e3); en.push_back((double)(h[4 * w + 1] - t0) / 1e3); cnt.push_back((double)h[4 * w + 2]); }
+            std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end()); std::sort(cnt.begin(), cnt.end());
+            auto q = [&](std::vector<double> &v, double f) { return v[(size_t)(f * (v.size() - 1))]; };
+            fprintf(stderr, "k1 warps=%zu span=%.1f us | start us p0 %.1f p50 %.1f p99 %.1f max %.1f | end us p0 %.1f p10 %.1f p50 %.1f p90 %.1f max %.1f | reads/warp min %.0f p50 %.0f max %.0f\n",
+                    nw, (double)(t1 - t0) / 1e3, q(st, 0), q(st, .5), q(st, .99), q(st, 1), q(en, 0), q(en, .1), q(en, .5), q(en, .9), q(en, 1), q(cnt, 0), q(cnt, .5), q(cnt, 1));
+        }
         if (getenv("LPS_DEBUG_K1"))
             fprintf(stderr, "k1 mode=%d attempt=%d grid=%d ms=%.4f pool=%llu/%zu calls=%llu clips=%llu overflow_reads=%u aborted=%u\n", mode, attempt, grid,
-                    ctx->stats.ms_kernel_call_alleles, hc.tmp_calls, ctx->d_calls_tmp.cap, hc.n_calls, hc.clips, hc.overflow_reads, hc.aborted_reads);
+                    ctx->stats.ms_kernel_call_alleles, hc.tmp_calls.v, ctx->d_calls_tmp.cap, hc.n_calls.v, hc.clips.v, hc.overflow_reads.v, hc.aborted_reads.v);
         // zero-copy accounting: one 32-byte sector of SEQ (phase: and one of QUAL) crosses PCIe per gathered candidate
-        if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers * (tag ? 32ull : 64ull);
-        if (hc.bad_cigar) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
-        if (hc.overflow_reads > ovf_cap) return ctx->fail(LPS_E_NOMEM, "too many reads overflow the candidate buffer");
-        if (hc.overflow_reads) {
+        if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers.v * (tag ? 32ull : 64ull);
+        if (hc.bad_cigar.v) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
+        if (hc.overflow_reads.v > ovf_cap) return ctx->fail(LPS_E_NOMEM, "too many reads overflow the candidate buffer");
+        if (hc.overflow_reads.v) {
             // second pass for the few reads with more candidates than the shared buffer: same kernel,
             // candidate lists in global memory sized from the first pass
-            std::vector<uint64_t> need(hc.overflow_reads), off(hc.overflow_reads + 1, 0);
-            LPS_CUDA(ctx, cudaMemcpy(need.data(), ctx->d_overflow_cand.p, 8 * (size_t)hc.overflow_reads, cudaMemcpyDeviceToHost));
-            for (uint32_t i = 0; i < hc.overflow_reads; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
+            std::vector<uint64_t> need(hc.overflow_reads.v), off(hc.overflow_reads.v + 1, 0);
+            LPS_CUDA(ctx, cudaMemcpy(need.data(), ctx->d_overflow_cand.p, 8 * (size_t)hc.overflow_reads.v, cudaMemcpyDeviceToHost));
+            for (uint32_t i = 0; i < hc.overflow_reads.v; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
             LPS_CUDA(ctx, ctx->d_overflow_off.reserve(off.size()));
             LPS_CUDA(ctx, cudaMemcpy(ctx->d_overflow_off.p, off.data(), 8 * off.size(), cudaMemcpyHostToDevice));
             DevBuf<Cand> ovf;
             LPS_CUDA(ctx, ovf.reserve((size_t)off.back() + 1));
             K1Args b2 = a;
             b2.overflow_reads = ctx->d_overflow_reads.p; b2.overflow_off = ctx->d_overflow_off.p; b2.overflow_buf = ovf.p;
-            b2.overflow_list_cap = hc.overflow_reads;
+            b2.overflow_list_cap = hc.overflow_reads.v;
             // the overflow pass must not append the clips / counters of these reads a second time
             b2.clip_cap = 0;
             DevBuf<CallCounters> scratch;
             LPS_CUDA(ctx, scratch.reserve(1));
             LPS_CUDA(ctx, cudaMemcpyAsync(scratch.p, ctx->d_counters.p, sizeof(CallCounters), cudaMemcpyDeviceToDevice, st));
             b2.counters = scratch.p;
-            const int g2 = ((int)hc.overflow_reads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+            const int g2 = ((int)hc.overflow_reads.v + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
             launch_k1(mode, g2, st, b2);
             ctx->stats.kernel_launches++;
             LPS_CUDA(ctx, cudaGetLastError());
             CallCounters h2;
             LPS_CUDA(ctx, cudaMemcpyAsync(&h2, scratch.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
             LPS_CUDA(ctx, cudaStreamSynchronize(st));
-            hc.tmp_calls = h2.tmp_calls; hc.n_calls = h2.n_calls; hc.wd_items = h2.wd_items; hc.aborted_reads = h2.aborted_reads;
+            hc.tmp_calls.v = h2.tmp_calls.v; hc.n_calls.v = h2.n_calls.v; hc.wd_items.v = h2.wd_items.v; hc.aborted_reads.v = h2.aborted_reads.v;
             ovf.release(); scratch.release();
         }
-        ctx->n_wd_items = hc.wd_items;
-        if (hc.tmp_calls <= ctx->d_calls_tmp.cap && hc.clips <= ctx->d_clip_keys.cap && hc.wd_items <= ctx->d_wd_items.cap) break;
-        cap = (size_t)hc.tmp_calls + (size_t)hc.tmp_calls / 8 + 65536;   // the block hand-out is not deterministic: leave slack
-        clip_cap = (size_t)hc.clips + 1024;
-        if (wd_cap) wd_cap = (size_t)hc.wd_items + 1024;
+        ctx->n_wd_items = hc.wd_items.v;
+        if (hc.tmp_calls.v <= ctx->d_calls_tmp.cap && hc.clips.v <= ctx->d_clip_keys.cap && hc.wd_items.v <= ctx->d_wd_items.cap) break;
+        cap = (size_t)hc.tmp_calls.v + (size_t)hc.tmp_calls.v / 8 + 65536;   // the block hand-out is not deterministic: leave slack
+        clip_cap = (size_t)hc.clips.v + 1024;
+        if (wd_cap) wd_cap = (size_t)hc.wd_items.v + 1024;
         if (attempt == 2) return ctx->fail(LPS_E_NOMEM, "call pool sizing did not converge");
     }
 
@@ -1235,7 +1273,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_call_off.p + n, 0, 8, st));
     cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, tmp_bytes, ctx->d_call_off.p, ctx->d_call_off.p, n + 1, st);
     ctx->stats.kernel_launches++;
-    ctx->n_calls = hc.n_calls;
+    ctx->n_calls = hc.n_calls.v;
     LPS_CUDA(ctx, ctx->d_calls.reserve((size_t)ctx->n_calls + 1));
     if (n > 0) {
         const long long threads = (long long)n * 32;
@@ -1246,8 +1284,8 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, cudaGetLastError());
 
     // clipCount map: sort the (pos << 1 | side) keys, run-length encode
-    const int nclip = (int)hc.clips;
-    if (nclip > 0 && hc.aborted_reads) {
+    const int nclip = (int)hc.clips.v;
+    if (nclip > 0 && hc.aborted_reads.v) {
         k_clip_filter<<<(nclip + 255) / 256, 256, 0, st>>>((unsigned long long)nclip, ctx->d_clip_keys.p, ctx->d_clip_meta.p, ctx->d_abort_of_read.p);
         ctx->stats.kernel_launches++;
     }

@@ -97,18 +97,21 @@ struct WdItem { uint32_t read, slot2, opi, qidx, off; };
 
 enum { LPS_MODE_PHASE = 0, LPS_MODE_GERMLINE = 1, LPS_MODE_EXTRACT_NORMAL = 2, LPS_MODE_EXTRACT_TUMOR = 3, LPS_MODE_SOMATIC_TAG = 4 };
 
-// counters written by the allele-calling kernel (one small struct, copied back once per call)
+// counters written by the allele-calling kernel (copied back once per call).  Every hot counter sits on its own 128-byte
+// line: same-line atomics serialise in one L2 slice, and with ~100 k reads per launch the work counter, the pool counter and
+// the clip counter together saturated it.
+struct alignas(128) CounterLine { unsigned long long v; unsigned long long pad[15]; };
 struct CallCounters {
-    unsigned long long tmp_calls;      // slots handed out from the scratch call pool (in per-warp blocks)
-    unsigned long long n_calls;        // calls actually written
-    unsigned long long clips;          // clip events appended
-    unsigned long long overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
-    unsigned long long gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
-    unsigned long long wd_items;       // window-diff work items appended (tumor extract pass)
-    unsigned int next_read;            // dynamic read fetch of the persistent k_call_alleles launch
-    unsigned int aborted_reads;        // reads dropped by get_snp's bounds check (their later clip events are cancelled)
-    unsigned int overflow_reads;
-    unsigned int bad_cigar;            // reads with an unsupported CIGAR op
+    CounterLine next_read;      // dynamic read fetch of the persistent k_call_alleles launch (low 32 bits used)
+    CounterLine tmp_calls;      // slots handed out from the scratch call pool (in per-warp blocks)
+    CounterLine n_calls;        // calls actually written (added once per warp, at its exit)
+    CounterLine clips;          // clip events appended
+    CounterLine wd_items;       // window-diff work items appended (tumor extract pass)
+    CounterLine gathers;        // SNP candidates whose base + quality were gathered (zero-copy accounting)
+    CounterLine overflow_cands; // candidate slots needed by reads that overflowed the smem buffer
+    CounterLine overflow_reads;
+    CounterLine aborted_reads;  // reads dropped by get_snp's bounds check (their later clip events are cancelled)
+    CounterLine bad_cigar;      // reads with an unsupported CIGAR op
 };
 
 struct lps_ctx {
@@ -161,6 +164,7 @@ struct lps_ctx {
     DevBuf<uint2> d_clip_meta;
     DevBuf<int32_t> d_first_var, d_abort_of_read;
     DevBuf<uint32_t> d_long_list, d_long_count;
+    DevBuf<unsigned long long> d_dbg_times;
     int sm_count = 148;
     DevBuf<int32_t> d_num_runs;
     DevBuf<CallCounters> d_counters;
