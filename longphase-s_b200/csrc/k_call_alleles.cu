@@ -26,10 +26,13 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 32;   // one CTA of 32 warps per SM: its 160 KB of (dynamic) shared memory pin the L1 / shared split,
+#ifndef LPS_WARPS
+#define LPS_WARPS 32
+#endif
+constexpr int WARPS_PER_CTA = LPS_WARPS;   // one CTA of 32 warps per SM: its 160 KB of (dynamic) shared memory pin the L1 / shared split,
                                      // so residency does not depend on the driver's carve-out heuristics
 #ifndef LPS_DECODE
-#define LPS_DECODE 2      // 0: two sums with selects, 1: packed multiply-add, multiplier from a shared-memory table, 2: ..., from the LUT word
+#define LPS_DECODE 0      // 0: two sums with selects, 1: packed multiply-add, multiplier from a shared-memory table, 2: ..., from the LUT word
 #endif
 #ifndef LPS_WALK_VEC
 #define LPS_WALK_VEC 1

@@ -1,14 +1,14 @@
 #!/bin/bash
-# A/B of k_call_alleles build variants on the GPU box: tools/ab_k1.sh "KOPS:CTAS:L2FETCH" ...
+# A/B of k_call_alleles build variants on the GPU box: tools/ab_k1.sh "KOPS:WARPS:GROUPS_CAP:DECODE:WALK_VEC" ...
 cd "$(dirname "$0")/.."
 for cfg in "$@"; do
-  IFS=: read K C L G D W F P <<< "$cfg"; G=${G:-384}; D=${D:-2}; W=${W:-0}; F=${F:-2}; P=${P:-1}
+  IFS=: read K W G D V C <<< "$cfg"; G=${G:-384}; D=${D:-0}; V=${V:-1}; C=${C:-1}
   touch longphase-s_b200/csrc/k_call_alleles.cu
-  make -C longphase-s_b200/csrc EXTRA="-DLPS_KOPS=$K -DLPS_CTAS_PER_SM=$C -DLPS_GROUPS_CAP=$G -DLPS_DECODE=$D -DLPS_WALK_VEC=$W -DLPS_FETCH=$F" > /dev/null 2>&1 || { echo "build failed $cfg"; continue; }
-  LPS_LPT=$P LPS_L2_FETCH=$L python bench.py --steps 5 --warmup 3 --no-cpu-baseline ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err || { tail -3 /tmp/ab.err; continue; }
+  make -C longphase-s_b200/csrc EXTRA="-DLPS_KOPS=$K -DLPS_WARPS=$W -DLPS_GROUPS_CAP=$G -DLPS_DECODE=$D -DLPS_WALK_VEC=$V -DLPS_CTAS_PER_SM=$C" > /dev/null 2>&1 || { echo "build failed $cfg"; continue; }
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-paths --contigs-per-gpu 1 ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err || { tail -3 /tmp/ab.err; continue; }
   python - "$cfg" <<'PY'
 import json,sys
 d=json.load(open('/tmp/ab.json'))
-print(sys.argv[1], "k1_ms=%.4f frac=%.3f step_ms=%.3f e2e_ms=%.2f call_alleles=%.3f" % (d["stage_ms"]["k_call_alleles"], d["roofline"]["frac"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["stage_ms"]["call_alleles"]))
+print(sys.argv[1], "k1_ms=%.4f frac=%.3f step_ms=%.3f e2e_ms=%.2f call_alleles=%.3f" % (d["stage_ms"]["k_call_alleles_alone"], d["roofline"]["frac"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["stage_ms"]["call_alleles"]))
 PY
 done
