@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
                                                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
                                                           const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
                                                           double edge_threshold, uint8_t *__restrict__ vote_info,
-                                                          unsigned long long *__restrict__ counters) {
+                                                          unsigned long long *__restrict__ counters, uint64_t n_merged) {
     extern __shared__ float s_acc[];                       // [WARPS][W*4]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS + wib;
@@ -185,46 +185,115 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
     __syncwarp();
     const uint64_t l0 = node_off[a], l1 = node_off[a + 1];
     unsigned long long contrib = 0, far = 0;
-    uint32_t m_next = l0 < l1 ? list[l0] : 0;
-    for (uint64_t t = l0; t < l1; t++) {
-        const uint32_t m = m_next;
-        if (t + 1 < l1) m_next = list[t + 1];
-        const uint32_t ea = M[m];
-        const uint32_t gend = M_gend[m];
-        const unsigned al_a = (ea >> 1) & 1u, hi_a = ea & 1u;
-        for (int j0 = 0; j0 < W; j0 += 32) {
-            const int j = j0 + lane;
-            const uint64_t idx = (uint64_t)m + 1 + (uint64_t)j;
-            const bool active = j < W && idx < gend;
-            const uint32_t eb = active ? M[idx] : 0xffffffffu;
-            const int nb = (int)(eb >> 2);
-            const uint32_t nb_prev = __shfl_up_sync(FULL, eb >> 2, 1);
-            const bool dup = active && lane > 0 && nb_prev == (uint32_t)nb;
+    if (W <= 64) {
+        // Software pipeline: the words of call t+1 (its own entry, the end of its merged read, the <= W entries that follow it in
+        // the read) are requested before call t is folded, so the fold never waits on a dependent load chain.  Lane l owns the
+        // successors l and 32 + l of a call (W <= 64): one round per call instead of two.
+        const int W2 = W > 32 ? W - 32 : 0;
+        const uint32_t nm = (uint32_t)n_merged;            // merged entries are indexed with 32 bits (d_M_idx is uint32)
+        auto fetch = [&](uint32_t m, uint32_t &ea, uint32_t &gend, uint32_t &e0, uint32_t &e1) {
+            ea = M[m]; gend = M_gend[m];
+            const uint32_t i0 = m + 1u + (uint32_t)lane, i1 = i0 + 32u;
+            e0 = (lane < W && i0 < nm) ? M[i0] : 0xffffffffu;
+            e1 = (lane < W2 && i1 < nm) ? M[i1] : 0xffffffffu;
+        };
+        uint32_t m_cur = 0, m_nxt = 0, ea = 0, gend = 0, e0 = 0xffffffffu, e1 = 0xffffffffu;
+        if (l0 < l1) { m_cur = list[l0]; fetch(m_cur, ea, gend, e0, e1); }
+        if (l0 + 1 < l1) m_nxt = list[l0 + 1];
+        unsigned c32 = 0, f32 = 0;                         // per-lane counts of this node (<= 2 per call), widened once at the end
+        const float wlo = (float)edge_weight;
+        (void)wlo;
+        for (uint64_t t = l0; t < l1; t++) {
+            const uint32_t m = m_cur, ea_c = ea, gend_c = gend;
+            uint32_t eb0 = e0, eb1 = e1;
+            if (t + 1 < l1) {
+                m_cur = m_nxt;
+                fetch(m_cur, ea, gend, e0, e1);
+                if (t + 2 < l1) m_nxt = list[t + 2];
+            }
+            const unsigned al_a = (ea_c >> 1) & 1u, hi_a = ea_c & 1u;
+            const bool act0 = lane < W && m + 1u + (uint32_t)lane < gend_c;
+            const bool act1 = lane < W2 && m + 33u + (uint32_t)lane < gend_c;
+            if (!act0) eb0 = 0xffffffffu;
+            if (!act1) eb1 = 0xffffffffu;
+            const int nb0 = (int)(eb0 >> 2), nb1 = (int)(eb1 >> 2);
+            const bool second = __any_sync(FULL, act1);     // the read reaches beyond 32 successors (warp-uniform)
+            // duplicates (two calls of one merged read at the same position) are adjacent in the read's sorted list
+            const uint32_t p0 = __shfl_up_sync(FULL, eb0 >> 2, 1);
+            bool dup = act0 && lane > 0 && p0 == (uint32_t)nb0;
+            if (second) {
+                const uint32_t p1 = __shfl_up_sync(FULL, eb1 >> 2, 1), last0 = __shfl_sync(FULL, eb0 >> 2, 31);
+                dup = dup || (act1 && (lane > 0 ? p1 : last0) == (uint32_t)nb1);
+            }
             const bool any_dup = __any_sync(FULL, dup);
-            const int d = nb - a - 1;
-            const bool dense = active && d >= 0 && d < W;
-            if (active) { if (dense) contrib++; else far++; }
-            float *cell = dense ? &acc[d * 4 + (int)(al_a * 2u + ((eb >> 1) & 1u))] : nullptr;
-            const bool high = hi_a && (eb & 1u);
+            const int d0 = nb0 - a - 1, d1 = nb1 - a - 1;
+            const bool dense0 = act0 && d0 >= 0 && d0 < W, dense1 = act1 && d1 >= 0 && d1 < W;
+            c32 += (unsigned)dense0 + (unsigned)dense1;
+            f32 += (unsigned)(act0 && !dense0) + (unsigned)(act1 && !dense1);
+            float *cell0 = dense0 ? &acc[d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u))] : nullptr;
+            float *cell1 = dense1 ? &acc[d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u))] : nullptr;
+            const bool high0 = hi_a && (eb0 & 1u), high1 = hi_a && (eb1 & 1u);
             if (!any_dup) {
-                if (dense) {
-                    float x = *cell;
-                    x = high ? x + 1.0f : (float)((double)x + edge_weight);      // SubEdge::addSubEdge :40-43, :62-65
-                    *cell = x;
-                }
+                // distinct successors of one read hit distinct cells
+                if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }   // SubEdge::addSubEdge :40-43, :62-65
+                if (second && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
             } else {
-                // two calls of one merged read at the same position: keep the read's own order
+                // keep the read's own order: successors 0..31, then 32..W-1
                 for (int l = 0; l < 32; l++) {
-                    if (lane == l && dense) {
-                        float x = *cell;
-                        x = high ? x + 1.0f : (float)((double)x + edge_weight);
-                        *cell = x;
-                    }
+                    if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                    __syncwarp();
+                }
+                for (int l = 0; l < W2; l++) {
+                    if (lane == l && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
                     __syncwarp();
                 }
             }
             __syncwarp();
-            if (!__any_sync(FULL, active)) break;
+        }
+        contrib += c32; far += f32;
+    } else {
+        // connect_adjacent > 64: plain rounds of 32 successors
+        uint32_t m_next = l0 < l1 ? list[l0] : 0;
+        for (uint64_t t = l0; t < l1; t++) {
+            const uint32_t m = m_next;
+            if (t + 1 < l1) m_next = list[t + 1];
+            const uint32_t ea = M[m];
+            const uint32_t gend = M_gend[m];
+            const unsigned al_a = (ea >> 1) & 1u, hi_a = ea & 1u;
+            for (int j0 = 0; j0 < W; j0 += 32) {
+                const int j = j0 + lane;
+                const uint64_t idx = (uint64_t)m + 1 + (uint64_t)j;
+                const bool active = j < W && idx < gend;
+                const uint32_t eb = active ? M[idx] : 0xffffffffu;
+                const int nb = (int)(eb >> 2);
+                const uint32_t nb_prev = __shfl_up_sync(FULL, eb >> 2, 1);
+                const bool dup = active && lane > 0 && nb_prev == (uint32_t)nb;
+                const bool any_dup = __any_sync(FULL, dup);
+                const int d = nb - a - 1;
+                const bool dense = active && d >= 0 && d < W;
+                if (active) { if (dense) contrib++; else far++; }
+                float *cell = dense ? &acc[d * 4 + (int)(al_a * 2u + ((eb >> 1) & 1u))] : nullptr;
+                const bool high = hi_a && (eb & 1u);
+                if (!any_dup) {
+                    if (dense) {
+                        float x = *cell;
+                        x = high ? x + 1.0f : (float)((double)x + edge_weight);      // SubEdge::addSubEdge :40-43, :62-65
+                        *cell = x;
+                    }
+                } else {
+                    // two calls of one merged read at the same position: keep the read's own order
+                    for (int l = 0; l < 32; l++) {
+                        if (lane == l && dense) {
+                            float x = *cell;
+                            x = high ? x + 1.0f : (float)((double)x + edge_weight);
+                            *cell = x;
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                if (!__any_sync(FULL, active)) break;
+            }
         }
     }
     __syncwarp();
@@ -431,7 +500,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
             cudaEventRecord(ctx->kev[2], st);
             k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
                 n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
-                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p);
+                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, (uint64_t)n_merged);
             cudaEventRecord(ctx->kev[3], st);
             ctx->stats.kernel_launches++;
         }
