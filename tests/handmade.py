@@ -76,3 +76,37 @@ def read_from_ref(ref, pos, cigar, name, edits=None, qual=30, **kw):
     d = dict(name=name, pos=pos, cigar=cigar, seq="".join(seq), qual=[qual] * len(seq))
     d.update(kw)
     return d
+
+
+class ManualUnion(ManualContig):
+    """A hand-written union variant map (std::map<int, MultiGenomeVar>): entries are dicts
+    pos, nor=(REF, ALT, hp1_is_alt, ps[, gt_kind]) | None, tum=(REF, ALT, gt_kind[, ps]) | None, somatic=0|1, derive=0|1|2."""
+
+    def __init__(self, ref, entries, reads):
+        entries = sorted(entries, key=lambda e: e["pos"])
+        base = []
+        for e in entries:
+            rec = e.get("nor") or e["tum"]
+            base.append((e["pos"], rec[0], rec[1], (e["nor"][2] if e.get("nor") else 0)))
+        super().__init__(ref, base, reads)
+        n = len(entries)
+        self.var_ps = np.array([(e["nor"][3] if e.get("nor") else 0) for e in entries], np.int32)
+        self.var_gt_kind = np.array([((e["nor"][4] if len(e["nor"]) > 4 else 1) if e.get("nor") else 0) for e in entries], np.uint8)
+        self.nor_present = np.array([1 if e.get("nor") else 0 for e in entries], np.uint8)
+        self.tum_present = np.array([1 if e.get("tum") else 0 for e in entries], np.uint8)
+        tum = [e.get("tum") or ("N", "N", 0) for e in entries]
+        self.tum_ref0 = np.array([ord(t[0][0]) for t in tum], np.uint8)
+        self.tum_alt0 = np.array([ord(t[1][0]) for t in tum], np.uint8)
+        self.tum_ref_len = np.array([len(t[0]) for t in tum], np.uint16)
+        self.tum_alt_len = np.array([len(t[1]) for t in tum], np.uint16)
+        self.tum_gt = np.array([t[2] for t in tum], np.uint8)
+        self.tum_hp1_is_alt = np.zeros(n, np.uint8)
+        self.tum_ps = np.array([(t[3] if len(t) > 3 else -1) for t in tum], np.int32)
+        blob, off = b"", [0]
+        for t in tum:
+            blob += t[0].encode() + b"\0" + t[1].encode() + b"\0"
+            off.append(len(blob))
+        self.tum_str, self.tum_str_off = blob, np.array(off, np.uint32)
+        self.is_somatic = np.array([e.get("somatic", 0) for e in entries], np.uint8)
+        self.derive_hp = np.array([e.get("derive", 0) for e in entries], np.int8)
+        self.var_is_somatic = self.is_somatic.copy()
