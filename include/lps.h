@@ -250,6 +250,13 @@ enum { LPS_PB_ALT = 0, LPS_PB_A, LPS_PB_C, LPS_PB_G, LPS_PB_T, LPS_PB_UNKNOWN, L
 /* read-case counters of SomaticData (HaplotagType.h:226-233), filled by classifyReadsByCase                      */
 enum { LPS_CASE_CLEAN_HP3 = 0, LPS_CASE_PURE_H1_1, LPS_CASE_PURE_H2_1, LPS_CASE_PURE_H3, LPS_CASE_MIXED, LPS_CASE_UNTAG,
        LPS_CASE_FIELDS };
+/* derived per-position ratios: PosBase::{VAF, nonDelVAF, filteredMpqVAF, lowMpqReadRatio, delRatio} and, tumor pass only,
+ * SomaticData::{Mixed_HP, pure_H1_1, pure_H2_1, pure_H3}_readRatio (HaplotagType.h:184-190, 239-242)                  */
+enum { LPS_RF_VAF = 0, LPS_RF_NONDEL_VAF, LPS_RF_MPQ_VAF, LPS_RF_LOW_MPQ_RATIO, LPS_RF_DEL_RATIO, LPS_RF_MIXED_RATIO,
+       LPS_RF_PURE_H1_1_RATIO, LPS_RF_PURE_H2_1_RATIO, LPS_RF_PURE_H3_RATIO, LPS_RF_FIELDS };
+/* PosBase::{germlineHaplotypeImbalanceRatio, percentageOfGermlineHp}, SomaticData::{allelicImbalanceRatio,
+ * somaticHaplotypeImbalanceRatio} (tumor pass)                                                                       */
+enum { LPS_RD_GERMLINE_IMBALANCE = 0, LPS_RD_PCT_GERMLINE_HP, LPS_RD_ALLELIC_IMBALANCE, LPS_RD_SOMATIC_IMBALANCE, LPS_RD_FIELDS };
 enum { LPS_READHP_FIELDS = 9 };   /* ReadHP: unTag 0, H1, H2, H3, H4, H1_1, H1_2, H2_1, H2_2 (HaplotagType.h:97-108)  */
 enum { LPS_WINDOW = 100, LPS_WINDOW_BINS = 2 * LPS_WINDOW + 1 };   /* getWindowsDiffRef windowSize, offsets -100..100 */
 
@@ -279,6 +286,11 @@ typedef struct {
     const int32_t *window_hist;    /* [n_tum][2][LPS_WINDOW_BINS] entries of PosSomaticOffsetBase[allele] per offset
                                       (bin = offset + 100): all the DenseAlt filter reads (SomaticVarCaller.cpp:1160) */
     uint64_t n_window_items;       /* (alignment, tumor position) pairs whose window was scanned                  */
+    /* ---- postProcess of both passes (SomaticVarCaller.cpp:176-210, 520-603; calculateBaseCommonInfo :13-40), host arithmetic
+     * in the reference's own float / double types; zero for slots whose tumor record is not a SNP / insertion / deletion ---- */
+    const float *ratios_f;         /* [n_tum][LPS_RF_FIELDS]                                                      */
+    const double *ratios_d;        /* [n_tum][LPS_RD_FIELDS]                                                      */
+    const int32_t *case_read_count;/* [n_tum] SomaticData::CaseReadCount (tumor pass)                             */
     /* per alignment, CSR: every variant that entered variantsHP or tumorSnpPosVec.  lps_call.allele = variantsHP
      * (SnpHP 1 H1, 2 H2, 3 H3, 0 none), lps_call.quality bit0 = in tumorSnpPosVec, bit1 = in tumorAllelePosVec
      * (ReadVarHpCount::posHpPairs, tumorPosReadCorrBaseHP; SomaticVarCaller.cpp:407-459)                         */

@@ -110,9 +110,12 @@ WINDOW_BINS = 201
 class LpsExtractResult(C.Structure):
     _fields_ = [("n_tum", C.c_int32), ("tum_var", i32p), ("pos_base", i32p), ("read_hp_count", i32p), ("reads", LpsReadTags),
                 ("somatic_read_hp_count", i32p), ("case_count", i32p), ("allele_count", i32p), ("window_hist", i32p),
-                ("n_window_items", C.c_uint64), ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))]
+                ("n_window_items", C.c_uint64), ("ratios_f", f32p), ("ratios_d", C.POINTER(C.c_double)), ("case_read_count", i32p),
+                ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))]
 
 
+RF_FIELDS = ["vaf", "non_del_vaf", "mpq_vaf", "low_mpq_ratio", "del_ratio", "mixed_ratio", "pure_h1_1_ratio", "pure_h2_1_ratio", "pure_h3_ratio"]
+RD_FIELDS = ["germline_imbalance", "pct_germline_hp", "allelic_imbalance", "somatic_imbalance"]
 SOMATIC_COUNTERS = ["total_alignment", "total_supplementary", "total_secondary", "total_unmapped", "total_tag", "total_untag",
                     "total_lower_quality", "total_other_case", "total_empty_variant", "total_high_similarity", "total_cross_two_block",
                     "total_without_variant", "total_read_only_h3"]

@@ -376,3 +376,61 @@ void lps_host_sweep(const lps_phase_params *p, int32_t N, int32_t W, const int32
     }
     if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
 }
+
+
+// ---- postProcess of the two extract passes (reference src/somatic_haplotag/SomaticVarCaller.cpp:176-210, 520-603) ----
+namespace {
+inline float vaf_of(int alt, int depth) { return (depth == 0 || alt == 0) ? 0.0f : (float)alt / (float)depth; }      // base_analysis::calculateVAF
+inline double imbalance_of(int h1, int h2, int total) {                                                               // calculateHaplotypeImbalanceRatio
+    if (h1 > 0 && h2 > 0) return h1 > h2 ? (double)h1 / (double)total : (double)h2 / (double)total;
+    if (h1 == 0 && h2 == 0) return 0.0;
+    return 1.0;
+}
+}  // namespace
+
+void lps_host_post_process(int n_tum, const int32_t *tum_var, const uint8_t *t_alt0, const uint16_t *t_ref_len, const uint16_t *t_alt_len,
+                           const int32_t *pos_base, const int32_t *read_hp_count, const int32_t *case_count, bool tumor, float *rf,
+                           double *rd, int32_t *case_reads) {
+    for (int s = 0; s < n_tum; s++) {
+        float *f = rf + (size_t)s * LPS_RF_FIELDS;
+        double *d = rd + (size_t)s * LPS_RD_FIELDS;
+        for (int k = 0; k < LPS_RF_FIELDS; k++) f[k] = 0.0f;
+        for (int k = 0; k < LPS_RD_FIELDS; k++) d[k] = 0.0;
+        case_reads[s] = 0;
+        const int v = tum_var[s], rl = t_ref_len[v], al = t_alt_len[v];
+        const bool snp = rl == 1 && al == 1, ins = rl == 1 && al > 1, del = rl > 1 && al == 1;
+        if (!snp && !ins && !del) continue;
+        const int32_t *pb = pos_base + (size_t)s * LPS_PB_FIELDS, *hp = read_hp_count + (size_t)s * 9;
+        // calculateBaseCommonInfo (:13-40): a SNP counts the reads that show the tumor ALT base, an indel the ALT observations
+        int alt = pb[LPS_PB_ALT], mpq_alt = pb[LPS_PB_MPQ_ALT];
+        if (snp) {
+            const int k = t_alt0[v] == 'A' ? 0 : t_alt0[v] == 'C' ? 1 : t_alt0[v] == 'G' ? 2 : t_alt0[v] == 'T' ? 3 : -1;
+            alt = k < 0 ? 0 : pb[LPS_PB_A + k];             // getBaseCount throws for other letters; such records do not occur in a VCF
+            mpq_alt = k < 0 ? 0 : pb[LPS_PB_MPQ_A + k];
+        }
+        const int depth = pb[LPS_PB_DEPTH], mpq_depth = pb[LPS_PB_MPQ_DEPTH], dele = pb[LPS_PB_DEL];
+        f[LPS_RF_VAF] = vaf_of(alt, depth);
+        f[LPS_RF_MPQ_VAF] = vaf_of(mpq_alt, mpq_depth);
+        f[LPS_RF_NONDEL_VAF] = vaf_of(alt, depth - dele);
+        f[LPS_RF_LOW_MPQ_RATIO] = depth == 0 ? 0.0f : (float)(depth - mpq_depth) / (float)depth;
+        f[LPS_RF_DEL_RATIO] = (depth == 0 || dele == 0) ? 0.0f : (float)dele / (float)depth;
+        const int h1 = hp[1], h2 = hp[2], germ = h1 + h2;
+        d[LPS_RD_GERMLINE_IMBALANCE] = imbalance_of(h1, h2, germ);
+        d[LPS_RD_PCT_GERMLINE_HP] = (depth == 0 || germ == 0) ? 0.0 : (double)germ / (double)depth;
+        if (tumor) {
+            const int32_t *cc = case_count + (size_t)s * LPS_CASE_FIELDS;
+            const int clean = cc[LPS_CASE_CLEAN_HP3], mixed = cc[LPS_CASE_MIXED];
+            case_reads[s] = clean + mixed;
+            if (clean + mixed != 0) {
+                const float den = (float)clean + (float)mixed;
+                f[LPS_RF_MIXED_RATIO] = (float)mixed / den;
+                f[LPS_RF_PURE_H1_1_RATIO] = (float)cc[LPS_CASE_PURE_H1_1] / den;
+                f[LPS_RF_PURE_H2_1_RATIO] = (float)cc[LPS_CASE_PURE_H2_1] / den;
+                f[LPS_RF_PURE_H3_RATIO] = (float)cc[LPS_CASE_PURE_H3] / den;
+            }
+            const int b1 = hp[1] + hp[5], b2 = hp[2] + hp[7];                       // H1 + H1_1, H2 + H2_1
+            d[LPS_RD_ALLELIC_IMBALANCE] = imbalance_of(b1, b2, b1 + b2);
+            d[LPS_RD_SOMATIC_IMBALANCE] = imbalance_of(hp[5], hp[7], hp[5] + hp[7]);
+        }
+    }
+}

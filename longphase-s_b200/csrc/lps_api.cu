@@ -391,6 +391,7 @@ int lps_contig_set_tumor_variants(lps_ctx *ctx, const lps_tumor_variants *t) {
         if (N && (nor_gt.empty() || nor_gt[i] == 1)) last_nor = ctx->h_vpos[i];
     }
     const size_t nt = ctx->h_tum_var.size();
+    ctx->h_t_alt0.assign(t->alt0, t->alt0 + n); ctx->h_t_ref_len.assign(t->ref_len, t->ref_len + n); ctx->h_t_alt_len.assign(t->alt_len, t->alt_len + n);
     DevSomatic &s = ctx->som;
     if (t->nor_present) { TRY(h2d(ctx, ctx->d_nor_present, t->nor_present, n)); s.nor_present = ctx->d_nor_present.p; } else s.nor_present = nullptr;
     TRY(h2d(ctx, ctx->d_tum_present, t->tum_present, n)); s.tum_present = ctx->d_tum_present.p;
@@ -474,6 +475,11 @@ int run_extract(lps_ctx *ctx, const lps_tag_params *p, int mode, lps_extract_res
     const int32_t *h = ctx->h_som_counters.data(), *d = ctx->d_som_counters.p;
     out->n_tum = s.n_tum; out->tum_var = ctx->h_tum_var.data();
     out->pos_base = h + (s.pos_base - d); out->read_hp_count = h + (s.read_hp_count - d);
+    ctx->h_ratios_f.resize((size_t)s.n_tum * LPS_RF_FIELDS + 1); ctx->h_ratios_d.resize((size_t)s.n_tum * LPS_RD_FIELDS + 1);
+    ctx->h_case_reads.resize((size_t)s.n_tum + 1);
+    lps_host_post_process(s.n_tum, ctx->h_tum_var.data(), ctx->h_t_alt0.data(), ctx->h_t_ref_len.data(), ctx->h_t_alt_len.data(), out->pos_base,
+                          out->read_hp_count, h + (s.case_count - d), tumor, ctx->h_ratios_f.data(), ctx->h_ratios_d.data(), ctx->h_case_reads.data());
+    out->ratios_f = ctx->h_ratios_f.data(); out->ratios_d = ctx->h_ratios_d.data(); out->case_read_count = ctx->h_case_reads.data();
     if (tumor) {
         out->somatic_read_hp_count = h + (s.somatic_read_hp_count - d); out->case_count = h + (s.case_count - d);
         out->allele_count = h + (s.allele_count - d); out->window_hist = h + (s.window_hist - d);

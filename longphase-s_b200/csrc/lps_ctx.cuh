@@ -197,7 +197,11 @@ struct lps_ctx {
     DevSomatic som;
     size_t som_counter_words = 0;
     bool have_tumor_variants = false;
-    std::vector<int32_t> h_tum_var, h_som_counters;
+    std::vector<int32_t> h_tum_var, h_som_counters, h_case_reads;
+    std::vector<uint8_t> h_t_alt0;
+    std::vector<uint16_t> h_t_ref_len, h_t_alt_len;
+    std::vector<float> h_ratios_f;
+    std::vector<double> h_ratios_d;
     DevBuf<int32_t> d_tag_h3, d_tag_end, d_tag_len;
     DevBuf<uint8_t> d_tag_nps;
     DevBuf<int8_t> d_tag_hpb;
@@ -272,5 +276,8 @@ void lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std:
 void lps_host_cnv_intervals(const std::vector<int32_t> &pos, const std::vector<int32_t> &front,
                             const std::vector<int32_t> &back, std::vector<int32_t> &cs, std::vector<int32_t> &ce);
 int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);
+void lps_host_post_process(int n_tum, const int32_t *tum_var, const uint8_t *t_alt0, const uint16_t *t_ref_len, const uint16_t *t_alt_len,
+                           const int32_t *pos_base, const int32_t *read_hp_count, const int32_t *case_count, bool tumor, float *rf,
+                           double *rd, int32_t *case_reads);
 void lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
                     const uint8_t *vote_info, int32_t *node_ps, int8_t *node_hap_ref);

@@ -145,7 +145,10 @@ class Context:
         nt = o.n_tum
         res = self._read_tags(o.reads)
         res.update(n_tum=nt, tum_var=g(o.tum_var, nt, np.int32), pos_base=g(o.pos_base, nt * 15, np.int32).reshape(nt, 15),
-                   read_hp_count=g(o.read_hp_count, nt * 9, np.int32).reshape(nt, 9))
+                   read_hp_count=g(o.read_hp_count, nt * 9, np.int32).reshape(nt, 9),
+                   ratios_f=g(o.ratios_f, nt * len(_ffi.RF_FIELDS), np.float32).reshape(nt, len(_ffi.RF_FIELDS)),
+                   ratios_d=g(o.ratios_d, nt * len(_ffi.RD_FIELDS), np.float64).reshape(nt, len(_ffi.RD_FIELDS)),
+                   case_read_count=g(o.case_read_count, nt, np.int32))
         if tumor:
             res.update(somatic_read_hp_count=g(o.somatic_read_hp_count, nt * 9, np.int32).reshape(nt, 9),
                        case_count=g(o.case_count, nt * 6, np.int32).reshape(nt, 6),

@@ -112,6 +112,9 @@ typedef struct {
     float *derive_similarity;
     int32_t *pos_base, *read_hp_count, *somatic_read_hp_count, *case_count, *allele_count, *window_hist;
     int32_t *hp_before_count, *hp_after_count, *h3_before_count, *h3_after_count, *cover_start, *cover_end;
+    float *ratios_f;         /* [n_tum][LPS_RF_FIELDS] postProcess (extract passes) */
+    double *ratios_d;        /* [n_tum][LPS_RD_FIELDS] */
+    int32_t *case_read_count;
     uint64_t n_window_items;
     uint64_t n_calls;
     uint64_t *call_off;

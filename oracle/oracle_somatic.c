@@ -260,6 +260,8 @@ int orc_somatic(int mode, const lps_read_batch *b, const lps_variants *v, const 
     out->hp_before_count = (int32_t *)calloc(nt * 9, 4); out->hp_after_count = (int32_t *)calloc(nt * 9, 4);
     out->h3_before_count = (int32_t *)calloc(nt * 9, 4); out->h3_after_count = (int32_t *)calloc(nt * 9, 4);
     out->cover_start = (int32_t *)malloc(nt * 4); out->cover_end = (int32_t *)malloc(nt * 4);
+    out->ratios_f = (float *)calloc(nt * LPS_RF_FIELDS, 4); out->ratios_d = (double *)calloc(nt * LPS_RD_FIELDS, 8);
+    out->case_read_count = (int32_t *)calloc(nt, 4);
     for (size_t i = 0; i < nt; i++) { out->cover_start[i] = INT_MAX; out->cover_end[i] = INT_MIN; }
     out->call_off = (uint64_t *)calloc((size_t)n + 2, 8);
     callvec cv = {0, 0, 0};
@@ -446,6 +448,47 @@ int orc_somatic(int mode, const lps_read_batch *b, const lps_variants *v, const 
         }
         out->read_hp[r] = (int8_t)hp; out->pq[r] = pq;
     }
+    /* postProcess of the extract passes: calculateBaseCommonInfo (SomaticVarCaller.cpp:13-40) via base_analysis
+     * (HaplotagStrategy.h:162-191), ExtractNorDataChrProcessor::postProcess (:176-210), ExtractTumDataChrProcessor::postProcess
+     * (:520-603).  Untouched positions keep the constructors' zeros, which is also what the formulas give for them. */
+    if (mode != ORC_SOM_TAG) {
+        for (int sl = 0; sl < out->n_tum; sl++) {
+            const int vi = out->tum_var[sl];
+            const int ty = var_type(t->ref_len[vi], t->alt_len[vi]);
+            if (ty != VT_SNP && ty != VT_INS && ty != VT_DEL) continue;
+            const int32_t *pb = out->pos_base + (size_t)sl * LPS_PB_FIELDS, *hpc = out->read_hp_count + (size_t)sl * 9;
+            float *f = out->ratios_f + (size_t)sl * LPS_RF_FIELDS;
+            double *d = out->ratios_d + (size_t)sl * LPS_RD_FIELDS;
+            int alt = pb[LPS_PB_ALT], malt = pb[LPS_PB_MPQ_ALT];
+            if (ty == VT_SNP) {
+                const char ab = (char)t->alt0[vi];
+                const int kk = ab == 'A' ? 0 : ab == 'C' ? 1 : ab == 'G' ? 2 : ab == 'T' ? 3 : -1;
+                alt = kk < 0 ? 0 : pb[LPS_PB_A + kk]; malt = kk < 0 ? 0 : pb[LPS_PB_MPQ_A + kk];
+            }
+            const int depth = pb[LPS_PB_DEPTH], mdepth = pb[LPS_PB_MPQ_DEPTH], del = pb[LPS_PB_DEL];
+#define VAF_(a_, d_) (((d_) == 0 || (a_) == 0) ? 0.0f : (float)(a_) / (float)(d_))
+            f[LPS_RF_VAF] = VAF_(alt, depth); f[LPS_RF_MPQ_VAF] = VAF_(malt, mdepth); f[LPS_RF_NONDEL_VAF] = VAF_(alt, depth - del);
+            f[LPS_RF_LOW_MPQ_RATIO] = depth == 0 ? 0.0f : (float)(depth - mdepth) / (float)depth;
+            f[LPS_RF_DEL_RATIO] = VAF_(del, depth);
+#define IMB_(a_, b_) (((a_) > 0 && (b_) > 0) ? ((a_) > (b_) ? (double)(a_) / (double)((a_) + (b_)) : (double)(b_) / (double)((a_) + (b_))) : (((a_) == 0 && (b_) == 0) ? 0.0 : 1.0))
+            const int g1 = hpc[1], g2 = hpc[2];
+            d[LPS_RD_GERMLINE_IMBALANCE] = IMB_(g1, g2);
+            d[LPS_RD_PCT_GERMLINE_HP] = (depth == 0 || g1 + g2 == 0) ? 0.0 : (double)(g1 + g2) / (double)depth;
+            if (mode == ORC_SOM_EXTRACT_TUMOR) {
+                const int32_t *cc = out->case_count + (size_t)sl * LPS_CASE_FIELDS;
+                const int clean = cc[LPS_CASE_CLEAN_HP3], mixed = cc[LPS_CASE_MIXED];
+                out->case_read_count[sl] = clean + mixed;
+                if (clean + mixed != 0) {
+                    const float den = (float)clean + (float)mixed;
+                    f[LPS_RF_MIXED_RATIO] = (float)mixed / den; f[LPS_RF_PURE_H1_1_RATIO] = (float)cc[LPS_CASE_PURE_H1_1] / den;
+                    f[LPS_RF_PURE_H2_1_RATIO] = (float)cc[LPS_CASE_PURE_H2_1] / den; f[LPS_RF_PURE_H3_RATIO] = (float)cc[LPS_CASE_PURE_H3] / den;
+                }
+                const int b1 = hpc[1] + hpc[5], b2 = hpc[2] + hpc[7];
+                d[LPS_RD_ALLELIC_IMBALANCE] = IMB_(b1, b2);
+                d[LPS_RD_SOMATIC_IMBALANCE] = IMB_(hpc[5], hpc[7]);
+            }
+        }
+    }
     for (int r = n; r >= 0; r--) if (r == n || out->call_off[r] > cv.n) out->call_off[r] = cv.n;
     out->call_off[n] = cv.n;
     out->n_calls = cv.n;
@@ -459,6 +502,6 @@ void orc_somatic_free(orc_somatic_out *o) {
     free(o->h3); free(o->n_ps); free(o->end_pos); free(o->read_len); free(o->derive_similarity); free(o->pos_base);
     free(o->read_hp_count); free(o->somatic_read_hp_count); free(o->case_count); free(o->allele_count); free(o->window_hist);
     free(o->hp_before_count); free(o->hp_after_count); free(o->h3_before_count); free(o->h3_after_count); free(o->cover_start);
-    free(o->cover_end); free(o->call_off); free(o->calls);
+    free(o->cover_end); free(o->call_off); free(o->calls); free(o->ratios_f); free(o->ratios_d); free(o->case_read_count);
     memset(o, 0, sizeof(*o));
 }

@@ -97,7 +97,8 @@ class OrcSomaticOut(C.Structure):
                 ("read_len", i32p), ("derive_similarity", f32p), ("pos_base", i32p), ("read_hp_count", i32p),
                 ("somatic_read_hp_count", i32p), ("case_count", i32p), ("allele_count", i32p), ("window_hist", i32p),
                 ("hp_before_count", i32p), ("hp_after_count", i32p), ("h3_before_count", i32p), ("h3_after_count", i32p),
-                ("cover_start", i32p), ("cover_end", i32p), ("n_window_items", C.c_uint64), ("n_calls", C.c_uint64),
+                ("cover_start", i32p), ("cover_end", i32p), ("ratios_f", f32p), ("ratios_d", C.POINTER(C.c_double)), ("case_read_count", i32p),
+                ("n_window_items", C.c_uint64), ("n_calls", C.c_uint64),
                 ("call_off", u64p), ("calls", callp)]
 
 
@@ -344,6 +345,9 @@ def _somatic_fields(self, o):
     self.allele_count = g(o.allele_count, nt * 2, np.int32).reshape(nt, 2)
     self.window_hist = g(o.window_hist, nt * 2 * 201, np.int32).reshape(nt, 2, 201)
     self.cover_start, self.cover_end = g(o.cover_start, nt, np.int32), g(o.cover_end, nt, np.int32)
+    self.ratios_f = g(o.ratios_f, nt * 9, np.float32).reshape(nt, 9)
+    self.ratios_d = g(o.ratios_d, nt * 4, np.float64).reshape(nt, 4)
+    self.case_read_count = g(o.case_read_count, nt, np.int32)
     self.n_window_items = int(o.n_window_items)
     self.call_off = g(o.call_off, n + 1, np.uint64)
     self.calls = g(o.calls, o.n_calls, _ffi.CALL_DTYPE)

@@ -98,6 +98,8 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
     out->hp_before_count = zalloc<int32_t>((size_t)nt * 9); out->hp_after_count = zalloc<int32_t>((size_t)nt * 9);
     out->h3_before_count = zalloc<int32_t>((size_t)nt * 9); out->h3_after_count = zalloc<int32_t>((size_t)nt * 9);
     out->cover_start = zalloc<int32_t>(nt); out->cover_end = zalloc<int32_t>(nt);
+    out->ratios_f = zalloc<float>((size_t)nt * LPS_RF_FIELDS); out->ratios_d = zalloc<double>((size_t)nt * LPS_RD_FIELDS);
+    out->case_read_count = zalloc<int32_t>(nt);
     for (int i = 0; i < nt; i++) { out->cover_start[i] = INT_MAX; out->cover_end[i] = INT_MIN; }
     out->call_off = zalloc<uint64_t>((size_t)n + 1);
     std::vector<lps_call> calls;
@@ -249,12 +251,23 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
     out->calls = zalloc<lps_call>(calls.size());
     if (!calls.empty()) memcpy(out->calls, calls.data(), sizeof(lps_call) * calls.size());
 
+    // the reference's own postProcess (ratios of every touched position)
+    if (mode == 0) norProc->postProcess(chr, currentVariants);
+    else if (mode == 1) tumProc->postProcess(chr, currentVariants);
+    auto fill_ratios = [&](size_t sl, const PosBase &pb) {
+        float *f = out->ratios_f + sl * LPS_RF_FIELDS;
+        double *d = out->ratios_d + sl * LPS_RD_FIELDS;
+        f[LPS_RF_VAF] = pb.VAF; f[LPS_RF_NONDEL_VAF] = pb.nonDelVAF; f[LPS_RF_MPQ_VAF] = pb.filteredMpqVAF;
+        f[LPS_RF_LOW_MPQ_RATIO] = pb.lowMpqReadRatio; f[LPS_RF_DEL_RATIO] = pb.delRatio;
+        d[LPS_RD_GERMLINE_IMBALANCE] = pb.germlineHaplotypeImbalanceRatio; d[LPS_RD_PCT_GERMLINE_HP] = pb.percentageOfGermlineHp;
+    };
     if (mode == 0) {
         for (auto &kv : chrPosNorBase[chr]) {
             auto s = slot_of_pos.find(kv.first);
             if (s == slot_of_pos.end()) { fprintf(stderr, "ref_tap_somatic: PosBase at a non-tumor position\n"); return -1; }
             fill_pos_base(out->pos_base + (size_t)s->second * LPS_PB_FIELDS, kv.second);
             fill_hp9(out->read_hp_count + (size_t)s->second * 9, kv.second.ReadHpCount);
+            fill_ratios((size_t)s->second, kv.second);
         }
     } else if (mode == 1) {
         for (auto &kv : chrPosSomaticInfo[chr]) {
@@ -269,6 +282,14 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
             cc[LPS_CASE_CLEAN_HP3] = sd.totalCleanHP3Read; cc[LPS_CASE_PURE_H1_1] = sd.pure_H1_1_read; cc[LPS_CASE_PURE_H2_1] = sd.pure_H2_1_read;
             cc[LPS_CASE_PURE_H3] = sd.pure_H3_read; cc[LPS_CASE_MIXED] = sd.Mixed_HP_read; cc[LPS_CASE_UNTAG] = sd.unTag;
             out->allele_count[sl * 2] = sd.alleleCount[0]; out->allele_count[sl * 2 + 1] = sd.alleleCount[1];
+            fill_ratios(sl, sd.base);
+            out->ratios_f[sl * LPS_RF_FIELDS + LPS_RF_MIXED_RATIO] = sd.Mixed_HP_readRatio;
+            out->ratios_f[sl * LPS_RF_FIELDS + LPS_RF_PURE_H1_1_RATIO] = sd.pure_H1_1_readRatio;
+            out->ratios_f[sl * LPS_RF_FIELDS + LPS_RF_PURE_H2_1_RATIO] = sd.pure_H2_1_readRatio;
+            out->ratios_f[sl * LPS_RF_FIELDS + LPS_RF_PURE_H3_RATIO] = sd.pure_H3_readRatio;
+            out->ratios_d[sl * LPS_RD_FIELDS + LPS_RD_ALLELIC_IMBALANCE] = sd.allelicImbalanceRatio;
+            out->ratios_d[sl * LPS_RD_FIELDS + LPS_RD_SOMATIC_IMBALANCE] = sd.somaticHaplotypeImbalanceRatio;
+            out->case_read_count[sl] = sd.CaseReadCount;
             for (int a = 0; a < 2; a++)
                 for (auto &ob : sd.PosSomaticOffsetBase[a]) {
                     if (ob.first < -LPS_WINDOW || ob.first > LPS_WINDOW) { fprintf(stderr, "ref_tap_somatic: offset out of range\n"); return -1; }
@@ -307,6 +328,6 @@ extern "C" void ref_tap_somatic_free(orc_somatic_out *o) {
     free(o->h3); free(o->n_ps); free(o->end_pos); free(o->read_len); free(o->derive_similarity); free(o->pos_base);
     free(o->read_hp_count); free(o->somatic_read_hp_count); free(o->case_count); free(o->allele_count); free(o->window_hist);
     free(o->hp_before_count); free(o->hp_after_count); free(o->h3_before_count); free(o->h3_after_count); free(o->cover_start);
-    free(o->cover_end); free(o->call_off); free(o->calls);
+    free(o->cover_end); free(o->call_off); free(o->calls); free(o->ratios_f); free(o->ratios_d); free(o->case_read_count);
     memset(o, 0, sizeof(*o));
 }

@@ -12,7 +12,7 @@ host = importlib.import_module("longphase_s_b200.host")
 
 MODES = ["extract_normal", "extract_tumor", "somatic_tag"]
 PER_SLOT = ["pos_base", "read_hp_count", "somatic_read_hp_count", "case_count", "window_hist", "hp_before_count", "hp_after_count",
-            "h3_before_count", "h3_after_count", "cover_start", "cover_end"]
+            "h3_before_count", "h3_after_count", "cover_start", "cover_end", "ratios_f", "ratios_d", "case_read_count"]
 # SomaticData::alleleCount is never initialised by the reference (HaplotagType.h:284-293: absent from the constructor's
 # initialiser list) and never read; it is compared between the CUDA path and the oracle only.
 
@@ -107,10 +107,11 @@ def check_gpu_somatic(c, tp, mode, ctx):
         assert res["derive_similarity"].tobytes() == orc.derive_similarity.tobytes()
         assert res["stats"] == stats_from(orc, c, tp)
     elif mode == "extract_tumor":
-        keys = ["pos_base", "read_hp_count", "somatic_read_hp_count", "case_count", "allele_count", "window_hist"]
+        keys = ["pos_base", "read_hp_count", "somatic_read_hp_count", "case_count", "allele_count", "window_hist", "ratios_f", "ratios_d",
+                "case_read_count"]
         assert res["n_window_items"] == orc.n_window_items
     else:
-        keys = ["pos_base", "read_hp_count"]
+        keys = ["pos_base", "read_hp_count", "ratios_f", "ratios_d"]
     for k in keys:
         assert np.array_equal(res[k], getattr(orc, k)), (mode, k)
     if mode != "extract_normal":
