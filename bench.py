@@ -27,12 +27,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb, a chr1-sized share of the genome), 30x ONT-like "
-            "20 kb reads, 1 het variant/kb (10% indels), ONT error model")
+WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb, a chr1-sized share of the genome), {depth:g}x ONT-like "
+            "{kb:g} kb reads, 1 het variant / {sp:g} bp (10% indels), ONT error model")
 
 
 def synth_kwargs(args, seed):
-    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000), indel_frac=0.1, depth=30.0, mean_len=20000.0)
+    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000), indel_frac=0.1, depth=args.depth, mean_len=args.mean_len,
+                variant_rate=1.0 / args.variant_spacing)
 
 
 def algorithmic_bytes_k1(contig, status, n_calls):
@@ -138,6 +139,9 @@ def main():
     ap.add_argument("--contig-mb", type=float, default=64.0)
     ap.add_argument("--contigs-per-gpu", type=int, default=4)
     ap.add_argument("--cpu-sample-mb", type=float, default=8.0)
+    ap.add_argument("--depth", type=float, default=30.0)               # C5 stress: --depth 120 --mean-len 50000 --variant-spacing 300
+    ap.add_argument("--mean-len", type=float, default=20000.0)
+    ap.add_argument("--variant-spacing", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
     args = ap.parse_args()
@@ -164,7 +168,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
                 "allele_calls_per_s": res["allele_calls_per_s"],
-                "config": {"workload": WORKLOAD.format(n=args.contigs_per_gpu, mb=args.contig_mb, tot=args.contigs_per_gpu * args.contig_mb),
+                "config": {"workload": WORKLOAD.format(n=args.contigs_per_gpu, mb=args.contig_mb, tot=args.contigs_per_gpu * args.contig_mb, depth=args.depth, kb=args.mean_len / 1e3, sp=args.variant_spacing),
                            "sample": res["sample"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -331,7 +335,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
         "allele_calls_per_s": total_calls / (ms_step * 1e-3),
-        "config": {"workload": WORKLOAD.format(n=C_, mb=args.contig_mb, tot=C_ * args.contig_mb), "contigs_per_gpu": C_,
+        "config": {"workload": WORKLOAD.format(n=C_, mb=args.contig_mb, tot=C_ * args.contig_mb, depth=args.depth, kb=args.mean_len / 1e3, sp=args.variant_spacing), "contigs_per_gpu": C_,
                    "reads_per_gpu": n_reads_gpu, "variants_per_gpu": int(sum(c.n_var for c in contigs)), "allele_calls_per_gpu": calls_gpu,
                    "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "input_bytes_per_gpu": input_bytes,
                    "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),

@@ -49,7 +49,7 @@ constexpr int FETCH = LPS_FETCH;              // work items claimed per atomic b
 #endif
 constexpr int KOPS = LPS_KOPS;                 // CIGAR ops per lane and chunk (32 * KOPS ops per chunk)
 constexpr int CTAS_PER_SM = LPS_CTAS_PER_SM;   // resident CTAs per SM the register budget is sized for
-constexpr int CAND_CAP = 256;        // candidates buffered per warp in shared memory
+constexpr int CAND_CAP = 512;        // 8-byte candidates buffered per warp in shared memory (256 of the 16-byte somatic ones)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t PAD_OP = 1u;     // zero-length insertion: advances nothing
 
@@ -1237,26 +1237,24 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             for (uint32_t i = 0; i < hc.overflow_reads.v; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
             LPS_CUDA(ctx, ctx->d_overflow_off.reserve(off.size()));
             LPS_CUDA(ctx, cudaMemcpy(ctx->d_overflow_off.p, off.data(), 8 * off.size(), cudaMemcpyHostToDevice));
-            DevBuf<Cand> ovf;
-            LPS_CUDA(ctx, ovf.reserve((size_t)off.back() + 1));
+            // persistent scratch of the context: the dense configs (C5) take this path on every call
+            LPS_CUDA(ctx, ctx->d_ovf_cand.reserve(8 * ((size_t)off.back() + 2)));
             K1Args b2 = a;
-            b2.overflow_reads = ctx->d_overflow_reads.p; b2.overflow_off = ctx->d_overflow_off.p; b2.overflow_buf = ovf.p;
+            b2.overflow_reads = ctx->d_overflow_reads.p; b2.overflow_off = ctx->d_overflow_off.p; b2.overflow_buf = reinterpret_cast<Cand *>(ctx->d_ovf_cand.p);
             b2.overflow_list_cap = hc.overflow_reads.v;
             // the overflow pass must not append the clips / counters of these reads a second time
             b2.clip_cap = 0;
-            DevBuf<CallCounters> scratch;
-            LPS_CUDA(ctx, scratch.reserve(1));
-            LPS_CUDA(ctx, cudaMemcpyAsync(scratch.p, ctx->d_counters.p, sizeof(CallCounters), cudaMemcpyDeviceToDevice, st));
-            b2.counters = scratch.p;
+            LPS_CUDA(ctx, ctx->d_counters2.reserve(1));
+            LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters2.p, ctx->d_counters.p, sizeof(CallCounters), cudaMemcpyDeviceToDevice, st));
+            b2.counters = ctx->d_counters2.p;
             const int g2 = ((int)hc.overflow_reads.v + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
             launch_k1(mode, g2, st, b2);
             ctx->stats.kernel_launches++;
             LPS_CUDA(ctx, cudaGetLastError());
             CallCounters h2;
-            LPS_CUDA(ctx, cudaMemcpyAsync(&h2, scratch.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
+            LPS_CUDA(ctx, cudaMemcpyAsync(&h2, ctx->d_counters2.p, sizeof(h2), cudaMemcpyDeviceToHost, st));
             LPS_CUDA(ctx, cudaStreamSynchronize(st));
             hc.tmp_calls.v = h2.tmp_calls.v; hc.n_calls.v = h2.n_calls.v; hc.wd_items.v = h2.wd_items.v; hc.aborted_reads.v = h2.aborted_reads.v;
-            ovf.release(); scratch.release();
         }
         ctx->n_wd_items = hc.wd_items.v;
         if (hc.tmp_calls.v <= ctx->d_calls_tmp.cap && hc.clips.v <= ctx->d_clip_keys.cap && hc.wd_items.v <= ctx->d_wd_items.cap) break;

@@ -167,7 +167,8 @@ struct lps_ctx {
     DevBuf<unsigned long long> d_dbg_times;
     int sm_count = 148;
     DevBuf<int32_t> d_num_runs;
-    DevBuf<CallCounters> d_counters;
+    DevBuf<CallCounters> d_counters, d_counters2;
+    DevBuf<uint8_t> d_ovf_cand;                     // candidate lists of the overflow pass (reads with more candidates than the smem buffer)
     DevBuf<uint32_t> d_overflow_reads;
     DevBuf<uint64_t> d_overflow_cand, d_overflow_off;
     DevBuf<uint8_t> d_cub_tmp;
