@@ -31,8 +31,8 @@ WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb,
             "{kb:g} kb reads, 1 het variant / {sp:g} bp (10% indels), ONT error model")
 
 
-def synth_kwargs(args, seed):
-    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000), indel_frac=0.1, depth=args.depth, mean_len=args.mean_len,
+def synth_kwargs(args, seed, scale=1.0):
+    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000 * scale), indel_frac=0.1, depth=args.depth, mean_len=args.mean_len,
                 variant_rate=1.0 / args.variant_spacing)
 
 
@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--variant-spacing", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
+    ap.add_argument("--unequal", type=int, default=0)   # 1: contig sizes +-25 % around --contig-mb (the largest one then bounds the step)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -191,7 +192,9 @@ def main():
     # contigs in flight per GPU: each needs a host thread, so never more than this rank's share of the host cores
     C_ = max(1, min(args.contigs_per_gpu, ncores // world))
     t_gen = time.time()
-    contigs = [synth_mod.Contig(**synth_kwargs(args, 100 + 16 * rank + i)) for i in range(C_)]
+    # unequal contigs (a genome's are): same total, +-25 % around --contig-mb
+    shape = [1.25, 0.9, 1.1, 0.75] if args.unequal and C_ % 4 == 0 else [1.0]
+    contigs = [synth_mod.Contig(**synth_kwargs(args, 100 + 16 * rank + i, shape[i % len(shape)])) for i in range(C_)]
     t_gen = time.time() - t_gen
     params = ffi.default_phase_params(True)
     # one context (own stream, own scratch) per contig in flight, driven by its own host thread: the reference runs its contig
@@ -261,9 +264,9 @@ def main():
         for ctx in ctxs:
             ctx.event_record(slot)
         t0 = time.perf_counter()
-        out = None
-        for _ in range(steps):
-            out = run_all(fn)
+        # every host thread runs its `steps` passes back to back, with no barrier between steps: like the reference's contig loop,
+        # the threads drift out of lockstep, so the host phases of one contig overlap the kernels of another
+        out = run_all(lambda i: [fn(i) for _ in range(steps)][-1])
         for ctx in ctxs:
             ctx.event_record(slot + 1)
         barrier()
