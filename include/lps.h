@@ -333,6 +333,31 @@ typedef struct {
  * (src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-579, src/haplotag/HaplotagStrategy.cpp:452-668).          */
 int lps_somatic_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls, lps_somatic_tag_result *out);
 
+/* ---- tumor purity: the host math that consumes the two extract passes ---------------------------------------------- *
+ * TumorPurityEstimator::estimateTumorPurity (src/somatic_haplotag/TumorPurityEstimator.cpp:31-84).  One entry per tumor position
+ * of the job, contigs concatenated in chrVec order: the `ratios_d` / `read_hp_count` columns of lps_extract_result of the TUMOR
+ * pass (germline imbalance) and of the NORMAL pass (germline imbalance, percentage of germline HP reads, ReadHpCount[H1], [H2]).
+ * Positions no read touched may be included: their zero ratios are rejected by the first filters, as in the reference.
+ * Pure host arithmetic (double); no context and no device work.                                                           */
+typedef struct {
+    int32_t n;
+    const double *tumor_germline_imbalance;    /* SomaticData::base.germlineHaplotypeImbalanceRatio                        */
+    const double *normal_germline_imbalance;   /* chrPosNorBase[chr][pos].germlineHaplotypeImbalanceRatio                   */
+    const double *normal_pct_germline_hp;      /* ...percentageOfGermlineHp                                                 */
+    const int32_t *normal_h1, *normal_h2;      /* ...ReadHpCount[H1], ReadHpCount[H2]                                       */
+    uint8_t *used;                             /* optional out [n]: SomaticData::statisticPurity (markStatisticFlag)        */
+} lps_purity_input;
+typedef struct {
+    double purity;                             /* 0.0 when the estimate failed (reference prints an error and uses 0.0)     */
+    int32_t ok;
+    int32_t read_count_threshold;              /* bimodal-valley threshold on the normal germline-HP read count             */
+    double median, q1, q3, iqr, lower_whisker, upper_whisker;   /* BoxPlotValue after the outlier round                    */
+    int32_t n_after_lcvf, n_used;
+    int32_t filtered_normal_imbalance_zero, filtered_tumor_imbalance_zero, filtered_normal_imbalance_high, filtered_normal_read_count,
+            filtered_pct_germline_hp, filtered_valley, filtered_outliers;              /* FilterCounts of the _purity.out log */
+} lps_purity_result;
+int lps_estimate_purity(const lps_purity_input *in, lps_purity_result *out);
+
 /* ---- timing / accounting ------------------------------------------------------------------ */
 typedef struct {
     float ms_call_alleles;   /* device time of the allele-calling kernels of the last call      */

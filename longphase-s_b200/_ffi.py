@@ -128,6 +128,23 @@ class LpsSomaticTagResult(C.Structure):
                 ("calls", C.POINTER(LpsCall))] + [(k, C.c_int64) for k in SOMATIC_COUNTERS] + [("total_hp", C.c_int64 * 9)]
 
 
+f64p = C.POINTER(C.c_double)
+
+
+class LpsPurityInput(C.Structure):
+    _fields_ = [("n", C.c_int32), ("tumor_germline_imbalance", f64p), ("normal_germline_imbalance", f64p), ("normal_pct_germline_hp", f64p),
+                ("normal_h1", i32p), ("normal_h2", i32p), ("used", u8p)]
+
+
+class LpsPurityResult(C.Structure):
+    _fields_ = [("purity", C.c_double), ("ok", C.c_int32), ("read_count_threshold", C.c_int32), ("median", C.c_double), ("q1", C.c_double),
+                ("q3", C.c_double), ("iqr", C.c_double), ("lower_whisker", C.c_double), ("upper_whisker", C.c_double),
+                ("n_after_lcvf", C.c_int32), ("n_used", C.c_int32), ("filtered_normal_imbalance_zero", C.c_int32),
+                ("filtered_tumor_imbalance_zero", C.c_int32), ("filtered_normal_imbalance_high", C.c_int32),
+                ("filtered_normal_read_count", C.c_int32), ("filtered_pct_germline_hp", C.c_int32), ("filtered_valley", C.c_int32),
+                ("filtered_outliers", C.c_int32)]
+
+
 class LpsStats(C.Structure):
     _fields_ = [("ms_call_alleles", C.c_float), ("ms_tag_reads", C.c_float), ("ms_build_edges", C.c_float), ("ms_read_correction", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_kernel_call_alleles", C.c_float),
@@ -157,6 +174,7 @@ SYMBOLS = {
     "lps_extract_normal": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_extract_tumor": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_somatic_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsSomaticTagResult)]),
+    "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -279,3 +279,30 @@ class SomaticHaplotagChrProcessor(_SomaticChrProcessor):
     def processSingleChrom(self, contig, want_calls=True):
         self._submit(contig)
         return self.ctx.somatic_tag_reads(self.tparams, want_calls)
+
+
+class TumorPurityEstimator:
+    """Mirror of reference TumorPurityEstimator (src/somatic_haplotag/TumorPurityEstimator.h:276-349): built from the results of the NORMAL
+    and TUMOR extract passes of every contig (chrVec order), estimateTumorPurity() returns the purity; `result` keeps the box-plot
+    values, the valley threshold and the filter counts of the `_purity.out` log, `used` the per-position statisticPurity flags."""
+
+    def __init__(self, normal_results, tumor_results):
+        cat = lambda rs, k, j: np.ascontiguousarray(np.concatenate([r[k][:, j] for r in rs]))   # noqa: E731
+        self.t_imb = cat(tumor_results, "ratios_d", 0).astype(np.float64)
+        self.n_imb = cat(normal_results, "ratios_d", 0).astype(np.float64)
+        self.n_pct = cat(normal_results, "ratios_d", 1).astype(np.float64)
+        self.n_h1 = cat(normal_results, "read_hp_count", 1).astype(np.int32)
+        self.n_h2 = cat(normal_results, "read_hp_count", 2).astype(np.int32)
+        self.used = np.zeros(len(self.t_imb), np.uint8)
+
+    def estimateTumorPurity(self):
+        P = _ffi.ptr
+        i = _ffi.LpsPurityInput(n=len(self.t_imb), tumor_germline_imbalance=P(self.t_imb, _ffi.f64p), normal_germline_imbalance=P(self.n_imb, _ffi.f64p),
+                                normal_pct_germline_hp=P(self.n_pct, _ffi.f64p), normal_h1=P(self.n_h1, _ffi.i32p), normal_h2=P(self.n_h2, _ffi.i32p),
+                                used=P(self.used, _ffi.u8p))
+        o = _ffi.LpsPurityResult()
+        rc = _ffi.load_library().lps_estimate_purity(C.byref(i), C.byref(o))
+        if rc != 0:
+            raise LpsError(rc, "lps_estimate_purity failed")
+        self.result = {f: getattr(o, f) for f, _ in o._fields_}
+        return o.purity

@@ -107,7 +107,13 @@ class TapSomIn(C.Structure):
                 ("var_str_off", _ffi.u32p), ("var_str", C.c_char_p), ("var_hp1_is_alt", u8p), ("var_ps", i32p), ("nor_gt", u8p),
                 ("nor_present", u8p), ("tum_present", u8p), ("tum_str_off", _ffi.u32p), ("tum_str", C.c_char_p), ("tum_gt", u8p),
                 ("tum_hp1_is_alt", u8p), ("tum_ps", i32p), ("is_somatic", u8p), ("derive_hp", i8p), ("batch", _ffi.LpsReadBatch),
-                ("names", C.c_char_p), ("name_stride", C.c_int32), ("p", _ffi.LpsTagParams), ("stats_out", C.POINTER(C.c_int64))]
+                ("names", C.c_char_p), ("name_stride", C.c_int32), ("p", _ffi.LpsTagParams), ("stats_out", C.POINTER(C.c_int64)),
+                ("keep", C.c_void_p)]
+
+
+class TapPurityOut(C.Structure):
+    _fields_ = [("purity", C.c_double), ("threshold", C.c_int32), ("n_after_lcvf", C.c_int32), ("n_used", C.c_int32), ("median", C.c_double),
+                ("q1", C.c_double), ("q3", C.c_double), ("iqr", C.c_double), ("lower_whisker", C.c_double), ("upper_whisker", C.c_double)]
 
 
 SOM_MODES = {"extract_normal": 0, "extract_tumor": 1, "somatic_tag": 2}
@@ -158,6 +164,9 @@ def tap_lib():
         lib.ref_tap_somatic.argtypes = [C.c_int, C.POINTER(TapSomIn), C.POINTER(OrcSomaticOut)]
         lib.ref_tap_somatic.restype = C.c_int
         lib.ref_tap_somatic_free.argtypes = [C.POINTER(OrcSomaticOut)]
+        lib.ref_tap_state_new.restype = C.c_void_p
+        lib.ref_tap_state_free.argtypes = [C.c_void_p]
+        lib.ref_tap_purity.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(TapPurityOut)]
         _tap = lib
     return _tap
 
@@ -371,7 +380,7 @@ class ReferenceSomatic:
     """The UNMODIFIED reference's extract / somatic-tagging objects on a union contig (oracle/ref_tap_somatic.cpp).
     Per-read values the reference keeps in locals come back as -1 (h1/h2/h3/end_pos/read_len), 255 (n_ps)."""
 
-    def __init__(self, contig, tparams, mode, chr_name="chrS"):
+    def __init__(self, contig, tparams, mode, chr_name="chrS", keep=None):
         lib = tap_lib()
         P = _ffi.ptr
         stats = (C.c_int64 * 22)()
@@ -382,9 +391,26 @@ class ReferenceSomatic:
                        tum_gt=P(contig.tum_gt, u8p), tum_hp1_is_alt=P(contig.tum_hp1_is_alt, u8p), tum_ps=P(contig.tum_ps, i32p),
                        is_somatic=P(contig.is_somatic, u8p), derive_hp=P(contig.derive_hp, i8p), batch=contig.batch_struct(),
                        names=contig.names, name_stride=contig.NAME_STRIDE, p=tparams,
-                       stats_out=C.cast(stats, C.POINTER(C.c_int64)))
+                       stats_out=C.cast(stats, C.POINTER(C.c_int64)), keep=keep)
         o = OrcSomaticOut()
         self.rc = lib.ref_tap_somatic(SOM_MODES[mode], C.byref(tin), C.byref(o))
         _somatic_fields(self, o)
         self.stats = dict(zip(_ffi.SOMATIC_COUNTERS + [f"hp{k}" for k in range(9)], list(stats)))
         lib.ref_tap_somatic_free(C.byref(o))
+
+
+class ReferencePurity:
+    """The UNMODIFIED reference's extract passes followed by its TumorPurityEstimator (oracle/ref_tap_somatic.cpp)."""
+
+    def __init__(self, normal_contig, tumor_contig, tparams, chr_name="chrS"):
+        lib = tap_lib()
+        st = lib.ref_tap_state_new()
+        try:
+            self.normal = ReferenceSomatic(normal_contig, tparams, "extract_normal", chr_name, keep=st)
+            self.tumor = ReferenceSomatic(tumor_contig, tparams, "extract_tumor", chr_name, keep=st)
+            o = TapPurityOut()
+            lib.ref_tap_purity(st, chr_name.encode(), C.byref(o))
+            self.result = {f: getattr(o, f) for f, _ in o._fields_}
+            self.purity = o.purity
+        finally:
+            lib.ref_tap_state_free(st)

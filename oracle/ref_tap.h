@@ -120,7 +120,18 @@ typedef struct {
     int32_t name_stride;
     lps_tag_params p;
     int64_t *stats_out;              /* [TAP_SOM_STATS], written in mode 2 */
+    void *keep;                      /* optional ref_tap_state: modes 0 / 1 leave the reference's chrPosNorBase / chrPosSomaticInfo there */
 } tap_som_in;
+
+/* the reference's TumorPurityEstimator on the maps two extract passes left in a state object */
+typedef struct {
+    double purity;                   /* TumorPurityEstimator::estimateTumorPurity() */
+    int32_t threshold, n_after_lcvf, n_used;
+    double median, q1, q3, iqr, lower_whisker, upper_whisker;
+} tap_purity_out;
+void *ref_tap_state_new(void);
+void ref_tap_state_free(void *state);
+int ref_tap_purity(void *state, const char *chr, tap_purity_out *out);
 
 int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out);
 void ref_tap_phase_free(tap_phase_out *out);

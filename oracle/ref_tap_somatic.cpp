@@ -33,6 +33,10 @@
 #include "ref_tap.h"
 
 namespace {
+struct TapState {
+    std::map<std::string, std::map<int, PosBase>> nor;
+    std::map<std::string, std::map<int, SomaticData>> tum;
+};
 template <typename T> T *zalloc(size_t n) { return (T *)calloc(n + 1, sizeof(T)); }
 
 VarData make_var(const char *s, int gt, int hp1_is_alt, int ps) {
@@ -318,8 +322,44 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
         for (int k = 0; k < 9; k++) { auto it = s.totalHpCount.find(k); st[13 + k] = it == s.totalHpCount.end() ? 0 : it->second; }
         memcpy(in->stats_out, st, sizeof(st));
     }
+    if (in->keep) {
+        TapState *st = (TapState *)in->keep;
+        if (mode == 0) st->nor[chr] = chrPosNorBase[chr];
+        else if (mode == 1) st->tum[chr] = chrPosSomaticInfo[chr];
+    }
     delete norProc; delete tumProc; delete tagProc;
     free(tname);
+    return 0;
+}
+
+extern "C" void *ref_tap_state_new(void) { return new TapState(); }
+extern "C" void ref_tap_state_free(void *state) { delete (TapState *)state; }
+
+// The reference's own estimator (TumorPurityEstimator.cpp:31-84) on the maps of the two passes; the intermediate values come from
+// running its private stages once more in the order estimateTumorPurity runs them.
+extern "C" int ref_tap_purity(void *state, const char *chr, tap_purity_out *out) {
+    TapState *st = (TapState *)state;
+    memset(out, 0, sizeof(*out));
+    std::vector<std::string> chrVec{std::string(chr)};
+    {
+        TumorPurityEstimator est(chrVec, st->nor, st->tum, false, "/tmp/ref_tap_purity");
+        out->purity = est.estimateTumorPurity();
+    }
+    try {
+        TumorPurityEstimator e2(chrVec, st->nor, st->tum, false, "/tmp/ref_tap_purity");
+        std::vector<PurityData> v;
+        e2.buildPurityFeatureValueVec(v);
+        out->n_after_lcvf = (int32_t)v.size();
+        int thr = e2.findBimodalValleyThreshold(v);
+        e2.bimodalValleyFilter(v, thr);
+        BoxPlotValue pv = e2.statisticPurityData(v);
+        e2.removeOutliers(v, pv);
+        pv = e2.statisticPurityData(v);
+        out->threshold = thr; out->n_used = (int32_t)v.size();
+        out->median = pv.median; out->q1 = pv.q1; out->q3 = pv.q3; out->iqr = pv.iqr; out->lower_whisker = pv.lowerWhisker; out->upper_whisker = pv.upperWhisker;
+    } catch (const std::exception &) {
+        out->n_used = -1;
+    }
     return 0;
 }
 
