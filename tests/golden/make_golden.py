@@ -51,5 +51,61 @@ def main():
         print(name, os.path.getsize(path) // 1024, "KiB", "cells", len(ref.cell_val), "calls", len(ref.stage_a["pos"]))
 
 
+def fingerprint(c):
+    return np.array([c.n_reads, c.n_var, int(c.cigar.sum() % (1 << 31)), int(c.qual.astype(np.uint64).sum() % (1 << 31)),
+                     int(c.var_pos.astype(np.int64).sum() % (1 << 31))], np.int64)
+
+
+SOM_FIELDS = ["tum_var", "category", "read_hp", "ps", "pq", "h1", "h2", "h3", "n_ps", "end_pos", "read_len", "pos_base", "read_hp_count",
+              "somatic_read_hp_count", "case_count", "window_hist", "hp_before_count", "hp_after_count", "h3_before_count", "h3_after_count",
+              "cover_start", "cover_end", "ratios_f", "ratios_d", "case_read_count", "call_off", "calls"]
+
+
+def tag_family():
+    """Germline haplotag, the three somatic passes and the purity estimate, from the reference's own objects."""
+    from tests import somatic_cases, tag_cases, test_purity
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, kind in (("snp_indel", "phase_result"), ("many_supplementary", "blocks50")):
+        c = tag_cases.get(name, kind)
+        out = {"input_fingerprint": fingerprint(c)}
+        for pname, tp in tag_cases.param_sets().items():
+            ref = po.ReferenceTag(c, tp)
+            for k in ("category", "hp", "ps", "pq", "h1", "h2", "n_ps", "var_off", "var_pos", "var_hp"):
+                out[f"{pname}_{k}"] = getattr(ref, k)
+            out[f"{pname}_stats"] = np.array([ref.stats[k] for k in sorted(ref.stats)], np.int64)
+        path = os.path.join(here, f"tag_{name}_{kind}.npz")
+        np.savez_compressed(path, **out)
+        print("tag", name, kind, os.path.getsize(path) // 1024, "KiB")
+    for name in ("snv_indel", "dense_somatic"):
+        un, ut = somatic_cases.get(name)
+        out = {"fingerprint_normal": fingerprint(un), "fingerprint_tumor": fingerprint(ut)}
+        for pname in ("purity_q20", "tag_q1"):
+            tp = somatic_cases.param_sets()[pname]
+            for mode in ("extract_normal", "extract_tumor", "somatic_tag"):
+                ref = po.ReferenceSomatic(un if mode == "extract_normal" else ut, tp, mode)
+                assert ref.rc == 0
+                for k in SOM_FIELDS:
+                    out[f"{pname}_{mode}_{k}"] = getattr(ref, k)
+                if mode == "somatic_tag":
+                    out[f"{pname}_{mode}_stats"] = np.array([ref.stats[k] for k in sorted(ref.stats)], np.int64)
+        path = os.path.join(here, f"somatic_{name}.npz")
+        np.savez_compressed(path, **out)
+        print("somatic", name, os.path.getsize(path) // 1024, "KiB")
+    out = {}
+    tp = somatic_cases.param_sets()["purity_q20"]
+    for name in test_purity.PURITY_CASES:
+        un, ut = test_purity.pair(name)
+        ref = po.ReferencePurity(un, ut, tp)
+        out[f"{name}_fingerprint"] = np.concatenate([fingerprint(un), fingerprint(ut)])
+        out[f"{name}_purity"] = np.array([ref.purity, ref.result["median"], ref.result["q1"], ref.result["q3"], ref.result["iqr"],
+                                          ref.result["lower_whisker"], ref.result["upper_whisker"]], np.float64)
+        out[f"{name}_counts"] = np.array([ref.result["threshold"], ref.result["n_after_lcvf"], ref.result["n_used"]], np.int64)
+    path = os.path.join(here, "purity.npz")
+    np.savez_compressed(path, **out)
+    print("purity", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "tag":
+        main()
+    tag_family()
