@@ -60,7 +60,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.4)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--variant-spacing", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
+    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block"])
     ap.add_argument("--unequal", type=int, default=0)   # 1: contig sizes +-25 % around --contig-mb (the largest one then bounds the step)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -181,6 +182,10 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    ffi0 = importlib.import_module("longphase_s_b200._ffi")
+    blocking = args.sync == "block"   # measured on 8 GPUs / 32 cores: blocking waits double the step (21.1 vs 9.8 ms), so "auto" spins
+    if blocking:
+        ffi0.load_library().lps_set_blocking_sync(local_rank, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -279,7 +284,8 @@ def main():
     for _ in range(args.warmup):
         run_all(step_resident)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()    # the JSON line is rank 0's: only its GPU is sampled (every nvidia-smi call costs host CPU)
     s0 = [ctx.stats() for ctx in ctxs]
     dev_ms, wall_ms, res = timed(step_resident, args.steps, 0)
     s1 = [ctx.stats() for ctx in ctxs]
@@ -342,6 +348,7 @@ def main():
                    "reads_per_gpu": n_reads_gpu, "variants_per_gpu": int(sum(c.n_var for c in contigs)), "allele_calls_per_gpu": calls_gpu,
                    "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "input_bytes_per_gpu": input_bytes,
                    "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
+                   "host_sync": "blocking" if blocking else "spin", "host_cores": ncores,
                    "parallelism": f"contig-sharded x{world} GPUs, {C_} contigs in flight per GPU (one lps_ctx + host thread each), no collective",
                    "timing": "CUDA events on every context's stream (the streams the kernels run on), max over contexts and ranks",
                    "wall_ms_per_step_rank0": wall_ms, "synth_seconds": t_gen},

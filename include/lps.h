@@ -149,6 +149,11 @@ typedef struct {
     const int8_t *hap_ref_sweep;  /* [n_variants] REF-allele haplotype after the sweep, -1 outside blocks  */
 } lps_phase_result;
 
+/* ---- process-wide ------------------------------------------------------------------------ */
+/* How host threads wait for the device on `device`: 0 = spin (lowest latency, one core per waiting thread), 1 = block on an
+ * interrupt (cudaDeviceScheduleBlockingSync).  Worth setting when the host threads of all ranks outnumber the cores.      */
+int lps_set_blocking_sync(int device, int on);
+
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int lps_ctx_create(int device, lps_ctx **out);
 void lps_ctx_destroy(lps_ctx *ctx);

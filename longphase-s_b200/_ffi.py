@@ -174,6 +174,7 @@ SYMBOLS = {
     "lps_extract_normal": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_extract_tumor": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_somatic_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsSomaticTagResult)]),
+    "lps_set_blocking_sync": (C.c_int, [C.c_int, C.c_int]),
     "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),

@@ -66,6 +66,13 @@ extern "C" {
 
 const char *lps_version(void) { return "longphase-s_b200 0.1 (sm_100a)"; }
 
+int lps_set_blocking_sync(int device, int on) {
+    if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
+    const cudaError_t e = cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleSpin);
+    cudaGetLastError();
+    return e == cudaSuccess ? LPS_OK : LPS_E_CUDA;
+}
+
 int lps_ctx_create(int device, lps_ctx **out) {
     if (!out) return LPS_E_ARG;
     *out = nullptr;
