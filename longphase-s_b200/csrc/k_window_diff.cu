@@ -5,11 +5,15 @@
 // The reference appends (offset, read_base) pairs to PosSomaticOffsetBase[allele]; its only consumer, the DenseAlt filter
 // (:1160-1203), counts entries per offset.  The kernel therefore bins straight into window_hist[slot][allele][offset + 100].
 //
-// Mapping: ONE THREAD PER (alignment, tumor position) work item emitted by k_call_alleles' tumor dialect.  The scan is a
-// sequential state machine with the reference's quirks (the budget is decremented BEFORE each step and the hop to the
+// Mapping: EIGHT LANES PER (alignment, tumor position) work item emitted by k_call_alleles' tumor dialect, four items per warp.
+// The reference's scan is a sequential state machine with quirks (the budget is decremented BEFORE each step and the hop to the
 // neighbouring CIGAR op happens at 0 or -1, so the backward scan skips the first base of every op; N / P / X ops consume
-// iterations without moving; offsets are iteration indices, not base distances), so it is replayed step by step per thread;
-// work items of one read are adjacent in the list, which keeps the CIGAR / SEQ / reference lines they share in L1.
+// iterations without moving; offsets are iteration indices, not base distances).  Its control flow only changes at hops, so the
+// scan is cut into SEGMENTS between hops: the (cheap, sequential) hop logic is replayed redundantly by the eight lanes, and the
+// iterations of a segment - consecutive read / reference bases - are compared eight at a time with coalesced byte loads.  The
+// first version used one thread per item and was bound by LSU wavefronts (every lane reading its own read): 0.61 ms for 302 k
+// items; this layout needs ~7x fewer wavefronts.
+#include <climits>
 #include "lps_ctx.cuh"
 
 namespace {
@@ -42,26 +46,47 @@ __device__ __forceinline__ bool next_op(const uint32_t *__restrict__ cig, int &c
     return false;
 }
 
-// getOrderWindowsDiffRef (:655-686)
+// getOrderWindowsDiffRef (:655-686), segment by segment.  `remaining` is the budget BEFORE the decrement of iteration i.
 __device__ __forceinline__ void scan(const WdArgs &a, const uint32_t *__restrict__ cig, int ci, int ncig, const uint8_t *__restrict__ seq, int lq,
-                                     int read_pos, int remaining, int ref_pos, int dir, int32_t *__restrict__ hist) {
+                                     int read_pos, int remaining, int ref_pos, const int dir, int32_t *__restrict__ hist, const int sub) {
     int op = (int)(cig[ci] & 15u);
-    for (int i = 1; i <= LPS_WINDOW; i++) {
-        remaining--;
-        if (remaining == 0 || remaining == -1)
+    int i = 1;
+    while (i <= LPS_WINDOW) {
+        int first = 0;
+        if (remaining == 1 || remaining == 0) {            // the decrement of iteration i gives 0 or -1: hop before executing it
+            remaining -= 1;
             if (!next_op(cig, ci, ncig, dir, remaining, read_pos, ref_pos, op)) return;
-        if (op == 2 || op == 1 || op == 3 || op == 6 || op == 8) continue;
-        read_pos += dir; ref_pos += dir;
-        if (read_pos > lq || (long long)ref_pos > a.ref_len || read_pos < 0 || ref_pos < 0) return;
-        if (read_pos == lq) return;                                        // one past SEQ: undefined in the reference
-        const char rb = "=ACMGRSVTWYHKDBN"[(seq[read_pos >> 1] >> ((~read_pos & 1) << 2)) & 0xfu];
-        const char fb = (long long)ref_pos == a.ref_len ? '\0' : a.ref[ref_pos];   // std::string::operator[](size())
-        if (rb != fb) atomicAdd(hist + i * dir + LPS_WINDOW, 1);
+            first = 1;                                     // iteration i runs in the new op without another decrement
+        }
+        // iterations that follow without a hop: until the decrement gives 0; a negative budget never hops again
+        const int extra = remaining >= 2 ? remaining - 1 : (remaining < 0 ? LPS_WINDOW : 0);
+        int run = first + extra;
+        if (run > LPS_WINDOW + 1 - i) run = LPS_WINDOW + 1 - i;
+        if (!(op == 2 || op == 1 || op == 3 || op == 6 || op == 8)) {
+            // a moving op: iteration i + t compares read[read_pos + dir (t+1)] with ref[ref_pos + dir (t+1)]; the scan ends at the
+            // first position out of range (read == l_qseq is one past SEQ, undefined in the reference: ends the scan as well)
+            int n_ok;
+            if (dir > 0) n_ok = min(lq - 1 - read_pos, (int)min((long long)INT_MAX, a.ref_len - (long long)ref_pos));
+            else n_ok = (read_pos > lq || (long long)ref_pos > a.ref_len + 1) ? 0 : min(read_pos, ref_pos);
+            if (n_ok < 0) n_ok = 0;
+            const int n = min(run, n_ok);
+            for (int t = sub; t < n; t += 8) {
+                const int rp = read_pos + dir * (t + 1), fp = ref_pos + dir * (t + 1);
+                const char rb = "=ACMGRSVTWYHKDBN"[(seq[rp >> 1] >> ((~rp & 1) << 2)) & 0xfu];
+                const char fb = (long long)fp == a.ref_len ? '\0' : a.ref[fp];     // std::string::operator[](size())
+                if (rb != fb) atomicAdd(hist + (i + t) * dir + LPS_WINDOW, 1);
+            }
+            if (n < run) return;
+            read_pos += dir * n; ref_pos += dir * n;
+        }
+        remaining -= run - first;
+        i += run;
     }
 }
 
 __global__ void __launch_bounds__(128) k_window_diff(WdArgs a) {
-    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long t = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
     if (t >= a.n_items) return;
     const WdItem it = a.items[t];
     const int r = (int)it.read;
@@ -74,8 +99,8 @@ __global__ void __launch_bounds__(128) k_window_diff(WdArgs a) {
     // getWindowsDiffRef (:688-710): the op is an M/=/X op, never an insertion
     const int oplen = (int)(cig[ci] >> 4);
     const int fwd = oplen - off > 0 ? oplen - off : 0, rev = off > 0 ? off : 0;
-    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, rev, var_pos, -1, hist);
-    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, fwd, var_pos, 1, hist);
+    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, rev, var_pos, -1, hist, sub);
+    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, fwd, var_pos, 1, hist, sub);
 }
 
 }  // namespace
@@ -89,7 +114,7 @@ int lps_launch_window_diff(lps_ctx *ctx, int have_reference) {
     a.ref = ctx->d_ref.p; a.ref_len = have_reference ? (long long)ctx->ref_len : 0; a.window_hist = ctx->som.window_hist;
     const int tb = 128;
     cudaEventRecord(ctx->kev[4], ctx->stream);
-    k_window_diff<<<(unsigned)((n + tb - 1) / tb), tb, 0, ctx->stream>>>(a);
+    k_window_diff<<<(unsigned)((8 * n + tb - 1) / tb), tb, 0, ctx->stream>>>(a);   // 8 lanes per item
     cudaEventRecord(ctx->kev[5], ctx->stream);
     ctx->stats.kernel_launches++;
     LPS_CUDA(ctx, cudaGetLastError());
