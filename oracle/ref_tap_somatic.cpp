@@ -341,12 +341,14 @@ extern "C" int ref_tap_purity(void *state, const char *chr, tap_purity_out *out)
     TapState *st = (TapState *)state;
     memset(out, 0, sizeof(*out));
     std::vector<std::string> chrVec{std::string(chr)};
+    // the estimator keeps a REFERENCE to the prefix (TumorPurityEstimator.h:292) and writes its report there: it must outlive both objects
+    const std::string prefix = "/tmp/ref_tap_purity";
     {
-        TumorPurityEstimator est(chrVec, st->nor, st->tum, false, "/tmp/ref_tap_purity");
+        TumorPurityEstimator est(chrVec, st->nor, st->tum, false, prefix);
         out->purity = est.estimateTumorPurity();
     }
     try {
-        TumorPurityEstimator e2(chrVec, st->nor, st->tum, false, "/tmp/ref_tap_purity");
+        TumorPurityEstimator e2(chrVec, st->nor, st->tum, false, prefix);
         std::vector<PurityData> v;
         e2.buildPurityFeatureValueVec(v);
         out->n_after_lcvf = (int32_t)v.size();
