@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contig-mb", type=float, default=64.0)
-    ap.add_argument("--contigs-per-gpu", type=int, default=4)
+    ap.add_argument("--contigs-per-gpu", type=int, default=8)       # in flight per GPU; capped by this rank's share of the host cores
     ap.add_argument("--cpu-sample-mb", type=float, default=8.0)
     ap.add_argument("--depth", type=float, default=30.0)               # C5 stress: --depth 120 --mean-len 50000 --variant-spacing 300
     ap.add_argument("--mean-len", type=float, default=20000.0)

@@ -189,6 +189,14 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
 int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
 /* all of the above for one contig (the body of the loop at PhasingProcess.cpp:113-173)         */
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
+/* The host half of lps_phase_solve on its own (no device): VairiantGraph::edgeConnectResult (PhasingGraph.cpp:286-474) over
+ * the one-byte summaries of VariantEdge::findBestEdgePair (:166-228) that the device derives from every edge cell.
+ * votes[k*window + d] describes the edge from graph node k to node k+1+d: bits 0-1 link (1 same haplotype, 2 opposite,
+ * 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1, bit 4 edgeSimilarRatio < 0.2.  node_type as lps_edges.node_type.
+ * Writes the phase-set id (0 = none) and the REF-allele haplotype (-1 = none) of every node; returns the SIMD path taken
+ * (0 scalar, 1 AVX2, 2 AVX-512; the environment variable LPS_SWEEP=scalar|avx2|avx512 caps it) or a negative error.   */
+int lps_sweep_votes(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
+                    const uint8_t *votes, int32_t *node_ps, int8_t *node_hap_ref);
 
 /* ---- haplotag (germline tag dialect) -------------------------------------------------------- */
 /* dispatch category of every alignment, in the order of ChromosomeProcessor::processSingleChrom
@@ -382,6 +390,8 @@ typedef struct {
     uint64_t kernel_launches; /* kernels launched by this context since creation                 */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    int32_t sweep_simd;           /* code path of the last host sweep: 0 scalar, 1 AVX2, 2 AVX-512   */
+    int32_t reserved_;
 } lps_stats;
 int lps_get_stats(lps_ctx *ctx, lps_stats *out);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on), so a

@@ -151,7 +151,7 @@ class LpsStats(C.Structure):
                 ("ms_kernel_fold_edges", C.c_float), ("ms_kernel_window_diff", C.c_float), ("ms_wall_call_alleles", C.c_float),
                 ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
                 ("ms_host_sweep", C.c_float), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sweep_simd", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # every symbol include/lps.h declares: name -> (restype, argtypes)
@@ -169,6 +169,7 @@ SYMBOLS = {
     "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
     "lps_phase_contig": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),
+    "lps_sweep_votes": (C.c_int, [C.POINTER(LpsPhaseParams), C.c_int32, C.c_int32, i32p, u8p, u8p, i32p, i8p]),
     "lps_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsTagResult)]),
     "lps_contig_set_tumor_variants": (C.c_int, [C.c_void_p, C.POINTER(LpsTumorVariants)]),
     "lps_extract_normal": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),

@@ -235,146 +235,245 @@ int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased) {
 }
 
 // --------------------------------------------------------------------------------------------
-// the sweep (edgeConnectResult).  It is a left-to-right chain — node k's haplotype comes from the
-// weighted votes of its <= W predecessors, then k votes on its W successors — so it runs on the
-// host; but nothing about a vote except its DIRECTION depends on the chain, and k_fold_edges' epilogue
-// already reduced every (node, successor) cell to one byte (findBestEdgePair, :166-228):
+// the sweep (edgeConnectResult, PhasingGraph.cpp:286-474).  It is a left-to-right chain — node k's haplotype comes from the
+// weighted votes of its <= W predecessors, then k votes on its W successors — so it runs on the host; but nothing about a vote
+// except its DIRECTION depends on the chain, and k_fold_edges' epilogue already reduced every (voter, successor) cell to one
+// byte (findBestEdgePair, :166-228):
 //   bits 0-1 link (1 same haplotype, 2 opposite, 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1,
 //   bit 4 edgeSimilarRatio < 0.2.
-// Only those W bytes per node cross PCIe, never the [nodes][W][4] float table.
-//   * hpCountMap2 is a float sum in voter order (weights 1, 20, 0.1f): successors receive their votes
-//     one voter at a time in ascending voter order, exactly like the reference;
-//   * Onelongcase's sums only ever add 1 or 20, so they are kept as integers;
-//   * inside a block the REF-allele haplotype telescopes to hp[k]-1 (the first member of a block
-//     always has hp 1) and PS = position(block start)+1; single-member blocks are dropped (:425).
+// Only those bytes cross PCIe, never the [nodes][W][4] float table.
+//   * hpCountMap2 is a float sum in voter order (weights 1, 20, 0.1f): successors receive their votes one voter at a time in
+//     ascending voter order, exactly like the reference;
+//   * Onelongcase's sums only ever add 1 or 20 (at most 35 x 20) and the count of single-read edges is at most W, so the three
+//     live in ONE 32-bit accumulator per node: bits 0-7 singles, 8-19 sum towards haplotype 1, 20-31 towards haplotype 2;
+//   * inside a block the REF-allele haplotype telescopes to hp[k]-1 (the first member of a block always has hp 1) and
+//     PS = position(block start)+1; single-member blocks are dropped (:425).
+// Layout.  The accumulators are cut into ALIGNED blocks of 16 nodes, and the device writes row k of the vote bytes already
+// shifted to those blocks: lps_vote_row_stride(W) bytes per row, byte j = vote on node 16*((k+1)/16) + j, zero where there is no
+// vote.  A voter therefore adds whole aligned vectors, with no edge masks, and every load of an accumulator block has exactly
+// the address and width of the store the previous voter made to it, so store-to-load forwarding always works (the first version
+// added at unaligned offsets t0+d: every load straddled two earlier stores and waited for both to retire — 47 ns per node).
 // --------------------------------------------------------------------------------------------
+int lps_vote_row_stride(int W) { return ((W + 15 + 15) / 16) * 16; }
+
 namespace {
 
-// Accumulators of every node (hpCountMap2 and Onelongcase's sums), SoA inside ONE allocation.  The five
-// arrays are staggered by a few cache lines so that w1[d], w2[d], ... never share their low 12 address
-// bits (4K aliasing would serialise the loads behind the stores).
 struct SweepAcc {
     std::vector<char> mem;
     float *w1, *w2;
-    int *s1, *s2, *singles;
+    uint32_t *pk;
     explicit SweepAcc(size_t len) {
+        // staggered by 13 cache lines so that w1[i], w2[i], pk[i] never share their low 12 address bits (4K aliasing)
         const size_t bytes = (len * 4 + 4095) & ~(size_t)4095;
-        mem.assign(5 * bytes + 5 * 832 + 64, 0);
+        mem.assign(3 * bytes + 3 * 832 + 64, 0);
         char *b = mem.data();
         b += (64 - ((uintptr_t)b & 63)) & 63;
         w1 = (float *)(b);
         w2 = (float *)(b + 1 * (bytes + 832));
-        s1 = (int *)(b + 2 * (bytes + 832));
-        s2 = (int *)(b + 3 * (bytes + 832));
-        singles = (int *)(b + 4 * (bytes + 832));
+        pk = (uint32_t *)(b + 2 * (bytes + 832));
     }
 };
+
+// Sums of the node that follows the voter, handed from the voter's registers to the next step of the chain: a scalar load of
+// them would have to wait for the voter's vector stores to leave the store buffer.
+struct NextNode { float h1, h2; uint32_t pk; int lane; bool valid; };
 
 inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t as_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-// node k votes on its successors t0 .. t0+dmax-1.  Mask arithmetic instead of branches: the vote directions are
-// data, not control flow (adding +0.0f is exact and the accumulators are never -0.0).  Returns the last d with a link.
-int cast_votes_scalar(const uint8_t *row, int dmax, int hp, unsigned type, const SweepAcc &A, size_t t0) {
+// Voter k (haplotype hp, node type `type`) votes on the nodes of its row; `base` = first node of the row = 16 * ((k+1) / 16).
+// Mask arithmetic instead of branches: the vote directions are data, not control flow (adding +0.0f is exact and the
+// accumulators are never -0.0).
+inline void cast_votes_scalar(const uint8_t *row, int RS, int hp, unsigned type, const SweepAcc &A, size_t base, NextNode &nx) {
     const uint32_t wtab[2] = {as_bits(type == 4u ? (float)0.1 : 1.f), as_bits(type == 4u ? (float)0.1 : 20.f)};   // :367-369
     const uint32_t itab[2] = {1u, 20u};
     const unsigned same = hp == 1 ? 1u : 2u, other = 3u - same;       // link code that sends the vote to haplotype 1
     const uint32_t type_ok = (type != 3u && type != 4u) ? ~0u : 0u;  // Onelongcase: weight >= 1, voter not an indel (:265)
-    int last = -1;
-    for (int d = 0; d < dmax; d++) {
-        const unsigned info = row[d];
-        const unsigned link = info & 3u;
+    for (int j = 0; j < RS; j++) {
+        const unsigned info = row[j], link = info & 3u;
+        if (!link) continue;
         const uint32_t mA = 0u - (uint32_t)(link == same), mB = 0u - (uint32_t)(link == other);
         const uint32_t wb = wtab[(info >> 2) & 1u];
-        A.w1[t0 + d] += as_float(wb & mA);
-        A.w2[t0 + d] += as_float(wb & mB);
+        A.w1[base + j] += as_float(wb & mA);
+        A.w2[base + j] += as_float(wb & mB);
         const uint32_t single = 0u - ((info >> 3) & 1u);
-        A.singles[t0 + d] += (int)((mA | mB) & single & 1u);
         const uint32_t qual = ~single & (0u - ((info >> 4) & 1u)) & type_ok;
         const uint32_t wi = itab[(info >> 2) & 1u];
-        A.s1[t0 + d] += (int)(wi & qual & mA);
-        A.s2[t0 + d] += (int)(wi & qual & mB);
-        const int md = (int)(mA | mB);
-        last = (d & md) | (last & ~md);
+        A.pk[base + j] += ((mA | mB) & single & 1u) | ((wi & qual & mA) << 8) | ((wi & qual & mB) << 20);
     }
-    return last;
+    nx.h1 = A.w1[base + nx.lane]; nx.h2 = A.w2[base + nx.lane]; nx.pk = A.pk[base + nx.lane];
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx2")))
-int cast_votes_avx2(const uint8_t *row, int dmax, int hp, unsigned type, const SweepAcc &A, size_t t0) {
+#define LPS_T_AVX2 __attribute__((target("avx2")))
+#define LPS_T_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq")))
+
+struct Avx2Consts {
+    __m256i c1, c3, c4, c8, c16, c20;
+};
+
+LPS_T_AVX2 inline __attribute__((always_inline)) void cast_votes_avx2(const uint8_t *row, int first, int last, int hp, unsigned type,
+                                                                    const SweepAcc &A, size_t base, const Avx2Consts &C, NextNode &nx) {
     const __m256 w_lo = _mm256_set1_ps(type == 4u ? (float)0.1 : 1.f), w_hi = _mm256_set1_ps(type == 4u ? (float)0.1 : 20.f);
-    const __m256i same = _mm256_set1_epi32(hp == 1 ? 1 : 2), other = _mm256_set1_epi32(hp == 1 ? 2 : 1);
+    const __m256i same = _mm256_set1_epi32(hp), other = _mm256_set1_epi32(3 - hp);       // link code that sends the vote to haplotype 1 / 2
     const __m256i type_ok = _mm256_set1_epi32((type != 3u && type != 4u) ? -1 : 0);
-    const __m256i iota = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
-    const __m256i c1 = _mm256_set1_epi32(1), c3 = _mm256_set1_epi32(3), c4 = _mm256_set1_epi32(4), c8 = _mm256_set1_epi32(8),
-                  c16 = _mm256_set1_epi32(16), c20 = _mm256_set1_epi32(20);
-    int last = -1;
-    for (int d = 0; d < dmax; d += 8) {
-        // 8 vote bytes (the read may run into the next row / the padding; those lanes are masked off)
-        const __m256i info = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(row + d)));
-        const __m256i valid = _mm256_cmpgt_epi32(_mm256_set1_epi32(dmax - d), iota);
-        const __m256i link = _mm256_and_si256(info, c3);
-        const __m256i mA = _mm256_and_si256(_mm256_cmpeq_epi32(link, same), valid);
-        const __m256i mB = _mm256_and_si256(_mm256_cmpeq_epi32(link, other), valid);
-        const __m256i heavy = _mm256_cmpeq_epi32(_mm256_and_si256(info, c4), c4);
+    for (int b = first; b <= last; b++) {                     // blocks of 8 nodes; the ones before `first` / after `last` hold no vote
+        const __m256i info = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i *)(row + 8 * b)));
+        const __m256i link = _mm256_and_si256(info, C.c3);
+        const __m256i mA = _mm256_cmpeq_epi32(link, same), mB = _mm256_cmpeq_epi32(link, other);
+        const __m256i heavy = _mm256_cmpeq_epi32(_mm256_and_si256(info, C.c4), C.c4);
         const __m256 wb = _mm256_blendv_ps(w_lo, w_hi, _mm256_castsi256_ps(heavy));
-        float *p1 = A.w1 + t0 + d, *p2 = A.w2 + t0 + d;
-        _mm256_storeu_ps(p1, _mm256_add_ps(_mm256_loadu_ps(p1), _mm256_and_ps(wb, _mm256_castsi256_ps(mA))));
-        _mm256_storeu_ps(p2, _mm256_add_ps(_mm256_loadu_ps(p2), _mm256_and_ps(wb, _mm256_castsi256_ps(mB))));
+        float *p1 = A.w1 + base + 8 * b, *p2 = A.w2 + base + 8 * b;
+        const __m256 v1 = _mm256_add_ps(_mm256_load_ps(p1), _mm256_and_ps(wb, _mm256_castsi256_ps(mA)));
+        const __m256 v2 = _mm256_add_ps(_mm256_load_ps(p2), _mm256_and_ps(wb, _mm256_castsi256_ps(mB)));
+        _mm256_store_ps(p1, v1);
+        _mm256_store_ps(p2, v2);
         const __m256i act = _mm256_or_si256(mA, mB);
-        const __m256i single = _mm256_cmpeq_epi32(_mm256_and_si256(info, c8), c8);
-        __m256i *ps = (__m256i *)(A.singles + t0 + d), *q1 = (__m256i *)(A.s1 + t0 + d), *q2 = (__m256i *)(A.s2 + t0 + d);
-        _mm256_storeu_si256(ps, _mm256_add_epi32(_mm256_loadu_si256(ps), _mm256_and_si256(_mm256_and_si256(act, single), c1)));
-        const __m256i qual = _mm256_and_si256(_mm256_andnot_si256(single, _mm256_cmpeq_epi32(_mm256_and_si256(info, c16), c16)), type_ok);
-        const __m256i wi = _mm256_blendv_epi8(c1, c20, heavy);
-        _mm256_storeu_si256(q1, _mm256_add_epi32(_mm256_loadu_si256(q1), _mm256_and_si256(wi, _mm256_and_si256(qual, mA))));
-        _mm256_storeu_si256(q2, _mm256_add_epi32(_mm256_loadu_si256(q2), _mm256_and_si256(wi, _mm256_and_si256(qual, mB))));
-        const unsigned bits = (unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(act));
-        if (bits) last = d + 31 - __builtin_clz(bits);
+        const __m256i single = _mm256_cmpeq_epi32(_mm256_and_si256(info, C.c8), C.c8);
+        const __m256i qual = _mm256_and_si256(_mm256_andnot_si256(single, _mm256_cmpeq_epi32(_mm256_and_si256(info, C.c16), C.c16)), type_ok);
+        const __m256i wi = _mm256_and_si256(_mm256_blendv_epi8(C.c1, C.c20, heavy), qual);
+        const __m256i add = _mm256_or_si256(_mm256_and_si256(_mm256_and_si256(act, single), C.c1),
+                                            _mm256_or_si256(_mm256_slli_epi32(_mm256_and_si256(wi, mA), 8),
+                                                            _mm256_slli_epi32(_mm256_and_si256(wi, mB), 20)));
+        __m256i *pp = (__m256i *)(A.pk + base + 8 * b);
+        const __m256i vp = _mm256_add_epi32(_mm256_load_si256(pp), add);
+        _mm256_store_si256(pp, vp);
+        if (b == first) {                                     // the next node sits in the first block: hand its sums over in registers
+            const __m256i lane = _mm256_set1_epi32(nx.lane & 7);
+            nx.h1 = _mm256_cvtss_f32(_mm256_permutevar8x32_ps(v1, lane));
+            nx.h2 = _mm256_cvtss_f32(_mm256_permutevar8x32_ps(v2, lane));
+            nx.pk = (uint32_t)_mm256_cvtsi256_si32(_mm256_permutevar8x32_epi32(vp, lane));
+        }
     }
-    return last;
+}
+
+struct Avx512Consts {
+    __m512i c1, c2, c3, c4, c8, c16, a1_lo, a1_hi, a2_lo, a2_hi;
+};
+
+LPS_T_AVX512 inline __attribute__((always_inline)) void cast_votes_avx512(const uint8_t *row, int nblk, int hp, unsigned type,
+                                                                        const SweepAcc &A, size_t base, const Avx512Consts &C, NextNode &nx) {
+    const __m512 w_lo = _mm512_set1_ps(type == 4u ? (float)0.1 : 1.f), w_hi = _mm512_set1_ps(type == 4u ? (float)0.1 : 20.f);
+    const __m512i same = _mm512_set1_epi32(hp), other = _mm512_set1_epi32(3 - hp);       // link code that sends the vote to haplotype 1 / 2
+    const __mmask16 tok = (type != 3u && type != 4u) ? (__mmask16)0xFFFF : (__mmask16)0;
+    for (int b = 0; b < nblk; b++) {                          // blocks of 16 nodes
+        const __m512i info = _mm512_cvtepu8_epi32(_mm_load_si128((const __m128i *)(row + 16 * b)));
+        const __m512i link = _mm512_and_si512(info, C.c3);
+        const __mmask16 mA = _mm512_cmpeq_epi32_mask(link, same), mB = _mm512_cmpeq_epi32_mask(link, other);
+        const __mmask16 heavy = _mm512_test_epi32_mask(info, C.c4), single = _mm512_test_epi32_mask(info, C.c8);
+        const __mmask16 qual = _kandn_mask16(single, _mm512_mask_test_epi32_mask(tok, info, C.c16));
+        const __m512 wb = _mm512_mask_blend_ps(heavy, w_lo, w_hi);
+        float *p1 = A.w1 + base + 16 * b, *p2 = A.w2 + base + 16 * b;
+        __m512 v1 = _mm512_load_ps(p1), v2 = _mm512_load_ps(p2);
+        v1 = _mm512_mask_add_ps(v1, mA, v1, wb);
+        v2 = _mm512_mask_add_ps(v2, mB, v2, wb);
+        _mm512_store_ps(p1, v1);
+        _mm512_store_ps(p2, v2);
+        __m512i *pp = (__m512i *)(A.pk + base + 16 * b);
+        __m512i pk = _mm512_load_si512(pp);
+        pk = _mm512_mask_add_epi32(pk, _kand_mask16(_kor_mask16(mA, mB), single), pk, C.c1);
+        pk = _mm512_mask_add_epi32(pk, _kand_mask16(mA, qual), pk, _mm512_mask_blend_epi32(heavy, C.a1_lo, C.a1_hi));
+        pk = _mm512_mask_add_epi32(pk, _kand_mask16(mB, qual), pk, _mm512_mask_blend_epi32(heavy, C.a2_lo, C.a2_hi));
+        _mm512_store_si512(pp, pk);
+        if (b == 0) {                                         // the next node sits in the first block: hand its sums over in registers
+            const __mmask16 one = (__mmask16)(1u << nx.lane);
+            nx.h1 = _mm512_cvtss_f32(_mm512_maskz_compress_ps(one, v1));
+            nx.h2 = _mm512_cvtss_f32(_mm512_maskz_compress_ps(one, v2));
+            nx.pk = (uint32_t)_mm512_cvtsi512_si32(_mm512_maskz_compress_epi32(one, pk));
+        }
+    }
+}
+#endif
+
+// the chain itself; CAST(row, hp, type, base, k) adds voter k's votes
+#define LPS_SWEEP_CHAIN(CAST)                                                                                                     \
+    int block_start = -1, block_size = 0, block_ps = 0, last_connect = -1;                                                        \
+    NextNode nx = {0.f, 0.f, 0u, 0, false};                                                                                       \
+    for (int k = 0; k + 1 < N; k++) {                                                                                             \
+        const bool handed = nx.valid;                                                                                             \
+        nx.valid = false;                                                                                                         \
+        if (std::abs(node_pos[k + 1] - node_pos[k]) > p->distance) continue;                   /* :318-320 */                     \
+        float h1 = handed ? nx.h1 : A.w1[k], h2 = handed ? nx.h2 : A.w2[k];                                                       \
+        const uint32_t pk = handed ? nx.pk : A.pk[k];                                                                             \
+        const int sg = (int)(pk & 0xFFu), a1 = (int)((pk >> 8) & 0xFFFu), a2 = (int)(pk >> 20);                                   \
+        const bool onelong = (sg > 3) & ((a1 | a2) != 0);                                      /* Onelongcase :276-281 */          \
+        const float f1 = (float)a1, f2 = (float)a2;                                                                               \
+        h1 = onelong ? f1 : h1;                                                                                                   \
+        h2 = onelong ? f2 : h2;                                                                                                   \
+        int hp;                                                                                                                   \
+        if (h1 == h2) {                                                                                                           \
+            if (last_connect >= 0 && k < last_connect) continue;                                /* :340-342 */                    \
+            if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }                \
+            block_start = k; block_size = 0; block_ps = node_pos[k] + 1; hp = 1;                                                  \
+        } else hp = 2 - (int)(h1 > h2);                                                                                           \
+        block_size++;                                                                                                             \
+        node_ps[k] = block_ps;                                                                                                    \
+        node_hap_ref[k] = (int8_t)(hp - 1);                                                                                       \
+        const int L = last_link[k];                                                                                               \
+        if (L < 0) continue;                                                                                                      \
+        const uint8_t *row = votes + (size_t)k * (size_t)RS;                                                                      \
+        const size_t base = ((size_t)k + 1) & ~(size_t)15;                                                                        \
+        nx.lane = (k + 1) & 15;                                                                                                   \
+        CAST;                                                                                                                     \
+        nx.valid = true;                                                                                                          \
+        last_connect = k + 1 + L;                                                                                                 \
+    }                                                                                                                             \
+    if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
+
+void sweep_scalar(const lps_phase_params *p, int N, int RS, const int32_t *node_pos, const uint8_t *node_type, const uint8_t *votes,
+                  const int8_t *last_link, int32_t *node_ps, int8_t *node_hap_ref, const SweepAcc &A) {
+    LPS_SWEEP_CHAIN(cast_votes_scalar(row, RS, hp, node_type[k], A, base, nx))
+}
+
+#if defined(__x86_64__)
+LPS_T_AVX2 void sweep_avx2(const lps_phase_params *p, int N, int RS, const int32_t *node_pos, const uint8_t *node_type,
+                           const uint8_t *votes, const int8_t *last_link, int32_t *node_ps, int8_t *node_hap_ref, const SweepAcc &A) {
+    const Avx2Consts C = {_mm256_set1_epi32(1), _mm256_set1_epi32(3), _mm256_set1_epi32(4), _mm256_set1_epi32(8), _mm256_set1_epi32(16),
+                          _mm256_set1_epi32(20)};
+    LPS_SWEEP_CHAIN(cast_votes_avx2(row, (int)((k + 1) & 15) >> 3, ((int)((k + 1) & 15) + L) >> 3, hp, node_type[k], A, base, C, nx))
+}
+
+LPS_T_AVX512 void sweep_avx512(const lps_phase_params *p, int N, int RS, const int32_t *node_pos, const uint8_t *node_type,
+                               const uint8_t *votes, const int8_t *last_link, int32_t *node_ps, int8_t *node_hap_ref, const SweepAcc &A) {
+    const Avx512Consts C = {_mm512_set1_epi32(1), _mm512_set1_epi32(2), _mm512_set1_epi32(3), _mm512_set1_epi32(4), _mm512_set1_epi32(8),
+                            _mm512_set1_epi32(16), _mm512_set1_epi32(1 << 8), _mm512_set1_epi32(20 << 8), _mm512_set1_epi32(1 << 20),
+                            _mm512_set1_epi32(20 << 20)};
+    const int nblk = RS >> 4;
+    LPS_SWEEP_CHAIN(cast_votes_avx512(row, nblk, hp, node_type[k], A, base, C, nx))
 }
 #endif
 
 }  // namespace
 
-void lps_host_sweep(const lps_phase_params *p, int32_t N, int32_t W, const int32_t *node_pos, const uint8_t *node_type,
-                    const uint8_t *vote_info, int32_t *node_ps, int8_t *node_hap_ref) {
+// votes: [N] rows of lps_vote_row_stride(W) bytes, 16-byte aligned, in the block-shifted layout described above;
+// last_link: [N] the largest successor offset d on which node k has a link, -1 if none.
+// Returns the code path taken (0 scalar, 1 AVX2, 2 AVX-512); LPS_SWEEP=scalar|avx2|avx512 forces one (tests).
+int lps_host_sweep(const lps_phase_params *p, int32_t N, int32_t W, const int32_t *node_pos, const uint8_t *node_type,
+                   const uint8_t *votes, const int8_t *last_link, int32_t *node_ps, int8_t *node_hap_ref) {
     for (int k = 0; k < N; k++) { node_ps[k] = 0; node_hap_ref[k] = -1; }
-    if (N < 2) return;
-    SweepAcc A((size_t)N + (size_t)W + 16);
+    int simd = 0;
 #if defined(__x86_64__)
-    const bool use_avx2 = __builtin_cpu_supports("avx2");
-#else
-    const bool use_avx2 = false;
-#endif
-    int block_start = -1, block_size = 0, block_ps = 0, last_connect = -1;
-    for (int k = 0; k + 1 < N; k++) {
-        if (std::abs(node_pos[k + 1] - node_pos[k]) > p->distance) continue;                   // :318-320
-        float h1 = A.w1[k], h2 = A.w2[k];
-        const int a1 = A.s1[k], a2 = A.s2[k], sg = A.singles[k];
-        if (!(sg <= 3 || (a1 == 0 && a2 == 0))) { h1 = (float)a1; h2 = (float)a2; }           // Onelongcase :276-281
-        int hp;
-        if (h1 == h2) {
-            if (last_connect >= 0 && k < last_connect) continue;                                // :340-342
-            if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
-            block_start = k; block_size = 0; block_ps = node_pos[k] + 1; hp = 1;
-        } else hp = h1 > h2 ? 1 : 2;
-        block_size++;
-        node_ps[k] = block_ps;
-        node_hap_ref[k] = (int8_t)(hp - 1);
-        const int dmax = std::min(W, N - 1 - k);
-        const uint8_t *row = vote_info + (size_t)k * (size_t)W;
-        int last;
-#if defined(__x86_64__)
-        if (use_avx2) last = cast_votes_avx2(row, dmax, hp, node_type[k], A, (size_t)k + 1);
-        else
-#endif
-            last = cast_votes_scalar(row, dmax, hp, node_type[k], A, (size_t)k + 1);
-        if (last >= 0) last_connect = k + 1 + last;
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx2")) simd = 1;
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+        __builtin_cpu_supports("avx512dq"))
+        simd = 2;
+    if (const char *env = getenv("LPS_SWEEP")) {
+        const int want = !strcmp(env, "scalar") ? 0 : !strcmp(env, "avx2") ? 1 : !strcmp(env, "avx512") ? 2 : simd;
+        if (want <= simd) simd = want;
     }
-    if (block_start >= 0 && block_size == 1) { node_ps[block_start] = 0; node_hap_ref[block_start] = -1; }
+    if (((uintptr_t)votes & 15) != 0) simd = 0;
+#endif
+    if (N < 2) return simd;
+    const int RS = lps_vote_row_stride(W);
+    SweepAcc A((size_t)N + (size_t)RS + 32);
+#if defined(__x86_64__)
+    if (simd == 2) sweep_avx512(p, N, RS, node_pos, node_type, votes, last_link, node_ps, node_hap_ref, A);
+    else if (simd == 1) sweep_avx2(p, N, RS, node_pos, node_type, votes, last_link, node_ps, node_hap_ref, A);
+    else
+#endif
+        sweep_scalar(p, N, RS, node_pos, node_type, votes, last_link, node_ps, node_hap_ref, A);
+    return simd;
 }
 
 

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
                                                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
                                                           const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
                                                           double edge_threshold, uint8_t *__restrict__ vote_info,
-                                                          unsigned long long *__restrict__ counters, uint64_t n_merged) {
+                                                          unsigned long long *__restrict__ counters, uint64_t n_merged,
+                                                          int8_t *__restrict__ last_link, int RS) {
     extern __shared__ float s_acc[];                       // [WARPS][W*4]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS + wib;
@@ -301,20 +302,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
     for (int i = lane; i < W * 4; i += 32) out[i] = acc[i];
     // epilogue: everything VariantEdge::findBestEdgePair (:166-228) derives from a cell, one byte per successor:
     //   bits 0-1 link (1 same haplotype, 2 opposite, 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1,
-    //   bit 4 edgeSimilarRatio < 0.2.  The sweep (k_sweep.cu) only reads these bytes.
-    for (int d = lane; d < W; d += 32) {
-        const float rr = acc[d * 4 + 0], ra = acc[d * 4 + 1], ar = acc[d * 4 + 2], aa = acc[d * 4 + 3];
-        const float para = rr + aa, cross = ar + ra;
-        const double esr = (double)fminf(para, cross) / (double)fmaxf(para, cross);
-        unsigned link = 0;
-        if (rr + aa > ra + ar) link = 1; else if (rr + aa < ra + ar) link = 2;
-        if (esr > edge_threshold) link = 0;
-        unsigned info = link;
-        if ((esr <= 0.1 && (rr + aa + ra + ar) >= 1) || ((rr + aa) < 1 && (ra + ar) >= 1) || ((rr + aa) >= 1 && (ra + ar) < 1)) info |= 4u;
-        if ((para + cross) <= 1) info |= 8u;
-        if (esr < 0.2) info |= 16u;
-        vote_info[(size_t)a * W + d] = (uint8_t)info;
+    //   bit 4 edgeSimilarRatio < 0.2.  The host sweep (host_phase.cpp) only reads these bytes.
+    // Row layout (see lps_host_sweep): RS = lps_vote_row_stride(W) bytes per voter, byte j = vote on node 16*((a+1)/16) + j, so that
+    // the host adds whole aligned 16-node blocks; bytes without a vote are written as 0 (the buffer is never memset).
+    int last = -1;
+    const int shift = (a + 1) & 15;
+    for (int j = lane; j < RS; j += 32) {
+        const int d = j - shift;
+        unsigned info = 0;
+        if (d >= 0 && d < W && a + 1 + d < n_nodes) {
+            const float rr = acc[d * 4 + 0], ra = acc[d * 4 + 1], ar = acc[d * 4 + 2], aa = acc[d * 4 + 3];
+            const float para = rr + aa, cross = ar + ra;
+            const double esr = (double)fminf(para, cross) / (double)fmaxf(para, cross);
+            unsigned link = 0;
+            if (rr + aa > ra + ar) link = 1; else if (rr + aa < ra + ar) link = 2;
+            if (esr > edge_threshold) link = 0;
+            info = link;
+            if ((esr <= 0.1 && (rr + aa + ra + ar) >= 1) || ((rr + aa) < 1 && (ra + ar) >= 1) || ((rr + aa) >= 1 && (ra + ar) < 1)) info |= 4u;
+            if ((para + cross) <= 1) info |= 8u;
+            if (esr < 0.2) info |= 16u;
+            if (info & 3u) last = max(last, d);
+        }
+        vote_info[(size_t)a * RS + j] = (uint8_t)info;
     }
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) last = max(last, __shfl_xor_sync(FULL, last, dd));
+    if (lane == 0) last_link[a] = (int8_t)last;
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) {
         contrib += __shfl_xor_sync(FULL, contrib, dd);
@@ -376,7 +389,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     cudaStream_t st = ctx->stream;
     const int n = ctx->batch.n_reads, nv = ctx->var.n, W = p->connect_adjacent;
     const int tb = 256;
-    if (W < 1 || W > 256) return ctx->fail(LPS_E_ARG, "connect_adjacent must be in [1,256]");
+    if (W < 1 || W > 127) return ctx->fail(LPS_E_ARG, "connect_adjacent must be in [1,127]");   // last_link is an int8, the sweep packs 12-bit sums
     LPS_CUDA(ctx, ctx->d_var_lastw.reserve((size_t)nv + 1));
     LPS_CUDA(ctx, ctx->d_alive_cnt.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_aln_keys.reserve((size_t)n + 1));
@@ -436,7 +449,8 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_node_cnt.reserve((size_t)n_nodes + 2));
     LPS_CUDA(ctx, ctx->d_node_off.reserve((size_t)n_nodes + 2));
     LPS_CUDA(ctx, ctx->d_weights.reserve((size_t)n_nodes * (size_t)W * 4 + 4));
-    LPS_CUDA(ctx, ctx->d_vote_info.reserve(((size_t)n_nodes + 130) * (size_t)W + 64));
+    LPS_CUDA(ctx, ctx->d_vote_info.reserve(((size_t)n_nodes + 2) * (size_t)lps_vote_row_stride(W) + 64));
+    LPS_CUDA(ctx, ctx->d_last_link.reserve((size_t)n_nodes + 16));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_cnt.p, 0, 4 * ((size_t)n_nodes + 2), st));
 
     // alive alignments: keys != ~0 are a prefix of the sorted array
@@ -493,14 +507,15 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     if (n_nodes > 0) {
         if (n_merged == 0) {
             LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_weights.p, 0, 4 * (size_t)n_nodes * W * 4, st));
-            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_vote_info.p, 0, (size_t)n_nodes * W, st));
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_vote_info.p, 0, (size_t)n_nodes * lps_vote_row_stride(W), st));
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_last_link.p, 0xFF, (size_t)n_nodes, st));
         } else {
             constexpr int WARPS = 8;
             size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
             cudaEventRecord(ctx->kev[2], st);
             k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
                 n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
-                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, (uint64_t)n_merged);
+                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, (uint64_t)n_merged, ctx->d_last_link.p, lps_vote_row_stride(W));
             cudaEventRecord(ctx->kev[3], st);
             ctx->stats.kernel_launches++;
         }

@@ -646,17 +646,29 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
     WallTimer wt;
     // ---- sweep (edgeConnectResult) on the host over the one-byte votes computed by the fold epilogue ----
-    const size_t W = (size_t)ctx->window;
-    LPS_CUDA(ctx, ctx->p_vote_info.reserve(nn * W + 16));
-    if (nn) LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_vote_info.p, ctx->d_vote_info.p, nn * W, cudaMemcpyDeviceToHost, st));
-    ctx->stats.d2h_bytes += nn * W;
+    const size_t RS = (size_t)lps_vote_row_stride(ctx->window);
+    LPS_CUDA(ctx, ctx->p_vote_info.reserve(nn * RS + 128));
+    LPS_CUDA(ctx, ctx->p_last_link.reserve(nn + 16));
+    if (nn) {
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_vote_info.p, ctx->d_vote_info.p, nn * RS, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_last_link.p, ctx->d_last_link.p, nn, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->stats.d2h_bytes += nn * RS + nn;
     LPS_CUDA(ctx, cudaStreamSynchronize(st));
     WallTimer ws;
     std::vector<int32_t> node_pos(nn), node_ps(nn);
     std::vector<int8_t> node_hap(nn);
     for (size_t k = 0; k < nn; k++) node_pos[k] = ctx->h_vpos[(size_t)ctx->h_node_var[k]];
-    lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->p_vote_info.p, node_ps.data(),
-                   node_hap.data());
+    if (const char *dump = getenv("LPS_DUMP_SWEEP")) {          // inputs of the sweep, for tools/sweep_bench (tuning the host code offline)
+        if (FILE *f = fopen(dump, "wb")) {
+            const int32_t hdr[4] = {(int32_t)nn, ctx->window, p->distance, (int32_t)RS};
+            fwrite(hdr, 4, 4, f); fwrite(node_pos.data(), 4, nn, f); fwrite(ctx->h_node_type.data(), 1, nn, f);
+            fwrite(ctx->p_vote_info.p, 1, nn * RS, f); fwrite(ctx->p_last_link.p, 1, nn, f);
+            fclose(f);
+        }
+    }
+    ctx->stats.sweep_simd = lps_host_sweep(p, ctx->n_nodes, ctx->window, node_pos.data(), ctx->h_node_type.data(), ctx->p_vote_info.p,
+                                           ctx->p_last_link.p, node_ps.data(), node_hap.data());
     ctx->h_ps_sweep.assign(nv, 0);
     ctx->h_hap_sweep.assign(nv, -1);
     for (size_t k = 0; k < nn; k++) {
@@ -684,6 +696,26 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     }
     ctx->stats.ms_wall_solve = wt.ms();
     return LPS_OK;
+}
+
+int lps_sweep_votes(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
+                    const uint8_t *votes, int32_t *node_ps, int8_t *node_hap_ref) {
+    if (!p || n_nodes < 0 || window < 1 || window > 127 || (n_nodes && (!node_pos || !node_type || !votes || !node_ps || !node_hap_ref)))
+        return LPS_E_ARG;
+    // plain [n_nodes][window] rows -> the block-shifted rows k_fold_edges writes (host_phase.cpp), plus last_link
+    const size_t N = (size_t)n_nodes, W = (size_t)window, RS = (size_t)lps_vote_row_stride(window);
+    std::vector<uint8_t> buf(N * RS + 64, 0);
+    uint8_t *rows = buf.data() + ((16 - ((uintptr_t)buf.data() & 15)) & 15);
+    std::vector<int8_t> last(N, -1);
+    for (size_t k = 0; k < N; k++) {
+        const size_t shift = (k + 1) & 15;
+        for (size_t d = 0; d < W && k + 1 + d < N; d++) {
+            const uint8_t info = votes[k * W + d];
+            rows[k * RS + shift + d] = info;
+            if (info & 3u) last[k] = (int8_t)d;
+        }
+    }
+    return lps_host_sweep(p, n_nodes, window, node_pos, node_type, rows, last.data(), node_ps, node_hap_ref);
 }
 
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {

@@ -231,7 +231,9 @@ struct lps_ctx {
     DevBuf<uint32_t> d_node_cnt;
     DevBuf<uint64_t> d_node_off;
     DevBuf<float> d_weights;
-    DevBuf<uint8_t> d_vote_info;                    // [n_nodes][window] one byte per (node, successor): see k_sweep.cu
+    DevBuf<uint8_t> d_vote_info;                    // [n_nodes][lps_vote_row_stride(window)] vote bytes of voter k, shifted to 16-node blocks (host_phase.cpp)
+    DevBuf<int8_t> d_last_link;                     // [n_nodes] largest successor offset a node links to, -1 if none
+    PinBuf<int8_t> p_last_link;
     DevBuf<int32_t> d_node_pos;
     PinBuf<uint8_t> p_vote_info;                    // pinned staging of the vote bytes for the host sweep
     DevBuf<unsigned long long> d_edge_counters;     // [0] contrib, [1] far
@@ -280,5 +282,6 @@ int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);
 void lps_host_post_process(int n_tum, const int32_t *tum_var, const uint8_t *t_alt0, const uint16_t *t_ref_len, const uint16_t *t_alt_len,
                            const int32_t *pos_base, const int32_t *read_hp_count, const int32_t *case_count, bool tumor, float *rf,
                            double *rd, int32_t *case_reads);
-void lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
-                    const uint8_t *vote_info, int32_t *node_ps, int8_t *node_hap_ref);
+int lps_vote_row_stride(int window);
+int lps_host_sweep(const lps_phase_params *p, int32_t n_nodes, int32_t window, const int32_t *node_pos, const uint8_t *node_type,
+                   const uint8_t *votes, const int8_t *last_link, int32_t *node_ps, int8_t *node_hap_ref);
