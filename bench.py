@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb, a chr1-sized share of the genome), {depth:g}x ONT-like "
+WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb), {depth:g}x ONT-like "
             "{kb:g} kb reads, 1 het variant / {sp:g} bp (10% indels), ONT error model")
 
 
@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
     ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block"])
+    ap.add_argument("--cigar32", action="store_true")    # end-to-end leg: send BAM's uint32 CIGAR ops instead of the compact 16-bit stream
     ap.add_argument("--unequal", type=int, default=0)   # 1: contig sizes +-25 % around --contig-mb (the largest one then bounds the step)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -229,8 +230,30 @@ def main():
     dtens = [{k: dev(getattr(c, k)) for k in names} for c in contigs]
     dev_batches = [batch_from(c, lambda k, d=d: d[k].data_ptr()) for c, d in zip(contigs, dtens)]
     # ---- pinned host copies for the end-to-end leg ----
-    ptens = [{k: torch.from_numpy(getattr(c, k).view(np.uint8).reshape(-1)).pin_memory() for k in names} for c in contigs]
-    pin_batches = [batch_from(c, lambda k, d=d: d[k].data_ptr()) for c, d in zip(contigs, ptens)]
+    # The host loop packs the CIGAR ops of every record into the compact 16-bit wire format while it appends the record to the
+    # batch (lps_pack_cigar16; include/lps.h): the pinned batch of the end-to-end leg holds that stream, not the uint32 ops.
+    e2e_names = list(names)
+    packed = None
+    if not args.cigar32:
+        packed = [c.pack_cigar16() for c in contigs]
+        e2e_names.remove("cigar")
+    ptens = [{k: torch.from_numpy(getattr(c, k).view(np.uint8).reshape(-1)).pin_memory() for k in e2e_names} for c in contigs]
+    pin_batches = []
+    for i, (c, d) in enumerate(zip(contigs, ptens)):
+        if packed is None:
+            pin_batches.append(batch_from(c, lambda k, d=d: d[k].data_ptr()))
+            continue
+        c16, long_len, long_at = packed[i]
+        d["cigar16"] = torch.from_numpy(c16.view(np.uint8)).pin_memory()
+        d["cigar_long_len"] = torch.from_numpy(np.ascontiguousarray(long_len).view(np.uint8)).pin_memory()
+        d["cigar_long_at"] = torch.from_numpy(np.ascontiguousarray(long_at).view(np.uint8)).pin_memory()
+        b = batch_from(c, lambda k, d=d: d[k].data_ptr() if k != "cigar" else None)
+        b.cigar16 = C.cast(d["cigar16"].data_ptr(), ffi.u16p)
+        b.n_cigar_long = len(long_len)
+        if len(long_len):
+            b.cigar_long_len = C.cast(d["cigar_long_len"].data_ptr(), ffi.u32p)
+            b.cigar_long_at = C.cast(d["cigar_long_at"].data_ptr(), ffi.u64p)
+        pin_batches.append(b)
     host_bytes = int(sum(t.numel() for d in ptens for t in d.values()))
     input_bytes = host_bytes
     n_reads_gpu = int(sum(c.n_reads for c in contigs))
@@ -355,7 +378,8 @@ def main():
         "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                 "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes,
                 "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
-                        "CIGAR and per-read records are copied; h2d bytes are the library's own count"},
+                        "CIGAR and per-read records are copied; h2d bytes are the library's own count",
+                "cigar_wire_format": "uint32 (BAM)" if args.cigar32 else "16-bit compact stream (lps_pack_cigar16), widened on the device"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

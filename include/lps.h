@@ -76,6 +76,16 @@ typedef struct {
     uint64_t seq_bytes;
     const uint8_t *qual;
     uint64_t qual_bytes;
+    /* --- optional compact wire format of the CIGAR stream (lps_batch_submit only) ----------- *
+     * The CIGAR is 80 % of what a batch sends to the device once SEQ / QUAL stay on the host.  When cigar16 != NULL,
+     * cigar[] is ignored (may be NULL): cigar16[i] holds op i of the same stream in 16 bits, len<<4|op for len < 4095,
+     * and 0xFFF0|op for a longer op, whose true length is listed in cigar_long_len[] / cigar_long_at[] (index into
+     * cigar16[], ascending).  lps_pack_cigar16 produces all three from BAM's uint32 ops while the host appends a record.
+     * The device widens the stream back to uint32 before any kernel reads it, so results cannot differ.            */
+    const uint16_t *cigar16;        /* [cigar_len]                                              */
+    const uint32_t *cigar_long_len; /* [n_cigar_long]                                           */
+    const uint64_t *cigar_long_at;  /* [n_cigar_long]                                           */
+    uint64_t n_cigar_long;
 } lps_read_batch;
 
 /* one allele call: replaces struct Variant (src/shared/Util.h:63-75)                        */
@@ -174,6 +184,12 @@ int lps_contig_get_notes(lps_ctx *ctx, lps_variant_notes *out);
  * are pinned).  The host buffers must stay valid until the next lps_* call on this context
  * returns.                                                                                     */
 int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b);
+/* Appends n BAM CIGAR ops (bam_get_cigar(aln), core.n_cigar) to a compact stream: out16[0..n) receives the 16-bit ops;
+ * an op of length >= 4095 also appends (length, base_index + i) to long_len[] / long_at[] starting at slot *n_long,
+ * which is advanced.  base_index = number of ops already in the stream.  Returns 0, or LPS_E_ARG when long_cap is too
+ * small (nothing is written past long_cap).  Pure host code; thread-safe on disjoint outputs.                      */
+int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint16_t *out16, uint32_t *long_len,
+                     uint64_t *long_at, uint64_t long_cap, uint64_t *n_long);
 /* Same, for buffers that already live in device memory (used for kernel-resident timing).      */
 int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b_dev);
 

@@ -25,7 +25,8 @@ class LpsReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("ref_start", i32p), ("l_qseq", i32p), ("n_cigar", u32p),
                 ("cigar_off", u64p), ("seq_off", u64p), ("qual_off", u64p), ("flag", u16p), ("mapq", u8p),
                 ("name_rank", i32p), ("cigar", u32p), ("cigar_len", C.c_uint64), ("seq4", u8p),
-                ("seq_bytes", C.c_uint64), ("qual", u8p), ("qual_bytes", C.c_uint64)]
+                ("seq_bytes", C.c_uint64), ("qual", u8p), ("qual_bytes", C.c_uint64),
+                ("cigar16", u16p), ("cigar_long_len", u32p), ("cigar_long_at", u64p), ("n_cigar_long", C.c_uint64)]
 
 
 class LpsCall(C.Structure):
@@ -165,6 +166,7 @@ SYMBOLS = {
     "lps_contig_get_notes": (C.c_int, [C.c_void_p, C.POINTER(LpsVariantNotes)]),
     "lps_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
     "lps_batch_submit_device": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
+    "lps_pack_cigar16": (C.c_int, [u32p, C.c_uint64, C.c_uint64, u16p, u32p, u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "lps_phase_call_alleles": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsCalls)]),
     "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),

@@ -33,6 +33,20 @@ __global__ void k_first_last(int m, const int32_t *__restrict__ reads, const uin
     ncalls[i] = (uint32_t)(c1 - c0);
 }
 
+// compact CIGAR stream -> BAM's uint32 ops: len<<4|op in 16 bits is the low half of the same value in 32 bits, so widening is a
+// zero extension, eight ops per thread (one 128-bit load, two 128-bit stores); ops marked 0xFFF are patched afterwards
+__global__ void k_widen_cigar16(size_t n8, const uint4 *__restrict__ in, uint4 *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 v = __ldg(in + i);
+    out[2 * i] = make_uint4(v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16);
+    out[2 * i + 1] = make_uint4(v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16);
+}
+__global__ void k_patch_long_ops(size_t n, const uint64_t *__restrict__ at, const uint32_t *__restrict__ len, uint32_t *__restrict__ cigar) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cigar[at[i]] = (len[i] << 4) | (cigar[at[i]] & 15u);
+}
+
 __global__ void k_mark_dead(int m, const int32_t *__restrict__ reads, uint8_t *__restrict__ dead) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) dead[reads[i]] = 1;
@@ -218,7 +232,27 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_flag, b->flag, n));
     TRY(h2d(ctx, ctx->d_mapq, b->mapq, n));
     TRY(h2d(ctx, ctx->d_name_rank, b->name_rank, n));
-    TRY(h2d(ctx, ctx->d_cigar, b->cigar, (size_t)b->cigar_len, 64));
+    if (b->cigar16) {
+        if (b->n_cigar_long && (!b->cigar_long_len || !b->cigar_long_at)) return ctx->fail(LPS_E_ARG, "cigar16 without its long-op table");
+        for (uint64_t i = 0; i < b->n_cigar_long; i++)
+            if (b->cigar_long_at[i] >= b->cigar_len || (b->cigar16[b->cigar_long_at[i]] >> 4) != 0xFFFu || (b->cigar_long_len[i] >> 28))
+                return ctx->fail(LPS_E_ARG, "cigar_long_at / cigar_long_len do not match cigar16");
+        const size_t n8 = ((size_t)b->cigar_len + 7) / 8;
+        TRY(h2d(ctx, ctx->d_cigar16, b->cigar16, (size_t)b->cigar_len, 16));
+        LPS_CUDA(ctx, ctx->d_cigar.reserve(n8 * 8 + 64 + 1));
+        if (n8) k_widen_cigar16<<<(unsigned)((n8 + 255) / 256), 256, 0, ctx->stream>>>(n8, (const uint4 *)ctx->d_cigar16.p, (uint4 *)ctx->d_cigar.p);
+        if (b->n_cigar_long) {
+            TRY(h2d(ctx, ctx->d_cigar_long_len, b->cigar_long_len, (size_t)b->n_cigar_long));
+            TRY(h2d(ctx, ctx->d_cigar_long_at, b->cigar_long_at, (size_t)b->n_cigar_long));
+            k_patch_long_ops<<<(unsigned)((b->n_cigar_long + 255) / 256), 256, 0, ctx->stream>>>((size_t)b->n_cigar_long, ctx->d_cigar_long_at.p,
+                                                                                                  ctx->d_cigar_long_len.p, ctx->d_cigar.p);
+        }
+        ctx->stats.kernel_launches += (n8 ? 1 : 0) + (b->n_cigar_long ? 1 : 0);
+        LPS_CUDA(ctx, cudaGetLastError());
+    } else {
+        if (b->cigar_len && !b->cigar) return ctx->fail(LPS_E_ARG, "null CIGAR stream");
+        TRY(h2d(ctx, ctx->d_cigar, b->cigar, (size_t)b->cigar_len, 64));
+    }
     // SEQ and QUAL are 85 % of a batch but the kernels touch ~2 bytes per allele call of them.  When the caller's
     // buffers are pinned (cudaHostAlloc / cudaHostRegister) they stay on the host and the resolve phase of the kernel
     // gathers the few sectors it needs straight over PCIe (UVA zero-copy); pageable buffers are copied as before.
@@ -258,6 +292,21 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.ms_h2d = elapsed(ctx, 0, 1);
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
+    return LPS_OK;
+}
+
+int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint16_t *out16, uint32_t *long_len, uint64_t *long_at,
+                     uint64_t long_cap, uint64_t *n_long) {
+    if ((n && (!cigar || !out16)) || !n_long) return LPS_E_ARG;
+    uint64_t nl = *n_long;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t w = cigar[i];
+        if ((w >> 4) < 0xFFFu) { out16[i] = (uint16_t)w; continue; }
+        if (nl >= long_cap || !long_len || !long_at) return LPS_E_ARG;
+        out16[i] = (uint16_t)(0xFFF0u | (w & 15u));
+        long_len[nl] = w >> 4; long_at[nl] = base_index + i; nl++;
+    }
+    *n_long = nl;
     return LPS_OK;
 }
 

@@ -143,6 +143,9 @@ struct lps_ctx {
     // ---- batch ----
     DevBuf<int32_t> d_ref_start, d_l_qseq, d_name_rank;
     DevBuf<uint32_t> d_n_cigar, d_cigar;
+    DevBuf<uint16_t> d_cigar16;                     // compact wire format of the CIGAR stream, widened into d_cigar on arrival
+    DevBuf<uint32_t> d_cigar_long_len;
+    DevBuf<uint64_t> d_cigar_long_at;
     DevBuf<uint64_t> d_cigar_off, d_seq_off, d_qual_off;
     DevBuf<uint16_t> d_flag;
     DevBuf<uint8_t> d_mapq, d_seq4, d_qual;

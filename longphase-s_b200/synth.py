@@ -218,6 +218,34 @@ class Contig:
                                  seq4=P(self.seq4, _ffi.u8p), seq_bytes=len(self.seq4), qual=P(self.qual, _ffi.u8p),
                                  qual_bytes=len(self.qual))
 
+    def pack_cigar16(self):
+        """The compact wire format of the CIGAR stream (include/lps.h, lps_read_batch.cigar16), made by the library's own
+        lps_pack_cigar16 as the host loop would while appending records.  Returns (cigar16, long_len, long_at)."""
+        n = len(self.cigar)
+        cap = int(((self.cigar >> 4) >= 0xFFF).sum())
+        c16 = np.zeros(n, np.uint16)
+        long_len, long_at = np.zeros(max(cap, 1), np.uint32), np.zeros(max(cap, 1), np.uint64)
+        n_long = C.c_uint64(0)
+        P = _ffi.ptr
+        rc = _ffi.load_library().lps_pack_cigar16(P(self.cigar, _ffi.u32p), n, 0, P(c16, _ffi.u16p), P(long_len, _ffi.u32p),
+                                                  P(long_at, _ffi.u64p), cap, C.byref(n_long))
+        if rc != 0 or n_long.value != cap:
+            raise RuntimeError(f"lps_pack_cigar16 failed: rc {rc}, {n_long.value} long ops of {cap}")
+        return c16, long_len[:cap], long_at[:cap]
+
+    def batch_struct16(self):
+        """batch_struct() with the CIGAR in the compact wire format; the arrays are kept alive on the object."""
+        self._c16 = self.pack_cigar16()
+        b = self.batch_struct()
+        P = _ffi.ptr
+        b.cigar = C.cast(None, _ffi.u32p)
+        b.cigar16 = P(self._c16[0], _ffi.u16p)
+        b.n_cigar_long = len(self._c16[1])
+        if b.n_cigar_long:
+            b.cigar_long_len = P(self._c16[1], _ffi.u32p)
+            b.cigar_long_at = P(self._c16[2], _ffi.u64p)
+        return b
+
     def name(self, i):
         s = self.names[i * self.NAME_STRIDE:(i + 1) * self.NAME_STRIDE]
         return s[:s.index(b"\0")].decode()

@@ -53,6 +53,11 @@ def check_phase(contig, params, ctx=None, verbose=False):
         res2 = ctx.phase_contig(params)
         for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
             assert np.array_equal(res2[k], res[k]), f"lps_phase_contig {k} differs from the staged calls"
+        # ... and so must the compact wire format of the CIGAR stream (lps_read_batch.cigar16)
+        ctx.submit(contig.batch_struct16())
+        res3 = ctx.phase_contig(params)
+        for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
+            assert np.array_equal(res3[k], res[k]), f"cigar16 submit: {k} differs"
         info = dict(reads=contig.n_reads, variants=contig.n_var, calls=len(orc.calls), nodes=orc.n_nodes,
                     phased=int(m.sum()), contrib=int(orc.n_contrib), lowq_cells=int((orc.weights != np.round(orc.weights)).sum()),
                     stats=ctx.stats())
