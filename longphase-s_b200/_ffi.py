@@ -29,6 +29,15 @@ class LpsReadBatch(C.Structure):
                 ("cigar16", u16p), ("cigar_long_len", u32p), ("cigar_long_at", u64p), ("n_cigar_long", C.c_uint64)]
 
 
+class LpsBgzfBlock(C.Structure):
+    _fields_ = [("comp_off", C.c_uint64), ("comp_len", C.c_uint32), ("out_len", C.c_uint32), ("out_off", C.c_uint64),
+                ("crc32", C.c_uint32), ("reserved_", C.c_uint32)]
+
+
+BGZF_BLOCK_DTYPE = np.dtype([("comp_off", "<u8"), ("comp_len", "<u4"), ("out_len", "<u4"), ("out_off", "<u8"), ("crc32", "<u4"),
+                             ("reserved_", "<u4")])
+
+
 class LpsCall(C.Structure):
     _fields_ = [("var", C.c_int32), ("quality", C.c_int16), ("allele", C.c_int8), ("origin", C.c_int8)]
 
@@ -152,7 +161,7 @@ class LpsStats(C.Structure):
                 ("ms_kernel_fold_edges", C.c_float), ("ms_kernel_window_diff", C.c_float), ("ms_wall_call_alleles", C.c_float),
                 ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
                 ("ms_host_sweep", C.c_float), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sweep_simd", C.c_int32), ("reserved_", C.c_int32)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sweep_simd", C.c_int32), ("ms_kernel_bgzf", C.c_float)]
 
 
 # every symbol include/lps.h declares: name -> (restype, argtypes)
@@ -177,6 +186,9 @@ SYMBOLS = {
     "lps_extract_normal": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_extract_tumor": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.POINTER(LpsExtractResult)]),
     "lps_somatic_tag_reads": (C.c_int, [C.c_void_p, C.POINTER(LpsTagParams), C.c_int, C.POINTER(LpsSomaticTagResult)]),
+    "lps_bgzf_scan": (C.c_int, [u8p, C.c_uint64, C.POINTER(LpsBgzfBlock), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "lps_bgzf_inflate": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(LpsBgzfBlock), C.c_uint64, u8p, C.c_uint64, C.c_int]),
+    "lps_bgzf_inflate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "lps_set_blocking_sync": (C.c_int, [C.c_int, C.c_int]),
     "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),

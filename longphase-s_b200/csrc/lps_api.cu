@@ -130,22 +130,7 @@ void lps_ctx_destroy(lps_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    // DevBuf members are plain structs; release the big ones explicitly
-    ctx->d_ref.release(); ctx->d_vpos.release(); ctx->d_vref0.release(); ctx->d_valt0.release(); ctx->d_vhom.release();
-    ctx->d_vdanger.release(); ctx->d_vfiltered.release(); ctx->d_vref_len.release(); ctx->d_valt_len.release();
-    ctx->d_ref_start.release(); ctx->d_l_qseq.release(); ctx->d_name_rank.release(); ctx->d_n_cigar.release();
-    ctx->d_cigar.release(); ctx->d_cigar_off.release(); ctx->d_seq_off.release(); ctx->d_qual_off.release();
-    ctx->d_flag.release(); ctx->d_mapq.release(); ctx->d_seq4.release(); ctx->d_qual.release();
-    ctx->d_calls_tmp.release(); ctx->d_calls.release(); ctx->d_tmp_start.release(); ctx->d_call_off.release();
-    ctx->d_ncalls.release(); ctx->d_status.release(); ctx->d_clip_keys.release(); ctx->d_clip_keys_sorted.release();
-    ctx->d_clip_unique.release(); ctx->d_clip_counts.release(); ctx->d_num_runs.release(); ctx->d_counters.release();
-    ctx->d_overflow_reads.release(); ctx->d_overflow_cand.release(); ctx->d_overflow_off.release(); ctx->d_cub_tmp.release();
-    ctx->d_read_dead.release(); ctx->d_call_erased.release(); ctx->d_var_lastw.release(); ctx->d_node_of_var.release();
-    ctx->d_node_var.release(); ctx->d_node_type.release(); ctx->d_aln_keys.release(); ctx->d_aln_keys_sorted.release();
-    ctx->d_alive_cnt.release(); ctx->d_grp_off.release(); ctx->d_M.release(); ctx->d_M_node.release();
-    ctx->d_M_node_sorted.release(); ctx->d_M_idx.release(); ctx->d_M_idx_sorted.release(); ctx->d_M_gend.release();
-    ctx->d_node_cnt.release(); ctx->d_node_off.release(); ctx->d_weights.release(); ctx->d_edge_counters.release();
-    ctx->d_ps.release(); ctx->d_hp_counts.release(); ctx->d_hap_ref.release(); ctx->d_read_hp.release();
+    // every DevBuf / PinBuf member frees itself in its destructor (delete below), with this device current
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->user_ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->kev) cudaEventDestroy(ev);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,6 +23,10 @@
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }          // lps_ctx_destroy makes the context's device current before it deletes the context
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
@@ -38,6 +43,10 @@ template <typename T> struct DevBuf {
 template <typename T> struct PinBuf {
     T *p = nullptr;
     size_t cap = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf &) = delete;
+    PinBuf &operator=(const PinBuf &) = delete;
+    ~PinBuf() { release(); }
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
@@ -143,6 +152,9 @@ struct lps_ctx {
     // ---- batch ----
     DevBuf<int32_t> d_ref_start, d_l_qseq, d_name_rank;
     DevBuf<uint32_t> d_n_cigar, d_cigar;
+    DevBuf<uint8_t> d_bgzf_in, d_bgzf_out, d_bgzf_status;   // lps_bgzf_inflate
+    DevBuf<lps_bgzf_block> d_bgzf_blocks;
+    std::vector<uint8_t> h_bgzf_status;
     DevBuf<uint16_t> d_cigar16;                     // compact wire format of the CIGAR stream, widened into d_cigar on arrival
     DevBuf<uint32_t> d_cigar_long_len;
     DevBuf<uint64_t> d_cigar_long_at;

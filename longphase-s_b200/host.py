@@ -179,10 +179,36 @@ class Context:
             res.update(call_off=g(o.call_off, n + 1, np.uint64), calls=g(o.calls, o.n_calls, _ffi.CALL_DTYPE))
         return res
 
+    # ---- BGZF (htslib bgzf_read_block / inflate_block) ----
+    def bgzf_inflate(self, data, check_crc=True):
+        """Inflates every BGZF block of `data` (bytes / uint8 array holding whole members) on the device; returns the bytes."""
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        blocks, out_bytes = bgzf_scan(buf)
+        out = np.zeros(max(out_bytes, 1), np.uint8)
+        self._check(self.lib.lps_bgzf_inflate(self.h, _ffi.ptr(buf, _ffi.u8p), len(buf), blocks.ctypes.data_as(C.POINTER(_ffi.LpsBgzfBlock)),
+                                              len(blocks), _ffi.ptr(out, _ffi.u8p), out_bytes, int(check_crc)))
+        return out[:out_bytes]
+
     def stats(self):
         s = _ffi.LpsStats()
         self._check(self.lib.lps_get_stats(self.h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
+
+
+def bgzf_scan(buf):
+    """lps_bgzf_scan: the block table (numpy, _ffi.BGZF_BLOCK_DTYPE) and the inflated size of a BGZF byte range.  Host only."""
+    lib = _ffi.load_library()
+    buf = np.ascontiguousarray(buf, np.uint8)
+    n, total = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.lps_bgzf_scan(_ffi.ptr(buf, _ffi.u8p), len(buf), None, 0, C.byref(n), C.byref(total))
+    if rc != 0:
+        raise LpsError(rc, "lps_bgzf_scan: malformed BGZF data")
+    blocks = np.zeros(max(n.value, 1), _ffi.BGZF_BLOCK_DTYPE)
+    rc = lib.lps_bgzf_scan(_ffi.ptr(buf, _ffi.u8p), len(buf), blocks.ctypes.data_as(C.POINTER(_ffi.LpsBgzfBlock)), n.value, C.byref(n),
+                           C.byref(total))
+    if rc != 0:
+        raise LpsError(rc, "lps_bgzf_scan failed")
+    return blocks[:n.value], int(total.value)
 
 
 class BamParser:
