@@ -40,7 +40,9 @@ def test_scan_rejects_malformed_members():
 
 
 @pytest.mark.gpu
-def test_inflate_matches_zlib_on_every_block_type():
+@pytest.mark.parametrize("speculate", ["1", "0"])
+def test_inflate_matches_zlib_on_every_block_type(speculate, monkeypatch):
+    monkeypatch.setenv("LPS_BGZF_SPECULATE", speculate)      # both decoders of k_bgzf_inflate
     ctx = host.Context(0)
     try:
         for name, (data, want) in bgzf_cases.streams().items():
