@@ -9,22 +9,31 @@
 //   * a match (length 3..258) is copied by all lanes at once from the warp's output window;
 //   * the window is flushed to global memory 32 consecutive bytes per store instruction;
 //   * the compressed input is staged 256 bytes at a time by coalesced loads issued one refill ahead.
-// The window is an 8 KiB ring in shared memory (12.4 KiB per warp with the tables: 18 resident warps per SM, 2664 blocks in
-// flight; a 16 KiB ring = 11 warps per SM measured 13.8 GB/s against 22.2 GB/s); matches that reach further back (up to 32 KiB)
-// read the already flushed bytes from global memory.
+// The window is a 2 KiB ring in shared memory; matches that reach further back (up to 32 KiB) read the already flushed bytes
+// from global memory (L2).  The kernel is bound by the latency of the decode chain, so what matters most is how many warps an SM
+// holds, and shared memory per warp decides that.  1 GB of BAM-like bytes on a B200, ring size -> warps per SM -> time:
+// 16 KiB -> 11 -> 68.3 ms, 8 KiB -> 17 -> 44.4 ms, 4 KiB -> 26 -> 36.5 ms, 2 KiB -> 32 (the CTA limit) -> 32.3 ms; two or four
+// warps per CTA with a 1 KiB ring (up to 42 warps per SM) were slower again (38 ms), and so was a 9-bit literal table.
 // Tables: a 10-bit (literal/length) and an 8-bit (distance) direct lookup with the canonical count/symbol arrays behind them for
 // longer codes, rebuilt per deflate block.
 #include "lps_ctx.cuh"
 
+#ifndef LPS_BGZF_LIT_FAST
+#define LPS_BGZF_LIT_FAST 10        // bits of the direct literal/length lookup
+#endif
+#ifndef LPS_BGZF_CTA_WARPS
+#define LPS_BGZF_CTA_WARPS 1        // BGZF blocks (= warps) per CTA; more than 32 resident warps per SM need more than one
+#endif
 #ifndef LPS_BGZF_RING
-#define LPS_BGZF_RING 8192          // bytes of output window per warp in shared memory (power of two >= 4096)
+#define LPS_BGZF_RING 2048          // bytes of output window per warp in shared memory (power of two >= 1024)
 #endif
 
 namespace {
 
 constexpr int RING = LPS_BGZF_RING, RMASK = RING - 1, FLUSH = RING / 4;
+constexpr int CTA_WARPS = LPS_BGZF_CTA_WARPS;
 constexpr int IN_WORDS = 64;                       // staged input, 32-bit words
-constexpr int LIT_FAST = 10, DIST_FAST = 8, CL_FAST = 7;
+constexpr int LIT_FAST = LPS_BGZF_LIT_FAST, DIST_FAST = 8, CL_FAST = 7;
 constexpr int NEAR_MAX = RING - 512;               // matches up to this distance are served by the ring
 
 enum { BGZF_OK = 0, BGZF_BAD_BLOCK_TYPE = 1, BGZF_BAD_STORED = 2, BGZF_BAD_CODE = 3, BGZF_BAD_DISTANCE = 4, BGZF_OVERRUN = 5,
@@ -171,12 +180,12 @@ __device__ __forceinline__ void flush(WarpSmem &s, uint8_t *__restrict__ out, ui
 // bytes (0.78 symbols per byte, 3.2 bytes per match): 44.3 ms against 49.5 ms.  Deferring the ring store of far matches until the
 // next near match was tried too and lost (50.7 ms): only 20 % of the matches are far and draining costs every near match.
 template <bool SPECULATE>
-__global__ void __launch_bounds__(32) k_bgzf_inflate(uint32_t n_blocks, const uint8_t *__restrict__ data, const lps_bgzf_block *__restrict__ blocks,
+__global__ void __launch_bounds__(32 * CTA_WARPS) k_bgzf_inflate(uint32_t n_blocks, const uint8_t *__restrict__ data, const lps_bgzf_block *__restrict__ blocks,
                                                      uint8_t *__restrict__ out_all, uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem &s = *reinterpret_cast<WarpSmem *>(smem_raw);
-    const int lane = threadIdx.x;
-    const uint32_t blk = blockIdx.x;
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];     // warps of a CTA share nothing
+    const int lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * CTA_WARPS + (threadIdx.x >> 5);
     if (blk >= n_blocks) return;
     const lps_bgzf_block B = blocks[blk];
     uint8_t *out = out_all + B.out_off;
@@ -396,7 +405,7 @@ int launch_inflate(lps_ctx *ctx, const uint8_t *d_data, const lps_bgzf_block *d_
     LPS_CUDA(ctx, ctx->d_bgzf_status.reserve((size_t)n_blocks + 1));
     cudaEventRecord(ctx->kev[4], ctx->stream);
     if (n_blocks)
-        (speculate ? k_bgzf_inflate<true> : k_bgzf_inflate<false>)<<<(unsigned)n_blocks, 32, sizeof(WarpSmem), ctx->stream>>>(
+        (speculate ? k_bgzf_inflate<true> : k_bgzf_inflate<false>)<<<(unsigned)((n_blocks + CTA_WARPS - 1) / CTA_WARPS), 32 * CTA_WARPS, CTA_WARPS * sizeof(WarpSmem), ctx->stream>>>(
             (uint32_t)n_blocks, d_data, d_blocks, d_out, ctx->d_bgzf_status.p);
     cudaEventRecord(ctx->kev[5], ctx->stream);
     LPS_CUDA(ctx, cudaGetLastError());
