@@ -210,7 +210,7 @@ def main():
     ap.add_argument("--variant-spacing", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
-    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block"])
+    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])   # yield: waits give the core away, contigs in flight are not capped by the cores
     ap.add_argument("--cigar32", action="store_true")    # end-to-end leg: send BAM's uint32 CIGAR ops instead of the compact 16-bit stream
     ap.add_argument("--unequal", type=int, default=0)   # 1: contig sizes +-25 % around --contig-mb (the largest one then bounds the step)
     args = ap.parse_args()
@@ -250,9 +250,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     ffi0 = importlib.import_module("longphase_s_b200._ffi")
-    blocking = args.sync == "block"   # measured on 8 GPUs / 32 cores: blocking waits double the step (21.1 vs 9.8 ms), so "auto" spins
-    if blocking:
-        ffi0.load_library().lps_set_blocking_sync(local_rank, 1)
+    # "auto": spin while every contig in flight has a host core of its own; with fewer cores (8 ranks on a 32-core box) keep all the
+    # contigs in flight anyway and let waiting threads yield their core.  Measured on 8 GPUs / 32 cores: 4 contigs per rank
+    # spinning 359.6 M reads/s, 8 per rank yielding 433.7 M; blocking waits double the step (21.1 vs 9.8 ms).  On 1 GPU / 16 cores
+    # spinning wins (80.3 M against 69.6 M with 8 yielding threads).
+    if args.sync == "auto":
+        args.sync = "yield" if ncores // world < args.contigs_per_gpu else "spin"
+    blocking = args.sync == "block"
+    if blocking or args.sync == "yield":
+        ffi0.load_library().lps_set_blocking_sync(local_rank, 1 if blocking else 2)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -262,7 +268,7 @@ def main():
 
     from concurrent.futures import ThreadPoolExecutor
     # contigs in flight per GPU: each needs a host thread, so never more than this rank's share of the host cores
-    C_ = max(1, min(args.contigs_per_gpu, ncores // world))
+    C_ = max(1, args.contigs_per_gpu if args.sync == "yield" else min(args.contigs_per_gpu, ncores // world))
     t_gen = time.time()
     # unequal contigs (a genome's are): same total, +-25 % around --contig-mb
     shape = [1.25, 0.9, 1.1, 0.75] if args.unequal and C_ % 4 == 0 else [1.0]
@@ -345,12 +351,14 @@ def main():
     def run_all(fn):
         return [f.result() for f in [pool.submit(fn, i) for i in range(C_)]]
 
-    def step_resident(i):
-        return ctxs[i].phase_contig(params)      # the batch was registered once with lps_batch_submit_device (no copy)
+    # `last`: only the final pass of a timed region turns the result into numpy arrays (Python work under the GIL, serialised over
+    # the host threads of a rank); every pass brings the result to host memory inside lps_phase_solve
+    def step_resident(i, last=True):
+        return ctxs[i].phase_contig(params, copy=last)      # the batch was registered once with lps_batch_submit_device (no copy)
 
-    def step_e2e(i):
+    def step_e2e(i, last=True):
         ctxs[i].submit(pin_batches[i])
-        return ctxs[i].phase_contig(params)
+        return ctxs[i].phase_contig(params, copy=last)
 
     def timed(fn, steps, slot):
         """`steps` passes over all contigs of this GPU; device time between the events of every context's stream, max over them."""
@@ -360,7 +368,7 @@ def main():
         t0 = time.perf_counter()
         # every host thread runs its `steps` passes back to back, with no barrier between steps: like the reference's contig loop,
         # the threads drift out of lockstep, so the host phases of one contig overlap the kernels of another
-        out = run_all(lambda i: [fn(i) for _ in range(steps)][-1])
+        out = run_all(lambda i: [fn(i, k == steps - 1) for k in range(steps)][-1])
         for ctx in ctxs:
             ctx.event_record(slot + 1)
         barrier()
@@ -437,7 +445,7 @@ def main():
                    "reads_per_gpu": n_reads_gpu, "variants_per_gpu": int(sum(c.n_var for c in contigs)), "allele_calls_per_gpu": calls_gpu,
                    "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "input_bytes_per_gpu": input_bytes,
                    "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
-                   "host_sync": "blocking" if blocking else "spin", "host_cores": ncores,
+                   "host_sync": "blocking" if blocking else ("yield" if args.sync == "yield" else "spin"), "host_cores": ncores,
                    "parallelism": f"contig-sharded x{world} GPUs, {C_} contigs in flight per GPU (one lps_ctx + host thread each), no collective",
                    "timing": "CUDA events on every context's stream (the streams the kernels run on), max over contexts and ranks",
                    "wall_ms_per_step_rank0": wall_ms, "synth_seconds": t_gen},

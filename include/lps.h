@@ -184,7 +184,8 @@ int lps_bgzf_inflate_device(lps_ctx *ctx, const uint8_t *d_data, const lps_bgzf_
 
 /* ---- process-wide ------------------------------------------------------------------------ */
 /* How host threads wait for the device on `device`: 0 = spin (lowest latency, one core per waiting thread), 1 = block on an
- * interrupt (cudaDeviceScheduleBlockingSync).  Worth setting when the host threads of all ranks outnumber the cores.      */
+ * interrupt (cudaDeviceScheduleBlockingSync), 2 = spin but yield the core between polls (cudaDeviceScheduleYield): the mode
+ * for more host threads than cores.  Must be called before the first context on the device is created.                   */
 int lps_set_blocking_sync(int device, int on);
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -409,6 +410,44 @@ typedef struct {
             filtered_pct_germline_hp, filtered_valley, filtered_outliers;              /* FilterCounts of the _purity.out log */
 } lps_purity_result;
 int lps_estimate_purity(const lps_purity_input *in, lps_purity_result *out);
+
+/* ---- somatic calling: the host stage between the extract passes and the tagging pass ------------------ *
+ * SomaticVarCaller::variantCalling without extraction and logs (src/somatic_haplotag/SomaticVarCaller.cpp:816-866):
+ * setFilterParamsWithPurity (:951-1060), getDenseTumorSnpInterval (:1243-1351), somaticFeatureFilter (:1062-1230),
+ * calibrateReadHP (:1366-1403), calculateReadSetHP (:1418-1439), statisticSomaticPosReadHP (:1441-1518) and getSomaticFlag
+ * (:2397-2412), for one contig.  `normal` / `tumor` are the results of lps_extract_normal / lps_extract_tumor of that contig
+ * (same tumor slots).  Pure host code.                                                                                     */
+typedef struct {
+    int32_t n_tum;
+    const int32_t *pos;            /* [n_tum] 0-based position of every tumor slot, ascending                              */
+    const uint8_t *callable;       /* [n_tum] 1 when the TUMOR record is a SNP, an insertion or a deletion                 */
+    const lps_extract_result *normal, *tumor;
+    double purity;                 /* lps_estimate_purity's value or --tumorPurity                                          */
+    int32_t enable_filter;         /* CallerConfig::enableFilter (default 1)                                                */
+    double percentage_threshold;   /* -p, as in lps_tag_params                                                              */
+} lps_somatic_call_input;
+enum { LPS_FILTER_TINC = 0, LPS_FILTER_MESSY_READ, LPS_FILTER_READ_COUNT, LPS_FILTER_HAP_CONSISTENCY, LPS_FILTER_VARIANT_CLUSTER,
+       LPS_FILTER_DENSE_ALT, LPS_FILTER_FIELDS };
+typedef struct {
+    /* caller-allocated, one entry per tumor slot; any pointer may be NULL */
+    uint8_t *touched;              /* the position has a SomaticData entry (a tumor alignment reached it)                   */
+    uint8_t *is_somatic;           /* SomaticData::isHighConSomaticSNP -> MultiGenomeVar::isSomaticVariant                  */
+    int8_t *derive_hp;             /* SomaticData::somaticReadDeriveByHP (SnpHP: 0 none, 1 H1, 2 H2)                        */
+    uint8_t *is_filter_out;        /* SomaticData::isFilterOut                                                              */
+    uint8_t *filtered_by;          /* [n_tum][LPS_FILTER_FIELDS] the per-filter flags                                       */
+    uint8_t *in_dense_interval;
+    float *mean_alt_per_var_read, *z_score;
+    int32_t *interval_snp_count, *min_distance, *dense_alt_same_count;
+    /* caller-allocated, one entry per alignment of the tumor batch; may be NULL */
+    int8_t *read_hp;               /* ReadVarHpCount::hpResult after calibration (ReadHP), -1 without a tumor position      */
+    int32_t *read_h3;              /* ReadVarHpCount::HP3 after calibrateReadHP, -1 without a tumor position                */
+    /* written by the call */
+    int32_t tier;                  /* FilterTier chosen from the purity: 1 (0.9-1.0) .. 5 (below 0.3)                       */
+    int32_t n_somatic;             /* positions flagged somatic                                                             */
+} lps_somatic_call_result;
+/* Returns LPS_E_DATA where the reference prints "[ERROR](calibrate read HP) ..." / "(statistic all read HP) ..." and exits. */
+int lps_somatic_call(const lps_somatic_call_input *in, lps_somatic_call_result *out);
+
 
 /* ---- timing / accounting ------------------------------------------------------------------ */
 typedef struct {

@@ -124,6 +124,22 @@ class LpsExtractResult(C.Structure):
                 ("n_calls", C.c_uint64), ("call_off", u64p), ("calls", C.POINTER(LpsCall))]
 
 
+class LpsSomaticCallInput(C.Structure):
+    _fields_ = [("n_tum", C.c_int32), ("pos", i32p), ("callable", u8p), ("normal", C.POINTER(LpsExtractResult)),
+                ("tumor", C.POINTER(LpsExtractResult)), ("purity", C.c_double), ("enable_filter", C.c_int32),
+                ("percentage_threshold", C.c_double)]
+
+
+FILTER_FIELDS = ["tinc", "messy_read", "read_count", "hap_consistency", "variant_cluster", "dense_alt"]
+
+
+class LpsSomaticCallResult(C.Structure):
+    _fields_ = [("touched", u8p), ("is_somatic", u8p), ("derive_hp", i8p), ("is_filter_out", u8p), ("filtered_by", u8p),
+                ("in_dense_interval", u8p), ("mean_alt_per_var_read", f32p), ("z_score", f32p), ("interval_snp_count", i32p),
+                ("min_distance", i32p), ("dense_alt_same_count", i32p), ("read_hp", i8p), ("read_h3", i32p), ("tier", C.c_int32),
+                ("n_somatic", C.c_int32)]
+
+
 RF_FIELDS = ["vaf", "non_del_vaf", "mpq_vaf", "low_mpq_ratio", "del_ratio", "mixed_ratio", "pure_h1_1_ratio", "pure_h2_1_ratio", "pure_h3_ratio"]
 RD_FIELDS = ["germline_imbalance", "pct_germline_hp", "allelic_imbalance", "somatic_imbalance"]
 SOMATIC_COUNTERS = ["total_alignment", "total_supplementary", "total_secondary", "total_unmapped", "total_tag", "total_untag",
@@ -191,6 +207,7 @@ SYMBOLS = {
     "lps_bgzf_inflate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "lps_set_blocking_sync": (C.c_int, [C.c_int, C.c_int]),
     "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
+    "lps_somatic_call": (C.c_int, [C.POINTER(LpsSomaticCallInput), C.POINTER(LpsSomaticCallResult)]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

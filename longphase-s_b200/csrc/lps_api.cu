@@ -82,7 +82,7 @@ const char *lps_version(void) { return "longphase-s_b200 0.1 (sm_100a)"; }
 
 int lps_set_blocking_sync(int device, int on) {
     if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
-    const cudaError_t e = cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleSpin);
+    const cudaError_t e = cudaSetDeviceFlags(on == 1 ? cudaDeviceScheduleBlockingSync : on == 2 ? cudaDeviceScheduleYield : cudaDeviceScheduleSpin);
     cudaGetLastError();
     return e == cudaSuccess ? LPS_OK : LPS_E_CUDA;
 }

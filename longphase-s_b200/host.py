@@ -101,10 +101,12 @@ class Context:
         self._check(self.lib.lps_phase_solve(self.h, C.byref(params), C.byref(o)))
         return self._result(o)
 
-    def phase_contig(self, params):
+    def phase_contig(self, params, copy=True):
+        """lps_phase_contig.  copy=False skips the numpy copies of the result (the library has already brought it to host memory
+        it owns; a caller that only wants the last of many steps saves the Python work, which holds the GIL)."""
         o = _ffi.LpsPhaseResult()
         self._check(self.lib.lps_phase_contig(self.h, C.byref(params), C.byref(o)))
-        return self._result(o)
+        return self._result(o) if copy else None
 
     def event_record(self, slot):
         self._check(self.lib.lps_event_record(self.h, int(slot)))
@@ -332,3 +334,68 @@ class TumorPurityEstimator:
             raise LpsError(rc, "lps_estimate_purity failed")
         self.result = {f: getattr(o, f) for f, _ in o._fields_}
         return o.purity
+
+
+class SomaticVarCaller:
+    """Mirror of the calling stage of reference SomaticVarCaller::variantCalling (src/somatic_haplotag/SomaticVarCaller.cpp:816-866)
+    for one contig: built from the union contig (positions and types of the TUMOR records), variantCalling() takes the results
+    of the NORMAL and TUMOR extract passes (dicts as ExtractNorDataChrProcessor / ExtractTumDataChrProcessor return them) and the
+    tumor purity, and returns per tumor slot the filter flags, isSomaticVariant / somaticReadDeriveByHP (getSomaticFlag) and per
+    alignment the calibrated read haplotype."""
+
+    def __init__(self, contig, tparams, enableFilter=True):
+        self.contig, self.tparams, self.enableFilter = contig, tparams, bool(enableFilter)
+
+    @staticmethod
+    def _as_struct(res, keep):
+        P = _ffi.ptr
+        def arr(k, dt):
+            a = np.ascontiguousarray(res[k], dt) if k in res and res[k] is not None else None
+            keep.append(a)
+            return a
+        n = len(res["h1"])
+        reads = _ffi.LpsReadTags(n_reads=n, category=P(arr("category", np.uint8), _ffi.u8p), read_hp=P(arr("read_hp", np.int8), _ffi.i8p),
+                                 h1=P(arr("h1", np.int32), _ffi.i32p), h2=P(arr("h2", np.int32), _ffi.i32p), h3=P(arr("h3", np.int32), _ffi.i32p),
+                                 n_ps=P(arr("n_ps", np.uint8), _ffi.u8p), end_pos=P(arr("end_pos", np.int32), _ffi.i32p))
+        o = _ffi.LpsExtractResult(n_tum=len(res["tum_var"]), tum_var=P(arr("tum_var", np.int32), _ffi.i32p),
+                                  pos_base=P(arr("pos_base", np.int32), _ffi.i32p), read_hp_count=P(arr("read_hp_count", np.int32), _ffi.i32p),
+                                  reads=reads, ratios_f=P(arr("ratios_f", np.float32), _ffi.f32p),
+                                  case_read_count=P(arr("case_read_count", np.int32), _ffi.i32p))
+        if "somatic_read_hp_count" in res and res["somatic_read_hp_count"] is not None and "calls" in res:
+            calls = np.ascontiguousarray(res["calls"], _ffi.CALL_DTYPE)
+            keep.append(calls)
+            o.somatic_read_hp_count = P(arr("somatic_read_hp_count", np.int32), _ffi.i32p)
+            o.window_hist = P(arr("window_hist", np.int32), _ffi.i32p)
+            o.call_off = P(arr("call_off", np.uint64), _ffi.u64p)
+            o.n_calls = len(calls)
+            o.calls = calls.ctypes.data_as(C.POINTER(_ffi.LpsCall))
+        return o
+
+    def variantCalling(self, normal_result, tumor_result, tumorPurity):
+        c = self.contig
+        tum_var = np.ascontiguousarray(tumor_result["tum_var"], np.int32)
+        nt, nr = len(tum_var), len(tumor_result["h1"])
+        pos = np.ascontiguousarray(c.var_pos[tum_var], np.int32)
+        rl, al = c.tum_ref_len[tum_var], c.tum_alt_len[tum_var]
+        callable_ = np.ascontiguousarray(((rl == 1) | (al == 1)).astype(np.uint8))          # SNP, insertion or deletion (VarData::setVariantType)
+        keep = []
+        sn, st = self._as_struct(normal_result, keep), self._as_struct(tumor_result, keep)
+        P = _ffi.ptr
+        i = _ffi.LpsSomaticCallInput(n_tum=nt, pos=P(pos, _ffi.i32p), callable=P(callable_, _ffi.u8p), normal=C.pointer(sn), tumor=C.pointer(st),
+                                     purity=float(tumorPurity), enable_filter=int(self.enableFilter),
+                                     percentage_threshold=self.tparams.percentage_threshold)
+        r = dict(touched=np.zeros(nt, np.uint8), is_somatic=np.zeros(nt, np.uint8), derive_hp=np.zeros(nt, np.int8),
+                 is_filter_out=np.zeros(nt, np.uint8), filtered_by=np.zeros((nt, len(_ffi.FILTER_FIELDS)), np.uint8),
+                 in_dense_interval=np.zeros(nt, np.uint8), mean_alt_per_var_read=np.zeros(nt, np.float32), z_score=np.zeros(nt, np.float32),
+                 interval_snp_count=np.zeros(nt, np.int32), min_distance=np.zeros(nt, np.int32), dense_alt_same_count=np.zeros(nt, np.int32),
+                 read_hp=np.zeros(nr, np.int8), read_h3=np.zeros(nr, np.int32))
+        types = dict(touched=_ffi.u8p, is_somatic=_ffi.u8p, derive_hp=_ffi.i8p, is_filter_out=_ffi.u8p, filtered_by=_ffi.u8p, in_dense_interval=_ffi.u8p,
+                     mean_alt_per_var_read=_ffi.f32p, z_score=_ffi.f32p, interval_snp_count=_ffi.i32p, min_distance=_ffi.i32p,
+                     dense_alt_same_count=_ffi.i32p, read_hp=_ffi.i8p, read_h3=_ffi.i32p)
+        o = _ffi.LpsSomaticCallResult(**{k: P(v, types[k]) for k, v in r.items()})
+        rc = _ffi.load_library().lps_somatic_call(C.byref(i), C.byref(o))
+        if rc != 0:
+            raise LpsError(rc, "lps_somatic_call: a tumor position without any read record (the reference prints [ERROR] and exits)"
+                           if rc == -6 else "lps_somatic_call failed")
+        r.update(tier=o.tier, n_somatic=o.n_somatic, tum_var=tum_var)
+        return r

@@ -116,6 +116,13 @@ class TapPurityOut(C.Structure):
                 ("q1", C.c_double), ("q3", C.c_double), ("iqr", C.c_double), ("lower_whisker", C.c_double), ("upper_whisker", C.c_double)]
 
 
+class TapCallOut(C.Structure):
+    _fields_ = [("n_tum", C.c_int32), ("n_reads", C.c_int32), ("touched", u8p), ("mean_alt", _ffi.f32p), ("z_score", _ffi.f32p),
+                ("interval_snp_count", i32p), ("min_distance", i32p), ("dense_alt_same", i32p), ("in_dense", u8p), ("filtered_by", u8p),
+                ("is_filter_out", u8p), ("high_con", u8p), ("derive_hp", i32p), ("is_somatic", u8p), ("flag_derive_hp", i32p),
+                ("read_hp", i8p), ("read_h3", i32p), ("tier", C.c_int32)]
+
+
 SOM_MODES = {"extract_normal": 0, "extract_tumor": 1, "somatic_tag": 2}
 
 _orc = None
@@ -167,6 +174,9 @@ def tap_lib():
         lib.ref_tap_state_new.restype = C.c_void_p
         lib.ref_tap_state_free.argtypes = [C.c_void_p]
         lib.ref_tap_purity.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(TapPurityOut)]
+        lib.ref_tap_somatic_call.argtypes = [C.c_void_p, C.POINTER(TapSomIn), C.c_double, C.c_int, C.POINTER(TapCallOut)]
+        lib.ref_tap_somatic_call.restype = C.c_int
+        lib.ref_tap_somatic_call_free.argtypes = [C.POINTER(TapCallOut)]
         _tap = lib
     return _tap
 
@@ -380,6 +390,18 @@ class ReferenceSomatic:
     """The UNMODIFIED reference's extract / somatic-tagging objects on a union contig (oracle/ref_tap_somatic.cpp).
     Per-read values the reference keeps in locals come back as -1 (h1/h2/h3/end_pos/read_len), 255 (n_ps)."""
 
+    @staticmethod
+    def tap_input(contig, tparams, chr_name, stats, keep):
+        P = _ffi.ptr
+        return TapSomIn(chr=chr_name.encode(), ref=contig.ref, ref_len=len(contig.ref), n_var=contig.n_var, var_pos=P(contig.var_pos, i32p),
+                        var_str_off=P(contig.var_str_off, _ffi.u32p), var_str=contig.var_str, var_hp1_is_alt=P(contig.var_hp1_is_alt, u8p),
+                        var_ps=P(contig.var_ps, i32p), nor_gt=P(contig.var_gt_kind, u8p), nor_present=P(contig.nor_present, u8p),
+                        tum_present=P(contig.tum_present, u8p), tum_str_off=P(contig.tum_str_off, _ffi.u32p), tum_str=contig.tum_str,
+                        tum_gt=P(contig.tum_gt, u8p), tum_hp1_is_alt=P(contig.tum_hp1_is_alt, u8p), tum_ps=P(contig.tum_ps, i32p),
+                        is_somatic=P(contig.is_somatic, u8p), derive_hp=P(contig.derive_hp, i8p), batch=contig.batch_struct(),
+                        names=contig.names, name_stride=contig.NAME_STRIDE, p=tparams,
+                        stats_out=C.cast(stats, C.POINTER(C.c_int64)), keep=keep)
+
     def __init__(self, contig, tparams, mode, chr_name="chrS", keep=None):
         lib = tap_lib()
         P = _ffi.ptr
@@ -412,5 +434,35 @@ class ReferencePurity:
             lib.ref_tap_purity(st, chr_name.encode(), C.byref(o))
             self.result = {f: getattr(o, f) for f, _ in o._fields_}
             self.purity = o.purity
+        finally:
+            lib.ref_tap_state_free(st)
+
+
+class ReferenceSomaticCall:
+    """The UNMODIFIED reference's two extract passes followed by the private stages of SomaticVarCaller::variantCalling and
+    getSomaticFlag on its own maps (oracle/ref_tap_somatic.cpp: ref_tap_somatic_call)."""
+
+    def __init__(self, normal_contig, tumor_contig, tparams, purity, enable_filter=True, chr_name="chrS"):
+        lib = tap_lib()
+        st = lib.ref_tap_state_new()
+        try:
+            self.normal = ReferenceSomatic(normal_contig, tparams, "extract_normal", chr_name, keep=st)
+            self.tumor = ReferenceSomatic(tumor_contig, tparams, "extract_tumor", chr_name, keep=st)
+            stats = (C.c_int64 * 22)()
+            tin = ReferenceSomatic.tap_input(tumor_contig, tparams, chr_name, stats, None)
+            o = TapCallOut()
+            self.rc = lib.ref_tap_somatic_call(st, C.byref(tin), float(purity), int(enable_filter), C.byref(o))
+            nt, n = o.n_tum, o.n_reads
+            self.touched, self.in_dense = g(o.touched, nt, np.uint8), g(o.in_dense, nt, np.uint8)
+            self.mean_alt, self.z_score = g(o.mean_alt, nt, np.float32), g(o.z_score, nt, np.float32)
+            self.interval_snp_count, self.min_distance = g(o.interval_snp_count, nt, np.int32), g(o.min_distance, nt, np.int32)
+            self.dense_alt_same = g(o.dense_alt_same, nt, np.int32)
+            self.filtered_by = g(o.filtered_by, nt * 6, np.uint8).reshape(nt, 6)
+            self.is_filter_out, self.high_con = g(o.is_filter_out, nt, np.uint8), g(o.high_con, nt, np.uint8)
+            self.derive_hp, self.flag_derive_hp = g(o.derive_hp, nt, np.int32), g(o.flag_derive_hp, nt, np.int32)
+            self.is_somatic = g(o.is_somatic, nt, np.uint8)
+            self.read_hp, self.read_h3 = g(o.read_hp, n, np.int8), g(o.read_h3, n, np.int32)
+            self.tier = o.tier
+            lib.ref_tap_somatic_call_free(C.byref(o))
         finally:
             lib.ref_tap_state_free(st)

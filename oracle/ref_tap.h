@@ -120,7 +120,8 @@ typedef struct {
     int32_t name_stride;
     lps_tag_params p;
     int64_t *stats_out;              /* [TAP_SOM_STATS], written in mode 2 */
-    void *keep;                      /* optional ref_tap_state: modes 0 / 1 leave the reference's chrPosNorBase / chrPosSomaticInfo there */
+    void *keep;                      /* optional ref_tap_state: modes 0 / 1 leave the reference's chrPosNorBase / chrPosSomaticInfo
+                                        (and, mode 1, readHpResultSet / tumorPosReadCorrBaseHP with the key of every alignment) there */
 } tap_som_in;
 
 /* the reference's TumorPurityEstimator on the maps two extract passes left in a state object */
@@ -129,6 +130,24 @@ typedef struct {
     int32_t threshold, n_after_lcvf, n_used;
     double median, q1, q3, iqr, lower_whisker, upper_whisker;
 } tap_purity_out;
+/* the reference's calling stage between the extract passes and the tagging pass (SomaticVarCaller::variantCalling,
+ * src/somatic_haplotag/SomaticVarCaller.cpp:816-866 + getSomaticFlag :2397-2412) on the maps a state object holds for `chr`;
+ * per tumor slot (same slot order as ref_tap_somatic), per alignment of the tumor batch                                   */
+typedef struct {
+    int32_t n_tum, n_reads;
+    uint8_t *touched;                /* the position has a SomaticData entry                                               */
+    float *mean_alt, *z_score;       /* SomaticData::meanAltCountPerVarRead, zScore                                        */
+    int32_t *interval_snp_count, *min_distance, *dense_alt_same;
+    uint8_t *in_dense, *filtered_by; /* filtered_by: [n_tum][6] TINC, MessyRead, ReadCount, HapConsistency, VariantCluster, DenseAlt */
+    uint8_t *is_filter_out, *high_con;
+    int32_t *derive_hp;              /* SomaticData::somaticReadDeriveByHP                                                 */
+    uint8_t *is_somatic; int32_t *flag_derive_hp;   /* what getSomaticFlag writes into the variant map                     */
+    int8_t *read_hp;                 /* ReadVarHpCount::hpResult after calculateReadSetHP, -1 for alignments without a record */
+    int32_t *read_h3;                /* ReadVarHpCount::HP3 after calibrateReadHP                                          */
+    int32_t tier;
+} tap_call_out;
+int ref_tap_somatic_call(void *state, const tap_som_in *in, double purity, int enable_filter, tap_call_out *out);
+void ref_tap_somatic_call_free(tap_call_out *out);
 void *ref_tap_state_new(void);
 void ref_tap_state_free(void *state);
 int ref_tap_purity(void *state, const char *chr, tap_purity_out *out);

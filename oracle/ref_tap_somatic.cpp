@@ -36,6 +36,9 @@ namespace {
 struct TapState {
     std::map<std::string, std::map<int, PosBase>> nor;
     std::map<std::string, std::map<int, SomaticData>> tum;
+    std::map<std::string, std::map<std::string, ReadVarHpCount>> readSet;
+    std::map<std::string, std::map<int, std::map<std::string, int>>> posRead;
+    std::map<std::string, std::vector<std::string>> readKey;    // per alignment of the tumor batch: its key in readSet, "" if none
 };
 template <typename T> T *zalloc(size_t n) { return (T *)calloc(n + 1, sizeof(T)); }
 
@@ -143,6 +146,7 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
     memset(&aln, 0, sizeof(aln));
     auto &readSet = chrReadHpResultSet[chr];
     auto &posRead = chrTumorPosReadCorrBaseHP[chr];
+    std::vector<std::string> readKeys((size_t)n);
 
     for (int32_t r = 0; r < n; r++) {
         out->call_off[r] = calls.size();
@@ -212,6 +216,7 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
                 auto rec = readSet.find(key);
                 if (rec == readSet.end()) { fprintf(stderr, "ref_tap_somatic: record %s not found\n", key.c_str()); return -1; }
                 const ReadVarHpCount &rv = rec->second;
+                readKeys[(size_t)r] = key;
                 out->read_hp[r] = (int8_t)rv.hpResult; out->h1[r] = rv.HP1; out->h2[r] = rv.HP2; out->h3[r] = rv.HP3;
                 out->n_ps[r] = (uint8_t)std::min<size_t>(rv.norCountPS.size(), 2);
                 out->end_pos[r] = rv.endPos; out->read_len[r] = rv.readLength;
@@ -325,7 +330,12 @@ extern "C" int ref_tap_somatic(int mode, const tap_som_in *in, orc_somatic_out *
     if (in->keep) {
         TapState *st = (TapState *)in->keep;
         if (mode == 0) st->nor[chr] = chrPosNorBase[chr];
-        else if (mode == 1) st->tum[chr] = chrPosSomaticInfo[chr];
+        else if (mode == 1) {
+            st->tum[chr] = chrPosSomaticInfo[chr];
+            st->readSet[chr] = chrReadHpResultSet[chr];
+            st->posRead[chr] = chrTumorPosReadCorrBaseHP[chr];
+            st->readKey[chr] = readKeys;
+        }
     }
     delete norProc; delete tumProc; delete tagProc;
     free(tname);
@@ -363,6 +373,92 @@ extern "C" int ref_tap_purity(void *state, const char *chr, tap_purity_out *out)
         out->n_used = -1;
     }
     return 0;
+}
+
+// The reference's own calling stage (SomaticVarCaller::variantCalling :816-866, minus extraction and logs) on the state of one
+// contig, then getSomaticFlag (:2397-2412).  The private stages are called in the order variantCalling calls them.
+extern "C" int ref_tap_somatic_call(void *state, const tap_som_in *in, double purity, int enable_filter, tap_call_out *out) {
+    TapState *st = (TapState *)state;
+    memset(out, 0, sizeof(*out));
+    const std::string chr = in->chr;
+    std::map<int, MultiGenomeVar> currentVariants;
+    std::vector<int> tum_pos;
+    for (int i = 0; i < in->n_var; i++) {
+        MultiGenomeVar &mv = currentVariants[in->var_pos[i]];
+        if (!in->nor_present || in->nor_present[i])
+            mv.Variant[NORMAL] = make_var(in->var_str + in->var_str_off[i], in->nor_gt ? in->nor_gt[i] : 1, in->var_hp1_is_alt[i], in->var_ps[i]);
+        if (in->tum_present[i]) {
+            mv.Variant[TUMOR] = make_var(in->tum_str + in->tum_str_off[i], in->tum_gt[i], in->tum_hp1_is_alt[i], in->tum_ps[i]);
+            tum_pos.push_back(in->var_pos[i]);
+        }
+    }
+    const int nt = (int)tum_pos.size(), n = in->batch.n_reads;
+    out->n_tum = nt; out->n_reads = n;
+    out->touched = zalloc<uint8_t>(nt); out->mean_alt = zalloc<float>(nt); out->z_score = zalloc<float>(nt);
+    out->interval_snp_count = zalloc<int32_t>(nt); out->min_distance = zalloc<int32_t>(nt); out->dense_alt_same = zalloc<int32_t>(nt);
+    out->in_dense = zalloc<uint8_t>(nt); out->filtered_by = zalloc<uint8_t>((size_t)nt * 6); out->is_filter_out = zalloc<uint8_t>(nt);
+    out->high_con = zalloc<uint8_t>(nt); out->derive_hp = zalloc<int32_t>(nt); out->is_somatic = zalloc<uint8_t>(nt);
+    out->flag_derive_hp = zalloc<int32_t>(nt); out->read_hp = zalloc<int8_t>(n); out->read_h3 = zalloc<int32_t>(n);
+
+    CallerConfig callerCfg(enable_filter != 0, false, purity, false);
+    ParsingBamConfig cfg;
+    cfg.numThreads = 1; cfg.qualityThreshold = in->p.mapping_quality; cfg.percentageThreshold = in->p.percentage_threshold;
+    cfg.resultPrefix = "/tmp/ref_tap_somatic"; cfg.region = ""; cfg.command = ""; cfg.version = ""; cfg.outputFormat = "bam";
+    cfg.tagSupplementary = in->p.tag_supplementary != 0; cfg.writeReadLog = false;
+    std::vector<std::string> chrVec{chr};
+    SomaticVarCaller caller(callerCfg, cfg, chrVec);
+    (*caller.chrPosNorBase)[chr] = st->nor[chr];
+    (*caller.chrPosSomaticInfo)[chr] = st->tum[chr];
+    (*caller.chrReadHpResultSet)[chr] = st->readSet[chr];
+    (*caller.chrTumorPosReadCorrBaseHP)[chr] = st->posRead[chr];
+
+    double tumorPurity = purity;
+    caller.setFilterParamsWithPurity(caller.somaticParams, tumorPurity);
+    const SomaticVarFilterParams &sp = caller.somaticParams;
+    out->tier = sp.zScore_maxThr == 5.233f ? 1 : sp.zScore_maxThr == 2.676f ? 2 : sp.zScore_maxThr == 5.683f ? 3 : sp.zScore_maxThr == 3.043f ? 4 : 5;
+    std::map<int, SomaticData> &somaticPosInfo = (*caller.chrPosSomaticInfo)[chr];
+    std::map<std::string, ReadVarHpCount> &readHpResultSet = (*caller.chrReadHpResultSet)[chr];
+    std::map<int, std::map<std::string, int>> &tumorPosReadCorrBaseHP = (*caller.chrTumorPosReadCorrBaseHP)[chr];
+    chrReadHpResult *distri = caller.callerReadHpDistri->getChrHpResultsPtr(chr);
+    caller.getDenseTumorSnpInterval(somaticPosInfo, readHpResultSet, tumorPosReadCorrBaseHP, (*caller.denseTumorSnpInterval)[chr]);
+    caller.somaticFeatureFilter(caller.somaticParams, currentVariants, chr, somaticPosInfo, tumorPurity);
+    caller.calibrateReadHP(chr, somaticPosInfo, readHpResultSet, tumorPosReadCorrBaseHP);
+    caller.calculateReadSetHP(chr, readHpResultSet, tumorPosReadCorrBaseHP, cfg.percentageThreshold);
+    caller.statisticSomaticPosReadHP(chr, somaticPosInfo, tumorPosReadCorrBaseHP, readHpResultSet, *distri);
+    std::map<std::string, std::map<int, MultiGenomeVar>> chrMultiVariants;
+    chrMultiVariants[chr] = currentVariants;
+    caller.getSomaticFlag(chrVec, chrMultiVariants);
+
+    for (int k = 0; k < nt; k++) {
+        auto it = somaticPosInfo.find(tum_pos[k]);
+        const MultiGenomeVar &mv = chrMultiVariants[chr][tum_pos[k]];
+        out->is_somatic[k] = mv.isSomaticVariant; out->flag_derive_hp[k] = mv.somaticReadDeriveByHP;
+        if (it == somaticPosInfo.end()) continue;
+        const SomaticData &sd = it->second;
+        out->touched[k] = 1; out->mean_alt[k] = sd.meanAltCountPerVarRead; out->z_score[k] = sd.zScore;
+        out->interval_snp_count[k] = sd.intervalSnpCount; out->min_distance[k] = sd.minDistance; out->dense_alt_same[k] = sd.denseAltSameCount;
+        out->in_dense[k] = sd.inDenseTumorInterval;
+        uint8_t *f = out->filtered_by + (size_t)k * 6;
+        f[0] = sd.filteredByTINC; f[1] = sd.filteredByMessyRead; f[2] = sd.filteredByReadCount; f[3] = sd.filteredByHapConsistency;
+        f[4] = sd.filteredByVariantCluster; f[5] = sd.filteredByDenseAlt;
+        out->is_filter_out[k] = sd.isFilterOut; out->high_con[k] = sd.isHighConSomaticSNP; out->derive_hp[k] = sd.somaticReadDeriveByHP;
+    }
+    const std::vector<std::string> &keys = st->readKey[chr];
+    for (int r = 0; r < n; r++) {
+        out->read_hp[r] = -1; out->read_h3[r] = -1;
+        if ((size_t)r >= keys.size() || keys[(size_t)r].empty()) continue;
+        auto it = readHpResultSet.find(keys[(size_t)r]);
+        if (it == readHpResultSet.end()) return -1;
+        out->read_hp[r] = (int8_t)it->second.hpResult; out->read_h3[r] = it->second.HP3;
+    }
+    return 0;
+}
+
+extern "C" void ref_tap_somatic_call_free(tap_call_out *o) {
+    free(o->touched); free(o->mean_alt); free(o->z_score); free(o->interval_snp_count); free(o->min_distance); free(o->dense_alt_same);
+    free(o->in_dense); free(o->filtered_by); free(o->is_filter_out); free(o->high_con); free(o->derive_hp); free(o->is_somatic);
+    free(o->flag_derive_hp); free(o->read_hp); free(o->read_h3);
+    memset(o, 0, sizeof(*o));
 }
 
 extern "C" void ref_tap_somatic_free(orc_somatic_out *o) {
