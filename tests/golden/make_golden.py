@@ -105,7 +105,36 @@ def tag_family():
     print("purity", os.path.getsize(path) // 1024, "KiB")
 
 
+CALL_FIELDS = ["touched", "mean_alt", "z_score", "interval_snp_count", "min_distance", "in_dense", "dense_alt_same", "filtered_by",
+               "is_filter_out", "high_con", "derive_hp", "is_somatic", "flag_derive_hp", "read_hp", "read_h3"]
+
+
+def somatic_call():
+    """The calling stage between the extract passes and the tagging pass (SomaticVarCaller::variantCalling + getSomaticFlag), from the
+    reference's own private stages run on its own extract passes."""
+    from tests import somatic_cases, test_purity, test_somatic_call
+    here = os.path.dirname(os.path.abspath(__file__))
+    tp = somatic_cases.param_sets()["purity_q20"]
+    out = {}
+    for name, purity, enable_filter in test_somatic_call.CALL_CASES:
+        un, ut = test_purity.pair(name)
+        ref = po.ReferenceSomaticCall(un, ut, tp, purity, enable_filter)
+        assert ref.rc == 0
+        key = f"{name}_{purity}_{int(enable_filter)}"
+        out[f"{key}_fingerprint"] = np.concatenate([fingerprint(un), fingerprint(ut)])
+        out[f"{key}_tier"] = np.array([ref.tier], np.int32)
+        for k in CALL_FIELDS:
+            out[f"{key}_{k}"] = getattr(ref, k)
+    path = os.path.join(here, "somatic_call.npz")
+    np.savez_compressed(path, **out)
+    print("somatic_call", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "call":
+        somatic_call()
+        sys.exit(0)
     if len(sys.argv) < 2 or sys.argv[1] != "tag":
         main()
     tag_family()
+    somatic_call()

@@ -91,3 +91,27 @@ def test_purity_matches_reference_golden():
             r = est.result
             assert [r["median"], r["q1"], r["q3"], r["iqr"], r["lower_whisker"], r["upper_whisker"]] == list(ref[1:])
             assert [r["read_count_threshold"], r["n_after_lcvf"], r["n_used"]] == list(cnt)
+
+
+def test_somatic_call_matches_reference_golden():
+    """lps_somatic_call on the oracle's extract passes against what the reference's own calling stage produced (fixture)."""
+    import importlib
+    import types
+    from oracle import pyoracle as po
+    from . import somatic_cases, test_purity, test_somatic_call
+    host = importlib.import_module("longphase_s_b200.host")
+    g = np.load(os.path.join(GOLDEN_DIR, "somatic_call.npz"))
+    tp = somatic_cases.param_sets()["purity_q20"]
+    passes = {}
+    for name, purity, enable_filter in test_somatic_call.CALL_CASES:
+        un, ut = test_purity.pair(name)
+        key = f"{name}_{purity}_{int(enable_filter)}"
+        assert np.array_equal(np.concatenate([_fp(un), _fp(ut)]), g[f"{key}_fingerprint"])
+        if name not in passes:
+            passes[name] = (po.OracleSomatic(un, tp, "extract_normal"), po.OracleSomatic(ut, tp, "extract_tumor"))
+        on, ot = passes[name]
+        got = host.SomaticVarCaller(ut, tp, enable_filter).variantCalling(test_somatic_call.as_result(on), test_somatic_call.as_result(ot), purity)
+        ref = types.SimpleNamespace(rc=0, tier=int(g[f"{key}_tier"][0]), **{k: g[f"{key}_{k}"] for k in
+                                    ("touched", "mean_alt", "z_score", "interval_snp_count", "min_distance", "in_dense", "dense_alt_same",
+                                     "filtered_by", "is_filter_out", "high_con", "derive_hp", "is_somatic", "flag_derive_hp", "read_hp", "read_h3")})
+        test_somatic_call.compare(got, ref)
