@@ -399,26 +399,36 @@ uint32_t crc32_host(const uint8_t *p, size_t n) {
     return ~c;
 }
 
-int launch_inflate(lps_ctx *ctx, const uint8_t *d_data, const lps_bgzf_block *d_blocks, uint64_t n_blocks, uint8_t *d_out) {
+// enqueues the kernel for blocks [0, n) of d_blocks on `st`; their status bytes go to d_status[0 .. n)
+void enqueue_inflate(lps_ctx *ctx, cudaStream_t st, const uint8_t *d_data, const lps_bgzf_block *d_blocks, uint64_t n, uint8_t *d_out,
+                     uint8_t *d_status) {
+    if (!n) return;
     const char *env = getenv("LPS_BGZF_SPECULATE");
     const bool speculate = !(env && env[0] == '0');
+    (speculate ? k_bgzf_inflate<true> : k_bgzf_inflate<false>)<<<(unsigned)((n + CTA_WARPS - 1) / CTA_WARPS), 32 * CTA_WARPS, CTA_WARPS * sizeof(WarpSmem), st>>>(
+        (uint32_t)n, d_data, d_blocks, d_out, d_status);
+    ctx->stats.kernel_launches++;
+}
+
+int check_status(lps_ctx *ctx, uint64_t n_blocks) {
+    for (uint64_t k = 0; k < n_blocks; k++)
+        if (ctx->h_bgzf_status[k] != BGZF_OK)
+            return ctx->fail(LPS_E_DATA, "BGZF block " + std::to_string(k) + ": " + bgzf_error_name(ctx->h_bgzf_status[k]));
+    return LPS_OK;
+}
+
+int launch_inflate(lps_ctx *ctx, const uint8_t *d_data, const lps_bgzf_block *d_blocks, uint64_t n_blocks, uint8_t *d_out) {
     LPS_CUDA(ctx, ctx->d_bgzf_status.reserve((size_t)n_blocks + 1));
     cudaEventRecord(ctx->kev[4], ctx->stream);
-    if (n_blocks)
-        (speculate ? k_bgzf_inflate<true> : k_bgzf_inflate<false>)<<<(unsigned)((n_blocks + CTA_WARPS - 1) / CTA_WARPS), 32 * CTA_WARPS, CTA_WARPS * sizeof(WarpSmem), ctx->stream>>>(
-            (uint32_t)n_blocks, d_data, d_blocks, d_out, ctx->d_bgzf_status.p);
+    enqueue_inflate(ctx, ctx->stream, d_data, d_blocks, n_blocks, d_out, ctx->d_bgzf_status.p);
     cudaEventRecord(ctx->kev[5], ctx->stream);
     LPS_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += n_blocks ? 1 : 0;
     ctx->h_bgzf_status.resize((size_t)n_blocks);
     if (n_blocks)
         LPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_bgzf_status.data(), ctx->d_bgzf_status.p, (size_t)n_blocks, cudaMemcpyDeviceToHost, ctx->stream));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_kernel_bgzf, ctx->kev[4], ctx->kev[5]);
-    for (uint64_t k = 0; k < n_blocks; k++)
-        if (ctx->h_bgzf_status[k] != BGZF_OK)
-            return ctx->fail(LPS_E_DATA, "BGZF block " + std::to_string(k) + ": " + bgzf_error_name(ctx->h_bgzf_status[k]));
-    return LPS_OK;
+    return check_status(ctx, n_blocks);
 }
 
 int check_blocks(lps_ctx *ctx, const lps_bgzf_block *blocks, uint64_t n_blocks, uint64_t n_bytes, uint64_t out_cap) {
@@ -473,15 +483,72 @@ int lps_bgzf_inflate(lps_ctx *ctx, const uint8_t *data, uint64_t n_bytes, const 
     LPS_CUDA(ctx, ctx->d_bgzf_in.reserve((size_t)n_bytes + 16));
     LPS_CUDA(ctx, ctx->d_bgzf_out.reserve((size_t)out_bytes + 16));
     LPS_CUDA(ctx, ctx->d_bgzf_blocks.reserve((size_t)n_blocks + 1));
-    if (n_bytes) LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_bgzf_in.p, data, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    LPS_CUDA(ctx, ctx->d_bgzf_status.reserve((size_t)n_blocks + 1));
+    ctx->h_bgzf_status.resize((size_t)n_blocks);
     if (n_blocks)
         LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_bgzf_blocks.p, blocks, (size_t)n_blocks * sizeof(lps_bgzf_block), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += n_bytes + n_blocks * sizeof(lps_bgzf_block);
-    rc = launch_inflate(ctx, ctx->d_bgzf_in.p, ctx->d_bgzf_blocks.p, n_blocks, ctx->d_bgzf_out.p);
-    if (rc != LPS_OK) return rc;
-    if (out_bytes) LPS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bgzf_out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += out_bytes;
-    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // The table lps_bgzf_scan makes is ascending in both offsets: the blocks are cut into chunks of ~64 MB of output, and the
+    // upload of chunk c+1, the kernel of chunk c and the download of chunk c-1 run at the same time on three streams (PCIe is full
+    // duplex).  Any other table takes the plain path: one upload, one launch, one download.
+    bool ascending = true;
+    for (uint64_t k = 1; k < n_blocks && ascending; k++)
+        ascending = blocks[k].comp_off >= blocks[k - 1].comp_off + blocks[k - 1].comp_len && blocks[k].out_off >= blocks[k - 1].out_off + blocks[k - 1].out_len;
+    uint64_t chunk_out = 64ull << 20;
+    if (const char *env = getenv("LPS_BGZF_CHUNK")) chunk_out = strtoull(env, nullptr, 10);       // bytes of output per chunk (tests)
+    if (!ascending || out_bytes <= chunk_out) {
+        if (n_bytes) LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_bgzf_in.p, data, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_inflate(ctx, ctx->d_bgzf_in.p, ctx->d_bgzf_blocks.p, n_blocks, ctx->d_bgzf_out.p);
+        if (rc != LPS_OK) return rc;
+        if (out_bytes) LPS_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bgzf_out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        if (!ctx->stream_up) LPS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_up, cudaStreamNonBlocking));
+        if (!ctx->stream_down) LPS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_down, cudaStreamNonBlocking));
+        // one block keeps a warp busy for milliseconds whatever the size of the launch, so a chunk alone (~1000 blocks) would leave
+        // most of the 4736 warp slots empty: the kernels of consecutive chunks go to four streams and run side by side
+        for (auto &cs : ctx->stream_k)
+            if (!cs) LPS_CUDA(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaEvent_t table_ready;
+        cudaEventCreateWithFlags(&table_ready, cudaEventDisableTiming);
+        cudaEventRecord(table_ready, ctx->stream);
+        for (auto &cs : ctx->stream_k) cudaStreamWaitEvent(cs, table_ready, 0);
+        size_t chunk_no = 0;
+        std::vector<cudaEvent_t> up, done;
+        cudaEventRecord(ctx->kev[4], ctx->stream);
+        for (uint64_t b0 = 0; b0 < n_blocks;) {
+            uint64_t b1 = b0 + 1;
+            while (b1 < n_blocks && blocks[b1].out_off + blocks[b1].out_len - blocks[b0].out_off <= chunk_out) b1++;
+            const uint64_t c_lo = blocks[b0].comp_off, c_hi = blocks[b1 - 1].comp_off + blocks[b1 - 1].comp_len;
+            const uint64_t o_lo = blocks[b0].out_off, o_hi = blocks[b1 - 1].out_off + blocks[b1 - 1].out_len;
+            cudaEvent_t e_up, e_done;
+            cudaEventCreateWithFlags(&e_up, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&e_done, cudaEventDisableTiming);
+            up.push_back(e_up); done.push_back(e_done);
+            if (c_hi > c_lo) cudaMemcpyAsync(ctx->d_bgzf_in.p + c_lo, data + c_lo, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, ctx->stream_up);
+            cudaEventRecord(e_up, ctx->stream_up);
+            cudaStream_t ks = ctx->stream_k[chunk_no++ % 4];
+            cudaStreamWaitEvent(ks, e_up, 0);
+            enqueue_inflate(ctx, ks, ctx->d_bgzf_in.p, ctx->d_bgzf_blocks.p + b0, b1 - b0, ctx->d_bgzf_out.p, ctx->d_bgzf_status.p + b0);
+            cudaEventRecord(e_done, ks);
+            cudaStreamWaitEvent(ctx->stream, e_done, 0);       // the context's stream joins every chunk: it carries the end event and the status copy
+            cudaStreamWaitEvent(ctx->stream_down, e_done, 0);
+            if (o_hi > o_lo) cudaMemcpyAsync(out + o_lo, ctx->d_bgzf_out.p + o_lo, (size_t)(o_hi - o_lo), cudaMemcpyDeviceToHost, ctx->stream_down);
+            b0 = b1;
+        }
+        cudaEventRecord(ctx->kev[5], ctx->stream);
+        cudaMemcpyAsync(ctx->h_bgzf_status.data(), ctx->d_bgzf_status.p, (size_t)n_blocks, cudaMemcpyDeviceToHost, ctx->stream);
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->stream_down), e3 = cudaStreamSynchronize(ctx->stream_up);
+        for (cudaEvent_t e : up) cudaEventDestroy(e);
+        for (cudaEvent_t e : done) cudaEventDestroy(e);
+        cudaEventDestroy(table_ready);
+        LPS_CUDA(ctx, e1); LPS_CUDA(ctx, e2); LPS_CUDA(ctx, e3);
+        LPS_CUDA(ctx, cudaGetLastError());
+        cudaEventElapsedTime(&ctx->stats.ms_kernel_bgzf, ctx->kev[4], ctx->kev[5]);   // first launch to last completion, waits for uploads included
+        rc = check_status(ctx, n_blocks);
+        if (rc != LPS_OK) return rc;
+    }
     if (check_crc)
         for (uint64_t k = 0; k < n_blocks; k++)
             if (crc32_host(out + blocks[k].out_off, blocks[k].out_len) != blocks[k].crc32)

@@ -135,6 +135,9 @@ void lps_ctx_destroy(lps_ctx *ctx) {
     for (auto &ev : ctx->user_ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->kev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    for (auto &cs : ctx->stream_k) if (cs) cudaStreamDestroy(cs);
+    if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
+    if (ctx->stream_down) cudaStreamDestroy(ctx->stream_down);
     delete ctx;
 }
 

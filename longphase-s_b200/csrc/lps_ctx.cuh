@@ -126,6 +126,8 @@ struct CallCounters {
 struct lps_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_k[4] = {nullptr, nullptr, nullptr, nullptr};   // ... and the streams its kernels alternate over
+    cudaStream_t stream_up = nullptr, stream_down = nullptr;   // lps_bgzf_inflate: upload / download streams of the chunk pipeline
     cudaEvent_t ev[8] = {};
     cudaEvent_t user_ev[4] = {};
     cudaEvent_t kev[6] = {};   // around the hot kernels

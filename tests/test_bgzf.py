@@ -53,6 +53,19 @@ def test_inflate_matches_zlib_on_every_block_type(speculate, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_inflate_chunk_pipeline(monkeypatch):
+    """Large inputs are cut into chunks whose upload, kernel and download overlap on three streams; here with tiny chunks."""
+    monkeypatch.setenv("LPS_BGZF_CHUNK", "150000")
+    ctx = host.Context(0)
+    try:
+        for name in ("bam_like_l6", "zeros_l9", "random_stored", "far_matches_l6", "tiny_members"):
+            data, want = bgzf_cases.streams()[name]
+            assert ctx.bgzf_inflate(data, check_crc=True).tobytes() == want, name
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
 def test_inflate_golden_bam_from_htslib():
     data = open(bgzf_cases.GOLDEN_BAM, "rb").read()
     ctx = host.Context(0)
