@@ -215,38 +215,56 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
             const unsigned al_a = (ea_c >> 1) & 1u, hi_a = ea_c & 1u;
             const bool act0 = lane < W && m + 1u + (uint32_t)lane < gend_c;
             const bool act1 = lane < W2 && m + 33u + (uint32_t)lane < gend_c;
+            // the read reaches beyond 32 successors (warp-uniform).  Rare for reads that carry ~20 calls, so everything that concerns
+            // the second slot of a lane sits behind this one branch instead of riding along predicated in every iteration.
+            const bool second = __any_sync(FULL, act1);
             if (!act0) eb0 = 0xffffffffu;
-            if (!act1) eb1 = 0xffffffffu;
-            const int nb0 = (int)(eb0 >> 2), nb1 = (int)(eb1 >> 2);
-            const bool second = __any_sync(FULL, act1);     // the read reaches beyond 32 successors (warp-uniform)
+            const int nb0 = (int)(eb0 >> 2);
             // duplicates (two calls of one merged read at the same position) are adjacent in the read's sorted list
             const uint32_t p0 = __shfl_up_sync(FULL, eb0 >> 2, 1);
             bool dup = act0 && lane > 0 && p0 == (uint32_t)nb0;
-            if (second) {
+            const int d0 = nb0 - a - 1;
+            const bool dense0 = act0 && d0 >= 0 && d0 < W;
+            c32 += (unsigned)dense0;
+            f32 += (unsigned)(act0 && !dense0);
+            float *cell0 = dense0 ? &acc[d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u))] : nullptr;
+            const bool high0 = hi_a && (eb0 & 1u);
+            if (!second) {
+                if (!__any_sync(FULL, dup)) {
+                    // distinct successors of one read hit distinct cells
+                    if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }   // SubEdge::addSubEdge :40-43, :62-65
+                } else {
+                    // keep the read's own order
+                    for (int l = 0; l < 32; l++) {
+                        if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                        __syncwarp();
+                    }
+                }
+            } else {
+                if (!act1) eb1 = 0xffffffffu;
+                const int nb1 = (int)(eb1 >> 2);
                 const uint32_t p1 = __shfl_up_sync(FULL, eb1 >> 2, 1), last0 = __shfl_sync(FULL, eb0 >> 2, 31);
                 dup = dup || (act1 && (lane > 0 ? p1 : last0) == (uint32_t)nb1);
-            }
-            const bool any_dup = __any_sync(FULL, dup);
-            const int d0 = nb0 - a - 1, d1 = nb1 - a - 1;
-            const bool dense0 = act0 && d0 >= 0 && d0 < W, dense1 = act1 && d1 >= 0 && d1 < W;
-            c32 += (unsigned)dense0 + (unsigned)dense1;
-            f32 += (unsigned)(act0 && !dense0) + (unsigned)(act1 && !dense1);
-            float *cell0 = dense0 ? &acc[d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u))] : nullptr;
-            float *cell1 = dense1 ? &acc[d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u))] : nullptr;
-            const bool high0 = hi_a && (eb0 & 1u), high1 = hi_a && (eb1 & 1u);
-            if (!any_dup) {
-                // distinct successors of one read hit distinct cells
-                if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }   // SubEdge::addSubEdge :40-43, :62-65
-                if (second && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
-            } else {
-                // keep the read's own order: successors 0..31, then 32..W-1
-                for (int l = 0; l < 32; l++) {
-                    if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
-                    __syncwarp();
-                }
-                for (int l = 0; l < W2; l++) {
-                    if (lane == l && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
-                    __syncwarp();
+                const bool any_dup = __any_sync(FULL, dup);
+                const int d1 = nb1 - a - 1;
+                const bool dense1 = act1 && d1 >= 0 && d1 < W;
+                c32 += (unsigned)dense1;
+                f32 += (unsigned)(act1 && !dense1);
+                float *cell1 = dense1 ? &acc[d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u))] : nullptr;
+                const bool high1 = hi_a && (eb1 & 1u);
+                if (!any_dup) {
+                    if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                    if (dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
+                } else {
+                    // keep the read's own order: successors 0..31, then 32..W-1
+                    for (int l = 0; l < 32; l++) {
+                        if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                        __syncwarp();
+                    }
+                    for (int l = 0; l < W2; l++) {
+                        if (lane == l && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
+                        __syncwarp();
+                    }
                 }
             }
             __syncwarp();
