@@ -1,0 +1,593 @@
+// haplotag_host.cpp — the `haplotag` sub-command above the C ABI: options, the phased-VCF loader, the ordered BAM
+// reader / writer with its @PG line, HP / PS / PQ tagging from the device verdicts, the --log table and the report.
+// See lps_host.h for the reference seams each stage replaces.
+//
+// The reference tags one record at a time inside its htslib loop (HaplotagParsingBam.cpp:453-492).  Here the loop appends
+// records to a chunk (LPS_TAG_CHUNK alignments, default 65536), one lps_tag_reads call judges the chunk on the device, and
+// the records are tagged and written in their original order, so the output file is the same byte stream.
+// Scope notes: --sv-file, --mod-file and --cram are parsed but rejected (outside the rebuilt hot path).
+#include "host_common.h"
+
+#include <getopt.h>
+
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iterator>
+#include <sstream>
+
+namespace {
+
+const char *TAG_USAGE =
+    "Usage:  haplotag [OPTION] ... READSFILE\n"
+    "      --help                          display this help and exit.\n\n"
+    "required arguments:\n"
+    "      -s, --snp-file=NAME             input SNP vcf file (phased).\n"
+    "      -b, --bam-file=NAME             input bam file.\n"
+    "      -r, --reference=NAME            reference fasta.\n"
+    "optional arguments:\n"
+    "      --tagSupplementary              tag supplementary alignment. default:false\n"
+    "      -q, --qualityThreshold=Num      not tag alignment if the mapping quality less than threshold. default:1\n"
+    "      -p, --percentageThreshold=Num   share of the alleles the winning haplotype needs. default:0.6\n"
+    "      -t, --threads=Num               number of BAM (de)compression threads. default:1\n"
+    "      -o, --out-prefix=NAME           prefix of the tagged BAM. default:result\n"
+    "      --region=REGION                 chrom | chrom:start | chrom:start-end. default:\"\"(all regions)\n"
+    "      --log                           an additional log file records the result of each read. default:false\n"
+    "not available in this build: --sv-file, --mod-file, --cram\n";
+
+enum { T_HELP = 1, T_SUP, T_SV, T_MOD, T_REGION, T_CRAM, T_LOG };
+
+const struct option TAG_LONG[] = {
+    {"help", no_argument, NULL, T_HELP},
+    {"snp-file", required_argument, NULL, 's'},
+    {"bam-file", required_argument, NULL, 'b'},
+    {"reference", required_argument, NULL, 'r'},
+    {"sv-file", required_argument, NULL, T_SV},
+    {"mod-file", required_argument, NULL, T_MOD},
+    {"threads", required_argument, NULL, 't'},
+    {"qualityThreshold", required_argument, NULL, 'q'},
+    {"percentageThreshold", required_argument, NULL, 'p'},
+    {"tagSupplementary", no_argument, NULL, T_SUP},
+    {"out-prefix", required_argument, NULL, 'o'},
+    {"region", required_argument, NULL, T_REGION},
+    {"cram", no_argument, NULL, T_CRAM},
+    {"log", no_argument, NULL, T_LOG},
+    {NULL, 0, NULL, 0}};
+
+struct TagOptions {
+    int threads = 1, quality = 1;
+    double percentage = 0.6;
+    bool tag_supplementary = false, log = false, cram = false;
+    std::string snp_file, sv_file, mod_file, bam, fasta, prefix = "result", region, command = "longphase-s ";
+};
+
+template <class T>
+void take(const char *text, T &dst) {
+    std::istringstream in(text ? text : "");
+    in >> dst;
+}
+
+bool required_file(const std::string &path, const char *what) {
+    if (path.empty()) { std::cerr << "[ERROR] haplotag: missing " << what << ".\n"; return false; }
+    if (!std::ifstream(path.c_str()).is_open()) { std::cerr << "[ERROR] haplotag: " << what << ": " << path << " not exist.\n\n"; return false; }
+    return true;
+}
+
+// one phased heterozygous record of the NORMAL sample (VarData, HaplotagType.h:110-143)
+struct PhasedVariant {
+    std::string ref, alt;
+    int ps = -1;
+    bool hp1_is_alt = false;   // GT 1|0
+    bool oriented = false;     // GT was 0|1 or 1|0 (otherwise HP1 / HP2 stay empty in the reference)
+};
+
+struct Chunk {
+    lpsh::PackedContig pack;
+    std::vector<bam1_t *> records;
+    void clear() {
+        for (bam1_t *b : records) bam_destroy1(b);
+        records.clear();
+        pack = lpsh::PackedContig();
+    }
+};
+
+}  // namespace
+
+struct lpsh_tag {
+    TagOptions opt;
+    std::vector<std::string> chr_names;               // VCF_Info::chrVec (##contig order), narrowed by --region
+    std::map<std::string, int> chr_length;
+    std::map<std::string, std::map<int, PhasedVariant>> variants;
+    std::map<std::string, std::string> reference;
+    // files
+    samFile *in = nullptr, *out = nullptr;
+    bam_hdr_t *hdr = nullptr;
+    hts_idx_t *idx = nullptr;
+    htsThreadPool pool = {NULL, 0};
+    std::ofstream log;
+    // contig in flight
+    int cur = -1;
+    hts_itr_t *itr = nullptr;
+    bool itr_done = false;
+    Chunk chunk;
+    std::vector<int32_t> cur_pos, cur_ps;             // variant table of the contig in flight
+    size_t chunk_reads = 65536;
+    // ReadStatistics (HaplotagProcess.h:21-45)
+    int64_t st_alignment = 0, st_supplementary = 0, st_secondary = 0, st_unmapped = 0, st_tag = 0, st_untag = 0, st_low = 0,
+            st_other = 0, st_empty = 0, st_similar = 0, st_no_variant = 0, st_hp[3] = {0, 0, 0};
+    std::time_t t_begin = time(NULL);
+};
+
+namespace {
+
+int parse_tag_options(int argc, char **argv, TagOptions &o) {   // ArgumentManager::parseOptions + Haplotag.cpp:60-150
+    optind = 1;
+    bool bad = false;
+    for (int c; (c = getopt_long(argc, argv, "s:b:o:t:q:p:r:", TAG_LONG, NULL)) != -1;) {
+        switch (c) {
+            case 't': take(optarg, o.threads); break;
+            case 'o': take(optarg, o.prefix); break;
+            case 'q': take(optarg, o.quality); break;
+            case 'p': take(optarg, o.percentage); break;
+            case T_SUP: o.tag_supplementary = true; break;
+            case T_REGION: take(optarg, o.region); break;
+            case T_CRAM: o.cram = true; break;
+            case T_LOG: o.log = true; break;
+            case 's': take(optarg, o.snp_file); break;
+            case 'b': take(optarg, o.bam); break;
+            case 'r': take(optarg, o.fasta); break;
+            case T_SV: take(optarg, o.sv_file); break;
+            case T_MOD: take(optarg, o.mod_file); break;
+            case T_HELP: std::cout << TAG_USAGE << std::endl; return 2;
+            default: bad = true;
+        }
+    }
+    for (int i = 0; i < argc; i++) { o.command += argv[i]; o.command += " "; }
+    bad |= !required_file(o.snp_file, "SNP file");
+    bad |= !required_file(o.bam, "BAM file");
+    bad |= !required_file(o.fasta, "reference file");
+    if (o.threads < 1) { std::cerr << "[ERROR] haplotag: invalid threads. value: " << o.threads << "\nplease check -t, --threads=Num\n"; bad = true; }
+    if (o.percentage > 1 || o.percentage < 0) {
+        std::cerr << "[ERROR] haplotag: invalid percentage threshold. value: " << o.percentage
+                  << "\nthis value need: 0~1, please check -p, --percentageThreshold=Num\n";
+        bad = true;
+    }
+    if (!o.sv_file.empty() || !o.mod_file.empty() || o.cram) {
+        std::cerr << "[ERROR] haplotag: --sv-file, --mod-file and --cram are not available in this build.\n";
+        bad = true;
+    }
+    if (bad) { std::cerr << "\n"; std::cout << TAG_USAGE << std::endl; return 1; }
+    return 0;
+}
+
+void tag_banner(const TagOptions &o) {   // HaplotagProcess::printParamsMessage
+    std::ostream &e = std::cerr;
+    e << "LongPhase-S v" << lpsh::REFERENCE_VERSION << " - Haplotag (" << lps_version() << ")\n\n";
+    e << "phased SNP file:   " << o.snp_file << "\nphased SV file:    " << o.sv_file << "\nphased MOD file:   " << o.mod_file << "\n";
+    e << "input bam file:    " << o.bam << "\ninput ref file:    " << o.fasta << "\noutput bam file:   " << o.prefix + ".bam" << "\n";
+    e << "number of threads: " << o.threads << "\nwrite log file:    " << (o.log ? "true" : "false") << "\n";
+    e << "log file:          " << (o.log ? (o.prefix + ".out") : "") << "\n-------------------------------------------\n";
+    e << "tag region:                    " << (!o.region.empty() ? o.region : "all") << "\n";
+    e << "filter mapping quality below:  " << o.quality << "\npercentage threshold:          " << o.percentage << "\n";
+    e << "tag supplementary:             " << (o.tag_supplementary ? "true" : "false") << "\n-------------------------------------------\n";
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phased VCF of the NORMAL sample (VcfParser::parserProcess, HaplotagVcfParser.cpp:206-345): a text parser, as in the reference
+int subfield_of(const std::string &format, const char *key) {
+    const size_t at = format.find(key);
+    if (at == std::string::npos) return 0;
+    return (int)std::count(format.begin(), format.begin() + at, ':');
+}
+size_t subfield_start(const std::string &sample, int k) {
+    size_t i = 0;
+    for (int seen = 0; i < sample.size() && seen < k; i++) seen += sample[i] == ':';
+    return i;
+}
+char peek(const std::string &s, size_t i) { return i < s.size() ? s[i] : '\0'; }
+
+struct VcfLoadState {
+    bool integer_ps = false;
+    std::map<std::string, int> ps_index;
+};
+
+void load_tag_line(lpsh_tag &job, const std::string &line, VcfLoadState &st) {
+    if (line.compare(0, 2, "##") == 0) {
+        if (line.find("contig=") != std::string::npos) {
+            const int id_start = (int)line.find("ID=") + 3, id_end = (int)line.find(",length=");
+            const int len_start = id_end + 8, len_end = (int)line.find(">");
+            const std::string chr = line.substr((size_t)id_start, (size_t)(id_end - id_start));
+            job.chr_names.push_back(chr);
+            job.chr_length[chr] = std::stoi(line.substr((size_t)len_start, (size_t)(len_end - len_start)));
+        }
+        if (line.compare(0, 16, "##FORMAT=<ID=PS,") == 0) {
+            if (line.find("Type=Integer") != std::string::npos) st.integer_ps = true;
+            else if (line.find("Type=String") != std::string::npos) { st.integer_ps = false; std::cerr << "PS type is String. Auto index to integer ... "; }
+            else { std::cerr << "[ERROR](VcfParser::processLine) => not found PS type (Type=Integer or Type=String).\n"; exit(EXIT_SUCCESS); }
+        }
+        return;
+    }
+    if (line.compare(0, 1, "#") == 0) return;
+    std::istringstream split(line);
+    std::vector<std::string> f((std::istream_iterator<std::string>(split)), std::istream_iterator<std::string>());
+    if (f.empty()) return;
+    if (f.size() < 10) { std::cerr << "[ERROR](VcfParser::parserProcess) => VCF file format not supported: " << line << std::endl; exit(EXIT_FAILURE); }
+    const std::string &format = f[8], &sample = f[9];
+    const size_t g = subfield_start(sample, subfield_of(format, "GT"));
+    const char a = peek(sample, g), bar = peek(sample, g + 1), b = peek(sample, g + 2);
+    if (a == b || bar != '|') return;   // only phased heterozygous records feed the germline tagger
+    const size_t p = subfield_start(sample, subfield_of(format, "PS"));
+    const size_t p_end = sample.find(':', p + 1);
+    const std::string ps_text = p_end != std::string::npos ? sample.substr(p, p_end - p) : sample.substr(std::min(p, sample.size()));
+    PhasedVariant v;
+    v.ref = f[3];
+    const std::string &alts = f[4];
+    if (alts.find(',') != std::string::npos) {
+        if (sample.find('2') != std::string::npos) return;   // the reference's "GT has a 2" test reduces to this (HaplotagVcfParser.cpp:283-286)
+        v.alt = alts.substr(0, alts.find(','));
+    } else {
+        v.alt = alts;
+    }
+    const size_t rl = v.ref.size(), al = v.alt.size();
+    if (!((rl == 1 && al >= 1) || (rl > 1 && al == 1) || (rl > 1 && rl == al))) {   // VarData::setVariantType throws
+        std::cerr << "terminate: (loadVariantType)Invalid allele: " << v.ref << " " << v.alt << "\n";
+        exit(1);
+    }
+    if (st.integer_ps) v.ps = std::stoi(ps_text);
+    else {
+        if (st.ps_index.find(ps_text) == st.ps_index.end()) { const int next = (int)st.ps_index.size(); st.ps_index[ps_text] = next; }
+        v.ps = st.ps_index[ps_text];
+    }
+    if (a == '0' && b == '1') { v.oriented = true; v.hp1_is_alt = false; }
+    else if (a == '1' && b == '0') { v.oriented = true; v.hp1_is_alt = true; }
+    if (!v.oriented) return;   // GT such as 0|2 without a second ALT: HP1 / HP2 stay empty in the reference; not representable, skipped
+    job.variants[f[0]][std::stoi(f[1]) - 1] = v;
+}
+
+int load_tag_vcf(lpsh_tag &job) {
+    const std::string &path = job.opt.snp_file;
+    VcfLoadState st;
+    if (path.find("gz") != std::string::npos) {
+        std::string text;
+        if (!lpsh::read_gz(path, text)) { std::cerr << "Fail to open vcf: " << path << "\n"; return 0; }
+        size_t at = 0;
+        for (size_t nl; (nl = text.find('\n', at)) != std::string::npos; at = nl + 1) load_tag_line(job, text.substr(at, nl - at), st);
+    } else if (path.find("vcf") != std::string::npos) {
+        std::ifstream in(path.c_str());
+        if (!in.is_open()) { std::cerr << "Fail to open vcf: " << path << "\n"; exit(1); }
+        std::string line;
+        while (!in.eof()) { std::getline(in, line); load_tag_line(job, line, st); }
+    } else {
+        std::cerr << "file: " << path << "\nnot vcf file. please check filename extension\n";
+        exit(EXIT_FAILURE);
+    }
+    return 0;
+}
+
+// HaplotagProcess::setProcessingChromRegion (HaplotagProcess.cpp:105-135)
+void narrow_to_region(lpsh_tag &job) {
+    if (!job.opt.region.empty()) {
+        const size_t colon = job.opt.region.find(':');
+        const std::string chr = colon != std::string::npos ? job.opt.region.substr(0, colon) : job.opt.region;
+        if (std::find(job.chr_names.begin(), job.chr_names.end(), chr) == job.chr_names.end()) {
+            std::cerr << "[ERROR] Incorrect chromosome for input region: " << chr << std::endl;
+            exit(1);
+        }
+        job.chr_names.assign(1, chr);
+    }
+    for (auto it = job.variants.begin(); it != job.variants.end();) {
+        if (std::find(job.chr_names.begin(), job.chr_names.end(), it->first) == job.chr_names.end()) it = job.variants.erase(it);
+        else ++it;
+    }
+}
+
+// getLastVarPos + FastaParser (HaplotagParsingBam.cpp:333-373, ParsingBam.cpp:17-59)
+int load_tag_reference(lpsh_tag &job) {
+    faidx_t *fai = fai_load(job.opt.fasta.c_str());
+    if (!fai) return lpsh::fail("cannot load the FASTA index of " + job.opt.fasta);
+    for (const std::string &chr : job.chr_names) {
+        int last = 0;
+        auto it = job.variants.find(chr);
+        if (it != job.variants.end() && !it->second.empty()) last = it->second.rbegin()->first;   // every loaded record has a phase set
+        int len = 0;
+        char *s = faidx_fetch_seq(fai, chr.c_str(), 0, last + 5, &len);
+        if (len == 0) std::cout << "nothing in reference file \n";
+        job.reference[chr] = s ? s : "";
+        free(s);
+    }
+    fai_destroy(fai);
+    return 0;
+}
+
+void write_log_header(lpsh_tag &job) {   // GermlineTagLog::addParamsMessage / writeBasicColumns (HaplotagProcess.cpp:181-208)
+    const TagOptions &o = job.opt;
+    job.log << "##snpFile:" << o.snp_file << "\n##svFile:" << o.sv_file << "\n##bamFile:" << o.bam << "\n##resultPrefix:" << o.prefix << "\n"
+            << "##numThreads:" << o.threads << "\n##region:" << o.region << "\n##qualityThreshold:" << o.quality << "\n"
+            << "##percentageThreshold:" << o.percentage << "\n##tagSupplementary:" << o.tag_supplementary << "\n";
+    job.log << "#ReadID\tCHROM\tReadStart\tConfidnet(%)\tHaplotype\tPhaseSet\tTotalAllele\tHP1Allele\tHP2Allele\tphasingQuality(PQ)\t(Variant,HP)\t(PhaseSet,Variantcount)\n";
+}
+
+void drop_aux(bam1_t *b, const char *tag) {
+    uint8_t *p = bam_aux_get(b, tag);
+    if (p) bam_aux_del(b, p);
+}
+
+void finish_contig(lpsh_tag &job) {
+    if (job.itr) hts_itr_destroy(job.itr);
+    job.itr = nullptr;
+    job.cur = -1;
+    job.chunk.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int lpsh_tag_open(int argc, char **argv, lpsh_tag **out) {
+    if (!out) return -1;
+    *out = nullptr;
+    lpsh_tag *job = new lpsh_tag();
+    const int rc = parse_tag_options(argc, argv, job->opt);
+    if (rc != 0) { delete job; return rc; }
+    if (const char *e = getenv("LPS_TAG_CHUNK")) { const long v = atol(e); if (v > 0) job->chunk_reads = (size_t)v; }
+    tag_banner(job->opt);
+    std::time_t t0 = time(NULL);
+    std::cerr << "parsing SNP VCF ... ";
+    load_tag_vcf(*job);
+    std::cerr << difftime(time(NULL), t0) << "s\n";
+    narrow_to_region(*job);
+    *out = job;
+    return 0;
+}
+
+int lpsh_tag_n_contigs(const lpsh_tag *h) { return h ? (int)h->chr_names.size() : 0; }
+const char *lpsh_tag_contig_name(const lpsh_tag *h, int i) {
+    return (h && i >= 0 && (size_t)i < h->chr_names.size()) ? h->chr_names[(size_t)i].c_str() : nullptr;
+}
+int lpsh_tag_params(const lpsh_tag *h, lps_tag_params *out) {
+    if (!h || !out) return -1;
+    memset(out, 0, sizeof(*out));
+    out->mapping_quality = h->opt.quality;
+    out->mapq_filter = 1;
+    out->tag_supplementary = h->opt.tag_supplementary;
+    out->have_reference = 1;
+    out->percentage_threshold = h->opt.percentage;
+    return 0;
+}
+
+int lpsh_tag_begin(lpsh_tag *h) {
+    if (!h) return -1;
+    const TagOptions &o = h->opt;
+    if (h->chr_names.empty()) { std::cerr << "[ERROR](HaplotagBamParser): chrVec is empty" << std::endl; return lpsh::fail("the VCF header lists no contig"); }
+    if (o.log) {
+        h->log.open((o.prefix + ".out").c_str());
+        if (!h->log.is_open()) { std::cerr << "Fail to open write file: " << o.prefix + ".out" << "\n"; return lpsh::fail("cannot open the log file"); }
+        write_log_header(*h);
+    }
+    if (load_tag_reference(*h) != 0) return -1;
+    if (!(h->pool.pool = hts_tpool_init(o.threads))) return lpsh::fail("Error creating thread pool");
+    // BamFileRAII (HaplotagParsingBam.cpp:20-82)
+    h->in = hts_open(o.bam.c_str(), "r");
+    if (!h->in) return lpsh::fail("Cannot open bam file " + o.bam);
+    if (hts_set_fai_filename(h->in, o.fasta.c_str()) != 0) return lpsh::fail("Cannot set FASTA index file for " + o.fasta);
+    h->hdr = sam_hdr_read(h->in);
+    if (!h->hdr) return lpsh::fail("Cannot read header from bam file " + o.bam);
+    sam_hdr_add_pg(h->hdr, "longphase-s", "VN", lpsh::REFERENCE_VERSION, "CL", o.command.c_str(), NULL);
+    h->idx = sam_index_load(h->in, o.bam.c_str());
+    if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.bam);
+    if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.bam);
+    const std::string out_path = o.prefix + ".bam";
+    h->out = hts_open(out_path.c_str(), "wb");
+    if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
+    hts_set_fai_filename(h->out, o.fasta.c_str());
+    if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);
+    if (hts_set_opt(h->out, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for output bam file " + o.bam);
+    return 0;
+}
+
+// next chunk of contig i: 1 = a chunk is packed, 0 = the contig is exhausted, < 0 error
+int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
+    if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    const std::string &chr = h->chr_names[(size_t)i];
+    if (h->cur != i) {
+        finish_contig(*h);
+        h->cur = i;
+        h->itr_done = false;
+        const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
+        h->itr = sam_itr_querys(h->idx, h->hdr, region.c_str());
+        if (!h->itr) h->itr_done = true;
+        h->cur_pos.clear();
+        h->cur_ps.clear();
+        for (const auto &kv : h->variants[chr]) { h->cur_pos.push_back(kv.first); h->cur_ps.push_back(kv.second.ps); }
+    }
+    h->chunk.clear();
+    lpsh::PackedContig &pc = h->chunk.pack;
+    pc.tagged_variants = true;
+    for (const auto &kv : h->variants[chr]) {
+        const PhasedVariant &v = kv.second;
+        pc.add_variant(kv.first, v.ref, v.alt);
+        pc.v_hp1_is_alt.push_back(v.hp1_is_alt);
+        pc.v_ps.push_back(v.ps);
+        pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
+    }
+    pc.ref = h->reference[chr];
+    while (!h->itr_done && h->chunk.records.size() < h->chunk_reads) {
+        bam1_t *b = bam_init1();
+        if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
+        pc.add_alignment(b);
+        h->chunk.records.push_back(b);
+    }
+    if (h->chunk.records.empty()) { finish_contig(*h); h->cur = i; h->itr_done = true; return 0; }
+    pc.finish();
+    pc.view(out);
+    return 1;
+}
+
+int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
+    if (!h || !r || h->cur != i || !h->out) return -1;
+    Chunk &ck = h->chunk;
+    const size_t n = ck.records.size();
+    if ((size_t)r->n_reads != n) return lpsh::fail("verdict count does not match the chunk");
+    const bool want_log = h->log.is_open();
+    if (want_log && !r->call_off)
+        for (size_t k = 0; k < n; k++)
+            if (r->category[k] == LPS_TAG_PROCESSED) return lpsh::fail("--log needs lps_tag_reads with want_calls");
+    const std::string &chr = h->chr_names[(size_t)i];
+    for (size_t k = 0; k < n; k++) {
+        bam1_t *b = ck.records[k];
+        const int cat = r->category[k];
+        h->st_alignment++;
+        if (cat != LPS_TAG_PROCESSED) {
+            h->st_untag++;
+            if (cat == LPS_TAG_LOW_MAPQ) h->st_low++;
+            else if (cat == LPS_TAG_UNMAPPED) h->st_unmapped++;
+            else if (cat == LPS_TAG_SECONDARY) h->st_secondary++;
+            else if (cat == LPS_TAG_SUPPLEMENTARY) h->st_supplementary++;
+            else if (cat == LPS_TAG_EMPTY_VARIANTS) h->st_empty++;
+            else h->st_other++;
+        } else {
+            // GermlineHaplotagChrProcessor::processRead (HaplotagProcess.cpp:318-355)
+            if (b->core.flag & 0x800) h->st_supplementary++;
+            int hp = r->hp[k], ps = r->ps[k], pq = r->pq[k];
+            const double h1 = r->h1[k], h2 = r->h2[k];
+            const double mx = h1 > h2 ? h1 : h2, mn = h1 > h2 ? h2 : h1;
+            if (mx / (mx + mn) < h->opt.percentage) h->st_similar++;
+            if (mx == 0) h->st_no_variant++;
+            if (want_log) {   // GermlineTagLog::writeTagReadLog (HaplotagProcess.cpp:210-237)
+                std::map<int, int> variants_hp, count_ps;
+                for (uint64_t c = r->call_off[k]; c < r->call_off[k + 1]; c++) {
+                    const lps_call &cl = r->calls[c];
+                    if (cl.allele >= 0) variants_hp[h->cur_pos[(size_t)cl.var]] = cl.allele;
+                    count_ps[h->cur_ps[(size_t)cl.var]]++;
+                }
+                h->log << bam_get_qname(b) << "\t" << chr << "\t" << b->core.pos << "\t" << (mx / (mx + mn)) << "\tH"
+                       << (hp == 0 ? std::string(".") : std::to_string(hp)) << "\t"
+                       << (hp == 0 ? std::string(".") : std::to_string(count_ps.begin()->first)) << "\t" << (int)(h1 + h2) << "\t" << (int)h1
+                       << "\t" << (int)h2 << "\t" << pq << "\t";
+                for (const auto &v : variants_hp) h->log << " " << v.first << "," << v.second;
+                h->log << "\t";
+                for (const auto &v : count_ps) h->log << " " << v.first << "," << v.second;
+                h->log << "\n";
+            }
+            drop_aux(b, "HP");
+            drop_aux(b, "PS");
+            drop_aux(b, "PQ");
+            if (hp != 0) {
+                h->st_hp[hp]++;
+                h->st_tag++;
+                bam_aux_append(b, "HP", 'i', sizeof(int), (uint8_t *)&hp);
+                bam_aux_append(b, "PS", 'i', sizeof(int), (uint8_t *)&ps);
+                bam_aux_append(b, "PQ", 'i', sizeof(int), (uint8_t *)&pq);
+            } else {
+                h->st_hp[0]++;
+                h->st_untag++;
+            }
+        }
+        if (sam_write1(h->out, h->hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+    }
+    ck.clear();
+    return 0;
+}
+
+int lpsh_tag_end(lpsh_tag *h) {
+    if (!h) return -1;
+    finish_contig(*h);
+    if (h->idx) hts_idx_destroy(h->idx);
+    if (h->hdr) bam_hdr_destroy(h->hdr);
+    if (h->in) sam_close(h->in);
+    int rc = 0;
+    if (h->out && sam_close(h->out) < 0) rc = lpsh::fail("closing the output bam failed");
+    h->idx = nullptr; h->hdr = nullptr; h->in = nullptr; h->out = nullptr;
+    if (h->pool.pool) hts_tpool_destroy(h->pool.pool);
+    h->pool.pool = NULL;
+    if (h->log.is_open()) h->log.close();
+    std::ostream &e = std::cerr;   // HaplotagProcess::printExecutionReport (HaplotagProcess.cpp:152-175)
+    e << "-------------------------------------------\n";
+    e << "total process time        : " << difftime(time(NULL), h->t_begin) << "s\n";
+    e << "total alignment           : " << h->st_alignment << "\ntotal supplementary       : " << h->st_supplementary << "\n";
+    e << "total secondary           : " << h->st_secondary << "\ntotal unmapped            : " << h->st_unmapped << "\n";
+    e << "total tagged alignments   : " << h->st_tag << "\n    L----total HP1        : " << h->st_hp[1] << "\n    L----total HP2        : " << h->st_hp[2] << "\n";
+    e << "    L----total HP1-1      : 0\n    L----total HP2-1      : 0\n    L----total HP3        : 0\n         L----only H3 SNP : 0\n";
+    e << "total untagged            : " << h->st_untag << "\n    L----lower mapping quality        : " << h->st_low << "\n";
+    e << "    L----no variant                   : " << h->st_empty << "\n    L----start pos > last variant pos : " << h->st_other << "\n";
+    e << "    L----judge to untag               : " << h->st_hp[0] << "\n         L----high similarity         : " << h->st_similar << "\n";
+    e << "         L----cross two block         : 0\n         L----no variant judge HP     : " << h->st_no_variant << "\n";
+    e << "-------------------------------------------\n";
+    return rc;
+}
+
+int lpsh_tag_run(lpsh_tag *h) {
+    if (!h) return -1;
+    if (lpsh_tag_begin(h) != 0) return -1;
+    lps_ctx *ctx = nullptr;
+    if (lps_ctx_create(0, &ctx) != 0) return lpsh::fail("no usable CUDA device (there is no CPU fallback)");
+    lps_tag_params tp;
+    lpsh_tag_params(h, &tp);
+    std::time_t t0 = time(NULL);
+    std::cerr << "tag read start ...\n";
+    int rc = 0;
+    for (int i = 0; i < (int)h->chr_names.size() && rc == 0; i++) {
+        const std::string &chr = h->chr_names[(size_t)i];
+        std::time_t c0 = time(NULL);
+        std::cerr << "chr: " << chr << " ... ";
+        const bool empty = h->variants.find(chr) == h->variants.end() || h->variants[chr].empty();
+        bool table_set = false;
+        lpsh_packed v;
+        for (int got; rc == 0 && (got = lpsh_tag_pack(h, i, &v)) != 0;) {
+            if (got < 0) { rc = -1; break; }
+            if (empty) {
+                // a contig without variants never reaches the tagger: the dispatch of processSingleChrom (HaplotagParsingBam.cpp:457-476)
+                // only looks at MAPQ and flags, so no device work exists for these records
+                const int n = v.batch.n_reads;
+                std::vector<uint8_t> cat((size_t)n);
+                std::vector<int8_t> hp((size_t)n, 0);
+                std::vector<int32_t> zero((size_t)n, 0);
+                for (int k = 0; k < n; k++) {
+                    const int flag = v.batch.flag[k];
+                    cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
+                                     : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
+                                     : LPS_TAG_EMPTY_VARIANTS;
+                }
+                lps_tag_result r;
+                memset(&r, 0, sizeof(r));
+                r.n_reads = n; r.category = cat.data(); r.hp = hp.data(); r.ps = zero.data(); r.pq = zero.data(); r.h1 = zero.data(); r.h2 = zero.data();
+                rc = lpsh_tag_emit(h, i, &r);
+                continue;
+            }
+            if (!table_set) {
+                rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
+                if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, 0);
+                table_set = true;
+            }
+            lps_tag_result r;
+            if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);
+            if (rc == 0) rc = lps_tag_reads(ctx, &tp, h->opt.log ? 1 : 0, &r);
+            if (rc != 0) { lpsh::fail(std::string("contig ") + chr + ": " + lps_last_error(ctx)); break; }
+            rc = lpsh_tag_emit(h, i, &r);
+        }
+        std::cerr << difftime(time(NULL), c0) << "s\n";
+    }
+    lps_ctx_destroy(ctx);
+    std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
+    const int rc_end = lpsh_tag_end(h);
+    return rc != 0 ? -1 : rc_end;
+}
+
+void lpsh_tag_close(lpsh_tag *h) {
+    if (!h) return;
+    if (h->in || h->out) lpsh_tag_end(h);
+    delete h;
+}
+
+int lpsh_tag_main(int argc, char **argv) {
+    lpsh_tag *job = nullptr;
+    const int rc = lpsh_tag_open(argc, argv, &job);
+    if (rc == 2) return 0;
+    if (rc != 0) { if (rc < 0) std::cerr << "haplotag: " << lpsh_last_error() << "\n"; return 1; }
+    const int run = lpsh_tag_run(job);
+    if (run != 0) std::cerr << "[ERROR] haplotag: " << lpsh_last_error() << "\n";
+    lpsh_tag_close(job);
+    return run != 0 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// host_common.h — pieces shared by the sub-commands of the C++ host: the SoA packer that turns htslib records into the
+// lps_read_batch / lps_variants of include/lps.h, error plumbing, small file helpers.
+#ifndef LPS_HOST_COMMON_H
+#define LPS_HOST_COMMON_H
+
+#include <htslib/faidx.h>
+#include <htslib/sam.h>
+#include <htslib/thread_pool.h>
+#include <htslib/vcf.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lps_host.h"
+
+namespace lpsh {
+
+// the output files carry the version of the tool whose format they follow (##longphaseVersion, @PG VN)
+static const char *const REFERENCE_VERSION = "1.0.0";
+
+int fail(const std::string &message);                     // remembers the message for lpsh_last_error, returns -1
+bool read_gz(const std::string &path, std::string &text); // whole file through zlib (plain files pass through)
+int device_count();                                       // CUDA devices liblps_b200.so can open a context on
+
+// One contig in the layout of include/lps.h.  Alignments are appended in file order; finish() derives the offsets'
+// companions that need the whole batch (name ranks).
+struct PackedContig {
+    // variant table
+    std::vector<int32_t> v_pos;
+    std::vector<uint8_t> v_ref0, v_alt0, v_hp1_is_alt, v_gt_kind;
+    std::vector<uint16_t> v_ref_len, v_alt_len;
+    std::vector<int32_t> v_ps;
+    bool tagged_variants = false;   // hp1_is_alt / ps / gt_kind are meaningful (tag family)
+    // reads
+    std::vector<int32_t> ref_start, l_qseq, name_rank;
+    std::vector<uint32_t> n_cigar, cigar;
+    std::vector<uint64_t> cigar_off, seq_off, qual_off, name_off;
+    std::vector<uint16_t> flag;
+    std::vector<uint8_t> mapq, seq4, qual;
+    std::string names;
+    std::string ref;
+
+    void add_variant(int pos, const std::string &ref_text, const std::string &alt_text) {
+        v_pos.push_back(pos);
+        v_ref0.push_back(ref_text.empty() ? 0 : (uint8_t)ref_text[0]);
+        v_alt0.push_back(alt_text.empty() ? 0 : (uint8_t)alt_text[0]);
+        v_ref_len.push_back((uint16_t)std::min<size_t>(ref_text.size(), 65535));
+        v_alt_len.push_back((uint16_t)std::min<size_t>(alt_text.size(), 65535));
+    }
+    void add_alignment(const bam1_t *b) {
+        const bam1_core_t &c = b->core;
+        ref_start.push_back((int32_t)c.pos);
+        l_qseq.push_back(c.l_qseq);
+        n_cigar.push_back(c.n_cigar);
+        flag.push_back(c.flag);
+        mapq.push_back(c.qual);
+        cigar_off.push_back(cigar.size());
+        const uint32_t *cg = bam_get_cigar(b);
+        cigar.insert(cigar.end(), cg, cg + c.n_cigar);
+        seq_off.push_back(seq4.size());
+        const uint8_t *s = bam_get_seq(b);
+        seq4.insert(seq4.end(), s, s + (c.l_qseq + 1) / 2);
+        qual_off.push_back(qual.size());
+        const uint8_t *q = bam_get_qual(b);
+        qual.insert(qual.end(), q, q + c.l_qseq);
+        name_off.push_back(names.size());
+        names.append(bam_get_qname(b));
+        names.push_back('\0');
+    }
+    int32_t n_reads() const { return (int32_t)ref_start.size(); }
+    // rank of every read name in std::string order; equal names share a rank (the reference folds edge weights in
+    // std::map<std::string, ...> order, PhasingGraph.cpp:697,848)
+    void finish() {
+        const size_t n = ref_start.size();
+        std::vector<uint32_t> order(n);
+        for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+        const char *base = names.data();
+        auto name = [&](uint32_t r) { return base + name_off[r]; };
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const int c = strcmp(name(a), name(b));   // strcmp compares as unsigned char, like char_traits<char>::compare
+            return c != 0 ? c < 0 : a < b;
+        });
+        name_rank.assign(n, 0);
+        int32_t rank = -1;
+        for (size_t k = 0; k < n; k++) {
+            if (k == 0 || strcmp(name(order[k - 1]), name(order[k])) != 0) rank++;
+            name_rank[order[k]] = rank;
+        }
+    }
+    void view(lpsh_packed *out) const {
+        memset(out, 0, sizeof(*out));
+        lps_variants &v = out->variants;
+        v.n = (int32_t)v_pos.size();
+        v.pos = v_pos.data(); v.ref0 = v_ref0.data(); v.alt0 = v_alt0.data();
+        v.ref_len = v_ref_len.data(); v.alt_len = v_alt_len.data();
+        if (tagged_variants) { v.hp1_is_alt = v_hp1_is_alt.data(); v.ps = v_ps.data(); v.gt_kind = v_gt_kind.data(); }
+        lps_read_batch &b = out->batch;
+        b.n_reads = n_reads();
+        b.ref_start = ref_start.data(); b.l_qseq = l_qseq.data(); b.n_cigar = n_cigar.data();
+        b.cigar_off = cigar_off.data(); b.seq_off = seq_off.data(); b.qual_off = qual_off.data();
+        b.flag = flag.data(); b.mapq = mapq.data(); b.name_rank = name_rank.data();
+        b.cigar = cigar.data(); b.cigar_len = cigar.size();
+        b.seq4 = seq4.data(); b.seq_bytes = seq4.size();
+        b.qual = qual.data(); b.qual_bytes = qual.size();
+        out->ref = ref.data(); out->ref_len = (int64_t)ref.size();
+        out->names = names.data(); out->name_off = name_off.data();
+    }
+};
+
+}  // namespace lpsh
+#endif

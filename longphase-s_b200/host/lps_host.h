@@ -1,0 +1,101 @@
+/*
+ * lps_host.h — the C++ host that sits ABOVE the C ABI of include/lps.h: the reference's own command-line and file surface
+ * (`longphase-s phase | haplotag`) kept as it is, with the per-contig hot path handed to liblps_b200.so.
+ *
+ * The host keeps htslib for BAM / VCF / FASTA decoding, exactly as BASELINE.json:north_star asks: it packs the decoded
+ * alignments into the SoA batch of include/lps.h, calls the kernels through the C ABI, and writes the reference's output
+ * files (phased VCF, tagged BAM, --log table) byte for byte.  htslib is compiled from the sources vendored with the
+ * reference (longphase-s_b200/host/Makefile), never copied into this repository.
+ *
+ * The entry points below are the stages of that host, exported with C linkage so that the CPU test-suite can drive every
+ * stage that does not need a GPU (option parsing, VCF / FASTA / BAM loading and packing, result writers) and compare the
+ * written files with those of the unmodified reference binary.  Only lpsh_*_run touches the GPU.
+ *
+ * Reference seams replaced (file:line relative to the reference tree):
+ *   PhasingOptions / PhasingMain            src/phase/Phasing.cpp:118-372
+ *   PhasingProcess::PhasingProcess          src/phase/PhasingProcess.cpp:5-208
+ *   SnpParser::SnpParser / writeResult      src/phase/ParsingBam.cpp:219-359, 444-635
+ *   FastaParser::FastaParser                src/phase/ParsingBam.cpp:17-59
+ *   BamParser::direct_detect_alleles        src/phase/ParsingBam.cpp:1243-1301  (the htslib loop; get_snp is on the device)
+ *   HaplotagOptions / HaplotagMain          src/haplotag/Haplotag.cpp:74-189
+ *   HaplotagProcess / HaplotagBamParser     src/haplotag/HaplotagProcess.cpp:20-262, src/haplotag/HaplotagParsingBam.cpp:176-492
+ *   VcfParser (germline)                    src/haplotag/HaplotagVcfParser.cpp:10-470
+ */
+#ifndef LPS_HOST_H
+#define LPS_HOST_H
+
+#include <stdint.h>
+#include "lps.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- phase ------------------------------------------------------------------------------------------------------ */
+typedef struct lpsh_phase lpsh_phase;
+
+/* one contig as the device sees it; every pointer is owned by the job and valid until lpsh_phase_release / close    */
+typedef struct {
+    lps_variants variants;      /* het variants of the contig in ascending position (SnpParser::chrVariant)          */
+    lps_read_batch batch;       /* all alignments of the region chr:1-lastSNP of every -b file, in file order        */
+    const char *ref;            /* FastaParser::chrString[chr] (0 .. lastSNP+5)                                       */
+    int64_t ref_len;
+    const char *names;          /* read names, NUL terminated, concatenated                                          */
+    const uint64_t *name_off;   /* [n_reads] offset of read r's name in names                                        */
+} lpsh_packed;
+
+/* argv[0] is the sub-command word ("phase"), as PhasingMain receives it (src/main.cpp:41).  Parses the options with the
+ * reference's names / defaults / checks, prints its banner on stderr, loads the VCF and the FASTA.  Returns 0; 1 when the
+ * options are invalid (usage printed, the reference exits with EXIT_FAILURE); 2 for --help.                          */
+int lpsh_phase_open(int argc, char **argv, lpsh_phase **out);
+int lpsh_phase_n_contigs(const lpsh_phase *h);                       /* SnpParser::getChrVec()                      */
+const char *lpsh_phase_contig_name(const lpsh_phase *h, int i);
+int lpsh_phase_last_variant(const lpsh_phase *h, int i);             /* SnpParser::getLastSNP, -1 = none            */
+int lpsh_phase_params(const lpsh_phase *h, lps_phase_params *out);
+/* decodes the contig's alignments with htslib and packs them; 0, or a negative value when a BAM / index cannot be opened */
+int lpsh_phase_pack(lpsh_phase *h, int i, lpsh_packed *out);
+void lpsh_phase_release(lpsh_phase *h, int i);
+/* VairiantGraph::exportResult for contig i from the arrays of lps_phase_result (PhasingGraph.cpp:1049-1077)           */
+int lpsh_phase_set_result(lpsh_phase *h, int i, int32_t n_variants, const int32_t *ps, const int8_t *hap_ref);
+/* SnpParser::writeResult: <prefix>.vcf (ParsingBam.cpp:444-635)                                                      */
+int lpsh_phase_write_result(lpsh_phase *h);
+/* the contig loop of PhasingProcess (PhasingProcess.cpp:113-173) on the GPU(s): pack, lps_phase_contig, set_result for
+ * every contig with -t host threads, one lps_ctx each, devices taken round-robin.  Prints the reference's progress on stderr. */
+int lpsh_phase_run(lpsh_phase *h);
+void lpsh_phase_close(lpsh_phase *h);
+/* everything: what `longphase-s phase ...` does.  Returns the process exit code.                                       */
+int lpsh_phase_main(int argc, char **argv);
+
+/* ---- haplotag --------------------------------------------------------------------------------------------------- */
+typedef struct lpsh_tag lpsh_tag;
+
+int lpsh_tag_open(int argc, char **argv, lpsh_tag **out);            /* argv[0] = "haplotag"                          */
+int lpsh_tag_n_contigs(const lpsh_tag *h);
+const char *lpsh_tag_contig_name(const lpsh_tag *h, int i);
+int lpsh_tag_params(const lpsh_tag *h, lps_tag_params *out);
+/* opens input and output, writes the header (HaplotagParsingBam.cpp:20-66); must precede the first lpsh_tag_pack       */
+int lpsh_tag_begin(lpsh_tag *h);
+/* reads the NEXT chunk of contig i's alignments (region aware; LPS_TAG_CHUNK records, default 65536) and packs it with the
+ * contig's phased variants; the records stay buffered for lpsh_tag_emit.  1 = a chunk is ready, 0 = contig exhausted, < 0 error */
+int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out);
+/* applies HP / PS / PQ to the buffered records of the chunk and writes them in their original order
+ * (HaplotagProcess.cpp:318-438), adds the chunk's share of the statistics and of the --log table                         */
+int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r);
+int lpsh_tag_end(lpsh_tag *h);                                         /* closes the files, prints the report            */
+int lpsh_tag_run(lpsh_tag *h);                                         /* begin, then pack / lps_tag_reads / emit per contig, end */
+void lpsh_tag_close(lpsh_tag *h);
+int lpsh_tag_main(int argc, char **argv);
+
+/* ---- tooling: the generator's SoA batches written as BAM + BAI with htslib (bench and tests; no samtools in the image) --- */
+typedef struct lpsh_bamw lpsh_bamw;
+lpsh_bamw *lpsh_bamw_open(const char *path, int n_contigs, const char **names, const int64_t *lens, int threads);
+/* appends the batch (coordinate order) as records of contig `tid`; names = fixed-stride NUL-terminated read names      */
+int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char *names, int name_stride);
+int lpsh_bamw_close(lpsh_bamw *w);                                     /* closes and builds <path>.bai                   */
+
+const char *lpsh_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,259 @@
+"""The C++ host above the C ABI (longphase-s_b200/host): `phase` and `haplotag` with the reference's command line and files.
+
+CPU tests drive every host stage that needs no GPU — options, VCF / FASTA / BAM loading and SoA packing with htslib, the
+phased-VCF writer, the tagged-BAM writer and the --log table — with the ORACLE standing in for the device between pack and
+write, and compare the written files with those of the UNMODIFIED reference binary (oracle/_ref/longphase-s) run on the same
+inputs: the phased VCF must be identical except for its ##commandline line, the tagged BAM's uncompressed byte stream and
+the .out table must be identical.  The -m gpu tests run the real binary (`longphase-s-b200`), device and all, the same way."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from . import host_cli as hc
+
+po = pytest.importorskip("oracle.pyoracle")
+ffi = importlib.import_module("longphase_s_b200._ffi")
+
+needs_host = pytest.mark.skipif(not os.path.exists(hc.HOST_LIB), reason="liblps_host.so not built (needs the reference's htslib sources)")
+needs_ref = pytest.mark.skipif(not (os.path.exists(hc.REF_BIN) and os.path.exists(hc.MKBAM)), reason="reference binary not built")
+
+_data = {}
+
+
+def dataset(tmp_path_factory, kind):
+    if kind not in _data:
+        d = str(tmp_path_factory.mktemp("hostcli_" + kind))
+        a = hc.synth.Contig(seed=201, contig_len=260_000, indel_frac=0.12, depth=18.0, mean_len=9_000.0)
+        b = hc.synth.Contig(seed=202, contig_len=180_000, indel_frac=0.05, depth=14.0, mean_len=7_000.0, supp_frac=0.2)
+        e = hc.synth.Contig(seed=203, contig_len=30_000, depth=4.0, mean_len=3_000.0)
+        files = hc.write_dataset(d, [("chrA", a, True), ("chrEmpty", e, False), ("chrB", b, True)],
+                                 with_ps=(kind == "ps_gz"), gz=(kind == "ps_gz"))
+        files["dir"] = d
+        _data[kind] = files
+    return _data[kind]
+
+
+def run_in(cwd, cmd):
+    os.makedirs(cwd, exist_ok=True)
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, (cmd, p.stdout[-2000:], p.stderr[-2000:])
+    return p
+
+
+def phase_args(files, extra):
+    return ["phase", "-s", files["vcf"], "-b", files["bam"], "-r", files["fasta"], "-o", "out", "-t", "2"] + extra
+
+
+def oracle_phase_through_host(files, extra, cwd):
+    """lpsh_phase_open -> per contig: lpsh_phase_pack -> ORACLE -> lpsh_phase_set_result -> lpsh_phase_write_result."""
+    lib = hc.host_lib()
+    os.makedirs(cwd, exist_ok=True)
+    old = os.getcwd()
+    os.chdir(cwd)
+    try:
+        h = C.c_void_p()
+        n, av = hc.argv(phase_args(files, extra))
+        assert lib.lpsh_phase_open(n, av, C.byref(h)) == 0, lib.lpsh_last_error()
+        p = ffi.LpsPhaseParams()
+        assert lib.lpsh_phase_params(h, C.byref(p)) == 0
+        seen = {}
+        for i in range(lib.lpsh_phase_n_contigs(h)):
+            name = lib.lpsh_phase_contig_name(h, i).decode()
+            if lib.lpsh_phase_last_variant(h, i) == -1:
+                continue
+            pk = hc.LpshPacked()
+            assert lib.lpsh_phase_pack(h, i, C.byref(pk)) == 0, lib.lpsh_last_error()
+            c = hc.packed_contig(pk)
+            lib.lpsh_phase_release(h, i)
+            seen[name] = c
+            if c.n_reads == 0:
+                continue
+            orc = po.OraclePhase(c, p)
+            assert orc.rc == 0
+            ps, hap = np.ascontiguousarray(orc.ps, np.int32), np.ascontiguousarray(orc.hap_ref, np.int8)
+            assert lib.lpsh_phase_set_result(h, i, c.n_var, ffi.ptr(ps, ffi.i32p), ffi.ptr(hap, ffi.i8p)) == 0
+        assert lib.lpsh_phase_write_result(h) == 0
+        lib.lpsh_phase_close(h)
+        return seen
+    finally:
+        os.chdir(old)
+
+
+PHASE_VARIANTS = [("plain", ["--ont"]), ("plain", ["--ont", "--indels"]), ("plain", ["--pb", "--indels", "--indelQuality", "30", "-q", "20", "-a", "20"]),
+                  ("ps_gz", ["--ont", "--indels"])]
+
+
+@needs_host
+@needs_ref
+@pytest.mark.parametrize("kind,extra", PHASE_VARIANTS)
+def test_phase_host_files_match_reference(tmp_path_factory, tmp_path, kind, extra):
+    files = dataset(tmp_path_factory, kind)
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + phase_args(files, extra))
+    seen = oracle_phase_through_host(files, extra, str(tmp_path / "own"))
+    assert set(seen) == {"chrA", "chrB"} and all(c.n_reads > 100 for c in seen.values())
+    ref = open(tmp_path / "ref" / "out.vcf").read()
+    own = open(tmp_path / "own" / "out.vcf").read()
+    assert "|" in own and ":PS" in own
+    assert hc.strip_commandline(own) == hc.strip_commandline(ref)
+    n_phased = sum(1 for ln in own.split("\n") if ln and ln[0] != "#" and "|" in ln.split("\t")[9])
+    assert n_phased > 100
+    if "--indelQuality" in extra:
+        assert open(tmp_path / "own" / "out_removed_indels.log").read() == open(tmp_path / "ref" / "out_removed_indels.log").read()
+        assert "INDEL_QUAL_FILTERED" in own
+
+
+@needs_host
+def test_pack_round_trips_the_synthetic_batch(tmp_path_factory, tmp_path):
+    """What htslib decodes and the host packs is the batch the generator made (region filter chr:1-lastSNP applied)."""
+    files = dataset(tmp_path_factory, "plain")
+    seen = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "own"))
+    src = hc.synth.Contig(seed=201, contig_len=260_000, indel_frac=0.12, depth=18.0, mean_len=9_000.0)
+    c = seen["chrA"]
+    last = int(c.var_pos[-1])
+    keep = np.nonzero(src.ref_start < last)[0]          # 1-based region chr:1-last = 0-based [0, last)
+    assert c.n_reads == len(keep)
+    assert np.array_equal(c.ref_start, src.ref_start[keep]) and np.array_equal(c.flag, src.flag[keep]) and np.array_equal(c.mapq, src.mapq[keep])
+    assert np.array_equal(c.n_cigar, src.n_cigar[keep]) and np.array_equal(c.l_qseq, src.l_qseq[keep])
+    for k in (0, len(keep) // 2, len(keep) - 1):
+        r = int(keep[k])
+        a, n = int(src.cigar_off[r]), int(src.n_cigar[r])
+        assert np.array_equal(c.cigar[int(c.cigar_off[k]):int(c.cigar_off[k]) + n], src.cigar[a:a + n])
+        lq = int(src.l_qseq[r])
+        assert np.array_equal(c.qual[int(c.qual_off[k]):int(c.qual_off[k]) + lq], np.minimum(src.qual[int(src.qual_off[r]):int(src.qual_off[r]) + lq], 93))
+        nb = lq // 2
+        assert np.array_equal(c.seq4[int(c.seq_off[k]):int(c.seq_off[k]) + nb], src.seq4[int(src.seq_off[r]):int(src.seq_off[r]) + nb])
+        assert c.read_names[k] == src.name(r)
+    # name ranks: the order of std::string names, equal names share a rank
+    order = sorted(range(c.n_reads), key=lambda k: c.read_names[k].encode())
+    for x, y in zip(order, order[1:]):
+        same = c.read_names[x] == c.read_names[y]
+        assert (c.name_rank[x] == c.name_rank[y]) if same else (c.name_rank[x] < c.name_rank[y])
+    # the reference string ends 5 bases after the last variant (FastaParser, ParsingBam.cpp:46)
+    assert c.ref == src.ref[:last + 5 + 1] or c.ref == src.ref[:last + 5]
+
+
+def tag_args(files, vcf, extra):
+    return ["haplotag", "-s", vcf, "-b", files["bam"], "-r", files["fasta"], "-o", "tagged", "-t", "2"] + extra
+
+
+def oracle_tag_through_host(files, vcf, extra, cwd, chunk=None):
+    lib = hc.host_lib()
+    os.makedirs(cwd, exist_ok=True)
+    old = os.getcwd()
+    os.chdir(cwd)
+    if chunk:
+        os.environ["LPS_TAG_CHUNK"] = str(chunk)
+    try:
+        h = C.c_void_p()
+        n, av = hc.argv(tag_args(files, vcf, extra))
+        assert lib.lpsh_tag_open(n, av, C.byref(h)) == 0, lib.lpsh_last_error()
+        tp = ffi.LpsTagParams()
+        assert lib.lpsh_tag_params(h, C.byref(tp)) == 0
+        assert lib.lpsh_tag_begin(h) == 0, lib.lpsh_last_error()
+        chunks = 0
+        for i in range(lib.lpsh_tag_n_contigs(h)):
+            while True:
+                pk = hc.LpshPacked()
+                got = lib.lpsh_tag_pack(h, i, C.byref(pk))
+                assert got >= 0, lib.lpsh_last_error()
+                if got == 0:
+                    break
+                chunks += 1
+                c = hc.packed_contig(pk)
+                r = ffi.LpsTagResult()
+                r.n_reads = c.n_reads
+                if c.n_var == 0:                      # the host's own dispatch for a contig without variants
+                    cat = np.where(c.mapq < tp.mapping_quality, 1, np.where(c.flag & 4, 2, np.where(c.flag & 0x100, 3, np.where(
+                        (c.flag & 0x800 != 0) & (tp.tag_supplementary == 0), 4, 5)))).astype(np.uint8)
+                    keep = [cat, np.zeros(c.n_reads, np.int8), np.zeros(c.n_reads, np.int32)]
+                    r.category, r.hp = ffi.ptr(keep[0], ffi.u8p), ffi.ptr(keep[1], ffi.i8p)
+                    r.ps = r.pq = r.h1 = r.h2 = ffi.ptr(keep[2], ffi.i32p)
+                else:
+                    orc = po.OracleTag(c, tp)
+                    assert orc.rc == 0
+                    keep = [np.ascontiguousarray(x) for x in (orc.category, orc.hp, orc.ps, orc.pq, orc.h1, orc.h2, orc.call_off, orc.calls)]
+                    r.category, r.hp, r.ps, r.pq = ffi.ptr(keep[0], ffi.u8p), ffi.ptr(keep[1], ffi.i8p), ffi.ptr(keep[2], ffi.i32p), ffi.ptr(keep[3], ffi.i32p)
+                    r.h1, r.h2, r.call_off = ffi.ptr(keep[4], ffi.i32p), ffi.ptr(keep[5], ffi.i32p), ffi.ptr(keep[6], ffi.u64p)
+                    r.n_calls = len(keep[7])
+                    r.calls = keep[7].ctypes.data_as(C.POINTER(ffi.LpsCall))
+                assert lib.lpsh_tag_emit(h, i, C.byref(r)) == 0, lib.lpsh_last_error()
+        assert lib.lpsh_tag_end(h) == 0
+        lib.lpsh_tag_close(h)
+        return chunks
+    finally:
+        os.environ.pop("LPS_TAG_CHUNK", None)
+        os.chdir(old)
+
+
+TAG_VARIANTS = [[], ["--log"], ["--log", "--tagSupplementary", "-q", "20", "-p", "0.75"], ["--log", "--region", "chrB:20000-120000"]]
+
+
+@needs_host
+@needs_ref
+@pytest.mark.parametrize("extra", TAG_VARIANTS)
+def test_haplotag_host_files_match_reference(tmp_path_factory, tmp_path, extra):
+    files = dataset(tmp_path_factory, "plain")
+    key = "phased_vcf"
+    if key not in files:                                  # the phased VCF both programs tag with: the reference's own phase output
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        files[key] = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, files[key], extra))
+    chunks = oracle_tag_through_host(files, files[key], extra, str(tmp_path / "own"), chunk=100 if "--region" in extra else 700)
+    assert chunks >= 3
+    ref, own = hc.bam_payload(str(tmp_path / "ref" / "tagged.bam")), hc.bam_payload(str(tmp_path / "own" / "tagged.bam"))
+    assert len(own) > 100_000 and b"HP" in own
+    assert own == ref, "tagged BAM differs from the reference's (uncompressed byte stream)"
+    if "--log" in extra:
+        assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
+
+
+@needs_host
+def test_host_rejects_bad_options(tmp_path, capfd):
+    lib = hc.host_lib()
+    h = C.c_void_p()
+    n, av = hc.argv(["phase", "-s", "/nonexistent.vcf", "-b", "x.bam", "-r", "/nonexistent.fa"])
+    assert lib.lpsh_phase_open(n, av, C.byref(h)) == 1 and not h.value
+    err = capfd.readouterr().err
+    assert "--ont or --pb" in err and "not exist" in err
+    n, av = hc.argv(["haplotag", "-b", "x.bam", "-p", "1.5"])
+    assert lib.lpsh_tag_open(n, av, C.byref(h)) == 1 and not h.value
+    assert "missing SNP file" in capfd.readouterr().err
+
+
+@needs_host
+def test_host_binary_needs_a_gpu(tmp_path_factory, tmp_path):
+    """No CPU fallback: without a CUDA device the binary stops with an error instead of computing anything on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    files = dataset(tmp_path_factory, "plain")
+    p = subprocess.run([hc.HOST_BIN] + phase_args(files, ["--ont"]), cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 1 and "no usable CUDA device" in p.stderr and not os.path.exists(tmp_path / "out.vcf")
+
+
+# ---- the real thing: the binary, device and all, against the reference binary ---------------------------------------------
+@pytest.mark.gpu
+@needs_host
+@needs_ref
+def test_gpu_cli_phase_and_haplotag_match_reference(tmp_path_factory, tmp_path):
+    files = dataset(tmp_path_factory, "plain")
+    for k, extra in enumerate([["--ont", "--indels"], ["--pb"]]):
+        run_in(str(tmp_path / f"ref{k}"), [hc.REF_BIN] + phase_args(files, extra))
+        run_in(str(tmp_path / f"own{k}"), [hc.HOST_BIN] + phase_args(files, extra))
+        ref, own = open(tmp_path / f"ref{k}" / "out.vcf").read(), open(tmp_path / f"own{k}" / "out.vcf").read()
+        assert hc.strip_commandline(own) == hc.strip_commandline(ref), extra
+    phased = str(tmp_path / "own0" / "out.vcf")
+    for k, extra in enumerate([["--log"], ["--log", "--tagSupplementary", "-q", "20", "-p", "0.75"]]):
+        run_in(str(tmp_path / f"tref{k}"), [hc.REF_BIN] + tag_args(files, phased, extra))
+        env_chunk = dict(os.environ, LPS_TAG_CHUNK="900") if k else None
+        os.makedirs(tmp_path / f"town{k}", exist_ok=True)
+        p = subprocess.run([hc.HOST_BIN] + tag_args(files, phased, extra), cwd=str(tmp_path / f"town{k}"), env=env_chunk,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert hc.bam_payload(str(tmp_path / f"town{k}" / "tagged.bam")) == hc.bam_payload(str(tmp_path / f"tref{k}" / "tagged.bam")), extra
+        assert open(tmp_path / f"town{k}" / "tagged.out").read() == open(tmp_path / f"tref{k}" / "tagged.out").read(), extra

@@ -1,0 +1,68 @@
+"""File-level end-to-end run: the reference binary (oracle/_ref/longphase-s, CPU, -t all cores) and this repository's binary
+(longphase-s_b200/longphase-s-b200, GPU hot path behind the C ABI) on the SAME synthetic BAM / VCF / FASTA, `phase` then `haplotag`.
+Checks that the phased VCF (minus ##commandline), the tagged BAM's uncompressed bytes and the --log table are identical, and
+prints one JSON object with the wall times.  Used on the GPU box:  python tools/cli_e2e.py --contigs 2 --mb 16 > gpurun_out/cli_e2e.json
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import host_cli as hc  # noqa: E402
+
+
+def timed(cmd, cwd, env=None):
+    os.makedirs(cwd, exist_ok=True)
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError(f"{cmd} failed: {p.stderr[-1500:]}")
+    return dt, p.stderr
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--contigs", type=int, default=2)
+    ap.add_argument("--mb", type=float, default=16.0)
+    ap.add_argument("--depth", type=float, default=30.0)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
+    ap.add_argument("--keep", default="")
+    a = ap.parse_args()
+    d = a.keep or tempfile.mkdtemp(prefix="cli_e2e_")
+    t0 = time.perf_counter()
+    contigs = [("chr%d" % (k + 1), hc.synth.Contig(seed=900 + k, contig_len=int(a.mb * 1e6), indel_frac=0.1, depth=a.depth), True)
+               for k in range(a.contigs)]
+    files = hc.write_dataset(d, contigs, fast_bam=True)
+    n_reads = sum(c.n_reads for _, c, _ in contigs)
+    out = {"config": {"contigs": a.contigs, "contig_mb": a.mb, "depth": a.depth, "reads": n_reads, "variants": sum(c.n_var for _, c, _ in contigs),
+                      "bam_bytes": os.path.getsize(files["bam"]), "threads": a.threads, "make_dataset_s": round(time.perf_counter() - t0, 2)}}
+    del contigs
+    t = str(a.threads)
+    phase = ["phase", "-s", files["vcf"], "-b", files["bam"], "-r", files["fasta"], "-o", "out", "-t", t, "--ont", "--indels"]
+    ref_s, _ = timed([hc.REF_BIN] + phase, os.path.join(d, "ref"))
+    own_s, own_err = timed([hc.HOST_BIN] + phase, os.path.join(d, "own"))
+    own2_s, _ = timed([hc.HOST_BIN] + phase, os.path.join(d, "own"))       # second run: page cache and CUDA context creation warm
+    same = hc.strip_commandline(open(os.path.join(d, "ref", "out.vcf")).read()) == hc.strip_commandline(open(os.path.join(d, "own", "out.vcf")).read())
+    out["phase"] = {"reference_s": round(ref_s, 3), "own_s": round(own_s, 3), "own_second_run_s": round(own2_s, 3), "identical_vcf": same,
+                    "reads_per_s_reference": n_reads / ref_s, "reads_per_s_own": n_reads / min(own_s, own2_s)}
+    vcf = os.path.join(d, "ref", "out.vcf")
+    tag = ["haplotag", "-s", vcf, "-b", files["bam"], "-r", files["fasta"], "-o", "tagged", "-t", t, "--log"]
+    ref_s, _ = timed([hc.REF_BIN] + tag, os.path.join(d, "ref"))
+    own_s, _ = timed([hc.HOST_BIN] + tag, os.path.join(d, "own"))
+    same_bam = hc.bam_payload(os.path.join(d, "ref", "tagged.bam")) == hc.bam_payload(os.path.join(d, "own", "tagged.bam"))
+    same_log = open(os.path.join(d, "ref", "tagged.out")).read() == open(os.path.join(d, "own", "tagged.out")).read()
+    out["haplotag"] = {"reference_s": round(ref_s, 3), "own_s": round(own_s, 3), "identical_bam": same_bam, "identical_log": same_log,
+                       "reads_per_s_reference": n_reads / ref_s, "reads_per_s_own": n_reads / own_s}
+    out["own_phase_stderr_tail"] = own_err[-400:]
+    print(json.dumps(out))
+    return 0 if (same and same_bam and same_log) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
