@@ -408,6 +408,7 @@ typedef struct {
     int32_t n_after_lcvf, n_used;
     int32_t filtered_normal_imbalance_zero, filtered_tumor_imbalance_zero, filtered_normal_imbalance_high, filtered_normal_read_count,
             filtered_pct_germline_hp, filtered_valley, filtered_outliers;              /* FilterCounts of the _purity.out log */
+    int32_t n_outliers_left;                   /* BoxPlotValue::outliers of the final statistic (values outside the new whiskers) */
 } lps_purity_result;
 int lps_estimate_purity(const lps_purity_input *in, lps_purity_result *out);
 

@@ -168,7 +168,7 @@ class LpsPurityResult(C.Structure):
                 ("n_after_lcvf", C.c_int32), ("n_used", C.c_int32), ("filtered_normal_imbalance_zero", C.c_int32),
                 ("filtered_tumor_imbalance_zero", C.c_int32), ("filtered_normal_imbalance_high", C.c_int32),
                 ("filtered_normal_read_count", C.c_int32), ("filtered_pct_germline_hp", C.c_int32), ("filtered_valley", C.c_int32),
-                ("filtered_outliers", C.c_int32)]
+                ("filtered_outliers", C.c_int32), ("n_outliers_left", C.c_int32)]
 
 
 class LpsStats(C.Structure):

@@ -241,6 +241,7 @@ extern "C" int lps_estimate_purity(const lps_purity_input *in, lps_purity_result
         b = box_plot(feat);
         out->median = b.median; out->q1 = b.q1; out->q3 = b.q3; out->iqr = b.iqr; out->lower_whisker = b.lo; out->upper_whisker = b.hi;
         out->n_used = (int32_t)feat.size();
+        for (const Feature &f : feat) out->n_outliers_left += (f.ratio < b.lo || f.ratio > b.hi);   // statisticPurityData :330-335
         if (in->used) for (const Feature &f : feat) in->used[f.idx] = 1;
         const double m = b.median, q = b.iqr;
         double purity = -3.3454 * m + 14.7747 * q + 4.0344 * m * m + -13.7777 * m * q + -5.2434 * q * q + 0.3058;

@@ -61,43 +61,13 @@ struct TagOptions {
     std::string snp_file, sv_file, mod_file, bam, fasta, prefix = "result", region, command = "longphase-s ";
 };
 
-template <class T>
-void take(const char *text, T &dst) {
-    std::istringstream in(text ? text : "");
-    in >> dst;
-}
-
-bool required_file(const std::string &path, const char *what) {
-    if (path.empty()) { std::cerr << "[ERROR] haplotag: missing " << what << ".\n"; return false; }
-    if (!std::ifstream(path.c_str()).is_open()) { std::cerr << "[ERROR] haplotag: " << what << ": " << path << " not exist.\n\n"; return false; }
-    return true;
-}
-
-// one phased heterozygous record of the NORMAL sample (VarData, HaplotagType.h:110-143)
-struct PhasedVariant {
-    std::string ref, alt;
-    int ps = -1;
-    bool hp1_is_alt = false;   // GT 1|0
-    bool oriented = false;     // GT was 0|1 or 1|0 (otherwise HP1 / HP2 stay empty in the reference)
-};
-
-struct Chunk {
-    lpsh::PackedContig pack;
-    std::vector<bam1_t *> records;
-    void clear() {
-        for (bam1_t *b : records) bam_destroy1(b);
-        records.clear();
-        pack = lpsh::PackedContig();
-    }
-};
-
 }  // namespace
 
 struct lpsh_tag {
     TagOptions opt;
     std::vector<std::string> chr_names;               // VCF_Info::chrVec (##contig order), narrowed by --region
     std::map<std::string, int> chr_length;
-    std::map<std::string, std::map<int, PhasedVariant>> variants;
+    std::map<std::string, std::map<int, lpsh::SampleRecord>> variants;   // phased heterozygous records of the NORMAL sample
     std::map<std::string, std::string> reference;
     // files
     samFile *in = nullptr, *out = nullptr;
@@ -109,7 +79,7 @@ struct lpsh_tag {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
-    Chunk chunk;
+    lpsh::Chunk chunk;
     std::vector<int32_t> cur_pos, cur_ps;             // variant table of the contig in flight
     size_t chunk_reads = 65536;
     // ReadStatistics (HaplotagProcess.h:21-45)
@@ -125,27 +95,27 @@ int parse_tag_options(int argc, char **argv, TagOptions &o) {   // ArgumentManag
     bool bad = false;
     for (int c; (c = getopt_long(argc, argv, "s:b:o:t:q:p:r:", TAG_LONG, NULL)) != -1;) {
         switch (c) {
-            case 't': take(optarg, o.threads); break;
-            case 'o': take(optarg, o.prefix); break;
-            case 'q': take(optarg, o.quality); break;
-            case 'p': take(optarg, o.percentage); break;
+            case 't': lpsh::take(optarg, o.threads); break;
+            case 'o': lpsh::take(optarg, o.prefix); break;
+            case 'q': lpsh::take(optarg, o.quality); break;
+            case 'p': lpsh::take(optarg, o.percentage); break;
             case T_SUP: o.tag_supplementary = true; break;
-            case T_REGION: take(optarg, o.region); break;
+            case T_REGION: lpsh::take(optarg, o.region); break;
             case T_CRAM: o.cram = true; break;
             case T_LOG: o.log = true; break;
-            case 's': take(optarg, o.snp_file); break;
-            case 'b': take(optarg, o.bam); break;
-            case 'r': take(optarg, o.fasta); break;
-            case T_SV: take(optarg, o.sv_file); break;
-            case T_MOD: take(optarg, o.mod_file); break;
+            case 's': lpsh::take(optarg, o.snp_file); break;
+            case 'b': lpsh::take(optarg, o.bam); break;
+            case 'r': lpsh::take(optarg, o.fasta); break;
+            case T_SV: lpsh::take(optarg, o.sv_file); break;
+            case T_MOD: lpsh::take(optarg, o.mod_file); break;
             case T_HELP: std::cout << TAG_USAGE << std::endl; return 2;
             default: bad = true;
         }
     }
     for (int i = 0; i < argc; i++) { o.command += argv[i]; o.command += " "; }
-    bad |= !required_file(o.snp_file, "SNP file");
-    bad |= !required_file(o.bam, "BAM file");
-    bad |= !required_file(o.fasta, "reference file");
+    bad |= !lpsh::required_file("haplotag", o.snp_file, "SNP file");
+    bad |= !lpsh::required_file("haplotag", o.bam, "BAM file");
+    bad |= !lpsh::required_file("haplotag", o.fasta, "reference file");
     if (o.threads < 1) { std::cerr << "[ERROR] haplotag: invalid threads. value: " << o.threads << "\nplease check -t, --threads=Num\n"; bad = true; }
     if (o.percentage > 1 || o.percentage < 0) {
         std::cerr << "[ERROR] haplotag: invalid percentage threshold. value: " << o.percentage
@@ -170,98 +140,6 @@ void tag_banner(const TagOptions &o) {   // HaplotagProcess::printParamsMessage
     e << "tag region:                    " << (!o.region.empty() ? o.region : "all") << "\n";
     e << "filter mapping quality below:  " << o.quality << "\npercentage threshold:          " << o.percentage << "\n";
     e << "tag supplementary:             " << (o.tag_supplementary ? "true" : "false") << "\n-------------------------------------------\n";
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// phased VCF of the NORMAL sample (VcfParser::parserProcess, HaplotagVcfParser.cpp:206-345): a text parser, as in the reference
-int subfield_of(const std::string &format, const char *key) {
-    const size_t at = format.find(key);
-    if (at == std::string::npos) return 0;
-    return (int)std::count(format.begin(), format.begin() + at, ':');
-}
-size_t subfield_start(const std::string &sample, int k) {
-    size_t i = 0;
-    for (int seen = 0; i < sample.size() && seen < k; i++) seen += sample[i] == ':';
-    return i;
-}
-char peek(const std::string &s, size_t i) { return i < s.size() ? s[i] : '\0'; }
-
-struct VcfLoadState {
-    bool integer_ps = false;
-    std::map<std::string, int> ps_index;
-};
-
-void load_tag_line(lpsh_tag &job, const std::string &line, VcfLoadState &st) {
-    if (line.compare(0, 2, "##") == 0) {
-        if (line.find("contig=") != std::string::npos) {
-            const int id_start = (int)line.find("ID=") + 3, id_end = (int)line.find(",length=");
-            const int len_start = id_end + 8, len_end = (int)line.find(">");
-            const std::string chr = line.substr((size_t)id_start, (size_t)(id_end - id_start));
-            job.chr_names.push_back(chr);
-            job.chr_length[chr] = std::stoi(line.substr((size_t)len_start, (size_t)(len_end - len_start)));
-        }
-        if (line.compare(0, 16, "##FORMAT=<ID=PS,") == 0) {
-            if (line.find("Type=Integer") != std::string::npos) st.integer_ps = true;
-            else if (line.find("Type=String") != std::string::npos) { st.integer_ps = false; std::cerr << "PS type is String. Auto index to integer ... "; }
-            else { std::cerr << "[ERROR](VcfParser::processLine) => not found PS type (Type=Integer or Type=String).\n"; exit(EXIT_SUCCESS); }
-        }
-        return;
-    }
-    if (line.compare(0, 1, "#") == 0) return;
-    std::istringstream split(line);
-    std::vector<std::string> f((std::istream_iterator<std::string>(split)), std::istream_iterator<std::string>());
-    if (f.empty()) return;
-    if (f.size() < 10) { std::cerr << "[ERROR](VcfParser::parserProcess) => VCF file format not supported: " << line << std::endl; exit(EXIT_FAILURE); }
-    const std::string &format = f[8], &sample = f[9];
-    const size_t g = subfield_start(sample, subfield_of(format, "GT"));
-    const char a = peek(sample, g), bar = peek(sample, g + 1), b = peek(sample, g + 2);
-    if (a == b || bar != '|') return;   // only phased heterozygous records feed the germline tagger
-    const size_t p = subfield_start(sample, subfield_of(format, "PS"));
-    const size_t p_end = sample.find(':', p + 1);
-    const std::string ps_text = p_end != std::string::npos ? sample.substr(p, p_end - p) : sample.substr(std::min(p, sample.size()));
-    PhasedVariant v;
-    v.ref = f[3];
-    const std::string &alts = f[4];
-    if (alts.find(',') != std::string::npos) {
-        if (sample.find('2') != std::string::npos) return;   // the reference's "GT has a 2" test reduces to this (HaplotagVcfParser.cpp:283-286)
-        v.alt = alts.substr(0, alts.find(','));
-    } else {
-        v.alt = alts;
-    }
-    const size_t rl = v.ref.size(), al = v.alt.size();
-    if (!((rl == 1 && al >= 1) || (rl > 1 && al == 1) || (rl > 1 && rl == al))) {   // VarData::setVariantType throws
-        std::cerr << "terminate: (loadVariantType)Invalid allele: " << v.ref << " " << v.alt << "\n";
-        exit(1);
-    }
-    if (st.integer_ps) v.ps = std::stoi(ps_text);
-    else {
-        if (st.ps_index.find(ps_text) == st.ps_index.end()) { const int next = (int)st.ps_index.size(); st.ps_index[ps_text] = next; }
-        v.ps = st.ps_index[ps_text];
-    }
-    if (a == '0' && b == '1') { v.oriented = true; v.hp1_is_alt = false; }
-    else if (a == '1' && b == '0') { v.oriented = true; v.hp1_is_alt = true; }
-    if (!v.oriented) return;   // GT such as 0|2 without a second ALT: HP1 / HP2 stay empty in the reference; not representable, skipped
-    job.variants[f[0]][std::stoi(f[1]) - 1] = v;
-}
-
-int load_tag_vcf(lpsh_tag &job) {
-    const std::string &path = job.opt.snp_file;
-    VcfLoadState st;
-    if (path.find("gz") != std::string::npos) {
-        std::string text;
-        if (!lpsh::read_gz(path, text)) { std::cerr << "Fail to open vcf: " << path << "\n"; return 0; }
-        size_t at = 0;
-        for (size_t nl; (nl = text.find('\n', at)) != std::string::npos; at = nl + 1) load_tag_line(job, text.substr(at, nl - at), st);
-    } else if (path.find("vcf") != std::string::npos) {
-        std::ifstream in(path.c_str());
-        if (!in.is_open()) { std::cerr << "Fail to open vcf: " << path << "\n"; exit(1); }
-        std::string line;
-        while (!in.eof()) { std::getline(in, line); load_tag_line(job, line, st); }
-    } else {
-        std::cerr << "file: " << path << "\nnot vcf file. please check filename extension\n";
-        exit(EXIT_FAILURE);
-    }
-    return 0;
 }
 
 // HaplotagProcess::setProcessingChromRegion (HaplotagProcess.cpp:105-135)
@@ -307,11 +185,6 @@ void write_log_header(lpsh_tag &job) {   // GermlineTagLog::addParamsMessage / w
     job.log << "#ReadID\tCHROM\tReadStart\tConfidnet(%)\tHaplotype\tPhaseSet\tTotalAllele\tHP1Allele\tHP2Allele\tphasingQuality(PQ)\t(Variant,HP)\t(PhaseSet,Variantcount)\n";
 }
 
-void drop_aux(bam1_t *b, const char *tag) {
-    uint8_t *p = bam_aux_get(b, tag);
-    if (p) bam_aux_del(b, p);
-}
-
 void finish_contig(lpsh_tag &job) {
     if (job.itr) hts_itr_destroy(job.itr);
     job.itr = nullptr;
@@ -333,7 +206,13 @@ int lpsh_tag_open(int argc, char **argv, lpsh_tag **out) {
     tag_banner(job->opt);
     std::time_t t0 = time(NULL);
     std::cerr << "parsing SNP VCF ... ";
-    load_tag_vcf(*job);
+    {
+        lpsh::SampleVcf vcf;   // VcfParser::parserProcess for the NORMAL sample (HaplotagVcfParser.cpp:206-345)
+        lpsh::load_sample_vcf(job->opt.snp_file, false, vcf);
+        job->chr_names.swap(vcf.chr_names);
+        job->chr_length.swap(vcf.chr_length);
+        job->variants.swap(vcf.records);
+    }
     std::cerr << difftime(time(NULL), t0) << "s\n";
     narrow_to_region(*job);
     *out = job;
@@ -404,7 +283,7 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
     lpsh::PackedContig &pc = h->chunk.pack;
     pc.tagged_variants = true;
     for (const auto &kv : h->variants[chr]) {
-        const PhasedVariant &v = kv.second;
+        const lpsh::SampleRecord &v = kv.second;
         pc.add_variant(kv.first, v.ref, v.alt);
         pc.v_hp1_is_alt.push_back(v.hp1_is_alt);
         pc.v_ps.push_back(v.ps);
@@ -425,7 +304,7 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
 
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
     if (!h || !r || h->cur != i || !h->out) return -1;
-    Chunk &ck = h->chunk;
+    lpsh::Chunk &ck = h->chunk;
     const size_t n = ck.records.size();
     if ((size_t)r->n_reads != n) return lpsh::fail("verdict count does not match the chunk");
     const bool want_log = h->log.is_open();
@@ -469,9 +348,9 @@ int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
                 for (const auto &v : count_ps) h->log << " " << v.first << "," << v.second;
                 h->log << "\n";
             }
-            drop_aux(b, "HP");
-            drop_aux(b, "PS");
-            drop_aux(b, "PQ");
+            lpsh::drop_aux(b, "HP");
+            lpsh::drop_aux(b, "PS");
+            lpsh::drop_aux(b, "PQ");
             if (hp != 0) {
                 h->st_hp[hp]++;
                 h->st_tag++;

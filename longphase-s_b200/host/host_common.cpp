@@ -39,6 +39,103 @@ int device_count() {
     return n;
 }
 
+// ---- VcfParser::parserProcess ---------------------------------------------------------------------------------------------
+namespace {
+struct TextVcfState {
+    bool integer_ps = false;
+    std::map<std::string, int> ps_index;
+};
+
+void check_alleles(const SampleRecord &v) {   // VarData::setVariantType throws for anything that is not SNP / insertion / deletion / MNP
+    const size_t rl = v.ref.size(), al = v.alt.size();
+    if ((rl == 1 && al >= 1) || (rl > 1 && al == 1) || (rl > 1 && rl == al)) return;
+    std::cerr << "terminate: (loadVariantType)Invalid allele: " << v.ref << " " << v.alt << "\n";
+    exit(1);
+}
+bool long_indel(const SampleRecord &v) {      // tumor sample only (HaplotagVcfParser.cpp:300-308)
+    const size_t rl = v.ref.size(), al = v.alt.size();
+    const bool indel = (rl == 1 && al > 1) || (rl > 1 && al == 1);
+    return indel && std::abs((int)al - (int)rl) > 100;
+}
+
+void load_sample_line(const std::string &line, bool tumor, TextVcfState &st, SampleVcf &out) {
+    if (line.compare(0, 2, "##") == 0) {
+        if (line.find("contig=") != std::string::npos) {
+            const int id_start = (int)line.find("ID=") + 3, id_end = (int)line.find(",length=");
+            const int len_start = id_end + 8, len_end = (int)line.find(">");
+            const std::string chr = line.substr((size_t)id_start, (size_t)(id_end - id_start));
+            out.chr_names.push_back(chr);
+            out.chr_length[chr] = std::stoi(line.substr((size_t)len_start, (size_t)(len_end - len_start)));
+        }
+        if (line.compare(0, 16, "##FORMAT=<ID=PS,") == 0) {
+            if (line.find("Type=Integer") != std::string::npos) st.integer_ps = true;
+            else if (line.find("Type=String") != std::string::npos) { st.integer_ps = false; std::cerr << "PS type is String. Auto index to integer ... "; }
+            else { std::cerr << "[ERROR](VcfParser::processLine) => not found PS type (Type=Integer or Type=String).\n"; exit(EXIT_SUCCESS); }
+        }
+        return;
+    }
+    if (line.compare(0, 1, "#") == 0) return;
+    std::istringstream split(line);
+    std::vector<std::string> f((std::istream_iterator<std::string>(split)), std::istream_iterator<std::string>());
+    if (f.empty()) return;
+    if (f.size() < 10) { std::cerr << "[ERROR](VcfParser::parserProcess) => VCF file format not supported: " << line << std::endl; exit(EXIT_FAILURE); }
+    const std::string &format = f[8], &sample = f[9];
+    const size_t g = subfield_start(sample, subfield_of(format, "GT"));
+    const char a = peek(sample, g), bar = peek(sample, g + 1), b = peek(sample, g + 2);
+    const int pos = std::stoi(f[1]) - 1;
+    SampleRecord v;
+    v.ref = f[3];
+    const std::string &alts = f[4];
+    const bool comma = alts.find(',') != std::string::npos;
+    v.alt = comma ? alts.substr(0, alts.find(',')) : alts;
+    if (a != b && bar == '|') {                       // phased heterozygous
+        const size_t p = subfield_start(sample, subfield_of(format, "PS"));
+        const size_t p_end = sample.find(':', p + 1);
+        const std::string ps_text = p_end != std::string::npos ? sample.substr(p, p_end - p) : sample.substr(std::min(p, sample.size()));
+        if (comma && sample.find('2') != std::string::npos) return;   // the reference's "GT has a 2" test reduces to this (:283-286)
+        v.gt_kind = 1;
+        check_alleles(v);
+        if (tumor && long_indel(v)) return;
+        if (st.integer_ps) v.ps = std::stoi(ps_text);
+        else {
+            // psIndex[psValue] = psIndex.size() (:316-320): as built here (g++ 13) the size is read before the entry is created, so the
+            // first distinct PS string gets 0 (checked against the reference binary, tests/test_host_cli.py string-PS case)
+            if (st.ps_index.find(ps_text) == st.ps_index.end()) { const int next = (int)st.ps_index.size(); st.ps_index[ps_text] = next; }
+            v.ps = st.ps_index[ps_text];
+        }
+        if (a == '0' && b == '1') v.hp1_is_alt = false;
+        else if (a == '1' && b == '0') v.hp1_is_alt = true;
+        else return;   // GT such as 0|2 without a second ALT: HP1 / HP2 stay empty in the reference; not representable, skipped
+        out.records[f[0]][pos] = v;
+    } else if (tumor) {
+        if (a == '1' && bar == '/' && b == '1') v.gt_kind = 3;
+        else if (a == '0' && bar == '/' && b == '1') v.gt_kind = 2;
+        else return;
+        check_alleles(v);
+        if (long_indel(v)) return;
+        out.records[f[0]][pos] = v;
+    }
+}
+}  // namespace
+
+void load_sample_vcf(const std::string &path, bool tumor, SampleVcf &out) {
+    TextVcfState st;
+    if (path.find("gz") != std::string::npos) {
+        std::string text;
+        if (!read_gz(path, text)) { std::cerr << "Fail to open vcf: " << path << "\n"; return; }
+        size_t at = 0;
+        for (size_t nl; (nl = text.find('\n', at)) != std::string::npos; at = nl + 1) load_sample_line(text.substr(at, nl - at), tumor, st, out);
+    } else if (path.find("vcf") != std::string::npos) {
+        std::ifstream in(path.c_str());
+        if (!in.is_open()) { std::cerr << "Fail to open vcf: " << path << "\n"; exit(1); }
+        std::string line;
+        while (!in.eof()) { std::getline(in, line); load_sample_line(line, tumor, st, out); }
+    } else {
+        std::cerr << "file: " << path << "\nnot vcf file. please check filename extension\n";
+        exit(EXIT_FAILURE);
+    }
+}
+
 }  // namespace lpsh
 
 extern "C" const char *lpsh_last_error(void) {

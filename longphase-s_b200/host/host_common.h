@@ -10,6 +10,10 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <fstream>
+#include <functional>
+#include <iterator>
+#include <sstream>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -113,6 +117,62 @@ struct PackedContig {
         out->names = names.data(); out->name_off = name_off.data();
     }
 };
+
+// ---- small helpers shared by the sub-commands ----------------------------------------------------------------------------
+template <class T>
+inline void take(const char *text, T &dst) {   // the reference reads every option value with operator>> of an istringstream
+    std::istringstream in(text ? text : "");
+    in >> dst;
+}
+// FileValidator::validateRequiredFile (src/shared/ArgumentManager.cpp:147-160)
+inline bool required_file(const char *program, const std::string &path, const char *what) {
+    if (path.empty()) { std::cerr << "[ERROR] " << program << ": missing " << what << ".\n"; return false; }
+    if (!std::ifstream(path.c_str()).is_open()) { std::cerr << "[ERROR] " << program << ": " << what << ": " << path << " not exist.\n\n"; return false; }
+    return true;
+}
+// the reference addresses FORMAT keys and sample values by counting ':' (ParsingBam.cpp:494-560, HaplotagVcfParser.cpp:238-262)
+inline int subfield_of(const std::string &format, const char *key) {   // index of the sub-field whose text contains `key`, 0 if absent
+    const size_t at = format.find(key);
+    if (at == std::string::npos) return 0;
+    return (int)std::count(format.begin(), format.begin() + at, ':');
+}
+inline size_t subfield_start(const std::string &sample, int k) {      // first character of the k-th ':' separated value (size() if fewer)
+    size_t i = 0;
+    for (int seen = 0; i < sample.size() && seen < k; i++) seen += sample[i] == ':';
+    return i;
+}
+inline char peek(const std::string &s, size_t i) { return i < s.size() ? s[i] : '\0'; }
+inline void drop_aux(bam1_t *b, const char *tag) {                     // GermlineHaplotagChrProcessor::initFlag (HaplotagProcess.cpp:428-436)
+    uint8_t *p = bam_aux_get(b, tag);
+    if (p) bam_aux_del(b, p);
+}
+
+// records of one chunk of a tagging pass, kept until the verdicts come back, next to their SoA form
+struct Chunk {
+    PackedContig pack;
+    std::vector<bam1_t *> records;
+    void clear() {
+        for (bam1_t *b : records) bam_destroy1(b);
+        records.clear();
+        pack = PackedContig();
+    }
+};
+
+// ---- the text VCF loader of the tag family (VcfParser::parserProcess, src/haplotag/HaplotagVcfParser.cpp:206-545) ---------
+// one record of one sample (VarData, HaplotagType.h:110-143)
+struct SampleRecord {
+    std::string ref, alt;
+    int ps = -1;              // VarData::NONE_PHASED_SET
+    int gt_kind = 0;          // GenomeType: 1 PHASED_HETERO, 2 UNPHASED_HETERO, 3 UNPHASED_HOMO
+    bool hp1_is_alt = false;  // GT 1|0
+};
+struct SampleVcf {
+    std::vector<std::string> chr_names;   // VCF_Info::chrVec (##contig order)
+    std::map<std::string, int> chr_length;
+    std::map<std::string, std::map<int, SampleRecord>> records;
+};
+// tumor = false: only phased heterozygous records are kept (NORMAL sample); tumor = true: also 0/1 and 1/1, indels above 100 bp dropped
+void load_sample_vcf(const std::string &path, bool tumor, SampleVcf &out);
 
 }  // namespace lpsh
 #endif

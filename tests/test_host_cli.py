@@ -213,6 +213,33 @@ def test_haplotag_host_files_match_reference(tmp_path_factory, tmp_path, extra):
 
 
 @needs_host
+@needs_ref
+def test_haplotag_string_phase_sets(tmp_path_factory, tmp_path):
+    """##FORMAT=<ID=PS,...Type=String>: phase-set names are indexed in order of first appearance, from 0 (HaplotagVcfParser.cpp:316-320)."""
+    files = dataset(tmp_path_factory, "plain")
+    out, i = [], 0
+    for ln in open(files["vcf"]).read().split("\n"):
+        if ln.startswith("#CHROM"):
+            out.append('##FORMAT=<ID=PS,Number=1,Type=String,Description="ps">')
+        if ln and not ln.startswith("#"):
+            t = ln.split("\t")
+            if len(t[3]) == 1 and "," not in t[4]:
+                t[8], t[9] = "GT:PS", ("0|1" if i % 2 else "1|0") + ":blk%d" % (i // 40)
+                i += 1
+                ln = "\t".join(t)
+        out.append(ln)
+    vcf = str(tmp_path / "string_ps.vcf")
+    open(vcf, "w").write("\n".join(out))
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, vcf, ["--log"]))
+    oracle_tag_through_host(files, vcf, ["--log"], str(tmp_path / "own"), chunk=5000)
+    assert hc.bam_payload(str(tmp_path / "own" / "tagged.bam")) == hc.bam_payload(str(tmp_path / "ref" / "tagged.bam"))
+    log = open(tmp_path / "own" / "tagged.out").read()
+    assert log == open(tmp_path / "ref" / "tagged.out").read()
+    seen = {ln.split("\t")[5] for ln in log.split("\n") if ln and ln[0] != "#"} - {"."}
+    assert "0" in seen and len(seen) >= 3
+
+
+@needs_host
 def test_host_rejects_bad_options(tmp_path, capfd):
     lib = hc.host_lib()
     h = C.c_void_p()
