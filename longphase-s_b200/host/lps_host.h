@@ -1,6 +1,6 @@
 /*
  * lps_host.h — the C++ host that sits ABOVE the C ABI of include/lps.h: the reference's own command-line and file surface
- * (`longphase-s phase | haplotag`) kept as it is, with the per-contig hot path handed to liblps_b200.so.
+ * (`longphase-s phase | haplotag | somatic_haplotag`) kept as it is, with the per-contig hot path handed to liblps_b200.so.
  *
  * The host keeps htslib for BAM / VCF / FASTA decoding, exactly as BASELINE.json:north_star asks: it packs the decoded
  * alignments into the SoA batch of include/lps.h, calls the kernels through the C ABI, and writes the reference's output
@@ -85,6 +85,34 @@ int lpsh_tag_end(lpsh_tag *h);                                         /* closes
 int lpsh_tag_run(lpsh_tag *h);                                         /* begin, then pack / lps_tag_reads / emit per contig, end */
 void lpsh_tag_close(lpsh_tag *h);
 int lpsh_tag_main(int argc, char **argv);
+
+/* ---- somatic_haplotag ---------------------------------------------------------------------------------------------- *
+ * SomaticHaplotagProcess::pipelineProcess (src/somatic_haplotag/SomaticHaplotagProcess.cpp:51-103): NORMAL + TUMOR VCFs into one
+ * union map, extract pass over the normal BAM and over the tumor BAM, purity (<prefix>_purity.out), calling, tagging of the
+ * tumor BAM (HP:Z, PS:i unless none, PQ:i).                                                                                */
+typedef struct lpsh_som lpsh_som;
+int lpsh_som_open(int argc, char **argv, lpsh_som **out);            /* argv[0] = "somatic_haplotag"                   */
+int lpsh_som_n_contigs(const lpsh_som *h);
+const char *lpsh_som_contig_name(const lpsh_som *h, int i);
+int lpsh_som_params(const lpsh_som *h, int pass, lps_tag_params *out); /* pass 0: extract passes, 1: tagging pass         */
+/* every alignment of contig i of the NORMAL (which = 0) or TUMOR (1) BAM, packed with the contig's union map; the arrays stay
+ * valid until the next lpsh_som_pack                                                                                      */
+int lpsh_som_pack(lpsh_som *h, int i, int which, lpsh_packed *out, lps_tumor_variants *tv);
+/* keeps a copy of the result of lps_extract_normal (which = 0) / lps_extract_tumor (1) for contig i                       */
+int lpsh_som_set_extract(lpsh_som *h, int i, int which, const lps_extract_result *r);
+/* runTumorPurityEstimator (or --tumor-purity), <prefix>_purity.out, the calling stage and getSomaticFlag for every contig
+ * (SomaticVarCaller.cpp:816-866, 937-949, 2397-2412); needs both extract results of every contig                          */
+int lpsh_som_call(lpsh_som *h);
+double lpsh_som_purity(const lpsh_som *h);
+int64_t lpsh_som_n_somatic(const lpsh_som *h);
+int lpsh_som_tag_begin(lpsh_som *h);
+/* next chunk of contig i of the tumor BAM, the union map now carrying isSomaticVariant / somaticReadDeriveByHP: 1, 0 or < 0 */
+int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv);
+int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r);
+int lpsh_som_tag_end(lpsh_som *h);
+int lpsh_som_run(lpsh_som *h);
+void lpsh_som_close(lpsh_som *h);
+int lpsh_som_main(int argc, char **argv);
 
 /* ---- tooling: the generator's SoA batches written as BAM + BAI with htslib (bench and tests; no samtools in the image) --- */
 typedef struct lpsh_bamw lpsh_bamw;

@@ -1,0 +1,778 @@
+// somatic_host.cpp — the `somatic_haplotag` sub-command above the C ABI: options, the NORMAL (phased) and TUMOR VCF loaders and
+// their union map, the two extract passes over the normal and the tumor BAM, tumor purity (+ <prefix>_purity.out), the somatic
+// calling stage, and the tagging pass over the tumor BAM (HP:Z, optional PS:i, PQ:i) with the @PG line and the stderr report.
+//
+// Reference seams replaced (file:line relative to the reference tree):
+//   SomaticHaplotagMain / option handling          src/somatic_haplotag/SomaticHaplotag.cpp:34-142
+//   SomaticHaplotagProcess::pipelineProcess        src/somatic_haplotag/SomaticHaplotagProcess.cpp:51-103, 105-235
+//   SomaticVarCaller::variantCalling               src/somatic_haplotag/SomaticVarCaller.cpp:816-949  (extract passes, purity, calling, getSomaticFlag :2397-2412)
+//   TumorPurityEstimator::writePurityResult        src/somatic_haplotag/TumorPurityEstimator.cpp:375-424
+//   SomaticHaplotagChrProcessor::processRead / addAuxiliaryTags   src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-400, 464-472
+// The device judges whole batches (lps_extract_normal / lps_extract_tumor / lps_somatic_tag_reads); purity and calling are the
+// host stages of liblps_b200.so (lps_estimate_purity, lps_somatic_call).
+// Scope notes: --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file and --cram are
+// parsed but rejected (benchmark tooling and text logs outside the rebuilt hot path).
+#include "host_common.h"
+
+#include <getopt.h>
+#include <omp.h>
+
+#include <climits>
+#include <cmath>
+#include <ctime>
+
+namespace {
+
+const char *SOM_USAGE =
+    "Usage:  somatic_haplotag [OPTION] ... READSFILE\n"
+    "      --help                          display this help and exit.\n\n"
+    "required arguments:\n"
+    "      -s, --snp-file=NAME             input phased normal sample SNP VCF file.\n"
+    "      -b, --bam-file=NAME             input normal sample BAM file.\n"
+    "      --tumor-snv-file=NAME           input tumor sample SNV VCF file.\n"
+    "      --tumor-bam-file=NAME           input tumor sample BAM file for somatic haplotag.\n"
+    "      -r, --reference=NAME            reference FASTA.\n\n"
+    "optional arguments:\n"
+    "      --tagSupplementary              tag supplementary alignment. default:false\n"
+    "      -q, --qualityThreshold=Num      not tag alignment if the mapping quality less than threshold. default:1\n"
+    "      -p, --percentageThreshold=Num   share of the alleles the winning haplotype needs. default:0.6\n"
+    "      -t, --threads=Num               number of thread. default:1\n"
+    "      -o, --out-prefix=NAME           prefix of the tagged tumor BAM. default:result\n"
+    "      --region=REGION                 chrom | chrom:start | chrom:start-end. default:\"\"(all regions)\n"
+    "      --tumor-purity=Num              tumor purity (0.1~1.0). default: automatic estimation.\n"
+    "      --disableFilter                 accept all tumor VCF variants as somatic. default: false.\n"
+    "not available in this build: --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file, --cram\n";
+
+enum { S_HELP = 1, S_SUP, S_SV, S_MOD, S_REGION, S_CRAM, S_LOG, S_TUM_SNP, S_TUM_BAM, S_DISABLE_FILTER, S_PURITY, S_OUT_VCF, S_CALL_LOG,
+       S_TRUTH_VCF, S_TRUTH_BED, S_BENCH_LOG };
+
+const struct option SOM_LONG[] = {
+    {"help", no_argument, NULL, S_HELP},
+    {"snp-file", required_argument, NULL, 's'},
+    {"bam-file", required_argument, NULL, 'b'},
+    {"reference", required_argument, NULL, 'r'},
+    {"sv-file", required_argument, NULL, S_SV},
+    {"mod-file", required_argument, NULL, S_MOD},
+    {"threads", required_argument, NULL, 't'},
+    {"qualityThreshold", required_argument, NULL, 'q'},
+    {"percentageThreshold", required_argument, NULL, 'p'},
+    {"tagSupplementary", no_argument, NULL, S_SUP},
+    {"out-prefix", required_argument, NULL, 'o'},
+    {"region", required_argument, NULL, S_REGION},
+    {"cram", no_argument, NULL, S_CRAM},
+    {"log", no_argument, NULL, S_LOG},
+    {"tumor-snv-file", required_argument, NULL, S_TUM_SNP},
+    {"tumor-bam-file", required_argument, NULL, S_TUM_BAM},
+    {"disableFilter", no_argument, NULL, S_DISABLE_FILTER},
+    {"tumor-purity", required_argument, NULL, S_PURITY},
+    {"output-somatic-vcf", no_argument, NULL, S_OUT_VCF},
+    {"somatic-calling-log", no_argument, NULL, S_CALL_LOG},
+    {"truth-vcf", required_argument, NULL, S_TRUTH_VCF},
+    {"truth-bed", required_argument, NULL, S_TRUTH_BED},
+    {"benchmark-log", no_argument, NULL, S_BENCH_LOG},
+    {NULL, 0, NULL, 0}};
+
+struct SomOptions {
+    int threads = 1, quality = 1;
+    double percentage = 0.6, purity = 0.2;
+    bool tag_supplementary = false, estimate_purity = true, enable_filter = true, unsupported = false;
+    std::string snp_file, bam, tumor_vcf, tumor_bam, fasta, prefix = "result", region, command = "longphase-s ";
+};
+
+// one position of the union map std::map<int, MultiGenomeVar> (HaplotagType.h:146-162)
+struct UnionVar {
+    bool has_nor = false, has_tum = false;
+    lpsh::SampleRecord nor, tum;
+    uint8_t is_somatic = 0;   // MultiGenomeVar::isSomaticVariant
+    int8_t derive_hp = 0;     // MultiGenomeVar::somaticReadDeriveByHP
+};
+
+// deep copy of what lps_somatic_call and lps_estimate_purity read from an lps_extract_result (the context owns the original
+// only until its next call)
+struct ExtractCopy {
+    bool set = false;
+    std::vector<int32_t> tum_var, pos_base, read_hp_count, somatic_read_hp_count, window_hist, case_read_count, h1, h2, h3, end_pos;
+    std::vector<float> ratios_f;
+    std::vector<double> ratios_d;
+    std::vector<uint8_t> category, n_ps;
+    std::vector<int8_t> read_hp;
+    std::vector<uint64_t> call_off;
+    std::vector<lps_call> calls;
+    template <class T>
+    static void put(std::vector<T> &dst, const T *src, size_t n) { if (src) dst.assign(src, src + n); else dst.clear(); }
+    void assign(const lps_extract_result &r) {
+        const size_t nt = (size_t)r.n_tum, nr = (size_t)r.reads.n_reads;
+        put(tum_var, r.tum_var, nt); put(pos_base, r.pos_base, nt * LPS_PB_FIELDS); put(read_hp_count, r.read_hp_count, nt * 9);
+        put(somatic_read_hp_count, r.somatic_read_hp_count, nt * 9); put(window_hist, r.window_hist, nt * 2 * LPS_WINDOW_BINS);
+        put(case_read_count, r.case_read_count, nt); put(ratios_f, r.ratios_f, nt * LPS_RF_FIELDS); put(ratios_d, r.ratios_d, nt * LPS_RD_FIELDS);
+        put(category, r.reads.category, nr); put(read_hp, r.reads.read_hp, nr); put(h1, r.reads.h1, nr); put(h2, r.reads.h2, nr);
+        put(h3, r.reads.h3, nr); put(n_ps, r.reads.n_ps, nr); put(end_pos, r.reads.end_pos, nr);
+        put(call_off, r.call_off, r.call_off ? nr + 1 : 0); put(calls, r.calls, r.calls ? (size_t)r.n_calls : 0);
+        set = true;
+    }
+    template <class T>
+    static const T *ptr(const std::vector<T> &v) { return v.empty() ? nullptr : v.data(); }
+    lps_extract_result view() const {
+        lps_extract_result r;
+        memset(&r, 0, sizeof(r));
+        r.n_tum = (int32_t)tum_var.size();
+        r.tum_var = ptr(tum_var); r.pos_base = ptr(pos_base); r.read_hp_count = ptr(read_hp_count);
+        r.reads.n_reads = (int32_t)category.size();
+        r.reads.category = ptr(category); r.reads.read_hp = ptr(read_hp); r.reads.h1 = ptr(h1); r.reads.h2 = ptr(h2); r.reads.h3 = ptr(h3);
+        r.reads.n_ps = ptr(n_ps); r.reads.end_pos = ptr(end_pos);
+        r.somatic_read_hp_count = ptr(somatic_read_hp_count); r.window_hist = ptr(window_hist); r.case_read_count = ptr(case_read_count);
+        r.ratios_f = ptr(ratios_f); r.ratios_d = ptr(ratios_d);
+        r.n_calls = calls.size(); r.call_off = ptr(call_off); r.calls = ptr(calls);
+        return r;
+    }
+};
+
+struct TumorArrays {   // lps_tumor_variants of one contig
+    std::vector<uint8_t> nor_present, tum_present, ref0, alt0, gt_kind, hp1_is_alt, is_somatic;
+    std::vector<uint16_t> ref_len, alt_len;
+    std::vector<int32_t> ps;
+    std::vector<int8_t> derive_hp;
+    void view(lps_tumor_variants *t) const {
+        memset(t, 0, sizeof(*t));
+        t->n = (int32_t)tum_present.size();
+        t->nor_present = nor_present.data(); t->tum_present = tum_present.data(); t->ref0 = ref0.data(); t->alt0 = alt0.data();
+        t->ref_len = ref_len.data(); t->alt_len = alt_len.data(); t->gt_kind = gt_kind.data(); t->hp1_is_alt = hp1_is_alt.data();
+        t->ps = ps.data(); t->is_somatic = is_somatic.data(); t->derive_hp = derive_hp.data();
+    }
+};
+
+struct ContigState {
+    ExtractCopy normal, tumor;
+};
+
+}  // namespace
+
+struct lpsh_som {
+    SomOptions opt;
+    std::vector<std::string> chr_names;
+    std::map<std::string, int> chr_length;
+    std::map<std::string, std::map<int, UnionVar>> variants;
+    std::map<std::string, std::string> ref_normal, ref_tumor;   // FastaParser strings of the NORMAL / TUMOR passes (different last positions)
+    bool have_reference = false;
+    std::vector<ContigState> contig;
+    double purity = 0.0;
+    lps_purity_result purity_result;
+    int64_t n_somatic = 0;
+    // whole-contig pack of an extract pass
+    lpsh::PackedContig pack;
+    TumorArrays tum;
+    // tagging pass
+    samFile *in = nullptr, *out = nullptr;
+    bam_hdr_t *hdr = nullptr;
+    hts_idx_t *idx = nullptr;
+    htsThreadPool pool = {NULL, 0};
+    int cur = -1;
+    hts_itr_t *itr = nullptr;
+    bool itr_done = false;
+    lpsh::Chunk chunk;
+    size_t chunk_reads = 65536;
+    // ReadStatistics
+    int64_t st_alignment = 0, st_supplementary = 0, st_secondary = 0, st_unmapped = 0, st_tag = 0, st_untag = 0, st_low = 0, st_other = 0,
+            st_empty = 0, st_similar = 0, st_cross = 0, st_no_variant = 0, st_only_h3 = 0, st_hp[LPS_READHP_FIELDS] = {0};
+    std::time_t t_begin = time(NULL);
+};
+
+namespace {
+
+const char *READ_HP_TEXT[LPS_READHP_FIELDS] = {".", "1", "2", "3", "4", "1-1", "1-2", "2-1", "2-2"};   // ReadHapUtil::readHapIntToString
+
+int parse_som_options(int argc, char **argv, SomOptions &o) {
+    optind = 1;
+    bool bad = false;
+    for (int c; (c = getopt_long(argc, argv, "s:b:o:t:q:p:r:", SOM_LONG, NULL)) != -1;) {
+        switch (c) {
+            case 't': lpsh::take(optarg, o.threads); break;
+            case 'o': lpsh::take(optarg, o.prefix); break;
+            case 'q': lpsh::take(optarg, o.quality); break;
+            case 'p': lpsh::take(optarg, o.percentage); break;
+            case S_SUP: o.tag_supplementary = true; break;
+            case S_REGION: lpsh::take(optarg, o.region); break;
+            case 's': lpsh::take(optarg, o.snp_file); break;
+            case 'b': lpsh::take(optarg, o.bam); break;
+            case 'r': lpsh::take(optarg, o.fasta); break;
+            case S_TUM_SNP: lpsh::take(optarg, o.tumor_vcf); break;
+            case S_TUM_BAM: lpsh::take(optarg, o.tumor_bam); break;
+            case S_DISABLE_FILTER: o.enable_filter = false; break;
+            case S_PURITY: lpsh::take(optarg, o.purity); o.estimate_purity = false; break;
+            case S_CRAM: case S_LOG: case S_SV: case S_MOD: case S_OUT_VCF: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
+                o.unsupported = true; break;
+            case S_HELP: std::cout << SOM_USAGE << std::endl; return 2;
+            default: bad = true;
+        }
+    }
+    for (int i = 0; i < argc; i++) { o.command += argv[i]; o.command += " "; }
+    const char *prog = "somatic_haplotag";
+    bad |= !lpsh::required_file(prog, o.snp_file, "SNP file");
+    bad |= !lpsh::required_file(prog, o.bam, "BAM file");
+    bad |= !lpsh::required_file(prog, o.fasta, "reference file");
+    bad |= !lpsh::required_file(prog, o.tumor_vcf, "tumor SNV file");
+    bad |= !lpsh::required_file(prog, o.tumor_bam, "tumor BAM file");
+    if (o.threads < 1) { std::cerr << "[ERROR] " << prog << ": invalid threads. value: " << o.threads << "\nplease check -t, --threads=Num\n"; bad = true; }
+    if (o.percentage > 1 || o.percentage < 0) {
+        std::cerr << "[ERROR] " << prog << ": invalid percentage threshold. value: " << o.percentage
+                  << "\nthis value need: 0~1, please check -p, --percentageThreshold=Num\n";
+        bad = true;
+    }
+    if (o.purity < 0.1 || o.purity > 1.0) {
+        std::cerr << "[ERROR] " << prog << ": invalid tumor purity. value: " << o.purity << "\nthis value need: 0.1~1.0, --tumor-purity=Number\n";
+        bad = true;
+    }
+    if (o.unsupported) {
+        std::cerr << "[ERROR] " << prog << ": --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file "
+                     "and --cram are not available in this build.\n";
+        bad = true;
+    }
+    if (bad) { std::cerr << "\n"; std::cout << SOM_USAGE << std::endl; return 1; }
+    return 0;
+}
+
+void som_banner(const SomOptions &o) {   // SomaticHaplotagProcess::printParamsMessage (SomaticHaplotagProcess.cpp:13-49)
+    std::ostream &e = std::cerr;
+    e << "LongPhase-S v" << lpsh::REFERENCE_VERSION << " - Somatic Haplotag (" << lps_version() << ")\n\n[Input Files]\n";
+    e << "phased normal SNP file       : " << o.snp_file << "\ntumor SNP file               : " << o.tumor_vcf << "\n";
+    e << "normal BAM file              : " << o.bam << "\ntumor BAM file               : " << o.tumor_bam << "\n";
+    e << "reference file               : " << o.fasta << "\n\n[Output Files]\n";
+    e << "tagged tumor BAM file        : " << o.prefix + ".bam" << "\npurity estimation file       : " << (o.estimate_purity ? o.prefix + "_purity.out" : "") << "\n";
+    e << "-------------------------------------------\n[Somatic Haplotagging Params] \n";
+    e << "number of threads            : " << o.threads << "\ntag region                   : " << (!o.region.empty() ? o.region : "all") << "\n";
+    e << "filter mapping quality below : " << o.quality << "\npercentage threshold         : " << o.percentage << "\n";
+    e << "tag supplementary            : " << (o.tag_supplementary ? "enabled" : "disabled") << "\n\n[Somatic Variant Calling Params] \n";
+    e << "mapping quality              : " << o.quality << "\ntumor purity value           : " << (o.estimate_purity ? "automatic estimation" : std::to_string(o.purity)) << "\n";
+    e << "variant filtering            : " << (o.enable_filter ? "enabled" : "disabled") << "\n-------------------------------------------\n";
+}
+
+bool is_snp(const lpsh::SampleRecord &v) { return v.ref.size() == 1 && v.alt.size() == 1; }
+bool is_ins(const lpsh::SampleRecord &v) { return v.ref.size() == 1 && v.alt.size() > 1; }
+bool is_del(const lpsh::SampleRecord &v) { return v.ref.size() > 1 && v.alt.size() == 1; }
+
+// parseVariantFiles + setChrVecAndChrLength + displaySnpCounts + setProcessingChromRegion (SomaticHaplotagProcess.cpp:105-235, HaplotagProcess.cpp:105-135)
+int load_union(lpsh_som &job) {
+    lpsh::SampleVcf nor, tum;
+    std::time_t t0 = time(NULL);
+    std::cerr << "parsing normal SNP VCF ... ";
+    lpsh::load_sample_vcf(job.opt.snp_file, false, nor);
+    std::cerr << difftime(time(NULL), t0) << "s\n";
+    t0 = time(NULL);
+    std::cerr << "parsing tumor SNP VCF ... ";
+    lpsh::load_sample_vcf(job.opt.tumor_vcf, true, tum);
+    std::cerr << difftime(time(NULL), t0) << "s\n";
+    for (const auto &c : tum.chr_length) {
+        auto it = nor.chr_length.find(c.first);
+        if (it == nor.chr_length.end()) { std::cerr << "[ERROR] (setChrVecAndChrLength) :tumor & normal VCFs chromosome count are not the same" << std::endl; return lpsh::fail("tumor & normal VCFs chromosome count are not the same"); }
+        if (it->second != c.second) { std::cerr << "[ERROR] (setChrVecAndChrLength) :tumor & normal VCFs chromosome length are not the same => chr: " << c.first << std::endl; return lpsh::fail("tumor & normal VCFs chromosome length are not the same"); }
+    }
+    if (tum.chr_names.empty()) {
+        std::cerr << "[WARNING] tumor VCF chromosome count is empty" << std::endl;
+        if (nor.chr_names.empty()) return lpsh::fail("tumor & normal VCFs chromosome count are empty");
+        std::cerr << "[INFO] use normal VCF chromosome count" << std::endl;
+        job.chr_names = nor.chr_names;
+        job.chr_length = nor.chr_length;
+    } else {
+        job.chr_names = tum.chr_names;
+        job.chr_length = tum.chr_length;
+    }
+    for (auto &c : nor.records) for (auto &kv : c.second) { UnionVar &u = job.variants[c.first][kv.first]; u.has_nor = true; u.nor = kv.second; }
+    for (auto &c : tum.records) for (auto &kv : c.second) { UnionVar &u = job.variants[c.first][kv.first]; u.has_tum = true; u.tum = kv.second; }
+    int n_nor = 0, n_snp = 0, n_both = 0, n_ins = 0, n_del = 0;
+    for (const std::string &chr : job.chr_names)
+        for (const auto &kv : job.variants[chr]) {
+            const UnionVar &u = kv.second;
+            if (u.has_tum) { n_snp += is_snp(u.tum); n_ins += is_ins(u.tum); n_del += is_del(u.tum); }
+            n_nor += u.has_nor;
+            n_both += u.has_nor && u.has_tum;
+        }
+    std::cerr << "Normal SNP count: " << n_nor << "\nTumor SNP count: " << n_snp << "\nOverlap SNP count: " << n_both << "\nTumor Insert count: " << n_ins
+              << "\nTumor Delete count: " << n_del << std::endl;
+    if (!job.opt.region.empty()) {
+        const size_t colon = job.opt.region.find(':');
+        const std::string chr = colon != std::string::npos ? job.opt.region.substr(0, colon) : job.opt.region;
+        if (std::find(job.chr_names.begin(), job.chr_names.end(), chr) == job.chr_names.end()) {
+            std::cerr << "[ERROR] Incorrect chromosome for input region: " << chr << std::endl;
+            exit(1);
+        }
+        job.chr_names.assign(1, chr);
+    }
+    for (auto it = job.variants.begin(); it != job.variants.end();) {
+        if (std::find(job.chr_names.begin(), job.chr_names.end(), it->first) == job.chr_names.end()) it = job.variants.erase(it);
+        else ++it;
+    }
+    return 0;
+}
+
+// getLastVarPos for both genome samples + FastaParser (HaplotagParsingBam.cpp:333-373, ParsingBam.cpp:17-59)
+int load_som_reference(lpsh_som &job) {
+    faidx_t *fai = fai_load(job.opt.fasta.c_str());
+    if (!fai) return lpsh::fail("cannot load the FASTA index of " + job.opt.fasta);
+    for (const std::string &chr : job.chr_names) {
+        int last_nor = 0, last_any = 0;
+        const auto &vars = job.variants[chr];
+        if (!vars.empty()) last_any = vars.rbegin()->first;   // every entry holds a TUMOR record or a phased NORMAL record
+        for (auto it = vars.rbegin(); it != vars.rend(); ++it) if (it->second.has_nor) { last_nor = it->first; break; }
+        for (int pass = 0; pass < 2; pass++) {
+            int len = 0;
+            char *s = faidx_fetch_seq(fai, chr.c_str(), 0, (pass ? last_any : last_nor) + 5, &len);
+            if (len == 0) std::cout << "nothing in reference file \n";
+            (pass ? job.ref_tumor : job.ref_normal)[chr] = s ? s : "";
+            free(s);
+        }
+    }
+    fai_destroy(fai);
+    job.have_reference = true;
+    return 0;
+}
+
+// the union map of one contig as lps_variants (NORMAL side) + lps_tumor_variants
+void pack_union(lpsh_som &job, const std::string &chr, lpsh::PackedContig &pc, TumorArrays &t) {
+    pc.tagged_variants = true;
+    t = TumorArrays();
+    for (const auto &kv : job.variants[chr]) {
+        const UnionVar &u = kv.second;
+        const lpsh::SampleRecord &n = u.has_nor ? u.nor : u.tum;   // NORMAL columns of a tumor-only position are never read (nor_present = 0)
+        pc.add_variant(kv.first, n.ref, n.alt);
+        pc.v_hp1_is_alt.push_back(u.has_nor ? n.hp1_is_alt : 0);
+        pc.v_ps.push_back(u.has_nor ? n.ps : 0);
+        pc.v_gt_kind.push_back(1);
+        const lpsh::SampleRecord &m = u.has_tum ? u.tum : u.nor;
+        t.nor_present.push_back(u.has_nor); t.tum_present.push_back(u.has_tum);
+        t.ref0.push_back(m.ref.empty() ? 0 : (uint8_t)m.ref[0]); t.alt0.push_back(m.alt.empty() ? 0 : (uint8_t)m.alt[0]);
+        t.ref_len.push_back((uint16_t)std::min<size_t>(m.ref.size(), 65535)); t.alt_len.push_back((uint16_t)std::min<size_t>(m.alt.size(), 65535));
+        t.gt_kind.push_back(u.has_tum ? (uint8_t)u.tum.gt_kind : 0);
+        t.hp1_is_alt.push_back(u.has_tum ? u.tum.hp1_is_alt : 0);
+        t.ps.push_back(u.has_tum ? u.tum.ps : -1);
+        t.is_somatic.push_back(u.is_somatic); t.derive_hp.push_back(u.derive_hp);
+    }
+}
+
+std::string contig_region(const lpsh_som &job, const std::string &chr) {
+    return !job.opt.region.empty() ? job.opt.region : chr + ":1-" + std::to_string(job.chr_length.at(chr));
+}
+
+void finish_contig(lpsh_som &job) {
+    if (job.itr) hts_itr_destroy(job.itr);
+    job.itr = nullptr;
+    job.cur = -1;
+    job.chunk.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int lpsh_som_open(int argc, char **argv, lpsh_som **out) {
+    if (!out) return -1;
+    *out = nullptr;
+    lpsh_som *job = new lpsh_som();
+    const int rc = parse_som_options(argc, argv, job->opt);
+    if (rc != 0) { delete job; return rc; }
+    if (const char *e = getenv("LPS_TAG_CHUNK")) { const long v = atol(e); if (v > 0) job->chunk_reads = (size_t)v; }
+    som_banner(job->opt);
+    if (load_union(*job) != 0 || load_som_reference(*job) != 0) { delete job; return -1; }
+    job->contig.resize(job->chr_names.size());
+    memset(&job->purity_result, 0, sizeof(job->purity_result));
+    *out = job;
+    return 0;
+}
+
+int lpsh_som_n_contigs(const lpsh_som *h) { return h ? (int)h->chr_names.size() : 0; }
+const char *lpsh_som_contig_name(const lpsh_som *h, int i) {
+    return (h && i >= 0 && (size_t)i < h->chr_names.size()) ? h->chr_names[(size_t)i].c_str() : nullptr;
+}
+// pass 0 = the two extract passes (ParsingBamControl defaults: no mapping-quality filter), pass 1 = the tagging pass
+int lpsh_som_params(const lpsh_som *h, int pass, lps_tag_params *out) {
+    if (!h || !out) return -1;
+    memset(out, 0, sizeof(*out));
+    out->mapping_quality = h->opt.quality;
+    out->mapq_filter = pass ? 1 : 0;
+    out->tag_supplementary = h->opt.tag_supplementary;
+    out->have_reference = 1;
+    out->percentage_threshold = h->opt.percentage;
+    return 0;
+}
+
+// every alignment of contig i of the NORMAL (which = 0) or TUMOR (which = 1) BAM with the contig's union map
+int lpsh_som_pack(lpsh_som *h, int i, int which, lpsh_packed *out, lps_tumor_variants *tv) {
+    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size()) return -1;
+    const std::string &chr = h->chr_names[(size_t)i];
+    const std::string &path = which ? h->opt.tumor_bam : h->opt.bam;
+    h->pack = lpsh::PackedContig();
+    pack_union(*h, chr, h->pack, h->tum);
+    h->pack.ref = (which ? h->ref_tumor : h->ref_normal)[chr];
+    samFile *in = hts_open(path.c_str(), "r");
+    if (!in) return lpsh::fail("Cannot open bam file " + path);
+    hts_set_fai_filename(in, h->opt.fasta.c_str());
+    bam_hdr_t *hdr = sam_hdr_read(in);
+    hts_idx_t *idx = hdr ? sam_index_load(in, path.c_str()) : NULL;
+    if (!idx) { if (hdr) bam_hdr_destroy(hdr); sam_close(in); return lpsh::fail("Cannot open index for bam file " + path); }
+    htsThreadPool pool = {NULL, 0};
+    if (h->opt.threads > 1 && (pool.pool = hts_tpool_init(h->opt.threads))) hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool);
+    hts_itr_t *it = sam_itr_querys(idx, hdr, contig_region(*h, chr).c_str());
+    bam1_t *aln = bam_init1();
+    if (it) {
+        while (sam_itr_multi_next(in, it, aln) >= 0) h->pack.add_alignment(aln);
+        hts_itr_destroy(it);
+    }
+    bam_destroy1(aln);
+    hts_idx_destroy(idx);
+    bam_hdr_destroy(hdr);
+    sam_close(in);
+    if (pool.pool) hts_tpool_destroy(pool.pool);
+    h->pack.finish();
+    h->pack.view(out);
+    h->tum.view(tv);
+    return 0;
+}
+
+int lpsh_som_set_extract(lpsh_som *h, int i, int which, const lps_extract_result *r) {
+    if (!h || !r || i < 0 || (size_t)i >= h->contig.size()) return -1;
+    (which ? h->contig[(size_t)i].tumor : h->contig[(size_t)i].normal).assign(*r);
+    return 0;
+}
+
+// runTumorPurityEstimator (+ <prefix>_purity.out) or --tumor-purity, then the calling stage and getSomaticFlag for every contig
+int lpsh_som_call(lpsh_som *h) {
+    if (!h) return -1;
+    const SomOptions &o = h->opt;
+    const size_t nc = h->chr_names.size();
+    for (size_t c = 0; c < nc; c++)
+        if (!h->contig[c].normal.set || !h->contig[c].tumor.set) return lpsh::fail("extract results of contig " + h->chr_names[c] + " are missing");
+    // positions with a SomaticData entry = tumor slots a tumor alignment reached (the keys of chrPosSomaticInfo)
+    std::vector<std::vector<uint8_t>> touched(nc);
+    for (size_t c = 0; c < nc; c++) {
+        const ExtractCopy &T = h->contig[c].tumor;
+        const size_t nt = T.tum_var.size();
+        touched[c].assign(nt, 0);
+        for (size_t k = 0; k < nt; k++) {
+            int64_t hp_sum = 0;
+            for (int j = 0; j < 9; j++) hp_sum += T.read_hp_count[k * 9 + (size_t)j] + (T.somatic_read_hp_count.empty() ? 0 : T.somatic_read_hp_count[k * 9 + (size_t)j]);
+            touched[c][k] = T.pos_base[k * LPS_PB_FIELDS + LPS_PB_DEPTH] > 0 || hp_sum > 0;   // same test as lps_somatic_call's `touched`
+        }
+    }
+    if (o.estimate_purity) {
+        std::time_t t0 = time(NULL);
+        std::cerr << "estimating tumor purity ... ";
+        std::vector<double> t_imb, n_imb, n_pct;
+        std::vector<int32_t> n_h1, n_h2;
+        for (size_t c = 0; c < nc; c++) {
+            const ExtractCopy &N = h->contig[c].normal, &T = h->contig[c].tumor;
+            if (N.tum_var.size() != T.tum_var.size()) return lpsh::fail("normal and tumor extract results of " + h->chr_names[c] + " differ in size");
+            for (size_t k = 0; k < T.tum_var.size(); k++) {
+                if (!touched[c][k]) continue;
+                t_imb.push_back(T.ratios_d[k * LPS_RD_FIELDS + LPS_RD_GERMLINE_IMBALANCE]);
+                n_imb.push_back(N.ratios_d[k * LPS_RD_FIELDS + LPS_RD_GERMLINE_IMBALANCE]);
+                n_pct.push_back(N.ratios_d[k * LPS_RD_FIELDS + LPS_RD_PCT_GERMLINE_HP]);
+                n_h1.push_back(N.read_hp_count[k * 9 + 1]);
+                n_h2.push_back(N.read_hp_count[k * 9 + 2]);
+            }
+        }
+        lps_purity_input in;
+        memset(&in, 0, sizeof(in));
+        in.n = (int32_t)t_imb.size();
+        in.tumor_germline_imbalance = t_imb.data(); in.normal_germline_imbalance = n_imb.data(); in.normal_pct_germline_hp = n_pct.data();
+        in.normal_h1 = n_h1.data(); in.normal_h2 = n_h2.data();
+        lps_purity_result &r = h->purity_result;
+        if (lps_estimate_purity(&in, &r) != 0) return lpsh::fail("lps_estimate_purity failed");
+        if (r.ok) {
+            std::cerr << difftime(time(NULL), t0) << "s\n";
+            std::ofstream f((o.prefix + "_purity.out").c_str());   // TumorPurityEstimator::writePurityResult (:375-424)
+            if (!f.is_open()) std::cerr << "[ERROR] :Failed to open purity log file: " << o.prefix << "_purity.out\n[ERROR] : Failed to write purity log" << std::endl;
+            else {
+                f << "#==================================\n# TUMOR PURITY ESTIMATION REPORT\n#==================================\n";
+                f << "#Initial data size: " << in.n << std::endl;
+                f << "#==========filter parameters==========" << std::endl;
+                f << "#GERMLINE_HP_IMBALANCE_RATIO_MIN_THR: " << 0.0f << std::endl << "#GERMLINE_HP_IMBALANCE_RATIO_IN_NOR_BAM_MIN_THR: " << 0.0f << std::endl;
+                f << "#GERMLINE_HP_IMBALANCE_RATIO_IN_NOR_BAM_MAX_THR: " << 0.7f << std::endl << "#GERMLINE_HP_PERCENTAGE_IN_NOR_BAM_MAX_THR: " << 0.7f << std::endl;
+                f << "#GERMLINE_HP_READ_COUNT_IN_NOR_BAM_MIN_THR: " << 5 << std::endl << "#GERMLINE_HP_READ_COUNT_IN_NOR_BAM_DYNAMIC_THR: " << r.read_count_threshold << std::endl;
+                f << "#==========Initial filter out data count==========" << std::endl;
+                f << "#imbalanceRatioInNorBam: " << r.filtered_normal_imbalance_zero << std::endl << "#imbalanceRatio: " << r.filtered_tumor_imbalance_zero << std::endl;
+                f << "#imbalanceRatioInNorBam_over_thr: " << r.filtered_normal_imbalance_high << std::endl << "#readHpCountInNorBam: " << r.filtered_normal_read_count << std::endl;
+                f << "#percentageOfGermlineHpInNorBam: " << r.filtered_pct_germline_hp << std::endl;
+                f << "#==========Second filter out data count==========" << std::endl << "#peakValley count: " << r.filtered_valley << std::endl;
+                f << "#==========Whisker filter out data count==========" << std::endl << "#iteration times: " << 1 << std::endl;
+                f << "#remove outliers: " << r.filtered_outliers << std::endl << "#==========Statistical analysis===========" << std::endl;
+                f << "Data size: " << r.n_used << std::endl << "Median: " << r.median << std::endl << "Q1: " << r.q1 << std::endl << "Q3: " << r.q3 << std::endl;
+                f << "IQR: " << r.iqr << std::endl << "Whiskers: " << r.lower_whisker << " to " << r.upper_whisker << std::endl;
+                f << "Outliers: " << r.n_outliers_left << std::endl << "#==========Estimation result===========" << std::endl;
+                f << "Tumor purity: " << r.purity << std::endl;
+            }
+        } else {
+            std::cerr << "[ERROR] Failed to estimate tumor purity, set purity to 0.0" << std::endl;
+        }
+        h->purity = r.purity;
+    } else {
+        h->purity = o.purity;
+    }
+    std::time_t t0 = time(NULL);
+    std::cerr << "calling somatic variants ... ";
+    int failed = 0;
+    h->n_somatic = 0;
+#pragma omp parallel for schedule(dynamic) num_threads(o.threads)
+    for (int c = 0; c < (int)nc; c++) {
+        const std::string &chr = h->chr_names[(size_t)c];
+        ExtractCopy &N = h->contig[(size_t)c].normal, &T = h->contig[(size_t)c].tumor;
+        const size_t nt = T.tum_var.size();
+        std::vector<int32_t> pos(nt);
+        std::vector<uint8_t> callable(nt), is_somatic(nt, 0);
+        std::vector<int8_t> derive(nt, 0);
+        std::vector<std::map<int, UnionVar>::iterator> slot(nt);
+        auto &vars = h->variants[chr];
+        {
+            size_t k = 0;
+            for (auto it = vars.begin(); it != vars.end(); ++it)
+                if (it->second.has_tum && k < nt) {
+                    pos[k] = it->first;
+                    callable[k] = is_snp(it->second.tum) || is_ins(it->second.tum) || is_del(it->second.tum);
+                    slot[k++] = it;
+                }
+            if (k != nt) {
+#pragma omp critical
+                { lpsh::fail("tumor slots of " + chr + " do not match the union map"); failed = 1; }
+                continue;
+            }
+        }
+        const lps_extract_result rn = N.view(), rt = T.view();
+        lps_somatic_call_input in;
+        memset(&in, 0, sizeof(in));
+        in.n_tum = (int32_t)nt; in.pos = pos.data(); in.callable = callable.data(); in.normal = &rn; in.tumor = &rt;
+        in.purity = h->purity; in.enable_filter = o.enable_filter; in.percentage_threshold = o.percentage;
+        lps_somatic_call_result out;
+        memset(&out, 0, sizeof(out));
+        out.is_somatic = is_somatic.data(); out.derive_hp = derive.data();
+        const int rc = nt ? lps_somatic_call(&in, &out) : 0;
+        if (rc != 0) {
+#pragma omp critical
+            { lpsh::fail("somatic calling failed on " + chr + (rc == LPS_E_DATA ? ": a tumor position without any read record (the reference exits here)" : "")); failed = 1; }
+            continue;
+        }
+        for (size_t k = 0; k < nt; k++) { slot[k]->second.is_somatic = is_somatic[k]; slot[k]->second.derive_hp = derive[k]; }   // getSomaticFlag
+#pragma omp critical
+        h->n_somatic += nt ? out.n_somatic : 0;
+    }
+    std::cerr << difftime(time(NULL), t0) << "s\n";
+    return failed ? -1 : 0;
+}
+
+double lpsh_som_purity(const lpsh_som *h) { return h ? h->purity : 0.0; }
+int64_t lpsh_som_n_somatic(const lpsh_som *h) { return h ? h->n_somatic : 0; }
+
+int lpsh_som_tag_begin(lpsh_som *h) {
+    if (!h) return -1;
+    const SomOptions &o = h->opt;
+    if (!(h->pool.pool = hts_tpool_init(o.threads))) return lpsh::fail("Error creating thread pool");
+    h->in = hts_open(o.tumor_bam.c_str(), "r");
+    if (!h->in) return lpsh::fail("Cannot open bam file " + o.tumor_bam);
+    if (hts_set_fai_filename(h->in, o.fasta.c_str()) != 0) return lpsh::fail("Cannot set FASTA index file for " + o.fasta);
+    h->hdr = sam_hdr_read(h->in);
+    if (!h->hdr) return lpsh::fail("Cannot read header from bam file " + o.tumor_bam);
+    sam_hdr_add_pg(h->hdr, "longphase-s", "VN", lpsh::REFERENCE_VERSION, "CL", o.command.c_str(), NULL);
+    h->idx = sam_index_load(h->in, o.tumor_bam.c_str());
+    if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.tumor_bam);
+    if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.tumor_bam);
+    const std::string out_path = o.prefix + ".bam";
+    h->out = hts_open(out_path.c_str(), "wb");
+    if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
+    hts_set_fai_filename(h->out, o.fasta.c_str());
+    if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);
+    if (hts_set_opt(h->out, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for output bam file " + out_path);
+    return 0;
+}
+
+// next chunk of contig i of the tumor BAM with the union map carrying the caller's flags: 1 = ready, 0 = exhausted, < 0 error
+int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv) {
+    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    const std::string &chr = h->chr_names[(size_t)i];
+    if (h->cur != i) {
+        finish_contig(*h);
+        h->cur = i;
+        h->itr_done = false;
+        h->itr = sam_itr_querys(h->idx, h->hdr, contig_region(*h, chr).c_str());
+        if (!h->itr) h->itr_done = true;
+    }
+    h->chunk.clear();
+    lpsh::PackedContig &pc = h->chunk.pack;
+    pack_union(*h, chr, pc, h->tum);
+    pc.ref = h->ref_tumor[chr];
+    while (!h->itr_done && h->chunk.records.size() < h->chunk_reads) {
+        bam1_t *b = bam_init1();
+        if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
+        pc.add_alignment(b);
+        h->chunk.records.push_back(b);
+    }
+    if (h->chunk.records.empty()) { finish_contig(*h); h->cur = i; h->itr_done = true; return 0; }
+    pc.finish();
+    pc.view(out);
+    h->tum.view(tv);
+    return 1;
+}
+
+// SomaticHaplotagChrProcessor: processRead's tag handling + addAuxiliaryTags (HaplotagProcess.cpp:318-355, SomaticHaplotagProcess.cpp:464-472)
+int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r) {
+    if (!h || !r || h->cur != i || !h->out) return -1;
+    lpsh::Chunk &ck = h->chunk;
+    const size_t n = ck.records.size();
+    if ((size_t)r->reads.n_reads != n) return lpsh::fail("verdict count does not match the chunk");
+    for (size_t k = 0; k < n; k++) {
+        bam1_t *b = ck.records[k];
+        if (r->reads.category[k] == LPS_TAG_PROCESSED) {
+            lpsh::drop_aux(b, "HP");
+            lpsh::drop_aux(b, "PS");
+            lpsh::drop_aux(b, "PQ");
+            const int hp = r->reads.read_hp[k];
+            if (hp != 0) {
+                if (hp < 0 || hp >= LPS_READHP_FIELDS) return lpsh::fail("read haplotype out of range");
+                const char *text = READ_HP_TEXT[hp];
+                int ps = r->reads.ps[k], pq = r->reads.pq[k];
+                bam_aux_append(b, "HP", 'Z', (int)strlen(text) + 1, (const uint8_t *)text);
+                if (ps != -1) bam_aux_append(b, "PS", 'i', sizeof(int), (uint8_t *)&ps);
+                bam_aux_append(b, "PQ", 'i', sizeof(int), (uint8_t *)&pq);
+            }
+        }
+        if (sam_write1(h->out, h->hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+    }
+    // ReadStatistics arrive reduced over the chunk
+    h->st_alignment += r->total_alignment; h->st_supplementary += r->total_supplementary; h->st_secondary += r->total_secondary;
+    h->st_unmapped += r->total_unmapped; h->st_tag += r->total_tag; h->st_untag += r->total_untag; h->st_low += r->total_lower_quality;
+    h->st_other += r->total_other_case; h->st_empty += r->total_empty_variant; h->st_similar += r->total_high_similarity;
+    h->st_cross += r->total_cross_two_block; h->st_no_variant += r->total_without_variant; h->st_only_h3 += r->total_read_only_h3;
+    for (int k = 0; k < LPS_READHP_FIELDS; k++) h->st_hp[k] += r->total_hp[k];
+    ck.clear();
+    return 0;
+}
+
+int lpsh_som_tag_end(lpsh_som *h) {
+    if (!h) return -1;
+    finish_contig(*h);
+    if (h->idx) hts_idx_destroy(h->idx);
+    if (h->hdr) bam_hdr_destroy(h->hdr);
+    if (h->in) sam_close(h->in);
+    int rc = 0;
+    if (h->out && sam_close(h->out) < 0) rc = lpsh::fail("closing the output bam failed");
+    h->idx = nullptr; h->hdr = nullptr; h->in = nullptr; h->out = nullptr;
+    if (h->pool.pool) hts_tpool_destroy(h->pool.pool);
+    h->pool.pool = NULL;
+    std::ostream &e = std::cerr;   // HaplotagProcess::printExecutionReport (HaplotagProcess.cpp:152-175)
+    e << "-------------------------------------------\n";
+    e << "total process time        : " << difftime(time(NULL), h->t_begin) << "s\n";
+    e << "total alignment           : " << h->st_alignment << "\ntotal supplementary       : " << h->st_supplementary << "\n";
+    e << "total secondary           : " << h->st_secondary << "\ntotal unmapped            : " << h->st_unmapped << "\n";
+    e << "total tagged alignments   : " << h->st_tag << "\n    L----total HP1        : " << h->st_hp[1] << "\n    L----total HP2        : " << h->st_hp[2] << "\n";
+    e << "    L----total HP1-1      : " << h->st_hp[5] << "\n    L----total HP2-1      : " << h->st_hp[7] << "\n    L----total HP3        : " << h->st_hp[3] << "\n";
+    e << "         L----only H3 SNP : " << h->st_only_h3 << "\n";
+    e << "total untagged            : " << h->st_untag << "\n    L----lower mapping quality        : " << h->st_low << "\n";
+    e << "    L----no variant                   : " << h->st_empty << "\n    L----start pos > last variant pos : " << h->st_other << "\n";
+    e << "    L----judge to untag               : " << h->st_hp[0] << "\n         L----high similarity         : " << h->st_similar << "\n";
+    e << "         L----cross two block         : " << h->st_cross << "\n         L----no variant judge HP     : " << h->st_no_variant << "\n";
+    e << "-------------------------------------------\n";
+    return rc;
+}
+
+int lpsh_som_run(lpsh_som *h) {
+    if (!h) return -1;
+    lps_ctx *ctx = nullptr;
+    if (lps_ctx_create(0, &ctx) != 0) return lpsh::fail("no usable CUDA device (there is no CPU fallback)");
+    lps_tag_params xp, tp;
+    lpsh_som_params(h, 0, &xp);
+    lpsh_som_params(h, 1, &tp);
+    int rc = 0;
+    const int nc = (int)h->chr_names.size();
+    // SomaticVarCaller::extractSomaticData: the NORMAL BAM, then the TUMOR BAM (SomaticVarCaller.cpp:907-935)
+    for (int which = 0; which < 2 && rc == 0; which++) {
+        std::time_t t0 = time(NULL);
+        std::cerr << (which ? "extracting data from tumor BAM ... " : "extracting data from normal BAM ... ");
+        for (int i = 0; i < nc && rc == 0; i++) {
+            lpsh_packed v;
+            lps_tumor_variants tv;
+            if (lpsh_som_pack(h, i, which, &v, &tv) != 0) { rc = -1; break; }
+            lps_extract_result r;
+            if (v.variants.n == 0) {      // a contig without any variant: nothing reaches the parsers (processEmptyVariants)
+                memset(&r, 0, sizeof(r));
+            } else {
+                rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
+                if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, 0);
+                if (rc == 0) rc = lps_contig_set_tumor_variants(ctx, &tv);
+                if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);
+                if (rc == 0) rc = which ? lps_extract_tumor(ctx, &xp, &r) : lps_extract_normal(ctx, &xp, &r);
+                if (rc != 0) { lpsh::fail(std::string("contig ") + h->chr_names[(size_t)i] + ": " + lps_last_error(ctx)); break; }
+            }
+            lpsh_som_set_extract(h, i, which, &r);
+        }
+        std::cerr << difftime(time(NULL), t0) << "s\n";
+    }
+    h->pack = lpsh::PackedContig();
+    if (rc == 0) rc = lpsh_som_call(h);
+    if (rc == 0) rc = lpsh_som_tag_begin(h);
+    std::time_t t0 = time(NULL);
+    std::cerr << "somatic tagging start ...\n";
+    for (int i = 0; i < nc && rc == 0; i++) {
+        const std::string &chr = h->chr_names[(size_t)i];
+        std::time_t c0 = time(NULL);
+        std::cerr << "chr: " << chr << " ... ";
+        bool table_set = false;
+        lpsh_packed v;
+        lps_tumor_variants tv;
+        for (int got; rc == 0 && (got = lpsh_som_tag_pack(h, i, &v, &tv)) != 0;) {
+            if (got < 0) { rc = -1; break; }
+            lps_somatic_tag_result r;
+            std::vector<uint8_t> cat;
+            std::vector<int8_t> hp;
+            std::vector<int32_t> zero;
+            if (v.variants.n == 0) {      // dispatch without variants: MAPQ and flags only (HaplotagParsingBam.cpp:457-476)
+                const int n = v.batch.n_reads;
+                cat.resize((size_t)n); hp.assign((size_t)n, 0); zero.assign((size_t)n, 0);
+                memset(&r, 0, sizeof(r));
+                for (int k = 0; k < n; k++) {
+                    const int flag = v.batch.flag[k];
+                    cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
+                                     : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
+                                     : LPS_TAG_EMPTY_VARIANTS;
+                    r.total_alignment++; r.total_untag++;
+                    if (cat[(size_t)k] == LPS_TAG_LOW_MAPQ) r.total_lower_quality++;
+                    else if (cat[(size_t)k] == LPS_TAG_UNMAPPED) r.total_unmapped++;
+                    else if (cat[(size_t)k] == LPS_TAG_SECONDARY) r.total_secondary++;
+                    else if (cat[(size_t)k] == LPS_TAG_SUPPLEMENTARY) r.total_supplementary++;
+                    else r.total_empty_variant++;
+                }
+                r.reads.n_reads = n; r.reads.category = cat.data(); r.reads.read_hp = hp.data(); r.reads.ps = zero.data(); r.reads.pq = zero.data();
+            } else {
+                if (!table_set) {
+                    rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
+                    if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, 0);
+                    if (rc == 0) rc = lps_contig_set_tumor_variants(ctx, &tv);
+                    table_set = true;
+                }
+                if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);
+                if (rc == 0) rc = lps_somatic_tag_reads(ctx, &tp, 0, &r);
+                if (rc != 0) { lpsh::fail(std::string("contig ") + chr + ": " + lps_last_error(ctx)); break; }
+            }
+            rc = lpsh_som_tag_emit(h, i, &r);
+        }
+        std::cerr << difftime(time(NULL), c0) << "s\n";
+    }
+    lps_ctx_destroy(ctx);
+    std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
+    const int rc_end = lpsh_som_tag_end(h);
+    return rc != 0 ? -1 : rc_end;
+}
+
+void lpsh_som_close(lpsh_som *h) {
+    if (!h) return;
+    if (h->in || h->out) lpsh_som_tag_end(h);
+    delete h;
+}
+
+int lpsh_som_main(int argc, char **argv) {
+    lpsh_som *job = nullptr;
+    const int rc = lpsh_som_open(argc, argv, &job);
+    if (rc == 2) return 0;
+    if (rc != 0) { if (rc < 0) std::cerr << "[ERROR] somatic_haplotag: " << lpsh_last_error() << "\n"; return 1; }
+    const int run = lpsh_som_run(job);
+    if (run != 0) std::cerr << "[ERROR] somatic_haplotag: " << lpsh_last_error() << "\n";
+    lpsh_som_close(job);
+    return run != 0 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -207,10 +207,65 @@ def write_dataset(d, contigs, with_ps=False, gz=False, fast_bam=False):
 
 
 def bam_payload(path):
-    """The uncompressed byte stream of a BAM file (BGZF = concatenated gzip members)."""
+    """The uncompressed byte stream of a BAM file, BGZF member by member (BSIZE at offset 16 of each member's header;
+    gzip.decompress on the whole file is quadratic in the number of members)."""
+    import zlib
     with open(path, "rb") as f:
-        return gzip.decompress(f.read())
+        data = f.read()
+    out, pos, view = [], 0, memoryview(data)
+    while pos < len(data):
+        assert data[pos:pos + 4] == b"\x1f\x8b\x08\x04" and data[pos + 12:pos + 14] == b"BC", "not a BGZF member"
+        size = int.from_bytes(data[pos + 16:pos + 18], "little") + 1
+        out.append(zlib.decompress(view[pos + 18:pos + size - 8], -15))
+        pos += size
+    return b"".join(out)
 
 
 def strip_commandline(text):
     return "\n".join(ln for ln in text.split("\n") if not ln.startswith("##commandline="))
+
+
+# ---- tumor / normal pair on disk (somatic_haplotag) -----------------------------------------------------------------------
+def _vcf_header(f, contigs, with_ps):
+    f.write("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n")
+    for name, ref_len in contigs:
+        f.write("##contig=<ID=%s,length=%d>\n" % (name, ref_len))
+    f.write("##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n")
+    if with_ps:
+        f.write("##FORMAT=<ID=PS,Number=1,Type=Integer,Description=\"Phase set identifier\">\n")
+    f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n")
+
+
+def write_somatic_dataset(d, pairs, seed=9):
+    """pairs: list of (name, normal synth.Contig, tumor synth.Contig) generated from the same seed (same reference and variants).
+    Writes ref.fa, normal.bam, tumor.bam, germline.vcf (unphased heterozygous germline variants, to be phased by `phase`) and
+    tumor.vcf (every somatic variant as 0/1, a share of the germline ones as 0/1, 1/1 or phased).  Returns the paths."""
+    rng = np.random.default_rng(seed)
+    out = {k: os.path.join(d, v) for k, v in dict(fasta="ref.fa", normal_bam="normal.bam", tumor_bam="tumor.bam", germline_vcf="germline.vcf",
+                                                  tumor_vcf="tumor.vcf").items()}
+    with open(out["fasta"], "w") as f:
+        for name, cn, _ in pairs:
+            s = cn.ref.decode()
+            f.write(">%s\n" % name + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+    write_bam_fast(out["normal_bam"], [(name, cn, True) for name, cn, _ in pairs], threads=4)
+    write_bam_fast(out["tumor_bam"], [(name, ct, True) for name, _, ct in pairs], threads=4)
+    lens = [(name, len(cn.ref)) for name, cn, _ in pairs]
+    with open(out["germline_vcf"], "w") as g, open(out["tumor_vcf"], "w") as t:
+        _vcf_header(g, lens, False)
+        _vcf_header(t, lens, True)
+        for name, cn, _ in pairs:
+            for i in range(cn.n_var):
+                pos = int(cn.var_pos[i]) + 1
+                ref, alt = cn.variant_strings(i)
+                if cn.var_is_somatic[i]:
+                    t.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:DP\t0/1:%d\n" % (name, pos, ref, alt, 30 + i % 7))
+                    continue
+                g.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:DP\t%s:%d\n" % (name, pos, ref, alt, "0/1" if i % 2 else "1/0", 25 + i % 5))
+                u = rng.random()
+                if u < 0.05:
+                    t.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:DP\t0/1:%d\n" % (name, pos, ref, alt, 30 + i % 7))
+                elif u < 0.10:
+                    t.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:DP\t1/1:%d\n" % (name, pos, ref, alt, 30 + i % 7))
+                elif u < 0.13:
+                    t.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:PS:DP\t%s:%d:%d\n" % (name, pos, ref, alt, "0|1" if i % 2 else "1|0", 5000 + i // 30, 30))
+    return out
