@@ -79,9 +79,10 @@ struct lpsh_tag {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
-    lpsh::Chunk chunk;
-    std::vector<int32_t> cur_pos, cur_ps;             // variant table of the contig in flight
-    size_t chunk_reads = 65536;
+    lpsh::Chunk chunk;                                // the chunk of the staged API (lpsh_tag_pack / lpsh_tag_emit)
+    int chunk_contig = -1;
+    size_t chunk_reads = 8192;                        // records per device call; small enough for htslib's asynchronous
+                                                      // BGZF decode / encode to stay busy around it (LPS_TAG_CHUNK overrides)
     // ReadStatistics (HaplotagProcess.h:21-45)
     int64_t st_alignment = 0, st_supplementary = 0, st_secondary = 0, st_unmapped = 0, st_tag = 0, st_untag = 0, st_low = 0,
             st_other = 0, st_empty = 0, st_similar = 0, st_no_variant = 0, st_hp[3] = {0, 0, 0};
@@ -189,6 +190,7 @@ void finish_contig(lpsh_tag &job) {
     if (job.itr) hts_itr_destroy(job.itr);
     job.itr = nullptr;
     job.cur = -1;
+    job.chunk_contig = -1;
     job.chunk.clear();
 }
 
@@ -264,47 +266,56 @@ int lpsh_tag_begin(lpsh_tag *h) {
     return 0;
 }
 
-// next chunk of contig i: 1 = a chunk is packed, 0 = the contig is exhausted, < 0 error
-int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
-    if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+// next chunk of contig i into `ck`: 1 = filled, 0 = the contig is exhausted, < 0 error
+static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
     const std::string &chr = h->chr_names[(size_t)i];
     if (h->cur != i) {
-        finish_contig(*h);
+        if (h->itr) hts_itr_destroy(h->itr);
         h->cur = i;
         h->itr_done = false;
         const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
         h->itr = sam_itr_querys(h->idx, h->hdr, region.c_str());
         if (!h->itr) h->itr_done = true;
-        h->cur_pos.clear();
-        h->cur_ps.clear();
-        for (const auto &kv : h->variants[chr]) { h->cur_pos.push_back(kv.first); h->cur_ps.push_back(kv.second.ps); }
     }
-    h->chunk.clear();
-    lpsh::PackedContig &pc = h->chunk.pack;
+    ck.clear();
+    lpsh::PackedContig &pc = ck.pack;
     pc.tagged_variants = true;
-    for (const auto &kv : h->variants[chr]) {
-        const lpsh::SampleRecord &v = kv.second;
-        pc.add_variant(kv.first, v.ref, v.alt);
-        pc.v_hp1_is_alt.push_back(v.hp1_is_alt);
-        pc.v_ps.push_back(v.ps);
-        pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
-    }
+    auto vars = h->variants.find(chr);
+    if (vars != h->variants.end())
+        for (const auto &kv : vars->second) {
+            const lpsh::SampleRecord &v = kv.second;
+            pc.add_variant(kv.first, v.ref, v.alt);
+            pc.v_hp1_is_alt.push_back(v.hp1_is_alt);
+            pc.v_ps.push_back(v.ps);
+            pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
+        }
     pc.ref = h->reference[chr];
-    while (!h->itr_done && h->chunk.records.size() < h->chunk_reads) {
+    while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
         pc.add_alignment(b);
-        h->chunk.records.push_back(b);
+        ck.records.push_back(b);
     }
-    if (h->chunk.records.empty()) { finish_contig(*h); h->cur = i; h->itr_done = true; return 0; }
+    if (ck.records.empty()) { ck.clear(); return 0; }
     pc.finish();
-    pc.view(out);
     return 1;
 }
 
+int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
+    if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    const int got = read_chunk(h, i, h->chunk);
+    if (got == 1) { h->chunk.pack.view(out); h->chunk_contig = i; }
+    return got;
+}
+
+static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result *r);
+
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
-    if (!h || !r || h->cur != i || !h->out) return -1;
-    lpsh::Chunk &ck = h->chunk;
+    if (!h || !r || h->chunk_contig != i || !h->out) return -1;
+    return emit_chunk(h, i, h->chunk, r);
+}
+
+static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result *r) {
     const size_t n = ck.records.size();
     if ((size_t)r->n_reads != n) return lpsh::fail("verdict count does not match the chunk");
     const bool want_log = h->log.is_open();
@@ -336,8 +347,8 @@ int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
                 std::map<int, int> variants_hp, count_ps;
                 for (uint64_t c = r->call_off[k]; c < r->call_off[k + 1]; c++) {
                     const lps_call &cl = r->calls[c];
-                    if (cl.allele >= 0) variants_hp[h->cur_pos[(size_t)cl.var]] = cl.allele;
-                    count_ps[h->cur_ps[(size_t)cl.var]]++;
+                    if (cl.allele >= 0) variants_hp[ck.pack.v_pos[(size_t)cl.var]] = cl.allele;
+                    count_ps[ck.pack.v_ps[(size_t)cl.var]]++;
                 }
                 h->log << bam_get_qname(b) << "\t" << chr << "\t" << b->core.pos << "\t" << (mx / (mx + mn)) << "\tH"
                        << (hp == 0 ? std::string(".") : std::to_string(hp)) << "\t"
@@ -395,61 +406,81 @@ int lpsh_tag_end(lpsh_tag *h) {
     return rc;
 }
 
-int lpsh_tag_run(lpsh_tag *h) {
-    if (!h) return -1;
+// The tagging pass with any judge: reader thread (htslib parsing + packing) | calling thread (judge, tags, sam_write1).
+int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
+    if (!h || !judge) return -1;
     if (lpsh_tag_begin(h) != 0) return -1;
-    lps_ctx *ctx = nullptr;
-    if (lps_ctx_create(0, &ctx) != 0) return lpsh::fail("no usable CUDA device (there is no CPU fallback)");
     lps_tag_params tp;
     lpsh_tag_params(h, &tp);
     std::time_t t0 = time(NULL);
     std::cerr << "tag read start ...\n";
-    int rc = 0;
-    for (int i = 0; i < (int)h->chr_names.size() && rc == 0; i++) {
-        const std::string &chr = h->chr_names[(size_t)i];
-        std::time_t c0 = time(NULL);
-        std::cerr << "chr: " << chr << " ... ";
-        const bool empty = h->variants.find(chr) == h->variants.end() || h->variants[chr].empty();
-        bool table_set = false;
+    auto handle = [&](int i, lpsh::Chunk &ck) -> int {
         lpsh_packed v;
-        for (int got; rc == 0 && (got = lpsh_tag_pack(h, i, &v)) != 0;) {
-            if (got < 0) { rc = -1; break; }
-            if (empty) {
-                // a contig without variants never reaches the tagger: the dispatch of processSingleChrom (HaplotagParsingBam.cpp:457-476)
-                // only looks at MAPQ and flags, so no device work exists for these records
-                const int n = v.batch.n_reads;
-                std::vector<uint8_t> cat((size_t)n);
-                std::vector<int8_t> hp((size_t)n, 0);
-                std::vector<int32_t> zero((size_t)n, 0);
-                for (int k = 0; k < n; k++) {
-                    const int flag = v.batch.flag[k];
-                    cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
-                                     : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
-                                     : LPS_TAG_EMPTY_VARIANTS;
-                }
-                lps_tag_result r;
-                memset(&r, 0, sizeof(r));
-                r.n_reads = n; r.category = cat.data(); r.hp = hp.data(); r.ps = zero.data(); r.pq = zero.data(); r.h1 = zero.data(); r.h2 = zero.data();
-                rc = lpsh_tag_emit(h, i, &r);
-                continue;
+        ck.pack.view(&v);
+        lps_tag_result r;
+        memset(&r, 0, sizeof(r));
+        std::vector<uint8_t> cat;
+        std::vector<int8_t> hp;
+        std::vector<int32_t> zero;
+        if (v.variants.n == 0) {
+            // a contig without variants never reaches the tagger: the dispatch of processSingleChrom (HaplotagParsingBam.cpp:457-476)
+            // only looks at MAPQ and flags, so no device work exists for these records
+            const int n = v.batch.n_reads;
+            cat.resize((size_t)n); hp.assign((size_t)n, 0); zero.assign((size_t)n, 0);
+            for (int k = 0; k < n; k++) {
+                const int flag = v.batch.flag[k];
+                cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
+                                 : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
+                                 : LPS_TAG_EMPTY_VARIANTS;
             }
-            if (!table_set) {
-                rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
-                if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, 0);
-                table_set = true;
-            }
-            lps_tag_result r;
-            if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);
-            if (rc == 0) rc = lps_tag_reads(ctx, &tp, h->opt.log ? 1 : 0, &r);
-            if (rc != 0) { lpsh::fail(std::string("contig ") + chr + ": " + lps_last_error(ctx)); break; }
-            rc = lpsh_tag_emit(h, i, &r);
+            r.n_reads = n; r.category = cat.data(); r.hp = hp.data(); r.ps = zero.data(); r.pq = zero.data(); r.h1 = zero.data(); r.h2 = zero.data();
+        } else if (judge(user, i, &v, h->opt.log ? 1 : 0, &r) != 0) {
+            return lpsh::fail(std::string("contig ") + h->chr_names[(size_t)i] + ": the judge failed");
         }
-        std::cerr << difftime(time(NULL), c0) << "s\n";
-    }
-    lps_ctx_destroy(ctx);
+        return emit_chunk(h, i, ck, &r);
+    };
+    const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) { return read_chunk(h, i, ck); }, handle);
     std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
     const int rc_end = lpsh_tag_end(h);
     return rc != 0 ? -1 : rc_end;
+}
+
+namespace {
+// the device as judge: lps_tag_reads on the chunk; the contig's tables are set when the contig changes
+struct DeviceJudge {
+    lps_ctx *ctx = nullptr;
+    lps_tag_params tp;
+    int contig = -1;
+    std::thread warm;
+    std::string error;
+};
+int device_judge(void *user, int contig, const lpsh_packed *v, int want_calls, lps_tag_result *out) {
+    DeviceJudge *d = (DeviceJudge *)user;
+    if (!d->ctx) {
+        if (d->warm.joinable()) d->warm.join();
+        if (lps_ctx_create(0, &d->ctx) != 0) { d->error = "no usable CUDA device (there is no CPU fallback)"; return -1; }
+    }
+    int rc = 0;
+    if (d->contig != contig) {
+        rc = lps_contig_set_reference(d->ctx, v->ref, v->ref_len);
+        if (rc == 0) rc = lps_contig_set_variants(d->ctx, &v->variants, 0);
+        d->contig = contig;
+    }
+    if (rc == 0) rc = lps_batch_submit(d->ctx, &v->batch);
+    if (rc == 0) rc = lps_tag_reads(d->ctx, &d->tp, want_calls, out);
+    if (rc != 0) d->error = lps_last_error(d->ctx);
+    return rc;
+}
+}  // namespace
+
+int lpsh_tag_run(lpsh_tag *h) {
+    if (!h) return -1;
+    DeviceJudge d;   // no device -> the first chunk fails with "no usable CUDA device"; nothing is ever judged on the host
+    lpsh_tag_params(h, &d.tp);
+    const int rc = lpsh_tag_run_with(h, device_judge, &d);
+    if (rc != 0 && !d.error.empty()) lpsh::fail(d.error);
+    if (d.ctx) lps_ctx_destroy(d.ctx);
+    return rc;
 }
 
 void lpsh_tag_close(lpsh_tag *h) {
@@ -459,6 +490,8 @@ void lpsh_tag_close(lpsh_tag *h) {
 }
 
 int lpsh_tag_main(int argc, char **argv) {
+    std::thread warm = lpsh::warm_up_device();   // the driver starts while the VCF and the FASTA are read
+    struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_warm{warm};
     lpsh_tag *job = nullptr;
     const int rc = lpsh_tag_open(argc, argv, &job);
     if (rc == 2) return 0;

@@ -29,6 +29,13 @@ bool read_gz(const std::string &path, std::string &text) {
     return true;
 }
 
+std::thread warm_up_device() {
+    return std::thread([] {
+        lps_ctx *c = nullptr;
+        if (lps_ctx_create(0, &c) == 0) lps_ctx_destroy(c);
+    });
+}
+
 int device_count() {
     int n = 0;
     for (; n < 64; n++) {

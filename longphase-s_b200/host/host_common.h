@@ -9,7 +9,10 @@
 #include <htslib/vcf.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
+#include <mutex>
+#include <thread>
 #include <fstream>
 #include <functional>
 #include <iterator>
@@ -157,6 +160,66 @@ struct Chunk {
         pack = PackedContig();
     }
 };
+
+// ---- reader / handler pipeline of a tagging pass -------------------------------------------------------------------------
+// One thread reads and packs chunk after chunk (htslib record parsing + SoA copies) while the calling thread judges the previous
+// chunk on the device, tags its records and writes them; at most `depth` finished chunks wait in between.  Chunks are handled
+// strictly in the order they were read, so the output file is the byte stream of the serial loop.
+//   read(contig, chunk)   -> 1 chunk filled, 0 contig exhausted, < 0 error      (reader thread only)
+//   handle(contig, chunk) -> 0 or < 0 error                                     (calling thread only)
+template <class ReadFn, class HandleFn>
+int run_chunk_pipeline(int n_contigs, ReadFn read, HandleFn handle, size_t depth = 2) {
+    struct Item { int contig; Chunk *chunk; };   // chunk == nullptr: end of stream (contig < 0: after a read error)
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<Item> q;
+    bool stop = false;
+    auto push = [&](Item it) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return q.size() < depth || stop; });
+        if (stop && it.chunk) { it.chunk->clear(); delete it.chunk; return; }
+        q.push_back(it);
+        cv.notify_all();
+    };
+    std::thread reader([&] {
+        for (int i = 0; i < n_contigs; i++) {
+            for (;;) {
+                { std::lock_guard<std::mutex> lk(m); if (stop) return; }
+                Chunk *c = new Chunk();
+                const int got = read(i, *c);
+                if (got <= 0) { c->clear(); delete c; if (got < 0) { push(Item{-1, nullptr}); return; } break; }
+                push(Item{i, c});
+            }
+        }
+        push(Item{0, nullptr});
+    });
+    int rc = 0;
+    for (;;) {
+        Item it;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return !q.empty(); });
+            it = q.front();
+            q.erase(q.begin());
+            cv.notify_all();
+        }
+        if (!it.chunk) { if (it.contig < 0) rc = -1; break; }
+        if (rc == 0) rc = handle(it.contig, *it.chunk);
+        it.chunk->clear();
+        delete it.chunk;
+        if (rc != 0) {   // tell the reader to stop and drop what it still delivers
+            { std::lock_guard<std::mutex> lk(m); stop = true; for (Item &x : q) if (x.chunk) { x.chunk->clear(); delete x.chunk; } q.clear(); }
+            cv.notify_all();
+            break;
+        }
+    }
+    reader.join();
+    return rc;
+}
+
+// Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
+// the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.
+std::thread warm_up_device();
 
 // ---- the text VCF loader of the tag family (VcfParser::parserProcess, src/haplotag/HaplotagVcfParser.cpp:206-545) ---------
 // one record of one sample (VarData, HaplotagType.h:110-143)

@@ -82,7 +82,12 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out);
  * (HaplotagProcess.cpp:318-438), adds the chunk's share of the statistics and of the --log table                         */
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r);
 int lpsh_tag_end(lpsh_tag *h);                                         /* closes the files, prints the report            */
-int lpsh_tag_run(lpsh_tag *h);                                         /* begin, then pack / lps_tag_reads / emit per contig, end */
+/* the verdicts of one packed chunk (the device in the real program; the test-suite passes the oracle): fills *out, 0 or != 0 */
+typedef int (*lpsh_tag_judge_fn)(void *user, int contig, const lpsh_packed *chunk, int want_calls, lps_tag_result *out);
+/* the whole tagging pass: a reader thread parses and packs chunk after chunk while the calling thread judges the previous one,
+ * tags its records and writes them in their original order (begin ... end included)                                          */
+int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user);
+int lpsh_tag_run(lpsh_tag *h);                                         /* lpsh_tag_run_with(lps_tag_reads on device 0)      */
 void lpsh_tag_close(lpsh_tag *h);
 int lpsh_tag_main(int argc, char **argv);
 

@@ -30,6 +30,8 @@ class LpshPacked(C.Structure):
                 ("names", C.POINTER(C.c_char)), ("name_off", ffi.u64p)]
 
 
+TAG_JUDGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(LpshPacked), C.c_int, C.POINTER(ffi.LpsTagResult))
+
 _lib = None
 
 
@@ -58,6 +60,7 @@ def host_lib():
         lib.lpsh_tag_pack.argtypes = [vp, C.c_int, C.POINTER(LpshPacked)]
         lib.lpsh_tag_emit.argtypes = [vp, C.c_int, C.POINTER(ffi.LpsTagResult)]
         lib.lpsh_tag_end.argtypes = [vp]
+        lib.lpsh_tag_run_with.argtypes = [vp, TAG_JUDGE_FN, vp]
         lib.lpsh_tag_close.argtypes = [vp]
         lib.lpsh_last_error.restype = C.c_char_p
         _lib = lib

@@ -212,6 +212,100 @@ def test_haplotag_host_files_match_reference(tmp_path_factory, tmp_path, extra):
         assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
 
 
+def oracle_tag_pipelined(files, vcf, extra, cwd, chunk):
+    """lpsh_tag_run_with: the host's own reader-thread / writer pipeline with the ORACLE as the judge of every chunk."""
+    lib = hc.host_lib()
+    os.makedirs(cwd, exist_ok=True)
+    old = os.getcwd()
+    os.chdir(cwd)
+    os.environ["LPS_TAG_CHUNK"] = str(chunk)
+    try:
+        h = C.c_void_p()
+        n, av = hc.argv(tag_args(files, vcf, extra))
+        assert lib.lpsh_tag_open(n, av, C.byref(h)) == 0, lib.lpsh_last_error()
+        tp = ffi.LpsTagParams()
+        lib.lpsh_tag_params(h, C.byref(tp))
+        state = dict(keep=None, chunks=0, contigs=set())
+
+        def judge(user, contig, pk, want_calls, out):
+            try:
+                c = hc.packed_contig(pk.contents)
+                orc = po.OracleTag(c, tp)
+                keep = [np.ascontiguousarray(x) for x in (orc.category, orc.hp, orc.ps, orc.pq, orc.h1, orc.h2, orc.call_off, orc.calls)]
+                r = out.contents
+                r.n_reads = c.n_reads
+                r.category, r.hp, r.ps, r.pq = ffi.ptr(keep[0], ffi.u8p), ffi.ptr(keep[1], ffi.i8p), ffi.ptr(keep[2], ffi.i32p), ffi.ptr(keep[3], ffi.i32p)
+                r.h1, r.h2 = ffi.ptr(keep[4], ffi.i32p), ffi.ptr(keep[5], ffi.i32p)
+                if want_calls:
+                    r.call_off, r.n_calls, r.calls = ffi.ptr(keep[6], ffi.u64p), len(keep[7]), keep[7].ctypes.data_as(C.POINTER(ffi.LpsCall))
+                state["keep"] = keep            # alive until the next chunk is judged
+                state["chunks"] += 1
+                state["contigs"].add(contig)
+                return 0 if orc.rc == 0 else -1
+            except Exception as e:  # noqa: BLE001
+                print("judge failed:", e)
+                return -1
+        cb = hc.TAG_JUDGE_FN(judge)
+        rc = lib.lpsh_tag_run_with(h, cb, None)
+        lib.lpsh_tag_close(h)
+        assert rc == 0, lib.lpsh_last_error()
+        return state
+    finally:
+        os.environ.pop("LPS_TAG_CHUNK", None)
+        os.chdir(old)
+
+
+@needs_host
+@needs_ref
+@pytest.mark.parametrize("chunk", [250, 100000])
+def test_haplotag_pipelined_run_matches_reference(tmp_path_factory, tmp_path, chunk):
+    files = dataset(tmp_path_factory, "plain")
+    if "phased_vcf" not in files:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        files["phased_vcf"] = os.path.join(d, "out.vcf")
+    extra = ["--log", "--tagSupplementary"]
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, files["phased_vcf"], extra))
+    st = oracle_tag_pipelined(files, files["phased_vcf"], extra, str(tmp_path / "own"), chunk)
+    assert st["contigs"] == {0, 2} and (st["chunks"] >= 4 if chunk == 250 else st["chunks"] == 2)   # chrEmpty never reaches the judge
+    assert hc.bam_payload(str(tmp_path / "own" / "tagged.bam")) == hc.bam_payload(str(tmp_path / "ref" / "tagged.bam"))
+    assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
+
+
+@needs_host
+def test_haplotag_pipelined_run_stops_on_judge_failure(tmp_path_factory, tmp_path):
+    files = dataset(tmp_path_factory, "plain")
+    lib = hc.host_lib()
+    old = os.getcwd()
+    os.chdir(str(tmp_path))
+    os.environ["LPS_TAG_CHUNK"] = "50"
+    try:
+        h = C.c_void_p()
+        n, av = hc.argv(tag_args(files, files.get("phased_vcf", files["vcf"]), []))
+        assert lib.lpsh_tag_open(n, av, C.byref(h)) == 0
+        calls = []
+        cb = hc.TAG_JUDGE_FN(lambda user, contig, pk, want, out: calls.append(contig) or (-1 if len(calls) == 3 else _zero_verdicts(pk, out, calls)))
+        assert lib.lpsh_tag_run_with(h, cb, None) != 0 and len(calls) == 3
+        assert b"judge failed" in lib.lpsh_last_error()
+        lib.lpsh_tag_close(h)
+    finally:
+        os.environ.pop("LPS_TAG_CHUNK", None)
+        os.chdir(old)
+
+
+_zero_keep = []
+
+
+def _zero_verdicts(pk, out, calls):
+    n = pk.contents.batch.n_reads
+    cat, z8, z = np.ones(n, np.uint8), np.zeros(n, np.int8), np.zeros(n, np.int32)
+    _zero_keep[:] = [cat, z8, z]
+    r = out.contents
+    r.n_reads, r.category, r.hp = n, ffi.ptr(cat, ffi.u8p), ffi.ptr(z8, ffi.i8p)
+    r.ps = r.pq = r.h1 = r.h2 = ffi.ptr(z, ffi.i32p)
+    return 0
+
+
 @needs_host
 @needs_ref
 def test_haplotag_string_phase_sets(tmp_path_factory, tmp_path):
