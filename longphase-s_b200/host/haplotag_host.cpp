@@ -439,8 +439,10 @@ int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
         }
         return emit_chunk(h, i, ck, &r);
     };
+    const double m0 = lpsh::now_ms();
     const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) { return read_chunk(h, i, ck); }, handle);
     std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
+    std::cerr << "[timing] tagging pass " << (lpsh::now_ms() - m0) << " ms\n";
     const int rc_end = lpsh_tag_end(h);
     return rc != 0 ? -1 : rc_end;
 }

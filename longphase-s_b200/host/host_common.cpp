@@ -3,10 +3,14 @@
 
 #include <zlib.h>
 
+#include <chrono>
+
 namespace lpsh {
 
 static thread_local std::string g_error;
 static std::string g_error_any;
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int fail(const std::string &message) {
     g_error = message;

@@ -32,6 +32,7 @@ namespace lpsh {
 // the output files carry the version of the tool whose format they follow (##longphaseVersion, @PG VN)
 static const char *const REFERENCE_VERSION = "1.0.0";
 
+double now_ms();                                           // monotonic clock, for the [timing] lines on stderr
 int fail(const std::string &message);                     // remembers the message for lpsh_last_error, returns -1
 bool read_gz(const std::string &path, std::string &text); // whole file through zlib (plain files pass through)
 int device_count();                                       // CUDA devices liblps_b200.so can open a context on

@@ -82,7 +82,7 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out);
  * (HaplotagProcess.cpp:318-438), adds the chunk's share of the statistics and of the --log table                         */
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r);
 int lpsh_tag_end(lpsh_tag *h);                                         /* closes the files, prints the report            */
-/* the verdicts of one packed chunk (the device in the real program; the test-suite passes the oracle): fills *out, 0 or != 0 */
+/* the verdicts of one packed chunk (the device in the real program; the test-suite passes its CPU checker): fills *out, 0 or != 0 */
 typedef int (*lpsh_tag_judge_fn)(void *user, int contig, const lpsh_packed *chunk, int want_calls, lps_tag_result *out);
 /* the whole tagging pass: a reader thread parses and packs chunk after chunk while the calling thread judges the previous one,
  * tags its records and writes them in their original order (begin ... end included)                                          */
@@ -115,6 +115,9 @@ int lpsh_som_tag_begin(lpsh_som *h);
 int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv);
 int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r);
 int lpsh_som_tag_end(lpsh_som *h);
+typedef int (*lpsh_som_judge_fn)(void *user, int contig, const lpsh_packed *chunk, const lps_tumor_variants *tv, lps_somatic_tag_result *out);
+/* the whole tagging pass, pipelined like lpsh_tag_run_with (begin ... end included); needs lpsh_som_call                     */
+int lpsh_som_tag_run_with(lpsh_som *h, lpsh_som_judge_fn judge, void *user);
 int lpsh_som_run(lpsh_som *h);
 void lpsh_som_close(lpsh_som *h);
 int lpsh_som_main(int argc, char **argv);

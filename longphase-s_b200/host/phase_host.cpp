@@ -79,12 +79,6 @@ struct PhaseOptions {
     std::vector<std::string> bams;
 };
 
-template <class T>
-void take(const char *text, T &dst) {   // the reference reads every value with operator>> of an istringstream
-    std::istringstream in(text ? text : "");
-    in >> dst;
-}
-
 bool readable(const std::string &path) { return std::ifstream(path.c_str()).is_open(); }
 
 struct VariantText {
@@ -118,27 +112,27 @@ int parse_phase_options(int argc, char **argv, PhaseOptions &o) {
     optind = 1;
     for (int c; (c = getopt_long(argc, argv, "s:b:o:t:r:d:1:a:q:x:p:e:n:m:L:w:h:", PHASE_LONG, NULL)) != -1;) {
         switch (c) {
-            case 's': take(optarg, o.snp_file); break;
-            case 't': take(optarg, o.threads); break;
-            case 'o': take(optarg, o.prefix); break;
-            case 'r': take(optarg, o.fasta); break;
-            case 'd': take(optarg, o.distance); break;
-            case '1': take(optarg, o.edge_threshold); break;
-            case 'a': take(optarg, o.connect_adjacent); break;
-            case 'q': take(optarg, o.mapping_quality); break;
-            case 'x': take(optarg, o.mismatch_rate); break;
-            case 'p': take(optarg, o.base_quality); break;
-            case 'e': take(optarg, o.edge_weight); break;
-            case 'n': take(optarg, o.snp_confidence); break;
-            case 'm': take(optarg, o.read_confidence); break;
-            case 'w': take(optarg, o.sv_window); break;
-            case 'h': take(optarg, o.sv_threshold); break;
-            case 'L': take(optarg, o.overlap_threshold); break;
-            case 'b': { std::string f; take(optarg, f); o.bams.push_back(f); break; }
-            case O_SV: take(optarg, o.sv_file); break;
-            case O_MOD: take(optarg, o.mod_file); break;
+            case 's': lpsh::take(optarg, o.snp_file); break;
+            case 't': lpsh::take(optarg, o.threads); break;
+            case 'o': lpsh::take(optarg, o.prefix); break;
+            case 'r': lpsh::take(optarg, o.fasta); break;
+            case 'd': lpsh::take(optarg, o.distance); break;
+            case '1': lpsh::take(optarg, o.edge_threshold); break;
+            case 'a': lpsh::take(optarg, o.connect_adjacent); break;
+            case 'q': lpsh::take(optarg, o.mapping_quality); break;
+            case 'x': lpsh::take(optarg, o.mismatch_rate); break;
+            case 'p': lpsh::take(optarg, o.base_quality); break;
+            case 'e': lpsh::take(optarg, o.edge_weight); break;
+            case 'n': lpsh::take(optarg, o.snp_confidence); break;
+            case 'm': lpsh::take(optarg, o.read_confidence); break;
+            case 'w': lpsh::take(optarg, o.sv_window); break;
+            case 'h': lpsh::take(optarg, o.sv_threshold); break;
+            case 'L': lpsh::take(optarg, o.overlap_threshold); break;
+            case 'b': { std::string f; lpsh::take(optarg, f); o.bams.push_back(f); break; }
+            case O_SV: lpsh::take(optarg, o.sv_file); break;
+            case O_MOD: lpsh::take(optarg, o.mod_file); break;
             case O_INDELS: o.indels = true; break;
-            case O_INDELQ: take(optarg, o.indel_quality); break;
+            case O_INDELQ: lpsh::take(optarg, o.indel_quality); break;
             case O_DEEPSOMATIC: o.deepsomatic = true; break;
             case O_DOT: o.dot = true; break;
             case O_ONT: o.ont = true; break;
@@ -526,8 +520,7 @@ int lpsh_phase_run(lpsh_phase *h) {
     if (!h) return -1;
     const PhaseOptions &o = h->opt;
     const int n = (int)h->chr_names.size();
-    const int n_dev = lpsh::device_count();
-    if (n_dev < 1) return lpsh::fail("no usable CUDA device (there is no CPU fallback)");
+    int n_dev = -1;   // counted when the first contig is packed: the driver starts (lpsh_phase_main) while the BAM is being decoded
     htsThreadPool pool = {NULL, 0};
     if (!(pool.pool = hts_tpool_init(o.threads))) fprintf(stderr, "Error creating thread pool\n");
     std::time_t t0 = time(NULL);
@@ -543,6 +536,14 @@ int lpsh_phase_run(lpsh_phase *h) {
             continue;
         }
         lpsh::PackedContig *pc = h->packed[(size_t)i];
+#pragma omp critical(lpsh_device_count)
+        if (n_dev < 0) n_dev = lpsh::device_count();
+        if (n_dev < 1) {
+#pragma omp critical
+            { lpsh::fail("no usable CUDA device (there is no CPU fallback)"); failed = 1; }
+            lpsh_phase_release(h, i);
+            continue;
+        }
         if (pc->n_reads() > 0) {
             lps_ctx *ctx = nullptr;
             lpsh_packed v;
@@ -579,16 +580,21 @@ void lpsh_phase_close(lpsh_phase *h) {
 
 int lpsh_phase_main(int argc, char **argv) {
     std::time_t t0 = time(NULL);
+    std::thread warm = lpsh::warm_up_device();   // the driver starts while the VCF, the FASTA and the first BAM regions are read
+    struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_warm{warm};
     lpsh_phase *job = nullptr;
+    const double m0 = lpsh::now_ms();
     const int rc = lpsh_phase_open(argc, argv, &job);
     if (rc == 2) return 0;
     if (rc != 0) { if (rc < 0) std::cerr << "phase: " << lpsh_last_error() << "\n"; return 1; }
+    const double m1 = lpsh::now_ms();
     if (lpsh_phase_run(job) != 0) { std::cerr << "phase: " << lpsh_last_error() << "\n"; lpsh_phase_close(job); return 1; }
     std::time_t t1 = time(NULL);
     std::cerr << "writeResult SNP ... ";
     lpsh_phase_write_result(job);
     std::cerr << difftime(time(NULL), t1) << "s\n";
     std::cerr << "\ntotal process: " << difftime(time(NULL), t0) << "s\n";
+    std::cerr << "[timing] load " << (m1 - m0) << " ms, contig loop " << (lpsh::now_ms() - m1) << " ms (incl. writing)\n";
     lpsh_phase_close(job);
     return 0;
 }

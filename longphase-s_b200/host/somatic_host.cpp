@@ -169,8 +169,9 @@ struct lpsh_som {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
-    lpsh::Chunk chunk;
-    size_t chunk_reads = 65536;
+    lpsh::Chunk chunk;          // the chunk of the staged API (lpsh_som_tag_pack / lpsh_som_tag_emit)
+    int chunk_contig = -1;
+    size_t chunk_reads = 8192;
     // ReadStatistics
     int64_t st_alignment = 0, st_supplementary = 0, st_secondary = 0, st_unmapped = 0, st_tag = 0, st_untag = 0, st_low = 0, st_other = 0,
             st_empty = 0, st_similar = 0, st_cross = 0, st_no_variant = 0, st_only_h3 = 0, st_hp[LPS_READHP_FIELDS] = {0};
@@ -356,6 +357,7 @@ void finish_contig(lpsh_som &job) {
     if (job.itr) hts_itr_destroy(job.itr);
     job.itr = nullptr;
     job.cur = -1;
+    job.chunk_contig = -1;
     job.chunk.clear();
 }
 
@@ -581,38 +583,54 @@ int lpsh_som_tag_begin(lpsh_som *h) {
     return 0;
 }
 
-// next chunk of contig i of the tumor BAM with the union map carrying the caller's flags: 1 = ready, 0 = exhausted, < 0 error
-int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv) {
-    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+// next chunk of contig i of the tumor BAM into `ck` (reads + the NORMAL side of the union map): 1 = filled, 0 = exhausted, < 0 error
+static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
     const std::string &chr = h->chr_names[(size_t)i];
     if (h->cur != i) {
-        finish_contig(*h);
+        if (h->itr) hts_itr_destroy(h->itr);
         h->cur = i;
         h->itr_done = false;
         h->itr = sam_itr_querys(h->idx, h->hdr, contig_region(*h, chr).c_str());
         if (!h->itr) h->itr_done = true;
     }
-    h->chunk.clear();
-    lpsh::PackedContig &pc = h->chunk.pack;
-    pack_union(*h, chr, pc, h->tum);
+    ck.clear();
+    lpsh::PackedContig &pc = ck.pack;
+    TumorArrays unused;
+    pack_union(*h, chr, pc, unused);
     pc.ref = h->ref_tumor[chr];
-    while (!h->itr_done && h->chunk.records.size() < h->chunk_reads) {
+    while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
         pc.add_alignment(b);
-        h->chunk.records.push_back(b);
+        ck.records.push_back(b);
     }
-    if (h->chunk.records.empty()) { finish_contig(*h); h->cur = i; h->itr_done = true; return 0; }
+    if (ck.records.empty()) { ck.clear(); return 0; }
     pc.finish();
-    pc.view(out);
-    h->tum.view(tv);
     return 1;
 }
 
-// SomaticHaplotagChrProcessor: processRead's tag handling + addAuxiliaryTags (HaplotagProcess.cpp:318-355, SomaticHaplotagProcess.cpp:464-472)
+// staged API: the chunk plus the TUMOR side of the union map, now carrying the caller's flags
+int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv) {
+    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    const int got = read_chunk(h, i, h->chunk);
+    if (got != 1) return got;
+    lpsh::PackedContig scratch;
+    pack_union(*h, h->chr_names[(size_t)i], scratch, h->tum);
+    h->chunk.pack.view(out);
+    h->tum.view(tv);
+    h->chunk_contig = i;
+    return 1;
+}
+
+static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result *r);
+
 int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r) {
-    if (!h || !r || h->cur != i || !h->out) return -1;
-    lpsh::Chunk &ck = h->chunk;
+    if (!h || !r || h->chunk_contig != i || !h->out) return -1;
+    return emit_chunk(h, h->chunk, r);
+}
+
+// SomaticHaplotagChrProcessor: processRead's tag handling + addAuxiliaryTags (HaplotagProcess.cpp:318-355, SomaticHaplotagProcess.cpp:464-472)
+static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result *r) {
     const size_t n = ck.records.size();
     if ((size_t)r->reads.n_reads != n) return lpsh::fail("verdict count does not match the chunk");
     for (size_t k = 0; k < n; k++) {
@@ -670,10 +688,84 @@ int lpsh_som_tag_end(lpsh_som *h) {
     return rc;
 }
 
+// The tagging pass with any judge: reader thread (htslib parsing + packing) | calling thread (judge, HP:Z / PS / PQ, sam_write1).
+// Needs lpsh_som_call (the flags travel in the TUMOR side of the union map).  begin ... end included.
+int lpsh_som_tag_run_with(lpsh_som *h, lpsh_som_judge_fn judge, void *user) {
+    if (!h || !judge) return -1;
+    if (lpsh_som_tag_begin(h) != 0) return -1;
+    lps_tag_params tp;
+    lpsh_som_params(h, 1, &tp);
+    std::time_t t0 = time(NULL);
+    std::cerr << "somatic tagging start ...\n";
+    int tum_contig = -1;
+    auto handle = [&](int i, lpsh::Chunk &ck) -> int {
+        if (tum_contig != i) {   // TUMOR side of the union map: once per contig, on this thread
+            lpsh::PackedContig scratch;
+            pack_union(*h, h->chr_names[(size_t)i], scratch, h->tum);
+            tum_contig = i;
+        }
+        lpsh_packed v;
+        lps_tumor_variants tv;
+        ck.pack.view(&v);
+        h->tum.view(&tv);
+        lps_somatic_tag_result r;
+        memset(&r, 0, sizeof(r));
+        std::vector<uint8_t> cat;
+        std::vector<int8_t> hp;
+        std::vector<int32_t> zero;
+        if (v.variants.n == 0) {      // dispatch without variants: MAPQ and flags only (HaplotagParsingBam.cpp:457-476)
+            const int n = v.batch.n_reads;
+            cat.resize((size_t)n); hp.assign((size_t)n, 0); zero.assign((size_t)n, 0);
+            for (int k = 0; k < n; k++) {
+                const int flag = v.batch.flag[k];
+                cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
+                                 : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
+                                 : LPS_TAG_EMPTY_VARIANTS;
+                r.total_alignment++; r.total_untag++;
+                if (cat[(size_t)k] == LPS_TAG_LOW_MAPQ) r.total_lower_quality++;
+                else if (cat[(size_t)k] == LPS_TAG_UNMAPPED) r.total_unmapped++;
+                else if (cat[(size_t)k] == LPS_TAG_SECONDARY) r.total_secondary++;
+                else if (cat[(size_t)k] == LPS_TAG_SUPPLEMENTARY) r.total_supplementary++;
+                else r.total_empty_variant++;
+            }
+            r.reads.n_reads = n; r.reads.category = cat.data(); r.reads.read_hp = hp.data(); r.reads.ps = zero.data(); r.reads.pq = zero.data();
+        } else if (judge(user, i, &v, &tv, &r) != 0) {
+            return lpsh::fail(std::string("contig ") + h->chr_names[(size_t)i] + ": the judge failed");
+        }
+        return emit_chunk(h, ck, &r);
+    };
+    const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) { return read_chunk(h, i, ck); }, handle);
+    std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
+    const int rc_end = lpsh_som_tag_end(h);
+    return rc != 0 ? -1 : rc_end;
+}
+
+namespace {
+struct SomDeviceJudge {
+    lps_ctx *ctx = nullptr;
+    lps_tag_params tp;
+    int contig = -1;
+    std::string error;
+};
+int som_device_judge(void *user, int contig, const lpsh_packed *v, const lps_tumor_variants *tv, lps_somatic_tag_result *out) {
+    SomDeviceJudge *d = (SomDeviceJudge *)user;
+    int rc = 0;
+    if (d->contig != contig) {
+        rc = lps_contig_set_reference(d->ctx, v->ref, v->ref_len);
+        if (rc == 0) rc = lps_contig_set_variants(d->ctx, &v->variants, 0);
+        if (rc == 0) rc = lps_contig_set_tumor_variants(d->ctx, tv);
+        d->contig = contig;
+    }
+    if (rc == 0) rc = lps_batch_submit(d->ctx, &v->batch);
+    if (rc == 0) rc = lps_somatic_tag_reads(d->ctx, &d->tp, 0, out);
+    if (rc != 0) d->error = lps_last_error(d->ctx);
+    return rc;
+}
+}  // namespace
+
 int lpsh_som_run(lpsh_som *h) {
     if (!h) return -1;
-    lps_ctx *ctx = nullptr;
-    if (lps_ctx_create(0, &ctx) != 0) return lpsh::fail("no usable CUDA device (there is no CPU fallback)");
+    lps_ctx *ctx = nullptr;   // created after the first contig is packed: the driver starts (lpsh_som_main) while the BAM is decoded
     lps_tag_params xp, tp;
     lpsh_som_params(h, 0, &xp);
     lpsh_som_params(h, 1, &tp);
@@ -687,6 +779,7 @@ int lpsh_som_run(lpsh_som *h) {
             lpsh_packed v;
             lps_tumor_variants tv;
             if (lpsh_som_pack(h, i, which, &v, &tv) != 0) { rc = -1; break; }
+            if (!ctx && lps_ctx_create(0, &ctx) != 0) { lpsh::fail("no usable CUDA device (there is no CPU fallback)"); rc = -1; break; }
             lps_extract_result r;
             if (v.variants.n == 0) {      // a contig without any variant: nothing reaches the parsers (processEmptyVariants)
                 memset(&r, 0, sizeof(r));
@@ -704,58 +797,14 @@ int lpsh_som_run(lpsh_som *h) {
     }
     h->pack = lpsh::PackedContig();
     if (rc == 0) rc = lpsh_som_call(h);
-    if (rc == 0) rc = lpsh_som_tag_begin(h);
-    std::time_t t0 = time(NULL);
-    std::cerr << "somatic tagging start ...\n";
-    for (int i = 0; i < nc && rc == 0; i++) {
-        const std::string &chr = h->chr_names[(size_t)i];
-        std::time_t c0 = time(NULL);
-        std::cerr << "chr: " << chr << " ... ";
-        bool table_set = false;
-        lpsh_packed v;
-        lps_tumor_variants tv;
-        for (int got; rc == 0 && (got = lpsh_som_tag_pack(h, i, &v, &tv)) != 0;) {
-            if (got < 0) { rc = -1; break; }
-            lps_somatic_tag_result r;
-            std::vector<uint8_t> cat;
-            std::vector<int8_t> hp;
-            std::vector<int32_t> zero;
-            if (v.variants.n == 0) {      // dispatch without variants: MAPQ and flags only (HaplotagParsingBam.cpp:457-476)
-                const int n = v.batch.n_reads;
-                cat.resize((size_t)n); hp.assign((size_t)n, 0); zero.assign((size_t)n, 0);
-                memset(&r, 0, sizeof(r));
-                for (int k = 0; k < n; k++) {
-                    const int flag = v.batch.flag[k];
-                    cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
-                                     : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
-                                     : LPS_TAG_EMPTY_VARIANTS;
-                    r.total_alignment++; r.total_untag++;
-                    if (cat[(size_t)k] == LPS_TAG_LOW_MAPQ) r.total_lower_quality++;
-                    else if (cat[(size_t)k] == LPS_TAG_UNMAPPED) r.total_unmapped++;
-                    else if (cat[(size_t)k] == LPS_TAG_SECONDARY) r.total_secondary++;
-                    else if (cat[(size_t)k] == LPS_TAG_SUPPLEMENTARY) r.total_supplementary++;
-                    else r.total_empty_variant++;
-                }
-                r.reads.n_reads = n; r.reads.category = cat.data(); r.reads.read_hp = hp.data(); r.reads.ps = zero.data(); r.reads.pq = zero.data();
-            } else {
-                if (!table_set) {
-                    rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
-                    if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, 0);
-                    if (rc == 0) rc = lps_contig_set_tumor_variants(ctx, &tv);
-                    table_set = true;
-                }
-                if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);
-                if (rc == 0) rc = lps_somatic_tag_reads(ctx, &tp, 0, &r);
-                if (rc != 0) { lpsh::fail(std::string("contig ") + chr + ": " + lps_last_error(ctx)); break; }
-            }
-            rc = lpsh_som_tag_emit(h, i, &r);
-        }
-        std::cerr << difftime(time(NULL), c0) << "s\n";
-    }
-    lps_ctx_destroy(ctx);
-    std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
-    const int rc_end = lpsh_som_tag_end(h);
-    return rc != 0 ? -1 : rc_end;
+    SomDeviceJudge d;
+    d.ctx = ctx;
+    d.tp = tp;
+    if (rc == 0 && !ctx) { lpsh::fail("no contig to process"); rc = -1; }
+    if (rc == 0) rc = lpsh_som_tag_run_with(h, som_device_judge, &d);
+    if (rc != 0 && !d.error.empty()) lpsh::fail(d.error);
+    if (ctx) lps_ctx_destroy(ctx);
+    return rc != 0 ? -1 : 0;
 }
 
 void lpsh_som_close(lpsh_som *h) {
@@ -765,6 +814,8 @@ void lpsh_som_close(lpsh_som *h) {
 }
 
 int lpsh_som_main(int argc, char **argv) {
+    std::thread warm = lpsh::warm_up_device();   // the driver starts while the VCFs, the FASTA and the first BAM regions are read
+    struct Join { std::thread &t; ~Join() { if (t.joinable()) t.join(); } } join_warm{warm};
     lpsh_som *job = nullptr;
     const int rc = lpsh_som_open(argc, argv, &job);
     if (rc == 2) return 0;

@@ -63,7 +63,11 @@ def som_lib():
     lib.lpsh_som_tag_emit.argtypes = [vp, C.c_int, C.POINTER(ffi.LpsSomaticTagResult)]
     lib.lpsh_som_tag_end.argtypes = [vp]
     lib.lpsh_som_close.argtypes = [vp]
+    lib.lpsh_som_tag_run_with.argtypes = [vp, SOM_JUDGE_FN, vp]
     return lib
+
+
+SOM_JUDGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(hc.LpshPacked), C.POINTER(ffi.LpsTumorVariants), C.POINTER(ffi.LpsSomaticTagResult))
 
 
 def union_contig(pk, tv):
@@ -117,7 +121,7 @@ def tag_struct(o, c, tp, keep):
     return r
 
 
-def oracle_somatic_through_host(files, extra, cwd, chunk=300):
+def oracle_somatic_through_host(files, extra, cwd, chunk=300, pipelined=False):
     lib = som_lib()
     os.makedirs(cwd, exist_ok=True)
     old = os.getcwd()
@@ -144,23 +148,43 @@ def oracle_somatic_through_host(files, extra, cwd, chunk=300):
                 assert lib.lpsh_som_set_extract(h, i, which, C.byref(r)) == 0
         assert lib.lpsh_som_call(h) == 0, lib.lpsh_last_error()
         info = dict(purity=lib.lpsh_som_purity(h), n_somatic=lib.lpsh_som_n_somatic(h), chunks=0, h3_reads=0)
-        assert lib.lpsh_som_tag_begin(h) == 0, lib.lpsh_last_error()
-        for i in range(nc):
-            while True:
-                pk, tv = hc.LpshPacked(), ffi.LpsTumorVariants()
-                got = lib.lpsh_som_tag_pack(h, i, C.byref(pk), C.byref(tv))
-                assert got >= 0, lib.lpsh_last_error()
-                if got == 0:
-                    break
-                info["chunks"] += 1
-                c = union_contig(pk, tv)
-                o = po.OracleSomatic(c, tp, "somatic_tag")
-                assert o.rc == 0
-                info["h3_reads"] += int((o.read_hp >= 3).sum())
-                keep = []
-                r = tag_struct(o, c, tp, keep)
-                assert lib.lpsh_som_tag_emit(h, i, C.byref(r)) == 0, lib.lpsh_last_error()
-        assert lib.lpsh_som_tag_end(h) == 0
+        if pipelined:     # the host's own reader-thread / writer pipeline with the oracle as the judge of every chunk
+            state = dict(keep=None)
+
+            def judge(user, contig, pk, tvp, out):
+                try:
+                    c = union_contig(pk.contents, tvp.contents)
+                    o = po.OracleSomatic(c, tp, "somatic_tag")
+                    info["h3_reads"] += int((o.read_hp >= 3).sum())
+                    info["chunks"] += 1
+                    keep = []
+                    r = tag_struct(o, c, tp, keep)
+                    C.memmove(out, C.byref(r), C.sizeof(r))
+                    state["keep"] = keep
+                    return 0 if o.rc == 0 else -1
+                except Exception as e:  # noqa: BLE001
+                    print("judge failed:", e)
+                    return -1
+            cb = SOM_JUDGE_FN(judge)
+            assert lib.lpsh_som_tag_run_with(h, cb, None) == 0, lib.lpsh_last_error()
+        else:
+            assert lib.lpsh_som_tag_begin(h) == 0, lib.lpsh_last_error()
+            for i in range(nc):
+                while True:
+                    pk, tv = hc.LpshPacked(), ffi.LpsTumorVariants()
+                    got = lib.lpsh_som_tag_pack(h, i, C.byref(pk), C.byref(tv))
+                    assert got >= 0, lib.lpsh_last_error()
+                    if got == 0:
+                        break
+                    info["chunks"] += 1
+                    c = union_contig(pk, tv)
+                    o = po.OracleSomatic(c, tp, "somatic_tag")
+                    assert o.rc == 0
+                    info["h3_reads"] += int((o.read_hp >= 3).sum())
+                    keep = []
+                    r = tag_struct(o, c, tp, keep)
+                    assert lib.lpsh_som_tag_emit(h, i, C.byref(r)) == 0, lib.lpsh_last_error()
+            assert lib.lpsh_som_tag_end(h) == 0
         lib.lpsh_som_close(h)
         return info
     finally:
@@ -177,7 +201,7 @@ SOM_VARIANTS = [[], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20"]
 def test_somatic_host_files_match_reference(tmp_path_factory, tmp_path, extra):
     files = dataset(tmp_path_factory)
     run_in(str(tmp_path / "ref"), [hc.REF_BIN] + som_args(files, extra))
-    info = oracle_somatic_through_host(files, extra, str(tmp_path / "own"))
+    info = oracle_somatic_through_host(files, extra, str(tmp_path / "own"), pipelined=(extra != SOM_VARIANTS[1]))
     assert info["chunks"] >= 4 and info["n_somatic"] > 20 and info["h3_reads"] > 50, info
     ref, own = hc.bam_payload(str(tmp_path / "ref" / "som.bam")), hc.bam_payload(str(tmp_path / "own" / "som.bam"))
     assert b"HPZ" in own, "no HP:Z tag was written"

@@ -54,12 +54,12 @@ def main():
     vcf = os.path.join(d, "ref", "out.vcf")
     tag = ["haplotag", "-s", vcf, "-b", files["bam"], "-r", files["fasta"], "-o", "tagged", "-t", t, "--log"]
     ref_s, _ = timed([hc.REF_BIN] + tag, os.path.join(d, "ref"))
-    own_s, _ = timed([hc.HOST_BIN] + tag, os.path.join(d, "own"))
+    own_s, tag_err = timed([hc.HOST_BIN] + tag, os.path.join(d, "own"))
     same_bam = hc.bam_payload(os.path.join(d, "ref", "tagged.bam")) == hc.bam_payload(os.path.join(d, "own", "tagged.bam"))
     same_log = open(os.path.join(d, "ref", "tagged.out")).read() == open(os.path.join(d, "own", "tagged.out")).read()
     out["haplotag"] = {"reference_s": round(ref_s, 3), "own_s": round(own_s, 3), "identical_bam": same_bam, "identical_log": same_log,
                        "reads_per_s_reference": n_reads / ref_s, "reads_per_s_own": n_reads / own_s}
-    out["own_phase_stderr_tail"] = own_err[-400:]
+    out["own_timing_lines"] = [ln for ln in (own_err + tag_err).split("\n") if ln.startswith("[timing]") or ln.startswith("tag read") or ln.startswith("parsing total")]
     print(json.dumps(out))
     return 0 if (same and same_bam and same_log) else 1
 
