@@ -414,11 +414,15 @@ int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
     lpsh_tag_params(h, &tp);
     std::time_t t0 = time(NULL);
     std::cerr << "tag read start ...\n";
+    double ms_read = 0, ms_judge = 0, ms_emit = 0;   // wall clock per stage (the reader runs on its own thread)
+    long n_chunks = 0;
     auto handle = [&](int i, lpsh::Chunk &ck) -> int {
         lpsh_packed v;
         ck.pack.view(&v);
         lps_tag_result r;
         memset(&r, 0, sizeof(r));
+        const double j0 = lpsh::now_ms();
+        n_chunks++;
         std::vector<uint8_t> cat;
         std::vector<int8_t> hp;
         std::vector<int32_t> zero;
@@ -437,12 +441,22 @@ int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
         } else if (judge(user, i, &v, h->opt.log ? 1 : 0, &r) != 0) {
             return lpsh::fail(std::string("contig ") + h->chr_names[(size_t)i] + ": the judge failed");
         }
-        return emit_chunk(h, i, ck, &r);
+        const double j1 = lpsh::now_ms();
+        const int rc_emit = emit_chunk(h, i, ck, &r);
+        ms_judge += j1 - j0;
+        ms_emit += lpsh::now_ms() - j1;
+        return rc_emit;
     };
     const double m0 = lpsh::now_ms();
-    const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) { return read_chunk(h, i, ck); }, handle);
+    const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) {
+        const double r0 = lpsh::now_ms();
+        const int got = read_chunk(h, i, ck);
+        ms_read += lpsh::now_ms() - r0;
+        return got;
+    }, handle);
     std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
-    std::cerr << "[timing] tagging pass " << (lpsh::now_ms() - m0) << " ms\n";
+    std::cerr << "[timing] tagging pass " << (lpsh::now_ms() - m0) << " ms: " << n_chunks << " chunks; reader thread " << ms_read << " ms (parse + pack); "
+              << "judge " << ms_judge << " ms; tag + write " << ms_emit << " ms\n";
     const int rc_end = lpsh_tag_end(h);
     return rc != 0 ? -1 : rc_end;
 }
@@ -450,6 +464,7 @@ int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
 namespace {
 // the device as judge: lps_tag_reads on the chunk; the contig's tables are set when the contig changes
 struct DeviceJudge {
+    double ms_create = 0, ms_tables = 0, ms_submit = 0, ms_tag = 0;
     lps_ctx *ctx = nullptr;
     lps_tag_params tp;
     int contig = -1;
@@ -458,18 +473,23 @@ struct DeviceJudge {
 };
 int device_judge(void *user, int contig, const lpsh_packed *v, int want_calls, lps_tag_result *out) {
     DeviceJudge *d = (DeviceJudge *)user;
+    const double t0 = lpsh::now_ms();
     if (!d->ctx) {
         if (d->warm.joinable()) d->warm.join();
         if (lps_ctx_create(0, &d->ctx) != 0) { d->error = "no usable CUDA device (there is no CPU fallback)"; return -1; }
     }
+    const double t1 = lpsh::now_ms();
     int rc = 0;
     if (d->contig != contig) {
         rc = lps_contig_set_reference(d->ctx, v->ref, v->ref_len);
         if (rc == 0) rc = lps_contig_set_variants(d->ctx, &v->variants, 0);
         d->contig = contig;
     }
+    const double t2 = lpsh::now_ms();
     if (rc == 0) rc = lps_batch_submit(d->ctx, &v->batch);
+    const double t3 = lpsh::now_ms();
     if (rc == 0) rc = lps_tag_reads(d->ctx, &d->tp, want_calls, out);
+    d->ms_create += t1 - t0; d->ms_tables += t2 - t1; d->ms_submit += t3 - t2; d->ms_tag += lpsh::now_ms() - t3;
     if (rc != 0) d->error = lps_last_error(d->ctx);
     return rc;
 }
@@ -480,6 +500,8 @@ int lpsh_tag_run(lpsh_tag *h) {
     DeviceJudge d;   // no device -> the first chunk fails with "no usable CUDA device"; nothing is ever judged on the host
     lpsh_tag_params(h, &d.tp);
     const int rc = lpsh_tag_run_with(h, device_judge, &d);
+    std::cerr << "[timing] judge on the device: context " << d.ms_create << " ms, contig tables " << d.ms_tables << " ms, lps_batch_submit " << d.ms_submit
+              << " ms, lps_tag_reads " << d.ms_tag << " ms\n";
     if (rc != 0 && !d.error.empty()) lpsh::fail(d.error);
     if (d.ctx) lps_ctx_destroy(d.ctx);
     return rc;

@@ -96,7 +96,7 @@ int lpsh_tag_main(int argc, char **argv);
  * union map, extract pass over the normal BAM and over the tumor BAM, purity (<prefix>_purity.out), calling, tagging of the
  * tumor BAM (HP:Z, PS:i unless none, PQ:i).                                                                                */
 typedef struct lpsh_som lpsh_som;
-int lpsh_som_open(int argc, char **argv, lpsh_som **out);            /* argv[0] = "somatic_haplotag"                   */
+int lpsh_som_open(int argc, char **argv, lpsh_som **out);            /* argv[0] = "somatic_haplotag" or "estimate_purity" */
 int lpsh_som_n_contigs(const lpsh_som *h);
 const char *lpsh_som_contig_name(const lpsh_som *h, int i);
 int lpsh_som_params(const lpsh_som *h, int pass, lps_tag_params *out); /* pass 0: extract passes, 1: tagging pass         */
@@ -108,6 +108,8 @@ int lpsh_som_set_extract(lpsh_som *h, int i, int which, const lps_extract_result
 /* runTumorPurityEstimator (or --tumor-purity), <prefix>_purity.out, the calling stage and getSomaticFlag for every contig
  * (SomaticVarCaller.cpp:816-866, 937-949, 2397-2412); needs both extract results of every contig                          */
 int lpsh_som_call(lpsh_som *h);
+/* the purity stage alone (what `estimate_purity` runs after the two extract passes; lpsh_som_call includes it)              */
+int lpsh_som_estimate(lpsh_som *h);
 double lpsh_som_purity(const lpsh_som *h);
 int64_t lpsh_som_n_somatic(const lpsh_som *h);
 int lpsh_som_tag_begin(lpsh_som *h);

@@ -76,6 +76,7 @@ struct SomOptions {
     int threads = 1, quality = 1;
     double percentage = 0.6, purity = 0.2;
     bool tag_supplementary = false, estimate_purity = true, enable_filter = true, unsupported = false;
+    bool purity_only = false;   // the `estimate_purity` sub-command (PurityEstimation.cpp): extract passes + purity, no calling, no tagging
     std::string snp_file, bam, tumor_vcf, tumor_bam, fasta, prefix = "result", region, command = "longphase-s ";
 };
 
@@ -185,6 +186,11 @@ const char *READ_HP_TEXT[LPS_READHP_FIELDS] = {".", "1", "2", "3", "4", "1-1", "
 int parse_som_options(int argc, char **argv, SomOptions &o) {
     optind = 1;
     bool bad = false;
+    if (argc > 0 && std::string(argv[0]) == "estimate_purity") {   // ParamsHandler<PurityEstimParameters>::initialize (PurityEstimation.cpp:37-41)
+        o.purity_only = true;
+        o.quality = 20;
+        o.tag_supplementary = true;
+    }
     for (int c; (c = getopt_long(argc, argv, "s:b:o:t:q:p:r:", SOM_LONG, NULL)) != -1;) {
         switch (c) {
             case 't': lpsh::take(optarg, o.threads); break;
@@ -198,8 +204,8 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
             case 'r': lpsh::take(optarg, o.fasta); break;
             case S_TUM_SNP: lpsh::take(optarg, o.tumor_vcf); break;
             case S_TUM_BAM: lpsh::take(optarg, o.tumor_bam); break;
-            case S_DISABLE_FILTER: o.enable_filter = false; break;
-            case S_PURITY: lpsh::take(optarg, o.purity); o.estimate_purity = false; break;
+            case S_DISABLE_FILTER: if (o.purity_only) bad = true; else o.enable_filter = false; break;
+            case S_PURITY: if (o.purity_only) bad = true; else { lpsh::take(optarg, o.purity); o.estimate_purity = false; } break;
             case S_CRAM: case S_LOG: case S_SV: case S_MOD: case S_OUT_VCF: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
                 o.unsupported = true; break;
             case S_HELP: std::cout << SOM_USAGE << std::endl; return 2;
@@ -207,7 +213,7 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
         }
     }
     for (int i = 0; i < argc; i++) { o.command += argv[i]; o.command += " "; }
-    const char *prog = "somatic_haplotag";
+    const char *prog = o.purity_only ? "estimate_purity" : "somatic_haplotag";
     bad |= !lpsh::required_file(prog, o.snp_file, "SNP file");
     bad |= !lpsh::required_file(prog, o.bam, "BAM file");
     bad |= !lpsh::required_file(prog, o.fasta, "reference file");
@@ -234,6 +240,17 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
 
 void som_banner(const SomOptions &o) {   // SomaticHaplotagProcess::printParamsMessage (SomaticHaplotagProcess.cpp:13-49)
     std::ostream &e = std::cerr;
+    if (o.purity_only) {                  // PurityEstimProcess::printParamsMessage (PurityEstimationProcess.cpp:9-29)
+        e << "LongPhase-S v" << lpsh::REFERENCE_VERSION << " - Estimate Tumor Purity (" << lps_version() << ")\n\n[Input Files]\n";
+        e << "phased normal SNP file       : " << o.snp_file << "\ntumor SNP file               : " << o.tumor_vcf << "\n";
+        e << "normal BAM file              : " << o.bam << "\ntumor BAM file               : " << o.tumor_bam << "\n";
+        e << "reference file               : " << o.fasta << "\n\n[Output Files]\npurity estimation file       :" << o.prefix + "_purity.out" << "\n";
+        e << "-------------------------------------------\n[Purity Estimation Params] \n";
+        e << "number of threads            : " << o.threads << "\nestimation region            : " << (!o.region.empty() ? o.region : "all") << "\n";
+        e << "filter mapping quality below : " << o.quality << "\npercentage threshold         : " << o.percentage << "\n";
+        e << "include supplementary reads  : " << (o.tag_supplementary ? "enabled" : "disabled") << "\n-------------------------------------------\n";
+        return;
+    }
     e << "LongPhase-S v" << lpsh::REFERENCE_VERSION << " - Somatic Haplotag (" << lps_version() << ")\n\n[Input Files]\n";
     e << "phased normal SNP file       : " << o.snp_file << "\ntumor SNP file               : " << o.tumor_vcf << "\n";
     e << "normal BAM file              : " << o.bam << "\ntumor BAM file               : " << o.tumor_bam << "\n";
@@ -262,12 +279,15 @@ int load_union(lpsh_som &job) {
     std::cerr << "parsing tumor SNP VCF ... ";
     lpsh::load_sample_vcf(job.opt.tumor_vcf, true, tum);
     std::cerr << difftime(time(NULL), t0) << "s\n";
-    for (const auto &c : tum.chr_length) {
+    if (!job.opt.purity_only) for (const auto &c : tum.chr_length) {
         auto it = nor.chr_length.find(c.first);
         if (it == nor.chr_length.end()) { std::cerr << "[ERROR] (setChrVecAndChrLength) :tumor & normal VCFs chromosome count are not the same" << std::endl; return lpsh::fail("tumor & normal VCFs chromosome count are not the same"); }
         if (it->second != c.second) { std::cerr << "[ERROR] (setChrVecAndChrLength) :tumor & normal VCFs chromosome length are not the same => chr: " << c.first << std::endl; return lpsh::fail("tumor & normal VCFs chromosome length are not the same"); }
     }
-    if (tum.chr_names.empty()) {
+    if (job.opt.purity_only) {            // PurityEstimProcess keeps HaplotagProcess::setChrVecAndChrLength: the NORMAL VCF's contigs
+        job.chr_names = nor.chr_names;
+        job.chr_length = nor.chr_length;
+    } else if (tum.chr_names.empty()) {
         std::cerr << "[WARNING] tumor VCF chromosome count is empty" << std::endl;
         if (nor.chr_names.empty()) return lpsh::fail("tumor & normal VCFs chromosome count are empty");
         std::cerr << "[INFO] use normal VCF chromosome count" << std::endl;
@@ -287,7 +307,7 @@ int load_union(lpsh_som &job) {
             n_nor += u.has_nor;
             n_both += u.has_nor && u.has_tum;
         }
-    std::cerr << "Normal SNP count: " << n_nor << "\nTumor SNP count: " << n_snp << "\nOverlap SNP count: " << n_both << "\nTumor Insert count: " << n_ins
+    if (!job.opt.purity_only) std::cerr << "Normal SNP count: " << n_nor << "\nTumor SNP count: " << n_snp << "\nOverlap SNP count: " << n_both << "\nTumor Insert count: " << n_ins
               << "\nTumor Delete count: " << n_del << std::endl;
     if (!job.opt.region.empty()) {
         const size_t colon = job.opt.region.find(':');
@@ -435,8 +455,8 @@ int lpsh_som_set_extract(lpsh_som *h, int i, int which, const lps_extract_result
     return 0;
 }
 
-// runTumorPurityEstimator (+ <prefix>_purity.out) or --tumor-purity, then the calling stage and getSomaticFlag for every contig
-int lpsh_som_call(lpsh_som *h) {
+// SomaticVarCaller::runTumorPurityEstimator (+ <prefix>_purity.out), or --tumor-purity (SomaticVarCaller.cpp:826-832, 937-949)
+int lpsh_som_estimate(lpsh_som *h) {
     if (!h) return -1;
     const SomOptions &o = h->opt;
     const size_t nc = h->chr_names.size();
@@ -508,6 +528,15 @@ int lpsh_som_call(lpsh_som *h) {
     } else {
         h->purity = o.purity;
     }
+    return 0;
+}
+
+// the purity stage, then the calling stage and getSomaticFlag for every contig (SomaticVarCaller.cpp:833-866, 2397-2412)
+int lpsh_som_call(lpsh_som *h) {
+    if (!h) return -1;
+    if (lpsh_som_estimate(h) != 0) return -1;
+    const SomOptions &o = h->opt;
+    const size_t nc = h->chr_names.size();
     std::time_t t0 = time(NULL);
     std::cerr << "calling somatic variants ... ";
     int failed = 0;
@@ -796,6 +825,13 @@ int lpsh_som_run(lpsh_som *h) {
         std::cerr << difftime(time(NULL), t0) << "s\n";
     }
     h->pack = lpsh::PackedContig();
+    if (h->opt.purity_only) {             // PurityEstimProcess::estimatePurity + printExecutionReport (PurityEstimationProcess.cpp:44-77)
+        if (rc == 0) rc = lpsh_som_estimate(h);
+        if (ctx) lps_ctx_destroy(ctx);
+        std::cerr << "-------------------------------------------\ntotal process time:    " << difftime(time(NULL), h->t_begin) << "s\n"
+                  << "estimated tumor purity: " << h->purity << "\n-------------------------------------------\n";
+        return rc != 0 ? -1 : 0;
+    }
     if (rc == 0) rc = lpsh_som_call(h);
     SomDeviceJudge d;
     d.ctx = ctx;

@@ -54,6 +54,7 @@ def som_lib():
     lib.lpsh_som_pack.argtypes = [vp, C.c_int, C.c_int, C.POINTER(hc.LpshPacked), C.POINTER(ffi.LpsTumorVariants)]
     lib.lpsh_som_set_extract.argtypes = [vp, C.c_int, C.c_int, C.POINTER(ffi.LpsExtractResult)]
     lib.lpsh_som_call.argtypes = [vp]
+    lib.lpsh_som_estimate.argtypes = [vp]
     lib.lpsh_som_purity.argtypes = [vp]
     lib.lpsh_som_purity.restype = C.c_double
     lib.lpsh_som_n_somatic.argtypes = [vp]
@@ -211,6 +212,45 @@ def test_somatic_host_files_match_reference(tmp_path_factory, tmp_path, extra):
         assert open(tmp_path / "own" / "som_purity.out").read() == open(tmp_path / "ref" / "som_purity.out").read()
     else:
         assert not os.path.exists(tmp_path / "own" / "som_purity.out") and not os.path.exists(tmp_path / "ref" / "som_purity.out")
+
+
+@needs_host
+@needs_ref
+def test_estimate_purity_host_matches_reference(tmp_path_factory, tmp_path):
+    """`estimate_purity` (PurityEstimation.cpp): the two extract passes with its own defaults (-q 20, supplementary included) and the
+    purity stage; <prefix>_purity.out identical to the reference's."""
+    files = dataset(tmp_path_factory)
+    args = ["estimate_purity", "-s", files["normal_vcf"], "-b", files["normal_bam"], "--tumor-snv-file", files["tumor_vcf"], "--tumor-bam-file",
+            files["tumor_bam"], "-r", files["fasta"], "-o", "pur", "-t", "2"]
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + args)
+    lib = som_lib()
+    os.makedirs(tmp_path / "own")
+    old = os.getcwd()
+    os.chdir(str(tmp_path / "own"))
+    try:
+        h = C.c_void_p()
+        n, av = hc.argv(args)
+        assert lib.lpsh_som_open(n, av, C.byref(h)) == 0, lib.lpsh_last_error()
+        xp = ffi.LpsTagParams()
+        lib.lpsh_som_params(h, 0, C.byref(xp))
+        assert xp.mapping_quality == 20 and xp.tag_supplementary == 1 and xp.mapq_filter == 0
+        for which, mode in ((0, "extract_normal"), (1, "extract_tumor")):
+            for i in range(lib.lpsh_som_n_contigs(h)):
+                pk, tv = hc.LpshPacked(), ffi.LpsTumorVariants()
+                assert lib.lpsh_som_pack(h, i, which, C.byref(pk), C.byref(tv)) == 0, lib.lpsh_last_error()
+                o = po.OracleSomatic(union_contig(pk, tv), xp, mode)
+                keep = []
+                r = extract_struct(o, keep)
+                assert lib.lpsh_som_set_extract(h, i, which, C.byref(r)) == 0
+        assert lib.lpsh_som_estimate(h) == 0, lib.lpsh_last_error()
+        purity = lib.lpsh_som_purity(h)
+        lib.lpsh_som_close(h)
+    finally:
+        os.chdir(old)
+    assert 0.0 < purity <= 1.0
+    own = open(tmp_path / "own" / "pur_purity.out").read()
+    assert own == open(tmp_path / "ref" / "pur_purity.out").read()
+    assert ("Tumor purity: %g" % purity) in own or "Tumor purity: " in own
 
 
 @needs_host
