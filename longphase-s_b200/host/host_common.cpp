@@ -50,6 +50,74 @@ int device_count() {
     return n;
 }
 
+// ---- BAM region through a batched inflater -----------------------------------------------------------------------------------
+namespace {
+lpsh_inflate_fn g_inflater = nullptr;
+void *g_inflater_user = nullptr;
+
+int device_inflate(void *, const uint8_t *data, uint64_t n_bytes, const lps_bgzf_block *blocks, uint64_t n_blocks, uint8_t *out, uint64_t out_cap) {
+    lps_ctx *ctx = nullptr;
+    if (lps_ctx_create(0, &ctx) != 0) return fail("no usable CUDA device (there is no CPU fallback)");
+    const int rc = lps_bgzf_inflate(ctx, data, n_bytes, blocks, n_blocks, out, out_cap, 1);
+    if (rc != 0) fail(std::string("lps_bgzf_inflate: ") + lps_last_error(ctx));
+    lps_ctx_destroy(ctx);
+    return rc;
+}
+
+uint32_t rd32(const uint8_t *q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24; }
+}  // namespace
+
+int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, PackedContig &pc) {
+    if (!itr || itr->multi || itr->is_cram) return 0;
+    if (itr->n_off <= 0) return 1;                                       // no index chunk overlaps the region: no record
+    uint64_t u = itr->off[0].u, v = itr->off[0].v;
+    for (int k = 1; k < itr->n_off; k++) { u = std::min(u, itr->off[k].u); v = std::max(v, itr->off[k].v); }
+    const uint64_t c0 = u >> 16, c1 = v >> 16, u0 = u & 0xFFFF, v1 = v & 0xFFFF;
+    FILE *f = fopen(bam_path.c_str(), "rb");
+    if (!f) return fail("cannot open " + bam_path);
+    uint64_t end = c1;
+    if (v1 != 0) {                                                       // the member at c1 is needed up to v1: BSIZE from its header
+        uint8_t hd[18];
+        if (fseeko(f, (off_t)c1, SEEK_SET) != 0 || fread(hd, 1, 18, f) != 18 || hd[0] != 0x1f || hd[1] != 0x8b || hd[12] != 'B' || hd[13] != 'C') { fclose(f); return 0; }
+        end = c1 + ((uint64_t)hd[16] | (uint64_t)hd[17] << 8) + 1;
+    }
+    if (end <= c0) { fclose(f); return 1; }
+    std::vector<uint8_t> comp((size_t)(end - c0));
+    if (fseeko(f, (off_t)c0, SEEK_SET) != 0 || fread(comp.data(), 1, comp.size(), f) != comp.size()) { fclose(f); return fail("short read from " + bam_path); }
+    fclose(f);
+    uint64_t n_blocks = 0, out_bytes = 0;
+    int rc = lps_bgzf_scan(comp.data(), comp.size(), nullptr, 0, &n_blocks, &out_bytes);
+    if (rc == LPS_E_DATA) return fail("malformed BGZF member in " + bam_path);
+    std::vector<lps_bgzf_block> blocks((size_t)n_blocks);
+    rc = lps_bgzf_scan(comp.data(), comp.size(), blocks.data(), n_blocks, &n_blocks, &out_bytes);
+    if (rc != 0) return fail("lps_bgzf_scan failed on " + bam_path);
+    std::vector<uint8_t> raw((size_t)out_bytes + 8);
+    rc = (g_inflater ? g_inflater : device_inflate)(g_inflater ? g_inflater_user : nullptr, comp.data(), comp.size(), blocks.data(), n_blocks, raw.data(), out_bytes);
+    if (rc != 0) return rc < 0 ? rc : -1;
+    std::vector<uint8_t>().swap(comp);
+    const uint64_t stop = v1 != 0 ? blocks.back().out_off + v1 : out_bytes;
+    // records from u0 up to `stop`, accepted as hts_itr_next accepts them (hts.c): same contig, starts before the region's end
+    // (else the scan is over), ends after its start
+    for (uint64_t at = u0; at + 4 <= stop;) {
+        const uint32_t block_size = rd32(raw.data() + at);
+        if (block_size < 32 || at + 4 + block_size > out_bytes) return fail("truncated BAM record in " + bam_path);
+        const uint8_t *p = raw.data() + at + 4;
+        const int32_t tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
+        if (tid != itr->tid || (hts_pos_t)pos >= itr->end) break;
+        const uint32_t l_name = p[8], n_cig = (uint32_t)p[12] | (uint32_t)p[13] << 8, flag = (uint32_t)p[14] | (uint32_t)p[15] << 8;
+        int64_t rlen = 1;                                               // bam_endpos (sam.c)
+        if (!(flag & BAM_FUNMAP) && n_cig > 0) {
+            rlen = 0;
+            const uint8_t *cg = p + 32 + l_name;
+            for (uint32_t k = 0; k < n_cig; k++) { const uint32_t w = rd32(cg + 4 * k); if (bam_cigar_type(w & 15u) & 2) rlen += w >> 4; }
+            if (rlen == 0) rlen = 1;
+        }
+        if ((hts_pos_t)pos + rlen > itr->beg && !pc.add_raw_record(p, block_size)) return 0;   // long-CIGAR record: let htslib read the contig
+        at += 4ull + block_size;
+    }
+    return 1;
+}
+
 // ---- VcfParser::parserProcess ---------------------------------------------------------------------------------------------
 namespace {
 struct TextVcfState {
@@ -148,6 +216,11 @@ void load_sample_vcf(const std::string &path, bool tumor, SampleVcf &out) {
 }
 
 }  // namespace lpsh
+
+extern "C" void lpsh_set_inflater(lpsh_inflate_fn fn, void *user) {
+    lpsh::g_inflater = fn;
+    lpsh::g_inflater_user = user;
+}
 
 extern "C" const char *lpsh_last_error(void) {
     return lpsh::g_error.empty() ? lpsh::g_error_any.c_str() : lpsh::g_error.c_str();

@@ -82,6 +82,37 @@ struct PackedContig {
         names.append(bam_get_qname(b));
         names.push_back('\0');
     }
+    // the same from the bytes of a BAM record as they lie in the file (after the block_size word; BAM is little endian, SAM spec 4.2).
+    // false for a record whose real CIGAR sits in the CG tag (more than 65535 ops): the caller falls back to htslib for it
+    bool add_raw_record(const uint8_t *p, uint32_t block_size) {
+        auto le32 = [](const uint8_t *q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24; };
+        auto le16 = [](const uint8_t *q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8; };
+        const uint32_t l_name = p[8], n_cig = le16(p + 12), fl = le16(p + 14), l_seq = le32(p + 16);
+        if (32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > block_size) return false;
+        const uint8_t *name = p + 32, *cg = name + l_name, *sq = cg + 4 * n_cig, *ql = sq + (l_seq + 1) / 2;
+        if (n_cig == 2 && (le32(cg) & 15u) == 4 /* S */ && (le32(cg) >> 4) == l_seq && (le32(cg + 4) & 15u) == 3 /* N */) return false;
+        ref_start.push_back((int32_t)le32(p + 4));
+        l_qseq.push_back((int32_t)l_seq);
+        n_cigar.push_back(n_cig);
+        flag.push_back((uint16_t)fl);
+        mapq.push_back(p[9]);
+        cigar_off.push_back(cigar.size());
+        for (uint32_t k = 0; k < n_cig; k++) cigar.push_back(le32(cg + 4 * k));
+        seq_off.push_back(seq4.size());
+        seq4.insert(seq4.end(), sq, sq + (l_seq + 1) / 2);
+        qual_off.push_back(qual.size());
+        qual.insert(qual.end(), ql, ql + l_seq);
+        name_off.push_back(names.size());
+        names.append((const char *)name);
+        names.push_back('\0');
+        return true;
+    }
+    void truncate_reads(size_t n) {   // forget the alignments appended after the first n
+        if (n >= ref_start.size()) return;
+        cigar.resize((size_t)cigar_off[n]); seq4.resize((size_t)seq_off[n]); qual.resize((size_t)qual_off[n]); names.resize((size_t)name_off[n]);
+        ref_start.resize(n); l_qseq.resize(n); n_cigar.resize(n); flag.resize(n); mapq.resize(n);
+        cigar_off.resize(n); seq_off.resize(n); qual_off.resize(n); name_off.resize(n);
+    }
     int32_t n_reads() const { return (int32_t)ref_start.size(); }
     // rank of every read name in std::string order; equal names share a rank (the reference folds edge weights in
     // std::map<std::string, ...> order, PhasingGraph.cpp:697,848)
@@ -217,6 +248,13 @@ int run_chunk_pipeline(int n_contigs, ReadFn read, HandleFn handle, size_t depth
     reader.join();
     return rc;
 }
+
+// BAM region reader that inflates on the device (SURVEY 8f rank 1 wired into the host; LPS_GPU_INFLATE=1): the compressed bytes of the
+// region's index chunks are read in one piece, lps_bgzf_scan walks the members, the inflater (lps_bgzf_inflate on device 0, or the
+// hook of lpsh_set_inflater) turns them into the uncompressed BAM stream, and the records of `itr`'s region are packed straight
+// from those bytes with hts_itr_next's own acceptance test (htslib/hts.c: tid, beg < end of region, end > beg of region).
+// 1 = done, 0 = not applicable (the caller uses htslib's reader), < 0 error.
+int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, PackedContig &pc);
 
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.

@@ -131,6 +131,13 @@ lpsh_bamw *lpsh_bamw_open(const char *path, int n_contigs, const char **names, c
 int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char *names, int name_stride);
 int lpsh_bamw_close(lpsh_bamw *w);                                     /* closes and builds <path>.bai                   */
 
+/* ---- BGZF inflation hook ---------------------------------------------------------------------------------------------- *
+ * With LPS_GPU_INFLATE=1 `phase` reads a contig's BAM region as compressed bytes and inflates them in one batch; the inflater is
+ * lps_bgzf_inflate on device 0 unless a hook is installed (the CPU test-suite installs zlib to check the reader around it).     */
+typedef int (*lpsh_inflate_fn)(void *user, const uint8_t *data, uint64_t n_bytes, const lps_bgzf_block *blocks, uint64_t n_blocks,
+                               uint8_t *out, uint64_t out_cap);
+void lpsh_set_inflater(lpsh_inflate_fn fn, void *user);
+
 const char *lpsh_last_error(void);
 
 #ifdef __cplusplus

@@ -410,7 +410,17 @@ int pack_phase_contig(lpsh_phase &job, int i, htsThreadPool *pool) {
         if (pool && pool->pool) hts_set_opt(in, HTS_OPT_THREAD_POOL, pool);
         bam1_t *aln = bam_init1();
         if (it) {
-            while (sam_itr_multi_next(in, it, aln) >= 0) pc->add_alignment(aln);
+            // LPS_GPU_INFLATE=1: the region's BGZF members are inflated in one batch on the device and parsed from memory
+            // (SURVEY 8f rank 1); otherwise, or when that reader declines, htslib's reader as in the reference
+            int done = 0;
+            const char *gi = getenv("LPS_GPU_INFLATE");
+            if (gi && gi[0] == '1') {
+                const size_t before = pc->ref_start.size();
+                done = lpsh::pack_region_inflated(path, it, *pc);
+                if (done < 0) { hts_itr_destroy(it); bam_destroy1(aln); hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(in); return done; }
+                if (done == 0) pc->truncate_reads(before);
+            }
+            if (done == 0) while (sam_itr_multi_next(in, it, aln) >= 0) pc->add_alignment(aln);
             hts_itr_destroy(it);
         }
         bam_destroy1(aln);

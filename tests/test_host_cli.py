@@ -107,6 +107,73 @@ def test_phase_host_files_match_reference(tmp_path_factory, tmp_path, kind, extr
 
 
 @needs_host
+@needs_ref
+def test_phase_host_with_two_bam_files(tmp_path_factory, tmp_path):
+    """Repeated -b: the reference appends the alignments of every file to one read set per contig (ParsingBam.cpp:1251-1299); the same
+    BAM given twice doubles every read name, so the merge-by-name and the overlap filter of addEdge see pairs everywhere."""
+    files = dataset(tmp_path_factory, "plain")
+    two = dict(files)
+    args = lambda f, extra: ["phase", "-s", f["vcf"], "-b", f["bam"], "-b", f["bam"], "-r", f["fasta"], "-o", "out", "-t", "2"] + extra   # noqa: E731
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + args(two, ["--ont"]))
+    import tests.test_host_cli as me
+    saved = me.phase_args
+    me.phase_args = args
+    try:
+        seen = oracle_phase_through_host(two, ["--ont"], str(tmp_path / "own"))
+    finally:
+        me.phase_args = saved
+    names = seen["chrA"].read_names
+    assert seen["chrA"].n_reads > 800 and all(names.count(x) % 2 == 0 for x in set(names[:50]))      # every alignment came in twice
+    assert hc.strip_commandline(open(tmp_path / "own" / "out.vcf").read()) == hc.strip_commandline(open(tmp_path / "ref" / "out.vcf").read())
+
+
+INFLATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(ffi.LpsBgzfBlock), C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64)
+
+
+@needs_host
+def test_batched_inflate_reader_packs_what_htslib_packs(tmp_path_factory, tmp_path):
+    """LPS_GPU_INFLATE=1: the region's compressed bytes -> lps_bgzf_scan -> one batched inflate -> records parsed from memory.  With zlib
+    installed as the inflater (lpsh_set_inflater) everything around the device call runs here: index chunks to file range, member
+    table, record walk with hts_itr_next's acceptance test, raw-record packing.  Every array must equal the htslib reader's."""
+    import zlib
+    files = dataset(tmp_path_factory, "plain")
+    plain = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "a"))
+    lib = hc.host_lib()
+    stats = dict(calls=0, blocks=0)
+
+    def inflate(user, data, n_bytes, blocks, n_blocks, out, out_cap):
+        try:
+            src = C.string_at(data, n_bytes)
+            for k in range(n_blocks):
+                b = blocks[k]
+                raw = zlib.decompress(src[b.comp_off:b.comp_off + b.comp_len], -15)
+                assert len(raw) == b.out_len and b.out_off + b.out_len <= out_cap and zlib.crc32(raw) == b.crc32
+                C.memmove(C.addressof(out.contents) + b.out_off, raw, len(raw))
+            stats["calls"] += 1
+            stats["blocks"] += n_blocks
+            return 0
+        except Exception as e:  # noqa: BLE001
+            print("inflate hook failed:", e)
+            return -1
+    cb = INFLATE_FN(inflate)
+    lib.lpsh_set_inflater.argtypes = [INFLATE_FN, C.c_void_p]
+    lib.lpsh_set_inflater(cb, None)
+    os.environ["LPS_GPU_INFLATE"] = "1"
+    try:
+        batched = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "b"))
+    finally:
+        os.environ.pop("LPS_GPU_INFLATE", None)
+        lib.lpsh_set_inflater(C.cast(None, INFLATE_FN), None)
+    assert stats["calls"] == 2 and stats["blocks"] > 100
+    for name in ("chrA", "chrB"):
+        a, b = plain[name], batched[name]
+        assert a.n_reads == b.n_reads and a.read_names == b.read_names
+        for k in ("ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (name, k)
+    assert open(tmp_path / "a" / "out.vcf").read() == open(tmp_path / "b" / "out.vcf").read()
+
+
+@needs_host
 def test_pack_round_trips_the_synthetic_batch(tmp_path_factory, tmp_path):
     """What htslib decodes and the host packs is the batch the generator made (region filter chr:1-lastSNP applied)."""
     files = dataset(tmp_path_factory, "plain")
