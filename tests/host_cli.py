@@ -272,3 +272,23 @@ def write_somatic_dataset(d, pairs, seed=9):
                 elif u < 0.13:
                     t.write("%s\t%d\t.\t%s\t%s\t40\tPASS\t.\tGT:PS:DP\t%s:%d:%d\n" % (name, pos, ref, alt, "0|1" if i % 2 else "1|0", 5000 + i // 30, 30))
     return out
+
+
+def bam_digest(path):
+    """sha256 of a BAM's content that does not depend on the command line: header text without the @PG line `longphase-s` adds
+    (its CL field holds the paths of the run), the reference dictionary, and every record byte."""
+    import hashlib
+    import struct
+    raw = bam_payload(path)
+    assert raw[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<i", raw, 4)[0]
+    text = raw[8:8 + l_text].rstrip(b"\0")
+    lines = [ln for ln in text.split(b"\n") if not ln.startswith(b"@PG\tID:longphase-s")]
+    h = hashlib.sha256(b"\n".join(lines))
+    h.update(raw[8 + l_text:])
+    return h.hexdigest()
+
+
+def text_digest(text):
+    import hashlib
+    return hashlib.sha256(text.encode()).hexdigest()
