@@ -289,7 +289,7 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
             pc.v_ps.push_back(v.ps);
             pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
         }
-    pc.ref = h->reference[chr];
+    pc.ref_shared = &h->reference[chr];
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }

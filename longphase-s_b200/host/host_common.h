@@ -54,6 +54,7 @@ struct PackedContig {
     std::vector<uint8_t> mapq, seq4, qual;
     std::string names;
     std::string ref;
+    const std::string *ref_shared = nullptr;   // when set, the reference string lives elsewhere (one copy per contig, not per chunk)
 
     void add_variant(int pos, const std::string &ref_text, const std::string &alt_text) {
         v_pos.push_back(pos);
@@ -148,7 +149,8 @@ struct PackedContig {
         b.cigar = cigar.data(); b.cigar_len = cigar.size();
         b.seq4 = seq4.data(); b.seq_bytes = seq4.size();
         b.qual = qual.data(); b.qual_bytes = qual.size();
-        out->ref = ref.data(); out->ref_len = (int64_t)ref.size();
+        const std::string &r = ref_shared ? *ref_shared : ref;
+        out->ref = r.data(); out->ref_len = (int64_t)r.size();
         out->names = names.data(); out->name_off = name_off.data();
     }
 };

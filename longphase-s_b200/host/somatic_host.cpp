@@ -10,7 +10,7 @@
 //   SomaticHaplotagChrProcessor::processRead / addAuxiliaryTags   src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-400, 464-472
 // The device judges whole batches (lps_extract_normal / lps_extract_tumor / lps_somatic_tag_reads); purity and calling are the
 // host stages of liblps_b200.so (lps_estimate_purity, lps_somatic_call).
-// Scope notes: --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file and --cram are
+// Scope notes: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file and --cram are
 // parsed but rejected (benchmark tooling and text logs outside the rebuilt hot path).
 #include "host_common.h"
 
@@ -41,7 +41,9 @@ const char *SOM_USAGE =
     "      --region=REGION                 chrom | chrom:start | chrom:start-end. default:\"\"(all regions)\n"
     "      --tumor-purity=Num              tumor purity (0.1~1.0). default: automatic estimation.\n"
     "      --disableFilter                 accept all tumor VCF variants as somatic. default: false.\n"
-    "not available in this build: --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file, --cram\n";
+    "      --output-somatic-vcf            write <prefix>_sc.vcf: the tumor VCF's SNP / indel records, FILTER PASS for called somatic\n"
+    "                                      variants and LowQual for the others. default: false.\n"
+    "not available in this build: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file, --cram\n";
 
 enum { S_HELP = 1, S_SUP, S_SV, S_MOD, S_REGION, S_CRAM, S_LOG, S_TUM_SNP, S_TUM_BAM, S_DISABLE_FILTER, S_PURITY, S_OUT_VCF, S_CALL_LOG,
        S_TRUTH_VCF, S_TRUTH_BED, S_BENCH_LOG };
@@ -76,6 +78,7 @@ struct SomOptions {
     int threads = 1, quality = 1;
     double percentage = 0.6, purity = 0.2;
     bool tag_supplementary = false, estimate_purity = true, enable_filter = true, unsupported = false;
+    bool write_sc_vcf = false;  // --output-somatic-vcf: <prefix>_sc.vcf
     bool purity_only = false;   // the `estimate_purity` sub-command (PurityEstimation.cpp): extract passes + purity, no calling, no tagging
     std::string snp_file, bam, tumor_vcf, tumor_bam, fasta, prefix = "result", region, command = "longphase-s ";
 };
@@ -206,7 +209,8 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
             case S_TUM_BAM: lpsh::take(optarg, o.tumor_bam); break;
             case S_DISABLE_FILTER: if (o.purity_only) bad = true; else o.enable_filter = false; break;
             case S_PURITY: if (o.purity_only) bad = true; else { lpsh::take(optarg, o.purity); o.estimate_purity = false; } break;
-            case S_CRAM: case S_LOG: case S_SV: case S_MOD: case S_OUT_VCF: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
+            case S_OUT_VCF: if (o.purity_only) bad = true; else o.write_sc_vcf = true; break;
+            case S_CRAM: case S_LOG: case S_SV: case S_MOD: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
                 o.unsupported = true; break;
             case S_HELP: std::cout << SOM_USAGE << std::endl; return 2;
             default: bad = true;
@@ -230,7 +234,7 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
         bad = true;
     }
     if (o.unsupported) {
-        std::cerr << "[ERROR] " << prog << ": --log, --output-somatic-vcf, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file "
+        std::cerr << "[ERROR] " << prog << ": --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file "
                      "and --cram are not available in this build.\n";
         bad = true;
     }
@@ -256,6 +260,7 @@ void som_banner(const SomOptions &o) {   // SomaticHaplotagProcess::printParamsM
     e << "normal BAM file              : " << o.bam << "\ntumor BAM file               : " << o.tumor_bam << "\n";
     e << "reference file               : " << o.fasta << "\n\n[Output Files]\n";
     e << "tagged tumor BAM file        : " << o.prefix + ".bam" << "\npurity estimation file       : " << (o.estimate_purity ? o.prefix + "_purity.out" : "") << "\n";
+    e << "somatic calling VCF file     : " << (o.write_sc_vcf ? o.prefix + "_sc.vcf" : "") << "\n";
     e << "-------------------------------------------\n[Somatic Haplotagging Params] \n";
     e << "number of threads            : " << o.threads << "\ntag region                   : " << (!o.region.empty() ? o.region : "all") << "\n";
     e << "filter mapping quality below : " << o.quality << "\npercentage threshold         : " << o.percentage << "\n";
@@ -367,6 +372,53 @@ void pack_union(lpsh_som &job, const std::string &chr, lpsh::PackedContig &pc, T
         t.ps.push_back(u.has_tum ? u.tum.ps : -1);
         t.is_somatic.push_back(u.is_somatic); t.derive_hp.push_back(u.derive_hp);
     }
+}
+
+// VcfParser::writingResultVCF / writeProcess (HaplotagVcfParser.cpp:60-85, 548-614): the tumor VCF's header, then only the records whose
+// TUMOR entry in the union map is a SNP, an insertion or a deletion, FILTER rewritten from the caller's verdict
+void write_sc_line(lpsh_som &job, const std::string &line, bool &wrote_command, std::ostream &out) {
+    if (line.size() >= 2 && line.compare(0, 2, "##") == 0) { out << line << std::endl; return; }
+    if (line.size() >= 6 && (line.compare(0, 6, "#CHROM") == 0 || line.compare(0, 6, "#chrom") == 0)) {
+        if (!wrote_command) {
+            out << "##longphase_s_version=" << lpsh::REFERENCE_VERSION << std::endl << "##commandline=" << job.opt.command << std::endl;
+            wrote_command = true;
+        }
+        out << line << std::endl;
+        return;
+    }
+    std::istringstream split(line);
+    std::vector<std::string> f((std::istream_iterator<std::string>(split)), std::istream_iterator<std::string>());
+    if (f.empty()) return;
+    if (f.size() < 7) { std::cerr << "[ERROR](VcfParser::writeProcess) => VCF file format error: " << line << std::endl; exit(EXIT_FAILURE); }
+    auto chr = job.variants.find(f[0]);
+    if (chr == job.variants.end()) return;
+    auto hit = chr->second.find(std::stoi(f[1]) - 1);
+    if (hit == chr->second.end() || !hit->second.has_tum) return;
+    const UnionVar &u = hit->second;
+    if (!(is_snp(u.tum) || is_ins(u.tum) || is_del(u.tum))) return;
+    if (u.is_somatic) f[6] = "PASS";
+    else if (f[6] == "PASS") f[6] = "LowQual";
+    for (size_t i = 0; i < f.size(); i++) out << (i ? "\t" : "") << f[i];
+    out << std::endl;
+}
+
+int write_sc_vcf(lpsh_som &job) {
+    const std::string &path = job.opt.tumor_vcf, out_path = job.opt.prefix + "_sc.vcf";
+    std::ofstream out(out_path.c_str());
+    if (!out.is_open()) { std::cerr << "Fail to open output file: " << out_path << "\n"; exit(EXIT_FAILURE); }
+    bool wrote_command = false;
+    if (path.find("gz") != std::string::npos) {
+        std::string text;
+        if (!lpsh::read_gz(path, text)) { std::cerr << "Fail to open vcf: " << path << "\n"; return 0; }
+        size_t at = 0;
+        for (size_t nl; (nl = text.find('\n', at)) != std::string::npos; at = nl + 1) write_sc_line(job, text.substr(at, nl - at), wrote_command, out);
+    } else if (path.find("vcf") != std::string::npos) {
+        std::ifstream in(path.c_str());
+        if (!in.is_open()) { std::cerr << "Fail to open vcf: " << path << "\n"; exit(1); }
+        std::string line;
+        while (!in.eof()) { std::getline(in, line); write_sc_line(job, line, wrote_command, out); }
+    }
+    return 0;
 }
 
 std::string contig_region(const lpsh_som &job, const std::string &chr) {
@@ -584,6 +636,12 @@ int lpsh_som_call(lpsh_som *h) {
         h->n_somatic += nt ? out.n_somatic : 0;
     }
     std::cerr << difftime(time(NULL), t0) << "s\n";
+    if (!failed && o.write_sc_vcf) {      // SomaticHaplotagProcess.cpp:77-85
+        std::time_t w0 = time(NULL);
+        std::cerr << "writing somatic variants to vcf file ... ";
+        write_sc_vcf(*h);
+        std::cerr << difftime(time(NULL), w0) << "s\n";
+    }
     return failed ? -1 : 0;
 }
 
@@ -626,7 +684,7 @@ static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
     lpsh::PackedContig &pc = ck.pack;
     TumorArrays unused;
     pack_union(*h, chr, pc, unused);
-    pc.ref = h->ref_tumor[chr];
+    pc.ref_shared = &h->ref_tumor[chr];
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }

@@ -193,7 +193,7 @@ def oracle_somatic_through_host(files, extra, cwd, chunk=300, pipelined=False):
         os.chdir(old)
 
 
-SOM_VARIANTS = [[], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20"], ["--disableFilter", "-p", "0.7"]]
+SOM_VARIANTS = [["--output-somatic-vcf"], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20"], ["--disableFilter", "-p", "0.7"]]
 
 
 @needs_host
@@ -207,6 +207,10 @@ def test_somatic_host_files_match_reference(tmp_path_factory, tmp_path, extra):
     ref, own = hc.bam_payload(str(tmp_path / "ref" / "som.bam")), hc.bam_payload(str(tmp_path / "own" / "som.bam"))
     assert b"HPZ" in own, "no HP:Z tag was written"
     assert own == ref, "tagged tumor BAM differs from the reference's (uncompressed byte stream)"
+    if "--output-somatic-vcf" in extra:
+        sc = open(tmp_path / "own" / "som_sc.vcf").read()
+        assert hc.strip_commandline(sc) == hc.strip_commandline(open(tmp_path / "ref" / "som_sc.vcf").read())
+        assert "\tLowQual\t" in sc and "\tPASS\t" in sc and "##longphase_s_version=" in sc
     if "--tumor-purity" not in extra:
         assert 0.0 < info["purity"] <= 1.0
         assert open(tmp_path / "own" / "som_purity.out").read() == open(tmp_path / "ref" / "som_purity.out").read()
@@ -257,7 +261,7 @@ def test_estimate_purity_host_matches_reference(tmp_path_factory, tmp_path):
 def test_somatic_host_rejects_bad_options(capfd):
     lib = som_lib()
     h = C.c_void_p()
-    n, av = hc.argv(["somatic_haplotag", "-s", "/nonexistent.vcf", "--tumor-purity", "1.5", "--log"])
+    n, av = hc.argv(["somatic_haplotag", "-s", "/nonexistent.vcf", "--tumor-purity", "1.5", "--log"])   # --log: per-read table, not rebuilt
     assert lib.lpsh_som_open(n, av, C.byref(h)) == 1 and not h.value
     err = capfd.readouterr().err
     assert "SNP file" in err and "invalid tumor purity" in err and "not available in this build" in err
