@@ -258,7 +258,7 @@ int lpsh_tag_begin(lpsh_tag *h) {
     if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.bam);
     if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.bam);
     const std::string out_path = o.prefix + ".bam";
-    h->out = hts_open(out_path.c_str(), "wb");
+    h->out = hts_open(out_path.c_str(), lpsh::bam_write_mode().c_str());
     if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
     hts_set_fai_filename(h->out, o.fasta.c_str());
     if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);

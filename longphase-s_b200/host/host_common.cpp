@@ -10,6 +10,12 @@ namespace lpsh {
 static thread_local std::string g_error;
 static std::string g_error_any;
 
+std::string bam_write_mode() {
+    const char *e = getenv("LPS_BAM_LEVEL");
+    if (e && e[0] >= '0' && e[0] <= '9' && e[1] == '\0') return std::string("wb") + e[0];
+    return "wb";
+}
+
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int fail(const std::string &message) {

@@ -32,6 +32,9 @@ namespace lpsh {
 // the output files carry the version of the tool whose format they follow (##longphaseVersion, @PG VN)
 static const char *const REFERENCE_VERSION = "1.0.0";
 
+// hts_open mode of the tagged BAM: "wb" as the reference, or "wb<L>" when LPS_BAM_LEVEL=0..9 is set (the BGZF writer's zlib deflate is
+// what the tagging passes wait for; a lower level trades file size for wall time, the records are the same)
+std::string bam_write_mode();
 double now_ms();                                           // monotonic clock, for the [timing] lines on stderr
 int fail(const std::string &message);                     // remembers the message for lpsh_last_error, returns -1
 bool read_gz(const std::string &path, std::string &text); // whole file through zlib (plain files pass through)

@@ -340,6 +340,26 @@ def test_haplotag_pipelined_run_matches_reference(tmp_path_factory, tmp_path, ch
 
 
 @needs_host
+@needs_ref
+def test_bam_level_changes_the_file_not_the_records(tmp_path_factory, tmp_path):
+    """LPS_BAM_LEVEL=1: a faster deflate level for the tagged BAM (the writer is what the pass waits for); same uncompressed stream."""
+    files = dataset(tmp_path_factory, "plain")
+    vcf = files.get("phased_vcf")
+    if not vcf:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        vcf = files["phased_vcf"] = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, vcf, []))
+    os.environ["LPS_BAM_LEVEL"] = "1"
+    try:
+        oracle_tag_pipelined(files, vcf, [], str(tmp_path / "own"), 400)
+    finally:
+        os.environ.pop("LPS_BAM_LEVEL", None)
+    assert hc.bam_payload(str(tmp_path / "own" / "tagged.bam")) == hc.bam_payload(str(tmp_path / "ref" / "tagged.bam"))
+    assert os.path.getsize(tmp_path / "own" / "tagged.bam") > os.path.getsize(tmp_path / "ref" / "tagged.bam")
+
+
+@needs_host
 def test_haplotag_pipelined_run_stops_on_judge_failure(tmp_path_factory, tmp_path):
     files = dataset(tmp_path_factory, "plain")
     lib = hc.host_lib()
