@@ -79,6 +79,8 @@ struct lpsh_tag {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
+    lpsh::InflatedRegion inflated;                    // LPS_GPU_INFLATE=1: the contig's region, inflated in one batch on the device
+    bool use_inflated = false;
     lpsh::Chunk chunk;                                // the chunk of the staged API (lpsh_tag_pack / lpsh_tag_emit)
     int chunk_contig = -1;
     size_t chunk_reads = 8192;                        // records per device call; small enough for htslib's asynchronous
@@ -276,6 +278,13 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
         const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
         h->itr = sam_itr_querys(h->idx, h->hdr, region.c_str());
         if (!h->itr) h->itr_done = true;
+        h->use_inflated = false;
+        h->inflated = lpsh::InflatedRegion();
+        if (h->itr && lpsh::gpu_inflate_requested()) {
+            const int got = lpsh::inflate_region(h->opt.bam, h->itr, h->inflated);
+            if (got < 0) return got;
+            h->use_inflated = got == 1;
+        }
     }
     ck.clear();
     lpsh::PackedContig &pc = ck.pack;
@@ -292,7 +301,13 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
     pc.ref_shared = &h->reference[chr];
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
-        if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
+        if (h->use_inflated) {
+            bool error = false;
+            uint32_t bs = 0;
+            const uint8_t *p = h->inflated.next(&bs, &error);
+            if (!p) { bam_destroy1(b); h->itr_done = true; if (error) return lpsh::fail("truncated BAM record in " + h->opt.bam); break; }
+            if (!lpsh::InflatedRegion::to_bam1(p, bs, b)) { bam_destroy1(b); return lpsh::fail("a record of " + h->opt.bam + " needs htslib's reader (unset LPS_GPU_INFLATE)"); }
+        } else if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
         pc.add_alignment(b);
         ck.records.push_back(b);
     }

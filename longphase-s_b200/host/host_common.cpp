@@ -73,8 +73,11 @@ int device_inflate(void *, const uint8_t *data, uint64_t n_bytes, const lps_bgzf
 uint32_t rd32(const uint8_t *q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24; }
 }  // namespace
 
-int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, PackedContig &pc) {
+// 1 = the region's uncompressed BAM stream is in r.raw (records of interest in [r.at, r.stop)), 0 = not applicable, < 0 error
+int inflate_region(const std::string &bam_path, const hts_itr_t *itr, InflatedRegion &r) {
+    r = InflatedRegion();
     if (!itr || itr->multi || itr->is_cram) return 0;
+    r.tid = itr->tid; r.beg = itr->beg; r.end = itr->end;
     if (itr->n_off <= 0) return 1;                                       // no index chunk overlaps the region: no record
     uint64_t u = itr->off[0].u, v = itr->off[0].v;
     for (int k = 1; k < itr->n_off; k++) { u = std::min(u, itr->off[k].u); v = std::max(v, itr->off[k].v); }
@@ -97,19 +100,27 @@ int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, Pack
     std::vector<lps_bgzf_block> blocks((size_t)n_blocks);
     rc = lps_bgzf_scan(comp.data(), comp.size(), blocks.data(), n_blocks, &n_blocks, &out_bytes);
     if (rc != 0) return fail("lps_bgzf_scan failed on " + bam_path);
-    std::vector<uint8_t> raw((size_t)out_bytes + 8);
-    rc = (g_inflater ? g_inflater : device_inflate)(g_inflater ? g_inflater_user : nullptr, comp.data(), comp.size(), blocks.data(), n_blocks, raw.data(), out_bytes);
+    r.raw.resize((size_t)out_bytes + 8);
+    rc = (g_inflater ? g_inflater : device_inflate)(g_inflater ? g_inflater_user : nullptr, comp.data(), comp.size(), blocks.data(), n_blocks, r.raw.data(), out_bytes);
     if (rc != 0) return rc < 0 ? rc : -1;
-    std::vector<uint8_t>().swap(comp);
-    const uint64_t stop = v1 != 0 ? blocks.back().out_off + v1 : out_bytes;
-    // records from u0 up to `stop`, accepted as hts_itr_next accepts them (hts.c): same contig, starts before the region's end
-    // (else the scan is over), ends after its start
-    for (uint64_t at = u0; at + 4 <= stop;) {
-        const uint32_t block_size = rd32(raw.data() + at);
-        if (block_size < 32 || at + 4 + block_size > out_bytes) return fail("truncated BAM record in " + bam_path);
+    r.bytes = out_bytes;
+    r.at = u0;
+    r.stop = v1 != 0 ? blocks.back().out_off + v1 : out_bytes;
+    return 1;
+}
+
+// next record of the region, accepted as hts_itr_next accepts them (hts.c): same contig, starts before the region's end (else the
+// scan is over), ends after its start.  Returns the record's bytes after the block_size word (nullptr = no more, *error set on a
+// truncated record).
+const uint8_t *InflatedRegion::next(uint32_t *block_size, bool *error) {
+    *error = false;
+    while (!done && at + 4 <= stop) {
+        const uint32_t bs = rd32(raw.data() + at);
+        if (bs < 32 || at + 4 + bs > bytes) { *error = true; done = true; return nullptr; }
         const uint8_t *p = raw.data() + at + 4;
-        const int32_t tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
-        if (tid != itr->tid || (hts_pos_t)pos >= itr->end) break;
+        const int32_t rec_tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
+        if (rec_tid != tid || (hts_pos_t)pos >= end) break;
+        at += 4ull + bs;
         const uint32_t l_name = p[8], n_cig = (uint32_t)p[12] | (uint32_t)p[13] << 8, flag = (uint32_t)p[14] | (uint32_t)p[15] << 8;
         int64_t rlen = 1;                                               // bam_endpos (sam.c)
         if (!(flag & BAM_FUNMAP) && n_cig > 0) {
@@ -118,10 +129,58 @@ int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, Pack
             for (uint32_t k = 0; k < n_cig; k++) { const uint32_t w = rd32(cg + 4 * k); if (bam_cigar_type(w & 15u) & 2) rlen += w >> 4; }
             if (rlen == 0) rlen = 1;
         }
-        if ((hts_pos_t)pos + rlen > itr->beg && !pc.add_raw_record(p, block_size)) return 0;   // long-CIGAR record: let htslib read the contig
-        at += 4ull + block_size;
+        if ((hts_pos_t)pos + rlen > beg) { *block_size = bs; return p; }
     }
-    return 1;
+    done = true;
+    return nullptr;
+}
+
+// the record as htslib's bam_read1 leaves it in a bam1_t (sam.c: core fields, name padded to a multiple of four with l_extranul NULs);
+// false for a record whose real CIGAR sits in the CG tag (bam_read1 rewrites those; the caller falls back to htslib's reader)
+bool InflatedRegion::to_bam1(const uint8_t *p, uint32_t block_size, bam1_t *b) {
+    const uint32_t l_name = p[8], n_cig = (uint32_t)p[12] | (uint32_t)p[13] << 8, l_seq = rd32(p + 16);
+    if (l_name == 0 || 32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > block_size) return false;
+    const uint8_t *cg = p + 32 + l_name;
+    if (n_cig == 2 && (rd32(cg) & 15u) == 4 && (rd32(cg) >> 4) == l_seq && (rd32(cg + 4) & 15u) == 3) return false;
+    bam1_core_t &c = b->core;
+    c.tid = (int32_t)rd32(p); c.pos = (int32_t)rd32(p + 4);
+    c.bin = (uint16_t)((uint32_t)p[10] | (uint32_t)p[11] << 8); c.qual = p[9];
+    c.flag = (uint16_t)((uint32_t)p[14] | (uint32_t)p[15] << 8); c.n_cigar = n_cig;
+    c.l_qseq = (int32_t)l_seq; c.mtid = (int32_t)rd32(p + 20); c.mpos = (int32_t)rd32(p + 24); c.isize = (int32_t)rd32(p + 28);
+    const uint32_t extranul = (l_name % 4 != 0) ? 4 - l_name % 4 : 0;
+    c.l_extranul = (uint8_t)extranul;
+    c.l_qname = (uint16_t)(l_name + extranul);
+    const size_t l_data = (size_t)block_size - 32 + extranul;
+    if (l_data > b->m_data) {
+        size_t m = l_data;
+        kroundup_size_t(m);
+        uint8_t *d = (uint8_t *)realloc(b->data, m);
+        if (!d) return false;
+        b->data = d; b->m_data = (uint32_t)m;
+    }
+    b->l_data = (int)l_data;
+    memcpy(b->data, p + 32, l_name);
+    memset(b->data + l_name, 0, extranul);
+    memcpy(b->data + l_name + extranul, p + 32 + l_name, (size_t)block_size - 32 - l_name);
+    if (p[32 + l_name - 1] != '\0') return false;                       // bam_read1 repairs a missing NUL; leave that to htslib
+    if (n_cig > 0) {                                                     // "recompute bin and check CIGAR-qlen consistency" (sam.c:782-793)
+        hts_pos_t rlen = bam_cigar2rlen((int)n_cig, bam_get_cigar(b)), qlen = bam_cigar2qlen((int)n_cig, bam_get_cigar(b));
+        if ((c.flag & BAM_FUNMAP) || rlen == 0) rlen = 1;
+        c.bin = (uint16_t)hts_reg2bin(c.pos, c.pos + rlen, 14, 5);
+        if (c.l_qseq > 0 && !(c.flag & BAM_FUNMAP) && qlen != c.l_qseq) return false;
+    }
+    return true;
+}
+
+int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, PackedContig &pc) {
+    InflatedRegion r;
+    const int rc = inflate_region(bam_path, itr, r);
+    if (rc != 1) return rc;
+    bool error = false;
+    uint32_t bs = 0;
+    while (const uint8_t *p = r.next(&bs, &error))
+        if (!pc.add_raw_record(p, bs)) return 0;                         // long-CIGAR record: let htslib read the contig
+    return error ? fail("truncated BAM record in " + bam_path) : 1;
 }
 
 // ---- VcfParser::parserProcess ---------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #define LPS_HOST_COMMON_H
 
 #include <htslib/faidx.h>
+#include <htslib/kroundup.h>
 #include <htslib/sam.h>
 #include <htslib/thread_pool.h>
 #include <htslib/vcf.h>
@@ -260,6 +261,18 @@ int run_chunk_pipeline(int n_contigs, ReadFn read, HandleFn handle, size_t depth
 // from those bytes with hts_itr_next's own acceptance test (htslib/hts.c: tid, beg < end of region, end > beg of region).
 // 1 = done, 0 = not applicable (the caller uses htslib's reader), < 0 error.
 int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, PackedContig &pc);
+// the same for the tagging passes, which need bam1_t records to tag and write: the inflated stream of a region and its record walk
+struct InflatedRegion {
+    std::vector<uint8_t> raw;
+    uint64_t bytes = 0, at = 0, stop = 0;
+    int tid = -1;
+    hts_pos_t beg = 0, end = 0;
+    bool done = false;
+    const uint8_t *next(uint32_t *block_size, bool *error);
+    static bool to_bam1(const uint8_t *record, uint32_t block_size, bam1_t *b);
+};
+int inflate_region(const std::string &bam_path, const hts_itr_t *itr, InflatedRegion &r);
+inline bool gpu_inflate_requested() { const char *e = getenv("LPS_GPU_INFLATE"); return e && e[0] == '1'; }
 
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.

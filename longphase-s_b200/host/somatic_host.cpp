@@ -173,6 +173,8 @@ struct lpsh_som {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
+    lpsh::InflatedRegion inflated;   // LPS_GPU_INFLATE=1: the contig's region of the tumor BAM, inflated in one batch on the device
+    bool use_inflated = false;
     lpsh::Chunk chunk;          // the chunk of the staged API (lpsh_som_tag_pack / lpsh_som_tag_emit)
     int chunk_contig = -1;
     size_t chunk_reads = 8192;
@@ -486,8 +488,15 @@ int lpsh_som_pack(lpsh_som *h, int i, int which, lpsh_packed *out, lps_tumor_var
     if (h->opt.threads > 1 && (pool.pool = hts_tpool_init(h->opt.threads))) hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool);
     hts_itr_t *it = sam_itr_querys(idx, hdr, contig_region(*h, chr).c_str());
     bam1_t *aln = bam_init1();
+    int inflate_rc = 0;
     if (it) {
-        while (sam_itr_multi_next(in, it, aln) >= 0) h->pack.add_alignment(aln);
+        int done = 0;
+        if (lpsh::gpu_inflate_requested()) {   // the region inflated in one batch on the device, records packed from memory
+            done = lpsh::pack_region_inflated(path, it, h->pack);
+            if (done < 0) inflate_rc = done;
+            if (done == 0) h->pack.truncate_reads(0);
+        }
+        if (done == 0) while (sam_itr_multi_next(in, it, aln) >= 0) h->pack.add_alignment(aln);
         hts_itr_destroy(it);
     }
     bam_destroy1(aln);
@@ -495,6 +504,7 @@ int lpsh_som_pack(lpsh_som *h, int i, int which, lpsh_packed *out, lps_tumor_var
     bam_hdr_destroy(hdr);
     sam_close(in);
     if (pool.pool) hts_tpool_destroy(pool.pool);
+    if (inflate_rc != 0) return inflate_rc;
     h->pack.finish();
     h->pack.view(out);
     h->tum.view(tv);
@@ -679,6 +689,13 @@ static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
         h->itr_done = false;
         h->itr = sam_itr_querys(h->idx, h->hdr, contig_region(*h, chr).c_str());
         if (!h->itr) h->itr_done = true;
+        h->use_inflated = false;
+        h->inflated = lpsh::InflatedRegion();
+        if (h->itr && lpsh::gpu_inflate_requested()) {
+            const int got = lpsh::inflate_region(h->opt.tumor_bam, h->itr, h->inflated);
+            if (got < 0) return got;
+            h->use_inflated = got == 1;
+        }
     }
     ck.clear();
     lpsh::PackedContig &pc = ck.pack;
@@ -687,7 +704,13 @@ static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
     pc.ref_shared = &h->ref_tumor[chr];
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
-        if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
+        if (h->use_inflated) {
+            bool error = false;
+            uint32_t bs = 0;
+            const uint8_t *p = h->inflated.next(&bs, &error);
+            if (!p) { bam_destroy1(b); h->itr_done = true; if (error) return lpsh::fail("truncated BAM record in " + h->opt.tumor_bam); break; }
+            if (!lpsh::InflatedRegion::to_bam1(p, bs, b)) { bam_destroy1(b); return lpsh::fail("a record of " + h->opt.tumor_bam + " needs htslib's reader (unset LPS_GPU_INFLATE)"); }
+        } else if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
         pc.add_alignment(b);
         ck.records.push_back(b);
     }

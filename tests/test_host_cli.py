@@ -130,40 +130,50 @@ def test_phase_host_with_two_bam_files(tmp_path_factory, tmp_path):
 INFLATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(ffi.LpsBgzfBlock), C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64)
 
 
+class zlib_inflater:
+    """with zlib_inflater() as stats: LPS_GPU_INFLATE=1 with zlib installed as the batched inflater (lpsh_set_inflater), so that the
+    readers around the device call run on the CPU."""
+
+    def __enter__(self):
+        import zlib
+        self.stats = stats = dict(calls=0, blocks=0)
+
+        def inflate(user, data, n_bytes, blocks, n_blocks, out, out_cap):
+            try:
+                src = C.string_at(data, n_bytes)
+                for k in range(n_blocks):
+                    b = blocks[k]
+                    raw = zlib.decompress(src[b.comp_off:b.comp_off + b.comp_len], -15)
+                    assert len(raw) == b.out_len and b.out_off + b.out_len <= out_cap and zlib.crc32(raw) == b.crc32
+                    C.memmove(C.addressof(out.contents) + b.out_off, raw, len(raw))
+                stats["calls"] += 1
+                stats["blocks"] += n_blocks
+                return 0
+            except Exception as e:  # noqa: BLE001
+                print("inflate hook failed:", e)
+                return -1
+        self.cb = INFLATE_FN(inflate)
+        lib = hc.host_lib()
+        lib.lpsh_set_inflater.argtypes = [INFLATE_FN, C.c_void_p]
+        lib.lpsh_set_inflater(self.cb, None)
+        os.environ["LPS_GPU_INFLATE"] = "1"
+        return stats
+
+    def __exit__(self, *exc):
+        os.environ.pop("LPS_GPU_INFLATE", None)
+        hc.host_lib().lpsh_set_inflater(C.cast(None, INFLATE_FN), None)
+        return False
+
+
 @needs_host
 def test_batched_inflate_reader_packs_what_htslib_packs(tmp_path_factory, tmp_path):
     """LPS_GPU_INFLATE=1: the region's compressed bytes -> lps_bgzf_scan -> one batched inflate -> records parsed from memory.  With zlib
     installed as the inflater (lpsh_set_inflater) everything around the device call runs here: index chunks to file range, member
     table, record walk with hts_itr_next's acceptance test, raw-record packing.  Every array must equal the htslib reader's."""
-    import zlib
     files = dataset(tmp_path_factory, "plain")
     plain = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "a"))
-    lib = hc.host_lib()
-    stats = dict(calls=0, blocks=0)
-
-    def inflate(user, data, n_bytes, blocks, n_blocks, out, out_cap):
-        try:
-            src = C.string_at(data, n_bytes)
-            for k in range(n_blocks):
-                b = blocks[k]
-                raw = zlib.decompress(src[b.comp_off:b.comp_off + b.comp_len], -15)
-                assert len(raw) == b.out_len and b.out_off + b.out_len <= out_cap and zlib.crc32(raw) == b.crc32
-                C.memmove(C.addressof(out.contents) + b.out_off, raw, len(raw))
-            stats["calls"] += 1
-            stats["blocks"] += n_blocks
-            return 0
-        except Exception as e:  # noqa: BLE001
-            print("inflate hook failed:", e)
-            return -1
-    cb = INFLATE_FN(inflate)
-    lib.lpsh_set_inflater.argtypes = [INFLATE_FN, C.c_void_p]
-    lib.lpsh_set_inflater(cb, None)
-    os.environ["LPS_GPU_INFLATE"] = "1"
-    try:
+    with zlib_inflater() as stats:
         batched = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "b"))
-    finally:
-        os.environ.pop("LPS_GPU_INFLATE", None)
-        lib.lpsh_set_inflater(C.cast(None, INFLATE_FN), None)
     assert stats["calls"] == 2 and stats["blocks"] > 100
     for name in ("chrA", "chrB"):
         a, b = plain[name], batched[name]
@@ -171,6 +181,26 @@ def test_batched_inflate_reader_packs_what_htslib_packs(tmp_path_factory, tmp_pa
         for k in ("ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), (name, k)
     assert open(tmp_path / "a" / "out.vcf").read() == open(tmp_path / "b" / "out.vcf").read()
+
+
+@needs_host
+@needs_ref
+@pytest.mark.parametrize("extra", [["--log"], ["--log", "--region", "chrB:20000-120000"]])
+def test_haplotag_over_the_batched_inflate_reader(tmp_path_factory, tmp_path, extra):
+    """The tagging pass reading its records from the batched-inflate stream (InflatedRegion::to_bam1 = what bam_read1 leaves in a bam1_t,
+    bin recomputed, name padding): tagged BAM and .out identical to the reference's, old HP / PS tags of the input replaced, other aux kept."""
+    files = dataset(tmp_path_factory, "plain")
+    if "phased_vcf" not in files:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        files["phased_vcf"] = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, files["phased_vcf"], extra))
+    with zlib_inflater() as stats:
+        oracle_tag_pipelined(files, files["phased_vcf"], extra, str(tmp_path / "own"), 150)
+    assert stats["calls"] == (1 if "--region" in extra else 3)
+    own = hc.bam_payload(str(tmp_path / "own" / "tagged.bam"))
+    assert own == hc.bam_payload(str(tmp_path / "ref" / "tagged.bam")) and b"XXZkeep" in own
+    assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
 
 
 @needs_host

@@ -259,6 +259,21 @@ def test_estimate_purity_host_matches_reference(tmp_path_factory, tmp_path):
 
 
 @needs_host
+@needs_ref
+def test_somatic_over_the_batched_inflate_reader(tmp_path_factory, tmp_path):
+    """LPS_GPU_INFLATE=1 with zlib as the inflater: the extract passes pack straight from the inflated stream, the tagging pass builds its
+    bam1_t records from it; same tagged tumor BAM and purity report as the reference."""
+    from .test_host_cli import zlib_inflater
+    files = dataset(tmp_path_factory)
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + som_args(files, []))
+    with zlib_inflater() as stats:
+        info = oracle_somatic_through_host(files, [], str(tmp_path / "own"), pipelined=True)
+    assert stats["calls"] == 6 and info["h3_reads"] > 50          # 2 contigs x (normal pass, tumor pass, tagging pass)
+    assert hc.bam_payload(str(tmp_path / "own" / "som.bam")) == hc.bam_payload(str(tmp_path / "ref" / "som.bam"))
+    assert open(tmp_path / "own" / "som_purity.out").read() == open(tmp_path / "ref" / "som_purity.out").read()
+
+
+@needs_host
 def test_somatic_host_rejects_bad_options(capfd):
     lib = som_lib()
     h = C.c_void_p()
