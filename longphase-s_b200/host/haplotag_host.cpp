@@ -79,6 +79,7 @@ struct lpsh_tag {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
+    lpsh::PackedContig::Sizes last_chunk;             // capacity hints for the next chunk
     lpsh::InflatedRegion inflated;                    // LPS_GPU_INFLATE=1: the contig's region, inflated in one batch on the device
     bool use_inflated = false;
     lpsh::Chunk chunk;                                // the chunk of the staged API (lpsh_tag_pack / lpsh_tag_emit)
@@ -299,6 +300,8 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
             pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
         }
     pc.ref_shared = &h->reference[chr];
+    pc.reserve_sizes(h->last_chunk);
+    ck.records.reserve(h->chunk_reads);
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (h->use_inflated) {
@@ -312,6 +315,7 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
         ck.records.push_back(b);
     }
     if (ck.records.empty()) { ck.clear(); return 0; }
+    if (ck.records.size() == h->chunk_reads) h->last_chunk = pc.sizes();
     pc.finish();
     return 1;
 }

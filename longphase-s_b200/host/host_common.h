@@ -112,6 +112,17 @@ struct PackedContig {
         names.push_back('\0');
         return true;
     }
+    // capacity hints from the previous chunk of the pass (chunks are alike): no regrowth copies while a chunk fills
+    struct Sizes { size_t reads = 0, cigar = 0, seq4 = 0, qual = 0, names = 0; };
+    Sizes sizes() const { Sizes z; z.reads = ref_start.size(); z.cigar = cigar.size(); z.seq4 = seq4.size(); z.qual = qual.size(); z.names = names.size(); return z; }
+    void reserve_sizes(const Sizes &z) {
+        auto grow = [](size_t n) { return n + n / 8 + 16; };
+        if (!z.reads) return;
+        const size_t n = grow(z.reads);
+        ref_start.reserve(n); l_qseq.reserve(n); n_cigar.reserve(n); flag.reserve(n); mapq.reserve(n);
+        cigar_off.reserve(n); seq_off.reserve(n); qual_off.reserve(n); name_off.reserve(n);
+        cigar.reserve(grow(z.cigar)); seq4.reserve(grow(z.seq4)); qual.reserve(grow(z.qual)); names.reserve(grow(z.names));
+    }
     void truncate_reads(size_t n) {   // forget the alignments appended after the first n
         if (n >= ref_start.size()) return;
         cigar.resize((size_t)cigar_off[n]); seq4.resize((size_t)seq_off[n]); qual.resize((size_t)qual_off[n]); names.resize((size_t)name_off[n]);

@@ -173,6 +173,7 @@ struct lpsh_som {
     int cur = -1;
     hts_itr_t *itr = nullptr;
     bool itr_done = false;
+    lpsh::PackedContig::Sizes last_chunk;             // capacity hints for the next chunk
     lpsh::InflatedRegion inflated;   // LPS_GPU_INFLATE=1: the contig's region of the tumor BAM, inflated in one batch on the device
     bool use_inflated = false;
     lpsh::Chunk chunk;          // the chunk of the staged API (lpsh_som_tag_pack / lpsh_som_tag_emit)
@@ -702,6 +703,8 @@ static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
     TumorArrays unused;
     pack_union(*h, chr, pc, unused);
     pc.ref_shared = &h->ref_tumor[chr];
+    pc.reserve_sizes(h->last_chunk);
+    ck.records.reserve(h->chunk_reads);
     while (!h->itr_done && ck.records.size() < h->chunk_reads) {
         bam1_t *b = bam_init1();
         if (h->use_inflated) {
@@ -715,6 +718,7 @@ static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
         ck.records.push_back(b);
     }
     if (ck.records.empty()) { ck.clear(); return 0; }
+    if (ck.records.size() == h->chunk_reads) h->last_chunk = pc.sizes();
     pc.finish();
     return 1;
 }

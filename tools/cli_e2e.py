@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--keep", default="")
+    ap.add_argument("--variants", action="store_true", help="also time the opt-in paths: LPS_GPU_INFLATE=1, LPS_BAM_LEVEL=1, both")
     a = ap.parse_args()
     d = a.keep or tempfile.mkdtemp(prefix="cli_e2e_")
     t0 = time.perf_counter()
@@ -59,6 +60,21 @@ def main():
     same_log = open(os.path.join(d, "ref", "tagged.out")).read() == open(os.path.join(d, "own", "tagged.out")).read()
     out["haplotag"] = {"reference_s": round(ref_s, 3), "own_s": round(own_s, 3), "identical_bam": same_bam, "identical_log": same_log,
                        "reads_per_s_reference": n_reads / ref_s, "reads_per_s_own": n_reads / own_s}
+    if a.variants:
+        out["variants"] = {}
+        for name, extra in (("gpu_inflate", {"LPS_GPU_INFLATE": "1"}), ("bam_level_1", {"LPS_BAM_LEVEL": "1"}),
+                            ("gpu_inflate_bam_level_1", {"LPS_GPU_INFLATE": "1", "LPS_BAM_LEVEL": "1"})):
+            env = dict(os.environ, **extra)
+            v = {}
+            if "LPS_GPU_INFLATE" in extra:
+                s_phase, err_p = timed([hc.HOST_BIN] + phase, os.path.join(d, name), env)
+                v["phase_s"] = round(s_phase, 3)
+                v["phase_identical"] = hc.strip_commandline(open(os.path.join(d, name, "out.vcf")).read()) == hc.strip_commandline(open(vcf).read())
+            s_tag, err_t = timed([hc.HOST_BIN] + tag, os.path.join(d, name), env)
+            v["haplotag_s"] = round(s_tag, 3)
+            v["haplotag_identical"] = hc.bam_payload(os.path.join(d, name, "tagged.bam")) == hc.bam_payload(os.path.join(d, "ref", "tagged.bam"))
+            v["timing"] = [ln for ln in err_t.split("\n") if ln.startswith("[timing]")]
+            out["variants"][name] = v
     out["own_timing_lines"] = [ln for ln in (own_err + tag_err).split("\n") if ln.startswith("[timing]") or ln.startswith("tag read") or ln.startswith("parsing total")]
     print(json.dumps(out))
     return 0 if (same and same_bam and same_log) else 1
