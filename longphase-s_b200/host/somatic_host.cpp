@@ -940,9 +940,10 @@ int lpsh_som_main(int argc, char **argv) {
     lpsh_som *job = nullptr;
     const int rc = lpsh_som_open(argc, argv, &job);
     if (rc == 2) return 0;
-    if (rc != 0) { if (rc < 0) std::cerr << "[ERROR] somatic_haplotag: " << lpsh_last_error() << "\n"; return 1; }
+    const char *prog = argc > 0 ? argv[0] : "somatic_haplotag";
+    if (rc != 0) { if (rc < 0) std::cerr << "[ERROR] " << prog << ": " << lpsh_last_error() << "\n"; return 1; }
     const int run = lpsh_som_run(job);
-    if (run != 0) std::cerr << "[ERROR] somatic_haplotag: " << lpsh_last_error() << "\n";
+    if (run != 0) std::cerr << "[ERROR] " << prog << ": " << lpsh_last_error() << "\n";
     lpsh_som_close(job);
     return run != 0 ? 1 : 0;
 }

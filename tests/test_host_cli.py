@@ -472,6 +472,8 @@ def test_host_binary_needs_a_gpu(tmp_path_factory, tmp_path):
     files = dataset(tmp_path_factory, "plain")
     p = subprocess.run([hc.HOST_BIN] + phase_args(files, ["--ont"]), cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 1 and "no usable CUDA device" in p.stderr and not os.path.exists(tmp_path / "out.vcf")
+    p = subprocess.run([hc.HOST_BIN] + tag_args(files, files["vcf"], []), cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 1 and "no usable CUDA device" in p.stderr
 
 
 # ---- the real thing: the binary, device and all, against the reference binary ---------------------------------------------

@@ -274,6 +274,20 @@ def test_somatic_over_the_batched_inflate_reader(tmp_path_factory, tmp_path):
 
 
 @needs_host
+def test_somatic_binaries_need_a_gpu(tmp_path_factory, tmp_path):
+    """No CPU fallback: `somatic_haplotag` and `estimate_purity` stop with an error when no CUDA device is usable."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    files = dataset(tmp_path_factory)
+    for sub in ("somatic_haplotag", "estimate_purity"):
+        args = [sub] + som_args(files, [])[1:]
+        p = subprocess.run([hc.HOST_BIN] + args, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 1 and "no usable CUDA device" in p.stderr, sub
+        assert not os.path.exists(tmp_path / "som.bam") and not os.path.exists(tmp_path / "som_purity.out")
+
+
+@needs_host
 def test_somatic_host_rejects_bad_options(capfd):
     lib = som_lib()
     h = C.c_void_p()
