@@ -204,6 +204,53 @@ def test_haplotag_over_the_batched_inflate_reader(tmp_path_factory, tmp_path, ex
 
 
 @needs_host
+@needs_ref
+def test_phase_vcf_rewrite_quirks(tmp_path):
+    """The text side of `phase` alone: 400 records on a contig without reads, with every FORMAT order, an old PS at any place, a key that
+    merely contains "PS", phased / unphased / missing / multi-allelic genotypes, indels, QUAL and FILTER variants.  Loader and writer
+    must rewrite each line exactly as SnpParser::writeLine does (colon counting, PS removal, 1|0 -> 0/1, :PS append, quality filter)."""
+    import random
+    d = str(tmp_path)
+    a = hc.synth.Contig(seed=301, contig_len=30_000, depth=5.0, mean_len=3_000.0)
+    e = hc.synth.Contig(seed=302, contig_len=20_000, depth=0.2, mean_len=2_000.0)
+    e.n_reads = 0                                            # no alignment on chrF: its records are only rewritten
+    files = hc.write_dataset(d, [("chrA", a, True), ("chrF", e, False)], fast_bam=True)
+    rng = random.Random(7)
+    ref = e.ref.decode()
+    gts = ["0/1", "1/0", "0|1", "1|0", "1/1", "0/0", "./.", "1|1", "0|0", "1/2", "0/2", "1|2", "2|1"]
+    fmts = [("GT", "{gt}"), ("GT:PS", "{gt}:{ps}"), ("GT:DP:PS", "{gt}:30:{ps}"), ("PS:GT", "{ps}:{gt}"), ("DP:GT:PS:GQ", "30:{gt}:{ps}:50"),
+            ("GT:GQ:DP", "{gt}:40:20"), ("DP:GT", "12:{gt}"), ("GT:PSX", "{gt}:9"), ("GT:AD:PS", "{gt}:3,4:{ps}")]
+    lines, pos = [], 100
+    for _ in range(400):
+        pos += rng.randint(3, 40)
+        r = ref[pos - 1].upper()
+        kind = rng.random()
+        if kind < 0.6:
+            R, alt = r, rng.choice([x for x in "ACGT" if x != r])
+        elif kind < 0.75:
+            R, alt = r, r + "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 4)))
+        elif kind < 0.9:
+            R, alt = ref[pos - 1:pos + rng.randint(1, 4)].upper(), r
+        else:
+            R, alt = r, rng.choice([x for x in "ACGT" if x != r]) + "," + rng.choice("ACGT")
+        fmt, smp = rng.choice(fmts)
+        lines.append("chrF\t%d\t.\t%s\t%s\t%s\t%s\tDP=3\t%s\t%s" % (pos, R, alt, rng.choice(["50", ".", "7.5", "30"]), rng.choice(["PASS", ".", "q10"]), fmt,
+                                                                        smp.format(gt=rng.choice(gts), ps=rng.randint(1, 5) * 100)))
+    text = open(files["vcf"]).read().split("\n")
+    hdr, body = [ln for ln in text if ln.startswith("#")], [ln for ln in text if ln and not ln.startswith("#")]
+    for extra_hdr in ('##FORMAT=<ID=PS,Number=1,Type=Integer,Description="ps">', '##FORMAT=<ID=AD,Number=R,Type=Integer,Description="ad">',
+                      '##FORMAT=<ID=PSX,Number=1,Type=Integer,Description="x">', '##FILTER=<ID=q10,Description="q">'):
+        hdr.insert(-1, extra_hdr)
+    open(files["vcf"], "w").write("\n".join(hdr + body + lines) + "\n")
+    for k, extra in enumerate((["--ont"], ["--ont", "--indels"], ["--pb", "--indels", "--indelQuality", "20"])):
+        run_in(os.path.join(d, "ref%d" % k), [hc.REF_BIN] + phase_args(files, extra))
+        oracle_phase_through_host(files, extra, os.path.join(d, "own%d" % k))
+        ref_text = hc.strip_commandline(open(os.path.join(d, "ref%d" % k, "out.vcf")).read())
+        assert hc.strip_commandline(open(os.path.join(d, "own%d" % k, "out.vcf")).read()) == ref_text, extra
+        assert ref_text.count("chrF\t") == 400
+
+
+@needs_host
 def test_pack_round_trips_the_synthetic_batch(tmp_path_factory, tmp_path):
     """What htslib decodes and the host packs is the batch the generator made (region filter chr:1-lastSNP applied)."""
     files = dataset(tmp_path_factory, "plain")
@@ -421,6 +468,43 @@ def _zero_verdicts(pk, out, calls):
     r.n_reads, r.category, r.hp = n, ffi.ptr(cat, ffi.u8p), ffi.ptr(z8, ffi.i8p)
     r.ps = r.pq = r.h1 = r.h2 = ffi.ptr(z, ffi.i32p)
     return 0
+
+
+@needs_host
+@needs_ref
+def test_haplotag_vcf_loader_quirks(tmp_path):
+    """The phased VCF as other tools write it: PS before GT, GT last, a second ALT allele (kept unless the sample text holds a '2',
+    HaplotagVcfParser.cpp:283-286), MNP records.  Same tags and the same .out as the reference."""
+    import random
+    d = str(tmp_path)
+    a = hc.synth.Contig(seed=311, contig_len=200_000, indel_frac=0.15, depth=14.0, mean_len=7_000.0)
+    files = hc.write_dataset(d, [("chrA", a, True)], fast_bam=True)
+    run_in(os.path.join(d, "p"), [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+    rng, ref, out, touched = random.Random(3), a.ref.decode(), [], 0
+    for ln in open(os.path.join(d, "p", "out.vcf")).read().split("\n"):
+        if ln and not ln.startswith("#"):
+            t = ln.split("\t")
+            fmt = t[8].split(":")
+            kv = dict(zip(fmt, t[9].split(":")))
+            u = rng.random()
+            order = (["PS", "GT"] + [k for k in fmt if k not in ("PS", "GT")]) if (u < 0.2 and "PS" in kv) else \
+                ([k for k in fmt if k != "GT"] + ["GT"]) if u < 0.3 else fmt
+            t[8], t[9] = ":".join(order), ":".join(kv[k] for k in order)
+            if u > 0.9 and len(t[3]) == 1 and len(t[4]) == 1:
+                t[4] += "," + rng.choice("ACGT")
+            if 0.85 < u < 0.9 and len(t[3]) == 1 and len(t[4]) == 1 and int(t[1]) + 2 < len(ref):
+                p = int(t[1])
+                t[3], t[4] = ref[p - 1:p + 1].upper(), t[4] + rng.choice("ACGT")
+            touched += order != fmt or "," in t[4] or len(t[3]) == 2
+            ln = "\t".join(t)
+        out.append(ln)
+    assert touched > 40
+    vcf = os.path.join(d, "odd.vcf")
+    open(vcf, "w").write("\n".join(out))
+    run_in(os.path.join(d, "ref"), [hc.REF_BIN] + tag_args(files, vcf, ["--log"]))
+    oracle_tag_pipelined(files, vcf, ["--log"], os.path.join(d, "own"), 500)
+    assert hc.bam_payload(os.path.join(d, "own", "tagged.bam")) == hc.bam_payload(os.path.join(d, "ref", "tagged.bam"))
+    assert open(os.path.join(d, "own", "tagged.out")).read() == open(os.path.join(d, "ref", "tagged.out")).read()
 
 
 @needs_host
