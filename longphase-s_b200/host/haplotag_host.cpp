@@ -5,7 +5,7 @@
 // The reference tags one record at a time inside its htslib loop (HaplotagParsingBam.cpp:453-492).  Here the loop appends
 // records to a chunk (LPS_TAG_CHUNK alignments, default 65536), one lps_tag_reads call judges the chunk on the device, and
 // the records are tagged and written in their original order, so the output file is the same byte stream.
-// Scope notes: --sv-file, --mod-file and --cram are parsed but rejected (outside the rebuilt hot path).
+// Scope notes: --sv-file and --mod-file are parsed but rejected (outside the rebuilt hot path).
 #include "host_common.h"
 
 #include <getopt.h>
@@ -33,7 +33,8 @@ const char *TAG_USAGE =
     "      -o, --out-prefix=NAME           prefix of the tagged BAM. default:result\n"
     "      --region=REGION                 chrom | chrom:start | chrom:start-end. default:\"\"(all regions)\n"
     "      --log                           an additional log file records the result of each read. default:false\n"
-    "not available in this build: --sv-file, --mod-file, --cram\n";
+    "      --cram                          the output file will be in the cram format. default:bam\n"
+    "not available in this build: --sv-file, --mod-file\n";
 
 enum { T_HELP = 1, T_SUP, T_SV, T_MOD, T_REGION, T_CRAM, T_LOG };
 
@@ -126,8 +127,8 @@ int parse_tag_options(int argc, char **argv, TagOptions &o) {   // ArgumentManag
                   << "\nthis value need: 0~1, please check -p, --percentageThreshold=Num\n";
         bad = true;
     }
-    if (!o.sv_file.empty() || !o.mod_file.empty() || o.cram) {
-        std::cerr << "[ERROR] haplotag: --sv-file, --mod-file and --cram are not available in this build.\n";
+    if (!o.sv_file.empty() || !o.mod_file.empty()) {
+        std::cerr << "[ERROR] haplotag: --sv-file and --mod-file are not available in this build.\n";
         bad = true;
     }
     if (bad) { std::cerr << "\n"; std::cout << TAG_USAGE << std::endl; return 1; }
@@ -138,7 +139,7 @@ void tag_banner(const TagOptions &o) {   // HaplotagProcess::printParamsMessage
     std::ostream &e = std::cerr;
     e << "LongPhase-S v" << lpsh::REFERENCE_VERSION << " - Haplotag (" << lps_version() << ")\n\n";
     e << "phased SNP file:   " << o.snp_file << "\nphased SV file:    " << o.sv_file << "\nphased MOD file:   " << o.mod_file << "\n";
-    e << "input bam file:    " << o.bam << "\ninput ref file:    " << o.fasta << "\noutput bam file:   " << o.prefix + ".bam" << "\n";
+    e << "input bam file:    " << o.bam << "\ninput ref file:    " << o.fasta << "\noutput bam file:   " << o.prefix + (o.cram ? ".cram" : ".bam") << "\n";
     e << "number of threads: " << o.threads << "\nwrite log file:    " << (o.log ? "true" : "false") << "\n";
     e << "log file:          " << (o.log ? (o.prefix + ".out") : "") << "\n-------------------------------------------\n";
     e << "tag region:                    " << (!o.region.empty() ? o.region : "all") << "\n";
@@ -260,8 +261,8 @@ int lpsh_tag_begin(lpsh_tag *h) {
     h->idx = sam_index_load(h->in, o.bam.c_str());
     if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.bam);
     if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.bam);
-    const std::string out_path = o.prefix + ".bam";
-    h->out = hts_open(out_path.c_str(), lpsh::bam_write_mode().c_str());
+    const std::string out_path = o.prefix + (o.cram ? ".cram" : ".bam");   // BamFileRAII: "wb" or "wc" (HaplotagParsingBam.cpp:56-60)
+    h->out = hts_open(out_path.c_str(), o.cram ? "wc" : lpsh::bam_write_mode().c_str());
     if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
     hts_set_fai_filename(h->out, o.fasta.c_str());
     if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);

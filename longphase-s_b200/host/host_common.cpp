@@ -335,6 +335,25 @@ int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char 
     return rc;
 }
 
+// BAM / CRAM -> SAM text (tests compare CRAM outputs through this)
+int lpsh_to_sam(const char *in_path, const char *fasta, const char *out_path) {
+    samFile *in = hts_open(in_path, "r");
+    if (!in) return -1;
+    if (fasta && fasta[0]) hts_set_fai_filename(in, fasta);
+    sam_hdr_t *hdr = sam_hdr_read(in);
+    samFile *out = hts_open(out_path, "w");
+    if (!hdr || !out || sam_hdr_write(out, hdr) < 0) { if (in) sam_close(in); if (out) sam_close(out); return -1; }
+    bam1_t *b = bam_init1();
+    int rc = 0, r;
+    while ((r = sam_read1(in, hdr, b)) >= 0) if (sam_write1(out, hdr, b) < 0) { rc = -1; break; }
+    if (r < -1) rc = -1;
+    bam_destroy1(b);
+    sam_hdr_destroy(hdr);
+    sam_close(in);
+    if (sam_close(out) < 0) rc = -1;
+    return rc;
+}
+
 int lpsh_bamw_close(lpsh_bamw *w) {
     if (!w) return -1;
     int rc = sam_close(w->out) < 0 ? -1 : 0;

@@ -10,7 +10,7 @@
 //   SomaticHaplotagChrProcessor::processRead / addAuxiliaryTags   src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-400, 464-472
 // The device judges whole batches (lps_extract_normal / lps_extract_tumor / lps_somatic_tag_reads); purity and calling are the
 // host stages of liblps_b200.so (lps_estimate_purity, lps_somatic_call).
-// Scope notes: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file and --cram are
+// Scope notes: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file and --mod-file are
 // parsed but rejected (benchmark tooling and text logs outside the rebuilt hot path).
 #include "host_common.h"
 
@@ -43,7 +43,8 @@ const char *SOM_USAGE =
     "      --disableFilter                 accept all tumor VCF variants as somatic. default: false.\n"
     "      --output-somatic-vcf            write <prefix>_sc.vcf: the tumor VCF's SNP / indel records, FILTER PASS for called somatic\n"
     "                                      variants and LowQual for the others. default: false.\n"
-    "not available in this build: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file, --cram\n";
+    "      --cram                          the output file will be in the cram format. default:bam\n"
+    "not available in this build: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file\n";
 
 enum { S_HELP = 1, S_SUP, S_SV, S_MOD, S_REGION, S_CRAM, S_LOG, S_TUM_SNP, S_TUM_BAM, S_DISABLE_FILTER, S_PURITY, S_OUT_VCF, S_CALL_LOG,
        S_TRUTH_VCF, S_TRUTH_BED, S_BENCH_LOG };
@@ -78,6 +79,7 @@ struct SomOptions {
     int threads = 1, quality = 1;
     double percentage = 0.6, purity = 0.2;
     bool tag_supplementary = false, estimate_purity = true, enable_filter = true, unsupported = false;
+    bool cram = false;
     bool write_sc_vcf = false;  // --output-somatic-vcf: <prefix>_sc.vcf
     bool purity_only = false;   // the `estimate_purity` sub-command (PurityEstimation.cpp): extract passes + purity, no calling, no tagging
     std::string snp_file, bam, tumor_vcf, tumor_bam, fasta, prefix = "result", region, command = "longphase-s ";
@@ -213,7 +215,8 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
             case S_DISABLE_FILTER: if (o.purity_only) bad = true; else o.enable_filter = false; break;
             case S_PURITY: if (o.purity_only) bad = true; else { lpsh::take(optarg, o.purity); o.estimate_purity = false; } break;
             case S_OUT_VCF: if (o.purity_only) bad = true; else o.write_sc_vcf = true; break;
-            case S_CRAM: case S_LOG: case S_SV: case S_MOD: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
+            case S_CRAM: if (o.purity_only) bad = true; else o.cram = true; break;
+            case S_LOG: case S_SV: case S_MOD: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
                 o.unsupported = true; break;
             case S_HELP: std::cout << SOM_USAGE << std::endl; return 2;
             default: bad = true;
@@ -237,8 +240,8 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
         bad = true;
     }
     if (o.unsupported) {
-        std::cerr << "[ERROR] " << prog << ": --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file "
-                     "and --cram are not available in this build.\n";
+        std::cerr << "[ERROR] " << prog << ": --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file and --mod-file "
+                     "are not available in this build.\n";
         bad = true;
     }
     if (bad) { std::cerr << "\n"; std::cout << SOM_USAGE << std::endl; return 1; }
@@ -262,7 +265,7 @@ void som_banner(const SomOptions &o) {   // SomaticHaplotagProcess::printParamsM
     e << "phased normal SNP file       : " << o.snp_file << "\ntumor SNP file               : " << o.tumor_vcf << "\n";
     e << "normal BAM file              : " << o.bam << "\ntumor BAM file               : " << o.tumor_bam << "\n";
     e << "reference file               : " << o.fasta << "\n\n[Output Files]\n";
-    e << "tagged tumor BAM file        : " << o.prefix + ".bam" << "\npurity estimation file       : " << (o.estimate_purity ? o.prefix + "_purity.out" : "") << "\n";
+    e << "tagged tumor BAM file        : " << o.prefix + (o.cram ? ".cram" : ".bam") << "\npurity estimation file       : " << (o.estimate_purity ? o.prefix + "_purity.out" : "") << "\n";
     e << "somatic calling VCF file     : " << (o.write_sc_vcf ? o.prefix + "_sc.vcf" : "") << "\n";
     e << "-------------------------------------------\n[Somatic Haplotagging Params] \n";
     e << "number of threads            : " << o.threads << "\ntag region                   : " << (!o.region.empty() ? o.region : "all") << "\n";
@@ -672,8 +675,8 @@ int lpsh_som_tag_begin(lpsh_som *h) {
     h->idx = sam_index_load(h->in, o.tumor_bam.c_str());
     if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.tumor_bam);
     if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.tumor_bam);
-    const std::string out_path = o.prefix + ".bam";
-    h->out = hts_open(out_path.c_str(), lpsh::bam_write_mode().c_str());
+    const std::string out_path = o.prefix + (o.cram ? ".cram" : ".bam");
+    h->out = hts_open(out_path.c_str(), o.cram ? "wc" : lpsh::bam_write_mode().c_str());
     if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
     hts_set_fai_filename(h->out, o.fasta.c_str());
     if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);

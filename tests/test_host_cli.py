@@ -437,6 +437,26 @@ def test_bam_level_changes_the_file_not_the_records(tmp_path_factory, tmp_path):
 
 
 @needs_host
+@needs_ref
+def test_haplotag_cram_output(tmp_path_factory, tmp_path):
+    """--cram: the tagged alignments as CRAM (hts_open "wc" with the FASTA, HaplotagParsingBam.cpp:56-60); decoded back to SAM text,
+    the file equals the reference's."""
+    files = dataset(tmp_path_factory, "plain")
+    if "phased_vcf" not in files:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        files["phased_vcf"] = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, files["phased_vcf"], ["--cram"]))
+    oracle_tag_pipelined(files, files["phased_vcf"], ["--cram"], str(tmp_path / "own"), 400)
+    lib = hc.host_lib()
+    lib.lpsh_to_sam.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    for side in ("ref", "own"):
+        assert lib.lpsh_to_sam(str(tmp_path / side / "tagged.cram").encode(), files["fasta"].encode(), str(tmp_path / side / "tagged.sam").encode()) == 0
+    own = open(tmp_path / "own" / "tagged.sam").read()
+    assert own == open(tmp_path / "ref" / "tagged.sam").read() and "\tHP:i:" in own and own.count("\n") > 900
+
+
+@needs_host
 def test_haplotag_pipelined_run_stops_on_judge_failure(tmp_path_factory, tmp_path):
     files = dataset(tmp_path_factory, "plain")
     lib = hc.host_lib()
