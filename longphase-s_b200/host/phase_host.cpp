@@ -1,8 +1,8 @@
 // phase_host.cpp — the `phase` sub-command above the C ABI: options, VCF / FASTA / BAM loading with htslib, SoA packing,
 // the contig loop on the GPU(s), and the phased-VCF writer.  See lps_host.h for the reference seams each stage replaces.
 //
-// Scope notes: --sv-file, --mod-file, --dot and --deepsomatic_output are accepted by the option parser (same names as the
-// reference) but rejected with a message: SV / MOD inputs are outside the hot path this repository rebuilds.
+// Scope notes: --sv-file, --mod-file and --dot are accepted by the option parser (same names as the reference) but rejected with
+// a message: SV / MOD inputs and the graph dump are outside the hot path this repository rebuilds.
 #include "host_common.h"
 
 #include <getopt.h>
@@ -12,6 +12,7 @@
 #include <ctime>
 #include <fstream>
 #include <iterator>
+#include <limits>
 #include <set>
 #include <sstream>
 
@@ -35,7 +36,8 @@ const char *PHASE_USAGE =
     "   -a, --connectAdjacent=Num   default:35         -d, --distance=Num          default:300000\n"
     "   -1, --edgeThreshold=[0~1]   default:0.7        -L, --overlapThreshold=[0~1] default:0.2\n"
     "   -m, --readConfidence=[0.5~1] default:0.65      -n, --snpConfidence=[0.5~1] default:0.75\n"
-    "not available in this build: --sv-file, --mod-file, --dot, --deepsomatic_output\n\n";
+    "   --deepsomatic_output        keep only GERMLINE records of a DeepSomatic VCF and re-genotype them from AD / VAF first.\n"
+    "not available in this build: --sv-file, --mod-file, --dot\n\n";
 
 enum { O_HELP = 1, O_DOT, O_SV, O_MOD, O_ONT, O_PB, O_INDELS, O_INDELQ, O_DEEPSOMATIC, O_VERSION };
 
@@ -163,8 +165,8 @@ int parse_phase_options(int argc, char **argv, PhaseOptions &o) {
     range(o.overlap_threshold >= 0 && o.overlap_threshold <= 1, "overlapThreshold", o.overlap_threshold, "-L, --overlapThreshold=[0~1]");
     range(o.read_confidence >= 0.5 && o.read_confidence <= 1, "readConfidence", o.read_confidence, "-m, --readConfidence=[0.5~1]");
     range(o.snp_confidence >= 0.5 && o.snp_confidence <= 1, "snpConfidence", o.snp_confidence, "-n, --snpConfidence=[0.5~1]");
-    if (!o.sv_file.empty() || !o.mod_file.empty() || o.dot || o.deepsomatic)
-        complain("phase: --sv-file, --mod-file, --dot and --deepsomatic_output are not available in this build.\n");
+    if (!o.sv_file.empty() || !o.mod_file.empty() || o.dot)
+        complain("phase: --sv-file, --mod-file and --dot are not available in this build.\n");
     if (o.connect_adjacent > 127) complain("phase: --connectAdjacent above 127 is not supported by the device path.\n");
     if (bad) { std::cerr << "\n" << PHASE_USAGE; return 1; }
     return 0;
@@ -192,6 +194,86 @@ void phase_banner(const PhaseOptions &o) {   // PhasingProcess.cpp:7-43
 bool unphased_or_phased_het(const int *gt, int n) {
     if (n < 2) return false;
     return (gt[0] == 2 && gt[1] == 4) || (gt[0] == 4 && gt[1] == 2) || (gt[0] == 2 && gt[1] == 5) || (gt[0] == 4 && gt[1] == 3);
+}
+
+// SnpParser::preprocessDeepsomaticVCF (ParsingBam.cpp:651-834): records whose FILTER mentions GERMLINE survive; their genotype becomes
+// the allele pair (a <= b) whose expected fractions (1 or 0.5 / 0.5) are closest, in squared error, to the observed allele fractions
+// taken from AD, or from VAF when AD is unusable.
+std::vector<std::string> split_on(const std::string &text, char sep) {   // std::getline's splitting: no trailing empty piece
+    std::vector<std::string> out;
+    std::istringstream in(text);
+    for (std::string piece; std::getline(in, piece, sep);) out.push_back(piece);
+    return out;
+}
+
+void preprocess_deepsomatic(const std::string &in_path, const std::string &out_path) {
+    std::ifstream in(in_path.c_str());
+    std::ofstream out(out_path.c_str());
+    if (!in.is_open()) { std::cerr << "Fail to open input VCF: " << in_path << "\n"; exit(1); }
+    if (!out.is_open()) { std::cerr << "Fail to open output VCF: " << out_path << "\n"; exit(1); }
+    for (std::string line; std::getline(in, line);) {
+        if (line.compare(0, 1, "#") == 0) { out << line << "\n"; continue; }
+        std::istringstream split(line);
+        std::vector<std::string> f((std::istream_iterator<std::string>(split)), std::istream_iterator<std::string>());
+        if (f.size() < 10 || f[6].find("GERMLINE") == std::string::npos) continue;
+        const std::vector<std::string> keys = split_on(f[8], ':');
+        std::vector<std::string> values = split_on(f[9], ':');
+        int gt = -1, vaf = -1, ad = -1;
+        for (size_t k = 0; k < keys.size(); k++) {
+            if (keys[k] == "GT") gt = (int)k;
+            if (keys[k] == "VAF") vaf = (int)k;
+            if (keys[k] == "AD") ad = (int)k;
+        }
+        if (gt >= 0 && gt < (int)values.size()) {
+            int n_alt = 0;
+            if (!f[4].empty() && f[4] != ".") for (const std::string &a : split_on(f[4], ',')) n_alt += !a.empty();
+            const int n_allele = n_alt + 1;
+            std::vector<double> seen;
+            if (ad >= 0 && ad < (int)values.size()) {
+                std::vector<long long> counts;
+                for (const std::string &tok : split_on(values[(size_t)ad], ',')) {
+                    long long c = 0;
+                    if (tok != "." && !tok.empty()) { try { c = std::stoll(tok); } catch (...) { c = 0; } }
+                    counts.push_back(c);
+                }
+                long long total = 0;
+                for (long long c : counts) total += c;
+                if (total > 0 && (int)counts.size() == n_allele) for (long long c : counts) seen.push_back((double)c / (double)total);
+            }
+            if (seen.empty() && vaf >= 0 && vaf < (int)values.size()) {
+                std::vector<double> alts;
+                for (const std::string &tok : split_on(values[(size_t)vaf], ',')) {
+                    if (tok == "." || tok.empty()) continue;
+                    try { alts.push_back(std::stod(tok)); } catch (...) {}
+                }
+                if (n_alt == (int)alts.size() && n_alt >= 1) {
+                    double sum = 0.0;
+                    for (double v : alts) sum += v;
+                    seen.push_back(std::max(0.0, 1.0 - sum));
+                    seen.insert(seen.end(), alts.begin(), alts.end());
+                }
+            }
+            if (!seen.empty()) {
+                int best_a = 0, best_b = 0;
+                double best = std::numeric_limits<double>::infinity();
+                for (int a = 0; a < n_allele; a++)
+                    for (int b = a; b < n_allele; b++) {
+                        double cost = 0.0;
+                        for (int i = 0; i < n_allele; i++) {
+                            const double want = a == b ? (i == a ? 1.0 : 0.0) : ((i == a || i == b) ? 0.5 : 0.0);
+                            const double diff = seen[(size_t)i] - want;
+                            cost += diff * diff;
+                        }
+                        if (cost < best) { best = cost; best_a = a; best_b = b; }
+                    }
+                values[(size_t)gt] = std::to_string(best_a) + "/" + std::to_string(best_b);
+                f[9].clear();
+                for (size_t k = 0; k < values.size(); k++) f[9] += (k ? ":" : "") + values[k];
+            }
+        }
+        for (size_t k = 0; k < f.size(); k++) out << (k ? "\t" : "") << f[k];
+        out << "\n";
+    }
 }
 
 int load_phase_vcf(lpsh_phase &job) {
@@ -460,6 +542,14 @@ int lpsh_phase_open(int argc, char **argv, lpsh_phase **out) {
     const int rc = parse_phase_options(argc, argv, job->opt);
     if (rc != 0) { delete job; return rc; }
     phase_banner(job->opt);
+    if (job->opt.deepsomatic) {   // PhasingProcess.cpp:47-61: the rest of the run reads the preprocessed file
+        std::time_t p0 = time(NULL);
+        std::cerr << "preprocessing DeepSomatic VCF (filter GERMLINE, adjust GT by VAF) ... ";
+        const std::string pre = job->opt.prefix + "_preprocessed.vcf";
+        preprocess_deepsomatic(job->opt.snp_file, pre);
+        std::cerr << difftime(time(NULL), p0) << "s\n";
+        job->opt.snp_file = pre;
+    }
     std::time_t t0 = time(NULL);
     std::cerr << "parsing VCF ... ";
     if (load_phase_vcf(*job) != 0) { delete job; return -1; }

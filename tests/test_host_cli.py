@@ -251,6 +251,51 @@ def test_phase_vcf_rewrite_quirks(tmp_path):
 
 
 @needs_host
+@needs_ref
+def test_phase_deepsomatic_preprocessing(tmp_path):
+    """--deepsomatic_output: GERMLINE records only, genotype re-derived from AD (or VAF) before phasing (ParsingBam.cpp:651-834);
+    <prefix>_preprocessed.vcf and the phased VCF equal the reference's."""
+    import random
+    d = str(tmp_path)
+    a = hc.synth.Contig(seed=321, contig_len=150_000, indel_frac=0.1, depth=14.0, mean_len=7_000.0)
+    files = hc.write_dataset(d, [("chrA", a, True)], fast_bam=True)
+    rng, out = random.Random(11), []
+    for ln in open(files["vcf"]).read().split("\n"):
+        if ln.startswith("#CHROM"):
+            out += ['##FILTER=<ID=GERMLINE,Description="g">', '##FILTER=<ID=SOMATIC,Description="s">', '##FORMAT=<ID=AD,Number=R,Type=Integer,Description="ad">',
+                    '##FORMAT=<ID=VAF,Number=A,Type=Float,Description="vaf">']
+        if ln and not ln.startswith("#"):
+            t = ln.split("\t")
+            t[6] = rng.choice(["GERMLINE", "GERMLINE", "GERMLINE", "SOMATIC", "PASS", "GERMLINE;LowQ"])
+            u, ref_n, alt_n = rng.random(), rng.randint(0, 30), rng.randint(0, 30)
+            vaf = "%.3f" % rng.random()
+            if u < 0.15 and len(t[3]) == 1 and len(t[4]) == 1:          # second ALT allele, three AD values
+                t[4] += "," + rng.choice([x for x in "ACGT" if x != t[4]])
+                t[8], t[9] = "GT:AD:VAF", "0/1:%d,%d,%d:%s,%s" % (ref_n, alt_n, rng.randint(0, 9), vaf, "0.05")
+            elif u < 0.5:
+                t[8], t[9] = "GT:AD:VAF", "0/1:%d,%d:%s" % (ref_n, alt_n, vaf)
+            elif u < 0.65:
+                t[8], t[9] = "GT:VAF", "1/1:%s" % vaf
+            elif u < 0.75:
+                t[8], t[9] = "GT:AD:VAF", "0/1:.,.:%s" % vaf                # AD unusable -> VAF
+            elif u < 0.85:
+                t[8], t[9] = "GT:AD", "0/0:%d" % ref_n                    # wrong AD arity and no VAF: genotype kept
+            else:
+                t[8], t[9] = "GT:DP:VAF", "0|1:30:."
+            ln = "\t".join(t)
+        out.append(ln)
+    open(files["vcf"], "w").write("\n".join(out))
+    extra = ["--ont", "--indels", "--deepsomatic_output"]
+    run_in(os.path.join(d, "ref"), [hc.REF_BIN] + phase_args(files, extra))
+    oracle_phase_through_host(files, extra, os.path.join(d, "own"))
+    pre = open(os.path.join(d, "own", "out_preprocessed.vcf")).read()
+    assert pre == open(os.path.join(d, "ref", "out_preprocessed.vcf")).read()
+    assert "SOMATIC" not in pre.split("#CHROM")[1] and "\t1/1:" in pre and "\t0/0:" in pre and "\t0/2:" in pre + "\t0/2:"
+    own = hc.strip_commandline(open(os.path.join(d, "own", "out.vcf")).read())
+    assert own == hc.strip_commandline(open(os.path.join(d, "ref", "out.vcf")).read()) and own.count("|") > 20
+
+
+@needs_host
 def test_pack_round_trips_the_synthetic_batch(tmp_path_factory, tmp_path):
     """What htslib decodes and the host packs is the batch the generator made (region filter chr:1-lastSNP applied)."""
     files = dataset(tmp_path_factory, "plain")
