@@ -335,6 +335,25 @@ int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char 
     return rc;
 }
 
+// the I/O floor of a BAM: every record through sam_read1 with `threads` BGZF threads, nothing else; returns the record count
+int64_t lpsh_decode_only(const char *in_path, int threads) {
+    samFile *in = hts_open(in_path, "r");
+    if (!in) return -1;
+    htsThreadPool pool = {NULL, 0};
+    if (threads > 1 && (pool.pool = hts_tpool_init(threads))) hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool);
+    sam_hdr_t *hdr = sam_hdr_read(in);
+    int64_t n = hdr ? 0 : -1;
+    if (hdr) {
+        bam1_t *b = bam_init1();
+        while (sam_read1(in, hdr, b) >= 0) n++;
+        bam_destroy1(b);
+        sam_hdr_destroy(hdr);
+    }
+    sam_close(in);
+    if (pool.pool) hts_tpool_destroy(pool.pool);
+    return n;
+}
+
 // BAM / CRAM -> SAM text (tests compare CRAM outputs through this)
 int lpsh_to_sam(const char *in_path, const char *fasta, const char *out_path) {
     samFile *in = hts_open(in_path, "r");

@@ -45,6 +45,14 @@ def main():
                       "bam_bytes": os.path.getsize(files["bam"]), "threads": a.threads, "make_dataset_s": round(time.perf_counter() - t0, 2)}}
     del contigs
     t = str(a.threads)
+    # the I/O floor: every record of the BAM through htslib's sam_read1 with the same number of BGZF threads, nothing else
+    import ctypes
+    lib = ctypes.CDLL(hc.HOST_LIB)
+    lib.lpsh_decode_only.restype = ctypes.c_int64
+    lib.lpsh_decode_only.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    t_dec = time.perf_counter()
+    n_dec = lib.lpsh_decode_only(files["bam"].encode(), a.threads)
+    out["sam_read1_only"] = {"s": round(time.perf_counter() - t_dec, 3), "records": int(n_dec)}
     phase = ["phase", "-s", files["vcf"], "-b", files["bam"], "-r", files["fasta"], "-o", "out", "-t", t, "--ont", "--indels"]
     ref_s, _ = timed([hc.REF_BIN] + phase, os.path.join(d, "ref"))
     own_s, own_err = timed([hc.HOST_BIN] + phase, os.path.join(d, "own"))
