@@ -183,6 +183,37 @@ int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, Pack
     return error ? fail("truncated BAM record in " + bam_path) : 1;
 }
 
+int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t end, int readers,
+                      PackedContig &pc) {
+    if (readers < 2 || end < (hts_pos_t)readers * 1000) return 0;          // not worth splitting: the caller reads the region in one piece
+    std::vector<PackedContig> parts((size_t)readers);
+    std::vector<int> rc((size_t)readers, 0);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < readers; k++)
+        workers.emplace_back([&, k] {
+            const hts_pos_t b = end * k / readers, e = end * (k + 1) / readers;
+            samFile *in = hts_open(bam_path.c_str(), "r");
+            if (!in) { rc[(size_t)k] = -1; return; }
+            if (!fasta.empty()) hts_set_fai_filename(in, fasta.c_str());
+            bam_hdr_t *hdr = sam_hdr_read(in);
+            hts_itr_t *it = hdr ? sam_itr_queryi(idx, tid, b, e) : NULL;
+            if (!it) rc[(size_t)k] = -1;
+            else {
+                bam1_t *aln = bam_init1();
+                while (sam_itr_next(in, it, aln) >= 0)
+                    if (aln->core.pos >= b) parts[(size_t)k].add_alignment(aln);   // a record that starts in an earlier slice was taken there
+                bam_destroy1(aln);
+                hts_itr_destroy(it);
+            }
+            if (hdr) bam_hdr_destroy(hdr);
+            sam_close(in);
+        });
+    for (std::thread &w : workers) w.join();
+    for (int r : rc) if (r != 0) return fail("cannot read " + bam_path);
+    pc.append_parts(parts);
+    return 1;
+}
+
 // ---- VcfParser::parserProcess ---------------------------------------------------------------------------------------------
 namespace {
 struct TextVcfState {

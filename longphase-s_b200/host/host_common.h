@@ -123,6 +123,40 @@ struct PackedContig {
         cigar_off.reserve(n); seq_off.reserve(n); qual_off.reserve(n); name_off.reserve(n);
         cigar.reserve(grow(z.cigar)); seq4.reserve(grow(z.seq4)); qual.reserve(grow(z.qual)); names.reserve(grow(z.names));
     }
+    // appends the alignments of `parts` (in that order) with one thread per part: sizes first, then every part copies itself into its
+    // slice of the grown arrays, offsets rebased
+    void append_parts(const std::vector<PackedContig> &parts) {
+        const size_t np = parts.size();
+        std::vector<size_t> r0(np + 1), c0(np + 1), s0(np + 1), q0(np + 1), n0(np + 1);
+        r0[0] = ref_start.size(); c0[0] = cigar.size(); s0[0] = seq4.size(); q0[0] = qual.size(); n0[0] = names.size();
+        for (size_t k = 0; k < np; k++) {
+            r0[k + 1] = r0[k] + parts[k].ref_start.size(); c0[k + 1] = c0[k] + parts[k].cigar.size(); s0[k + 1] = s0[k] + parts[k].seq4.size();
+            q0[k + 1] = q0[k] + parts[k].qual.size(); n0[k + 1] = n0[k] + parts[k].names.size();
+        }
+        ref_start.resize(r0[np]); l_qseq.resize(r0[np]); n_cigar.resize(r0[np]); flag.resize(r0[np]); mapq.resize(r0[np]);
+        cigar_off.resize(r0[np]); seq_off.resize(r0[np]); qual_off.resize(r0[np]); name_off.resize(r0[np]);
+        cigar.resize(c0[np]); seq4.resize(s0[np]); qual.resize(q0[np]); names.resize(n0[np]);
+        std::vector<std::thread> workers;
+        for (size_t k = 0; k < np; k++)
+            workers.emplace_back([&, k] {
+                const PackedContig &p = parts[k];
+                const size_t n = p.ref_start.size();
+                std::copy(p.ref_start.begin(), p.ref_start.end(), ref_start.begin() + (ptrdiff_t)r0[k]);
+                std::copy(p.l_qseq.begin(), p.l_qseq.end(), l_qseq.begin() + (ptrdiff_t)r0[k]);
+                std::copy(p.n_cigar.begin(), p.n_cigar.end(), n_cigar.begin() + (ptrdiff_t)r0[k]);
+                std::copy(p.flag.begin(), p.flag.end(), flag.begin() + (ptrdiff_t)r0[k]);
+                std::copy(p.mapq.begin(), p.mapq.end(), mapq.begin() + (ptrdiff_t)r0[k]);
+                for (size_t r = 0; r < n; r++) {
+                    cigar_off[r0[k] + r] = p.cigar_off[r] + c0[k]; seq_off[r0[k] + r] = p.seq_off[r] + s0[k];
+                    qual_off[r0[k] + r] = p.qual_off[r] + q0[k]; name_off[r0[k] + r] = p.name_off[r] + n0[k];
+                }
+                std::copy(p.cigar.begin(), p.cigar.end(), cigar.begin() + (ptrdiff_t)c0[k]);
+                std::copy(p.seq4.begin(), p.seq4.end(), seq4.begin() + (ptrdiff_t)s0[k]);
+                std::copy(p.qual.begin(), p.qual.end(), qual.begin() + (ptrdiff_t)q0[k]);
+                std::copy(p.names.begin(), p.names.end(), names.begin() + (ptrdiff_t)n0[k]);
+            });
+        for (std::thread &w : workers) w.join();
+    }
     void truncate_reads(size_t n) {   // forget the alignments appended after the first n
         if (n >= ref_start.size()) return;
         cigar.resize((size_t)cigar_off[n]); seq4.resize((size_t)seq_off[n]); qual.resize((size_t)qual_off[n]); names.resize((size_t)name_off[n]);
@@ -284,6 +318,12 @@ struct InflatedRegion {
 };
 int inflate_region(const std::string &bam_path, const hts_itr_t *itr, InflatedRegion &r);
 inline bool gpu_inflate_requested() { const char *e = getenv("LPS_GPU_INFLATE"); return e && e[0] == '1'; }
+
+// The alignments of tid:[0, end) of one BAM read by `readers` threads, each with its own file handle, on equal slices of the range; a
+// record belongs to the slice its start lies in, so the concatenation is the single iterator's sequence (the file is coordinate sorted).
+// Every reader inflates and parses inline: for a run with fewer contigs than threads this is where the spare threads go.
+int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t end, int readers,
+                      PackedContig &pc);
 
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.

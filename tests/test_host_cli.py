@@ -296,6 +296,26 @@ def test_phase_deepsomatic_preprocessing(tmp_path):
 
 
 @needs_host
+@pytest.mark.parametrize("readers", [3, 7])
+def test_split_region_readers_pack_the_same_batch(tmp_path_factory, tmp_path, readers):
+    """LPS_READ_SPLIT=K (what `phase -t N` does by itself when it has fewer contigs than threads): K readers on slices of the contig's
+    region, a record belonging to the slice its start lies in; the packed batch must be the single iterator's, array for array."""
+    files = dataset(tmp_path_factory, "plain")
+    plain = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "a"))
+    os.environ["LPS_READ_SPLIT"] = str(readers)
+    try:
+        split = oracle_phase_through_host(files, ["--ont", "--indels"], str(tmp_path / "b"))
+    finally:
+        os.environ.pop("LPS_READ_SPLIT", None)
+    for name in ("chrA", "chrB"):
+        a, b = plain[name], split[name]
+        assert a.n_reads == b.n_reads > 300 and a.read_names == b.read_names
+        for k in ("ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (name, k)
+    assert open(tmp_path / "a" / "out.vcf").read() == open(tmp_path / "b" / "out.vcf").read()
+
+
+@needs_host
 def test_pack_round_trips_the_synthetic_batch(tmp_path_factory, tmp_path):
     """What htslib decodes and the host packs is the batch the generator made (region filter chr:1-lastSNP applied)."""
     files = dataset(tmp_path_factory, "plain")
