@@ -183,15 +183,15 @@ int pack_region_inflated(const std::string &bam_path, const hts_itr_t *itr, Pack
     return error ? fail("truncated BAM record in " + bam_path) : 1;
 }
 
-int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t end, int readers,
-                      PackedContig &pc) {
-    if (readers < 2 || end < (hts_pos_t)readers * 1000) return 0;          // not worth splitting: the caller reads the region in one piece
+int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end,
+                      int readers, PackedContig &pc) {
+    if (readers < 2 || end - beg < (hts_pos_t)readers * 1000) return 0;    // not worth splitting: the caller reads the region in one piece
     std::vector<PackedContig> parts((size_t)readers);
     std::vector<int> rc((size_t)readers, 0);
     std::vector<std::thread> workers;
     for (int k = 0; k < readers; k++)
         workers.emplace_back([&, k] {
-            const hts_pos_t b = end * k / readers, e = end * (k + 1) / readers;
+            const hts_pos_t b = beg + (end - beg) * k / readers, e = beg + (end - beg) * (k + 1) / readers;
             samFile *in = hts_open(bam_path.c_str(), "r");
             if (!in) { rc[(size_t)k] = -1; return; }
             if (!fasta.empty()) hts_set_fai_filename(in, fasta.c_str());
@@ -201,7 +201,7 @@ int pack_region_split(const std::string &bam_path, const std::string &fasta, con
             else {
                 bam1_t *aln = bam_init1();
                 while (sam_itr_next(in, it, aln) >= 0)
-                    if (aln->core.pos >= b) parts[(size_t)k].add_alignment(aln);   // a record that starts in an earlier slice was taken there
+                    if (k == 0 || aln->core.pos >= b) parts[(size_t)k].add_alignment(aln);   // a record that starts in an earlier slice was taken there
                 bam_destroy1(aln);
                 hts_itr_destroy(it);
             }

@@ -319,11 +319,12 @@ struct InflatedRegion {
 int inflate_region(const std::string &bam_path, const hts_itr_t *itr, InflatedRegion &r);
 inline bool gpu_inflate_requested() { const char *e = getenv("LPS_GPU_INFLATE"); return e && e[0] == '1'; }
 
-// The alignments of tid:[0, end) of one BAM read by `readers` threads, each with its own file handle, on equal slices of the range; a
-// record belongs to the slice its start lies in, so the concatenation is the single iterator's sequence (the file is coordinate sorted).
-// Every reader inflates and parses inline: for a run with fewer contigs than threads this is where the spare threads go.
-int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t end, int readers,
-                      PackedContig &pc);
+// The alignments overlapping tid:[beg, end) of one BAM read by `readers` threads, each with its own file handle, on equal slices of the
+// range; a record belongs to the slice its start lies in (the first slice also takes those that start before beg), so the concatenation
+// is the single iterator's sequence (the file is coordinate sorted).  Every reader inflates and parses inline: for a run with fewer
+// contigs than threads this is where the spare threads go.  1 = done, 0 = not split (the caller reads the region in one piece), < 0 error.
+int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end,
+                      int readers, PackedContig &pc);
 
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.

@@ -504,7 +504,7 @@ int pack_phase_contig(lpsh_phase &job, int i, htsThreadPool *pool, int readers =
             }
             // spare host threads (fewer contigs than -t): the region read by several readers on slices of it, same record sequence
             if (done == 0 && readers > 1) {
-                done = lpsh::pack_region_split(path, job.opt.fasta, idx, it->tid, it->end, readers, *pc);
+                done = lpsh::pack_region_split(path, job.opt.fasta, idx, it->tid, it->beg, it->end, readers, *pc);
                 if (done < 0) { hts_itr_destroy(it); bam_destroy1(aln); hts_idx_destroy(idx); bam_hdr_destroy(hdr); sam_close(in); return done; }
             }
             if (done == 0) while (sam_itr_multi_next(in, it, aln) >= 0) pc->add_alignment(aln);

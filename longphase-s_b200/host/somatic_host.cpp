@@ -500,6 +500,14 @@ int lpsh_som_pack(lpsh_som *h, int i, int which, lpsh_packed *out, lps_tumor_var
             if (done < 0) inflate_rc = done;
             if (done == 0) h->pack.truncate_reads(0);
         }
+        if (done == 0) {   // the contigs of an extract pass come one after the other: all -t threads read slices of this one (LPS_READ_SPLIT overrides)
+            int readers = h->opt.threads >= 4 ? h->opt.threads : 1;
+            if (const char *e = getenv("LPS_READ_SPLIT")) { const int v = atoi(e); if (v >= 1) readers = v; }
+            if (readers > 1 && !it->multi) {
+                done = lpsh::pack_region_split(path, h->opt.fasta, idx, it->tid, it->beg, it->end, readers, h->pack);
+                if (done < 0) inflate_rc = done;
+            }
+        }
         if (done == 0) while (sam_itr_multi_next(in, it, aln) >= 0) h->pack.add_alignment(aln);
         hts_itr_destroy(it);
     }

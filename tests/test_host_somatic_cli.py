@@ -274,6 +274,24 @@ def test_somatic_over_the_batched_inflate_reader(tmp_path_factory, tmp_path):
 
 
 @needs_host
+@needs_ref
+@pytest.mark.parametrize("extra", [[], ["--region", "chrA:40000-260000", "--tumor-purity", "0.6"]])
+def test_somatic_extract_passes_with_split_readers(tmp_path_factory, tmp_path, extra):
+    """LPS_READ_SPLIT=5: the whole-contig batches of the two extract passes read by five readers on slices of the region (also a user region
+    that starts inside the contig: the first slice takes the alignments that start before it); same files as the reference."""
+    files = dataset(tmp_path_factory)
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + som_args(files, extra))
+    os.environ["LPS_READ_SPLIT"] = "5"
+    try:
+        oracle_somatic_through_host(files, extra, str(tmp_path / "own"), pipelined=True)
+    finally:
+        os.environ.pop("LPS_READ_SPLIT", None)
+    assert hc.bam_payload(str(tmp_path / "own" / "som.bam")) == hc.bam_payload(str(tmp_path / "ref" / "som.bam"))
+    if not extra:
+        assert open(tmp_path / "own" / "som_purity.out").read() == open(tmp_path / "ref" / "som_purity.out").read()
+
+
+@needs_host
 def test_somatic_binaries_need_a_gpu(tmp_path_factory, tmp_path):
     """No CPU fallback: `somatic_haplotag` and `estimate_purity` stop with an error when no CUDA device is usable."""
     import torch
