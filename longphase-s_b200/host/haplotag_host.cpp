@@ -321,6 +321,65 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
     return 1;
 }
 
+// ---- LPS_TAG_READERS=K: position slices of every contig's region, read by K threads with their own file handles -------------------
+namespace {
+struct TagSlice { int contig; int tid; hts_pos_t b, e; bool first; };
+struct TagReader { samFile *in = nullptr; bam_hdr_t *hdr = nullptr; };
+
+std::vector<TagSlice> tag_slices(lpsh_tag *h) {
+    hts_pos_t step = 1000000;
+    if (const char *e = getenv("LPS_TAG_SLICE_BP")) { const long v = atol(e); if (v >= 1000) step = v; }
+    std::vector<TagSlice> out;
+    for (size_t i = 0; i < h->chr_names.size(); i++) {
+        const std::string &chr = h->chr_names[i];
+        const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
+        hts_itr_t *it = sam_itr_querys(h->idx, h->hdr, region.c_str());
+        if (!it) continue;
+        hts_pos_t end = it->end;
+        const int64_t len = h->hdr->target_len && it->tid >= 0 ? (int64_t)h->hdr->target_len[it->tid] : 0;
+        if (len > 0 && end > len) end = len;                 // "chr" or "chr:start" leave the end open
+        for (hts_pos_t b = it->beg; b < end; b += step) out.push_back(TagSlice{(int)i, it->tid, b, std::min(b + step, end), b == it->beg});
+        hts_itr_destroy(it);
+    }
+    return out;
+}
+
+int read_tag_slice(lpsh_tag *h, const TagSlice &sl, TagReader &rd, lpsh::Chunk &ck) {
+    if (!rd.in) {
+        rd.in = hts_open(h->opt.bam.c_str(), "r");
+        if (!rd.in) return lpsh::fail("Cannot open bam file " + h->opt.bam);
+        hts_set_fai_filename(rd.in, h->opt.fasta.c_str());
+        rd.hdr = sam_hdr_read(rd.in);
+        if (!rd.hdr) return lpsh::fail("Cannot read header from bam file " + h->opt.bam);
+    }
+    const std::string &chr = h->chr_names[(size_t)sl.contig];
+    lpsh::PackedContig &pc = ck.pack;
+    pc.tagged_variants = true;
+    auto vars = h->variants.find(chr);
+    if (vars != h->variants.end())
+        for (const auto &kv : vars->second) {
+            pc.add_variant(kv.first, kv.second.ref, kv.second.alt);
+            pc.v_hp1_is_alt.push_back(kv.second.hp1_is_alt);
+            pc.v_ps.push_back(kv.second.ps);
+            pc.v_gt_kind.push_back(1);
+        }
+    pc.ref_shared = &h->reference[chr];
+    hts_itr_t *it = sam_itr_queryi(h->idx, sl.tid, sl.b, sl.e);
+    if (!it) return lpsh::fail("cannot query " + h->opt.bam);
+    bam1_t *b = bam_init1();
+    while (sam_itr_next(rd.in, it, b) >= 0) {
+        if (!sl.first && b->core.pos < sl.b) continue;       // starts in an earlier slice: taken there
+        pc.add_alignment(b);
+        ck.records.push_back(b);
+        b = bam_init1();
+    }
+    bam_destroy1(b);
+    hts_itr_destroy(it);
+    pc.finish();
+    return 0;
+}
+}  // namespace
+
 int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
     if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
     const int got = read_chunk(h, i, h->chunk);
@@ -468,12 +527,25 @@ int lpsh_tag_run_with(lpsh_tag *h, lpsh_tag_judge_fn judge, void *user) {
         return rc_emit;
     };
     const double m0 = lpsh::now_ms();
-    const int rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) {
-        const double r0 = lpsh::now_ms();
-        const int got = read_chunk(h, i, ck);
-        ms_read += lpsh::now_ms() - r0;
-        return got;
-    }, handle);
+    int n_readers = 1;
+    if (const char *e = getenv("LPS_TAG_READERS")) { const int v = atoi(e); if (v >= 1 && v <= 256) n_readers = v; }
+    int rc;
+    if (n_readers > 1 && !lpsh::gpu_inflate_requested()) {
+        // K readers on position slices, handled in order (opt-in: pays off once the BAM writer is no longer what the pass waits for)
+        const std::vector<TagSlice> slices = tag_slices(h);
+        std::vector<TagReader> rd((size_t)n_readers);
+        rc = lpsh::run_ordered_slices(slices.size(), n_readers, (size_t)n_readers * 2,
+                                      [&](size_t s, int r, lpsh::Chunk &ck) { return read_tag_slice(h, slices[s], rd[(size_t)r], ck); },
+                                      [&](size_t s, lpsh::Chunk &ck) { return ck.records.empty() ? 0 : handle(slices[s].contig, ck); });
+        for (TagReader &x : rd) { if (x.hdr) bam_hdr_destroy(x.hdr); if (x.in) sam_close(x.in); }
+    } else {
+        rc = lpsh::run_chunk_pipeline((int)h->chr_names.size(), [&](int i, lpsh::Chunk &ck) {
+            const double r0 = lpsh::now_ms();
+            const int got = read_chunk(h, i, ck);
+            ms_read += lpsh::now_ms() - r0;
+            return got;
+        }, handle);
+    }
     std::cerr << "tag read " << difftime(time(NULL), t0) << "s\n";
     std::cerr << "[timing] tagging pass " << (lpsh::now_ms() - m0) << " ms: " << n_chunks << " chunks; reader thread " << ms_read << " ms (parse + pack); "
               << "judge " << ms_judge << " ms; tag + write " << ms_emit << " ms\n";

@@ -326,6 +326,60 @@ inline bool gpu_inflate_requested() { const char *e = getenv("LPS_GPU_INFLATE");
 int pack_region_split(const std::string &bam_path, const std::string &fasta, const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end,
                       int readers, PackedContig &pc);
 
+// Ordered parallel readers (LPS_TAG_READERS=K): the slices of a pass are read by K threads in any order and handled by the calling
+// thread strictly in slice order, so the output is again the byte stream of the serial loop; a reader may run at most `ahead` slices
+// in front of the handler (bounded memory).
+//   read(slice, reader, chunk)  -> 0 or < 0 error      (reader threads; `reader` = 0..K-1 for per-thread file handles)
+//   handle(slice, chunk)        -> 0 or < 0 error      (calling thread only, slices 0, 1, 2, ...)
+template <class ReadFn, class HandleFn>
+int run_ordered_slices(size_t n_slices, int readers, size_t ahead, ReadFn read, HandleFn handle) {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<Chunk *> ready(n_slices, nullptr);
+    size_t next = 0, handled = 0;
+    bool stop = false, failed = false;
+    std::vector<std::thread> pool;
+    for (int r = 0; r < readers; r++)
+        pool.emplace_back([&, r] {
+            for (;;) {
+                size_t s;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return stop || next >= n_slices || next < handled + ahead; });
+                    if (stop || next >= n_slices) return;
+                    s = next++;
+                }
+                Chunk *c = new Chunk();
+                const int rc = read(s, r, *c);
+                std::lock_guard<std::mutex> lk(m);
+                if (rc < 0) { c->clear(); delete c; failed = true; stop = true; }
+                else ready[s] = c;
+                cv.notify_all();
+            }
+        });
+    int rc = 0;
+    for (size_t s = 0; s < n_slices && rc == 0; s++) {
+        Chunk *c = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return ready[s] != nullptr || failed; });
+            if (failed) { rc = -1; break; }
+            c = ready[s];
+            ready[s] = nullptr;
+        }
+        rc = handle(s, *c);
+        c->clear();
+        delete c;
+        { std::lock_guard<std::mutex> lk(m); handled = s + 1; }
+        cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    for (std::thread &t : pool) t.join();
+    for (Chunk *c : ready) if (c) { c->clear(); delete c; }
+    return rc;
+}
+
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.
 std::thread warm_up_device();

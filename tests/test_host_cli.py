@@ -522,6 +522,30 @@ def test_haplotag_cram_output(tmp_path_factory, tmp_path):
 
 
 @needs_host
+@needs_ref
+@pytest.mark.parametrize("extra", [["--log", "--tagSupplementary"], ["--log", "--region", "chrB:20000-120000"], ["--region", "chrA"]])
+def test_haplotag_ordered_slice_readers(tmp_path_factory, tmp_path, extra):
+    """LPS_TAG_READERS=3: position slices of every contig read by three threads with their own file handles, handled in slice order;
+    tagged BAM and .out are the serial loop's, i.e. the reference's."""
+    files = dataset(tmp_path_factory, "plain")
+    if "phased_vcf" not in files:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        files["phased_vcf"] = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, files["phased_vcf"], extra))
+    os.environ.update(LPS_TAG_READERS="3", LPS_TAG_SLICE_BP="30000")
+    try:
+        st = oracle_tag_pipelined(files, files["phased_vcf"], extra, str(tmp_path / "own"), 8192)
+    finally:
+        os.environ.pop("LPS_TAG_READERS", None)
+        os.environ.pop("LPS_TAG_SLICE_BP", None)
+    assert st["chunks"] >= 4
+    assert hc.bam_payload(str(tmp_path / "own" / "tagged.bam")) == hc.bam_payload(str(tmp_path / "ref" / "tagged.bam"))
+    if "--log" in extra:
+        assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
+
+
+@needs_host
 def test_haplotag_pipelined_run_stops_on_judge_failure(tmp_path_factory, tmp_path):
     files = dataset(tmp_path_factory, "plain")
     lib = hc.host_lib()
