@@ -71,7 +71,8 @@ def main():
     if a.variants:
         out["variants"] = {}
         for name, extra in (("gpu_inflate", {"LPS_GPU_INFLATE": "1"}), ("bam_level_1", {"LPS_BAM_LEVEL": "1"}),
-                            ("gpu_inflate_bam_level_1", {"LPS_GPU_INFLATE": "1", "LPS_BAM_LEVEL": "1"})):
+                            ("gpu_inflate_bam_level_1", {"LPS_GPU_INFLATE": "1", "LPS_BAM_LEVEL": "1"}),
+                            ("bam_level_1_readers_4", {"LPS_BAM_LEVEL": "1", "LPS_TAG_READERS": "4"})):
             env = dict(os.environ, **extra)
             v = {}
             if "LPS_GPU_INFLATE" in extra:
