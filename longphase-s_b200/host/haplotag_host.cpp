@@ -70,19 +70,8 @@ struct lpsh_tag {
     std::map<std::string, int> chr_length;
     std::map<std::string, std::map<int, lpsh::SampleRecord>> variants;   // phased heterozygous records of the NORMAL sample
     std::map<std::string, std::string> reference;
-    // files
-    samFile *in = nullptr, *out = nullptr;
-    bam_hdr_t *hdr = nullptr;
-    hts_idx_t *idx = nullptr;
-    htsThreadPool pool = {NULL, 0};
+    lpsh::TagBamIO io;                                // input / output BAM, index, thread pool, region reader
     std::ofstream log;
-    // contig in flight
-    int cur = -1;
-    hts_itr_t *itr = nullptr;
-    bool itr_done = false;
-    lpsh::PackedContig::Sizes last_chunk;             // capacity hints for the next chunk
-    lpsh::InflatedRegion inflated;                    // LPS_GPU_INFLATE=1: the contig's region, inflated in one batch on the device
-    bool use_inflated = false;
     lpsh::Chunk chunk;                                // the chunk of the staged API (lpsh_tag_pack / lpsh_tag_emit)
     int chunk_contig = -1;
     size_t chunk_reads = 8192;                        // records per device call; small enough for htslib's asynchronous
@@ -191,9 +180,7 @@ void write_log_header(lpsh_tag &job) {   // GermlineTagLog::addParamsMessage / w
 }
 
 void finish_contig(lpsh_tag &job) {
-    if (job.itr) hts_itr_destroy(job.itr);
-    job.itr = nullptr;
-    job.cur = -1;
+    job.io.end_region();
     job.chunk_contig = -1;
     job.chunk.clear();
 }
@@ -250,43 +237,17 @@ int lpsh_tag_begin(lpsh_tag *h) {
         write_log_header(*h);
     }
     if (load_tag_reference(*h) != 0) return -1;
-    if (!(h->pool.pool = hts_tpool_init(o.threads))) return lpsh::fail("Error creating thread pool");
-    // BamFileRAII (HaplotagParsingBam.cpp:20-82)
-    h->in = hts_open(o.bam.c_str(), "r");
-    if (!h->in) return lpsh::fail("Cannot open bam file " + o.bam);
-    if (hts_set_fai_filename(h->in, o.fasta.c_str()) != 0) return lpsh::fail("Cannot set FASTA index file for " + o.fasta);
-    h->hdr = sam_hdr_read(h->in);
-    if (!h->hdr) return lpsh::fail("Cannot read header from bam file " + o.bam);
-    sam_hdr_add_pg(h->hdr, "longphase-s", "VN", lpsh::REFERENCE_VERSION, "CL", o.command.c_str(), NULL);
-    h->idx = sam_index_load(h->in, o.bam.c_str());
-    if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.bam);
-    if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.bam);
-    const std::string out_path = o.prefix + (o.cram ? ".cram" : ".bam");   // BamFileRAII: "wb" or "wc" (HaplotagParsingBam.cpp:56-60)
-    h->out = hts_open(out_path.c_str(), o.cram ? "wc" : lpsh::bam_write_mode().c_str());
-    if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
-    hts_set_fai_filename(h->out, o.fasta.c_str());
-    if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);
-    if (hts_set_opt(h->out, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for output bam file " + o.bam);
-    return 0;
+    // BamFileRAII (HaplotagParsingBam.cpp:20-82): "wb" or "wc"
+    return h->io.open(o.bam, o.fasta, o.prefix + (o.cram ? ".cram" : ".bam"), o.cram ? "wc" : lpsh::bam_write_mode(), o.threads, o.command);
 }
 
 // next chunk of contig i into `ck`: 1 = filled, 0 = the contig is exhausted, < 0 error
 static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
     const std::string &chr = h->chr_names[(size_t)i];
-    if (h->cur != i) {
-        if (h->itr) hts_itr_destroy(h->itr);
-        h->cur = i;
-        h->itr_done = false;
+    if (h->io.cur != i) {
         const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
-        h->itr = sam_itr_querys(h->idx, h->hdr, region.c_str());
-        if (!h->itr) h->itr_done = true;
-        h->use_inflated = false;
-        h->inflated = lpsh::InflatedRegion();
-        if (h->itr && lpsh::gpu_inflate_requested()) {
-            const int got = lpsh::inflate_region(h->opt.bam, h->itr, h->inflated);
-            if (got < 0) return got;
-            h->use_inflated = got == 1;
-        }
+        const int rc = h->io.start_region(i, region);
+        if (rc < 0) return rc;
     }
     ck.clear();
     lpsh::PackedContig &pc = ck.pack;
@@ -301,22 +262,8 @@ static int read_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck) {
             pc.v_gt_kind.push_back(1);   // GenomeType::PHASED_HETERO
         }
     pc.ref_shared = &h->reference[chr];
-    pc.reserve_sizes(h->last_chunk);
-    ck.records.reserve(h->chunk_reads);
-    while (!h->itr_done && ck.records.size() < h->chunk_reads) {
-        bam1_t *b = bam_init1();
-        if (h->use_inflated) {
-            bool error = false;
-            uint32_t bs = 0;
-            const uint8_t *p = h->inflated.next(&bs, &error);
-            if (!p) { bam_destroy1(b); h->itr_done = true; if (error) return lpsh::fail("truncated BAM record in " + h->opt.bam); break; }
-            if (!lpsh::InflatedRegion::to_bam1(p, bs, b)) { bam_destroy1(b); return lpsh::fail("a record of " + h->opt.bam + " needs htslib's reader (unset LPS_GPU_INFLATE)"); }
-        } else if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
-        pc.add_alignment(b);
-        ck.records.push_back(b);
-    }
-    if (ck.records.empty()) { ck.clear(); return 0; }
-    if (ck.records.size() == h->chunk_reads) h->last_chunk = pc.sizes();
+    const int got = h->io.fill(ck, h->chunk_reads);
+    if (got <= 0) { ck.clear(); return got; }
     pc.finish();
     return 1;
 }
@@ -333,10 +280,10 @@ std::vector<TagSlice> tag_slices(lpsh_tag *h) {
     for (size_t i = 0; i < h->chr_names.size(); i++) {
         const std::string &chr = h->chr_names[i];
         const std::string region = !h->opt.region.empty() ? h->opt.region : chr + ":1-" + std::to_string(h->chr_length[chr]);
-        hts_itr_t *it = sam_itr_querys(h->idx, h->hdr, region.c_str());
+        hts_itr_t *it = sam_itr_querys(h->io.idx, h->io.hdr, region.c_str());
         if (!it) continue;
         hts_pos_t end = it->end;
-        const int64_t len = h->hdr->target_len && it->tid >= 0 ? (int64_t)h->hdr->target_len[it->tid] : 0;
+        const int64_t len = h->io.hdr->target_len && it->tid >= 0 ? (int64_t)h->io.hdr->target_len[it->tid] : 0;
         if (len > 0 && end > len) end = len;                 // "chr" or "chr:start" leave the end open
         for (hts_pos_t b = it->beg; b < end; b += step) out.push_back(TagSlice{(int)i, it->tid, b, std::min(b + step, end), b == it->beg});
         hts_itr_destroy(it);
@@ -364,7 +311,7 @@ int read_tag_slice(lpsh_tag *h, const TagSlice &sl, TagReader &rd, lpsh::Chunk &
             pc.v_gt_kind.push_back(1);
         }
     pc.ref_shared = &h->reference[chr];
-    hts_itr_t *it = sam_itr_queryi(h->idx, sl.tid, sl.b, sl.e);
+    hts_itr_t *it = sam_itr_queryi(h->io.idx, sl.tid, sl.b, sl.e);
     if (!it) return lpsh::fail("cannot query " + h->opt.bam);
     bam1_t *b = bam_init1();
     while (sam_itr_next(rd.in, it, b) >= 0) {
@@ -381,7 +328,7 @@ int read_tag_slice(lpsh_tag *h, const TagSlice &sl, TagReader &rd, lpsh::Chunk &
 }  // namespace
 
 int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
-    if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    if (!h || !out || i < 0 || (size_t)i >= h->chr_names.size() || !h->io.in) return -1;
     const int got = read_chunk(h, i, h->chunk);
     if (got == 1) { h->chunk.pack.view(out); h->chunk_contig = i; }
     return got;
@@ -390,7 +337,7 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
 static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result *r);
 
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
-    if (!h || !r || h->chunk_contig != i || !h->out) return -1;
+    if (!h || !r || h->chunk_contig != i || !h->io.out) return -1;
     return emit_chunk(h, i, h->chunk, r);
 }
 
@@ -452,7 +399,7 @@ static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result 
                 h->st_untag++;
             }
         }
-        if (sam_write1(h->out, h->hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+        if (sam_write1(h->io.out, h->io.hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
     }
     ck.clear();
     return 0;
@@ -461,14 +408,7 @@ static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result 
 int lpsh_tag_end(lpsh_tag *h) {
     if (!h) return -1;
     finish_contig(*h);
-    if (h->idx) hts_idx_destroy(h->idx);
-    if (h->hdr) bam_hdr_destroy(h->hdr);
-    if (h->in) sam_close(h->in);
-    int rc = 0;
-    if (h->out && sam_close(h->out) < 0) rc = lpsh::fail("closing the output bam failed");
-    h->idx = nullptr; h->hdr = nullptr; h->in = nullptr; h->out = nullptr;
-    if (h->pool.pool) hts_tpool_destroy(h->pool.pool);
-    h->pool.pool = NULL;
+    const int rc = h->io.close();
     if (h->log.is_open()) h->log.close();
     std::ostream &e = std::cerr;   // HaplotagProcess::printExecutionReport (HaplotagProcess.cpp:152-175)
     e << "-------------------------------------------\n";
@@ -601,7 +541,7 @@ int lpsh_tag_run(lpsh_tag *h) {
 
 void lpsh_tag_close(lpsh_tag *h) {
     if (!h) return;
-    if (h->in || h->out) lpsh_tag_end(h);
+    if (h->io.in || h->io.out) lpsh_tag_end(h);
     delete h;
 }
 

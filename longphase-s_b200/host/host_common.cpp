@@ -214,6 +214,84 @@ int pack_region_split(const std::string &bam_path, const std::string &fasta, con
     return 1;
 }
 
+// ---- files and region reader of a tagging pass ------------------------------------------------------------------------------------
+int TagBamIO::open(const std::string &bam, const std::string &fasta, const std::string &out_path, const std::string &out_mode, int threads,
+                   const std::string &command) {
+    bam_path = bam;
+    if (!(pool.pool = hts_tpool_init(threads))) return fail("Error creating thread pool");
+    in = hts_open(bam.c_str(), "r");
+    if (!in) return fail("Cannot open bam file " + bam);
+    if (hts_set_fai_filename(in, fasta.c_str()) != 0) return fail("Cannot set FASTA index file for " + fasta);
+    hdr = sam_hdr_read(in);
+    if (!hdr) return fail("Cannot read header from bam file " + bam);
+    sam_hdr_add_pg(hdr, "longphase-s", "VN", REFERENCE_VERSION, "CL", command.c_str(), NULL);
+    idx = sam_index_load(in, bam.c_str());
+    if (!idx) return fail("Cannot open index for bam file " + bam);
+    if (hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool) != 0) return fail("Cannot set thread pool for input bam file " + bam);
+    out = hts_open(out_path.c_str(), out_mode.c_str());
+    if (!out) return fail("Cannot open output bam file " + out_path);
+    hts_set_fai_filename(out, fasta.c_str());
+    if (sam_hdr_write(out, hdr) < 0) return fail("Cannot write header to output bam file " + out_path);
+    if (hts_set_opt(out, HTS_OPT_THREAD_POOL, &pool) != 0) return fail("Cannot set thread pool for output bam file " + out_path);
+    return 0;
+}
+
+int TagBamIO::start_region(int contig, const std::string &region) {
+    end_region();
+    cur = contig;
+    itr = sam_itr_querys(idx, hdr, region.c_str());
+    itr_done = itr == nullptr;
+    if (itr && gpu_inflate_requested()) {
+        const int got = inflate_region(bam_path, itr, inflated);
+        if (got < 0) return got;
+        use_inflated = got == 1;
+    }
+    return 0;
+}
+
+int TagBamIO::fill(Chunk &ck, size_t max_records) {
+    PackedContig &pc = ck.pack;
+    pc.reserve_sizes(last_chunk);
+    ck.records.reserve(max_records);
+    while (!itr_done && ck.records.size() < max_records) {
+        bam1_t *b = bam_init1();
+        if (use_inflated) {
+            bool error = false;
+            uint32_t bs = 0;
+            const uint8_t *p = inflated.next(&bs, &error);
+            if (!p) { bam_destroy1(b); itr_done = true; if (error) return fail("truncated BAM record in " + bam_path); break; }
+            if (!InflatedRegion::to_bam1(p, bs, b)) { bam_destroy1(b); return fail("a record of " + bam_path + " needs htslib's reader (unset LPS_GPU_INFLATE)"); }
+        } else if (sam_itr_multi_next(in, itr, b) < 0) { bam_destroy1(b); itr_done = true; break; }
+        pc.add_alignment(b);
+        ck.records.push_back(b);
+    }
+    if (ck.records.empty()) return 0;
+    if (ck.records.size() == max_records) last_chunk = pc.sizes();
+    return 1;
+}
+
+void TagBamIO::end_region() {
+    if (itr) hts_itr_destroy(itr);
+    itr = nullptr;
+    cur = -1;
+    itr_done = false;
+    use_inflated = false;
+    inflated = InflatedRegion();
+}
+
+int TagBamIO::close() {
+    end_region();
+    if (idx) hts_idx_destroy(idx);
+    if (hdr) bam_hdr_destroy(hdr);
+    if (in) sam_close(in);
+    int rc = 0;
+    if (out && sam_close(out) < 0) rc = fail("closing the output bam failed");
+    idx = nullptr; hdr = nullptr; in = nullptr; out = nullptr;
+    if (pool.pool) hts_tpool_destroy(pool.pool);
+    pool.pool = NULL;
+    return rc;
+}
+
 // ---- VcfParser::parserProcess ---------------------------------------------------------------------------------------------
 namespace {
 struct TextVcfState {

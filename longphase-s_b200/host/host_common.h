@@ -380,6 +380,30 @@ int run_ordered_slices(size_t n_slices, int readers, size_t ahead, ReadFn read, 
     return rc;
 }
 
+// The files of a tagging pass (BamFileRAII, src/haplotag/HaplotagParsingBam.cpp:20-82: input with index, output with the @PG line
+// `longphase-s` and the same header, one BGZF thread pool for both) and the region in flight with its chunked record reader
+// (htslib's iterator, or the batched-inflate stream when LPS_GPU_INFLATE=1).  Shared by `haplotag` and `somatic_haplotag`.
+struct TagBamIO {
+    samFile *in = nullptr, *out = nullptr;
+    bam_hdr_t *hdr = nullptr;
+    hts_idx_t *idx = nullptr;
+    htsThreadPool pool = {NULL, 0};
+    std::string bam_path;
+    int cur = -1;                      // contig whose region is being read
+    hts_itr_t *itr = nullptr;
+    bool itr_done = false, use_inflated = false;
+    InflatedRegion inflated;
+    PackedContig::Sizes last_chunk;    // capacity hints for the next chunk
+    int open(const std::string &bam, const std::string &fasta, const std::string &out_path, const std::string &out_mode, int threads,
+             const std::string &command);
+    int start_region(int contig, const std::string &region);
+    // appends up to max_records alignments of the region to ck.records / ck.pack: 1 = some, 0 = region exhausted, < 0 error
+    int fill(Chunk &ck, size_t max_records);
+    void end_region();
+    int close();
+    bool is_open() const { return in != nullptr || out != nullptr; }
+};
+
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps
 // the VCF / FASTA / first BAM reads; join before the first real lps_ctx_create.
 std::thread warm_up_device();

@@ -168,16 +168,7 @@ struct lpsh_som {
     lpsh::PackedContig pack;
     TumorArrays tum;
     // tagging pass
-    samFile *in = nullptr, *out = nullptr;
-    bam_hdr_t *hdr = nullptr;
-    hts_idx_t *idx = nullptr;
-    htsThreadPool pool = {NULL, 0};
-    int cur = -1;
-    hts_itr_t *itr = nullptr;
-    bool itr_done = false;
-    lpsh::PackedContig::Sizes last_chunk;             // capacity hints for the next chunk
-    lpsh::InflatedRegion inflated;   // LPS_GPU_INFLATE=1: the contig's region of the tumor BAM, inflated in one batch on the device
-    bool use_inflated = false;
+    lpsh::TagBamIO io;          // tumor BAM in, tagged BAM out, index, thread pool, region reader
     lpsh::Chunk chunk;          // the chunk of the staged API (lpsh_som_tag_pack / lpsh_som_tag_emit)
     int chunk_contig = -1;
     size_t chunk_reads = 8192;
@@ -432,9 +423,7 @@ std::string contig_region(const lpsh_som &job, const std::string &chr) {
 }
 
 void finish_contig(lpsh_som &job) {
-    if (job.itr) hts_itr_destroy(job.itr);
-    job.itr = nullptr;
-    job.cur = -1;
+    job.io.end_region();
     job.chunk_contig = -1;
     job.chunk.clear();
 }
@@ -673,70 +662,30 @@ int64_t lpsh_som_n_somatic(const lpsh_som *h) { return h ? h->n_somatic : 0; }
 int lpsh_som_tag_begin(lpsh_som *h) {
     if (!h) return -1;
     const SomOptions &o = h->opt;
-    if (!(h->pool.pool = hts_tpool_init(o.threads))) return lpsh::fail("Error creating thread pool");
-    h->in = hts_open(o.tumor_bam.c_str(), "r");
-    if (!h->in) return lpsh::fail("Cannot open bam file " + o.tumor_bam);
-    if (hts_set_fai_filename(h->in, o.fasta.c_str()) != 0) return lpsh::fail("Cannot set FASTA index file for " + o.fasta);
-    h->hdr = sam_hdr_read(h->in);
-    if (!h->hdr) return lpsh::fail("Cannot read header from bam file " + o.tumor_bam);
-    sam_hdr_add_pg(h->hdr, "longphase-s", "VN", lpsh::REFERENCE_VERSION, "CL", o.command.c_str(), NULL);
-    h->idx = sam_index_load(h->in, o.tumor_bam.c_str());
-    if (!h->idx) return lpsh::fail("Cannot open index for bam file " + o.tumor_bam);
-    if (hts_set_opt(h->in, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for input bam file " + o.tumor_bam);
-    const std::string out_path = o.prefix + (o.cram ? ".cram" : ".bam");
-    h->out = hts_open(out_path.c_str(), o.cram ? "wc" : lpsh::bam_write_mode().c_str());
-    if (!h->out) return lpsh::fail("Cannot open output bam file " + out_path);
-    hts_set_fai_filename(h->out, o.fasta.c_str());
-    if (sam_hdr_write(h->out, h->hdr) < 0) return lpsh::fail("Cannot write header to output bam file " + out_path);
-    if (hts_set_opt(h->out, HTS_OPT_THREAD_POOL, &h->pool) != 0) return lpsh::fail("Cannot set thread pool for output bam file " + out_path);
-    return 0;
+    return h->io.open(o.tumor_bam, o.fasta, o.prefix + (o.cram ? ".cram" : ".bam"), o.cram ? "wc" : lpsh::bam_write_mode(), o.threads, o.command);
 }
 
 // next chunk of contig i of the tumor BAM into `ck` (reads + the NORMAL side of the union map): 1 = filled, 0 = exhausted, < 0 error
 static int read_chunk(lpsh_som *h, int i, lpsh::Chunk &ck) {
     const std::string &chr = h->chr_names[(size_t)i];
-    if (h->cur != i) {
-        if (h->itr) hts_itr_destroy(h->itr);
-        h->cur = i;
-        h->itr_done = false;
-        h->itr = sam_itr_querys(h->idx, h->hdr, contig_region(*h, chr).c_str());
-        if (!h->itr) h->itr_done = true;
-        h->use_inflated = false;
-        h->inflated = lpsh::InflatedRegion();
-        if (h->itr && lpsh::gpu_inflate_requested()) {
-            const int got = lpsh::inflate_region(h->opt.tumor_bam, h->itr, h->inflated);
-            if (got < 0) return got;
-            h->use_inflated = got == 1;
-        }
+    if (h->io.cur != i) {
+        const int rc = h->io.start_region(i, contig_region(*h, chr));
+        if (rc < 0) return rc;
     }
     ck.clear();
     lpsh::PackedContig &pc = ck.pack;
     TumorArrays unused;
     pack_union(*h, chr, pc, unused);
     pc.ref_shared = &h->ref_tumor[chr];
-    pc.reserve_sizes(h->last_chunk);
-    ck.records.reserve(h->chunk_reads);
-    while (!h->itr_done && ck.records.size() < h->chunk_reads) {
-        bam1_t *b = bam_init1();
-        if (h->use_inflated) {
-            bool error = false;
-            uint32_t bs = 0;
-            const uint8_t *p = h->inflated.next(&bs, &error);
-            if (!p) { bam_destroy1(b); h->itr_done = true; if (error) return lpsh::fail("truncated BAM record in " + h->opt.tumor_bam); break; }
-            if (!lpsh::InflatedRegion::to_bam1(p, bs, b)) { bam_destroy1(b); return lpsh::fail("a record of " + h->opt.tumor_bam + " needs htslib's reader (unset LPS_GPU_INFLATE)"); }
-        } else if (sam_itr_multi_next(h->in, h->itr, b) < 0) { bam_destroy1(b); h->itr_done = true; break; }
-        pc.add_alignment(b);
-        ck.records.push_back(b);
-    }
-    if (ck.records.empty()) { ck.clear(); return 0; }
-    if (ck.records.size() == h->chunk_reads) h->last_chunk = pc.sizes();
+    const int got = h->io.fill(ck, h->chunk_reads);
+    if (got <= 0) { ck.clear(); return got; }
     pc.finish();
     return 1;
 }
 
 // staged API: the chunk plus the TUMOR side of the union map, now carrying the caller's flags
 int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *tv) {
-    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size() || !h->in) return -1;
+    if (!h || !out || !tv || i < 0 || (size_t)i >= h->chr_names.size() || !h->io.in) return -1;
     const int got = read_chunk(h, i, h->chunk);
     if (got != 1) return got;
     lpsh::PackedContig scratch;
@@ -750,7 +699,7 @@ int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *
 static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result *r);
 
 int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r) {
-    if (!h || !r || h->chunk_contig != i || !h->out) return -1;
+    if (!h || !r || h->chunk_contig != i || !h->io.out) return -1;
     return emit_chunk(h, h->chunk, r);
 }
 
@@ -774,7 +723,7 @@ static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result
                 bam_aux_append(b, "PQ", 'i', sizeof(int), (uint8_t *)&pq);
             }
         }
-        if (sam_write1(h->out, h->hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+        if (sam_write1(h->io.out, h->io.hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
     }
     // ReadStatistics arrive reduced over the chunk
     h->st_alignment += r->total_alignment; h->st_supplementary += r->total_supplementary; h->st_secondary += r->total_secondary;
@@ -789,14 +738,7 @@ static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result
 int lpsh_som_tag_end(lpsh_som *h) {
     if (!h) return -1;
     finish_contig(*h);
-    if (h->idx) hts_idx_destroy(h->idx);
-    if (h->hdr) bam_hdr_destroy(h->hdr);
-    if (h->in) sam_close(h->in);
-    int rc = 0;
-    if (h->out && sam_close(h->out) < 0) rc = lpsh::fail("closing the output bam failed");
-    h->idx = nullptr; h->hdr = nullptr; h->in = nullptr; h->out = nullptr;
-    if (h->pool.pool) hts_tpool_destroy(h->pool.pool);
-    h->pool.pool = NULL;
+    const int rc = h->io.close();
     std::ostream &e = std::cerr;   // HaplotagProcess::printExecutionReport (HaplotagProcess.cpp:152-175)
     e << "-------------------------------------------\n";
     e << "total process time        : " << difftime(time(NULL), h->t_begin) << "s\n";
@@ -941,7 +883,7 @@ int lpsh_som_run(lpsh_som *h) {
 
 void lpsh_som_close(lpsh_som *h) {
     if (!h) return;
-    if (h->in || h->out) lpsh_som_tag_end(h);
+    if (h->io.in || h->io.out) lpsh_som_tag_end(h);
     delete h;
 }
 
