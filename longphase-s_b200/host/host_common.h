@@ -380,6 +380,13 @@ int run_ordered_slices(size_t n_slices, int readers, size_t ahead, ReadFn read, 
     return rc;
 }
 
+// processSingleChrom's dispatch for a contig without variants (src/haplotag/HaplotagParsingBam.cpp:457-476): MAPQ and flags only, nothing
+// reaches the tagger, so no device work exists for these records
+inline uint8_t category_without_variants(int mapq, int flag, const lps_tag_params &tp) {
+    return mapq < tp.mapping_quality && tp.mapq_filter ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED : (flag & 0x100) ? LPS_TAG_SECONDARY
+           : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY : LPS_TAG_EMPTY_VARIANTS;
+}
+
 // The files of a tagging pass (BamFileRAII, src/haplotag/HaplotagParsingBam.cpp:20-82: input with index, output with the @PG line
 // `longphase-s` and the same header, one BGZF thread pool for both) and the region in flight with its chunked record reader
 // (htslib's iterator, or the batched-inflate stream when LPS_GPU_INFLATE=1).  Shared by `haplotag` and `somatic_haplotag`.

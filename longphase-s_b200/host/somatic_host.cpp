@@ -785,9 +785,7 @@ int lpsh_som_tag_run_with(lpsh_som *h, lpsh_som_judge_fn judge, void *user) {
             cat.resize((size_t)n); hp.assign((size_t)n, 0); zero.assign((size_t)n, 0);
             for (int k = 0; k < n; k++) {
                 const int flag = v.batch.flag[k];
-                cat[(size_t)k] = v.batch.mapq[k] < tp.mapping_quality ? LPS_TAG_LOW_MAPQ : (flag & 0x4) ? LPS_TAG_UNMAPPED
-                                 : (flag & 0x100) ? LPS_TAG_SECONDARY : ((flag & 0x800) && !tp.tag_supplementary) ? LPS_TAG_SUPPLEMENTARY
-                                 : LPS_TAG_EMPTY_VARIANTS;
+                cat[(size_t)k] = lpsh::category_without_variants(v.batch.mapq[k], flag, tp);
                 r.total_alignment++; r.total_untag++;
                 if (cat[(size_t)k] == LPS_TAG_LOW_MAPQ) r.total_lower_quality++;
                 else if (cat[(size_t)k] == LPS_TAG_UNMAPPED) r.total_unmapped++;
