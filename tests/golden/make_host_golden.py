@@ -27,6 +27,7 @@ if __name__ == "__main__":
         run_in(os.path.join(d, "sref"), [hc.REF_BIN] + tg.SOM_ARGS(sfiles))
         out["somatic_bam"] = hc.bam_digest(os.path.join(d, "sref", "som.bam"))
         out["somatic_purity_out"] = hc.text_digest(open(os.path.join(d, "sref", "som_purity.out")).read())
+        out["somatic_sc_vcf"] = hc.text_digest(hc.strip_commandline(open(os.path.join(d, "sref", "som_sc.vcf")).read()))
     path = os.path.join(ROOT, "tests", "golden", "host_cli.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print(path, out)

@@ -47,7 +47,7 @@ def TAG_ARGS(files, vcf):
 
 
 def SOM_ARGS(files):
-    return ts.som_args(files, [])
+    return ts.som_args(files, ["--output-somatic-vcf"])
 
 
 def log_without_paths(text):
@@ -67,6 +67,7 @@ def test_host_files_match_golden_digests(tmp_path):
     assert hc.bam_digest(os.path.join(d, "own", "tagged.bam")) == gold["haplotag_bam"], "tagged BAM differs from the reference's"
     assert hc.text_digest(log_without_paths(open(os.path.join(d, "own", "tagged.out")).read())) == gold["haplotag_log"]
     sfiles = somatic_files(d)
-    ts.oracle_somatic_through_host(sfiles, [], os.path.join(d, "sown"), chunk=400, pipelined=True)
+    ts.oracle_somatic_through_host(sfiles, ["--output-somatic-vcf"], os.path.join(d, "sown"), chunk=400, pipelined=True)
     assert hc.bam_digest(os.path.join(d, "sown", "som.bam")) == gold["somatic_bam"], "tagged tumor BAM differs from the reference's"
     assert hc.text_digest(open(os.path.join(d, "sown", "som_purity.out")).read()) == gold["somatic_purity_out"]
+    assert hc.text_digest(hc.strip_commandline(open(os.path.join(d, "sown", "som_sc.vcf")).read())) == gold["somatic_sc_vcf"]
