@@ -65,10 +65,24 @@ __global__ void k_filter_snp_chain(int n, const int32_t *__restrict__ pos, const
     }
 }
 
+// the 8-byte record the walking kernel reads per variant (DevVariants::vrec)
+__global__ void k_pack_vrec(int n, const int32_t *__restrict__ pos, const uint8_t *__restrict__ ref0, const uint8_t *__restrict__ alt0,
+                            const uint16_t *__restrict__ ref_len, const uint16_t *__restrict__ alt_len, const uint8_t *__restrict__ hom,
+                            const uint8_t *__restrict__ danger, const uint8_t *__restrict__ filtered, const uint8_t *__restrict__ hp1_is_alt,
+                            uint2 *__restrict__ vrec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned fl = (ref_len[i] == 1 ? 1u : 0u) | (alt_len[i] == 1 ? 2u : 0u) | (danger[i] ? 4u : 0u) | (filtered[i] ? 8u : 0u);
+    if (hp1_is_alt && hp1_is_alt[i]) fl |= 16u;
+    vrec[i] = make_uint2((unsigned)pos[i], (unsigned)ref0[i] | ((unsigned)alt0[i] << 8) | (fl << 16) | ((unsigned)hom[i] << 24));
+}
+
 }  // namespace
 
 int lps_launch_annotate(lps_ctx *ctx) {
     int n = ctx->var.n;
+    LPS_CUDA(ctx, ctx->d_vrec.reserve((size_t)n + 1));
+    ctx->var.vrec = ctx->d_vrec.p;
     if (n == 0) return LPS_OK;
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_vfiltered.p, 0, (size_t)n, ctx->stream));
     int tb = 256, gb = (n + tb - 1) / tb;
@@ -79,6 +93,10 @@ int lps_launch_annotate(lps_ctx *ctx) {
         k_filter_snp_chain<<<gb, tb, 0, ctx->stream>>>(n, ctx->var.pos, ctx->d_vhom.p, ctx->d_vfiltered.p);
         ctx->stats.kernel_launches++;
     }
+    k_pack_vrec<<<gb, tb, 0, ctx->stream>>>(n, ctx->var.pos, ctx->var.ref0, ctx->var.alt0, ctx->var.ref_len, ctx->var.alt_len, ctx->d_vhom.p,
+                                           ctx->d_vdanger.p, ctx->d_vfiltered.p, ctx->have_tag_variants ? ctx->d_vhp1_is_alt.p : nullptr,
+                                           ctx->d_vrec.p);
+    ctx->stats.kernel_launches++;
     LPS_CUDA(ctx, cudaGetLastError());
     return LPS_OK;
 }

@@ -1,25 +1,33 @@
-// k_call_alleles.cu — KERNEL 1 (phase dialect): per-read CIGAR walk + allele call at every overlapped
-// SNP / indel.  Replaces BamParser::direct_detect_alleles' read filter, BamParser::get_snp and getClip
-// (reference src/phase/ParsingBam.cpp:1243-1301, 1303-1634, 1636-1645) and the call-erasing half of
-// SnpParser::filterSNP (:891-911).
+// k_call_alleles.cu — KERNEL 1: per-read CIGAR walk + allele call at every overlapped SNP / indel, five dialects.
+// Replaces BamParser::direct_detect_alleles' read filter, BamParser::get_snp and getClip (reference
+// src/phase/ParsingBam.cpp:1243-1301, 1303-1634, 1636-1645), the call-erasing half of SnpParser::filterSNP (:891-911),
+// CigarParser::parsingCigar with the hooks of its four parsers (src/haplotag/HaplotagParsingBam.cpp:541-670,
+// src/haplotag/HaplotagStrategy.cpp, src/somatic_haplotag/SomaticVarCaller.cpp:123-759,
+// src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-579).
 //
-// Mapping: ONE WARP PER READ.
-//   * the CIGAR is streamed in chunks of 32*K ops (K ops per lane, 128-bit loads, the next chunk is in
-//     flight while the current one is scanned); a warp exclusive scan of (ref advance, query advance)
-//     replaces the sequential walk;
-//   * the pending variant position is compared with the chunk's reference span once per chunk; only a
-//     hit does more work (owner lane found by ballot), so the common "no variant in this chunk" path is
-//     a handful of instructions;
-//   * SNP hits are only RECORDED (variant index, query index) in a per-warp shared-memory candidate
-//     list; the scattered seq-nibble / base-quality gathers happen afterwards, 32 at a time, so their
-//     DRAM latency overlaps instead of serialising inside the scan;
-//   * calls are compacted with warp ballots and written contiguously per read into a scratch pool
-//     (one atomicAdd per read); a CSR in read order is rebuilt by k_gather_calls after a prefix sum.
+// Mapping: ONE WARP PER READ, persistent CTAs (one per SM), reads claimed from a global counter.
+//   * The CIGAR lives in HBM as a 16-bit stream (len << 4 | op, lengths >= 4095 escaped into a side table): 2 bytes per op.
+//   * k_prep_reads turns the SoA batch into one 48-byte descriptor per read that has to be walked (filtered reads never reach
+//     the walking kernel) and sorts the descriptors into four work segments, reads with many CIGAR ops first.
+//   * Every warp owns two CIGAR buffers in shared memory.  A whole super-chunk of a read (up to 1536 ops, 3 KB) is brought in
+//     by ONE cp.async.bulk (1-D TMA) that completes on the warp's own mbarrier; the copy of the NEXT super-chunk - of this
+//     read, or the first of the next claimed read - is in flight while the current one is decoded, and the descriptors of
+//     the next two reads arrive by cp.async.  No register is spent on data in flight and the only wait on HBM is the
+//     mbarrier.
+//   * phase 1 (streaming, from shared memory): 16 ops per lane and iteration; two dot-product instructions per pair of ops
+//     (IDP.2A of the two 12-bit lengths with the (consumes reference, consumes query) flags of the two op codes, looked up
+//     as a pair) give the lane's advance sums; one packed warp scan gives the (reference, query) position at which every
+//     group of 8 ops starts; the positions go into a shared-memory index.  No per-op position is ever materialised.
+//   * phase 2 (once per super-chunk): every lane takes one pending variant, finds its group by binary search in the index,
+//     reads the group's 8 ops back from shared memory (one 128-bit load) and walks them in registers to the covering op.
+//     SNP hits are only RECORDED; the scattered SEQ-nibble / QUAL gathers happen afterwards, 32 at a time.
+//   * calls are compacted with warp ballots and written contiguously per read into a scratch pool; k_gather_calls rebuilds
+//     the CSR in read order after a prefix sum, so the output is deterministic.
 //
-// Sequential quirks of the reference that are reproduced: cursor == lower_bound of the
-// op start; only the FIRST pending variant of a D op is examined (homopolymer >= 3 rule); a variant
-// whose query index is beyond l_qseq drops the whole read but keeps the clips seen before it; indel
-// alleles look at the op that follows the M op; clips are FRONT iff the CIGAR index is 0.
+// Sequential quirks of the reference that are reproduced: cursor == lower_bound of the op start; only the
+// FIRST pending variant of a D op is examined (homopolymer >= 3 rule); a variant whose query index is beyond l_qseq drops
+// the whole read but keeps the clips seen before it; indel alleles look at the op that follows the M op; clips are FRONT
+// iff the CIGAR index is 0.
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "lps_ctx.cuh"
@@ -27,31 +35,24 @@
 namespace {
 
 #ifndef LPS_WARPS
-#define LPS_WARPS 32
+#define LPS_WARPS 24
 #endif
-constexpr int WARPS_PER_CTA = LPS_WARPS;   // one CTA of 32 warps per SM: its 160 KB of (dynamic) shared memory pin the L1 / shared split,
-                                     // so residency does not depend on the driver's carve-out heuristics
-#ifndef LPS_DECODE
-#define LPS_DECODE 0      // 0: two sums with selects, 1: packed multiply-add, multiplier from a shared-memory table, 2: ..., from the LUT word
+#ifndef LPS_SC_OPS
+#define LPS_SC_OPS 1536
 #endif
-#ifndef LPS_WALK_VEC
-#define LPS_WALK_VEC 1
+#ifndef LPS_CAND_CAP
+#define LPS_CAND_CAP 192
 #endif
-#ifndef LPS_FETCH
-#define LPS_FETCH 2
-#endif
-constexpr int FETCH = LPS_FETCH;              // work items claimed per atomic by a warp
-#ifndef LPS_KOPS
-#define LPS_KOPS 8
-#endif
-#ifndef LPS_CTAS_PER_SM
-#define LPS_CTAS_PER_SM 1
-#endif
-constexpr int KOPS = LPS_KOPS;                 // CIGAR ops per lane and chunk (32 * KOPS ops per chunk)
-constexpr int CTAS_PER_SM = LPS_CTAS_PER_SM;   // resident CTAs per SM the register budget is sized for
-constexpr int CAND_CAP = 512;        // 8-byte candidates buffered per warp in shared memory (256 of the 16-byte somatic ones)
+constexpr int WARPS_PER_CTA = LPS_WARPS;      // one CTA per SM; its dynamic shared memory (~9.2 KB per warp) pins the L1 / shared split
+constexpr int SC = LPS_SC_OPS;                // CIGAR ops per super-chunk (one bulk copy, one phase-2 pass); multiple of 512
+constexpr int IT_OPS = 512;                   // ops per phase-1 iteration: 16 per lane
+constexpr int NGRP = SC / 8;                  // index entries: one per group of 8 ops
+constexpr int SC_BUF = SC + 8;                // + one 16-byte unit: the op that follows the super-chunk's last op
+constexpr int CAND_CAP = LPS_CAND_CAP;        // 8-byte candidates buffered per warp in shared memory (half as many 16-byte somatic ones)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr uint32_t PAD_OP = 1u;     // zero-length insertion: advances nothing
+constexpr uint32_t PAD16 = 1u;                // zero-length insertion: advances nothing
+constexpr uint32_t PAD_WORD = PAD16 | (PAD16 << 16);
+static_assert(SC % IT_OPS == 0 && SC >= IT_OPS, "a super-chunk is a whole number of phase-1 iterations");
 
 // candidate encoding: x = kind << 30 | payload
 //   kind 0: SNP seen inside an M/=/X op, payload = query index
@@ -73,23 +74,21 @@ struct K1Args {
     uint8_t *status;
     uint32_t *clip_keys;
     uint2 *clip_meta;                 // (read, CIGAR index) of every clip event
-    int32_t *abort_of_read;           // CIGAR index at which get_snp dropped the read, INT_MAX otherwise
-    const int32_t *first_var;         // per read: lower_bound of its start in the variant positions
-    const uint32_t *long_list;        // [3][n_reads] reads with many CIGAR ops, longest tier first: they are started first
-    const uint32_t *long_count;       // [3] entries per tier (device memory, written by k_first_var)
-    uint32_t long_thr;                // n_cigar above which a read is in a tier (and skipped by the in-order pass)
+    int32_t *abort_of_read;           // CIGAR index at which get_snp dropped the read, INT_MAX otherwise (preset by k_prep_reads)
+    const uint4 *work;                // read descriptors (3 x uint4 each), four segments: reads with many CIGAR ops first
+    const uint32_t *seg_count;        // [4] descriptors per segment (device memory, written by k_prep_reads)
+    uint32_t seg_base[4];             // first slot of each segment
     unsigned long long *dbg_times;    // LPS_DEBUG_K1: per warp {globaltimer at start, at end, reads processed, SM id}
     unsigned long long clip_cap;
     CallCounters *counters;
     // overflow pass
-    const uint32_t *overflow_reads;   // null in the main pass
+    const uint32_t *overflow_reads;   // null in the main pass; else the work slots of the reads to redo
     const uint64_t *overflow_off;
     Cand *overflow_buf;
-    uint32_t *overflow_list_out;      // main pass: list of reads that overflowed
+    uint32_t *overflow_list_out;      // main pass: work slots of the reads that overflowed
     uint64_t *overflow_need_out;      // main pass: candidates they need
     uint32_t overflow_list_cap;
     // ---- tag dialect (CigarParser::parsingCigar + GermlineHaplotagStrategy) ----
-    const uint8_t *hp1_is_alt;        // per variant: HP1 carries ALT (GT 1|0)
     const int32_t *var_ps;            // per variant: phase set
     int mapq_filter;                  // ParsingBamControl::mappingQualityFilter
     int tag_supplementary;            // ParsingBamConfig::tagSupplementary
@@ -97,6 +96,7 @@ struct K1Args {
     int count_gathers;                // SEQ/QUAL live in pinned host memory: count the gathered sectors
     double percentage;                // ParsingBamConfig::percentageThreshold
     const int8_t *pq_lut;             // [256][256] PQ by (min, max), built on the host with the host libm
+    const uint8_t *hp1_is_alt;        // per variant: HP1 carries ALT (GT 1|0)  (somatic dialects; the others read the packed record)
     int8_t *tag_hp;                   // ReadHP: 0 unTag, 1 H1, 2 H2
     int32_t *tag_ps, *tag_pq, *tag_h1, *tag_h2;
     uint8_t *tag_cat;                 // dispatch category, see LPS_TAG_* in lps.h
@@ -110,72 +110,65 @@ struct K1Args {
     float *tag_sim;
 };
 
-__device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ pos, int n, int key, int lane) {
-    int lo = 0, hi = n;   // answer in [lo, hi]
-    while (hi - lo > 32) {
-        int step = (hi - lo + 31) >> 5;
-        int q = lo + (lane + 1) * step - 1;
-        if (q > hi - 1) q = hi - 1;
-        bool pred = pos[q] < key;
-        unsigned m = __ballot_sync(FULL, pred);
-        int cnt = __popc(m);
-        int nlo = cnt ? (min(lo + cnt * step - 1, hi - 1) + 1) : lo;
-        int nhi = cnt < 32 ? min(lo + (cnt + 1) * step - 1, hi - 1) : hi;
-        lo = nlo; hi = nhi;
-    }
-    int q = lo + lane;
-    bool pred = (q < hi) && (pos[q] < key);
-    return lo + __popc(__ballot_sync(FULL, pred));
-}
+// ---- packed variant record (k_pack_vrec, k_annotate.cu): x = position, y = ref0 | alt0 << 8 | flags << 16 | homopolymer << 24 ----
+constexpr unsigned VF_REF1 = 1u << 16, VF_ALT1 = 1u << 17, VF_DANGER = 1u << 18, VF_FILTERED = 1u << 19, VF_HP1ALT = 1u << 20;
 
-// K consecutive ops of this lane, starting at index g0 of `rc` (the read's CIGAR, rebased to a 16-byte boundary; g0 is a
-// multiple of 4 -> 128-bit loads).  The read owns [lo, hi); `edge` (warp-uniform) is set for the first / last chunk of a read
-// and near the end of the whole array (tot): only there can ops fall outside [lo, hi); they become "I, len 0" (no effect).
-template <int K>
-__device__ __forceinline__ void load_ops(const uint32_t *__restrict__ rc, int tot, int g0, int lo, int hi, bool edge, uint32_t (&ops)[K]) {
-    if (!edge) {
-#pragma unroll
-        for (int j = 0; j < K; j += 4) {
-            uint4 t = __ldg(reinterpret_cast<const uint4 *>(rc + g0 + j));
-            ops[j] = t.x; ops[j + 1] = t.y; ops[j + 2] = t.z; ops[j + 3] = t.w;
-        }
-        return;
-    }
-    if (g0 + K <= lo || g0 >= hi) {
-#pragma unroll
-        for (int j = 0; j < K; j++) ops[j] = PAD_OP;
-        return;
-    }
-    if (g0 + K <= tot) {
-#pragma unroll
-        for (int j = 0; j < K; j += 4) {
-            uint4 t = __ldg(reinterpret_cast<const uint4 *>(rc + g0 + j));
-            ops[j] = t.x; ops[j + 1] = t.y; ops[j + 2] = t.z; ops[j + 3] = t.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; j++) ops[j] = (g0 + j < tot) ? rc[g0 + j] : PAD_OP;
-    }
-#pragma unroll
-    for (int j = 0; j < K; j++) if ((unsigned)(g0 + j - lo) >= (unsigned)(hi - lo)) ops[j] = PAD_OP;
-}
-
-// per-op advance bits, two bits per op code: bit0 = consumes the reference (M D N = X),
-// bit1 = consumes the query (M I S = X)
+// per-op advance bits, two bits per op code: bit0 = consumes the reference (M D N = X), bit1 = consumes the query (M I S = X)
 constexpr uint32_t ADV_LUT = (3u << 0) | (2u << 2) | (1u << 4) | (1u << 6) | (2u << 8) | (3u << 14) | (3u << 16);
-// op codes that need the slow path: S, H (clips), P, and the unsupported codes 9..15
-constexpr uint32_t RARE_OPS = 0xFE70u;
 
-#ifndef LPS_GROUPS_CAP
-#define LPS_GROUPS_CAP 384
-#endif
-constexpr int GROUPS_CAP = LPS_GROUPS_CAP;     // K-op groups indexed per super-chunk (3072 ops); longer reads are walked in several super-chunks
+// ---- mbarrier / bulk copy / cp.async (PTX; SASS: SYNCS, UBLKCP, LDGSTS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LPS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LPS_DONE;\n\t"
+        "bra LPS_WAIT;\n\t"
+        "LPS_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K>
-struct WarpScratch {
-    int2 grp[GROUPS_CAP];     // (reference, query) position at which each group of K consecutive ops starts
+struct alignas(16) WarpScratch {
+    uint16_t cig[2][SC_BUF];          // destinations of the bulk copies
+    int2 grp[NGRP];                   // (reference, query) position at which each group of 8 consecutive ops starts
     Cand cand[CAND_CAP];
+    uint4 desc[3][3];                 // ring of read descriptors: the read being walked and the next two
+    unsigned long long mbar[2];
 };
+static_assert((SC_BUF * 2) % 16 == 0 && sizeof(WarpScratch) % 16 == 0, "bulk copy destinations must stay 16-byte aligned");
+
+// true length of an escaped op (12-bit field == 0xFFF): binary search of its global index in the side table
+__device__ __noinline__ uint32_t esc_len(const uint64_t *__restrict__ long_at, const uint32_t *__restrict__ long_len, uint32_t n_long, uint64_t gop) {
+    uint32_t lo = 0, hi = n_long;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (long_at[mid] < gop) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n_long && long_at[lo] == gop) ? long_len[lo] : 0xFFFu;
+}
+__device__ __forceinline__ uint32_t op_len(const DevBatch &b, uint32_t x, uint64_t gop) {
+    const uint32_t len = x >> 4;
+    return len == 0xFFFu ? esc_len(b.long_at, b.long_len, b.n_long, gop) : len;
+}
 
 // HaplotagVariantType (HaplotagType.h:76-85): 1 SNP, 2 INSERTION, 3 DELETION, 4 MNP, 0 = setVariantType would throw
 __device__ __forceinline__ int hvt(int rl, int al) {
@@ -204,11 +197,9 @@ __device__ __forceinline__ unsigned long long pool_alloc(const K1Args &a, PoolCu
 
 template <int MODE>
 __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane, uint4 *cand4, int ncand, int ref_start, int ref_end,
-                                                int q_end, int lq, PoolCursor &pc) {
+                                                int q_end, int lq, PoolCursor &pc, const uint8_t *__restrict__ seq, const bool mpq_ok) {
     constexpr bool XNOR = MODE == LPS_MODE_EXTRACT_NORMAL, XTUM = MODE == LPS_MODE_EXTRACT_TUMOR, STAG = MODE == LPS_MODE_SOMATIC_TAG;
     const DevSomatic &s = a.som;
-    const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
-    const bool mpq_ok = (int)a.b.mapq[r] >= a.mapping_quality;
     int h1 = 0, h2 = 0, h3 = 0, ps_min = INT_MAX, ps_max = INT_MIN, d1 = 0, d2 = 0;
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         const int c = c0 + lane;
@@ -428,13 +419,6 @@ __device__ __forceinline__ void resolve_somatic(const K1Args &a, int r, int lane
     }
 }
 
-// One read, one warp.
-//   phase 1 (streaming): the CIGAR goes through registers in chunks of 32*K ops; per chunk only the per-lane advance sums and
-//     one warp exclusive scan are computed, and the (ref, query) position at which each lane's group of K ops starts is
-//     written to a shared-memory index.  No per-op positions are materialised.
-//   phase 2 (once per super-chunk, i.e. once per read for reads up to 3072 ops): every lane takes one pending variant,
-//     finds its group by binary search in the index, and re-walks the <= K ops of that group (L1/L2 hits: the lines were
-//     streamed moments ago) to get the covering op, its start positions and the op that follows it.
 // Slots of the scratch call pool are handed out in blocks of POOL_BLOCK per warp (one global atomic per ~50 reads instead of
 // one per read on the critical path); the unused tail of a block stays empty, k_gather_calls compacts the pool anyway.
 constexpr unsigned POOL_BLOCK = 1024;
@@ -454,107 +438,147 @@ __device__ __forceinline__ unsigned long long pool_alloc(const K1Args &a, PoolCu
     pc.used += (unsigned)n;
     return start;
 }
+// ---- read descriptor (written by k_prep_reads, 3 x uint4) ----
+struct ReadDesc {
+    uint64_t cigar_off, seq_off, qual_off;
+    int ref_start, lq, ncig, first_var;
+    uint32_t r;                        // read index in the batch; 0xFFFFFFFF = no read (the work list is exhausted)
+    uint32_t flags;                    // mapq | flag << 8
+};
+__device__ __forceinline__ ReadDesc unpack_desc(const uint4 d0, const uint4 d1, const uint4 d2) {
+    ReadDesc D;
+    D.cigar_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+    D.seq_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    D.qual_off = (uint64_t)d1.x | ((uint64_t)d1.y << 32);
+    D.ref_start = (int)d1.z; D.lq = (int)d1.w;
+    D.ncig = (int)d2.x; D.first_var = (int)d2.y; D.r = d2.z; D.flags = d2.w;
+    return D;
+}
 
-template <int K, int MODE>
-__device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S, const uint32_t *__restrict__ s_mult, const int r, Cand *cand,
-                                             int cand_cap, const int lane, const bool overflow_pass, PoolCursor &pc, unsigned &nxt, bool &claimed) {
+// work item -> slot of the descriptor array: the four segments are handed out one after the other
+__device__ __forceinline__ uint32_t slot_of_item(const K1Args &a, uint32_t t, uint32_t c0, uint32_t c1, uint32_t c2) {
+    if (t < c0) return a.seg_base[0] + t;
+    if (t < c0 + c1) return a.seg_base[1] + (t - c0);
+    if (t < c0 + c1 + c2) return a.seg_base[2] + (t - c0 - c1);
+    return a.seg_base[3] + (t - c0 - c1 - c2);
+}
+
+// state of a warp's two CIGAR buffers
+struct Pipe {
+    int buf;                           // buffer the NEXT super-chunk to be consumed arrives in
+    uint32_t phase;                    // bit b = parity the next wait on mbar[b] uses
+};
+
+// one bulk copy: super-chunk s of the read, into buffer `buf`.  All positions are in the read's ALIGNED op space: index 0 is the
+// 16-byte boundary at or before the read's first op (mis = cigar_off & 7 ops before it), so every super-chunk starts on a 16-byte
+// boundary of both the global stream and the shared buffer.  The copy carries one extra 16-byte unit (the op after the last one),
+// clamped to the padded end of the stream.
+__device__ __forceinline__ void issue_sc(const K1Args &a, WarpScratch &S, const ReadDesc &D, int s, int buf, int lane) {
+    if (lane == 0) {
+        const int mis = (int)(D.cigar_off & 7ull);
+        const int tot_a = mis + D.ncig;
+        const int cnt = min(SC, tot_a - s * SC);
+        const uint64_t start = D.cigar_off - (uint64_t)mis + (uint64_t)s * SC;          // multiple of 8 ops
+        uint64_t ops = (uint64_t)((cnt + 7) & ~7) + 8;
+        const uint64_t avail = ((a.b.cigar_len + 7ull) & ~7ull) - start;
+        if (ops > avail) ops = avail;
+        const uint32_t bytes = (uint32_t)ops * 2u;
+        const uint32_t bar = smem_u32(&S.mbar[buf]);
+        fence_proxy_async();           // orders this warp's earlier generic accesses to the buffer before the async write
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(&S.cig[buf][0]), a.b.cigar16 + start, bytes, bar);
+    }
+}
+
+// One read, one warp.  `cand` is the warp's shared candidate buffer (or the global list of the overflow pass).
+//   next: descriptor of the read this warp walks next (r == 0xFFFFFFFF: none); its first super-chunk is requested while the
+//   last super-chunk of this read is being decoded.
+template <int MODE>
+__device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, const uint32_t *__restrict__ s_pair, const ReadDesc &D,
+                                             const ReadDesc &next, Pipe &pp, Cand *cand, int cand_cap, const uint32_t work_slot,
+                                             const int lane, PoolCursor &pc) {
     constexpr bool TAG = MODE != LPS_MODE_PHASE;          // CigarParser::parsingCigar instead of BamParser::get_snp
     constexpr bool SOM = MODE >= LPS_MODE_EXTRACT_NORMAL; // raw 16-byte candidates, resolved by resolve_somatic
     if (SOM) cand_cap >>= 1;                              // 16-byte candidates
     uint4 *cand4 = reinterpret_cast<uint4 *>(cand);
     const int nv = a.v.n;
-    const int ref_start = a.b.ref_start[r];
-    const int lq = a.b.l_qseq[r];
-    const int ncig = (int)a.b.n_cigar[r];
-    const int flag = a.b.flag[r];
-    int cur = a.first_var[r];                              // lower_bound(variants, ref_start), from k_first_var
-    const int64_t lo64 = (int64_t)a.b.cigar_off[r];
-    if (!TAG) {
-        // iterator region "chr:1-lastSNP" (ParsingBam.cpp:1273) + read filter (:1282-1291)
-        if (ref_start >= a.last_var_pos || (int)a.b.mapq[r] < a.mapping_quality || (flag & (0x4 | 0x100 | 0x400))) {
-            if (lane == 0) { a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED; a.abort_of_read[r] = INT_MAX; }
-            return;
-        }
-    } else {
-        // dispatch of ChromosomeProcessor::processSingleChrom (HaplotagParsingBam.cpp:457-486), in its order
-        int cat = LPS_TAG_PROCESSED;
-        if ((int)a.b.mapq[r] < a.mapping_quality && a.mapq_filter) cat = LPS_TAG_LOW_MAPQ;
-        else if (flag & 0x4) cat = LPS_TAG_UNMAPPED;
-        else if (flag & 0x100) cat = LPS_TAG_SECONDARY;
-        else if ((flag & 0x800) && !a.tag_supplementary) cat = LPS_TAG_SUPPLEMENTARY;
-        else if (nv == 0) cat = LPS_TAG_EMPTY_VARIANTS;
-        else if (!(ref_start <= a.last_var_pos)) cat = LPS_TAG_OTHER;
-        if (lane == 0 && !overflow_pass) a.tag_cat[r] = (uint8_t)cat;
-        if (cat != LPS_TAG_PROCESSED) {
-            if (lane == 0) {
-                a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_FILTERED;
-                a.tag_hp[r] = 0; a.tag_ps[r] = 0; a.tag_pq[r] = 0; a.tag_h1[r] = 0; a.tag_h2[r] = 0;
-                if (SOM) { a.tag_h3[r] = 0; a.tag_end[r] = 0; a.tag_len[r] = 0; a.tag_nps[r] = 0; a.tag_hpb[r] = 0; a.tag_sim[r] = 0.f; }
-            }
-            return;
-        }
-    }
-    const int32_t *__restrict__ vpos = a.v.pos;
-    // the read's CIGAR rebased to a 16-byte boundary: 32-bit indices from here on; the read owns [lo, hi) of rc
-    const int64_t abase = lo64 & ~(int64_t)3;
-    const uint32_t *__restrict__ rc = a.b.cigar + abase;
-    const int lo = (int)(lo64 - abase), hi = lo + ncig;
-    const int64_t left = (int64_t)a.b.cigar_len - abase;
-    const int tot = left > (int64_t)INT_MAX ? INT_MAX : (int)left;
-    constexpr int CH = 32 * K;
+    const int r = (int)D.r;
+    const int ref_start = D.ref_start, lq = D.lq, ncig = D.ncig;
+    int cur = D.first_var;                                // lower_bound(variants, ref_start), from k_prep_reads
+    const uint2 *__restrict__ vrec = a.v.vrec;
+    const int mis = (int)(D.cigar_off & 7ull);
+    const int tot_a = mis + ncig;
+    const int n_sc = ncig > 0 ? (tot_a + SC - 1) / SC : 0;
+    const uint64_t gop0 = D.cigar_off - (uint64_t)mis;    // global op index of aligned position 0
 
     int ref_pos = ref_start, qpos = 0;
     int ncand = 0;
     bool aborted = false;
     int abort_op = INT_MAX, bad_op = INT_MAX;
 
-    uint32_t nxt_ops[K];
-    load_ops<K>(rc, tot, lane * K, lo, hi, true, nxt_ops);
-    int cb = 0;
-    while (cb < hi) {
-        // ================= phase 1: stream one super-chunk, index the group starts =================
-        const int sc_cb = cb;
-        int k = 0;
-        for (; k < GROUPS_CAP / 32 && cb < hi; k++, cb += CH) {
-            uint32_t ops[K];
+    if (n_sc == 0 && next.r != 0xFFFFFFFFu && next.ncig > 0) issue_sc(a, S, next, 0, pp.buf, lane);   // keeps "the next read's copy is under way"
+    for (int s = 0; s < n_sc; s++) {
+        const int buf = pp.buf;
+        // request what this warp decodes next, then wait for what it decodes now
+        if (s + 1 < n_sc) issue_sc(a, S, D, s + 1, buf ^ 1, lane);
+        else if (next.r != 0xFFFFFFFFu && next.ncig > 0) issue_sc(a, S, next, 0, buf ^ 1, lane);
+        mbar_wait(smem_u32(&S.mbar[buf]), (pp.phase >> buf) & 1u);
+        pp.phase ^= 1u << buf;
+        pp.buf = buf ^ 1;
+        uint16_t *__restrict__ cg = S.cig[buf];
+        const int a_base = s * SC;                        // aligned position of cg[0]
+        const int cnt = min(SC, tot_a - a_base);          // aligned positions of this super-chunk
+        const int cnt16 = (cnt + 15) & ~15;
+        // positions before the read's first op and behind its last one hold the neighbours' ops: blank them
+        if (s == 0 && lane < mis) cg[lane] = (uint16_t)PAD16;
+        if (s == n_sc - 1 && lane < 16 && cnt + lane < cnt16) cg[cnt + lane] = (uint16_t)PAD16;
+        fence_proxy_async();           // these generic writes precede the next bulk copy into this buffer
+        __syncwarp();
+
+        // ================= phase 1: index the group starts of this super-chunk =================
+        const int n_it = (cnt + IT_OPS - 1) / IT_OPS;
+        for (int it = 0; it < n_it; it++) {
+            const int a0 = it * IT_OPS + lane * 16;       // this lane's 16 ops start here (position inside the super-chunk)
+            uint32_t w[8];
+            if (a0 < cnt16) {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(cg + a0), hi = *reinterpret_cast<const uint4 *>(cg + a0 + 8);
+                w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < K; j++) ops[j] = nxt_ops[j];
-            if (cb + CH < hi) {
-                const bool edge = (cb + 2 * CH > hi) || (cb + 2 * CH > tot);
-                load_ops<K>(rc, tot, cb + CH + lane * K, lo, hi, edge, nxt_ops);
+                for (int j = 0; j < 8; j++) w[j] = PAD_WORD;
             }
-            // per-lane advance sums.  Fast path: both sums in one register (ref in bits 0..15, query in bits 16..31), one
-            // multiply-add per op with the multiplier 0 / 1 / 0x10000 / 0x10001 looked up by op code; exact while every op of
-            // the warp's chunk is shorter than 2048 (8 ops * 2047 < 2^16, no carry between the halves)
-            unsigned pk = 0, rare = 0;
+            // advance sums of the lane's two groups of 8 ops: per pair of ops one table word (flags of both op codes) and two
+            // dot products of the two 12-bit lengths with them
+            unsigned rs = 0, qs = 0, r0 = 0, q0 = 0, acc = 0;
 #pragma unroll
-            for (int j = 0; j < K; j++) {
-                const unsigned c = ops[j];
-#if LPS_DECODE == 1
-                pk = (c >> 4) * s_mult[c & 15u] + pk;
-#elif LPS_DECODE == 2
-                const unsigned t = ADV_LUT >> ((c << 1) & 30u);
-                pk = (c >> 4) * ((t & 1u) | ((t & 2u) << 15)) + pk;
-#endif
-                rare |= c;                                // op code bits 2..3 set <=> some op code >= 4 (S H P = X or unsupported)
+            for (int j = 0; j < 8; j++) {
+                const unsigned x = w[j];
+                const unsigned lens = (x >> 4) & 0x0FFF0FFFu;
+                const unsigned fl = s_pair[(x & 0xFu) | ((x >> 12) & 0xF0u)];
+                rs = __dp2a_lo(lens, fl, rs);
+                qs = __dp2a_hi(lens, fl, qs);
+                acc |= x;
+                if (j == 3) { r0 = rs; q0 = qs; }
             }
-            int rs, qs;
-            if (LPS_DECODE != 0 && !__any_sync(FULL, rare >= (2048u << 4))) { rs = (int)(pk & 0xffffu); qs = (int)(pk >> 16); }
-            else {
-                rs = 0; qs = 0;
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const unsigned c = ops[j];
-                    const unsigned t = ADV_LUT >> ((c << 1) & 30u);
-                    const int len = (int)(c >> 4);
-                    rs += (int)(t & 1u) * len;
-                    qs += (int)((t >> 1) & 1u) * len;
+            // an escaped length (field == 0xFFF) somewhere in the lane's ops?  (the OR can only err towards "yes")
+            const bool esc = ((acc >> 4) & 0xFFFu) == 0xFFFu || (acc >> 20) == 0xFFFu;
+            if (__any_sync(FULL, esc)) {
+                if (esc) {
+                    rs = 0; qs = 0;
+#pragma unroll 1
+                    for (int j = 0; j < 16; j++) {
+                        const unsigned x = a0 < cnt16 ? (unsigned)cg[a0 + j] : PAD16;   // from shared memory: no dynamic register indexing
+                        const unsigned t = ADV_LUT >> ((x << 1) & 30u);
+                        const unsigned len = op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + j));
+                        rs += (t & 1u) * len; qs += ((t >> 1) & 1u) * len;
+                        if (j == 7) { r0 = rs; q0 = qs; }
+                    }
                 }
             }
             // exclusive scan of both cursors: one packed scan when every lane sum fits 11 bits (so the totals fit 16)
             int er, eq, rtot, qtot;
-            if (!__any_sync(FULL, (unsigned)(rs | qs) >= 2048u)) {
-                const unsigned pk2 = (unsigned)rs | ((unsigned)qs << 16);
+            if (!__any_sync(FULL, (rs | qs) >= 2048u)) {
+                const unsigned pk2 = rs | (qs << 16);
                 unsigned inc = pk2;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -565,51 +589,51 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                 er = (int)(exc & 0xffffu); eq = (int)(exc >> 16);
                 rtot = (int)(tt & 0xffffu); qtot = (int)(tt >> 16);
             } else {
-                int ri = rs, qi = qs;
+                int ri = (int)rs, qi = (int)qs;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const int t = __shfl_up_sync(FULL, ri, d);
                     const int u = __shfl_up_sync(FULL, qi, d);
                     if (lane >= d) { ri += t; qi += u; }
                 }
-                er = ri - rs; eq = qi - qs;
+                er = ri - (int)rs; eq = qi - (int)qs;
                 rtot = __shfl_sync(FULL, ri, 31); qtot = __shfl_sync(FULL, qi, 31);
             }
-            S.grp[k * 32 + lane] = make_int2(ref_pos + er, qpos + eq);
-            // ---- clips (S/H longer than 5) and unsupported ops: first / last chunk of a read, normally ----
-            if (__any_sync(FULL, (rare & 0xCu) != 0)) {
+            *reinterpret_cast<int4 *>(&S.grp[it * 64 + lane * 2]) =
+                make_int4(ref_pos + er, qpos + eq, ref_pos + er + (int)r0, qpos + eq + (int)q0);
+            // ---- clips (S/H longer than 5) and unsupported ops: op codes with bit 2 or 3 set (S H P = X and 9..15) ----
+            if (__any_sync(FULL, ((acc | (acc >> 16)) & 0xCu) != 0)) {
                 int rr = ref_pos + er;
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const unsigned op = ops[j] & 15u;
-                    const int len = (int)(ops[j] >> 4);
-                    const int g = cb + lane * K + j;
-                    if (!TAG && (op == 4 || op == 5) && len > 5) {
-                        // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
-                        const unsigned long long slot = atomicAdd(&a.counters->clips.v, 1ull);
-                        if (slot < a.clip_cap) {
-                            a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == lo ? 0u : 1u);
-                            a.clip_meta[slot] = make_uint2((unsigned)r, (unsigned)(g - lo));
+#pragma unroll 1
+                for (int j = 0; j < 16; j++) {
+                    const unsigned x = a0 < cnt16 ? (unsigned)cg[a0 + j] : PAD16;
+                    const unsigned op = x & 15u;
+                    const int g = a_base + a0 + j - mis;  // CIGAR index inside the read (pads are zero-length insertions: no effect)
+                    if (op >= 4u && op != 7u && op != 8u) {
+                        const int len = (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + j));
+                        if (!TAG && (op == 4u || op == 5u) && len > 5) {
+                            // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
+                            const unsigned long long slot = atomicAdd(&a.counters->clips.v, 1ull);
+                            if (slot < a.clip_cap) {
+                                a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == 0 ? 0u : 1u);
+                                a.clip_meta[slot] = make_uint2((unsigned)r, (unsigned)g);
+                            }
                         }
-                    }
-                    if (op > 8) bad_op = min(bad_op, (int)(g - lo));
-                    rr += ((0x18Du >> op) & 1u) ? len : 0;
+                        if (op > 8u) bad_op = min(bad_op, g);
+                    } else if ((0x18Du >> op) & 1u) rr += (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + j));
                 }
             }
             ref_pos += rtot; qpos += qtot;
         }
-        const int ng = k * 32;
-        // claim the NEXT work item now: the streaming registers are dead, and phase 2 + the gathers hide the atomic's round trip
-        if (!claimed) {
-            if (lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);
-            claimed = true;
-        }
+        const int ng = n_it * 64;
         __syncwarp();
 
         // ================= phase 2: every pending variant below ref_pos, one per lane =================
         while (true) {
             const int vi = cur + lane;
-            const int vp = vi < nv ? vpos[vi] : INT_MAX;
+            uint2 vr = make_uint2((unsigned)INT_MAX, 0u);
+            if (vi < nv) vr = vrec[vi];
+            const int vp = (int)vr.x;
             const bool mine = vp < ref_pos;
             const unsigned mmask = __ballot_sync(FULL, mine);
             if (mmask == 0) break;
@@ -621,48 +645,33 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                 // group: the last one that starts at or before vp
                 int g = 0;
 #pragma unroll
-                for (int step = 256; step >= 1; step >>= 1) {
-                    const int mid = g + step;
-                    if (mid < ng && S.grp[mid].x <= vp) g = mid;
+                for (int step = (NGRP >= 256 ? 256 : 128); step >= 1; step >>= 1) {
+                    const int midg = g + step;
+                    if (midg < ng && S.grp[midg].x <= vp) g = midg;
                 }
                 const int2 gs = S.grp[g];
-                const int g0 = sc_cb + g * K;
                 int wr = gs.x, wq = gs.y;
-                unsigned c = PAD_OP;
-#if LPS_WALK_VEC
-                // covering op: the last op of the group that starts at or before vp (two 128-bit loads, walked in registers)
-                uint32_t gops[K];
-                load_ops<K>(rc, tot, g0, lo, hi, true, gops);
-                int jsel = 0;
+                // covering op: the last op of the group that starts at or before vp (one 128-bit load, walked in registers)
+                const uint4 g8 = *reinterpret_cast<const uint4 *>(cg + g * 8);
+                const unsigned gw[4] = {g8.x, g8.y, g8.z, g8.w};
+                const bool gesc = ((((g8.x | g8.y | g8.z | g8.w) >> 4) & 0xFFFu) == 0xFFFu) || (((g8.x | g8.y | g8.z | g8.w) >> 20) == 0xFFFu);
+                unsigned c = PAD16;
+                int o_len = 0, jsel = 0;
 #pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const unsigned cc = gops[j];
-                    if (wr <= vp) { c = cc; o_r = wr; o_q = wq; jsel = j; }
+                for (int j = 0; j < 8; j++) {
+                    const unsigned cc = (gw[j >> 1] >> ((j & 1) << 4)) & 0xFFFFu;
+                    int len = (int)(cc >> 4);
+                    if (gesc) len = (int)op_len(a.b, cc, gop0 + (uint64_t)(a_base + g * 8 + j));
+                    if (wr <= vp) { c = cc; o_r = wr; o_q = wq; jsel = j; o_len = len; }
                     const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
-                    const int len = (int)(cc >> 4);
                     wr += (int)(t & 1u) * len;
                     wq += (int)((t >> 1) & 1u) * len;
                 }
-                const int gidx = g0 + jsel;
-#else
-                // covering op: the last op of the group that starts at or before vp
-                int gidx = g0;
-#pragma unroll 1
-                for (int j = 0; j < K; j++) {
-                    const int idx = g0 + j;
-                    if (idx >= hi) break;
-                    if (idx < lo) continue;
-                    const unsigned cc = rc[idx];
-                    if (wr > vp) break;
-                    c = cc; o_r = wr; o_q = wq; gidx = idx;
-                    const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
-                    const int len = (int)(cc >> 4);
-                    wr += (int)(t & 1u) * len;
-                    wq += (int)((t >> 1) & 1u) * len;
-                }
-#endif
-                const int o_op = (int)(c & 15u), o_len = (int)(c >> 4);
-                opi = (int)(gidx - lo);
+                const int lidx = g * 8 + jsel;            // position inside the super-chunk; the buffer also holds position lidx + 1
+                const int o_op = (int)(c & 15u);
+                opi = a_base + lidx - mis;
+                const unsigned nop = (unsigned)cg[lidx + 1] & 15u;   // only meaningful when opi + 1 < ncig
+                const bool rl1 = (vr.y & VF_REF1) != 0, al1 = (vr.y & VF_ALT1) != 0;
                 if (SOM) {
                     // union map: every variant inside an M/=/X op (HaplotagParsingBam.cpp:585-614) or a D op (:623-631) becomes a
                     // raw candidate {variant, query index, op index | op start, offset | flags}; the hooks run in resolve_somatic
@@ -671,7 +680,6 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                         if (o_q + off < lq) {                      // beyond SEQ the reference reads undefined memory: dropped
                             unsigned fl = 0;
                             if (opi + 1 < ncig) {
-                                const unsigned nop = rc[gidx + 1] & 15u;
                                 fl = 1u;                           // i + 1 < n_cigar
                                 if (o_r + o_len - 1 == vp) fl |= (nop == 1u ? 2u : 0u) | (nop == 2u ? 4u : 0u);
                             }
@@ -686,22 +694,20 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     // CigarParser::parsingCigar M branch (HaplotagParsingBam.cpp:585-614) + judgeSnpHap (HaplotagStrategy.cpp:20-130)
                     if (o_op == 0 || o_op == 7 || o_op == 8) {
                         const int off = vp - o_r;
-                        const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
-                        if (rl == 1 && al == 1) {
+                        if (rl1 && al1) {
                             // the reference reads seq[query_pos+offset] without a bounds check; past l_qseq that is
                             // memory of the BAM record (undefined) — such a hit is dropped here
                             if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
-                        } else if ((rl == 1) != (al == 1)) {
+                        } else if (rl1 != al1) {
                             if (opi + 1 < ncig) {
-                                const unsigned nop = rc[gidx + 1] & 15u;
-                                const unsigned want = (rl == 1) ? 1u : 2u;
+                                const unsigned want = rl1 ? 1u : 2u;
                                 const bool has = (o_r + o_len - 1 == vp && nop == want);
-                                const bool h1alt = a.hp1_is_alt[vi] != 0;
-                                const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;       // lengths of the HP1 / HP2 allele strings
+                                const bool h1alt = (vr.y & VF_HP1ALT) != 0;
+                                const bool l1_is1 = h1alt ? al1 : rl1, l2_is1 = h1alt ? rl1 : al1;   // lengths of the HP1 / HP2 allele strings == 1
                                 // read shows the indel: the haplotype whose allele string is not 1 long gets the vote, else the other
                                 int hpbit = -1;
-                                if (l1 != 1 && l2 == 1) hpbit = has ? 0 : 1;
-                                else if (l1 == 1 && l2 != 1) hpbit = has ? 1 : 0;
+                                if (!l1_is1 && l2_is1) hpbit = has ? 0 : 1;
+                                else if (l1_is1 && !l2_is1) hpbit = has ? 1 : 0;
                                 cand_var = vi;
                                 cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
                             }
@@ -711,15 +717,13 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     const int off = vp - o_r;
                     if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
                     else {
-                        const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
-                        if (rl == 1 && al == 1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
-                        else if ((rl == 1) != (al == 1)) {
+                        if (rl1 && al1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                        else if (rl1 != al1) {
                             if (opi + 1 < ncig) {                                                   // :1470, :1495
-                                const unsigned nop = rc[gidx + 1] & 15u;
-                                const unsigned want = (rl == 1) ? 1u : 2u;                          // I after an insertion anchor, D after a deletion anchor
+                                const unsigned want = rl1 ? 1u : 2u;                                // I after an insertion anchor, D after a deletion anchor
                                 const int allele = (o_r + o_len - 1 == vp && nop == want) ? 1 : 0;
                                 cand_var = vi;
-                                cand_x = (2u << 30) | ((unsigned)allele << 1) | (unsigned)a.v.danger[vi];
+                                cand_x = (2u << 30) | ((unsigned)allele << 1) | ((vr.y & VF_DANGER) ? 1u : 0u);
                             }
                         }
                     }
@@ -727,27 +731,27 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
             }
             // D-op rule: only the FIRST pending variant of the op (the previous variant lies before the op)
             if (!SOM && in_del) {
-                const int pv = vi > 0 ? vpos[vi - 1] : INT_MIN;
-                if (a.have_reference && pv < o_r && a.v.hom[vi] >= 3) {
-                    const int rl = a.v.ref_len[vi], al = a.v.alt_len[vi];
+                const int pv = vi > 0 ? (int)vrec[vi - 1].x : INT_MIN;
+                if (a.have_reference && pv < o_r && (vr.y >> 24) >= 3u) {
+                    const bool rl1 = (vr.y & VF_REF1) != 0, al1 = (vr.y & VF_ALT1) != 0;
                     if (TAG) {
                         // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
                         // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
-                        if (rl == 1 && al == 1) {
+                        if (rl1 && al1) {
                             if (o_q < lq) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
-                        } else if (rl != 1 && al == 1) {
-                            const bool h1alt = a.hp1_is_alt[vi] != 0;
-                            const int l1 = h1alt ? al : rl, l2 = h1alt ? rl : al;
+                        } else if (!rl1 && al1) {
+                            const bool h1alt = (vr.y & VF_HP1ALT) != 0;
+                            const bool l1_is1 = h1alt ? al1 : rl1, l2_is1 = h1alt ? rl1 : al1;
                             int hpbit = -1;
-                            if (l1 != 1 && l2 == 1) hpbit = 0; else if (l1 == 1 && l2 != 1) hpbit = 1;
+                            if (!l1_is1 && l2_is1) hpbit = 0; else if (l1_is1 && !l2_is1) hpbit = 1;
                             cand_var = vi;
                             cand_x = (2u << 30) | (hpbit >= 0 ? 2u : 0u) | (unsigned)(hpbit > 0);
                         }
                     } else {
                         // get_snp D branch (:1539-1607)
                         if (o_q + 1 > lq) ab = true;                                                // :1559-1561
-                        else if (rl == 1 && al == 1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
-                        else if (rl != 1 && al == 1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
+                        else if (rl1 && al1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                        else if (!rl1 && al1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
                     }
                 }
             }
@@ -773,14 +777,25 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
             cur += handled;
             if (handled < 32) break;
         }
-        if (aborted) break;
-        __syncwarp();   // the next super-chunk overwrites the index
+        __syncwarp();   // the next super-chunk overwrites the index; the buffer may be refilled from the next iteration on
+        if (aborted) {
+            // the remaining super-chunks are not decoded, but the copies already requested must be consumed to keep the
+            // pipeline's parities in step: drain the one in flight (if it belongs to this read) and request the next read's
+            if (s + 1 < n_sc) {
+                const int b2 = pp.buf;
+                mbar_wait(smem_u32(&S.mbar[b2]), (pp.phase >> b2) & 1u);
+                pp.phase ^= 1u << b2;
+                __syncwarp();
+                if (next.r != 0xFFFFFFFFu && next.ncig > 0) issue_sc(a, S, next, 0, b2, lane);
+            }
+            break;
+        }
     }
     const bool bad = __any_sync(FULL, bad_op < abort_op);
     if (bad && lane == 0) atomicAdd(&a.counters->bad_cigar.v, 1ull);
-    if (!TAG && lane == 0) {
-        a.abort_of_read[r] = aborted ? abort_op : INT_MAX;
-        if (aborted) atomicAdd(&a.counters->aborted_reads.v, 1ull);
+    if (!TAG && lane == 0 && aborted) {
+        a.abort_of_read[r] = abort_op;
+        atomicAdd(&a.counters->aborted_reads.v, 1ull);
     }
 
     if (aborted || bad) {
@@ -792,20 +807,20 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
         if (lane == 0) {
             unsigned k = (unsigned)atomicAdd(&a.counters->overflow_reads.v, 1ull);
             atomicAdd(&a.counters->overflow_cands.v, (unsigned long long)ncand);
-            if (k < a.overflow_list_cap) { a.overflow_list_out[k] = (uint32_t)r; a.overflow_need_out[k] = (uint64_t)ncand; }
+            if (k < a.overflow_list_cap) { a.overflow_list_out[k] = work_slot; a.overflow_need_out[k] = (uint64_t)ncand; }
             a.ncalls[r] = 0; a.tmp_start[r] = 0; a.status[r] = LPS_READ_OK;
         }
         return;
     }
     __syncwarp();
 
+    const uint8_t *__restrict__ seq = a.b.seq4 + D.seq_off;
     if (SOM) {
-        resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq, pc);
+        resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq, pc, seq, (int)(D.flags & 0xFFu) >= a.mapping_quality);
         return;
     }
     if (TAG) {
         // ---- resolve: per candidate the haplotype bit and the "counts towards countPS" flag, then judgeReadHap ----
-        const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
         int h1 = 0, h2 = 0, ps_min = INT_MAX, ps_max = INT_MIN, nout = 0, ngather = 0;
         for (int c0 = 0; c0 < ncand; c0 += 32) {
             const int c = c0 + lane;
@@ -819,8 +834,9 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                     const int qi = (int)(cd.x & 0x3fffffffu);
                     const unsigned code = (seq[qi >> 1] >> ((~qi & 1) << 2)) & 0xfu;
                     const char base = "=ACMGRSVTWYHKDBN"[code];
-                    const char rb = (char)a.v.ref0[var], ab = (char)a.v.alt0[var];
-                    const bool h1alt = a.hp1_is_alt[var] != 0;
+                    const unsigned vy = vrec[var].y;
+                    const char rb = (char)(vy & 0xFFu), ab = (char)((vy >> 8) & 0xFFu);
+                    const bool h1alt = (vy & VF_HP1ALT) != 0;
                     const char hp1 = h1alt ? ab : rb, hp2 = h1alt ? rb : ab;
                     // M op: only a REF/ALT base counts at all (HaplotagStrategy.cpp:39); D-op rule: countPS unconditionally (:186)
                     if (kind == 1 || base == rb || base == ab) {
@@ -884,8 +900,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     }
 
     // ---- resolve candidates: gather base + quality, decide the allele, drop filterSNP variants ----
-    const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
-    const uint8_t *__restrict__ qual = a.b.qual + a.b.qual_off[r];
+    const uint8_t *__restrict__ qual = a.b.qual + D.qual_off;
     int nvalid = 0, ngather = 0;
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         const int c = c0 + lane;
@@ -896,6 +911,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
             const Cand cd = cand[c];
             const unsigned kind = cd.x >> 30;
             out.var = cd.var;
+            const unsigned vy = vrec[cd.var].y;
             if (kind == 2) {
                 out.allele = (int8_t)((cd.x >> 1) & 1u);
                 out.origin = (int8_t)((cd.x >> 2) & 1u);
@@ -907,13 +923,13 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
                 const unsigned byte = seq[qi >> 1];
                 const unsigned code = (byte >> ((~qi & 1) << 2)) & 0xfu;            // bam_seqi
                 const char base = "=ACMGRSVTWYHKDBN"[code];                          // seq_nt16_str
-                const char rb = (char)a.v.ref0[cd.var], ab = (char)a.v.alt0[cd.var];
+                const char rb = (char)(vy & 0xFFu), ab = (char)((vy >> 8) & 0xFFu);
                 out.quality = (int16_t)qual[qi];
                 out.origin = (int8_t)kind;
                 if (base == rb) { out.allele = 0; valid = true; }
                 else if (base == ab) { out.allele = 1; valid = true; }
             }
-            if (valid && a.apply_filter && a.v.filtered[cd.var]) valid = false;
+            if (valid && a.apply_filter && (vy & VF_FILTERED)) valid = false;
         }
         // compact inside the candidate buffer (reused as the staging area of the final write)
         const unsigned m = __ballot_sync(FULL, valid);
@@ -947,51 +963,96 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch<K> &S,
     }
 }
 
-// Persistent launch: every warp fetches the next read from a global counter until the batch is exhausted, so a CTA is never
-// held hostage by its longest read (read lengths are log-normal).  The overflow pass walks its list one read per warp.
-template <int K, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) k_call_alleles(K1Args a) {
+__device__ __forceinline__ ReadDesc load_desc(const uint4 *slot) { return unpack_desc(slot[0], slot[1], slot[2]); }
+
+// Persistent launch: every warp takes its reads from a global counter until the work list is exhausted, so a CTA is never held
+// hostage by its longest read (read lengths are log-normal).  Three descriptors are resident per warp (the read being walked and
+// the next two), fetched with cp.async two reads ahead; the claim that feeds the ring is issued one read ahead.  The overflow pass
+// walks its list one read per warp.
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_call_alleles(K1Args a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    WarpScratch<K> *s_all = reinterpret_cast<WarpScratch<K> *>(s_dyn);
-    __shared__ uint32_t s_mult[16];   // per op code: (consumes reference) | (consumes query) << 16; M I D N S H P = X, 0 for the rest
-    if (threadIdx.x < 16) s_mult[threadIdx.x] = ((ADV_LUT >> (2 * threadIdx.x)) & 1u) | (((ADV_LUT >> (2 * threadIdx.x + 1)) & 1u) << 16);
-    __syncthreads();
+    WarpScratch *s_all = reinterpret_cast<WarpScratch *>(s_dyn);
+    // flags of a PAIR of op codes (low 4 bits: first op, high 4 bits: second op), one byte each:
+    // consumes-reference(op0), consumes-reference(op1), consumes-query(op0), consumes-query(op1)  ->  operands of IDP.2A lo / hi
+    __shared__ uint32_t s_pair[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const unsigned t0 = (ADV_LUT >> (2 * (i & 15))) & 3u, t1 = (ADV_LUT >> (2 * (i >> 4))) & 3u;
+        s_pair[i] = (t0 & 1u) | ((t1 & 1u) << 8) | ((t0 >> 1) << 16) | ((t1 >> 1) << 24);
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpScratch<K> &S = s_all[wib];
+    WarpScratch &S = s_all[wib];
+    if (lane == 0) { mbar_init(smem_u32(&S.mbar[0]), 1u); mbar_init(smem_u32(&S.mbar[1]), 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
     PoolCursor pc;
     pc.next = 0; pc.end = 0; pc.used = 0;
+    Pipe pp;
+    pp.buf = 0; pp.phase = 0u;
+    ReadDesc none;
+    none.cigar_off = 0; none.seq_off = 0; none.qual_off = 0; none.ref_start = 0; none.lq = 0; none.ncig = 0; none.first_var = 0;
+    none.r = 0xFFFFFFFFu; none.flags = 0;
     unsigned long long dbg_t0 = 0, dbg_n = 0;
     if (a.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     if (a.overflow_reads != nullptr) {
         const long long wid = (long long)blockIdx.x * WARPS_PER_CTA + wib;
         if (wid >= a.overflow_list_cap) return;
-        unsigned none = 0;
-        bool claimed = true;
-        process_read<K, MODE>(a, S, s_mult, (int)a.overflow_reads[wid], a.overflow_buf + a.overflow_off[wid],
-                              (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]), lane, true, pc, none, claimed);
+        const uint32_t slot = a.overflow_reads[wid];
+        if (lane < 3) cp_async16(smem_u32(&S.desc[0][lane]), a.work + (size_t)slot * 3 + lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        const ReadDesc cur = load_desc(S.desc[0]);
+        if (cur.ncig > 0) issue_sc(a, S, cur, 0, 0, lane);
+        process_read<MODE>(a, S, s_pair, cur, none, pp, a.overflow_buf + a.overflow_off[wid], (int)(a.overflow_off[wid + 1] - a.overflow_off[wid]),
+                           slot, lane, pc);
         if (lane == 0 && pc.used) atomicAdd(&a.counters->n_calls.v, pc.used);
         return;
     }
-    // Work items: first the long-read tiers (longest first), then every read in batch order (reads already taken from a tier are
-    // skipped).  The NEXT item is claimed while the current read is between its two phases, so the atomic's round trip is hidden
-    // (claiming at the top of the loop made the compiler spill the pending result, i.e. wait for it at once).
-    const unsigned n0 = a.long_count[0], n1 = n0 + a.long_count[1], n2 = n1 + a.long_count[2];
-    const unsigned n_items = n2 + (unsigned)a.b.n_reads;
-    unsigned nxt = 0;
-    if (lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);
+    const uint32_t c0 = a.seg_count[0], c1 = a.seg_count[1], c2 = a.seg_count[2], n_items = c0 + c1 + c2 + a.seg_count[3];
+    // slot of the descriptor array each ring entry came from (reported when a read overflows the candidate buffer)
+    uint32_t ring_slot[3] = {0u, 0u, 0u};
+    auto fetch = [&](int k, uint32_t t) -> uint32_t {
+        uint32_t slot = 0;
+        if (t < n_items) {
+            slot = slot_of_item(a, t, c0, c1, c2);
+            if (lane < 3) cp_async16(smem_u32(&S.desc[k][lane]), a.work + (size_t)slot * 3 + lane);
+        } else if (lane == 2) S.desc[k][2].z = 0xFFFFFFFFu;
+        return slot;
+    };
+    uint32_t t_base = 0;
+    if (lane == 0) t_base = (uint32_t)atomicAdd(&a.counters->next_read.v, 3ull);
+    t_base = __shfl_sync(FULL, t_base, 0);
+    ring_slot[0] = fetch(0, t_base); ring_slot[1] = fetch(1, t_base + 1u); ring_slot[2] = fetch(2, t_base + 2u);
+    cp_async_commit();
+    uint32_t claim = 0;
+    if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);     // feeds the ring after the first read; consumed one read later
+    cp_async_wait<0>();
+    __syncwarp();
+    {
+        const ReadDesc first = load_desc(S.desc[0]);
+        if (first.r != 0xFFFFFFFFu && first.ncig > 0) issue_sc(a, S, first, 0, 0, lane);
+    }
+    int sl = 0;
     while (true) {
-        const unsigned t = __shfl_sync(FULL, nxt, 0);
-        if (t >= n_items) break;
-        bool claimed = false;
-        unsigned r;
-        bool skip = false;
-        if (t < n2) r = a.long_list[(size_t)(t < n0 ? 0 : t < n1 ? 1 : 2) * a.b.n_reads + (t < n0 ? t : t < n1 ? t - n0 : t - n1)];
-        else { r = t - n2; skip = a.b.n_cigar[r] > a.long_thr; }
-        if (!skip) process_read<K, MODE>(a, S, s_mult, (int)r, S.cand, CAND_CAP, lane, false, pc, nxt, claimed);
-        if (!claimed && lane == 0) nxt = (unsigned)atomicAdd(&a.counters->next_read.v, 1ull);   // filtered / skipped reads never reach the claim point
+        cp_async_wait<1>();            // everything but the refill issued at the end of the previous read has landed
         __syncwarp();
+        const ReadDesc cur = load_desc(S.desc[sl]);
+        if (cur.r == 0xFFFFFFFFu) break;
+        const int sn = sl == 2 ? 0 : sl + 1;
+        const ReadDesc next = load_desc(S.desc[sn]);
+        process_read<MODE>(a, S, s_pair, cur, next, pp, S.cand, CAND_CAP, sl == 0 ? ring_slot[0] : sl == 1 ? ring_slot[1] : ring_slot[2], lane, pc);
+        __syncwarp();
+        // refill this ring entry with the read claimed one read ago; claim the one after it
+        const uint32_t t = __shfl_sync(FULL, claim, 0);
+        const uint32_t ns = fetch(sl, t);
+        if (sl == 0) ring_slot[0] = ns; else if (sl == 1) ring_slot[1] = ns; else ring_slot[2] = ns;
+        cp_async_commit();
+        if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);
+        sl = sn;
         dbg_n++;
     }
+    cp_async_wait<0>();
     if (lane == 0 && pc.used) atomicAdd(&a.counters->n_calls.v, pc.used);
     if (a.dbg_times && lane == 0) {
         unsigned long long t1; unsigned smid;
@@ -1002,27 +1063,91 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) k_call_allele
     }
 }
 
-// lower_bound of every read start in the variant positions (the reference's stateful firstVariantIter, ParsingBam.cpp:1318-1319,
-// HaplotagParsingBam.cpp:555-563, equals it for a coordinate-sorted batch); one thread per read
-// Also sorts the reads with many CIGAR ops into three tiers (> 4x, > 2.5x, > 1.6x the mean): the persistent kernel starts
-// those first, so that the longest reads do not form its tail.
-__global__ void k_first_var(int n_reads, const int32_t *__restrict__ ref_start, int nv, const int32_t *__restrict__ vpos,
-                            int32_t *__restrict__ first_var, const uint32_t *__restrict__ n_cigar, uint32_t thr0, uint32_t thr1, uint32_t thr2,
-                            uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count) {
+// ---- k_prep_reads: one thread per alignment ------------------------------------------------------------------------------
+// The read filter of BamParser::direct_detect_alleles (iterator region "chr:1-lastSNP", ParsingBam.cpp:1273; MAPQ / flag filter
+// :1282-1291) or the dispatch of ChromosomeProcessor::processSingleChrom (HaplotagParsingBam.cpp:457-486, in its order): alignments
+// that are not walked get their (empty) products here and never reach k_call_alleles.  Every other alignment gets a 48-byte
+// descriptor - with lower_bound(variants, ref_start), the reference's stateful firstVariantIter (ParsingBam.cpp:1318-1319,
+// HaplotagParsingBam.cpp:555-563), which equals it for a coordinate-sorted batch - appended to one of four work segments: reads
+// with more than thr0 / thr1 / thr2 CIGAR ops (> 4x, > 2.5x, > 1.6x the mean) and the rest.  The walking kernel starts the long ones
+// first, so that they do not form its tail.
+struct PrepArgs {
+    DevBatch b;
+    int nv;
+    const int32_t *vpos;
+    int mode, mapping_quality, mapq_filter, tag_supplementary, last_var_pos;
+    uint32_t thr[3];
+    uint32_t seg_base[4];
+    uint4 *work;
+    uint32_t *seg_count;
+    uint64_t *tmp_start;
+    uint32_t *ncalls;
+    uint8_t *status;
+    int32_t *abort_of_read;
+    int8_t *tag_hp;
+    int32_t *tag_ps, *tag_pq, *tag_h1, *tag_h2;
+    uint8_t *tag_cat;
+    int32_t *tag_h3, *tag_end, *tag_len;
+    uint8_t *tag_nps;
+    int8_t *tag_hpb;
+    float *tag_sim;
+};
+
+__global__ void __launch_bounds__(256) k_prep_reads(PrepArgs p) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    {
-        const uint32_t nc = n_cigar[r];
-        const int tier = nc > thr0 ? 0 : nc > thr1 ? 1 : nc > thr2 ? 2 : -1;
-        if (tier >= 0) long_list[(size_t)tier * n_reads + atomicAdd(long_count + tier, 1u)] = (uint32_t)r;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = r < p.b.n_reads;
+    int seg = -1;
+    int ref_start = 0, lq = 0, flag = 0, mapq = 0;
+    uint32_t ncig = 0;
+    if (in_range) {
+        ref_start = p.b.ref_start[r]; lq = p.b.l_qseq[r]; ncig = p.b.n_cigar[r]; flag = p.b.flag[r]; mapq = p.b.mapq[r];
+        const bool tag = p.mode != LPS_MODE_PHASE, som = p.mode >= LPS_MODE_EXTRACT_NORMAL;
+        bool walk;
+        if (!tag) {
+            walk = !(ref_start >= p.last_var_pos || mapq < p.mapping_quality || (flag & (0x4 | 0x100 | 0x400)));
+            p.abort_of_read[r] = INT_MAX;
+        } else {
+            int cat = LPS_TAG_PROCESSED;
+            if (mapq < p.mapping_quality && p.mapq_filter) cat = LPS_TAG_LOW_MAPQ;
+            else if (flag & 0x4) cat = LPS_TAG_UNMAPPED;
+            else if (flag & 0x100) cat = LPS_TAG_SECONDARY;
+            else if ((flag & 0x800) && !p.tag_supplementary) cat = LPS_TAG_SUPPLEMENTARY;
+            else if (p.nv == 0) cat = LPS_TAG_EMPTY_VARIANTS;
+            else if (!(ref_start <= p.last_var_pos)) cat = LPS_TAG_OTHER;
+            p.tag_cat[r] = (uint8_t)cat;
+            walk = cat == LPS_TAG_PROCESSED;
+            if (!walk) {
+                p.tag_hp[r] = 0; p.tag_ps[r] = 0; p.tag_pq[r] = 0; p.tag_h1[r] = 0; p.tag_h2[r] = 0;
+                if (som) { p.tag_h3[r] = 0; p.tag_end[r] = 0; p.tag_len[r] = 0; p.tag_nps[r] = 0; p.tag_hpb[r] = 0; p.tag_sim[r] = 0.f; }
+            }
+        }
+        if (!walk) { p.ncalls[r] = 0; p.tmp_start[r] = 0; p.status[r] = LPS_READ_FILTERED; }
+        else seg = ncig > p.thr[0] ? 0 : ncig > p.thr[1] ? 1 : ncig > p.thr[2] ? 2 : 3;
     }
-    const int key = ref_start[r];
-    int lo = 0, hi = nv;
+    // one atomic per warp and segment
+    uint32_t slot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(FULL, seg == k);
+        if (m == 0) continue;
+        uint32_t base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(p.seg_count + k, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (seg == k) slot = p.seg_base[k] + base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    }
+    if (seg < 0) return;
+    int lo = 0, hi = p.nv;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (vpos[mid] < key) lo = mid + 1; else hi = mid;
+        if (p.vpos[mid] < ref_start) lo = mid + 1; else hi = mid;
     }
-    first_var[r] = lo;
+    const uint64_t co = p.b.cigar_off[r], so = p.b.seq_off[r], qo = p.b.qual_off[r];
+    uint4 *w = p.work + (size_t)slot * 3;
+    w[0] = make_uint4((uint32_t)co, (uint32_t)(co >> 32), (uint32_t)so, (uint32_t)(so >> 32));
+    w[1] = make_uint4((uint32_t)qo, (uint32_t)(qo >> 32), (uint32_t)ref_start, (uint32_t)lq);
+    w[2] = make_uint4(ncig, (uint32_t)lo, (uint32_t)r, (uint32_t)mapq | ((uint32_t)flag << 8));
 }
 
 // clip events of aborted reads: the reference stops walking at the aborting op, so events at or after it never happened
@@ -1058,35 +1183,43 @@ __global__ void k_widen_u32(int n, const uint32_t *__restrict__ in, uint64_t *__
 static_assert(sizeof(lps_call) == 8, "lps_call must be 8 bytes");
 
 namespace {
-constexpr size_t K1_SMEM = sizeof(WarpScratch<KOPS>) * WARPS_PER_CTA;
+constexpr size_t K1_SMEM = sizeof(WarpScratch) * WARPS_PER_CTA;
 
-template <int MODE> void prepare_k1() {
-    cudaFuncSetAttribute(k_call_alleles<KOPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM);
-    cudaFuncSetAttribute(k_call_alleles<KOPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+template <int MODE> cudaError_t prepare_k1() {
+    cudaError_t e = cudaFuncSetAttribute(k_call_alleles<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_call_alleles<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     if (getenv("LPS_DEBUG_OCC")) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_call_alleles<KOPS, MODE>, WARPS_PER_CTA * 32, K1_SMEM);
-        fprintf(stderr, "k_call_alleles<%d,%d>: %d resident CTAs per SM\n", KOPS, MODE, nb);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_call_alleles<MODE>, WARPS_PER_CTA * 32, K1_SMEM);
+        fprintf(stderr, "k_call_alleles<%d>: %d resident CTAs per SM, %zu bytes of dynamic shared memory\n", MODE, nb, K1_SMEM);
     }
+    return cudaSuccess;
 }
 
 void launch_k1(int mode, int grid, cudaStream_t st, const K1Args &a) {
     const int tb = WARPS_PER_CTA * 32;
-    static bool prepared = false;
-    if (!prepared) {
-        prepare_k1<LPS_MODE_PHASE>(); prepare_k1<LPS_MODE_GERMLINE>(); prepare_k1<LPS_MODE_EXTRACT_NORMAL>();
-        prepare_k1<LPS_MODE_EXTRACT_TUMOR>(); prepare_k1<LPS_MODE_SOMATIC_TAG>();
-        prepared = true;
-    }
     switch (mode) {
-        case LPS_MODE_PHASE: k_call_alleles<KOPS, LPS_MODE_PHASE><<<grid, tb, K1_SMEM, st>>>(a); break;
-        case LPS_MODE_GERMLINE: k_call_alleles<KOPS, LPS_MODE_GERMLINE><<<grid, tb, K1_SMEM, st>>>(a); break;
-        case LPS_MODE_EXTRACT_NORMAL: k_call_alleles<KOPS, LPS_MODE_EXTRACT_NORMAL><<<grid, tb, K1_SMEM, st>>>(a); break;
-        case LPS_MODE_EXTRACT_TUMOR: k_call_alleles<KOPS, LPS_MODE_EXTRACT_TUMOR><<<grid, tb, K1_SMEM, st>>>(a); break;
-        default: k_call_alleles<KOPS, LPS_MODE_SOMATIC_TAG><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_PHASE: k_call_alleles<LPS_MODE_PHASE><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_GERMLINE: k_call_alleles<LPS_MODE_GERMLINE><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_EXTRACT_NORMAL: k_call_alleles<LPS_MODE_EXTRACT_NORMAL><<<grid, tb, K1_SMEM, st>>>(a); break;
+        case LPS_MODE_EXTRACT_TUMOR: k_call_alleles<LPS_MODE_EXTRACT_TUMOR><<<grid, tb, K1_SMEM, st>>>(a); break;
+        default: k_call_alleles<LPS_MODE_SOMATIC_TAG><<<grid, tb, K1_SMEM, st>>>(a); break;
     }
 }
 }  // namespace
+
+// Function attributes belong to the device (its primary context), not to the process: called from lps_ctx_create with the
+// context's device current, so every GPU a process opens a context on gets the shared-memory opt-in.
+int lps_prepare_call_alleles(lps_ctx *ctx) {
+    LPS_CUDA(ctx, prepare_k1<LPS_MODE_PHASE>());
+    LPS_CUDA(ctx, prepare_k1<LPS_MODE_GERMLINE>());
+    LPS_CUDA(ctx, prepare_k1<LPS_MODE_EXTRACT_NORMAL>());
+    LPS_CUDA(ctx, prepare_k1<LPS_MODE_EXTRACT_TUMOR>());
+    LPS_CUDA(ctx, prepare_k1<LPS_MODE_SOMATIC_TAG>());
+    return LPS_OK;
+}
 
 int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls, int mode) {
     const bool tag = t != nullptr;
@@ -1100,21 +1233,8 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     LPS_CUDA(ctx, ctx->d_ncalls.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_status.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_counters.reserve(1));
-    LPS_CUDA(ctx, ctx->d_first_var.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_abort_of_read.reserve((size_t)n + 1));
-    LPS_CUDA(ctx, ctx->d_long_list.reserve(3 * (size_t)n + 4));
-    LPS_CUDA(ctx, ctx->d_long_count.reserve(4));
-    const double mean_ops = n > 0 ? (double)ctx->batch.cigar_len / (double)n : 0.0;
-    const char *lpt_env = getenv("LPS_LPT");
-    const bool lpt = !(lpt_env && lpt_env[0] == '0');
-    const uint32_t thr0 = lpt ? (uint32_t)(4.0 * mean_ops) + 64 : 0xFFFFFFFFu, thr1 = lpt ? (uint32_t)(2.5 * mean_ops) + 64 : 0xFFFFFFFFu,
-                   thr2 = lpt ? (uint32_t)(1.6 * mean_ops) + 64 : 0xFFFFFFFFu;
-    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_long_count.p, 0, 4 * sizeof(uint32_t), st));
-    if (n > 0) {
-        k_first_var<<<(n + 255) / 256, 256, 0, st>>>(n, ctx->batch.ref_start, nv, ctx->var.pos, ctx->d_first_var.p, ctx->batch.n_cigar, thr0, thr1,
-                                                     thr2, ctx->d_long_list.p, ctx->d_long_count.p);
-        ctx->stats.kernel_launches++;
-    }
+    LPS_CUDA(ctx, ctx->d_seg_count.reserve(4));
     if (tag) {
         LPS_CUDA(ctx, ctx->d_tag_hp.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_ps.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_pq.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_h1.reserve((size_t)n + 1));
@@ -1124,6 +1244,34 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, ctx->d_tag_h3.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_end.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_len.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_nps.reserve((size_t)n + 1));
         LPS_CUDA(ctx, ctx->d_tag_hpb.reserve((size_t)n + 1)); LPS_CUDA(ctx, ctx->d_tag_sim.reserve((size_t)n + 1));
+    }
+    // ---- work list: descriptors of the alignments that are walked, long reads first ----
+    // Segment capacities follow from Markov's inequality on the batch's own mean: at most n / k reads have more than k x mean ops.
+    const double mean_ops = n > 0 ? (double)ctx->batch.cigar_len / (double)n : 0.0;
+    const char *lpt_env = getenv("LPS_LPT");
+    const bool lpt = !(lpt_env && lpt_env[0] == '0');
+    PrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.thr[0] = lpt ? (uint32_t)(4.0 * mean_ops) + 64 : 0xFFFFFFFFu;
+    pa.thr[1] = lpt ? (uint32_t)(2.5 * mean_ops) + 64 : 0xFFFFFFFFu;
+    pa.thr[2] = lpt ? (uint32_t)(1.6 * mean_ops) + 64 : 0xFFFFFFFFu;
+    const size_t seg_cap[4] = {(size_t)n / 4 + 2, (size_t)(n / 2.5) + 2, (size_t)(n / 1.6) + 2, (size_t)n + 2};
+    pa.seg_base[0] = 0;
+    for (int k = 1; k < 4; k++) pa.seg_base[k] = pa.seg_base[k - 1] + (uint32_t)seg_cap[k - 1];
+    LPS_CUDA(ctx, ctx->d_work.reserve(3 * ((size_t)pa.seg_base[3] + seg_cap[3]) + 3));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_seg_count.p, 0, 4 * sizeof(uint32_t), st));
+    pa.b = ctx->batch; pa.nv = nv; pa.vpos = ctx->var.pos; pa.mode = mode;
+    pa.mapping_quality = tag ? t->mapping_quality : p->mapping_quality;
+    pa.mapq_filter = tag ? t->mapq_filter : 0; pa.tag_supplementary = tag ? t->tag_supplementary : 0;
+    pa.last_var_pos = nv ? ctx->h_vpos[nv - 1] : -1;
+    pa.work = ctx->d_work.p; pa.seg_count = ctx->d_seg_count.p;
+    pa.tmp_start = ctx->d_tmp_start.p; pa.ncalls = ctx->d_ncalls.p; pa.status = ctx->d_status.p; pa.abort_of_read = ctx->d_abort_of_read.p;
+    pa.tag_hp = ctx->d_tag_hp.p; pa.tag_ps = ctx->d_tag_ps.p; pa.tag_pq = ctx->d_tag_pq.p; pa.tag_h1 = ctx->d_tag_h1.p; pa.tag_h2 = ctx->d_tag_h2.p;
+    pa.tag_cat = ctx->d_tag_cat.p; pa.tag_h3 = ctx->d_tag_h3.p; pa.tag_end = ctx->d_tag_end.p; pa.tag_len = ctx->d_tag_len.p;
+    pa.tag_nps = ctx->d_tag_nps.p; pa.tag_hpb = ctx->d_tag_hpb.p; pa.tag_sim = ctx->d_tag_sim.p;
+    if (n > 0) {
+        k_prep_reads<<<(n + 255) / 256, 256, 0, st>>>(pa);
+        ctx->stats.kernel_launches++;
     }
     // tumor pass: one window-diff work item per (alignment, covered tumor position); sized from the tumor density, re-run on overflow
     size_t wd_cap = 0;
@@ -1137,19 +1285,20 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     double density = 0.0;
     if (nv > 1) density = (double)nv / ((double)ctx->h_vpos[nv - 1] - (double)ctx->h_vpos[0] + 1.0);
     size_t cap = (size_t)((double)ctx->sum_l_qseq * density * 1.5) + (size_t)n * 4 + 4096 +
-                 (size_t)ctx->sm_count * CTAS_PER_SM * WARPS_PER_CTA * POOL_BLOCK;   // every warp may leave one block partly unused
+                 (size_t)ctx->sm_count * WARPS_PER_CTA * POOL_BLOCK;   // every warp may leave one block partly unused
     if (cap < ctx->d_calls_tmp.cap) cap = ctx->d_calls_tmp.cap;
     size_t clip_cap = (size_t)n * 2 + 1024;
     if (clip_cap < ctx->d_clip_keys.cap) clip_cap = ctx->d_clip_keys.cap;
-    const uint32_t ovf_cap = 1u << 16;
-    LPS_CUDA(ctx, ctx->d_overflow_reads.reserve(ovf_cap));
-    LPS_CUDA(ctx, ctx->d_overflow_cand.reserve(ovf_cap));
+    size_t ovf_cap = 1u << 14;                                         // reads beyond the shared candidate buffer; grown on demand
+    if (ovf_cap < ctx->d_overflow_reads.cap) ovf_cap = ctx->d_overflow_reads.cap;
 
     CallCounters hc;
-    for (int attempt = 0; attempt < 3; attempt++) {
+    for (int attempt = 0; attempt < 4; attempt++) {
         LPS_CUDA(ctx, ctx->d_calls_tmp.reserve(cap));
         LPS_CUDA(ctx, ctx->d_clip_keys.reserve(clip_cap));
         LPS_CUDA(ctx, ctx->d_clip_meta.reserve(ctx->d_clip_keys.cap));
+        LPS_CUDA(ctx, ctx->d_overflow_reads.reserve(ovf_cap));
+        LPS_CUDA(ctx, ctx->d_overflow_cand.reserve(ctx->d_overflow_reads.cap));
         LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(CallCounters), st));
         if (som) {
             // per-slot counters start from zero on every attempt (a re-run after a pool overflow must not count twice)
@@ -1186,19 +1335,21 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         a.calls_tmp = ctx->d_calls_tmp.p; a.calls_cap = ctx->d_calls_tmp.cap;
         a.tmp_start = ctx->d_tmp_start.p; a.ncalls = ctx->d_ncalls.p; a.status = ctx->d_status.p;
         a.clip_keys = ctx->d_clip_keys.p; a.clip_cap = ctx->d_clip_keys.cap; a.clip_meta = ctx->d_clip_meta.p;
-        a.abort_of_read = ctx->d_abort_of_read.p; a.first_var = ctx->d_first_var.p;
-        a.long_list = ctx->d_long_list.p; a.long_count = ctx->d_long_count.p; a.long_thr = thr2;
+        a.abort_of_read = ctx->d_abort_of_read.p;
+        a.work = ctx->d_work.p; a.seg_count = ctx->d_seg_count.p;
+        for (int k = 0; k < 4; k++) a.seg_base[k] = pa.seg_base[k];
+        const int max_warps = ctx->sm_count * WARPS_PER_CTA;
         if (getenv("LPS_DEBUG_K1")) {
-            LPS_CUDA(ctx, ctx->d_dbg_times.reserve(4 * (size_t)ctx->sm_count * CTAS_PER_SM * WARPS_PER_CTA + 64));
+            LPS_CUDA(ctx, ctx->d_dbg_times.reserve(4 * (size_t)max_warps + 64));
             LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_dbg_times.p, 0, 8 * ctx->d_dbg_times.cap, st));
             a.dbg_times = ctx->d_dbg_times.p;
         }
         a.counters = ctx->d_counters.p;
         a.count_gathers = ctx->zero_copy ? 1 : 0;
         a.overflow_list_out = ctx->d_overflow_reads.p; a.overflow_need_out = ctx->d_overflow_cand.p;
-        a.overflow_list_cap = ovf_cap;
+        a.overflow_list_cap = (uint32_t)std::min<size_t>(ctx->d_overflow_reads.cap, 0xFFFFFFFFu);
         int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        if (grid > ctx->sm_count * CTAS_PER_SM) grid = ctx->sm_count * CTAS_PER_SM;   // resident CTAs only, reads fetched dynamically
+        if (grid > ctx->sm_count) grid = ctx->sm_count;   // resident CTAs only (one per SM), reads fetched dynamically
         if (grid > 0) {
             cudaEventRecord(ctx->kev[0], st);
             launch_k1(mode, grid, st, a);
@@ -1215,33 +1366,40 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             cudaMemcpy(h.data(), a.dbg_times, 32 * nw, cudaMemcpyDeviceToHost);
             unsigned long long t0 = ~0ull, t1 = 0;
             for (size_t w = 0; w < nw; w++) { if (h[4 * w] && h[4 * w] < t0) t0 = h[4 * w]; if (h[4 * w + 1] > t1) t1 = h[4 * w + 1]; }
-            std::vector<double> st, en, cnt;
-            for (size_t w = 0; w < nw; w++) { st.push_back((double)(h[4 * w] - t0) / 1e3); en.push_back((double)(h[4 * w + 1] - t0) / 1e3); cnt.push_back((double)h[4 * w + 2]); }
-            std::sort(st.begin(), st.end()); std::sort(en.begin(), en.end()); std::sort(cnt.begin(), cnt.end());
+            std::vector<double> st_, en, cnt;
+            for (size_t w = 0; w < nw; w++) { st_.push_back((double)(h[4 * w] - t0) / 1e3); en.push_back((double)(h[4 * w + 1] - t0) / 1e3); cnt.push_back((double)h[4 * w + 2]); }
+            std::sort(st_.begin(), st_.end()); std::sort(en.begin(), en.end()); std::sort(cnt.begin(), cnt.end());
             auto q = [&](std::vector<double> &v, double f) { return v[(size_t)(f * (v.size() - 1))]; };
             fprintf(stderr, "k1 warps=%zu span=%.1f us | start us p0 %.1f p50 %.1f p99 %.1f max %.1f | end us p0 %.1f p10 %.1f p50 %.1f p90 %.1f max %.1f | reads/warp min %.0f p50 %.0f max %.0f\n",
-                    nw, (double)(t1 - t0) / 1e3, q(st, 0), q(st, .5), q(st, .99), q(st, 1), q(en, 0), q(en, .1), q(en, .5), q(en, .9), q(en, 1), q(cnt, 0), q(cnt, .5), q(cnt, 1));
+                    nw, (double)(t1 - t0) / 1e3, q(st_, 0), q(st_, .5), q(st_, .99), q(st_, 1), q(en, 0), q(en, .1), q(en, .5), q(en, .9), q(en, 1), q(cnt, 0), q(cnt, .5), q(cnt, 1));
         }
         if (getenv("LPS_DEBUG_K1"))
             fprintf(stderr, "k1 mode=%d attempt=%d grid=%d ms=%.4f pool=%llu/%zu calls=%llu clips=%llu overflow_reads=%u aborted=%u\n", mode, attempt, grid,
-                    ctx->stats.ms_kernel_call_alleles, hc.tmp_calls.v, ctx->d_calls_tmp.cap, hc.n_calls.v, hc.clips.v, hc.overflow_reads.v, hc.aborted_reads.v);
+                    ctx->stats.ms_kernel_call_alleles, hc.tmp_calls.v, ctx->d_calls_tmp.cap, hc.n_calls.v, hc.clips.v, (unsigned)hc.overflow_reads.v, (unsigned)hc.aborted_reads.v);
         // zero-copy accounting: one 32-byte sector of SEQ (phase: and one of QUAL) crosses PCIe per gathered candidate
         if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers.v * (tag ? 32ull : 64ull);
         if (hc.bad_cigar.v) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
-        if (hc.overflow_reads.v > ovf_cap) return ctx->fail(LPS_E_NOMEM, "too many reads overflow the candidate buffer");
+        if (hc.overflow_reads.v > ctx->d_overflow_reads.cap) {
+            // more reads overflow the shared candidate buffer than the list holds (dense variants, long reads): grow the list and redo
+            // the attempt, like the call pool
+            if (attempt == 3) return ctx->fail(LPS_E_NOMEM, "overflow list sizing did not converge");
+            ovf_cap = (size_t)hc.overflow_reads.v + (size_t)hc.overflow_reads.v / 8 + 1024;
+            if (hc.tmp_calls.v > ctx->d_calls_tmp.cap) cap = (size_t)hc.tmp_calls.v + (size_t)hc.tmp_calls.v / 8 + 65536;
+            continue;
+        }
         if (hc.overflow_reads.v) {
-            // second pass for the few reads with more candidates than the shared buffer: same kernel,
-            // candidate lists in global memory sized from the first pass
+            // second pass for the reads with more candidates than the shared buffer: same kernel, candidate lists in global memory
+            // sized from the first pass
             std::vector<uint64_t> need(hc.overflow_reads.v), off(hc.overflow_reads.v + 1, 0);
             LPS_CUDA(ctx, cudaMemcpy(need.data(), ctx->d_overflow_cand.p, 8 * (size_t)hc.overflow_reads.v, cudaMemcpyDeviceToHost));
-            for (uint32_t i = 0; i < hc.overflow_reads.v; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
+            for (size_t i = 0; i < hc.overflow_reads.v; i++) off[i + 1] = off[i] + need[i] * (som ? 2 : 1);   // 8-byte units
             LPS_CUDA(ctx, ctx->d_overflow_off.reserve(off.size()));
             LPS_CUDA(ctx, cudaMemcpy(ctx->d_overflow_off.p, off.data(), 8 * off.size(), cudaMemcpyHostToDevice));
             // persistent scratch of the context: the dense configs (C5) take this path on every call
             LPS_CUDA(ctx, ctx->d_ovf_cand.reserve(8 * ((size_t)off.back() + 2)));
             K1Args b2 = a;
             b2.overflow_reads = ctx->d_overflow_reads.p; b2.overflow_off = ctx->d_overflow_off.p; b2.overflow_buf = reinterpret_cast<Cand *>(ctx->d_ovf_cand.p);
-            b2.overflow_list_cap = hc.overflow_reads.v;
+            b2.overflow_list_cap = (uint32_t)hc.overflow_reads.v;
             // the overflow pass must not append the clips / counters of these reads a second time
             b2.clip_cap = 0;
             LPS_CUDA(ctx, ctx->d_counters2.reserve(1));
@@ -1261,8 +1419,9 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         cap = (size_t)hc.tmp_calls.v + (size_t)hc.tmp_calls.v / 8 + 65536;   // the block hand-out is not deterministic: leave slack
         clip_cap = (size_t)hc.clips.v + 1024;
         if (wd_cap) wd_cap = (size_t)hc.wd_items.v + 1024;
-        if (attempt == 2) return ctx->fail(LPS_E_NOMEM, "call pool sizing did not converge");
+        if (attempt == 3) return ctx->fail(LPS_E_NOMEM, "call pool sizing did not converge");
     }
+
 
     // CSR offsets in read order
     const int tb = 256;

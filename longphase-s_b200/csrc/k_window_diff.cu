@@ -29,14 +29,26 @@ struct WdArgs {
     int32_t *window_hist;       // [n_tum][2][LPS_WINDOW_BINS]
 };
 
+// length of op `ci` of a read whose ops start at index `gop0` of the 16-bit stream: the 12-bit field, or the side table for an escaped op
+__device__ __forceinline__ int wd_len(const DevBatch &b, const uint16_t *__restrict__ cig, int ci, uint64_t gop0) {
+    const uint32_t len = (uint32_t)cig[ci] >> 4;
+    if (len != 0xFFFu) return (int)len;
+    uint32_t lo = 0, hi = b.n_long;
+    const uint64_t gop = gop0 + (uint64_t)ci;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (b.long_at[mid] < gop) lo = mid + 1; else hi = mid;
+    }
+    return (lo < b.n_long && b.long_at[lo] == gop) ? (int)b.long_len[lo] : 0xFFF;
+}
+
 // processCigarOperation (:627-654)
-__device__ __forceinline__ bool next_op(const uint32_t *__restrict__ cig, int &ci, int ci_end, int dir, int &remaining, int &read_pos, int &ref_pos,
-                                        int &op) {
+__device__ __forceinline__ bool next_op(const DevBatch &b, const uint16_t *__restrict__ cig, uint64_t gop0, int &ci, int ci_end, int dir, int &remaining,
+                                        int &read_pos, int &ref_pos, int &op) {
     ci += dir;
     while (ci < ci_end && ci >= 0) {
-        const uint32_t c = cig[ci];
-        op = (int)(c & 15u);
-        const int len = (int)(c >> 4);
+        op = (int)(cig[ci] & 15u);
+        const int len = wd_len(b, cig, ci, gop0);
         if (op == 0 || op == 3 || op == 6 || op == 7 || op == 8) { remaining += len; return true; }
         else if (op == 1) read_pos += len * dir;
         else if (op == 2) ref_pos += len * dir;
@@ -47,7 +59,7 @@ __device__ __forceinline__ bool next_op(const uint32_t *__restrict__ cig, int &c
 }
 
 // getOrderWindowsDiffRef (:655-686), segment by segment.  `remaining` is the budget BEFORE the decrement of iteration i.
-__device__ __forceinline__ void scan(const WdArgs &a, const uint32_t *__restrict__ cig, int ci, int ncig, const uint8_t *__restrict__ seq, int lq,
+__device__ __forceinline__ void scan(const WdArgs &a, const uint16_t *__restrict__ cig, uint64_t gop0, int ci, int ncig, const uint8_t *__restrict__ seq, int lq,
                                      int read_pos, int remaining, int ref_pos, const int dir, int32_t *__restrict__ hist, const int sub) {
     int op = (int)(cig[ci] & 15u);
     int i = 1;
@@ -55,7 +67,7 @@ __device__ __forceinline__ void scan(const WdArgs &a, const uint32_t *__restrict
         int first = 0;
         if (remaining == 1 || remaining == 0) {            // the decrement of iteration i gives 0 or -1: hop before executing it
             remaining -= 1;
-            if (!next_op(cig, ci, ncig, dir, remaining, read_pos, ref_pos, op)) return;
+            if (!next_op(a.b, cig, gop0, ci, ncig, dir, remaining, read_pos, ref_pos, op)) return;
             first = 1;                                     // iteration i runs in the new op without another decrement
         }
         // iterations that follow without a hop: until the decrement gives 0; a negative budget never hops again
@@ -90,17 +102,18 @@ __global__ void __launch_bounds__(128) k_window_diff(WdArgs a) {
     if (t >= a.n_items) return;
     const WdItem it = a.items[t];
     const int r = (int)it.read;
-    const uint32_t *__restrict__ cig = a.b.cigar + a.b.cigar_off[r];
+    const uint64_t gop0 = a.b.cigar_off[r];
+    const uint16_t *__restrict__ cig = a.b.cigar16 + gop0;
     const uint8_t *__restrict__ seq = a.b.seq4 + a.b.seq_off[r];
     const int ncig = (int)a.b.n_cigar[r], lq = a.b.l_qseq[r];
     const int ci = (int)it.opi, off = (int)it.off;
     const int var_pos = a.vpos[a.tum_var[it.slot2 >> 1]];
     int32_t *hist = a.window_hist + (size_t)it.slot2 * LPS_WINDOW_BINS;
     // getWindowsDiffRef (:688-710): the op is an M/=/X op, never an insertion
-    const int oplen = (int)(cig[ci] >> 4);
+    const int oplen = wd_len(a.b, cig, ci, gop0);
     const int fwd = oplen - off > 0 ? oplen - off : 0, rev = off > 0 ? off : 0;
-    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, rev, var_pos, -1, hist, sub);
-    scan(a, cig, ci, ncig, seq, lq, (int)it.qidx, fwd, var_pos, 1, hist, sub);
+    scan(a, cig, gop0, ci, ncig, seq, lq, (int)it.qidx, rev, var_pos, -1, hist, sub);
+    scan(a, cig, gop0, ci, ncig, seq, lq, (int)it.qidx, fwd, var_pos, 1, hist, sub);
 }
 
 }  // namespace

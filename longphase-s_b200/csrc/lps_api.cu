@@ -2,6 +2,7 @@
 #include <chrono>
 #include <climits>
 #include <cmath>
+#include <cub/cub.cuh>
 #include "lps_ctx.cuh"
 
 namespace {
@@ -33,18 +34,35 @@ __global__ void k_first_last(int m, const int32_t *__restrict__ reads, const uin
     ncalls[i] = (uint32_t)(c1 - c0);
 }
 
-// compact CIGAR stream -> BAM's uint32 ops: len<<4|op in 16 bits is the low half of the same value in 32 bits, so widening is a
-// zero extension, eight ops per thread (one 128-bit load, two 128-bit stores); ops marked 0xFFF are patched afterwards
-__global__ void k_widen_cigar16(size_t n8, const uint4 *__restrict__ in, uint4 *__restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
-    const uint4 v = __ldg(in + i);
-    out[2 * i] = make_uint4(v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16);
-    out[2 * i + 1] = make_uint4(v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16);
+// BAM's uint32 CIGAR ops -> the 16-bit stream the kernels read (len << 4 | op; a length >= 4095 becomes 0xFFF and goes to the side
+// table).  Eight ops per thread: two 128-bit loads, one 128-bit store.  Escapes are appended as (op index << 28 | length) keys and
+// sorted afterwards (they are rare: N ops, long matches of high-accuracy reads), which gives the table in ascending op order.
+__global__ void k_narrow_cigar32(size_t n, const uint32_t *__restrict__ in, uint16_t *__restrict__ out, unsigned long long *__restrict__ long_keys,
+                                 unsigned int long_cap, unsigned int *__restrict__ n_long) {
+    const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i8 >= n) return;
+    uint32_t w[8];
+    if (i8 + 8 <= n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(in + i8)), b = __ldg(reinterpret_cast<const uint4 *>(in + i8 + 4));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+        for (int j = 0; j < 8; j++) w[j] = i8 + j < n ? in[i8 + j] : 1u;
+    }
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t len = w[j] >> 4;
+        if (len >= 0xFFFu) {
+            h[j] = 0xFFF0u | (w[j] & 15u);
+            const unsigned int k = atomicAdd(n_long, 1u);
+            if (k < long_cap) long_keys[k] = ((unsigned long long)(i8 + j) << 28) | (unsigned long long)len;
+        } else h[j] = w[j] & 0xFFFFu;
+    }
+    *reinterpret_cast<uint4 *>(out + i8) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
 }
-__global__ void k_patch_long_ops(size_t n, const uint64_t *__restrict__ at, const uint32_t *__restrict__ len, uint32_t *__restrict__ cigar) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) cigar[at[i]] = (len[i] << 4) | (cigar[at[i]] & 15u);
+__global__ void k_unpack_long_keys(unsigned int n, const unsigned long long *__restrict__ keys, uint64_t *__restrict__ at, uint32_t *__restrict__ len) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { at[i] = keys[i] >> 28; len[i] = (uint32_t)(keys[i] & 0xFFFFFFFull); }
 }
 
 __global__ void k_mark_dead(int m, const int32_t *__restrict__ reads, uint8_t *__restrict__ dead) {
@@ -72,6 +90,61 @@ float elapsed(lps_ctx *ctx, int a, int b) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
     return ms;
+}
+
+// a uint32 CIGAR stream in DEVICE memory -> ctx->d_cigar16 + the side table of escaped lengths
+int narrow_cigar(lps_ctx *ctx, const uint32_t *d_cigar32, uint64_t n_ops) {
+    cudaStream_t st = ctx->stream;
+    LPS_CUDA(ctx, ctx->d_cigar16.reserve((size_t)n_ops + 64));
+    LPS_CUDA(ctx, ctx->d_n_long.reserve(1));
+    unsigned int n_long = 0;
+    size_t cap = std::max<size_t>(ctx->d_long_keys.cap, 4096);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        LPS_CUDA(ctx, ctx->d_long_keys.reserve(cap));
+        LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_long.p, 0, 4, st));
+        if (n_ops) {
+            const size_t threads = (n_ops + 7) / 8;
+            k_narrow_cigar32<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((size_t)n_ops, d_cigar32, ctx->d_cigar16.p,
+                                                                                (unsigned long long *)ctx->d_long_keys.p,
+                                                                                (unsigned int)std::min<size_t>(ctx->d_long_keys.cap, 0xFFFFFFFFu), ctx->d_n_long.p);
+            ctx->stats.kernel_launches++;
+        }
+        LPS_CUDA(ctx, cudaMemcpyAsync(&n_long, ctx->d_n_long.p, 4, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n_long <= ctx->d_long_keys.cap) break;
+        cap = (size_t)n_long + 1024;
+    }
+    LPS_CUDA(ctx, ctx->d_cigar_long_at.reserve((size_t)n_long + 1));
+    LPS_CUDA(ctx, ctx->d_cigar_long_len.reserve((size_t)n_long + 1));
+    if (n_long) {
+        DevBuf<uint64_t> &sorted = ctx->d_aln_keys_sorted;       // scratch of the graph stage, free at submit time
+        LPS_CUDA(ctx, sorted.reserve((size_t)n_long + 1));
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->d_long_keys.p, sorted.p, (int)n_long, 0, 64, st);
+        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(tmp + 256));
+        cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, tmp, ctx->d_long_keys.p, sorted.p, (int)n_long, 0, 64, st);
+        k_unpack_long_keys<<<(n_long + 255) / 256, 256, 0, st>>>(n_long, (const unsigned long long *)sorted.p, ctx->d_cigar_long_at.p, ctx->d_cigar_long_len.p);
+        ctx->stats.kernel_launches += 2;
+    }
+    LPS_CUDA(ctx, cudaGetLastError());
+    DevBatch &d = ctx->batch;
+    d.cigar16 = ctx->d_cigar16.p; d.long_at = ctx->d_cigar_long_at.p; d.long_len = ctx->d_cigar_long_len.p; d.n_long = n_long;
+    return LPS_OK;
+}
+
+// O(n) sanity of the offsets an integrator hands in: the kernels index with them directly
+int validate_batch(lps_ctx *ctx, const lps_read_batch *b) {
+    for (int32_t i = 0; i < b->n_reads; i++) {
+        const int64_t lq = b->l_qseq[i];
+        if (lq < 0) return ctx->fail(LPS_E_ARG, "negative l_qseq");
+        if (b->cigar_off[i] > b->cigar_len || (uint64_t)b->n_cigar[i] > b->cigar_len - b->cigar_off[i])
+            return ctx->fail(LPS_E_ARG, "cigar_off + n_cigar runs past cigar_len");
+        if (lq > 0 && (b->seq_off[i] > b->seq_bytes || (uint64_t)(lq + 1) / 2 > b->seq_bytes - b->seq_off[i]))
+            return ctx->fail(LPS_E_ARG, "seq_off + (l_qseq + 1) / 2 runs past seq_bytes");
+        if (lq > 0 && (b->qual_off[i] > b->qual_bytes || (uint64_t)lq > b->qual_bytes - b->qual_off[i]))
+            return ctx->fail(LPS_E_ARG, "qual_off + l_qseq runs past qual_bytes");
+    }
+    return LPS_OK;
 }
 
 }  // namespace
@@ -122,6 +195,7 @@ int lps_ctx_create(int device, lps_ctx **out) {
         if (ctx->d_pq_lut.reserve(lut.size()) != cudaSuccess ||
             cudaMemcpy(ctx->d_pq_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
     }
+    if (lps_prepare_call_alleles(ctx) != LPS_OK) { delete ctx; return LPS_E_CUDA; }   // function attributes are per device
     *out = ctx;
     return LPS_OK;
 }
@@ -147,6 +221,7 @@ int lps_contig_set_reference(lps_ctx *ctx, const char *ref_ascii, int64_t len) {
     if (!ctx || (len > 0 && !ref_ascii) || len < 0) return LPS_E_ARG;
     cudaSetDevice(ctx->device);
     TRY(h2d(ctx, ctx->d_ref, ref_ascii, (size_t)len));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller may free or reuse ref_ascii as soon as this returns
     ctx->ref_len = len;
     ctx->have_variants = false;
     return LPS_OK;
@@ -209,6 +284,7 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     if (n && (!b->ref_start || !b->l_qseq || !b->n_cigar || !b->cigar_off || !b->seq_off || !b->qual_off || !b->flag || !b->mapq ||
               !b->name_rank))
         return ctx->fail(LPS_E_ARG, "null read array");
+    TRY(validate_batch(ctx, b));
     cudaSetDevice(ctx->device);
     cudaEventRecord(ctx->ev[0], ctx->stream);
     TRY(h2d(ctx, ctx->d_ref_start, b->ref_start, n));
@@ -223,23 +299,18 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     if (b->cigar16) {
         if (b->n_cigar_long && (!b->cigar_long_len || !b->cigar_long_at)) return ctx->fail(LPS_E_ARG, "cigar16 without its long-op table");
         for (uint64_t i = 0; i < b->n_cigar_long; i++)
-            if (b->cigar_long_at[i] >= b->cigar_len || (b->cigar16[b->cigar_long_at[i]] >> 4) != 0xFFFu || (b->cigar_long_len[i] >> 28))
+            if (b->cigar_long_at[i] >= b->cigar_len || (b->cigar16[b->cigar_long_at[i]] >> 4) != 0xFFFu || (b->cigar_long_len[i] >> 28) ||
+                (i && b->cigar_long_at[i] <= b->cigar_long_at[i - 1]))
                 return ctx->fail(LPS_E_ARG, "cigar_long_at / cigar_long_len do not match cigar16");
-        const size_t n8 = ((size_t)b->cigar_len + 7) / 8;
-        TRY(h2d(ctx, ctx->d_cigar16, b->cigar16, (size_t)b->cigar_len, 16));
-        LPS_CUDA(ctx, ctx->d_cigar.reserve(n8 * 8 + 64 + 1));
-        if (n8) k_widen_cigar16<<<(unsigned)((n8 + 255) / 256), 256, 0, ctx->stream>>>(n8, (const uint4 *)ctx->d_cigar16.p, (uint4 *)ctx->d_cigar.p);
-        if (b->n_cigar_long) {
-            TRY(h2d(ctx, ctx->d_cigar_long_len, b->cigar_long_len, (size_t)b->n_cigar_long));
-            TRY(h2d(ctx, ctx->d_cigar_long_at, b->cigar_long_at, (size_t)b->n_cigar_long));
-            k_patch_long_ops<<<(unsigned)((b->n_cigar_long + 255) / 256), 256, 0, ctx->stream>>>((size_t)b->n_cigar_long, ctx->d_cigar_long_at.p,
-                                                                                                  ctx->d_cigar_long_len.p, ctx->d_cigar.p);
-        }
-        ctx->stats.kernel_launches += (n8 ? 1 : 0) + (b->n_cigar_long ? 1 : 0);
-        LPS_CUDA(ctx, cudaGetLastError());
+        TRY(h2d(ctx, ctx->d_cigar16, b->cigar16, (size_t)b->cigar_len, 64));
+        TRY(h2d(ctx, ctx->d_cigar_long_len, b->cigar_long_len, (size_t)b->n_cigar_long));
+        TRY(h2d(ctx, ctx->d_cigar_long_at, b->cigar_long_at, (size_t)b->n_cigar_long));
+        ctx->batch.cigar16 = ctx->d_cigar16.p; ctx->batch.long_at = ctx->d_cigar_long_at.p; ctx->batch.long_len = ctx->d_cigar_long_len.p;
+        ctx->batch.n_long = (uint32_t)b->n_cigar_long;
     } else {
         if (b->cigar_len && !b->cigar) return ctx->fail(LPS_E_ARG, "null CIGAR stream");
         TRY(h2d(ctx, ctx->d_cigar, b->cigar, (size_t)b->cigar_len, 64));
+        TRY(narrow_cigar(ctx, ctx->d_cigar.p, b->cigar_len));
     }
     // SEQ and QUAL are 85 % of a batch but the kernels touch ~2 bytes per allele call of them.  When the caller's
     // buffers are pinned (cudaHostAlloc / cudaHostRegister) they stay on the host and the resolve phase of the kernel
@@ -275,7 +346,7 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     d.ref_start = ctx->d_ref_start.p; d.l_qseq = ctx->d_l_qseq.p; d.n_cigar = ctx->d_n_cigar.p;
     d.cigar_off = ctx->d_cigar_off.p; d.seq_off = ctx->d_seq_off.p; d.qual_off = ctx->d_qual_off.p;
     d.flag = ctx->d_flag.p; d.mapq = ctx->d_mapq.p; d.name_rank = ctx->d_name_rank.p;
-    d.cigar = ctx->d_cigar.p; d.cigar_len = b->cigar_len; d.seq4 = seq_dev; d.seq_bytes = b->seq_bytes;
+    d.cigar_len = b->cigar_len; d.seq4 = seq_dev; d.seq_bytes = b->seq_bytes;
     d.qual = qual_dev; d.qual_bytes = b->qual_bytes;
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.ms_h2d = elapsed(ctx, 0, 1);
@@ -305,8 +376,18 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     d.n_reads = b->n_reads;
     d.ref_start = b->ref_start; d.l_qseq = b->l_qseq; d.n_cigar = b->n_cigar; d.cigar_off = b->cigar_off;
     d.seq_off = b->seq_off; d.qual_off = b->qual_off; d.flag = b->flag; d.mapq = b->mapq; d.name_rank = b->name_rank;
-    d.cigar = b->cigar; d.cigar_len = b->cigar_len; d.seq4 = b->seq4; d.seq_bytes = b->seq_bytes;
+    d.cigar_len = b->cigar_len; d.seq4 = b->seq4; d.seq_bytes = b->seq_bytes;
     d.qual = b->qual; d.qual_bytes = b->qual_bytes;
+    if (b->cigar16) {
+        // the 16-bit stream is used where it lies: the bulk copies of k_call_alleles need a 16-byte aligned base
+        if (((uintptr_t)b->cigar16 & 15u) != 0) return ctx->fail(LPS_E_ARG, "a device-resident cigar16 stream must be 16-byte aligned");
+        if (b->n_cigar_long && (!b->cigar_long_len || !b->cigar_long_at)) return ctx->fail(LPS_E_ARG, "cigar16 without its long-op table");
+        if (b->n_cigar_long >> 32) return ctx->fail(LPS_E_ARG, "too many escaped CIGAR ops");
+        d.cigar16 = b->cigar16; d.long_at = b->cigar_long_at; d.long_len = b->cigar_long_len; d.n_long = (uint32_t)b->n_cigar_long;
+    } else {
+        if (b->cigar_len && !b->cigar) return ctx->fail(LPS_E_ARG, "null CIGAR stream");
+        TRY(narrow_cigar(ctx, b->cigar, b->cigar_len));
+    }
     TRY(d2h(ctx, ctx->h_name_rank, b->name_rank, (size_t)b->n_reads));
     TRY(d2h(ctx, ctx->h_flag, b->flag, (size_t)b->n_reads));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -68,8 +68,13 @@ struct DevBatch {
     const uint16_t *flag = nullptr;
     const uint8_t *mapq = nullptr;
     const int32_t *name_rank = nullptr;
-    const uint32_t *cigar = nullptr;
+    // CIGAR stream as it lives in HBM: 16 bits per op, len << 4 | op (BAM's op codes); a length >= 4095 is stored as 0xFFF and its
+    // true value sits in the side table (long_at = op index in the stream, ascending; long_len)
+    const uint16_t *cigar16 = nullptr;
     uint64_t cigar_len = 0;
+    const uint64_t *long_at = nullptr;
+    const uint32_t *long_len = nullptr;
+    uint32_t n_long = 0;
     const uint8_t *seq4 = nullptr;
     uint64_t seq_bytes = 0;
     const uint8_t *qual = nullptr;
@@ -83,6 +88,9 @@ struct DevVariants {
     const uint8_t *ref0 = nullptr, *alt0 = nullptr;
     const uint16_t *ref_len = nullptr, *alt_len = nullptr;
     const uint8_t *hom = nullptr, *danger = nullptr, *filtered = nullptr;
+    // one 8-byte record per variant for the walking kernel (k_pack_vrec): x = position, y = ref0 | alt0 << 8 | flags << 16 |
+    // min(homopolymer, 255) << 24; flags: 1 strlen(REF) == 1, 2 strlen(ALT) == 1, 4 danger, 8 erased by filterSNP, 16 HP1 carries ALT
+    const uint2 *vrec = nullptr;
 };
 
 // TUMOR side of the union variant map + per-slot counter block of the somatic family (see lps.h); DEVICE pointers
@@ -146,6 +154,7 @@ struct lps_ctx {
     DevVariants var;
     DevBuf<uint8_t> d_vhp1_is_alt;
     DevBuf<int32_t> d_vps;
+    DevBuf<uint2> d_vrec;
     bool have_tag_variants = false;
     DevBuf<int8_t> d_pq_lut;
     bool have_variants = false;
@@ -157,7 +166,9 @@ struct lps_ctx {
     DevBuf<uint8_t> d_bgzf_in, d_bgzf_out, d_bgzf_status;   // lps_bgzf_inflate
     DevBuf<lps_bgzf_block> d_bgzf_blocks;
     std::vector<uint8_t> h_bgzf_status;
-    DevBuf<uint16_t> d_cigar16;                     // compact wire format of the CIGAR stream, widened into d_cigar on arrival
+    DevBuf<uint16_t> d_cigar16;                     // the CIGAR stream in 16 bits per op (what the kernels read)
+    DevBuf<unsigned int> d_n_long;                  // escaped ops found while narrowing a uint32 stream on the device
+    DevBuf<uint64_t> d_long_keys;                   // ... (op index << 28 | length), sorted into the side table
     DevBuf<uint32_t> d_cigar_long_len;
     DevBuf<uint64_t> d_cigar_long_at;
     DevBuf<uint64_t> d_cigar_off, d_seq_off, d_qual_off;
@@ -179,8 +190,9 @@ struct lps_ctx {
     DevBuf<uint8_t> d_status;
     DevBuf<uint32_t> d_clip_keys, d_clip_keys_sorted, d_clip_unique, d_clip_counts;
     DevBuf<uint2> d_clip_meta;
-    DevBuf<int32_t> d_first_var, d_abort_of_read;
-    DevBuf<uint32_t> d_long_list, d_long_count;
+    DevBuf<int32_t> d_abort_of_read;
+    DevBuf<uint4> d_work;                           // read descriptors of k_prep_reads (3 x uint4 each), four segments
+    DevBuf<uint32_t> d_seg_count;
     DevBuf<unsigned long long> d_dbg_times;
     int sm_count = 148;
     DevBuf<int32_t> d_num_runs;
@@ -284,6 +296,7 @@ struct lps_ctx {
 
 // kernels (k_*.cu)
 int lps_launch_annotate(lps_ctx *ctx);
+int lps_prepare_call_alleles(lps_ctx *ctx);   // per-device function attributes of k_call_alleles (called by lps_ctx_create)
 int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t = nullptr, int want_calls = 0,
                             int mode = -1 /* LPS_MODE_*; -1: PHASE when t is null, GERMLINE otherwise */);
 int lps_launch_window_diff(lps_ctx *ctx, int have_reference);

@@ -122,6 +122,8 @@ const uint8_t *InflatedRegion::next(uint32_t *block_size, bool *error) {
         if (rec_tid != tid || (hts_pos_t)pos >= end) break;
         at += 4ull + bs;
         const uint32_t l_name = p[8], n_cig = (uint32_t)p[12] | (uint32_t)p[13] << 8, flag = (uint32_t)p[14] | (uint32_t)p[15] << 8;
+        // a corrupt record must not send the CIGAR walk below (or the packers behind it) past the record: name and CIGAR lie inside it
+        if (32ull + l_name + 4ull * n_cig > bs) { *error = true; done = true; return nullptr; }
         int64_t rlen = 1;                                               // bam_endpos (sam.c)
         if (!(flag & BAM_FUNMAP) && n_cig > 0) {
             rlen = 0;

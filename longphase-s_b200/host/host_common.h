@@ -94,6 +94,7 @@ struct PackedContig {
         auto le16 = [](const uint8_t *q) { return (uint32_t)q[0] | (uint32_t)q[1] << 8; };
         const uint32_t l_name = p[8], n_cig = le16(p + 12), fl = le16(p + 14), l_seq = le32(p + 16);
         if (32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > block_size) return false;
+        if (l_name == 0 || p[32 + l_name - 1] != '\0') return false;      // name not NUL-terminated inside l_read_name: htslib repairs it, we decline
         const uint8_t *name = p + 32, *cg = name + l_name, *sq = cg + 4 * n_cig, *ql = sq + (l_seq + 1) / 2;
         if (n_cig == 2 && (le32(cg) & 15u) == 4 /* S */ && (le32(cg) >> 4) == l_seq && (le32(cg + 4) & 15u) == 3 /* N */) return false;
         ref_start.push_back((int32_t)le32(p + 4));
@@ -108,7 +109,7 @@ struct PackedContig {
         qual_off.push_back(qual.size());
         qual.insert(qual.end(), ql, ql + l_seq);
         name_off.push_back(names.size());
-        names.append((const char *)name);
+        names.append((const char *)name, strnlen((const char *)name, l_name - 1));   // never reads beyond the name field
         names.push_back('\0');
         return true;
     }

@@ -531,6 +531,58 @@ int readers_per_contig(const lpsh_phase &job) {
     return spare >= 4 ? spare : 1;
 }
 
+// Weight of every contig = mapped reads the index of the first BAM counts for it (hts_idx_get_stat: metadata of the .bai / .csi,
+// nothing is decoded); without usable statistics, the position of its last variant.  order: contigs by descending weight.
+void plan_contigs(const lpsh_phase &job, std::vector<int> &order, std::vector<double> &w) {
+    const int n = (int)job.chr_names.size();
+    w.assign((size_t)n, 0.0);
+    for (int i = 0; i < n; i++) { const int lv = last_variant(job, job.chr_names[(size_t)i]); w[(size_t)i] = lv > 0 ? (double)lv : 0.0; }
+    if (!job.opt.bams.empty()) {
+        if (samFile *in = hts_open(job.opt.bams[0].c_str(), "r")) {
+            hts_set_fai_filename(in, job.opt.fasta.c_str());
+            bam_hdr_t *hdr = sam_hdr_read(in);
+            hts_idx_t *idx = hdr ? sam_index_load(in, job.opt.bams[0].c_str()) : NULL;
+            if (idx) {
+                std::vector<double> reads((size_t)n, 0.0);
+                bool all = true;
+                for (int i = 0; i < n && all; i++) {
+                    if (w[(size_t)i] == 0.0) continue;
+                    const int tid = bam_name2id(hdr, job.chr_names[(size_t)i].c_str());
+                    uint64_t mapped = 0, unmapped = 0;
+                    if (tid < 0 || hts_idx_get_stat(idx, tid, &mapped, &unmapped) != 0) all = false;
+                    else reads[(size_t)i] = (double)mapped + 1.0;
+                }
+                if (all) for (int i = 0; i < n; i++) if (w[(size_t)i] != 0.0) w[(size_t)i] = reads[(size_t)i];
+                hts_idx_destroy(idx);
+            }
+            if (hdr) bam_hdr_destroy(hdr);
+            sam_close(in);
+        }
+    }
+    order.resize((size_t)n);
+    for (int i = 0; i < n; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[(size_t)a] > w[(size_t)b]; });
+}
+
+// device_of: greedy longest-processing-time partition of the weights over the devices (called once the device count is known:
+// the driver starts on a background thread while the first BAM regions are decoded).  LPS_PLACEMENT=roundrobin deals the
+// contigs out in turn instead.
+void assign_devices(const std::vector<int> &order, const std::vector<double> &w, int n_bins, std::vector<int> &device_of) {
+    const int n = (int)order.size();
+    if (n_bins < 1) n_bins = 1;
+    device_of.assign((size_t)n, 0);
+    const char *pl = getenv("LPS_PLACEMENT");
+    if (pl && !strcmp(pl, "roundrobin")) { for (int k = 0; k < n; k++) device_of[(size_t)order[(size_t)k]] = k % n_bins; return; }
+    std::vector<double> load((size_t)n_bins, 0.0);
+    for (int k = 0; k < n; k++) {
+        const int i = order[(size_t)k];
+        int best = 0;
+        for (int b = 1; b < n_bins; b++) if (load[(size_t)b] < load[(size_t)best]) best = b;
+        device_of[(size_t)i] = best;
+        load[(size_t)best] += w[(size_t)i];
+    }
+}
+
 lps_phase_params device_params(const PhaseOptions &o, bool have_reference) {
     lps_phase_params p;
     memset(&p, 0, sizeof(p));
@@ -643,8 +695,17 @@ int lpsh_phase_run(lpsh_phase *h) {
     if (!(pool.pool = hts_tpool_init(o.threads))) fprintf(stderr, "Error creating thread pool\n");
     std::time_t t0 = time(NULL);
     int failed = 0;
-#pragma omp parallel for schedule(dynamic) num_threads(o.threads)
-    for (int i = 0; i < n; i++) {
+    // every contig gets its slot in the shared maps BEFORE the threads start: operator[] on a std::map inserts, and concurrent
+    // inserts from the contig threads would race on the tree (lpsh_phase_set_result, pack_phase_contig)
+    for (const std::string &chr : h->chr_names) { h->phased[chr]; h->variants[chr]; h->reference[chr]; }
+    // Placement: contigs are handed out heaviest first (so the largest one never starts last), and each is pinned to
+    // the device a greedy LPT partition of the read counts gives it; the counts come from the BAM index, no record is read.
+    std::vector<int> order, device_of((size_t)n, 0);
+    std::vector<double> weight;
+    plan_contigs(*h, order, weight);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(o.threads)
+    for (int oi = 0; oi < n; oi++) {
+        const int i = order[(size_t)oi];
         const std::string &chr = h->chr_names[(size_t)i];
         std::time_t c0 = time(NULL);
         if (last_variant(*h, chr) == -1) continue;
@@ -655,7 +716,7 @@ int lpsh_phase_run(lpsh_phase *h) {
         }
         lpsh::PackedContig *pc = h->packed[(size_t)i];
 #pragma omp critical(lpsh_device_count)
-        if (n_dev < 0) n_dev = lpsh::device_count();
+        if (n_dev < 0) { n_dev = lpsh::device_count(); assign_devices(order, weight, n_dev, device_of); }
         if (n_dev < 1) {
 #pragma omp critical
             { lpsh::fail("no usable CUDA device (there is no CPU fallback)"); failed = 1; }
@@ -668,7 +729,7 @@ int lpsh_phase_run(lpsh_phase *h) {
             pc->view(&v);
             const lps_phase_params p = device_params(o, !pc->ref.empty());
             lps_phase_result r;
-            int rc = lps_ctx_create(omp_get_thread_num() % n_dev, &ctx);
+            int rc = lps_ctx_create(device_of[(size_t)i], &ctx);
             if (rc == 0) rc = lps_contig_set_reference(ctx, v.ref, v.ref_len);
             if (rc == 0) rc = lps_contig_set_variants(ctx, &v.variants, o.ont);
             if (rc == 0) rc = lps_batch_submit(ctx, &v.batch);

@@ -604,6 +604,7 @@ int lpsh_som_call(lpsh_som *h) {
     std::cerr << "calling somatic variants ... ";
     int failed = 0;
     h->n_somatic = 0;
+    for (const std::string &chr : h->chr_names) h->variants[chr];   // operator[] inserts: give every contig its slot before the threads start
 #pragma omp parallel for schedule(dynamic) num_threads(o.threads)
     for (int c = 0; c < (int)nc; c++) {
         const std::string &chr = h->chr_names[(size_t)c];

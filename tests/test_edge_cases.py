@@ -154,3 +154,84 @@ def test_gpu_empty_and_degenerate_batches():
                                                  R(REF, 55, "10M", "c"), R(REF, 56, "10M", "d")])
     parity.check_phase(c1, p, ctx=ctx)
     ctx.close()
+
+
+# ---- CIGAR ops of 4095 bases and more (escaped in the 16-bit stream the kernels read) and reads of several super-chunks ----
+def long_op_contig(seed=7):
+    rng = np.random.default_rng(seed)
+    L = 60_000
+    ref = "".join(rng.choice(list("ACGT"), L))
+    # homopolymer runs so that the D-op rule has something to look at
+    ref = list(ref)
+    for s in range(500, L - 20, 997):
+        ref[s:s + 5] = ref[s] * 5
+    ref = "".join(ref)
+    vs = []
+    for p in range(200, L - 200, 173):
+        alt = "ACGT"[("ACGT".index(ref[p]) + 1 + (p % 3)) % 4]
+        if p % 11 == 0:
+            vs.append((p, ref[p], ref[p] + "GG", p % 2))                  # insertion
+        elif p % 13 == 0:
+            vs.append((p, ref[p:p + 3], ref[p], p % 2))                   # deletion
+        else:
+            vs.append((p, ref[p], alt, p % 2))
+    R = handmade.read_from_ref
+    reads = [
+        R(ref, 10, "4094M", "l00"),                       # largest length that fits the 12-bit field
+        R(ref, 11, "4095M", "l01"),                       # smallest escaped length
+        R(ref, 12, "4096M3I5000M2D3000M", "l02"),
+        R(ref, 13, "100M5000N3000M", "l03"),              # escaped N op: variants under it are skipped
+        R(ref, 14, "7S4200=1X800=9S", "l04"),             # = / X ops, counted clips around an escaped op
+        R(ref, 15, "300M6000D2000M", "l05"),              # escaped D op over many variants (D-op rule on the first only)
+        R(ref, 16, "5000M", "l06", edits={k: "A" for k in range(100, 4900, 37)}),
+        R(ref, 20000, "4500M1I4500M", "l07"),
+        R(ref, 30000, "12000M", "l08"),
+    ]
+    # reads of > 1536 and > 3072 ops (several super-chunks), with an escaped op in the middle of a later super-chunk
+    def chopped(pos, n_units, name, long_at=None):
+        cig = []
+        for u in range(n_units):
+            if long_at is not None and u == long_at:
+                cig.append("4300M")
+            cig.append("5M1I" if u % 3 else "4M1D")
+        return R(ref, pos, "".join(cig) + "20M", name)
+    reads += [chopped(100, 900, "m00"), chopped(101, 1700, "m01", long_at=1200), chopped(5000, 2500, "m02", long_at=50),
+              chopped(9000, 800, "m03"), chopped(9001, 770, "m04")]
+    # short reads in between shift the CIGAR offsets of their neighbours through every alignment (mod 8 ops)
+    for k in range(23):
+        reads.append(R(ref, 50 + 97 * k, "%dM" % (300 + k) if k % 4 else "%dM1I%dM" % (100 + k, 150), "s%02d" % k))
+    reads.sort(key=lambda r: r["pos"])
+    return handmade.ManualContig(ref, vs, reads)
+
+
+def test_oracle_matches_reference_on_long_ops():
+    po = pytest.importorskip("oracle.pyoracle")
+    if not po.tap_available():
+        pytest.skip("reference tap not built")
+    c = long_op_contig()
+    assert ((c.cigar >> 4) >= 4095).sum() >= 10 and c.n_cigar.max() > 3072
+    p = ffi.default_phase_params(True)
+    ref = po.ReferencePhase(c, p, stop_after_calls=True)
+    a = po.OraclePhase(c, p, apply_filter=False, stages=1)
+    cmp.assert_same_calls(cmp.calls_by_read(a.call_off, a.calls, c.var_pos), cmp.tap_stage_by_read(ref.stage_a), "long ops A")
+    for k in ("clip_pos", "clip_front", "clip_back"):
+        assert np.array_equal(getattr(a, k), getattr(ref, k)), k
+    assert len(a.calls) > 500
+
+
+@pytest.mark.gpu
+def test_gpu_long_ops_match_oracle():
+    """Escaped lengths, multi-super-chunk reads and every CIGAR offset alignment through the bulk-copy pipeline of k_call_alleles,
+    in the phase dialect (uint32 and 16-bit submission) and the germline tag dialect."""
+    po = pytest.importorskip("oracle.pyoracle")
+    from .test_tag import check_gpu_tag
+    c = long_op_contig()
+    for is_ont in (True, False):
+        parity.check_phase(c, ffi.default_phase_params(is_ont))
+    p = ffi.default_phase_params(True)
+    orc = po.OraclePhase(c, p)
+    ps = np.where(orc.ps != 0, orc.ps, 1 + (np.arange(c.n_var) // 40) * 1000).astype(np.int32)    # every variant in some phase set
+    hap = np.where(orc.ps != 0, orc.hap_ref == 1, (np.arange(c.n_var) % 2) == 1)
+    ctx = host.Context(0)
+    check_gpu_tag(c.phased(ps, hap), ffi.default_tag_params(), ctx)
+    ctx.close()

@@ -14,6 +14,7 @@ from .test_somatic import MODES, check_gpu_somatic
 synth = importlib.import_module("longphase_s_b200.synth")
 ffi = importlib.import_module("longphase_s_b200._ffi")
 host = importlib.import_module("longphase_s_b200.host")
+workloads = importlib.import_module("longphase_s_b200.workloads")
 
 
 @pytest.mark.gpu
@@ -26,6 +27,35 @@ def test_gpu_bench_shape_contig_matches_oracle():
     orc = po.OraclePhase(c, p)
     ctx = host.Context(0)
     check_gpu_tag(c.phased(orc.ps, orc.hap_ref == 1), ffi.default_tag_params(), ctx)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_timed_64mb_contig_matches_oracle_at_every_stage():
+    """The contig bench.py times first (workloads.weak_seed(0, 0), 64 Mb, 30x, ~99 k reads, 1.8 M calls): every stage of the phase path
+    and the germline tagging pass against the oracle, at the timed size; its digest must be the committed one bench.py gates on."""
+    po = pytest.importorskip("oracle.pyoracle")
+    c = synth.Contig(**workloads.phase_kwargs(workloads.weak_seed(0, 0)))
+    p = ffi.default_phase_params(True)
+    info = parity.check_phase(c, p)
+    assert info["reads"] > 90_000 and info["calls"] > 1_500_000
+    orc = po.OraclePhase(c, p)
+    want = workloads.load_digests().get(workloads.key_of(workloads.phase_kwargs(workloads.weak_seed(0, 0))))
+    assert want is not None and want["digest"] == workloads.oracle_phase_digest(orc, c.n_reads), "committed bench digest is stale"
+    ctx = host.Context(0)
+    check_gpu_tag(c.phased(orc.ps, orc.hap_ref == 1), ffi.default_tag_params(), ctx)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_timed_c4_shard_matches_oracle():
+    """The C4 shard bench.py times (tumor 50x / normal 25x pair over one 32 Mb contig): the three somatic passes against the oracle."""
+    un, ut = workloads.c4_pair(synth, 32.0)
+    tp = ffi.LpsTagParams(mapping_quality=20, mapq_filter=0, tag_supplementary=1, have_reference=1, percentage_threshold=0.6)
+    ctx = host.Context(0)
+    for mode in MODES:
+        res = check_gpu_somatic(un if mode == "extract_normal" else ut, tp, mode, ctx)
+        assert res["n_tum"] > 1000
     ctx.close()
 
 
@@ -49,7 +79,7 @@ def test_gpu_dense_stress_contig_matches_oracle():
 def test_gpu_full_size_properties():
     import ctypes as C
     import torch
-    c = synth.Contig(seed=100, contig_len=64_000_000, indel_frac=0.1, depth=30.0, mean_len=20000.0)     # the bench's first contig
+    c = synth.Contig(**workloads.phase_kwargs(workloads.weak_seed(0, 0)))     # the bench's first contig
     p = ffi.default_phase_params(True)
     ctx = host.Context(0)
     ctx.set_reference(c.ref)
