@@ -390,8 +390,10 @@ def main():
     ms_step = max_over_ranks(dev_ms)
     launches = int(sum(b_["kernel_launches"] - a_["kernel_launches"] for a_, b_ in zip(s0, s1)))
     stage_keys = ("ms_call_alleles", "ms_build_edges", "ms_read_correction", "ms_wall_call_alleles", "ms_wall_build_edges", "ms_wall_solve",
-                  "ms_host_filters", "ms_host_sweep", "ms_kernel_fold_edges")
+                  "ms_host_filters", "ms_host_sweep", "ms_kernel_fold_edges", "ms_sweep")
     stage = {k[3:]: float(np.mean([st[k] for st in s1])) for k in stage_keys}
+    stage["sweep_fallbacks"] = int(sum(b_["sweep_fallbacks"] - a_["sweep_fallbacks"] for a_, b_ in zip(s0, s1)))
+    stage["slow_path_contigs"] = int(sum(b_["slow_path_contigs"] - a_["slow_path_contigs"] for a_, b_ in zip(s0, s1)))
 
     # ---- the dominant kernel timed alone (one context, nothing else on the GPU): roofline ----
     ctx0, contig0 = ctxs[0], contigs[0]

@@ -471,6 +471,9 @@ typedef struct {
     uint64_t d2h_bytes;
     int32_t sweep_simd;           /* code path of the last host sweep: 0 scalar, 1 AVX2, 2 AVX-512   */
     float ms_kernel_bgzf;         /* k_bgzf_inflate of the last lps_bgzf_inflate[_device] call       */
+    float ms_sweep;               /* device time of the edgeConnectResult kernels (lps_phase_contig)  */
+    uint32_t sweep_fallbacks;     /* contigs whose segmented sweep did not verify and was redone sequentially (on the device) */
+    uint32_t slow_path_contigs;   /* contigs redone stage by stage because host code was needed between the kernels          */
 } lps_stats;
 int lps_get_stats(lps_ctx *ctx, lps_stats *out);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on), so a

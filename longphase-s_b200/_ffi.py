@@ -177,7 +177,8 @@ class LpsStats(C.Structure):
                 ("ms_kernel_fold_edges", C.c_float), ("ms_kernel_window_diff", C.c_float), ("ms_wall_call_alleles", C.c_float),
                 ("ms_wall_build_edges", C.c_float), ("ms_wall_solve", C.c_float), ("ms_host_filters", C.c_float),
                 ("ms_host_sweep", C.c_float), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sweep_simd", C.c_int32), ("ms_kernel_bgzf", C.c_float)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sweep_simd", C.c_int32), ("ms_kernel_bgzf", C.c_float),
+                ("ms_sweep", C.c_float), ("sweep_fallbacks", C.c_uint32), ("slow_path_contigs", C.c_uint32)]
 
 
 # every symbol include/lps.h declares: name -> (restype, argtypes)

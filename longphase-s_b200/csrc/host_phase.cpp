@@ -17,8 +17,9 @@
 
 // --------------------------------------------------------------------------------------------
 // overlap filter.  Only read names that own more than one alignment in the batch can be affected, so the
-// batch is indexed once at submit time (lps_host_index_names) and the state machine runs on those groups
-// alone, on (first called position, last called position, #calls) of just their alignments.
+// batch is indexed once at submit time (lps_host_index_names); the state machine itself runs on the device, one
+// thread per such name (k_overlap_filter, k_edges.cu), on (first called position, last called position, #calls)
+// of just their alignments.
 // --------------------------------------------------------------------------------------------
 void lps_host_index_names(lps_ctx *ctx) {
     const std::vector<int32_t> &rank = ctx->h_name_rank;
@@ -41,45 +42,6 @@ void lps_host_index_names(lps_ctx *ctx) {
     for (const auto &g : groups) {
         ctx->h_multi_members.insert(ctx->h_multi_members.end(), g.begin(), g.end());
         ctx->h_multi_group_off.push_back((int32_t)ctx->h_multi_members.size());
-    }
-}
-
-// first_pos / last_pos / ncalls are indexed like ctx->h_multi_members; returns the batch indices of deleted alignments
-void lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
-                             const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls, std::vector<int32_t> &dead) {
-    dead.clear();
-    std::vector<int32_t> kept;   // readIdxVec[name] (indices into the member arrays)
-    const size_t ngroups = ctx->h_multi_group_off.size() - 1;
-    for (size_t g = 0; g < ngroups; g++) {
-        const int b0 = ctx->h_multi_group_off[g], b1 = ctx->h_multi_group_off[g + 1];
-        kept.clear();
-        // alignRange[name]: inserted as {0,0} before the find(), so .first is always 0 (:712-716)
-        int range_end = 0;
-        for (int m = b0; m < b1; m++) {
-            if (!ncalls[(size_t)m]) continue;   // alignments without calls never reach addEdge
-            const int first = first_pos[(size_t)m], last = last_pos[(size_t)m];
-            bool drop_cur = false;
-            while (0 <= first && first <= range_end) {
-                if (last < range_end) { drop_cur = true; break; }
-                if (kept.empty()) break;
-                const int prev = kept.back();
-                const int prev_start = first_pos[(size_t)prev], prev_end = last_pos[(size_t)prev];
-                const double ov_start = std::max(prev_start, first), ov_end = std::min(prev_end, last);
-                if (ov_start > ov_end) break;
-                const double ov_len = ov_end - ov_start + 1;
-                const double span = (double)std::max(prev_end, last) - (double)std::min(prev_start, first) + 1;
-                if (ov_len / span >= p->overlap_threshold) {
-                    const int len_prev = prev_end - prev_start + 1, len_cur = last - first + 1;
-                    if (len_cur <= len_prev) { drop_cur = true; break; }
-                    dead.push_back(ctx->h_multi_members[(size_t)prev]);
-                    kept.pop_back();
-                    range_end = kept.empty() ? first : last_pos[(size_t)kept.back()];
-                } else break;
-            }
-            range_end = last;
-            if (drop_cur) dead.push_back(ctx->h_multi_members[(size_t)m]);
-            else kept.push_back(m);
-        }
     }
 }
 

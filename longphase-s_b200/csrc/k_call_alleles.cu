@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "lps_ctx.cuh"
+#include "lps_async.cuh"
 
 namespace {
 
@@ -42,6 +43,15 @@ namespace {
 #endif
 #ifndef LPS_CAND_CAP
 #define LPS_CAND_CAP 192
+#endif
+#ifndef LPS_PREFETCH_SQ
+#define LPS_PREFETCH_SQ 1      // L2 prefetch of the SEQ / QUAL sectors when a SNP candidate is found
+#endif
+#ifndef LPS_PREFETCH_VREC
+#define LPS_PREFETCH_VREC 1    // variant records of the first phase-2 round requested before phase 1
+#endif
+#ifndef LPS_PAIR_WALK
+#define LPS_PAIR_WALK 1        // phase-2 walk over pairs of ops with the pair table (0: op by op)
 #endif
 constexpr int WARPS_PER_CTA = LPS_WARPS;      // one CTA per SM; its dynamic shared memory (~9.2 KB per warp) pins the L1 / shared split
 constexpr int SC = LPS_SC_OPS;                // CIGAR ops per super-chunk (one bulk copy, one phase-2 pass); multiple of 512
@@ -115,37 +125,6 @@ constexpr unsigned VF_REF1 = 1u << 16, VF_ALT1 = 1u << 17, VF_DANGER = 1u << 18,
 
 // per-op advance bits, two bits per op code: bit0 = consumes the reference (M D N = X), bit1 = consumes the query (M I S = X)
 constexpr uint32_t ADV_LUT = (3u << 0) | (2u << 2) | (1u << 4) | (1u << 6) | (2u << 8) | (3u << 14) | (3u << 16);
-
-// ---- mbarrier / bulk copy / cp.async (PTX; SASS: SYNCS, UBLKCP, LDGSTS) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LPS_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LPS_DONE;\n\t"
-        "bra LPS_WAIT;\n\t"
-        "LPS_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct alignas(16) WarpScratch {
     uint16_t cig[2][SC_BUF];          // destinations of the bulk copies
@@ -511,6 +490,18 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     const int n_sc = ncig > 0 ? (tot_a + SC - 1) / SC : 0;
     const uint64_t gop0 = D.cigar_off - (uint64_t)mis;    // global op index of aligned position 0
 
+    const uint8_t *__restrict__ seq = a.b.seq4 + D.seq_off;
+    const uint8_t *__restrict__ qual = a.b.qual + D.qual_off;
+    // resolve gathers one SEQ nibble (phase: and one QUAL byte) per SNP candidate from anywhere in the read: ask L2 for the sectors
+    // as soon as the query index is known, the rest of phase 2 runs while they travel
+    auto prefetch_base = [&](int qi) {
+#if LPS_PREFETCH_SQ
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(seq + (qi >> 1)));
+        if (!TAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(qual + qi));
+#else
+        (void)qi;
+#endif
+    };
     int ref_pos = ref_start, qpos = 0;
     int ncand = 0;
     bool aborted = false;
@@ -519,6 +510,11 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     if (n_sc == 0 && next.r != 0xFFFFFFFFu && next.ncig > 0) issue_sc(a, S, next, 0, pp.buf, lane);   // keeps "the next read's copy is under way"
     for (int s = 0; s < n_sc; s++) {
         const int buf = pp.buf;
+        // the variant records the first phase-2 round of this super-chunk looks at: requested now, used after phase 1
+        uint2 vr_first = make_uint2((unsigned)INT_MAX, 0u);
+#if LPS_PREFETCH_VREC
+        if (cur + lane < nv) vr_first = vrec[cur + lane];
+#endif
         // request what this warp decodes next, then wait for what it decodes now
         if (s + 1 < n_sc) issue_sc(a, S, D, s + 1, buf ^ 1, lane);
         else if (next.r != 0xFFFFFFFFu && next.ncig > 0) issue_sc(a, S, next, 0, buf ^ 1, lane);
@@ -601,18 +597,27 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
             }
             *reinterpret_cast<int4 *>(&S.grp[it * 64 + lane * 2]) =
                 make_int4(ref_pos + er, qpos + eq, ref_pos + er + (int)r0, qpos + eq + (int)q0);
-            // ---- clips (S/H longer than 5) and unsupported ops: op codes with bit 2 or 3 set (S H P = X and 9..15) ----
+            // ---- clips (S/H longer than 5) and unsupported ops: op codes with bit 2 or 3 set (S H P = X and 9..15).  Only the pairs
+            // that hold such a code are looked at; the reference position of a clip is summed up on demand (clips are rare). ----
             if (__any_sync(FULL, ((acc | (acc >> 16)) & 0xCu) != 0)) {
-                int rr = ref_pos + er;
-#pragma unroll 1
-                for (int j = 0; j < 16; j++) {
-                    const unsigned x = a0 < cnt16 ? (unsigned)cg[a0 + j] : PAD16;
-                    const unsigned op = x & 15u;
-                    const int g = a_base + a0 + j - mis;  // CIGAR index inside the read (pads are zero-length insertions: no effect)
-                    if (op >= 4u && op != 7u && op != 8u) {
-                        const int len = (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + j));
-                        if (!TAG && (op == 4u || op == 5u) && len > 5) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned x2 = w[j];
+                    if ((x2 & 0x000C000Cu) == 0u) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const unsigned x = (x2 >> (16 * h)) & 0xFFFFu;
+                        const unsigned op = x & 15u;
+                        if (op < 4u || op == 7u || op == 8u) continue;
+                        const int jj = 2 * j + h;
+                        const int g = a_base + a0 + jj - mis;   // CIGAR index inside the read
+                        if (!TAG && (op == 4u || op == 5u) && (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + jj)) > 5) {
                             // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
+                            int rr = ref_pos + er;
+                            for (int t = 0; t < jj; t++) {
+                                const unsigned y = cg[a0 + t];
+                                if ((0x18Du >> (y & 15u)) & 1u) rr += (int)op_len(a.b, y, gop0 + (uint64_t)(a_base + a0 + t));
+                            }
                             const unsigned long long slot = atomicAdd(&a.counters->clips.v, 1ull);
                             if (slot < a.clip_cap) {
                                 a.clip_keys[slot] = ((uint32_t)rr << 1) | (g == 0 ? 0u : 1u);
@@ -620,7 +625,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                             }
                         }
                         if (op > 8u) bad_op = min(bad_op, g);
-                    } else if ((0x18Du >> op) & 1u) rr += (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + j));
+                    }
                 }
             }
             ref_pos += rtot; qpos += qtot;
@@ -629,10 +634,12 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
         __syncwarp();
 
         // ================= phase 2: every pending variant below ref_pos, one per lane =================
+        bool first_round = true;
         while (true) {
             const int vi = cur + lane;
-            uint2 vr = make_uint2((unsigned)INT_MAX, 0u);
-            if (vi < nv) vr = vrec[vi];
+            uint2 vr = vr_first;
+            if (!LPS_PREFETCH_VREC || !first_round) { vr = make_uint2((unsigned)INT_MAX, 0u); if (vi < nv) vr = vrec[vi]; }
+            first_round = false;
             const int vp = (int)vr.x;
             const bool mine = vp < ref_pos;
             const unsigned mmask = __ballot_sync(FULL, mine);
@@ -651,21 +658,45 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                 }
                 const int2 gs = S.grp[g];
                 int wr = gs.x, wq = gs.y;
-                // covering op: the last op of the group that starts at or before vp (one 128-bit load, walked in registers)
+                // covering op: the last op of the group that starts at or before vp.  One 128-bit load; the four PAIRS of ops are summed
+                // with the same table + dot products as phase 1, the pair is picked by counting starts <= vp, then one of its two ops
                 const uint4 g8 = *reinterpret_cast<const uint4 *>(cg + g * 8);
                 const unsigned gw[4] = {g8.x, g8.y, g8.z, g8.w};
-                const bool gesc = ((((g8.x | g8.y | g8.z | g8.w) >> 4) & 0xFFFu) == 0xFFFu) || (((g8.x | g8.y | g8.z | g8.w) >> 20) == 0xFFFu);
+                const unsigned gor = g8.x | g8.y | g8.z | g8.w;
+                const bool gesc = (((gor >> 4) & 0xFFFu) == 0xFFFu) || ((gor >> 20) == 0xFFFu);
                 unsigned c = PAD16;
                 int o_len = 0, jsel = 0;
+                if (LPS_PAIR_WALK && !gesc) {
+                    unsigned fl[4], pr[4], pq[4];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const unsigned cc = (gw[j >> 1] >> ((j & 1) << 4)) & 0xFFFFu;
-                    int len = (int)(cc >> 4);
-                    if (gesc) len = (int)op_len(a.b, cc, gop0 + (uint64_t)(a_base + g * 8 + j));
-                    if (wr <= vp) { c = cc; o_r = wr; o_q = wq; jsel = j; o_len = len; }
-                    const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
-                    wr += (int)(t & 1u) * len;
-                    wq += (int)((t >> 1) & 1u) * len;
+                    for (int k = 0; k < 4; k++) {
+                        fl[k] = s_pair[(gw[k] & 0xFu) | ((gw[k] >> 12) & 0xF0u)];
+                        const unsigned lens = (gw[k] >> 4) & 0x0FFF0FFFu;
+                        pr[k] = __dp2a_lo(lens, fl[k], 0u);
+                        pq[k] = __dp2a_hi(lens, fl[k], 0u);
+                    }
+                    const int s1 = wr + (int)pr[0], s2 = s1 + (int)pr[1], s3 = s2 + (int)pr[2];
+                    const int q1 = wq + (int)pq[0], q2 = q1 + (int)pq[1], q3 = q2 + (int)pq[2];
+                    const int k = (s1 <= vp) + (s2 <= vp) + (s3 <= vp);          // starts never decrease: the last pair that starts at or before vp
+                    const unsigned wsel = k == 0 ? gw[0] : k == 1 ? gw[1] : k == 2 ? gw[2] : gw[3];
+                    const unsigned fsel = k == 0 ? fl[0] : k == 1 ? fl[1] : k == 2 ? fl[2] : fl[3];
+                    const int ps = k == 0 ? wr : k == 1 ? s1 : k == 2 ? s2 : s3, qs_ = k == 0 ? wq : k == 1 ? q1 : k == 2 ? q2 : q3;
+                    const int lenA = (int)((wsel >> 4) & 0xFFFu), lenB = (int)(wsel >> 20);
+                    const int sB = ps + (int)(fsel & 1u) * lenA, qB = qs_ + (int)((fsel >> 16) & 1u) * lenA;
+                    const bool second = sB <= vp;
+                    c = second ? (wsel >> 16) : (wsel & 0xFFFFu);
+                    o_r = second ? sB : ps; o_q = second ? qB : qs_; o_len = second ? lenB : lenA;
+                    jsel = 2 * k + (second ? 1 : 0);
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < 8; j++) {
+                        const unsigned cc = (unsigned)cg[g * 8 + j];
+                        const int len = (int)op_len(a.b, cc, gop0 + (uint64_t)(a_base + g * 8 + j));
+                        if (wr <= vp) { c = cc; o_r = wr; o_q = wq; jsel = j; o_len = len; }
+                        const unsigned t = ADV_LUT >> ((cc << 1) & 30u);
+                        wr += (int)(t & 1u) * len;
+                        wq += (int)((t >> 1) & 1u) * len;
+                    }
                 }
                 const int lidx = g * 8 + jsel;            // position inside the super-chunk; the buffer also holds position lidx + 1
                 const int o_op = (int)(c & 15u);
@@ -685,6 +716,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                             }
                             cand_var = vi;
                             c4 = make_uint4((unsigned)vi, (unsigned)(o_q + off), (unsigned)opi, (unsigned)off | (fl << 28));
+                            prefetch_base(o_q + off);
                         }
                     } else if (o_op == 2) {
                         cand_var = vi;
@@ -697,7 +729,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                         if (rl1 && al1) {
                             // the reference reads seq[query_pos+offset] without a bounds check; past l_qseq that is
                             // memory of the BAM record (undefined) — such a hit is dropped here
-                            if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                            if (o_q + off < lq) { cand_var = vi; cand_x = (uint32_t)(o_q + off); prefetch_base(o_q + off); }
                         } else if (rl1 != al1) {
                             if (opi + 1 < ncig) {
                                 const unsigned want = rl1 ? 1u : 2u;
@@ -717,7 +749,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                     const int off = vp - o_r;
                     if (o_q + off + 1 > lq) ab = true;                                              // :1453-1455
                     else {
-                        if (rl1 && al1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); }
+                        if (rl1 && al1) { cand_var = vi; cand_x = (uint32_t)(o_q + off); prefetch_base(o_q + off); }
                         else if (rl1 != al1) {
                             if (opi + 1 < ncig) {                                                   // :1470, :1495
                                 const unsigned want = rl1 ? 1u : 2u;                                // I after an insertion anchor, D after a deletion anchor
@@ -738,7 +770,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                         // processDeletionOperation (HaplotagProcess.cpp:492-501): first variant of the D op only;
                         // judgeDeletionHap (HaplotagStrategy.cpp:147-209): homopolymer >= 3, SNP compares the next aligned base
                         if (rl1 && al1) {
-                            if (o_q < lq) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                            if (o_q < lq) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; prefetch_base(o_q); }
                         } else if (!rl1 && al1) {
                             const bool h1alt = (vr.y & VF_HP1ALT) != 0;
                             const bool l1_is1 = h1alt ? al1 : rl1, l2_is1 = h1alt ? rl1 : al1;
@@ -750,7 +782,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                     } else {
                         // get_snp D branch (:1539-1607)
                         if (o_q + 1 > lq) ab = true;                                                // :1559-1561
-                        else if (rl1 && al1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; }
+                        else if (rl1 && al1) { cand_var = vi; cand_x = (1u << 30) | (uint32_t)o_q; prefetch_base(o_q); }
                         else if (!rl1 && al1) { cand_var = vi; cand_x = (2u << 30) | (1u << 2) | (1u << 1); }
                     }
                 }
@@ -814,7 +846,6 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     }
     __syncwarp();
 
-    const uint8_t *__restrict__ seq = a.b.seq4 + D.seq_off;
     if (SOM) {
         resolve_somatic<MODE>(a, r, lane, cand4, ncand, ref_start, ref_pos, qpos, lq, pc, seq, (int)(D.flags & 0xFFu) >= a.mapping_quality);
         return;
@@ -900,7 +931,6 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     }
 
     // ---- resolve candidates: gather base + quality, decide the allele, drop filterSNP variants ----
-    const uint8_t *__restrict__ qual = a.b.qual + D.qual_off;
     int nvalid = 0, ngather = 0;
     for (int c0 = 0; c0 < ncand; c0 += 32) {
         const int c = c0 + lane;
@@ -1221,7 +1251,7 @@ int lps_prepare_call_alleles(lps_ctx *ctx) {
     return LPS_OK;
 }
 
-int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls, int mode) {
+int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t, int want_calls, int mode, bool defer_clips) {
     const bool tag = t != nullptr;
     if (mode < 0) mode = tag ? LPS_MODE_GERMLINE : LPS_MODE_PHASE;
     const bool som = mode >= LPS_MODE_EXTRACT_NORMAL;
@@ -1449,12 +1479,17 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         k_clip_filter<<<(nclip + 255) / 256, 256, 0, st>>>((unsigned long long)nclip, ctx->d_clip_keys.p, ctx->d_clip_meta.p, ctx->d_abort_of_read.p);
         ctx->stats.kernel_launches++;
     }
-    ctx->h_clip_pos.clear(); ctx->h_clip_front.clear(); ctx->h_clip_back.clear();
+    // the sorted, run-length encoded keys travel to pinned memory asynchronously; lps_finish_clips turns them into the map
+    ctx->n_clip_events = nclip;
+    ctx->clips_pending = true;
     if (nclip > 0) {
         LPS_CUDA(ctx, ctx->d_clip_keys_sorted.reserve((size_t)nclip));
         LPS_CUDA(ctx, ctx->d_clip_unique.reserve((size_t)nclip));
         LPS_CUDA(ctx, ctx->d_clip_counts.reserve((size_t)nclip));
         LPS_CUDA(ctx, ctx->d_num_runs.reserve(1));
+        LPS_CUDA(ctx, ctx->p_clip_unique.reserve((size_t)nclip));
+        LPS_CUDA(ctx, ctx->p_clip_counts.reserve((size_t)nclip));
+        LPS_CUDA(ctx, ctx->p_num_runs.reserve(1));
         size_t b1 = 0, b2 = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->d_clip_keys.p, ctx->d_clip_keys_sorted.p, nclip, 0, 32, st);
         cub::DeviceRunLengthEncode::Encode(nullptr, b2, ctx->d_clip_keys_sorted.p, ctx->d_clip_unique.p, ctx->d_clip_counts.p,
@@ -1464,23 +1499,33 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         cub::DeviceRunLengthEncode::Encode(ctx->d_cub_tmp.p, b2, ctx->d_clip_keys_sorted.p, ctx->d_clip_unique.p, ctx->d_clip_counts.p,
                                            ctx->d_num_runs.p, nclip, st);
         ctx->stats.kernel_launches += 2;
-        int32_t runs = 0;
-        LPS_CUDA(ctx, cudaMemcpyAsync(&runs, ctx->d_num_runs.p, 4, cudaMemcpyDeviceToHost, st));
-        LPS_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<uint32_t> keys((size_t)runs), cnts((size_t)runs);
-        LPS_CUDA(ctx, cudaMemcpy(keys.data(), ctx->d_clip_unique.p, 4 * (size_t)runs, cudaMemcpyDeviceToHost));
-        LPS_CUDA(ctx, cudaMemcpy(cnts.data(), ctx->d_clip_counts.p, 4 * (size_t)runs, cudaMemcpyDeviceToHost));
-        ctx->stats.d2h_bytes += 8ull * (uint64_t)runs;
-        for (int i = 0; i < runs; i++) {
-            if (keys[i] == 0xFFFFFFFFu) continue;   // cancelled by k_clip_filter
-            int32_t pos = (int32_t)(keys[i] >> 1);
-            if (ctx->h_clip_pos.empty() || ctx->h_clip_pos.back() != pos) {
-                ctx->h_clip_pos.push_back(pos); ctx->h_clip_front.push_back(0); ctx->h_clip_back.push_back(0);
-            }
-            if (keys[i] & 1u) ctx->h_clip_back.back() += (int32_t)cnts[i]; else ctx->h_clip_front.back() += (int32_t)cnts[i];
-        }
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_num_runs.p, ctx->d_num_runs.p, 4, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_unique.p, ctx->d_clip_unique.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_counts.p, ctx->d_clip_counts.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaEventRecord(ctx->ev_clips, st));
     }
     ctx->have_calls = !tag;
     ctx->host_calls_valid = false;
+    if (!defer_clips) return lps_finish_clips(ctx);
+    return LPS_OK;
+}
+
+int lps_finish_clips(lps_ctx *ctx) {
+    if (!ctx->clips_pending) return LPS_OK;
+    ctx->clips_pending = false;
+    ctx->h_clip_pos.clear(); ctx->h_clip_front.clear(); ctx->h_clip_back.clear();
+    if (ctx->n_clip_events <= 0) return LPS_OK;
+    LPS_CUDA(ctx, cudaEventSynchronize(ctx->ev_clips));
+    const int runs = ctx->p_num_runs.p[0];
+    const uint32_t *keys = ctx->p_clip_unique.p, *cnts = ctx->p_clip_counts.p;
+    ctx->stats.d2h_bytes += 8ull * (uint64_t)runs;
+    for (int i = 0; i < runs; i++) {
+        if (keys[i] == 0xFFFFFFFFu) continue;   // cancelled by k_clip_filter
+        int32_t pos = (int32_t)(keys[i] >> 1);
+        if (ctx->h_clip_pos.empty() || ctx->h_clip_pos.back() != pos) {
+            ctx->h_clip_pos.push_back(pos); ctx->h_clip_front.push_back(0); ctx->h_clip_back.push_back(0);
+        }
+        if (keys[i] & 1u) ctx->h_clip_back.back() += (int32_t)cnts[i]; else ctx->h_clip_front.back() += (int32_t)cnts[i];
+    }
     return LPS_OK;
 }

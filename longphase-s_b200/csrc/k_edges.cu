@@ -89,6 +89,7 @@ __global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorte
     if (wid >= n_aln) return;
     int i = (int)wid;
     uint64_t key = keys_sorted[i];
+    if (key == ~0ull) return;                                                   // alignments without an alive call sort to the end
     uint32_t rank = (uint32_t)(key >> 32);
     int r = (int)(uint32_t)key;
     // end of the merged group: first later alignment with another name
@@ -120,24 +121,28 @@ __global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorte
 // for the host, which replays the same std::sort as the reference (ReadVariant::sort, Util.cpp:3-5).
 __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
                                     uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted, uint2 *__restrict__ tie_groups,
-                                    uint32_t tie_cap, unsigned int *__restrict__ n_tie) {
+                                    uint32_t tie_cap, unsigned int *__restrict__ n_tie, int record_only) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_aln) return;
+    if (keys_sorted[i] == ~0ull) return;
     uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
     if (i > 0 && (uint32_t)(keys_sorted[i - 1] >> 32) == rank) return;          // not a group head
     int j = i + 1;
     while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
     if (j == i + 1) return;                                                      // single alignment
     uint64_t g0 = grp_off[i], g1 = grp_off[j];
-    for (uint64_t a = g0; a < g1; a++) M_unsorted[a] = M[a];                     // concatenation order, for the host replay
-    bool tie = false;
-    for (uint64_t a = g0 + 1; a < g1; a++) {
-        uint32_t v = M[a];
-        uint64_t b = a;
-        while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
-        if (b > g0 && (M[b - 1] >> 2) == (v >> 2)) tie = true;
-        M[b] = v;
+    if (!record_only) {
+        for (uint64_t a = g0; a < g1; a++) M_unsorted[a] = M[a];                 // concatenation order, for the host replay
+        for (uint64_t a = g0 + 1; a < g1; a++) {
+            uint32_t v = M[a];
+            uint64_t b = a;
+            while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
+            M[b] = v;
+        }
     }
+    // a tie = two calls of the merged read at one position: adjacent after the sort
+    bool tie = false;
+    for (uint64_t a = g0 + 1; a < g1 && !tie; a++) tie = (M[a - 1] >> 2) == (M[a] >> 2);
     if (tie && g1 - g0 > 16) {
         unsigned k = atomicAdd(n_tie, 1u);
         if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
@@ -157,9 +162,13 @@ __global__ void k_tie_copy(int n_groups, const uint2 *__restrict__ groups, const
     }
 }
 
-__global__ void k_split_merged(uint64_t n, const uint32_t *__restrict__ M, uint32_t *__restrict__ node, uint32_t *__restrict__ idx) {
+// n_upper >= number of merged calls (read from device memory): the tail gets the key `pad_node`, which sorts behind every node
+__global__ void k_split_merged(uint64_t n_upper, const uint64_t *__restrict__ n_merged, uint32_t pad_node, const uint32_t *__restrict__ M,
+                               uint32_t *__restrict__ node, uint32_t *__restrict__ idx) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { node[i] = M[i] >> 2; idx[i] = (uint32_t)i; }
+    if (i >= n_upper) return;
+    node[i] = i < *n_merged ? (M[i] >> 2) : pad_node;
+    idx[i] = (uint32_t)i;
 }
 
 __global__ void k_widen_u32b(int n, const uint32_t *__restrict__ in, uint64_t *__restrict__ out) {
@@ -169,16 +178,19 @@ __global__ void k_widen_u32b(int n, const uint32_t *__restrict__ in, uint64_t *_
 
 // the fold: one warp per node
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, double edge_weight,
+__global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__restrict__ n_nodes_ptr, int W, double edge_weight,
                                                           const uint64_t *__restrict__ node_off,
                                                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
                                                           const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
                                                           double edge_threshold, uint8_t *__restrict__ vote_info,
-                                                          unsigned long long *__restrict__ counters, uint64_t n_merged,
-                                                          int8_t *__restrict__ last_link, int RS) {
+                                                          unsigned long long *__restrict__ counters, const uint64_t *__restrict__ n_merged_ptr,
+                                                          int8_t *__restrict__ last_link, int RS, const int32_t *__restrict__ node_pos,
+                                                          const uint8_t *__restrict__ node_type, int distance, uint16_t *__restrict__ sweep_meta) {
     extern __shared__ float s_acc[];                       // [WARPS][W*4]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * WARPS + wib;
+    const int n_nodes = *n_nodes_ptr;
+    const uint64_t n_merged = *n_merged_ptr;
     if (wid >= n_nodes) return;
     const int a = (int)wid;
     float *acc = s_acc + (size_t)wib * W * 4;
@@ -345,7 +357,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(int n_nodes, int W, d
     }
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) last = max(last, __shfl_xor_sync(FULL, last, dd));
-    if (lane == 0) last_link[a] = (int8_t)last;
+    if (lane == 0) {
+        last_link[a] = (int8_t)last;
+        // what the sweep needs to know about node a besides its votes: type, "the next node is farther than `distance`" (:318-320), last link
+        int gap = 0;
+        if (a + 1 < n_nodes) { const int d = node_pos[a + 1] - node_pos[a]; gap = (d < 0 ? -d : d) > distance; }
+        sweep_meta[a] = (uint16_t)((unsigned)node_type[a] | (gap ? 8u : 0u) | ((unsigned)(last + 1) << 8));
+    }
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) {
         contrib += __shfl_xor_sync(FULL, contrib, dd);
@@ -403,11 +421,94 @@ int lps_host_fix_tie_groups(lps_ctx *ctx, int n_groups) {
     return LPS_OK;
 }
 
-int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
+// first / last called position of the listed reads (what the overlap filter looks at)
+namespace {
+__global__ void k_first_last(int m, const int32_t *__restrict__ reads, const uint64_t *__restrict__ call_off,
+                             const lps_call *__restrict__ calls, const int32_t *__restrict__ vpos, int32_t *__restrict__ first_pos,
+                             int32_t *__restrict__ last_pos, uint32_t *__restrict__ ncalls) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int r = reads[i];
+    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
+    first_pos[i] = c1 > c0 ? vpos[calls[c0].var] : -1;
+    last_pos[i] = c1 > c0 ? vpos[calls[c1 - 1].var] : -1;
+    ncalls[i] = (uint32_t)(c1 - c0);
+}
+
+// The overlap filter at the head of VairiantGraph::addEdge (PhasingGraph.cpp:707-781) among the alignments of ONE read name: a
+// small state machine per name, so one thread per name that owns more than one alignment of the batch (the names are grouped on
+// the host at submit time, lps_host_index_names).  alignRange[name] is inserted as {0, 0} before the find() (:712-716), so its
+// .first is always 0; `kept` (readIdxVec[name]) is a stack in the scratch array parallel to the members.
+__global__ void k_overlap_filter(int n_groups, const int32_t *__restrict__ group_off, const int32_t *__restrict__ members,
+                                 const int32_t *__restrict__ first_pos, const int32_t *__restrict__ last_pos,
+                                 const uint32_t *__restrict__ ncalls, double overlap_threshold, int32_t *__restrict__ kept,
+                                 uint8_t *__restrict__ read_dead) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int b0 = group_off[g], b1 = group_off[g + 1];
+    int top = b0;                        // kept[b0 .. top) is the stack
+    int range_end = 0;
+    for (int m = b0; m < b1; m++) {
+        if (!ncalls[m]) continue;        // alignments without calls never reach addEdge
+        const int first = first_pos[m], last = last_pos[m];
+        bool drop_cur = false;
+        while (0 <= first && first <= range_end) {
+            if (last < range_end) { drop_cur = true; break; }
+            if (top == b0) break;
+            const int prev = kept[top - 1];
+            const int prev_start = first_pos[prev], prev_end = last_pos[prev];
+            const double ov_start = (double)max(prev_start, first), ov_end = (double)min(prev_end, last);
+            if (ov_start > ov_end) break;
+            const double ov_len = ov_end - ov_start + 1;
+            const double span = (double)max(prev_end, last) - (double)min(prev_start, first) + 1;
+            if (ov_len / span >= overlap_threshold) {
+                const int len_prev = prev_end - prev_start + 1, len_cur = last - first + 1;
+                if (len_cur <= len_prev) { drop_cur = true; break; }
+                read_dead[members[prev]] = 1;
+                top--;
+                range_end = top == b0 ? first : last_pos[kept[top - 1]];
+            } else break;
+        }
+        range_end = last;
+        if (drop_cur) read_dead[members[m]] = 1;
+        else kept[top++] = m;
+    }
+}
+}  // namespace
+
+// device half of the filters at the head of addEdge: d_read_dead for the batch.  No host synchronisation.
+int lps_launch_overlap_filter(lps_ctx *ctx, const lps_phase_params *p) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->batch.n_reads;
+    const int m = (int)ctx->h_multi_members.size(), ng = (int)ctx->h_multi_group_off.size() - 1;
+    LPS_CUDA(ctx, ctx->d_read_dead.reserve((size_t)n + 1));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_read_dead.p, 0, (size_t)n + 1, st));
+    if (m <= 0 || ng <= 0) return LPS_OK;
+    LPS_CUDA(ctx, ctx->d_first_pos.reserve((size_t)m + 1));
+    LPS_CUDA(ctx, ctx->d_last_pos.reserve((size_t)m + 1));
+    LPS_CUDA(ctx, ctx->d_multi_ncalls.reserve((size_t)m + 1));
+    LPS_CUDA(ctx, ctx->d_multi_kept.reserve((size_t)m + 1));
+    k_first_last<<<(m + 255) / 256, 256, 0, st>>>(m, ctx->d_multi_members.p, ctx->d_call_off.p, ctx->d_calls.p, ctx->var.pos,
+                                                  ctx->d_first_pos.p, ctx->d_last_pos.p, ctx->d_multi_ncalls.p);
+    k_overlap_filter<<<(ng + 127) / 128, 128, 0, st>>>(ng, ctx->d_multi_group_off.p, ctx->d_multi_members.p, ctx->d_first_pos.p, ctx->d_last_pos.p,
+                                                       ctx->d_multi_ncalls.p, p->overlap_threshold, ctx->d_multi_kept.p, ctx->d_read_dead.p);
+    ctx->stats.kernel_launches += 2;
+    LPS_CUDA(ctx, cudaGetLastError());
+    return LPS_OK;
+}
+
+// Graph construction + ordered fold.  The host knows upper bounds only (calls of the batch >= merged calls, variants >= nodes); the
+// real counts stay in device memory (d_n_nodes, d_n_merged) and every kernel reads them there, so nothing here waits for the
+// device - except, with sync_ties, the replay of tied merged reads on the host (std::sort of > 16 calls with equal positions).
+// Without sync_ties the number of such groups is left in d_n_tie for the caller to check at the end of the contig.
+int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ties) {
     cudaStream_t st = ctx->stream;
     const int n = ctx->batch.n_reads, nv = ctx->var.n, W = p->connect_adjacent;
     const int tb = 256;
     if (W < 1 || W > 127) return ctx->fail(LPS_E_ARG, "connect_adjacent must be in [1,127]");   // last_link is an int8, the sweep packs 12-bit sums
+    const size_t MU = (size_t)ctx->n_calls;      // upper bound of the merged calls
+    const int NU = nv;                           // upper bound of the nodes
+    const int RS = lps_vote_row_stride(W);
     LPS_CUDA(ctx, ctx->d_var_lastw.reserve((size_t)nv + 1));
     LPS_CUDA(ctx, ctx->d_alive_cnt.reserve((size_t)n + 1));
     LPS_CUDA(ctx, ctx->d_aln_keys.reserve((size_t)n + 1));
@@ -418,9 +519,26 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
     LPS_CUDA(ctx, ctx->d_node_pos.reserve((size_t)nv + 66));
     LPS_CUDA(ctx, ctx->d_grp_off.reserve((size_t)n + 2));
     LPS_CUDA(ctx, ctx->d_edge_counters.reserve(4));
+    LPS_CUDA(ctx, ctx->d_M.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_gend.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_node.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_node_sorted.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_idx.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_idx_sorted.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_M_unsorted.reserve(MU + 1));
+    LPS_CUDA(ctx, ctx->d_node_cnt.reserve((size_t)NU + 2));
+    LPS_CUDA(ctx, ctx->d_node_off.reserve((size_t)NU + 2));
+    LPS_CUDA(ctx, ctx->d_weights.reserve((size_t)NU * (size_t)W * 4 + 4));
+    LPS_CUDA(ctx, ctx->d_vote_info.reserve(((size_t)NU + 2) * (size_t)RS + 64));
+    LPS_CUDA(ctx, ctx->d_last_link.reserve((size_t)NU + 16));
+    LPS_CUDA(ctx, ctx->d_sweep_meta.reserve((size_t)NU + 16));
+    LPS_CUDA(ctx, ctx->d_n_tie.reserve(1));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_var_lastw.p, 0, 8 * ((size_t)nv + 1), st));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_edge_counters.p, 0, 32, st));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_cnt.p, 0, 4 * ((size_t)NU + 2), st));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_tie.p, 0, 4, st));
     const uint8_t *erased = ctx->have_erased ? ctx->d_call_erased.p : nullptr;
+    ctx->window = W;
 
     // 1. alive calls per read, node marking, alignment keys
     if (n > 0) {
@@ -429,121 +547,111 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p) {
             (unsigned long long *)ctx->d_var_lastw.p, ctx->d_alive_cnt.p, ctx->d_aln_keys.p);
         ctx->stats.kernel_launches++;
     }
-    // 2. node numbering
+    // 2. node numbering; the node count stays on the device behind the last element of the scan
     size_t cub_bytes = 0, need = 0;
-    k_node_flags<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->d_node_of_var.p);
     cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_node_of_var.p, ctx->d_node_of_var.p, nv + 1, st);
     cub_bytes = need;
-    cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 0, 64, st);
+    // name ranks are < n: the key (rank << 32 | read) only has to be ordered by rank - the sort is stable and the keys arrive in read
+    // order - so only the rank's bits are sorted
+    const int rank_bits = bits_for((uint32_t)(n > 0 ? n : 1)) + 1;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 32, std::min(64, 32 + rank_bits), st);
     if (need > cub_bytes) cub_bytes = need;
     cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_grp_off.p, ctx->d_grp_off.p, n + 1, st);
     if (need > cub_bytes) cub_bytes = need;
+    const int node_bits = bits_for((uint32_t)NU + 1);
+    if (MU > 0) {
+        cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p, ctx->d_M_idx_sorted.p, (int)MU, 0, node_bits, st);
+        if (need > cub_bytes) cub_bytes = need;
+    }
+    cub::DeviceScan::ExclusiveSum(nullptr, need, ctx->d_node_off.p, ctx->d_node_off.p, NU + 1, st);
+    if (need > cub_bytes) cub_bytes = need;
     LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(cub_bytes + 256));
+    k_node_flags<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->d_node_of_var.p);
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_of_var.p + nv, 0, 4, st));
     cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_node_of_var.p, ctx->d_node_of_var.p, nv + 1, st);
-    int32_t n_nodes = 0;
-    LPS_CUDA(ctx, cudaMemcpyAsync(&n_nodes, ctx->d_node_of_var.p + nv, 4, cudaMemcpyDeviceToHost, st));
+    // the scan's last element IS the node count; copy it out of the array k_fill_nodes rewrites
+    LPS_CUDA(ctx, ctx->d_n_nodes.reserve(2));
+    LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_n_nodes.p, ctx->d_node_of_var.p + nv, 4, cudaMemcpyDeviceToDevice, st));
     k_fill_nodes<<<(nv + tb) / tb, tb, 0, st>>>(nv, (const unsigned long long *)ctx->d_var_lastw.p, ctx->var.pos, ctx->d_node_of_var.p,
                                                 ctx->d_node_var.p, ctx->d_node_pos.p, ctx->d_node_type.p);
     ctx->stats.kernel_launches += 3;
-    // 3. alignments in (name rank, BAM order); offsets of their calls inside M
-    int rank_bits = 32 + 32;
-    cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, cub_bytes, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 0, rank_bits, st);
+    // 3. alignments in (name rank, BAM order); offsets of their calls inside M.  Alignments without an alive call carry the key ~0: they
+    //    sort to the end and own zero calls, the kernels below skip them.
+    if (n > 0) cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, cub_bytes, ctx->d_aln_keys.p, ctx->d_aln_keys_sorted.p, n, 32, std::min(64, 32 + rank_bits), st);
     k_sorted_counts<<<(n + 1 + tb) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_alive_cnt.p, ctx->d_grp_off.p);
     cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_grp_off.p, ctx->d_grp_off.p, n + 1, st);
     ctx->stats.kernel_launches += 3;
-    uint64_t n_merged = 0;
-    LPS_CUDA(ctx, cudaMemcpyAsync(&n_merged, ctx->d_grp_off.p + n, 8, cudaMemcpyDeviceToHost, st));
-    LPS_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->n_nodes = n_nodes; ctx->window = W; ctx->n_merged = n_merged;
-    // number of alive alignments = sorted keys that are not the sentinel: they are a prefix; count via grp_off on host is
-    // avoidable: dead entries own zero calls, the kernels below simply skip them (their key is ~0).
-    LPS_CUDA(ctx, ctx->d_M.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_M_gend.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_M_node.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_M_node_sorted.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_M_idx.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_M_idx_sorted.reserve((size_t)n_merged + 1));
-    LPS_CUDA(ctx, ctx->d_node_cnt.reserve((size_t)n_nodes + 2));
-    LPS_CUDA(ctx, ctx->d_node_off.reserve((size_t)n_nodes + 2));
-    LPS_CUDA(ctx, ctx->d_weights.reserve((size_t)n_nodes * (size_t)W * 4 + 4));
-    LPS_CUDA(ctx, ctx->d_vote_info.reserve(((size_t)n_nodes + 2) * (size_t)lps_vote_row_stride(W) + 64));
-    LPS_CUDA(ctx, ctx->d_last_link.reserve((size_t)n_nodes + 16));
-    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_node_cnt.p, 0, 4 * ((size_t)n_nodes + 2), st));
-
-    // alive alignments: keys != ~0 are a prefix of the sorted array
-    int n_aln = 0;
-    {
-        // binary search on the device array would need a kernel; the host already knows which reads have calls:
-        // count = reads that are not dead and have >= 1 surviving call == entries with alive_cnt > 0.
-        std::vector<uint32_t> cnt((size_t)n);
-        LPS_CUDA(ctx, cudaMemcpy(cnt.data(), ctx->d_alive_cnt.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-        ctx->stats.d2h_bytes += 4ull * (uint64_t)n;
-        for (int r = 0; r < n; r++) if (cnt[r]) n_aln++;
-    }
-    if (n_aln > 0 && n_merged > 0) {
-        k_fill_merged<<<(unsigned)(((long long)n_aln * 32 + tb - 1) / tb), tb, 0, st>>>(
-            n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_call_off.p, ctx->d_calls.p, erased, ctx->d_node_of_var.p,
+    const uint64_t *d_n_merged = ctx->d_grp_off.p + n;      // the scan's last element: merged calls
+    if (n > 0 && MU > 0) {
+        k_fill_merged<<<(unsigned)(((long long)n * 32 + tb - 1) / tb), tb, 0, st>>>(
+            n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_call_off.p, ctx->d_calls.p, erased, ctx->d_node_of_var.p,
             p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
         // multi-alignment merged reads
-        DevBuf<uint2> &tie_groups = ctx->d_tie_groups;
-        DevBuf<unsigned int> &n_tie = ctx->d_n_tie;
-        const uint32_t tie_cap = 1u << 18;
-        LPS_CUDA(ctx, tie_groups.reserve(tie_cap));
-        LPS_CUDA(ctx, n_tie.reserve(1));
-        LPS_CUDA(ctx, ctx->d_M_unsorted.reserve((size_t)n_merged + 1));
-        LPS_CUDA(ctx, cudaMemsetAsync(n_tie.p, 0, 4, st));
-        k_sort_multi_groups<<<(n_aln + tb - 1) / tb, tb, 0, st>>>(n_aln, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p,
-                                                                  ctx->d_M_unsorted.p, tie_groups.p, tie_cap, n_tie.p);
+        LPS_CUDA(ctx, ctx->d_tie_groups.reserve(std::max<size_t>(ctx->d_tie_groups.cap, 4096)));
+        k_sort_multi_groups<<<(n + tb - 1) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
+                                                          ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu), ctx->d_n_tie.p, 0);
         ctx->stats.kernel_launches += 2;
-        unsigned int h_tie = 0;
-        LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, n_tie.p, 4, cudaMemcpyDeviceToHost, st));
-        LPS_CUDA(ctx, cudaStreamSynchronize(st));
-        if (h_tie > tie_cap) return ctx->fail(LPS_E_NOMEM, "too many tied merged reads");
-        if (h_tie) {
-            int rc = lps_host_fix_tie_groups(ctx, (int)h_tie);
-            if (rc) return rc;
+        if (sync_ties) {
+            unsigned int h_tie = 0;
+            LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, ctx->d_n_tie.p, 4, cudaMemcpyDeviceToHost, st));
+            LPS_CUDA(ctx, cudaStreamSynchronize(st));
+            if (h_tie > ctx->d_tie_groups.cap) {
+                // more tied groups than the list holds: grow it and list them again (the merged reads are sorted by now)
+                LPS_CUDA(ctx, ctx->d_tie_groups.reserve((size_t)h_tie + 1024));
+                LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_tie.p, 0, 4, st));
+                k_sort_multi_groups<<<(n + tb - 1) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
+                                                                  ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu),
+                                                                  ctx->d_n_tie.p, 1);
+                ctx->stats.kernel_launches++;
+                LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, ctx->d_n_tie.p, 4, cudaMemcpyDeviceToHost, st));
+                LPS_CUDA(ctx, cudaStreamSynchronize(st));
+                if (h_tie > ctx->d_tie_groups.cap) return ctx->fail(LPS_E_NOMEM, "tie group list sizing did not converge");
+            }
+            if (h_tie) {
+                int rc = lps_host_fix_tie_groups(ctx, (int)h_tie);
+                if (rc) return rc;
+                LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_tie.p, 0, 4, st));
+            }
         }
-
         // 4. per-node call lists in merged (= name rank) order: one stable radix sort by node
-        k_split_merged<<<(unsigned)((n_merged + tb - 1) / tb), tb, 0, st>>>(n_merged, ctx->d_M.p, ctx->d_M_node.p, ctx->d_M_idx.p);
-        size_t sort_bytes = 0;
-        const int nb = bits_for((uint32_t)n_nodes);
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p,
-                                        ctx->d_M_idx_sorted.p, (int)n_merged, 0, nb, st);
-        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(sort_bytes + 256));
-        cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, sort_bytes, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p,
-                                        ctx->d_M_idx_sorted.p, (int)n_merged, 0, nb, st);
-        k_widen_u32b<<<(n_nodes + 1 + tb) / tb, tb, 0, st>>>(n_nodes, ctx->d_node_cnt.p, ctx->d_node_off.p);
-        size_t scan_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_node_off.p, ctx->d_node_off.p, n_nodes + 1, st);
-        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(scan_bytes + 256));
-        cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, scan_bytes, ctx->d_node_off.p, ctx->d_node_off.p, n_nodes + 1, st);
-        ctx->stats.kernel_launches += 4;
+        k_split_merged<<<(unsigned)((MU + tb - 1) / tb), tb, 0, st>>>((uint64_t)MU, d_n_merged, (uint32_t)NU, ctx->d_M.p, ctx->d_M_node.p, ctx->d_M_idx.p);
+        cub::DeviceRadixSort::SortPairs(ctx->d_cub_tmp.p, cub_bytes, ctx->d_M_node.p, ctx->d_M_node_sorted.p, ctx->d_M_idx.p, ctx->d_M_idx_sorted.p, (int)MU, 0,
+                                        node_bits, st);
+        ctx->stats.kernel_launches += 2;
     }
-    // 5. the fold
-    if (n_nodes > 0) {
-        if (n_merged == 0) {
-            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_weights.p, 0, 4 * (size_t)n_nodes * W * 4, st));
-            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_vote_info.p, 0, (size_t)n_nodes * lps_vote_row_stride(W), st));
-            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_last_link.p, 0xFF, (size_t)n_nodes, st));
-        } else {
-            constexpr int WARPS = 8;
-            size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
-            cudaEventRecord(ctx->kev[2], st);
-            k_fold_edges<WARPS><<<(n_nodes + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
-                n_nodes, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
-                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, (uint64_t)n_merged, ctx->d_last_link.p, lps_vote_row_stride(W));
-            cudaEventRecord(ctx->kev[3], st);
-            ctx->stats.kernel_launches++;
-        }
+    k_widen_u32b<<<(NU + 1 + tb) / tb, tb, 0, st>>>(NU, ctx->d_node_cnt.p, ctx->d_node_off.p);
+    cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, cub_bytes, ctx->d_node_off.p, ctx->d_node_off.p, NU + 1, st);
+    ctx->stats.kernel_launches += 2;
+    // 5. the fold (nodes without calls in M - there are none - would simply write an empty row)
+    if (NU > 0) {
+        constexpr int WARPS = 8;
+        size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
+        cudaEventRecord(ctx->kev[2], st);
+        k_fold_edges<WARPS><<<(NU + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
+            ctx->d_n_nodes.p, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
+            p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, d_n_merged, ctx->d_last_link.p, RS, ctx->d_node_pos.p,
+            ctx->d_node_type.p, p->distance, ctx->d_sweep_meta.p);
+        cudaEventRecord(ctx->kev[3], st);
+        ctx->stats.kernel_launches++;
     }
     LPS_CUDA(ctx, cudaGetLastError());
+    ctx->have_graph = true;
+    return LPS_OK;
+}
+
+// counts of the graph (nodes, merged calls, pair contributions) to the host; waits for the stream
+int lps_fetch_graph_counts(lps_ctx *ctx) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->batch.n_reads;
+    int32_t n_nodes = 0;
+    uint64_t n_merged = 0;
     unsigned long long hc[2] = {0, 0};
+    LPS_CUDA(ctx, cudaMemcpyAsync(&n_nodes, ctx->d_n_nodes.p, 4, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaMemcpyAsync(&n_merged, ctx->d_grp_off.p + n, 8, cudaMemcpyDeviceToHost, st));
     LPS_CUDA(ctx, cudaMemcpyAsync(hc, ctx->d_edge_counters.p, 16, cudaMemcpyDeviceToHost, st));
     LPS_CUDA(ctx, cudaStreamSynchronize(st));
-    if (n_nodes > 0 && n_merged > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_fold_edges, ctx->kev[2], ctx->kev[3]);
+    if (ctx->var.n > 0) cudaEventElapsedTime(&ctx->stats.ms_kernel_fold_edges, ctx->kev[2], ctx->kev[3]);
+    ctx->n_nodes = n_nodes; ctx->n_merged = n_merged;
     ctx->n_contrib = hc[0]; ctx->n_contrib_far = hc[1];
-    ctx->have_graph = true;
     return LPS_OK;
 }

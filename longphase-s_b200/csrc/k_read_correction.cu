@@ -88,6 +88,5 @@ int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p) {
         LPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_hap_ref.p, hap_final.p, (size_t)nv, cudaMemcpyDeviceToDevice, st));
     }
     LPS_CUDA(ctx, cudaGetLastError());
-    LPS_CUDA(ctx, cudaStreamSynchronize(st));
-    return LPS_OK;
+    return LPS_OK;          // asynchronous: the caller waits for the stream when it needs the result
 }

@@ -1,0 +1,322 @@
+// k_sweep.cu — VairiantGraph::edgeConnectResult on the device (reference src/phase/PhasingGraph.cpp:286-474, with
+// VariantEdge::findBestEdgePair :166-228 already reduced to one vote byte per edge cell by k_fold_edges and Onelongcase :251-283).
+//
+// The sweep is a left-to-right chain: node k's haplotype comes from the votes of its <= W predecessors (two float sums whose
+// order of addition is part of the result, plus Onelongcase's integer counters), then k votes on its <= W successors.  One
+// sequential pass over 65 k nodes costs milliseconds on any single processor.  But the state that crosses a point of the chain
+// is small: the haplotypes (up to one global flip - the rule is symmetric in the two haplotypes) and voted / skipped status of
+// the last W voters, and `lastConnectPos`.  So the chain is cut into SEGMENTS of S nodes, one warp each, all running at once:
+//   1. k_sweep_segments: segment p starts H nodes EARLY (a halo) from an empty state; by the time it reaches its own first
+//      node the accumulators only hold votes of nodes it decided itself.  It records its decisions for its core nodes, and for
+//      the last W halo nodes separately.
+//   2. k_sweep_verify: for every boundary, the W halo decisions of segment p are compared with what segment p-1 decided for
+//      the same nodes: same assigned / new-block / voted pattern and haplotypes equal up to ONE flip.  If so the state at the
+//      boundary is the true one (by induction from segment 0, which starts at the true start), up to that flip, which is
+//      resolved by a scan over the segments (a block start inside a segment re-anchors the orientation: hp = 1).
+//   3. k_sweep_fallback: if any boundary disagrees, ONE warp redoes the whole chain sequentially (exact by construction) -
+//      the launch is unconditional, the kernel returns at once when step 2 succeeded, so the host never has to look.
+//   4. finish: block starts by a max-scan, single-member blocks dropped (:425), PS = position(block start) + 1, per VARIANT.
+// Inside a warp node s lives in lane s & 31, slot (s >> 5) & 1 (the window of W <= 63 successors never holds two nodes of one
+// slot), so no accumulator ever moves; the vote rows and the per-node meta words are staged through shared memory by bulk
+// copies (cp.async.bulk on an mbarrier) one chunk ahead of the chain.
+#include <climits>
+#include <cub/cub.cuh>
+#include "lps_ctx.cuh"
+#include "lps_async.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SW_CH = 64;        // nodes per staged chunk
+constexpr int SW_RS_MAX = 80;    // lps_vote_row_stride(63)
+constexpr int SW_WARPS = 4;      // segments per CTA
+constexpr int SW_SEG = 512;      // core nodes per segment
+constexpr int SW_HALO_W = 4;     // halo = SW_HALO_W * W nodes
+
+struct SweepArgs {
+    const int32_t *n_nodes;      // device: number of graph nodes
+    int W, RS, seg, halo, n_seg;
+    const uint8_t *votes;        // [n_nodes][RS] vote bytes of voter k, byte j = vote on node 16 * ((k + 1) / 16) + j
+    const uint16_t *meta;        // [n_nodes] node type | gap << 3 | (last_link + 1) << 8
+    uint8_t *flags;              // [n_nodes] 1 assigned | 2 new block | (hp - 1) << 2 | 8 voted
+    uint8_t *halo_flags;         // [n_seg][W]
+    int32_t *first_nb;           // [n_seg] first block start inside the segment's core, INT_MAX if none
+    uint8_t *seg_flip;           // [n_seg] flip of the core nodes before first_nb
+    int32_t *all_ok;             // 1 when every boundary verified
+};
+
+struct alignas(16) SweepSmem {
+    uint8_t rows[2][SW_CH * SW_RS_MAX];
+    uint16_t meta[2][SW_CH];
+    unsigned long long mbar[2];
+};
+
+// everything VariantEdge::findBestEdgePair / edgeConnectResult (:360-417) make of one vote byte, for a voter of haplotype `same`
+__device__ __forceinline__ void vote_of(unsigned info, unsigned same, float w_lo, float w_hi, bool type_ok, float &d1, float &d2, unsigned &dp) {
+    const unsigned link = info & 3u;
+    const bool heavy = (info & 4u) != 0;
+    const float wb = heavy ? w_hi : w_lo;                                    // 1 / 20 / 0.1f (:367-369)
+    const bool tA = link == same, tB = link != 0u && !tA;
+    d1 = tA ? wb : 0.f; d2 = tB ? wb : 0.f;                                   // + 0.0f is exact; the sums are never -0.0
+    const bool single = (info & 8u) != 0;
+    const bool qual = !single && (info & 16u) != 0 && type_ok;              // Onelongcase: weight >= 1, voter not an indel (:265)
+    const unsigned wi = heavy ? 20u : 1u;
+    dp = ((link != 0u && single) ? 1u : 0u) | ((qual && tA) ? (wi << 8) : 0u) | ((qual && tB) ? (wi << 20) : 0u);
+}
+
+// the chain over nodes [k_begin, k_end), from an empty state at k_begin; decisions of nodes >= k_core go to flags[], those of the
+// W nodes before k_core to halo_flags[seg]
+__device__ __forceinline__ void sweep_range(const SweepArgs &a, SweepSmem &S, const int N, const int k_begin, const int k_core, const int k_end,
+                                            const int seg, const int lane) {
+    float w1a = 0.f, w2a = 0.f, w1b = 0.f, w2b = 0.f;
+    unsigned pka = 0u, pkb = 0u;
+    int last_connect = -1, first_nb = INT_MAX;
+    const int W = a.W, RS = a.RS;
+    const int k_stop = min(k_end, N - 1);            // the loop of :313 needs a successor
+    if (k_begin < k_stop) {
+        int c = k_begin / SW_CH;
+        const int c_last = (k_stop - 1) / SW_CH;
+        auto issue = [&](int chunk, int b) {
+            if (lane == 0) {
+                const int k0 = chunk * SW_CH;
+                const int rows = min(SW_CH, N - k0);
+                const uint32_t b_rows = (uint32_t)rows * (uint32_t)RS, b_meta = (uint32_t)((rows * 2 + 15) & ~15);
+                const uint32_t bar = smem_u32(&S.mbar[b]);
+                mbar_expect_tx(bar, b_rows + b_meta);
+                bulk_g2s(smem_u32(&S.rows[b][0]), a.votes + (size_t)k0 * RS, b_rows, bar);
+                bulk_g2s(smem_u32(&S.meta[b][0]), a.meta + k0, b_meta, bar);
+            }
+        };
+        int buf = 0;
+        uint32_t phase = 0u;
+        issue(c, 0);
+        for (; c <= c_last; c++) {
+            if (c + 1 <= c_last) issue(c + 1, buf ^ 1);
+            mbar_wait(smem_u32(&S.mbar[buf]), (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            const int k0 = c * SW_CH;
+            const int ka = max(k0, k_begin), kb = min(k0 + SW_CH, k_stop);
+            for (int k = ka; k < kb; k++) {
+                const unsigned m = S.meta[buf][k - k0];
+                const bool gap = (m & 8u) != 0;                                 // |pos[k+1] - pos[k]| > distance (:318-320)
+                const unsigned type = m & 7u;
+                const int Lp1 = (int)(m >> 8);
+                const int owner = k & 31;
+                const bool sb = ((k >> 5) & 1) != 0;
+                float h1 = sb ? w1b : w1a, h2 = sb ? w2b : w2a;
+                const unsigned pk = sb ? pkb : pka;
+                if (lane == owner) { if (sb) { w1b = 0.f; w2b = 0.f; pkb = 0u; } else { w1a = 0.f; w2a = 0.f; pka = 0u; } }   // the slot now belongs to node k + 64
+                unsigned f = 0u;
+                bool votes = false;
+                int hp = 1;
+                if (!gap) {
+                    const int sg = (int)(pk & 0xFFu), a1 = (int)((pk >> 8) & 0xFFFu), a2 = (int)(pk >> 20);
+                    if (sg > 3 && (a1 | a2) != 0) { h1 = (float)a1; h2 = (float)a2; }                                      // Onelongcase :276-281
+                    unsigned bits = (h1 == h2 ? 1u : 0u) | (h1 > h2 ? 2u : 0u);
+                    bits = __shfl_sync(FULL, bits, owner);
+                    bool assigned = true, nb = false;
+                    if (bits & 1u) {
+                        if (last_connect >= 0 && k < last_connect) assigned = false;                                       // :340-342
+                        else nb = true;                                                                                     // new block, hp = 1
+                    } else hp = (bits & 2u) ? 1 : 2;
+                    if (assigned) {
+                        votes = Lp1 != 0;
+                        f = 1u | (nb ? 2u : 0u) | ((unsigned)(hp - 1) << 2) | (votes ? 8u : 0u);
+                        if (nb && k >= k_core && first_nb == INT_MAX) first_nb = k;
+                    }
+                }
+                if (lane == 0) {
+                    if (k >= k_core) a.flags[k] = (uint8_t)f;
+                    else if (seg >= 0 && k >= k_core - W) a.halo_flags[(size_t)seg * W + (k - (k_core - W))] = (uint8_t)f;
+                }
+                if (votes) {
+                    const int base = (k + 1) & ~15;
+                    const uint8_t *row = S.rows[buf] + (k - k0) * RS;
+                    const unsigned same = hp == 1 ? 1u : 2u;
+                    const float w_lo = type == 4u ? (float)0.1 : 1.f, w_hi = type == 4u ? (float)0.1 : 20.f;
+                    const bool type_ok = type != 3u && type != 4u;
+                    const int j0 = (lane - base) & 31;
+                    bool slot = (((base + j0) >> 5) & 1) != 0;
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        const int j = j0 + 32 * t;
+                        if (j < RS) {
+                            float d1, d2; unsigned dp;
+                            vote_of(row[j], same, w_lo, w_hi, type_ok, d1, d2, dp);
+                            if (slot) { w1b += d1; w2b += d2; pkb += dp; } else { w1a += d1; w2a += d2; pka += dp; }
+                        }
+                        slot = !slot;
+                    }
+                    last_connect = k + Lp1;
+                }
+            }
+            __syncwarp();
+            buf ^= 1;
+        }
+    }
+    if (seg >= 0 && lane == 0) a.first_nb[seg] = first_nb;
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32) k_sweep_segments(SweepArgs a) {
+    __shared__ SweepSmem s_all[SW_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    SweepSmem &S = s_all[wib];
+    if (lane == 0) { mbar_init(smem_u32(&S.mbar[0]), 1u); mbar_init(smem_u32(&S.mbar[1]), 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int N = *a.n_nodes;
+    const int p = blockIdx.x * SW_WARPS + wib;
+    if (p >= a.n_seg) return;
+    const int b = p * a.seg, e = min(N, b + a.seg);
+    // halo nodes without a decision (before node 0) read as "nothing there" in the comparison
+    if (lane == 0) for (int i = 0; i < a.W; i++) a.halo_flags[(size_t)p * a.W + i] = 0xFFu;
+    __syncwarp();
+    if (b >= N) { if (lane == 0) a.first_nb[p] = INT_MAX; return; }
+    sweep_range(a, S, N, max(0, b - a.halo), b, e, p, lane);
+}
+
+// boundary checks + flips (one CTA; thread p checks the boundary in front of segment p)
+__global__ void __launch_bounds__(1024) k_sweep_verify(SweepArgs a) {
+    __shared__ int s_ok;
+    const int N = *a.n_nodes;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    for (int p = 1 + (int)threadIdx.x; p < a.n_seg; p += blockDim.x) {
+        const int b = p * a.seg;
+        int ok = 1, flip = -1;
+        if (b < N - 1 && b - a.halo > 0) {          // a halo that starts at node 0 starts from the true state: nothing to check
+            for (int i = 0; i < a.W; i++) {
+                const int kk = b - a.W + i;
+                if (kk < 0) continue;
+                const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
+                if (h == 0xFFu || ((t ^ h) & 0xBu)) { ok = 0; break; }
+                if (t & 1u) {
+                    const int x = (int)(((t ^ h) >> 2) & 1u);
+                    if (flip < 0) flip = x; else if (flip != x) { ok = 0; break; }
+                }
+            }
+        }
+        a.seg_flip[p] = (uint8_t)(flip > 0 ? 1 : 0);     // relative to segment p - 1 for now
+        if (!ok) s_ok = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // flips relative to the truth: a block start inside a segment's core re-anchors the orientation from there on
+        unsigned carry = 0u;                              // flip in force at the end of the previous segment
+        for (int p = 0; p < a.n_seg; p++) {
+            const int b = p * a.seg, e = min(N, b + a.seg);
+            const unsigned F = p == 0 ? 0u : ((unsigned)a.seg_flip[p] ^ carry);
+            a.seg_flip[p] = (uint8_t)F;
+            carry = (b < N && a.first_nb[p] < e) ? 0u : F;
+        }
+        *a.all_ok = s_ok;
+    }
+}
+
+// the exact sequential chain, only when a boundary did not verify
+__global__ void __launch_bounds__(32) k_sweep_fallback(SweepArgs a) {
+    __shared__ SweepSmem S;
+    if (*a.all_ok) return;
+    const int lane = threadIdx.x;
+    if (lane == 0) { mbar_init(smem_u32(&S.mbar[0]), 1u); mbar_init(smem_u32(&S.mbar[1]), 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int N = *a.n_nodes;
+    sweep_range(a, S, N, 0, 0, N, -1, lane);
+    for (int p = lane; p < a.n_seg; p += 32) a.seg_flip[p] = 0;
+}
+
+__global__ void k_sweep_block_start(int n_upper, const int32_t *__restrict__ n_nodes, const uint8_t *__restrict__ flags, int32_t *__restrict__ start) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_upper) return;
+    start[k] = (k < *n_nodes && (flags[k] & 3u) == 3u) ? k : -1;
+}
+
+// a block is kept when it has a second member (:425): any assigned node that is not a block start marks its block
+__global__ void k_sweep_mark_multi(int n_upper, const int32_t *__restrict__ n_nodes, const uint8_t *__restrict__ flags, const int32_t *__restrict__ start,
+                                   uint8_t *__restrict__ multi) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_upper || k >= *n_nodes) return;
+    if ((flags[k] & 3u) == 1u && start[k] >= 0) multi[start[k]] = 1;
+}
+
+// per VARIANT: phase set (block start position + 1) and REF-allele haplotype after the sweep
+__global__ void k_sweep_finish(int nv, const int32_t *__restrict__ node_of_var, const uint8_t *__restrict__ flags, const int32_t *__restrict__ start,
+                               const uint8_t *__restrict__ multi, const int32_t *__restrict__ node_pos, const int32_t *__restrict__ first_nb,
+                               const uint8_t *__restrict__ seg_flip, int seg, int32_t *__restrict__ ps, int8_t *__restrict__ hap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const int k = node_of_var[i];
+    int out_ps = 0, out_hap = -1;
+    if (k >= 0) {
+        const unsigned f = flags[k];
+        const int st = (f & 1u) ? start[k] : -1;
+        if (st >= 0 && !(st == k && !multi[k])) {
+            const int p = k / seg;
+            const unsigned flip = k < first_nb[p] ? (unsigned)seg_flip[p] : 0u;
+            out_ps = node_pos[st] + 1;
+            out_hap = (int)(((f >> 2) & 1u) ^ flip);
+        }
+    }
+    ps[i] = out_ps;
+    hap[i] = (int8_t)out_hap;
+}
+
+struct MaxOp { __device__ __forceinline__ int32_t operator()(int32_t x, int32_t y) const { return x > y ? x : y; } };
+
+}  // namespace
+
+// d_vote_info / d_sweep_meta / d_node_pos / d_node_of_var hold the graph of this contig; n_upper >= number of nodes (the host may
+// not know the exact count).  Writes the sweep result per variant into d_ps / d_hap_ref.  No host synchronisation.
+int lps_launch_sweep(lps_ctx *ctx, const lps_phase_params *p, int n_upper) {
+    cudaStream_t st = ctx->stream;
+    const int nv = ctx->var.n, W = ctx->window;
+    (void)p;
+    LPS_CUDA(ctx, ctx->d_ps.reserve((size_t)nv + 1));
+    LPS_CUDA(ctx, ctx->d_hap_ref.reserve((size_t)nv + 1));
+    if (n_upper <= 0 || nv <= 0) {
+        if (nv > 0) {
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_ps.p, 0, 4 * (size_t)nv, st));
+            LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_hap_ref.p, 0xFF, (size_t)nv, st));
+        }
+        return LPS_OK;
+    }
+    SweepArgs a;
+    a.n_nodes = ctx->d_n_nodes.p;
+    a.W = W; a.RS = lps_vote_row_stride(W); a.seg = SW_SEG; a.halo = SW_HALO_W * W;
+    if (a.seg < 2 * W) a.seg = 2 * W;
+    a.n_seg = (n_upper + a.seg - 1) / a.seg;
+    LPS_CUDA(ctx, ctx->d_sweep_flags.reserve((size_t)n_upper + 16));
+    LPS_CUDA(ctx, ctx->d_sweep_halo.reserve((size_t)a.n_seg * W + 16));
+    LPS_CUDA(ctx, ctx->d_sweep_first_nb.reserve((size_t)a.n_seg + 1));
+    LPS_CUDA(ctx, ctx->d_sweep_flip.reserve((size_t)a.n_seg + 1));
+    LPS_CUDA(ctx, ctx->d_sweep_ok.reserve(1));
+    LPS_CUDA(ctx, ctx->d_sweep_start.reserve((size_t)n_upper + 1));
+    LPS_CUDA(ctx, ctx->d_sweep_multi.reserve((size_t)n_upper + 1));
+    a.votes = ctx->d_vote_info.p; a.meta = ctx->d_sweep_meta.p; a.flags = ctx->d_sweep_flags.p; a.halo_flags = ctx->d_sweep_halo.p;
+    a.first_nb = ctx->d_sweep_first_nb.p; a.seg_flip = ctx->d_sweep_flip.p; a.all_ok = ctx->d_sweep_ok.p;
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_flags.p, 0, (size_t)n_upper + 16, st));
+    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_multi.p, 0, (size_t)n_upper + 1, st));
+    const char *force = getenv("LPS_SWEEP_SEQUENTIAL");      // A/B and tests: skip the speculation, run the exact chain on one warp
+    if (force && force[0] == '1') {
+        LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_ok.p, 0, 4, st));
+        LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_first_nb.p, 0, 4 * (size_t)a.n_seg, st));
+    } else {
+        k_sweep_segments<<<(a.n_seg + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, 0, st>>>(a);
+        k_sweep_verify<<<1, 1024, 0, st>>>(a);
+        ctx->stats.kernel_launches += 2;
+    }
+    k_sweep_fallback<<<1, 32, 0, st>>>(a);
+    const int tb = 256, gb = (n_upper + tb - 1) / tb;
+    k_sweep_block_start<<<gb, tb, 0, st>>>(n_upper, ctx->d_n_nodes.p, ctx->d_sweep_flags.p, ctx->d_sweep_start.p);
+    size_t tmp = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, tmp, ctx->d_sweep_start.p, ctx->d_sweep_start.p, MaxOp(), n_upper, st);
+    LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(tmp + 256));
+    cub::DeviceScan::InclusiveScan(ctx->d_cub_tmp.p, tmp, ctx->d_sweep_start.p, ctx->d_sweep_start.p, MaxOp(), n_upper, st);
+    k_sweep_mark_multi<<<gb, tb, 0, st>>>(n_upper, ctx->d_n_nodes.p, ctx->d_sweep_flags.p, ctx->d_sweep_start.p, ctx->d_sweep_multi.p);
+    k_sweep_finish<<<(nv + tb - 1) / tb, tb, 0, st>>>(nv, ctx->d_node_of_var.p, ctx->d_sweep_flags.p, ctx->d_sweep_start.p, ctx->d_sweep_multi.p,
+                                                      ctx->d_node_pos.p, ctx->d_sweep_first_nb.p, ctx->d_sweep_flip.p, a.seg, ctx->d_ps.p, ctx->d_hap_ref.p);
+    ctx->stats.kernel_launches += 5;
+    LPS_CUDA(ctx, cudaGetLastError());
+    return LPS_OK;
+}

@@ -21,19 +21,6 @@ template <typename T> int d2h(lps_ctx *ctx, std::vector<T> &dst, const T *src, s
 }
 #define TRY(x) do { int rc__ = (x); if (rc__ != LPS_OK) return rc__; } while (0)
 
-// first / last called position of the listed reads (what the overlap filter looks at)
-__global__ void k_first_last(int m, const int32_t *__restrict__ reads, const uint64_t *__restrict__ call_off,
-                             const lps_call *__restrict__ calls, const int32_t *__restrict__ vpos, int32_t *__restrict__ first_pos,
-                             int32_t *__restrict__ last_pos, uint32_t *__restrict__ ncalls) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int r = reads[i];
-    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
-    first_pos[i] = c1 > c0 ? vpos[calls[c0].var] : -1;
-    last_pos[i] = c1 > c0 ? vpos[calls[c1 - 1].var] : -1;
-    ncalls[i] = (uint32_t)(c1 - c0);
-}
-
 // BAM's uint32 CIGAR ops -> the 16-bit stream the kernels read (len << 4 | op; a length >= 4095 becomes 0xFFF and goes to the side
 // table).  Eight ops per thread: two 128-bit loads, one 128-bit store.  Escapes are appended as (op index << 28 | length) keys and
 // sorted afterwards (they are rare: N ops, long matches of high-accuracy reads), which gives the table in ascending op order.
@@ -63,11 +50,6 @@ __global__ void k_narrow_cigar32(size_t n, const uint32_t *__restrict__ in, uint
 __global__ void k_unpack_long_keys(unsigned int n, const unsigned long long *__restrict__ keys, uint64_t *__restrict__ at, uint32_t *__restrict__ len) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { at[i] = keys[i] >> 28; len[i] = (uint32_t)(keys[i] & 0xFFFFFFFull); }
-}
-
-__global__ void k_mark_dead(int m, const int32_t *__restrict__ reads, uint8_t *__restrict__ dead) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) dead[reads[i]] = 1;
 }
 
 int fetch_host_calls(lps_ctx *ctx) {
@@ -183,6 +165,7 @@ int lps_ctx_create(int device, lps_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->user_ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->kev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&ctx->ev_clips, cudaEventDisableTiming);
     {
         // PQ = (int)(-10*log10(min/(max+min))) (HaplotagStrategy.cpp:287) tabulated with the HOST libm, so that the
         // truncation to int agrees with the reference on the same machine; the kernel only looks it up
@@ -208,6 +191,7 @@ void lps_ctx_destroy(lps_ctx *ctx) {
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->user_ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->kev) cudaEventDestroy(ev);
+    if (ctx->ev_clips) cudaEventDestroy(ctx->ev_clips);
     cudaStreamDestroy(ctx->stream);
     for (auto &cs : ctx->stream_k) if (cs) cudaStreamDestroy(cs);
     if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);
@@ -338,6 +322,7 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     ctx->h_flag.assign(b->flag, b->flag + n);
     lps_host_index_names(ctx);
     TRY(h2d(ctx, ctx->d_multi_members, ctx->h_multi_members.data(), ctx->h_multi_members.size()));
+    TRY(h2d(ctx, ctx->d_multi_group_off, ctx->h_multi_group_off.data(), ctx->h_multi_group_off.size()));
     uint64_t s = 0;
     for (size_t i = 0; i < n; i++) s += (uint64_t)(b->l_qseq[i] > 0 ? b->l_qseq[i] : 0);
     ctx->sum_l_qseq = s;
@@ -393,6 +378,8 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     lps_host_index_names(ctx);
     TRY(h2d(ctx, ctx->d_multi_members, ctx->h_multi_members.data(), ctx->h_multi_members.size()));
+    TRY(h2d(ctx, ctx->d_multi_group_off, ctx->h_multi_group_off.data(), ctx->h_multi_group_off.size()));
+    LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->sum_l_qseq = b->qual_bytes;
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
     return LPS_OK;
@@ -682,46 +669,17 @@ int lps_somatic_tag_reads(lps_ctx *ctx, const lps_tag_params *p, int want_calls,
     return LPS_OK;
 }
 
-int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_edges *out) {
-    if (!ctx || !p) return LPS_E_ARG;
-    if (!ctx->have_calls) return ctx->fail(LPS_E_STATE, "lps_phase_call_alleles must run first");
-    cudaSetDevice(ctx->device);
-    const int n = ctx->batch.n_reads;
-    cudaStream_t st = ctx->stream;
-    WallTimer wt;
-    // ---- host filters at the head of addEdge (PhasingGraph.cpp:707-791) ----
-    std::vector<int32_t> first_pos, last_pos, dead;
-    std::vector<uint32_t> ncalls;
-    const int m = (int)ctx->h_multi_members.size();
-    LPS_CUDA(ctx, ctx->d_read_dead.reserve((size_t)n + 1));
-    LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_read_dead.p, 0, (size_t)n + 1, st));
-    WallTimer wf;
-    ctx->h_read_dead.assign((size_t)n, 0);
-    if (m > 0) {
-        DevBuf<int32_t> &d_first = ctx->d_first_pos, &d_last = ctx->d_last_pos;
-        LPS_CUDA(ctx, d_first.reserve((size_t)m + 1));
-        LPS_CUDA(ctx, d_last.reserve((size_t)m + 1));
-        LPS_CUDA(ctx, ctx->d_multi_ncalls.reserve((size_t)m + 1));
-        k_first_last<<<(m + 255) / 256, 256, 0, st>>>(m, ctx->d_multi_members.p, ctx->d_call_off.p, ctx->d_calls.p, ctx->var.pos,
-                                                      d_first.p, d_last.p, ctx->d_multi_ncalls.p);
-        ctx->stats.kernel_launches++;
-        TRY(d2h(ctx, first_pos, d_first.p, (size_t)m));
-        TRY(d2h(ctx, last_pos, d_last.p, (size_t)m));
-        TRY(d2h(ctx, ncalls, ctx->d_multi_ncalls.p, (size_t)m));
-        LPS_CUDA(ctx, cudaStreamSynchronize(st));
-        lps_host_overlap_filter(ctx, p, first_pos, last_pos, ncalls, dead);
-        if (!dead.empty()) {
-            for (int32_t r : dead) ctx->h_read_dead[(size_t)r] = 1;
-            TRY(h2d(ctx, ctx->d_dead_list, dead.data(), dead.size()));
-            k_mark_dead<<<((int)dead.size() + 255) / 256, 256, 0, st>>>((int)dead.size(), ctx->d_dead_list.p, ctx->d_read_dead.p);
-            ctx->stats.kernel_launches++;
-        }
-    }
+// CNV mismatch filter of addEdge (PhasingGraph.cpp:783-791) from the clip map: the state machine over the clip positions
+// (run twice, as in PhasingProcess.cpp:147-148) is host code; without an interval (the normal case) nothing is erased
+static int host_cnv_filter(lps_ctx *ctx) {
     ctx->h_cnv_start.clear(); ctx->h_cnv_end.clear();
     lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
     lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
     ctx->have_erased = false;
     if (!ctx->h_cnv_start.empty()) {
+        // the filter looks at which alignments survive the overlap filter
+        const size_t n = (size_t)ctx->batch.n_reads;
+        TRY(d2h(ctx, ctx->h_read_dead, ctx->d_read_dead.p, n));
         TRY(fetch_host_calls(ctx));
         std::vector<uint8_t> erased;
         TRY(lps_host_cnv_filter(ctx, erased));
@@ -732,12 +690,26 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
             ctx->have_erased = true;
         }
     }
+    return LPS_OK;
+}
+
+int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_edges *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_calls) return ctx->fail(LPS_E_STATE, "lps_phase_call_alleles must run first");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    WallTimer wt;
+    // ---- filters at the head of addEdge (PhasingGraph.cpp:707-791): overlap filter on the device, CNV filter from the clip map ----
+    WallTimer wf;
+    TRY(lps_finish_clips(ctx));
+    TRY(lps_launch_overlap_filter(ctx, p));
+    TRY(host_cnv_filter(ctx));
     ctx->stats.ms_host_filters = wf.ms();
     // ---- device: merge by name, fan out, ordered fold ----
     cudaEventRecord(ctx->ev[2], st);
-    TRY(lps_launch_build_edges(ctx, p));
+    TRY(lps_launch_build_edges(ctx, p, true));
     cudaEventRecord(ctx->ev[3], st);
-    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    TRY(lps_fetch_graph_counts(ctx));
     ctx->stats.ms_build_edges = elapsed(ctx, 2, 3);
     const size_t nn = (size_t)ctx->n_nodes;
     TRY(d2h(ctx, ctx->h_node_var, ctx->d_node_var.p, nn));
@@ -756,17 +728,17 @@ int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host
     return LPS_OK;
 }
 
-int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
-    if (!ctx || !p) return LPS_E_ARG;
-    if (!ctx->have_graph) return ctx->fail(LPS_E_STATE, "lps_phase_build_edges must run first");
-    cudaSetDevice(ctx->device);
+// edgeConnectResult on the HOST over the device's vote bytes: kept for windows beyond the device sweep's 63 successors and as an
+// A/B switch (LPS_HOST_SWEEP=1); lps_sweep_votes exposes the same code without any device
+static int host_sweep(lps_ctx *ctx, const lps_phase_params *p) {
     cudaStream_t st = ctx->stream;
-    const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
-    WallTimer wt;
-    // ---- sweep (edgeConnectResult) on the host over the one-byte votes computed by the fold epilogue ----
+    TRY(lps_fetch_graph_counts(ctx));
+    const size_t nn = (size_t)ctx->n_nodes, nv = (size_t)ctx->var.n;
     const size_t RS = (size_t)lps_vote_row_stride(ctx->window);
     LPS_CUDA(ctx, ctx->p_vote_info.reserve(nn * RS + 128));
     LPS_CUDA(ctx, ctx->p_last_link.reserve(nn + 16));
+    TRY(d2h(ctx, ctx->h_node_var, ctx->d_node_var.p, nn));
+    TRY(d2h(ctx, ctx->h_node_type, ctx->d_node_type.p, nn));
     if (nn) {
         LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_vote_info.p, ctx->d_vote_info.p, nn * RS, cudaMemcpyDeviceToHost, st));
         LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_last_link.p, ctx->d_last_link.p, nn, cudaMemcpyDeviceToHost, st));
@@ -796,6 +768,30 @@ int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *o
     ctx->stats.ms_host_sweep = ws.ms();
     TRY(h2d(ctx, ctx->d_ps, ctx->h_ps_sweep.data(), nv));
     TRY(h2d(ctx, ctx->d_hap_ref, ctx->h_hap_sweep.data(), nv));
+    return LPS_OK;
+}
+
+static bool use_host_sweep(const lps_ctx *ctx) {
+    const char *env = getenv("LPS_HOST_SWEEP");
+    return ctx->window > 63 || (env && env[0] == '1');
+}
+
+int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_graph) return ctx->fail(LPS_E_STATE, "lps_phase_build_edges must run first");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
+    WallTimer wt;
+    ctx->stats.ms_host_sweep = 0.f;
+    // ---- sweep (edgeConnectResult) over the one-byte votes computed by the fold epilogue ----
+    if (use_host_sweep(ctx)) TRY(host_sweep(ctx, p));
+    else {
+        TRY(lps_launch_sweep(ctx, p, ctx->var.n));
+        TRY(d2h(ctx, ctx->h_ps_sweep, ctx->d_ps.p, nv));
+        TRY(d2h(ctx, ctx->h_hap_sweep, ctx->d_hap_ref.p, nv));
+        LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     // ---- device: read correction ----
     cudaEventRecord(ctx->ev[2], st);
     TRY(lps_launch_read_correction(ctx, p));
@@ -836,10 +832,86 @@ int lps_sweep_votes(const lps_phase_params *p, int32_t n_nodes, int32_t window, 
     return lps_host_sweep(p, n_nodes, window, node_pos, node_type, rows, last.data(), node_ps, node_hap_ref);
 }
 
+// The body of the contig loop (PhasingProcess.cpp:113-173) as ONE asynchronous pipeline: after the allele-calling kernel has
+// reported its counters (the one wait in the middle: they size everything downstream) every stage is only enqueued - overlap
+// filter, graph construction and fold, sweep, read correction, the copies of the results into pinned memory - and the host waits
+// once, at the end.  While the device works the host turns the clip map into CNV intervals; two rare conditions need host code in
+// the middle of the pipeline (a CNV interval: calls have to be erased before the graph is built; a merged read of > 16 calls
+// with tied positions: libstdc++'s std::sort order has to be replayed) - then the result of the fast pipeline is discarded and
+// the contig is redone stage by stage (lps_phase_build_edges / lps_phase_solve), which handles both.
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out) {
-    TRY(lps_phase_call_alleles(ctx, p, 0, nullptr));
-    TRY(lps_phase_build_edges(ctx, p, 0, nullptr));
-    return lps_phase_solve(ctx, p, out);
+    if (!ctx || !p) return LPS_E_ARG;
+    if (!ctx->have_variants || !ctx->have_batch) return ctx->fail(LPS_E_STATE, "variants and a read batch must be set first");
+    const char *staged = getenv("LPS_STAGED");
+    if (use_host_sweep(ctx) || p->connect_adjacent > 63 || (staged && staged[0] == '1')) {
+        TRY(lps_phase_call_alleles(ctx, p, 0, nullptr));
+        TRY(lps_phase_build_edges(ctx, p, 0, nullptr));
+        return lps_phase_solve(ctx, p, out);
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t nv = (size_t)ctx->var.n, n = (size_t)ctx->batch.n_reads;
+    WallTimer wt;
+    cudaEventRecord(ctx->ev[2], st);
+    TRY(lps_launch_call_alleles(ctx, p, nullptr, 0, -1, true));
+    cudaEventRecord(ctx->ev[3], st);
+    ctx->stats.ms_wall_call_alleles = wt.ms();
+    WallTimer wb;
+    ctx->have_erased = false;
+    TRY(lps_launch_overlap_filter(ctx, p));
+    cudaEventRecord(ctx->ev[4], st);
+    TRY(lps_launch_build_edges(ctx, p, false));
+    cudaEventRecord(ctx->ev[5], st);
+    TRY(lps_launch_sweep(ctx, p, ctx->var.n));
+    LPS_CUDA(ctx, ctx->p_ps_sweep.reserve(nv + 1)); LPS_CUDA(ctx, ctx->p_hap_sweep.reserve(nv + 1));
+    LPS_CUDA(ctx, ctx->p_ps.reserve(nv + 1)); LPS_CUDA(ctx, ctx->p_hap.reserve(nv + 1));
+    LPS_CUDA(ctx, ctx->p_read_hp.reserve(n + 1)); LPS_CUDA(ctx, ctx->p_hp_counts.reserve(4 * nv + 4));
+    LPS_CUDA(ctx, ctx->p_status.reserve(8));
+    if (nv) {
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_ps_sweep.p, ctx->d_ps.p, 4 * nv, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_hap_sweep.p, ctx->d_hap_ref.p, nv, cudaMemcpyDeviceToHost, st));
+    }
+    cudaEventRecord(ctx->ev[6], st);
+    TRY(lps_launch_read_correction(ctx, p));
+    cudaEventRecord(ctx->ev[7], st);
+    if (nv) {
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_ps.p, ctx->d_ps.p, 4 * nv, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_hap.p, ctx->d_hap_ref.p, nv, cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_hp_counts.p, ctx->d_hp_counts.p, 16 * nv, cudaMemcpyDeviceToHost, st));
+    }
+    if (n) LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_read_hp.p, ctx->d_read_hp.p, n, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_status.p, ctx->d_n_tie.p, 4, cudaMemcpyDeviceToHost, st));
+    LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_status.p + 1, ctx->d_sweep_ok.p, 4, cudaMemcpyDeviceToHost, st));
+    ctx->stats.d2h_bytes += 26 * nv + n + 8;
+    // ---- host, while the device works: clip map -> CNV intervals ----
+    WallTimer wf;
+    TRY(lps_finish_clips(ctx));
+    ctx->h_cnv_start.clear(); ctx->h_cnv_end.clear();
+    lps_host_cnv_intervals(ctx->h_clip_pos, ctx->h_clip_front, ctx->h_clip_back, ctx->h_cnv_start, ctx->h_cnv_end);
+    ctx->stats.ms_host_filters = wf.ms();
+    ctx->stats.ms_host_sweep = 0.f;
+    LPS_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->stats.ms_wall_build_edges = wb.ms();
+    ctx->stats.ms_wall_solve = 0.f;
+    ctx->stats.ms_call_alleles = elapsed(ctx, 2, 3);
+    ctx->stats.ms_build_edges = elapsed(ctx, 4, 5);
+    ctx->stats.ms_sweep = elapsed(ctx, 5, 6);
+    ctx->stats.ms_read_correction = elapsed(ctx, 6, 7);
+    cudaEventElapsedTime(&ctx->stats.ms_kernel_fold_edges, ctx->kev[2], ctx->kev[3]);
+    ctx->stats.sweep_fallbacks += ctx->p_status.p[1] ? 0 : 1;
+    if (!ctx->h_cnv_start.empty() || ctx->p_status.p[0] != 0) {
+        // rare: host code is needed between the kernels; redo the contig stage by stage (the calls are still on the device)
+        ctx->stats.slow_path_contigs++;
+        TRY(lps_phase_build_edges(ctx, p, 0, nullptr));
+        return lps_phase_solve(ctx, p, out);
+    }
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->n_variants = ctx->var.n; out->ps = ctx->p_ps.p; out->hap_ref = ctx->p_hap.p;
+        out->n_reads = ctx->batch.n_reads; out->read_hp = ctx->p_read_hp.p; out->hp_counts = ctx->p_hp_counts.p;
+        out->ps_sweep = ctx->p_ps_sweep.p; out->hap_ref_sweep = ctx->p_hap_sweep.p;
+    }
+    return LPS_OK;
 }
 
 int lps_event_record(lps_ctx *ctx, int slot) {

@@ -139,6 +139,7 @@ struct lps_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t user_ev[4] = {};
     cudaEvent_t kev[6] = {};   // around the hot kernels
+    cudaEvent_t ev_clips = nullptr;   // the clip map has reached the pinned staging buffers
     std::string err;
     int err_code = 0;
     lps_stats stats = {};
@@ -177,7 +178,7 @@ struct lps_ctx {
     DevBatch batch;
     std::vector<int32_t> h_name_rank;
     std::vector<int32_t> h_multi_members, h_multi_group_off;   // alignments of names that occur more than once, grouped by name
-    DevBuf<int32_t> d_multi_members, d_dead_list;
+    DevBuf<int32_t> d_multi_members, d_multi_group_off, d_multi_kept, d_dead_list;
     DevBuf<uint32_t> d_multi_ncalls;
     uint64_t sum_l_qseq = 0;
     bool have_batch = false;
@@ -263,7 +264,10 @@ struct lps_ctx {
     DevBuf<uint8_t> d_vote_info;                    // [n_nodes][lps_vote_row_stride(window)] vote bytes of voter k, shifted to 16-node blocks (host_phase.cpp)
     DevBuf<int8_t> d_last_link;                     // [n_nodes] largest successor offset a node links to, -1 if none
     PinBuf<int8_t> p_last_link;
-    DevBuf<int32_t> d_node_pos;
+    DevBuf<int32_t> d_node_pos, d_n_nodes;            // d_n_nodes[0]: node count of the graph, as the device knows it
+    DevBuf<uint16_t> d_sweep_meta;                  // per node: type | gap << 3 | (last_link + 1) << 8 (k_fold_edges -> k_sweep)
+    DevBuf<uint8_t> d_sweep_flags, d_sweep_halo, d_sweep_flip, d_sweep_multi;
+    DevBuf<int32_t> d_sweep_first_nb, d_sweep_ok, d_sweep_start;
     PinBuf<uint8_t> p_vote_info;                    // pinned staging of the vote bytes for the host sweep
     DevBuf<unsigned long long> d_edge_counters;     // [0] contrib, [1] far
     DevBuf<uint2> d_tie_groups;
@@ -287,6 +291,13 @@ struct lps_ctx {
     std::vector<int8_t> h_hap_ref, h_read_hp, h_hap_sweep;
     std::vector<int32_t> h_ps_sweep;
 
+    // ---- asynchronous per-contig path (lps_phase_contig): results and the clip map land in pinned memory ----
+    PinBuf<uint32_t> p_clip_unique, p_clip_counts;
+    PinBuf<int32_t> p_num_runs, p_ps, p_ps_sweep, p_hp_counts, p_status;
+    PinBuf<int8_t> p_hap, p_hap_sweep, p_read_hp;
+    int32_t n_clip_events = 0;
+    bool clips_pending = false;
+
     int fail(int code, const std::string &msg) {
         err_code = code;
         err = msg;
@@ -298,14 +309,16 @@ struct lps_ctx {
 int lps_launch_annotate(lps_ctx *ctx);
 int lps_prepare_call_alleles(lps_ctx *ctx);   // per-device function attributes of k_call_alleles (called by lps_ctx_create)
 int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_tag_params *t = nullptr, int want_calls = 0,
-                            int mode = -1 /* LPS_MODE_*; -1: PHASE when t is null, GERMLINE otherwise */);
+                            int mode = -1 /* LPS_MODE_*; -1: PHASE when t is null, GERMLINE otherwise */, bool defer_clips = false);
+int lps_finish_clips(lps_ctx *ctx);   // waits for the clip map of a deferred call and builds h_clip_pos / front / back
 int lps_launch_window_diff(lps_ctx *ctx, int have_reference);
-int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p);
+int lps_launch_overlap_filter(lps_ctx *ctx, const lps_phase_params *p);
+int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ties);
+int lps_fetch_graph_counts(lps_ctx *ctx);
+int lps_launch_sweep(lps_ctx *ctx, const lps_phase_params *p, int n_upper);
 int lps_launch_read_correction(lps_ctx *ctx, const lps_phase_params *p);
 // host restatements that sit between the kernels (host_phase.cpp)
 void lps_host_index_names(lps_ctx *ctx);
-void lps_host_overlap_filter(lps_ctx *ctx, const lps_phase_params *p, const std::vector<int32_t> &first_pos,
-                             const std::vector<int32_t> &last_pos, const std::vector<uint32_t> &ncalls, std::vector<int32_t> &dead);
 void lps_host_cnv_intervals(const std::vector<int32_t> &pos, const std::vector<int32_t> &front,
                             const std::vector<int32_t> &back, std::vector<int32_t> &cs, std::vector<int32_t> &ce);
 int lps_host_cnv_filter(lps_ctx *ctx, std::vector<uint8_t> &erased);

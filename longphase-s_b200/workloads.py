@@ -1,6 +1,6 @@
-"""The synthetic workloads bench.py times, defined ONCE so that the parity tests (`tests/test_gpu_large.py`), the committed oracle
-digests (`tests/golden/bench_digests.json`, written by `tools/make_bench_digests.py`) and the bench itself build byte-identical
-contigs.  BASELINE.json configs: C2 shard (phase SNP+indel, 64 Mb contigs, 30x ONT-like 20 kb reads), C4 shard (tumor 50x /
+"""The synthetic workloads bench.py times, defined ONCE so that the parity tests (`tests/test_gpu_large.py`), the committed
+known-answer digests (`tests/golden/bench_digests.json`, written by `tools/make_bench_digests.py` from the CPU checker) and the bench
+itself build byte-identical contigs.  BASELINE.json configs: C2 shard (phase SNP+indel, 64 Mb contigs, 30x ONT-like 20 kb reads), C4 shard (tumor 50x /
 normal 25x pair), and the whole-genome shape of C2 (24 GRCh38-proportioned contigs, strong scaling by LPT over the ranks).
 
 No torch / CUDA imports: host logic, usable from the CPU tests.
@@ -73,13 +73,6 @@ def phase_digest(ps, hap_ref, read_hp, hp_counts):
     for a, dt in ((ps, np.int32), (hap_ref, np.int8), (read_hp, np.int8), (hp_counts, np.int32)):
         h.update(np.ascontiguousarray(np.asarray(a), dtype=dt).tobytes())
     return h.hexdigest()
-
-
-def oracle_phase_digest(orc, n_reads):
-    """The same digest from an oracle.pyoracle.OraclePhase result (test / tool side only)."""
-    hp = np.full(n_reads, -2, np.int8)
-    hp[orc.aln_read] = orc.read_hp
-    return phase_digest(orc.ps, orc.hap_ref, hp, orc.hp_counts)
 
 
 def load_digests():

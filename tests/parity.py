@@ -10,6 +10,14 @@ host = importlib.import_module("longphase_s_b200.host")
 ffi = importlib.import_module("longphase_s_b200._ffi")
 
 
+def oracle_phase_digest(orc, n_reads):
+    """workloads.phase_digest of an oracle.pyoracle.OraclePhase result (what bench.py's gate compares the GPU result with)."""
+    workloads = importlib.import_module("longphase_s_b200.workloads")
+    hp = np.full(n_reads, -2, np.int8)
+    hp[orc.aln_read] = orc.read_hp
+    return workloads.phase_digest(orc.ps, orc.hap_ref, hp, orc.hp_counts)
+
+
 def check_phase(contig, params, ctx=None, verbose=False):
     """Runs the whole phase path on the GPU and asserts bit-exact equality with the oracle at every stage.
     Returns a dict of sizes for reporting."""

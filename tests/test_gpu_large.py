@@ -41,7 +41,7 @@ def test_gpu_timed_64mb_contig_matches_oracle_at_every_stage():
     assert info["reads"] > 90_000 and info["calls"] > 1_500_000
     orc = po.OraclePhase(c, p)
     want = workloads.load_digests().get(workloads.key_of(workloads.phase_kwargs(workloads.weak_seed(0, 0))))
-    assert want is not None and want["digest"] == workloads.oracle_phase_digest(orc, c.n_reads), "committed bench digest is stale"
+    assert want is not None and want["digest"] == parity.oracle_phase_digest(orc, c.n_reads), "committed bench digest is stale"
     ctx = host.Context(0)
     check_gpu_tag(c.phased(orc.ps, orc.hap_ref == 1), ffi.default_tag_params(), ctx)
     ctx.close()

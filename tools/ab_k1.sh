@@ -1,11 +1,11 @@
 #!/bin/bash
-# A/B of k_call_alleles build variants on the GPU box: tools/ab_k1.sh "KOPS:WARPS:GROUPS_CAP:DECODE:WALK_VEC" ...
+# A/B of k_call_alleles build variants on the GPU box: tools/ab_k1.sh "WARPS:SC_OPS:CAND_CAP[:extra -D flags]" ...   (the last one stays built)
 cd "$(dirname "$0")/.."
 for cfg in "$@"; do
-  IFS=: read K W G D V C <<< "$cfg"; G=${G:-384}; D=${D:-0}; V=${V:-1}; C=${C:-1}
+  IFS=: read W S C X <<< "$cfg"
   touch longphase-s_b200/csrc/k_call_alleles.cu
-  make -C longphase-s_b200/csrc EXTRA="-DLPS_KOPS=$K -DLPS_WARPS=$W -DLPS_GROUPS_CAP=$G -DLPS_DECODE=$D -DLPS_WALK_VEC=$V -DLPS_CTAS_PER_SM=$C" > /dev/null 2>&1 || { echo "build failed $cfg"; continue; }
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-paths --contigs-per-gpu 1 ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err || { tail -3 /tmp/ab.err; continue; }
+  make -C longphase-s_b200/csrc EXTRA="-DLPS_WARPS=$W -DLPS_SC_OPS=$S -DLPS_CAND_CAP=$C $X" > /dev/null 2>&1 || { echo "build failed $cfg"; continue; }
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-other-paths --contigs-per-gpu 1 ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err || { tail -3 /tmp/ab.err; continue; }
   python - "$cfg" <<'PY'
 import json,sys
 d=json.load(open('/tmp/ab.json'))

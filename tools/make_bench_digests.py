@@ -24,9 +24,10 @@ def one(kw):
     ffi = importlib.import_module("longphase_s_b200._ffi")
     wl = importlib.import_module("longphase_s_b200.workloads")
     from oracle import pyoracle as po
+    from tests import parity
     c = synth.Contig(**kw)
     orc = po.OraclePhase(c, ffi.default_phase_params(True))
-    return wl.key_of(kw), {"digest": wl.oracle_phase_digest(orc, c.n_reads), "reads": int(c.n_reads), "variants": int(c.n_var),
+    return wl.key_of(kw), {"digest": parity.oracle_phase_digest(orc, c.n_reads), "reads": int(c.n_reads), "variants": int(c.n_var),
                            "calls": int(len(orc.calls)), "phased": int((orc.ps != 0).sum())}
 
 
