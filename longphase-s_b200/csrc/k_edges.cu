@@ -119,6 +119,86 @@ __global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorte
 // sorted, so an in-place insertion sort moves little.  Equal positions keep their concatenation order,
 // which is what std::sort's insertion-sort branch (n <= 16) does; larger groups with ties are flagged
 // for the host, which replays the same std::sort as the reference (ReadVariant::sort, Util.cpp:3-5).
+// ---- libstdc++'s std::sort, replayed: merged reads with tied positions and more than 16 calls -------------------------------
+// ReadVariant::sort (Util.cpp:3-5) is std::sort by position; with equal positions the order of the tied calls is whatever
+// introsort leaves, and the edge weights are folded in that order.  The algorithm is deterministic, so it is restated here step for
+// step (GCC's bits/stl_algo.h: __introsort_loop with the median-of-three pivot moved to the front and the unguarded partition,
+// then __final_insertion_sort: guarded insertion over the first 16, unguarded over the rest).  The heapsort branch behind the
+// depth limit 2 * floor(log2(n)) is not restated: a group that reaches it is reported to the host instead (never seen so far).
+// Keys are the merged entries themselves (node << 2 | allele << 1 | q_hi); the comparator looks at the node only.
+__device__ __forceinline__ bool ss_less(uint32_t a, uint32_t b) { return (a >> 2) < (b >> 2); }
+__device__ __forceinline__ void ss_swap(uint32_t *v, long long i, long long j) { const uint32_t t = v[i]; v[i] = v[j]; v[j] = t; }
+
+__device__ bool std_sort_replay(uint32_t *v, long long n) {
+    if (n < 2) return true;
+    // __introsort_loop, the recursion on the right part turned into an explicit stack of (first, last, depth_limit)
+    long long stk_first[48], stk_last[48];
+    int stk_depth[48];
+    int top = 0;
+    int lg = 0;
+    for (long long t = n; t > 1; t >>= 1) lg++;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; top = 1;
+    while (top > 0) {
+        top--;
+        long long first = stk_first[top], last = stk_last[top];
+        int depth = stk_depth[top];
+        // the reference implementation recurses into [cut, last) FIRST and then loops on [first, cut); the parts are disjoint, so the
+        // order in which they are finished does not change the result
+        while (last - first > 16) {
+            if (depth == 0) return false;                       // would switch to heapsort
+            depth--;
+            // __unguarded_partition_pivot
+            const long long mid = first + (last - first) / 2;
+            {   // __move_median_to_first(first, first + 1, mid, last - 1)
+                const long long a = first + 1, b = mid, c = last - 1;
+                if (ss_less(v[a], v[b])) {
+                    if (ss_less(v[b], v[c])) ss_swap(v, first, b);
+                    else if (ss_less(v[a], v[c])) ss_swap(v, first, c);
+                    else ss_swap(v, first, a);
+                } else if (ss_less(v[a], v[c])) ss_swap(v, first, a);
+                else if (ss_less(v[b], v[c])) ss_swap(v, first, c);
+                else ss_swap(v, first, b);
+            }
+            long long lo = first + 1, hi = last;
+            const long long pivot = first;
+            while (true) {                                      // __unguarded_partition(first + 1, last, first)
+                while (ss_less(v[lo], v[pivot])) lo++;
+                hi--;
+                while (ss_less(v[pivot], v[hi])) hi--;
+                if (!(lo < hi)) break;
+                ss_swap(v, lo, hi);
+                lo++;
+            }
+            const long long cut = lo;
+            if (top >= 48) return false;
+            stk_first[top] = cut; stk_last[top] = last; stk_depth[top] = depth; top++;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    auto unguarded_linear_insert = [&](long long lastp) {
+        const uint32_t val = v[lastp];
+        long long next = lastp - 1;
+        while (ss_less(val, v[next])) { v[lastp] = v[next]; lastp = next; next--; }
+        v[lastp] = val;
+    };
+    auto insertion_sort = [&](long long f, long long l) {
+        if (f == l) return;
+        for (long long i = f + 1; i != l; i++) {
+            if (ss_less(v[i], v[f])) {
+                const uint32_t val = v[i];
+                for (long long k = i; k > f; k--) v[k] = v[k - 1];    // move_backward(first, i, i + 1)
+                v[f] = val;
+            } else unguarded_linear_insert(i);
+        }
+    };
+    if (n > 16) {
+        insertion_sort(0, 16);
+        for (long long i = 16; i != n; i++) unguarded_linear_insert(i);
+    } else insertion_sort(0, n);
+    return true;
+}
+
 __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
                                     uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted, uint2 *__restrict__ tie_groups,
                                     uint32_t tie_cap, unsigned int *__restrict__ n_tie, int record_only) {
@@ -144,8 +224,25 @@ __global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys
     bool tie = false;
     for (uint64_t a = g0 + 1; a < g1 && !tie; a++) tie = (M[a - 1] >> 2) == (M[a] >> 2);
     if (tie && g1 - g0 > 16) {
-        unsigned k = atomicAdd(n_tie, 1u);
-        if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
+        // more than 16 calls with a tie: the order of the tied calls is std::sort's - replay it from the concatenation order
+        bool done = false;
+        if (!record_only) {
+            for (uint64_t a = g0; a < g1; a++) M[a] = M_unsorted[a];
+            done = std_sort_replay(M + g0, (long long)(g1 - g0));
+            if (!done) {                                         // leave the group position-sorted for the host replay's write-back
+                for (uint64_t a = g0; a < g1; a++) M[a] = M_unsorted[a];
+                for (uint64_t a = g0 + 1; a < g1; a++) {
+                    uint32_t v = M[a];
+                    uint64_t b = a;
+                    while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
+                    M[b] = v;
+                }
+            }
+        }
+        if (!done) {
+            unsigned k = atomicAdd(n_tie, 1u);
+            if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
+        }
     }
 }
 

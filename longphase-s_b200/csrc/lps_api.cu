@@ -899,6 +899,8 @@ int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *
     ctx->stats.ms_read_correction = elapsed(ctx, 6, 7);
     cudaEventElapsedTime(&ctx->stats.ms_kernel_fold_edges, ctx->kev[2], ctx->kev[3]);
     ctx->stats.sweep_fallbacks += ctx->p_status.p[1] ? 0 : 1;
+    if (getenv("LPS_DEBUG_SLOW") && (!ctx->h_cnv_start.empty() || ctx->p_status.p[0] != 0))
+        fprintf(stderr, "lps_phase_contig: slow path (cnv intervals %zu, tie groups for the host %d)\n", ctx->h_cnv_start.size(), ctx->p_status.p[0]);
     if (!ctx->h_cnv_start.empty() || ctx->p_status.p[0] != 0) {
         // rare: host code is needed between the kernels; redo the contig stage by stage (the calls are still on the device)
         ctx->stats.slow_path_contigs++;

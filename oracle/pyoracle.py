@@ -70,7 +70,7 @@ class TapOut(C.Structure):
                 ("n_result", C.c_int32), ("res_pos", i32p), ("res_block", i32p), ("res_hap_ref", i32p),
                 ("res_hap_alt", i32p), ("t_get_snp", C.c_double), ("t_filter_snp", C.c_double),
                 ("t_clip", C.c_double), ("t_add_edge", C.c_double), ("t_sweep", C.c_double),
-                ("t_read_correction", C.c_double)]
+                ("t_read_correction", C.c_double), ("t_export", C.c_double), ("n_result_calls", C.c_int64)]
 
 
 class OrcTags(C.Structure):
@@ -299,6 +299,26 @@ class ReferencePhase:
                 self.res_hap_ref, self.res_hap_alt = g(out.res_hap_ref, n, np.int32), g(out.res_hap_alt, n, np.int32)
         finally:
             lib.ref_tap_phase_free(C.byref(out))
+
+
+class ReferencePhaseTimed:
+    """The UNMODIFIED reference's phase path on a synth.Contig in the tap's timing mode: nothing is flattened or copied out; only
+    the seconds spent inside the reference's own calls (get_snp loop, filterSNP, Clip, addEdge, edgeConnectResult, readCorrection,
+    exportResult) and the counts come back.  bench.py's reference arm."""
+
+    def __init__(self, contig, params, chr_name="chrS"):
+        lib = tap_lib()
+        tin = TapIn(chr=chr_name.encode(), ref=contig.ref, ref_len=len(contig.ref), n_var=contig.n_var,
+                    var_pos=_ffi.ptr(contig.var_pos, i32p), var_str_off=_ffi.ptr(contig.var_str_off, _ffi.u32p),
+                    var_str=contig.var_str, batch=contig.batch_struct(), names=contig.names,
+                    name_stride=contig.NAME_STRIDE, stop_after_calls=2, p=params)
+        out = TapOut()
+        self.rc = lib.ref_tap_phase(C.byref(tin), C.byref(out))
+        self.times = dict(get_snp=out.t_get_snp, filter_snp=out.t_filter_snp, clip=out.t_clip, add_edge=out.t_add_edge,
+                          sweep=out.t_sweep, read_correction=out.t_read_correction, export=out.t_export)
+        self.seconds = float(sum(self.times.values()))
+        self.n_calls, self.n_aln, self.n_result = int(out.n_result_calls), int(out.stage_a.n_aln), int(out.n_result)
+        lib.ref_tap_phase_free(C.byref(out))
 
 
 class OracleTag:

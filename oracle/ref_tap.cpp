@@ -166,6 +166,9 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
 
     int lastSNPpos = snpFile.getLastSNP(chr);
     if (lastSNPpos == -1) { free(tname); return -2; }
+    // stop_after_calls == 2: timing mode (bench.py's reference arm) - the whole path, nothing flattened for the caller; only the
+    // timers around the reference's own calls and the counts are returned
+    const bool timing = in->stop_after_calls == 2;
 
     // ---- stage A: get_snp over the batch ----
     double t0 = now_s();
@@ -207,8 +210,11 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
     }
     delete bamParser;
     out->t_get_snp = now_s() - t0;
-    dump_stage(readVariantVec, &out->stage_a);
-    {
+    if (timing) {
+        out->stage_a.n_aln = (int32_t)readVariantVec.size();
+        for (auto &r : readVariantVec) out->n_result_calls += (int64_t)r.variantVec.size();
+    } else dump_stage(readVariantVec, &out->stage_a);
+    if (!timing) {
         std::vector<int32_t> p, f, k;
         for (auto &kv : clipCount) {
             p.push_back(kv.first);
@@ -224,8 +230,8 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
     t0 = now_s();
     if (params.isONT) snpFile.filterSNP(chr, readVariantVec, chr_reference);
     out->t_filter_snp = now_s() - t0;
-    dump_stage(readVariantVec, &out->stage_b);
-    if (readVariantVec.empty() || in->stop_after_calls) { free(tname); return 0; }
+    if (!timing) dump_stage(readVariantVec, &out->stage_b);
+    if (readVariantVec.empty() || in->stop_after_calls == 1) { free(tname); return 0; }
 
     // the reference dereferences front()/back() of EMPTY variantVecs in addEdge (UB); report them
     for (auto &r : readVariantVec) if (r.variantVec.empty()) out->n_empty_after_filter++;
@@ -236,7 +242,7 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
     Clip *clip = new Clip(chr, clipCount);
     clip->getCNVInterval(clipCount, chr);
     out->t_clip = now_s() - t0;
-    {
+    if (!timing) {
         std::vector<int32_t> s, e;
         for (auto &c : clip->cnvVec) { s.push_back(c.first); e.push_back(c.second); }
         out->n_cnv = (int32_t)s.size();
@@ -248,8 +254,8 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
     VairiantGraph *g = new VairiantGraph(chr_reference, params, chr);
     g->addEdge(readVariantVec, *clip);
     out->t_add_edge = now_s() - t0;
-    dump_stage(readVariantVec, &out->stage_c);
-    {
+    if (!timing) dump_stage(readVariantVec, &out->stage_c);
+    if (!timing) {
         std::vector<int32_t> ap, bp;
         std::vector<uint8_t> which;
         std::vector<float> val;
@@ -272,12 +278,12 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
     t0 = now_s();
     g->edgeConnectResult();
     out->t_sweep = now_s() - t0;
-    dump_nodes(*g, &out->nodes_sweep);
+    if (!timing) dump_nodes(*g, &out->nodes_sweep);
     t0 = now_s();
     g->readCorrection();
     out->t_read_correction = now_s() - t0;
-    dump_nodes(*g, &out->nodes_final);
-    {
+    if (!timing) dump_nodes(*g, &out->nodes_final);
+    if (!timing) {
         std::vector<int32_t> hp;
         for (auto &r : readVariantVec) {
             auto it = g->readHpMap->find(r.read_name);
@@ -286,8 +292,11 @@ extern "C" int ref_tap_phase(const tap_phase_in *in, tap_phase_out *out) {
         out->read_hp = dup_vec(hp);
     }
     PhasingResult result;
+    t0 = now_s();
     g->exportResult(chr, result);
-    {
+    out->t_export = now_s() - t0;
+    out->n_result = (int32_t)result.size();
+    if (!timing) {
         std::vector<int32_t> pos, blk, h1, h2;
         for (auto &kv : result) {
             pos.push_back(std::stoi(kv.first.substr(chr.size() + 1)));

@@ -60,6 +60,8 @@ typedef struct {
     int32_t n_result;              /* exportResult                                         */
     int32_t *res_pos, *res_block, *res_hap_ref, *res_hap_alt;
     double t_get_snp, t_filter_snp, t_clip, t_add_edge, t_sweep, t_read_correction;
+    double t_export;               /* exportResult                                          */
+    int64_t n_result_calls;        /* timing mode (stop_after_calls == 2): calls after get_snp */
 } tap_phase_out;
 
 /* ---- germline haplotag tap (ref_tap_tag.cpp) ---- */
