@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py — throughput of the LongPhase-S `phase` read-to-variant hot path on B200.
 
-One "step" = one pass of the whole hot path (allele calling -> host filters -> edge fold -> host sweep
--> read correction) over the synthetic contigs of this GPU (BASELINE.json config C2, contig-sharded; by default 4 x 64 Mb
-per GPU, in flight concurrently on one lps_ctx + host thread each, like the reference's omp-parallel contig loop).
-  value : reads/s with the read batch already resident in HBM (lps_batch_submit_device)
+One "step" = one pass of the whole hot path (allele calling -> overlap filter -> graph construction + edge fold ->
+edgeConnectResult sweep -> read correction) over the contigs of this GPU.
+
+Workloads (longphase-s_b200/workloads.py; BASELINE.json config C2, "phase SNP+indel whole-genome ... contig-sharded 1/2/4/8 B200"):
+  --workload genome (default): 24 GRCh38-proportioned contigs, --genome-mb megabases in total, 30x ONT-like 20 kb reads.  The contigs
+      are dealt to the ranks by a greedy LPT partition of their read counts (shard.lpt_partition), so the total work is FIXED as the
+      number of GPUs grows: "scaling": "strong".  The whole 3.1 Gb genome does not fit one GPU next to its scratch (165 GB of reads),
+      so the default is the half-scale genome (1536 Mb, chr1 = 124 Mb ... chr21 = 23 Mb): the largest single-GPU configuration.
+  --workload weak: --contigs-per-gpu equal contigs of --contig-mb per GPU (round 1's shape), "scaling": "weak".
+  value : reads/s with every read batch already resident in HBM (lps_batch_submit_device, 16-bit CIGAR stream)
   e2e   : reads/s through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region
-  roofline : the dominant kernel (k_call_alleles) against the measured HBM copy peak
+  roofline / rooflines : the dominant kernel (k_call_alleles) and the other kernels against the measured HBM copy peak
   cpu_baseline / --impl reference : the unmodified reference (oracle/_ref) on the host cores
-Launch: `python bench.py --gpus 1` or torchrun for N > 1 (one rank per GPU, contigs are independent:
-no collective on the data path; NCCL is only used for the barrier and the max-over-ranks of the time).
+Before a value is printed the phase result of EVERY contig of every rank is digested (workloads.phase_digest) and compared with
+the committed digest of the CPU checker for that contig (tests/golden/bench_digests.json); a mismatch aborts the run.
+Launch: `python bench.py --gpus 1` or torchrun for N > 1 (one rank per GPU, contigs are independent: no collective on the data
+path; NCCL is only used for the barrier and the max-over-ranks of the time).
 """
 import argparse
 import ctypes as C
@@ -27,17 +35,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-WORKLOAD = ("C2 shard: phase SNP+indel, {n} x {mb} Mb contigs per GPU ({tot} Mb), {depth:g}x ONT-like "
-            "{kb:g} kb reads, 1 het variant / {sp:g} bp (10% indels), ONT error model")
+METRIC = "phase_hot_path_reads_per_s"
 
 
-def synth_kwargs(args, seed, scale=1.0):
-    return dict(seed=seed, contig_len=int(args.contig_mb * 1_000_000 * scale), indel_frac=0.1, depth=args.depth, mean_len=args.mean_len,
-                variant_rate=1.0 / args.variant_spacing)
+def workload_text(args, world, n_contigs_rank0):
+    if args.workload == "genome":
+        return ("C2 whole-genome shape at %.0f Mb: phase SNP+indel over 24 GRCh38-proportioned contigs (%.1f .. %.1f Mb), %gx ONT-like %g kb reads, "
+                "1 het variant / %g bp (10%% indels), ONT error model; contigs dealt to %d GPU(s) by LPT on read counts (%d on rank 0)"
+                % (args.genome_mb, args.genome_mb * 46.71 / 3088.27, args.genome_mb * 248.96 / 3088.27, args.depth, args.mean_len / 1e3,
+                   args.variant_spacing, world, n_contigs_rank0))
+    return ("C2 shard: phase SNP+indel, %d x %g Mb contigs per GPU (%g Mb), %gx ONT-like %g kb reads, 1 het variant / %g bp (10%% indels), "
+            "ONT error model" % (args.contigs_per_gpu, args.contig_mb, args.contigs_per_gpu * args.contig_mb, args.depth, args.mean_len / 1e3,
+                                 args.variant_spacing))
 
 
 def algorithmic_bytes_k1(contig, status, n_calls):
-    """SURVEY.md §8d: B1 = sum_reads (16 + 4 n_cigar) + 18 n_calls; reads rejected by the flag/MAPQ filter
+    """SURVEY.md 8d: B1 = sum_reads (16 + 4 n_cigar) + 18 n_calls; reads rejected by the flag/MAPQ filter
     are never walked, so only their 16-byte record counts."""
     walked = status != 2
     return int(16 * contig.n_reads + 4 * int(contig.n_cigar[walked].sum()) + 18 * n_calls)
@@ -60,7 +73,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.4)
+            time.sleep(0.2)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -82,61 +95,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def run_reference_cpu(args, n_threads, sample_mb):
-    """The UNMODIFIED reference (oracle/_ref/libref_tap.so: get_snp, filterSNP, Clip, addEdge, edgeConnectResult,
-    readCorrection, exportResult) on one bounded sample contig, every host thread running its own replica —
-    the reference parallelises over contigs the same way (PhasingProcess.cpp:113)."""
+def run_reference_cpu(args, n_threads, rounds, warmup):
+    """The UNMODIFIED reference (oracle/_ref/libref_tap.so: BamParser::get_snp over every record, SnpParser::filterSNP, Clip,
+    VairiantGraph::addEdge, edgeConnectResult, readCorrection, exportResult) on one contig of the workload (the contig the GPU arm
+    phases first in the weak shape), every host thread running its own replica - the reference parallelises over contigs the same
+    way (PhasingProcess.cpp:113).  The time of a replica is the sum of the seconds spent INSIDE the reference's own calls (the tap's
+    timing mode: nothing is flattened or copied for the caller); a round's throughput is replicas x reads / mean replica time.
+    Falls back to the C restatement under oracle/ when the reference library is absent."""
     from oracle import pyoracle as po
     synth = importlib.import_module("longphase_s_b200.synth")
     ffi = importlib.import_module("longphase_s_b200._ffi")
-    kw = synth_kwargs(args, 1000)
-    kw["contig_len"] = int(sample_mb * 1_000_000)
-    contig = synth.Contig(**kw)
+    wl = importlib.import_module("longphase_s_b200.workloads")
+    contig = synth.Contig(**wl.phase_kwargs(wl.weak_seed(0, 0), args.contig_mb, args.depth, args.mean_len, args.variant_spacing))
     params = ffi.default_phase_params(True)
-    if not po.tap_available():
-        kind = "port"
-        runner = lambda: po.OraclePhase(contig, params)  # noqa: E731
-    else:
-        kind = "reference"
-        runner = lambda: po.ReferencePhase(contig, params)  # noqa: E731
-    calls = []
-
-    def work():
-        r = runner()
-        if kind == "reference":
-            calls.append(int(r.stage_a["off"][-1]))
-        else:
-            calls.append(len(r.calls))
+    kind = "reference" if po.tap_available() else "port"
 
     def one_round():
-        ths = [threading.Thread(target=work) for _ in range(n_threads)]
+        secs, calls = [0.0] * n_threads, [0] * n_threads
+
+        def work(k):
+            if kind == "reference":
+                r = po.ReferencePhaseTimed(contig, params)
+                secs[k], calls[k] = r.seconds, r.n_calls
+            else:
+                t0 = time.perf_counter()
+                r = po.OraclePhase(contig, params)
+                secs[k], calls[k] = time.perf_counter() - t0, len(r.calls)
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
         t0 = time.perf_counter()
         for t in ths:
             t.start()
         for t in ths:
             t.join()
-        return time.perf_counter() - t0
+        return float(np.mean(secs)), time.perf_counter() - t0, calls[0]
 
-    times = []
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_round()
-    for _ in range(args.steps):
-        times.append(one_round())
-    dt = float(np.mean(times))
-    reads = contig.n_reads * n_threads
-    return dict(value=reads / dt, unit="reads/s", cores=n_threads, kind=kind,
-                sample=f"{n_threads} replicas of one {sample_mb} Mb contig ({contig.n_reads} reads each), "
-                       f"{dt:.2f} s per round, {args.steps} rounds",
-                allele_calls_per_s=(calls[0] * n_threads / dt) if calls else None, ms_per_step=dt * 1e3)
+    res = [one_round() for _ in range(max(1, rounds))]
+    per = [contig.n_reads * n_threads / r[0] for r in res]
+    value = float(np.mean(per))
+    mean_s = float(np.mean([r[0] for r in res]))
+    spread = 100.0 * (max(per) - min(per)) / value if value else 0.0
+    return dict(value=value, unit="reads/s", cores=n_threads, kind=kind,
+                sample="%d replicas of one %g Mb contig of the workload (%d reads each), %.1f s inside the reference's calls per replica, %d round(s), "
+                       "spread %.1f%%" % (n_threads, args.contig_mb, contig.n_reads, mean_s, len(res), spread),
+                allele_calls_per_s=res[0][2] * n_threads / mean_s, ms_per_step=1e3 * float(np.mean([r[1] for r in res])), spread_pct=spread)
 
 
 def bench_bgzf(ctx, host, ffi, torch, ncores, args, mb=1024):
-    """SURVEY §8f rank 1: inflation of BGZF blocks (htslib bgzf_read_block / inflate_block).  BAM-like synthetic bytes, deflated
+    """SURVEY 8f rank 1: inflation of BGZF blocks (htslib bgzf_read_block / inflate_block).  BAM-like synthetic bytes, deflated
     by zlib level 6 in 65280-byte members like htslib writes them; kernel-resident, end-to-end (host in, host out) and zlib on all
     host cores (what the reference's htslib build calls) on the same members."""
     import zlib
     from concurrent.futures import ThreadPoolExecutor
-    sys.path.insert(0, ROOT)
     from tests import bgzf_cases
     rng = np.random.default_rng(1)
     unit = bgzf_cases.bam_like(rng, 8 << 20)
@@ -155,12 +166,6 @@ def bench_bgzf(ctx, host, ffi, torch, ncores, args, mb=1024):
             raise RuntimeError(ctx.lib.lps_last_error(ctx.h).decode())
         ms.append(ctx.stats()["ms_kernel_bgzf"])
     k_ms = float(np.mean(ms[args.warmup:]))
-    os.environ["LPS_BGZF_SPECULATE"] = "0"           # A/B: the plain decoder (one table lookup per symbol)
-    ms0 = []
-    for _ in range(3):
-        ctx.lib.lps_bgzf_inflate_device(ctx.h, d_data.data_ptr(), d_blocks.data_ptr(), len(blocks), d_out.data_ptr())
-        ms0.append(ctx.stats()["ms_kernel_bgzf"])
-    del os.environ["LPS_BGZF_SPECULATE"]
     got = d_out[:len(unit)].cpu().numpy().tobytes()
     assert got == unit, "device inflation differs from the input text"
     pin_in = torch.from_numpy(data.copy()).pin_memory()
@@ -175,8 +180,8 @@ def bench_bgzf(ctx, host, ffi, torch, ncores, args, mb=1024):
             raise RuntimeError(ctx.lib.lps_last_error(ctx.h).decode())
         e2e.append((time.perf_counter() - t0) * 1e3)
     e2e_ms = float(np.mean(e2e[2:]))
-    # CPU: zlib inflate of the same members on every host core (a bounded sample: one pass over `unit`'s members per thread)
     raw = [m[18:-8] for m in members]
+
     def cpu_pass(_):
         n = 0
         for r in raw:
@@ -186,12 +191,9 @@ def bench_bgzf(ctx, host, ffi, torch, ncores, args, mb=1024):
         t0 = time.perf_counter()
         done = sum(tp.map(cpu_pass, range(ncores)))
         cpu_s = time.perf_counter() - t0
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     alg = len(data) + out_bytes
     return {"config": "%d MB of BAM-like bytes in %d BGZF members (zlib level 6, 65280 bytes each), ratio %.2f" % (out_bytes >> 20, len(blocks), out_bytes / len(data)),
-            "kernel_ms": k_ms, "kernel_ms_plain_decoder": float(np.mean(ms0[1:])), "out_gb_per_s": out_bytes / (k_ms * 1e-3) / 1e9, "algorithmic_bytes": alg,
-            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
-                         "note": "compressed bytes read + inflated bytes written; the kernel is bound by the serial Huffman chain of each block, not by HBM"},
+            "kernel_ms": k_ms, "out_gb_per_s": out_bytes / (k_ms * 1e-3) / 1e9, "algorithmic_bytes": alg,
             "e2e_ms": e2e_ms, "e2e_out_gb_per_s": out_bytes / (e2e_ms * 1e-3) / 1e9, "h2d_bytes": int(len(data)), "d2h_bytes": int(out_bytes),
             "cpu_zlib_out_gb_per_s": done / cpu_s / 1e9, "cpu_cores": ncores, "cpu_sample": "%d MB inflated per core, python zlib (libz inflate, GIL released)" % (len(unit) >> 20)}
 
@@ -202,17 +204,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--contig-mb", type=float, default=64.0)
-    ap.add_argument("--contigs-per-gpu", type=int, default=8)       # in flight per GPU; capped by this rank's share of the host cores
-    ap.add_argument("--cpu-sample-mb", type=float, default=8.0)
+    ap.add_argument("--workload", default="genome", choices=["genome", "weak"])
+    ap.add_argument("--genome-mb", type=float, default=1536.0)
+    ap.add_argument("--contig-mb", type=float, default=64.0)            # weak shape; also the contig of the CPU reference arm
+    ap.add_argument("--contigs-per-gpu", type=int, default=8)          # weak shape
+    ap.add_argument("--threads", type=int, default=0)                  # host threads per rank driving the contigs; 0: min(contigs, cores / ranks, 8)
     ap.add_argument("--depth", type=float, default=30.0)               # C5 stress: --depth 120 --mean-len 50000 --variant-spacing 300
     ap.add_argument("--mean-len", type=float, default=20000.0)
     ap.add_argument("--variant-spacing", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
-    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])   # yield: waits give the core away, contigs in flight are not capped by the cores
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])
     ap.add_argument("--cigar32", action="store_true")    # end-to-end leg: send BAM's uint32 CIGAR ops instead of the compact 16-bit stream
-    ap.add_argument("--unequal", type=int, default=0)   # 1: contig sizes +-25 % around --contig-mb (the largest one then bounds the step)
+    ap.add_argument("--allow-unpinned", action="store_true")   # run contigs that have no committed digest (custom shapes); the line says so
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -227,18 +232,19 @@ def main():
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     entry.load_package()
+    wl = importlib.import_module("longphase_s_b200.workloads")
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         os.environ["OMP_NUM_THREADS"] = str(ncores)
-        res = run_reference_cpu(args, min(ncores, 64), args.cpu_sample_mb)
-        line = {"impl": "reference", "metric": "phase_hot_path_reads_per_s", "value": res["value"], "unit": "reads/s",
+        res = run_reference_cpu(args, min(ncores, 64), args.steps, min(args.warmup, 1))
+        n0 = len(wl.genome_partition(args.genome_mb, max(1, args.gpus))[0]) if args.workload == "genome" else args.contigs_per_gpu
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "reads/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
-                "allele_calls_per_s": res["allele_calls_per_s"],
-                "config": {"workload": WORKLOAD.format(n=args.contigs_per_gpu, mb=args.contig_mb, tot=args.contigs_per_gpu * args.contig_mb, depth=args.depth, kb=args.mean_len / 1e3, sp=args.variant_spacing),
-                           "sample": res["sample"]},
+                "higher_is_better": True, "scaling": "strong" if args.workload == "genome" else "weak", "vs_baseline": None, "dtype": "int32/f32",
+                "data": "synthetic", "allele_calls_per_s": res["allele_calls_per_s"],
+                "config": {"workload": workload_text(args, max(1, args.gpus), n0), "sample": res["sample"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         json_out.write(json.dumps(line) + "\n")
@@ -249,85 +255,79 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    ffi0 = importlib.import_module("longphase_s_b200._ffi")
-    # "auto": spin while every contig in flight has a host core of its own; with fewer cores (8 ranks on a 32-core box) keep all the
-    # contigs in flight anyway and let waiting threads yield their core.  Measured on 8 GPUs / 32 cores: 4 contigs per rank
-    # spinning 359.6 M reads/s, 8 per rank yielding 433.7 M; blocking waits double the step (21.1 vs 9.8 ms).  On 1 GPU / 16 cores
-    # spinning wins (80.3 M against 69.6 M with 8 yielding threads).
+    ffi = importlib.import_module("longphase_s_b200._ffi")
+    # ---- this rank's contigs ----
+    if args.workload == "genome":
+        mine = wl.genome_partition(args.genome_mb, world)[rank]          # [(name, seed, mb)], heaviest first
+        specs = [(name, wl.phase_kwargs(seed, mb, args.depth, args.mean_len, args.variant_spacing)) for name, seed, mb in mine]
+    else:
+        specs = [("w%d_%d" % (rank, i), wl.phase_kwargs(wl.weak_seed(rank, i), args.contig_mb, args.depth, args.mean_len, args.variant_spacing))
+                 for i in range(args.contigs_per_gpu)]
+    n_ctg = len(specs)
+    T_ = args.threads if args.threads > 0 else max(1, min(n_ctg, max(1, ncores // world), 8))
+    # waiting host threads spin while each has a core of its own, otherwise they yield it
     if args.sync == "auto":
-        args.sync = "yield" if ncores // world < args.contigs_per_gpu else "spin"
+        args.sync = "yield" if ncores // world < T_ else "spin"
     blocking = args.sync == "block"
     if blocking or args.sync == "yield":
-        ffi0.load_library().lps_set_blocking_sync(local_rank, 1 if blocking else 2)
+        ffi.load_library().lps_set_blocking_sync(local_rank, 1 if blocking else 2)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     synth_mod = importlib.import_module("longphase_s_b200.synth")
     host = importlib.import_module("longphase_s_b200.host")
-    ffi = importlib.import_module("longphase_s_b200._ffi")
-
     from concurrent.futures import ThreadPoolExecutor
-    # contigs in flight per GPU: each needs a host thread, so never more than this rank's share of the host cores
-    C_ = max(1, args.contigs_per_gpu if args.sync == "yield" else min(args.contigs_per_gpu, ncores // world))
+
     t_gen = time.time()
-    # unequal contigs (a genome's are): same total, +-25 % around --contig-mb
-    shape = [1.25, 0.9, 1.1, 0.75] if args.unequal and C_ % 4 == 0 else [1.0]
-    contigs = [synth_mod.Contig(**synth_kwargs(args, 100 + 16 * rank + i, shape[i % len(shape)])) for i in range(C_)]
+    contigs = [synth_mod.Contig(**kw) for _, kw in specs]
     t_gen = time.time() - t_gen
+    digests = wl.load_digests()
+    want = [digests.get(wl.key_of(kw)) for _, kw in specs]
+    if any(w is None for w in want) and not args.allow_unpinned:
+        raise SystemExit("bench.py: no committed digest for %s; run tools/make_bench_digests.py for this shape or pass --allow-unpinned"
+                         % [n for (n, _), w in zip(specs, want) if w is None])
     params = ffi.default_phase_params(True)
-    # one context (own stream, own scratch) per contig in flight, driven by its own host thread: the reference runs its contig
-    # loop the same way (`#pragma omp parallel for`, PhasingProcess.cpp:113), and the host parts of one contig (overlap filter,
-    # edgeConnectResult chain) overlap the kernels of the others
-    ctxs = [host.Context(local_rank) for _ in range(C_)]
+    # one context (own stream, own scratch, resident reference + variant table) per contig, like a job that keeps every contig of
+    # its shard on the device; T_ host threads drive them, each its own share, heaviest first (the reference runs its contig loop
+    # the same way: `#pragma omp parallel for schedule(dynamic)`, PhasingProcess.cpp:113)
+    ctxs = [host.Context(local_rank) for _ in range(n_ctg)]
     keep = []
     for ctx, contig in zip(ctxs, contigs):
         ctx.set_reference(contig.ref)
         vs = contig.variants_struct()
         keep.append(vs)
         ctx.set_variants(vs, True)
+    share = [list(range(t, n_ctg, T_)) for t in range(T_)]
 
-    # ---- device-resident copy of every batch (torch owns the memory) ----
+    # ---- device-resident copy of every batch (torch owns the memory): the 16-bit CIGAR stream + its side table, SEQ, QUAL, records ----
     def dev(a):
         view = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}.get(a.dtype)
         return torch.from_numpy(a.view(view) if view else a).cuda()
 
-    names = ["ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "cigar", "seq4", "qual"]
+    names = ["ref_start", "l_qseq", "n_cigar", "cigar_off", "seq_off", "qual_off", "flag", "mapq", "name_rank", "seq4", "qual"]
     ptypes = dict(ref_start=ffi.i32p, l_qseq=ffi.i32p, n_cigar=ffi.u32p, cigar_off=ffi.u64p, seq_off=ffi.u64p, qual_off=ffi.u64p,
                   flag=ffi.u16p, mapq=ffi.u8p, name_rank=ffi.i32p, cigar=ffi.u32p, seq4=ffi.u8p, qual=ffi.u8p)
+    packed = [c.pack_cigar16() for c in contigs]
 
-    def batch_from(contig, ptr_of):
-        return ffi.LpsReadBatch(n_reads=contig.n_reads, cigar_len=len(contig.cigar), seq_bytes=len(contig.seq4),
-                                qual_bytes=len(contig.qual), **{k: C.cast(ptr_of(k), ptypes[k]) for k in names})
+    def batch_from(contig, ptr_of, pk):
+        b = ffi.LpsReadBatch(n_reads=contig.n_reads, cigar_len=len(contig.cigar), seq_bytes=len(contig.seq4), qual_bytes=len(contig.qual),
+                             **{k: C.cast(ptr_of(k), ptypes[k]) for k in names})
+        b.cigar16 = C.cast(ptr_of("cigar16"), ffi.u16p)
+        b.n_cigar_long = len(pk[1])
+        if len(pk[1]):
+            b.cigar_long_len = C.cast(ptr_of("cigar_long_len"), ffi.u32p)
+            b.cigar_long_at = C.cast(ptr_of("cigar_long_at"), ffi.u64p)
+        return b
 
-    dtens = [{k: dev(getattr(c, k)) for k in names} for c in contigs]
-    dev_batches = [batch_from(c, lambda k, d=d: d[k].data_ptr()) for c, d in zip(contigs, dtens)]
-    # ---- pinned host copies for the end-to-end leg ----
-    # The host loop packs the CIGAR ops of every record into the compact 16-bit wire format while it appends the record to the
-    # batch (lps_pack_cigar16; include/lps.h): the pinned batch of the end-to-end leg holds that stream, not the uint32 ops.
-    e2e_names = list(names)
-    packed = None
-    if not args.cigar32:
-        packed = [c.pack_cigar16() for c in contigs]
-        e2e_names.remove("cigar")
-    ptens = [{k: torch.from_numpy(getattr(c, k).view(np.uint8).reshape(-1)).pin_memory() for k in e2e_names} for c in contigs]
-    pin_batches = []
-    for i, (c, d) in enumerate(zip(contigs, ptens)):
-        if packed is None:
-            pin_batches.append(batch_from(c, lambda k, d=d: d[k].data_ptr()))
-            continue
-        c16, long_len, long_at = packed[i]
-        d["cigar16"] = torch.from_numpy(c16.view(np.uint8)).pin_memory()
-        d["cigar_long_len"] = torch.from_numpy(np.ascontiguousarray(long_len).view(np.uint8)).pin_memory()
-        d["cigar_long_at"] = torch.from_numpy(np.ascontiguousarray(long_at).view(np.uint8)).pin_memory()
-        b = batch_from(c, lambda k, d=d: d[k].data_ptr() if k != "cigar" else None)
-        b.cigar16 = C.cast(d["cigar16"].data_ptr(), ffi.u16p)
-        b.n_cigar_long = len(long_len)
-        if len(long_len):
-            b.cigar_long_len = C.cast(d["cigar_long_len"].data_ptr(), ffi.u32p)
-            b.cigar_long_at = C.cast(d["cigar_long_at"].data_ptr(), ffi.u64p)
-        pin_batches.append(b)
-    host_bytes = int(sum(t.numel() for d in ptens for t in d.values()))
-    input_bytes = host_bytes
+    dtens, dev_batches = [], []
+    for c, pk in zip(contigs, packed):
+        d = {k: dev(getattr(c, k)) for k in names}
+        d["cigar16"] = dev(pk[0])
+        d["cigar_long_len"] = dev(np.ascontiguousarray(pk[1])) if len(pk[1]) else None
+        d["cigar_long_at"] = dev(np.ascontiguousarray(pk[2])) if len(pk[2]) else None
+        dtens.append(d)
+        dev_batches.append(batch_from(c, lambda k, d=d: d[k].data_ptr() if d.get(k) is not None else None, pk))
+    resident_bytes = int(sum(t.numel() * t.element_size() for d in dtens for t in d.values() if t is not None))
     n_reads_gpu = int(sum(c.n_reads for c in contigs))
 
     def barrier():
@@ -345,177 +345,251 @@ def main():
 
     max_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MAX if world > 1 else None)  # noqa: E731
     sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM if world > 1 else None)  # noqa: E731
+    min_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MIN if world > 1 else None)  # noqa: E731
 
-    pool = ThreadPoolExecutor(max_workers=C_)
+    pool = ThreadPoolExecutor(max_workers=T_)
+    results = [None] * n_ctg
 
-    def run_all(fn):
-        return [f.result() for f in [pool.submit(fn, i) for i in range(C_)]]
+    def run_threads(fn, steps):
+        """Every host thread runs `steps` passes over its share of the contigs back to back (no barrier between steps or contigs: the
+        host parts of one contig overlap the kernels of the others); the last pass keeps the results."""
+        def body(t):
+            for k in range(steps):
+                for i in share[t]:
+                    r = fn(i, k == steps - 1)
+                    if r is not None:
+                        results[i] = r
+        for f in [pool.submit(body, t) for t in range(T_)]:
+            f.result()
 
-    # `last`: only the final pass of a timed region turns the result into numpy arrays (Python work under the GIL, serialised over
-    # the host threads of a rank); every pass brings the result to host memory inside lps_phase_solve
-    def step_resident(i, last=True):
+    def step_resident(i, last):
         return ctxs[i].phase_contig(params, copy=last)      # the batch was registered once with lps_batch_submit_device (no copy)
 
-    def step_e2e(i, last=True):
-        ctxs[i].submit(pin_batches[i])
-        return ctxs[i].phase_contig(params, copy=last)
-
     def timed(fn, steps, slot):
-        """`steps` passes over all contigs of this GPU; device time between the events of every context's stream, max over them."""
+        """device time between the events of every context's stream (the streams the kernels run on), max over them"""
         barrier()
         for ctx in ctxs:
             ctx.event_record(slot)
         t0 = time.perf_counter()
-        # every host thread runs its `steps` passes back to back, with no barrier between steps: like the reference's contig loop,
-        # the threads drift out of lockstep, so the host phases of one contig overlap the kernels of another
-        out = run_all(lambda i: [fn(i, k == steps - 1) for k in range(steps)][-1])
+        run_threads(fn, steps)
         for ctx in ctxs:
             ctx.event_record(slot + 1)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        return max(ctx.event_elapsed_ms(slot, slot + 1) for ctx in ctxs) / steps, wall / steps, out
+        return max(ctx.event_elapsed_ms(slot, slot + 1) for ctx in ctxs) / steps, wall / steps
 
     # ---- kernel-resident leg ----
-    for i in range(C_):
+    for i in range(n_ctg):
         ctxs[i].submit_device(dev_batches[i])
-    for _ in range(args.warmup):
-        run_all(step_resident)
+    if args.warmup:
+        run_threads(step_resident, args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()    # the JSON line is rank 0's: only its GPU is sampled (every nvidia-smi call costs host CPU)
     s0 = [ctx.stats() for ctx in ctxs]
-    dev_ms, wall_ms, res = timed(step_resident, args.steps, 0)
+    dev_ms, wall_ms = timed(step_resident, args.steps, 0)
     s1 = [ctx.stats() for ctx in ctxs]
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(dev_ms)
     launches = int(sum(b_["kernel_launches"] - a_["kernel_launches"] for a_, b_ in zip(s0, s1)))
-    stage_keys = ("ms_call_alleles", "ms_build_edges", "ms_read_correction", "ms_wall_call_alleles", "ms_wall_build_edges", "ms_wall_solve",
-                  "ms_host_filters", "ms_host_sweep", "ms_kernel_fold_edges", "ms_sweep")
+    stage_keys = ("ms_call_alleles", "ms_build_edges", "ms_sweep", "ms_read_correction", "ms_wall_call_alleles", "ms_wall_build_edges",
+                  "ms_host_filters", "ms_host_sweep", "ms_kernel_call_alleles", "ms_kernel_fold_edges")
     stage = {k[3:]: float(np.mean([st[k] for st in s1])) for k in stage_keys}
     stage["sweep_fallbacks"] = int(sum(b_["sweep_fallbacks"] - a_["sweep_fallbacks"] for a_, b_ in zip(s0, s1)))
     stage["slow_path_contigs"] = int(sum(b_["slow_path_contigs"] - a_["slow_path_contigs"] for a_, b_ in zip(s0, s1)))
+    res_resident = list(results)
 
-    # ---- the dominant kernel timed alone (one context, nothing else on the GPU): roofline ----
-    ctx0, contig0 = ctxs[0], contigs[0]
-    calls = ctx0.call_alleles(params, want_host=True)
-    n_calls0 = calls["n_calls"]
-    b1 = algorithmic_bytes_k1(contig0, calls["read_status"], n_calls0)
-    k1_ms = []
-    for _ in range(max(args.steps, 5)):
-        ctx0.call_alleles(params, want_host=False)
-        k1_ms.append(ctx0.stats()["ms_kernel_call_alleles"])
-    k1 = float(np.mean(k1_ms))
+    # ---- parity gate: the digest of every contig's result against the committed digest of the CPU checker ----
+    def digest_ok(res_list):
+        ok, checked = True, 0
+        for r, w in zip(res_list, want):
+            if w is None:
+                continue
+            checked += 1
+            ok = ok and wl.phase_digest(r["ps"], r["hap_ref"], r["read_hp"], r["hp_counts"]) == w["digest"]
+        return ok, checked
+    ok_resident, n_checked = digest_ok(res_resident)
+    if min_over_ranks(1.0 if ok_resident else 0.0) < 1.0:
+        raise SystemExit("bench.py: the phase result of a timed contig differs from the committed digest of the CPU checker: no value is reported")
+
+    # ---- the kernels timed alone (one context, nothing else on the GPU): rooflines ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy; the kernel is timed alone)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = b1 / (k1 * 1e-3) / 1e9 if k1 > 0 else 0.0
+    big = int(np.argmax([c.n_reads for c in contigs]))
+    ctx0, contig0 = ctxs[big], contigs[big]
+    calls = ctx0.call_alleles(params, want_host=True)
+    n_calls0 = int(calls["n_calls"])
+    b1 = algorithmic_bytes_k1(contig0, calls["read_status"], n_calls0)
+    k1_ms, fold_ms = [], []
+    for _ in range(max(args.steps, 5)):
+        ctx0.call_alleles(params, want_host=False)
+        k1_ms.append(ctx0.stats()["ms_kernel_call_alleles"])
+    edges = None
+    for _ in range(3):
+        ctx0.call_alleles(params, want_host=False)
+        edges = ctx0.build_edges(params, want_host=False)
+        fold_ms.append(ctx0.stats()["ms_kernel_fold_edges"])
+    k1, kf = float(np.mean(k1_ms)), float(np.mean(fold_ms))
+    # 8d: B2 = 24 n_contrib + 16 n_cells, cells = node x successor-in-window pairs the fold writes (4 floats each)
+    n_cells = int(edges["n_nodes"]) * int(edges["window"])
+    b2 = 24 * int(edges["n_contrib"]) + 16 * n_cells
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_k1_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("contig_mb") == args.contig_mb and tj.get("reads") == contig0.n_reads:
+        if tj.get("reads") == contig0.n_reads:
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    achieved = b1 / (k1 * 1e-3) / 1e9 if k1 > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1,
+                "peak_source": peak_src + " (of measured)", "launch": "the largest contig of rank 0 (%d reads, %d allele calls), timed alone" % (contig0.n_reads, n_calls0),
+                "note": "algorithmic bytes follow SURVEY 8d (4 bytes per CIGAR op); the kernel reads the stream in 16 bits per op, so its "
+                        "DRAM traffic is below the algorithmic figure, and it is bound by instruction issue / latency, not by HBM (profiles/)"}
+    rooflines = [dict(roofline), {"bound": "hbm", "kernel": "k_fold_edges", "achieved": b2 / (kf * 1e-3) / 1e9 if kf > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                   "frac": (b2 / (kf * 1e-3) / 1e9 / peak) if kf > 0 else 0.0, "algorithmic_bytes_per_launch": b2, "kernel_ms": kf,
+                                   "note": "24 B per pair contribution + 16 B per (node, successor) cell; the ordered float fold is bound by issue, not by HBM"}]
+    ctxs[big].submit_device(dev_batches[big])
 
     # ---- end-to-end leg: pinned host buffers through the C ABI ----
-    for _ in range(min(args.warmup, 2)):
-        run_all(step_e2e)
-    s2 = [ctx.stats() for ctx in ctxs]
-    e2e_dev_ms, e2e_wall_ms, res_e2e = timed(step_e2e, args.steps, 2)
-    e2e_ms = max_over_ranks(e2e_dev_ms)
-    s3 = [ctx.stats() for ctx in ctxs]
-    d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
-    h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
-    for ra, rb in zip(res, res_e2e):
-        for k in ("ps", "hap_ref", "read_hp"):
-            assert np.array_equal(ra[k], rb[k]), "resident and end-to-end legs disagree"
-    # allele calls of every contig (one extra pass, outside the timed regions)
+    e2e = None
+    if not args.no_e2e:
+        # The host loop packs the CIGAR ops of every record into the compact 16-bit wire format while it appends the record to the
+        # batch (lps_pack_cigar16; include/lps.h).  The big streams are pinned in place (cudaHostRegister), the small ones copied.
+        cudart = torch.cuda.cudart()
+        pinned_in_place, ptens, pin_batches = [], [], []
+
+        def pin(a):
+            a = np.ascontiguousarray(a)
+            if a.nbytes >= (1 << 20):
+                rc = cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+                if int(rc) == 0:
+                    pinned_in_place.append(a)
+                    return a, a.ctypes.data
+            t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+            return t, t.data_ptr()
+        for c, pk in zip(contigs, packed):
+            d, ptr = {}, {}
+            for k in names:
+                d[k], ptr[k] = pin(getattr(c, k))
+            if args.cigar32:
+                d["cigar"], ptr["cigar"] = pin(c.cigar)
+                b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
+                                     **{k: C.cast(ptr[k], ptypes[k]) for k in names + ["cigar"]})
+            else:
+                d["cigar16"], ptr["cigar16"] = pin(pk[0])
+                if len(pk[1]):
+                    d["cigar_long_len"], ptr["cigar_long_len"] = pin(pk[1])
+                    d["cigar_long_at"], ptr["cigar_long_at"] = pin(pk[2])
+                b = batch_from(c, lambda k, ptr=ptr: ptr.get(k), pk)
+            ptens.append(d)
+            pin_batches.append(b)
+        host_bytes = int(sum((t.nbytes if isinstance(t, np.ndarray) else t.numel()) for d in ptens for t in d.values()))
+
+        def step_e2e(i, last):
+            ctxs[i].submit(pin_batches[i])
+            return ctxs[i].phase_contig(params, copy=last)
+        run_threads(step_e2e, min(args.warmup, 2))
+        s2 = [ctx.stats() for ctx in ctxs]
+        e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps, 2)
+        e2e_ms = max_over_ranks(e2e_dev_ms)
+        s3 = [ctx.stats() for ctx in ctxs]
+        d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+        h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+        ok_e2e, _ = digest_ok(results)
+        if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0:
+            raise SystemExit("bench.py: the end-to-end leg's result differs from the committed digest: no value is reported")
+        e2e = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes)
+        for i in range(n_ctg):
+            ctxs[i].submit_device(dev_batches[i])       # nothing refers to the host buffers any more
+        for a in pinned_in_place:
+            cudart.cudaHostUnregister(a.ctypes.data)
+
     calls_gpu = 0
-    for i in range(C_):
+    for i in range(n_ctg):
         ctxs[i].submit_device(dev_batches[i])
         calls_gpu += int(ctxs[i].call_alleles(params, want_host=False)["n_calls"])
-
     total_reads = sum_over_ranks(float(n_reads_gpu))
     total_calls = sum_over_ranks(float(calls_gpu))
+    max_reads = max_over_ranks(float(n_reads_gpu))
     line = {
-        "metric": "phase_hot_path_reads_per_s", "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
+        "metric": METRIC, "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
-        "allele_calls_per_s": total_calls / (ms_step * 1e-3),
-        "config": {"workload": WORKLOAD.format(n=C_, mb=args.contig_mb, tot=C_ * args.contig_mb, depth=args.depth, kb=args.mean_len / 1e3, sp=args.variant_spacing), "contigs_per_gpu": C_,
-                   "reads_per_gpu": n_reads_gpu, "variants_per_gpu": int(sum(c.n_var for c in contigs)), "allele_calls_per_gpu": calls_gpu,
-                   "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "input_bytes_per_gpu": input_bytes,
-                   "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (input_bytes / 1e9),
+        "scaling": "strong" if args.workload == "genome" else "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
+        "allele_calls_per_s": total_calls / (ms_step * 1e-3), "parity_digest_ok": True, "parity_digests_checked_rank0": n_checked,
+        "config": {"workload": workload_text(args, world, n_ctg), "contigs_rank0": n_ctg, "host_threads_per_rank": T_,
+                   "reads_total": int(total_reads), "reads_rank0": n_reads_gpu, "largest_rank_share_of_reads": max_reads / total_reads * world,
+                   "variants_rank0": int(sum(c.n_var for c in contigs)), "allele_calls_total": int(total_calls),
+                   "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "resident_bytes_rank0": resident_bytes,
+                   "l2": "inputs (%.1f GB on rank 0) are far larger than the 126 MB L2; no flush needed" % (resident_bytes / 1e9),
                    "host_sync": "blocking" if blocking else ("yield" if args.sync == "yield" else "spin"), "host_cores": ncores,
-                   "parallelism": f"contig-sharded x{world} GPUs, {C_} contigs in flight per GPU (one lps_ctx + host thread each), no collective",
+                   "parallelism": "contigs sharded over %d GPU(s) by LPT on read counts, one lps_ctx (stream + scratch) per contig, %d host thread(s) per "
+                                  "rank, no collective" % (world, T_),
                    "timing": "CUDA events on every context's stream (the streams the kernels run on), max over contexts and ranks",
                    "wall_ms_per_step_rank0": wall_ms, "synth_seconds": t_gen},
-        "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes,
-                "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
-                        "CIGAR and per-read records are copied; h2d bytes are the library's own count",
-                "cigar_wire_format": "uint32 (BAM)" if args.cigar32 else "16-bit compact stream (lps_pack_cigar16), widened on the device"},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1,
-                     "peak_source": peak_src, "launch": f"one {args.contig_mb} Mb contig ({contig0.n_reads} reads), timed alone"},
-        "stage_ms": dict(k_call_alleles_alone=k1, **stage),
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
+        "stage_ms": dict(k_call_alleles_alone=k1, k_fold_edges_alone=kf, **stage),
     }
+    if e2e is not None:
+        e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes = e2e
+        line["e2e"] = {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                       "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes, "parity_digest_ok": True,
+                       "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
+                               "CIGAR and per-read records are copied; h2d bytes are the library's own count",
+                       "cigar_wire_format": "uint32 (BAM), narrowed on the device" if args.cigar32 else "16-bit stream (lps_pack_cigar16), used as it arrives"}
     if rank == 0 and world == 1 and not args.no_other_paths:
         # ---- the other dialects of the hot path (BASELINE configs C3 / C4), kernel-resident device time of one call each ----
         other = {}
         try:
+            small = int(np.argmin([abs(c.n_reads - 99000) for c in contigs]))
+            cs, ctx_s = contigs[small], ctxs[small]
             tp = ffi.default_tag_params()
-            phased = contig0.phased(res[0]["ps"], res[0]["hap_ref"] == 1)
+            phased = cs.phased(res_resident[small]["ps"], res_resident[small]["hap_ref"] == 1)
             pv = phased.variants_struct()
-            ctx0.set_variants(pv, 0)
-            ctx0.submit_device(dev_batches[0])
+            ctx_s.set_variants(pv, 0)
+            ctx_s.submit_device(dev_batches[small])
             ms = []
             for _ in range(args.warmup + args.steps):
-                r_tag = ctx0.tag_reads(tp, want_calls=False)
-                ms.append(ctx0.stats()["ms_tag_reads"])
+                r_tag = ctx_s.tag_reads(tp, want_calls=False)
+                ms.append(ctx_s.stats()["ms_tag_reads"])
             ms = float(np.mean(ms[args.warmup:]))
-            other["haplotag"] = {"config": "C3: germline haplotag of one %.0f Mb contig with the phase set of this run" % args.contig_mb,
-                                 "reads_per_s": contig0.n_reads / (ms * 1e-3), "device_ms": ms, "alignments": contig0.n_reads,
+            other["haplotag"] = {"config": "C3: germline haplotag of one %.0f Mb contig with the phase set of this run" % (len(cs.ref) / 1e6),
+                                 "reads_per_s": cs.n_reads / (ms * 1e-3), "device_ms": ms, "alignments": cs.n_reads,
                                  "tagged": int((r_tag["hp"] != 0).sum())}
-            kw = synth_kwargs(args, 900)
-            kw.update(contig_len=int(min(args.contig_mb, 32.0) * 1_000_000), somatic_rate=3000.0 / 64e6, indel_frac=0.1)
-            kn, kt = dict(kw), dict(kw)
-            kn.update(depth=25.0, purity=0.0, read_seed=901)
-            kt.update(depth=50.0, purity=0.6, read_seed=902)
-            cn, ct = synth_mod.Contig(**kn), synth_mod.Contig(**kt)
-            un = cn.somatic_union(seed=9)
-            ut = un.with_reads_of(ct)
+            un, ut = wl.c4_pair(synth_mod, 32.0)
             sp = ffi.LpsTagParams(mapping_quality=20, mapq_filter=0, tag_supplementary=1, have_reference=1, percentage_threshold=0.6)
             for name, c, cls in (("extract_normal", un, host.ExtractNorDataChrProcessor), ("extract_tumor", ut, host.ExtractTumDataChrProcessor),
                                  ("somatic_tag", ut, host.SomaticHaplotagChrProcessor)):
-                proc = cls(ctx0, c, sp)
+                proc = cls(ctx_s, c, sp)
                 ms, wd = [], []
                 for _ in range(args.warmup + args.steps):
                     r_s = proc.processSingleChrom(c)
-                    st = ctx0.stats()
+                    st = ctx_s.stats()
                     ms.append(st["ms_tag_reads"]); wd.append(st["ms_kernel_window_diff"])
                 ms = float(np.mean(ms[args.warmup:]))
                 other[name] = {"reads_per_s": c.n_reads / (ms * 1e-3), "device_ms": ms, "alignments": c.n_reads, "tumor_positions": int(r_s["n_tum"])}
                 if name == "extract_tumor":
                     wdm = float(np.mean(wd[args.warmup:]))
-                    # SURVEY §8d: 250 B of SEQ / reference / CIGAR + 8 B of histogram update per (tumor position, alignment) pair
-                    other[name].update(window_items=r_s["n_window_items"], k_window_diff_ms=wdm,
-                                       k_window_diff_gbs=258.0 * r_s["n_window_items"] / (wdm * 1e-3) / 1e9 if wdm > 0 else None)
-            other["somatic_config"] = "C4 shard: tumor 50x (purity 0.6) / normal 25x pair of one %.0f Mb contig, ~%d somatic SNV+indel, union map of %d positions" % (
-                kw["contig_len"] / 1e6, int(un.var_is_somatic.sum()), un.n_var)
+                    # SURVEY 8d: 250 B of SEQ / reference / CIGAR + 8 B of histogram update per (tumor position, alignment) pair
+                    gbs = 258.0 * r_s["n_window_items"] / (wdm * 1e-3) / 1e9 if wdm > 0 else None
+                    other[name].update(window_items=r_s["n_window_items"], k_window_diff_ms=wdm, k_window_diff_gbs=gbs)
+                    if gbs:
+                        line["rooflines"].append({"bound": "hbm", "kernel": "k_window_diff", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                                  "algorithmic_bytes_per_launch": int(258 * r_s["n_window_items"]), "kernel_ms": wdm})
+            other["somatic_config"] = "C4 shard: tumor 50x (purity 0.6) / normal 25x pair of one 32 Mb contig, ~%d somatic SNV+indel, union map of %d positions" % (
+                int(un.var_is_somatic.sum()), un.n_var)
         except Exception as e:  # secondary numbers: never fail the headline line
             other["error"] = repr(e)
         try:
-            other["bgzf_inflate"] = bench_bgzf(ctx0, host, ffi, torch, ncores, args)
+            other["bgzf_inflate"] = bench_bgzf(ctxs[0], host, ffi, torch, ncores, args)
         except Exception as e:
             other["bgzf_inflate"] = {"error": repr(e)}
         line["other_paths"] = other
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cb = run_reference_cpu(args, min(ncores, 64), args.cpu_sample_mb)
+            cb = run_reference_cpu(args, min(ncores, 64), 1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}

@@ -600,16 +600,17 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
             // ---- clips (S/H longer than 5) and unsupported ops: op codes with bit 2 or 3 set (S H P = X and 9..15).  Only the pairs
             // that hold such a code are looked at; the reference position of a clip is summed up on demand (clips are rare). ----
             if (__any_sync(FULL, ((acc | (acc >> 16)) & 0xCu) != 0)) {
+                unsigned pairs = 0u;                       // bit j: pair j of this lane holds an op code >= 4
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const unsigned x2 = w[j];
-                    if ((x2 & 0x000C000Cu) == 0u) continue;
-#pragma unroll
+                for (int j = 0; j < 8; j++) pairs |= ((w[j] & 0x000C000Cu) != 0u ? 1u : 0u) << j;
+                while (pairs) {
+                    const int j = __ffs(pairs) - 1;
+                    pairs &= pairs - 1u;
                     for (int h = 0; h < 2; h++) {
-                        const unsigned x = (x2 >> (16 * h)) & 0xFFFFu;
+                        const int jj = 2 * j + h;
+                        const unsigned x = cg[a0 + jj];    // back from shared memory: no dynamically indexed registers
                         const unsigned op = x & 15u;
                         if (op < 4u || op == 7u || op == 8u) continue;
-                        const int jj = 2 * j + h;
                         const int g = a_base + a0 + jj - mis;   // CIGAR index inside the read
                         if (!TAG && (op == 4u || op == 5u) && (int)op_len(a.b, x, gop0 + (uint64_t)(a_base + a0 + jj)) > 5) {
                             // getClip (ParsingBam.cpp:1636-1645); a later abort of the read cancels the events at or after the aborting op
