@@ -41,12 +41,14 @@ struct WdView {
     const DevBatch *b;
     const uint16_t *cig;            // the read's ops (global)
     uint64_t gop0;
-    const uint16_t *s_ops; int op0;                 // s_ops[k] = op op0 + k
-    const uint8_t *seq; const uint8_t *s_seq; long long seq0;   // s_seq[k] = seq byte seq0 + k (byte index inside the read's SEQ)
-    const char *ref; const uint8_t *s_ref; long long ref0; long long ref_len;
+    // each window holds the elements [x0 + lo, x0 + hi) of its array (the 16-byte units that lie inside the array); anything else is
+    // read from global memory
+    const uint16_t *s_ops; int op0, op_lo, op_hi;   // s_ops[k] = op op0 + k
+    const uint8_t *seq; const uint8_t *s_seq; long long seq0; int seq_lo, seq_hi;   // s_seq[k] = byte seq0 + k of the read's SEQ
+    const char *ref; const uint8_t *s_ref; long long ref0; int ref_lo, ref_hi; long long ref_len;
     __device__ __forceinline__ unsigned op_word(int ci) const {
-        const unsigned k = (unsigned)(ci - op0);
-        return k < (unsigned)WD_OPS ? (unsigned)s_ops[k] : (unsigned)cig[ci];
+        const int k = ci - op0;
+        return (k >= op_lo && k < op_hi) ? (unsigned)s_ops[k] : (unsigned)cig[ci];
     }
     __device__ __forceinline__ int op_len(int ci, unsigned w) const {
         const unsigned len = w >> 4;
@@ -61,13 +63,13 @@ struct WdView {
     }
     __device__ __forceinline__ char base(int rp) const {
         const long long byte = (long long)(rp >> 1) - seq0;
-        const unsigned v = (unsigned long long)byte < (unsigned long long)WD_SEQ ? (unsigned)s_seq[byte] : (unsigned)seq[rp >> 1];
+        const unsigned v = (byte >= seq_lo && byte < seq_hi) ? (unsigned)s_seq[byte] : (unsigned)seq[rp >> 1];
         return "=ACMGRSVTWYHKDBN"[(v >> ((~rp & 1) << 2)) & 0xfu];
     }
     __device__ __forceinline__ char ref_at(int fp) const {
         if ((long long)fp == ref_len) return '\0';                             // std::string::operator[](size())
         const long long k = (long long)fp - ref0;
-        return (unsigned long long)k < (unsigned long long)WD_REF ? (char)s_ref[k] : ref[fp];
+        return (k >= ref_lo && k < ref_hi) ? (char)s_ref[k] : ref[fp];
     }
 };
 
@@ -141,23 +143,30 @@ __global__ void __launch_bounds__(WD_ITEMS * 8) k_window_diff(WdArgs a) {
     const int ci = (int)it.opi, off = (int)it.off, qidx = (int)it.qidx;
     const int var_pos = a.vpos[a.tum_var[it.slot2 >> 1]];
     v.ref = a.ref; v.ref_len = a.ref_len;
-    // ---- stage the three windows (each lane its share, the item's eight lanes are consecutive lanes of one warp) ----
-    v.op0 = ci - WD_OPS / 2;
-    for (int k = sub; k < WD_OPS; k += 8) {
-        const int idx = v.op0 + k;
-        s_ops[slot][k] = (idx >= 0 && idx < ncig) ? v.cig[idx] : (uint16_t)0;
-    }
-    const long long seq_bytes = ((long long)lq + 1) >> 1;
-    v.seq0 = (long long)(qidx >> 1) - WD_SEQ / 2;
-    for (int k = sub; k < WD_SEQ; k += 8) {
-        const long long byte = v.seq0 + k;
-        s_seq[slot][k] = (byte >= 0 && byte < seq_bytes) ? v.seq[byte] : (uint8_t)0;
-    }
-    v.ref0 = (long long)var_pos - WD_REF / 2;
-    for (int k = sub; k < WD_REF; k += 8) {
-        const long long fp = v.ref0 + k;
-        s_ref[slot][k] = (fp >= 0 && fp < a.ref_len) ? (uint8_t)a.ref[fp] : (uint8_t)0;
-    }
+    // ---- stage the three windows: 16-byte units, aligned in the GLOBAL address space (so a window may start a few elements before
+    //      the wanted position: whatever lies there - the previous read's ops or bases - is never looked at); units that would
+    //      reach outside the arrays stay zero ----
+    // a unit is loaded when it lies inside [base rounded up, end rounded DOWN to 16 bytes): no byte outside the caller's arrays is touched
+    auto stage = [&](const void *array, uint64_t n_bytes, const void *want_ptr, int window_bytes, uint8_t *dst, long long &x0_bytes, int &lo, int &hi) {
+        const uintptr_t base = ((uintptr_t)array + 15u) & ~(uintptr_t)15, lim = ((uintptr_t)array + (uintptr_t)n_bytes) & ~(uintptr_t)15;
+        const uintptr_t g0 = ((uintptr_t)want_ptr - (uintptr_t)(window_bytes / 2)) & ~(uintptr_t)15;
+        x0_bytes = (long long)g0;
+        for (int u = sub; u < window_bytes / 16; u += 8) {
+            const uintptr_t addr = g0 + 16u * (unsigned)u;
+            if (addr >= base && addr + 16 <= lim) reinterpret_cast<uint4 *>(dst)[u] = *reinterpret_cast<const uint4 *>(addr);
+        }
+        const long long l = (long long)base - (long long)g0, h = (long long)lim - (long long)g0;
+        lo = (int)(l < 0 ? 0 : (l > window_bytes ? window_bytes : l));
+        hi = (int)(h < 0 ? 0 : (h > window_bytes ? window_bytes : h));
+        if (hi < lo) hi = lo;
+    };
+    long long x0;
+    stage(a.b.cigar16, a.b.cigar_len * 2ull, v.cig + ci, WD_OPS * 2, reinterpret_cast<uint8_t *>(s_ops[slot]), x0, v.op_lo, v.op_hi);
+    v.op0 = (int)((x0 - (long long)(uintptr_t)v.cig) / 2); v.op_lo = (v.op_lo + 1) / 2; v.op_hi /= 2;      // bytes -> ops
+    stage(a.b.seq4, a.b.seq_bytes, v.seq + (qidx >> 1), WD_SEQ, s_seq[slot], x0, v.seq_lo, v.seq_hi);
+    v.seq0 = x0 - (long long)(uintptr_t)v.seq;
+    stage(a.ref, (uint64_t)(a.ref_len > 0 ? a.ref_len : 0), a.ref + var_pos, WD_REF, s_ref[slot], x0, v.ref_lo, v.ref_hi);
+    v.ref0 = x0 - (long long)(uintptr_t)a.ref;
     v.s_ops = s_ops[slot]; v.s_seq = s_seq[slot]; v.s_ref = s_ref[slot];
     __syncwarp();
     int32_t *hist = a.window_hist + (size_t)it.slot2 * LPS_WINDOW_BINS;
