@@ -77,12 +77,14 @@ typedef struct {
     uint64_t seq_bytes;
     const uint8_t *qual;
     uint64_t qual_bytes;
-    /* --- optional compact wire format of the CIGAR stream (lps_batch_submit only) ----------- *
-     * The CIGAR is 80 % of what a batch sends to the device once SEQ / QUAL stay on the host.  When cigar16 != NULL,
-     * cigar[] is ignored (may be NULL): cigar16[i] holds op i of the same stream in 16 bits, len<<4|op for len < 4095,
-     * and 0xFFF0|op for a longer op, whose true length is listed in cigar_long_len[] / cigar_long_at[] (index into
-     * cigar16[], ascending).  lps_pack_cigar16 produces all three from BAM's uint32 ops while the host appends a record.
-     * The device widens the stream back to uint32 before any kernel reads it, so results cannot differ.            */
+    /* --- the CIGAR stream in 16 bits per op: what the kernels read -------------------------------------------------- *
+     * When cigar16 != NULL, cigar[] is ignored (may be NULL): cigar16[i] holds op i of the same stream in 16 bits, len<<4|op
+     * for len < 4095, and 0xFFF0|op for a longer op, whose true length is listed in cigar_long_len[] / cigar_long_at[] (index
+     * into cigar16[], strictly ascending).  lps_pack_cigar16 produces all three from BAM's uint32 ops while the host appends a
+     * record.  This IS the device-resident format (2 bytes per op in HBM and on the wire); a batch submitted with uint32 ops is
+     * narrowed to it on the device on arrival (k_narrow_cigar32).  With lps_batch_submit_device the three arrays are device
+     * pointers and are used where they lie: cigar16 must be 16-byte aligned (the walking kernel brings super-chunks of it into
+     * shared memory with 16-byte granular bulk copies; it never reads past the 16-byte unit that holds the last op).          */
     const uint16_t *cigar16;        /* [cigar_len]                                              */
     const uint32_t *cigar_long_len; /* [n_cigar_long]                                           */
     const uint64_t *cigar_long_at;  /* [n_cigar_long]                                           */
@@ -196,7 +198,8 @@ const char *lps_version(void);
 
 /* ---- per-contig static data -------------------------------------------------------------- */
 /* FastaParser::chrString (ParsingBam.cpp:17-59) as used by homopolymerLength (Util.cpp:21-54),
- * getVariants_markindel (ParsingBam.cpp:378-417) and getWindowsDiffRef (SomaticVarCaller.cpp:627). */
+ * getVariants_markindel (ParsingBam.cpp:378-417) and getWindowsDiffRef (SomaticVarCaller.cpp:627).
+ * The string is copied before the call returns (the caller may free it at once).                   */
 int lps_contig_set_reference(lps_ctx *ctx, const char *ref_ascii, int64_t len);
 /* BamParser::BamParser variant copy + mark-indel (ParsingBam.cpp:1207-1235, 378-417) and, when
  * is_ont, the variant side of SnpParser::filterSNP (ParsingBam.cpp:866-888).                  */
@@ -204,9 +207,12 @@ int lps_contig_set_variants(lps_ctx *ctx, const lps_variants *v, int is_ont);
 int lps_contig_get_notes(lps_ctx *ctx, lps_variant_notes *out);
 
 /* ---- reads -------------------------------------------------------------------------------- */
-/* Copies the batch to the device (asynchronously on the context's stream when the host buffers
- * are pinned).  The host buffers must stay valid until the next lps_* call on this context
- * returns.                                                                                     */
+/* Copies the batch to the device and waits for the copies.  The offsets are validated first (cigar_off + n_cigar within
+ * cigar_len, seq_off / qual_off + the read's bytes within seq_bytes / qual_bytes, l_qseq >= 0): LPS_E_ARG otherwise.
+ * Lifetime: the per-read arrays and the CIGAR stream may be freed as soon as the call returns.  seq4 / qual are different when
+ * they are PINNED host memory (cudaHostAlloc / cudaHostRegister): then they are NOT copied - the kernels gather the few sectors
+ * they need straight from the host buffers (zero-copy) - and must stay valid and unchanged until the next lps_batch_submit /
+ * lps_batch_submit_device on this context, or lps_ctx_destroy.  Pageable seq4 / qual are copied like everything else.        */
 int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b);
 /* Appends n BAM CIGAR ops (bam_get_cigar(aln), core.n_cigar) to a compact stream: out16[0..n) receives the 16-bit ops;
  * an op of length >= 4095 also appends (length, base_index + i) to long_len[] / long_at[] starting at slot *n_long,
@@ -214,7 +220,9 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b);
  * small (nothing is written past long_cap).  Pure host code; thread-safe on disjoint outputs.                      */
 int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint16_t *out16, uint32_t *long_len,
                      uint64_t *long_at, uint64_t long_cap, uint64_t *n_long);
-/* Same, for buffers that already live in device memory (used for kernel-resident timing).      */
+/* Same, for buffers that already live in device memory (a batch that stays resident across calls): nothing is copied except the
+ * name ranks and flags the host needs (to group the alignments of one read name).  The arrays must stay valid until the next
+ * submit on this context.  Either cigar (uint32 ops, narrowed into a buffer of the context) or cigar16 (+ its side table).  */
 int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b_dev);
 
 /* ---- phase -------------------------------------------------------------------------------- */
@@ -222,14 +230,19 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b_dev);
  * (ParsingBam.cpp:1243-1301, 1303-1634, 1636-1645) and the call-erasing half of
  * SnpParser::filterSNP (ParsingBam.cpp:891-911).  want_host!=0 copies the result to the host. */
 int lps_phase_call_alleles(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_calls *out);
-/* VairiantGraph::addEdge (PhasingGraph.cpp:694-889): overlap filter and CNV filter on the host,
- * merge by read name, fan-out and the ordered float fold of SubEdge::addSubEdge (:25-70).      */
+/* VairiantGraph::addEdge (PhasingGraph.cpp:694-889): overlap filter on the device, CNV filter from the clip map
+ * (host; it only acts when clip pile-ups exist), merge by read name, fan-out and the ordered float fold of
+ * SubEdge::addSubEdge (:25-70).                                                                  */
 int lps_phase_build_edges(lps_ctx *ctx, const lps_phase_params *p, int want_host, lps_edges *out);
-/* VairiantGraph::phasingProcess + exportResult (PhasingGraph.cpp:286-474, 891-1029, 1049-1077) */
+/* VairiantGraph::phasingProcess + exportResult (PhasingGraph.cpp:286-474, 891-1029, 1049-1077): edgeConnectResult as a
+ * segmented sweep on the device (k_sweep.cu; windows beyond 63 successors and LPS_HOST_SWEEP=1 use the host sweep below),
+ * then readCorrection.                                                                          */
 int lps_phase_solve(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
-/* all of the above for one contig (the body of the loop at PhasingProcess.cpp:113-173)         */
+/* all of the above for one contig (the body of the loop at PhasingProcess.cpp:113-173) as one asynchronous pipeline: the host
+ * waits for the device twice (the allele-calling kernel's counters, the end).  Result arrays live in pinned memory of the
+ * context until the next call.  LPS_STAGED=1 runs the three calls above instead.                */
 int lps_phase_contig(lps_ctx *ctx, const lps_phase_params *p, lps_phase_result *out);
-/* The host half of lps_phase_solve on its own (no device): VairiantGraph::edgeConnectResult (PhasingGraph.cpp:286-474) over
+/* edgeConnectResult on the host, no device: VairiantGraph::edgeConnectResult (PhasingGraph.cpp:286-474) over
  * the one-byte summaries of VariantEdge::findBestEdgePair (:166-228) that the device derives from every edge cell.
  * votes[k*window + d] describes the edge from graph node k to node k+1+d: bits 0-1 link (1 same haplotype, 2 opposite,
  * 0 none), bit 2 weight-20 rule, bit 3 (para+cross) <= 1, bit 4 edgeSimilarRatio < 0.2.  node_type as lps_edges.node_type.

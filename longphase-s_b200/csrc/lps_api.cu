@@ -133,7 +133,11 @@ int validate_batch(lps_ctx *ctx, const lps_read_batch *b) {
 
 extern "C" {
 
-const char *lps_version(void) { return "longphase-s_b200 0.1 (sm_100a)"; }
+#ifndef LPS_SOURCE_HASH
+#define LPS_SOURCE_HASH "unknown"
+#endif
+// the hash covers every source of this library (csrc/Makefile), so a stale binary is recognisable
+const char *lps_version(void) { return "longphase-s_b200 0.2 (sm_100a) src:" LPS_SOURCE_HASH; }
 
 int lps_set_blocking_sync(int device, int on) {
     if (cudaSetDevice(device) != cudaSuccess) return LPS_E_CUDA;
