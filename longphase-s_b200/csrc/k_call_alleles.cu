@@ -1491,19 +1491,25 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
         LPS_CUDA(ctx, ctx->p_clip_unique.reserve((size_t)nclip));
         LPS_CUDA(ctx, ctx->p_clip_counts.reserve((size_t)nclip));
         LPS_CUDA(ctx, ctx->p_num_runs.reserve(1));
+        // off the critical path: nothing on the device waits for the clip map (the host turns it into CNV intervals), so it is sorted,
+        // run-length encoded and copied on the context's side stream while the main stream goes on with the graph
+        cudaStream_t sd = ctx->stream_side;
+        LPS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        LPS_CUDA(ctx, cudaStreamWaitEvent(sd, ctx->ev_fork, 0));
+        const int key_bits = 32;
         size_t b1 = 0, b2 = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->d_clip_keys.p, ctx->d_clip_keys_sorted.p, nclip, 0, 32, st);
+        cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->d_clip_keys.p, ctx->d_clip_keys_sorted.p, nclip, 0, key_bits, sd);
         cub::DeviceRunLengthEncode::Encode(nullptr, b2, ctx->d_clip_keys_sorted.p, ctx->d_clip_unique.p, ctx->d_clip_counts.p,
-                                           ctx->d_num_runs.p, nclip, st);
-        LPS_CUDA(ctx, ctx->d_cub_tmp.reserve(b1 > b2 ? b1 : b2));
-        cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp.p, b1, ctx->d_clip_keys.p, ctx->d_clip_keys_sorted.p, nclip, 0, 32, st);
-        cub::DeviceRunLengthEncode::Encode(ctx->d_cub_tmp.p, b2, ctx->d_clip_keys_sorted.p, ctx->d_clip_unique.p, ctx->d_clip_counts.p,
-                                           ctx->d_num_runs.p, nclip, st);
+                                           ctx->d_num_runs.p, nclip, sd);
+        LPS_CUDA(ctx, ctx->d_cub_tmp_side.reserve(b1 > b2 ? b1 : b2));
+        cub::DeviceRadixSort::SortKeys(ctx->d_cub_tmp_side.p, b1, ctx->d_clip_keys.p, ctx->d_clip_keys_sorted.p, nclip, 0, key_bits, sd);
+        cub::DeviceRunLengthEncode::Encode(ctx->d_cub_tmp_side.p, b2, ctx->d_clip_keys_sorted.p, ctx->d_clip_unique.p, ctx->d_clip_counts.p,
+                                           ctx->d_num_runs.p, nclip, sd);
         ctx->stats.kernel_launches += 2;
-        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_num_runs.p, ctx->d_num_runs.p, 4, cudaMemcpyDeviceToHost, st));
-        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_unique.p, ctx->d_clip_unique.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, st));
-        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_counts.p, ctx->d_clip_counts.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, st));
-        LPS_CUDA(ctx, cudaEventRecord(ctx->ev_clips, st));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_num_runs.p, ctx->d_num_runs.p, 4, cudaMemcpyDeviceToHost, sd));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_unique.p, ctx->d_clip_unique.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, sd));
+        LPS_CUDA(ctx, cudaMemcpyAsync(ctx->p_clip_counts.p, ctx->d_clip_counts.p, 4 * (size_t)nclip, cudaMemcpyDeviceToHost, sd));
+        LPS_CUDA(ctx, cudaEventRecord(ctx->ev_clips, sd));
     }
     ctx->have_calls = !tag;
     ctx->host_calls_valid = false;

@@ -199,50 +199,68 @@ __device__ bool std_sort_replay(uint32_t *v, long long n) {
     return true;
 }
 
-__global__ void k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ grp_off,
-                                    uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted, uint2 *__restrict__ tie_groups,
-                                    uint32_t tie_cap, unsigned int *__restrict__ n_tie, int record_only) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_aln) return;
-    if (keys_sorted[i] == ~0ull) return;
-    uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
-    if (i > 0 && (uint32_t)(keys_sorted[i - 1] >> 32) == rank) return;          // not a group head
-    int j = i + 1;
-    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
-    if (j == i + 1) return;                                                      // single alignment
-    uint64_t g0 = grp_off[i], g1 = grp_off[j];
-    if (!record_only) {
-        for (uint64_t a = g0; a < g1; a++) M_unsorted[a] = M[a];                 // concatenation order, for the host replay
-        for (uint64_t a = g0 + 1; a < g1; a++) {
-            uint32_t v = M[a];
-            uint64_t b = a;
-            while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
-            M[b] = v;
-        }
+constexpr int SMG_WARPS = 8, SMG_CAP = 1024;      // merged reads of up to SMG_CAP calls are sorted in shared memory
+
+// in-place insertion sort of concatenated sorted runs (equal positions keep their concatenation order)
+__device__ __forceinline__ void insertion_sort_runs(uint32_t *v, long long n) {
+    for (long long a = 1; a < n; a++) {
+        const uint32_t x = v[a];
+        long long b = a;
+        while (b > 0 && (v[b - 1] >> 2) > (x >> 2)) { v[b] = v[b - 1]; b--; }
+        v[b] = x;
     }
-    // a tie = two calls of the merged read at one position: adjacent after the sort
-    bool tie = false;
-    for (uint64_t a = g0 + 1; a < g1 && !tie; a++) tie = (M[a - 1] >> 2) == (M[a] >> 2);
-    if (tie && g1 - g0 > 16) {
-        // more than 16 calls with a tie: the order of the tied calls is std::sort's - replay it from the concatenation order
-        bool done = false;
-        if (!record_only) {
-            for (uint64_t a = g0; a < g1; a++) M[a] = M_unsorted[a];
-            done = std_sort_replay(M + g0, (long long)(g1 - g0));
-            if (!done) {                                         // leave the group position-sorted for the host replay's write-back
-                for (uint64_t a = g0; a < g1; a++) M[a] = M_unsorted[a];
-                for (uint64_t a = g0 + 1; a < g1; a++) {
-                    uint32_t v = M[a];
-                    uint64_t b = a;
-                    while (b > g0 && (M[b - 1] >> 2) > (v >> 2)) { M[b] = M[b - 1]; b--; }
-                    M[b] = v;
+}
+
+// One WARP per alignment of the sorted list; only the first alignment of a merged read made of several alignments does anything.
+// The group is copied to shared memory by the whole warp (it is small and the work on it is a dependent chain: in global memory
+// every step waited for L2), lane 0 orders it, the warp writes it back.
+__global__ void __launch_bounds__(SMG_WARPS * 32) k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted,
+                                    const uint64_t *__restrict__ grp_off, uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted,
+                                    uint2 *__restrict__ tie_groups, uint32_t tie_cap, unsigned int *__restrict__ n_tie, int record_only) {
+    __shared__ uint32_t s_buf[SMG_WARPS][SMG_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * SMG_WARPS + wib;
+    if (wid >= n_aln) return;
+    const int i = (int)wid;
+    if (keys_sorted[i] == ~0ull) return;
+    const uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
+    if (i > 0 && (uint32_t)(keys_sorted[i - 1] >> 32) == rank) return;          // not a group head
+    if (i + 1 >= n_aln || (uint32_t)(keys_sorted[i + 1] >> 32) != rank) return; // single alignment
+    int j = i + 2;
+    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
+    const uint64_t g0 = grp_off[i], g1 = grp_off[j];
+    const long long n = (long long)(g1 - g0);
+    if (n < 2) return;
+    const bool in_smem = n <= SMG_CAP;
+    uint32_t *v = in_smem ? s_buf[wib] : M + g0;
+    if (!record_only) for (long long a = lane; a < n; a += 32) M_unsorted[g0 + a] = M[g0 + a];      // concatenation order, for the replays
+    if (in_smem) for (long long a = lane; a < n; a += 32) v[a] = M[g0 + a];
+    __syncwarp();
+    bool report = false;
+    if (lane == 0) {
+        if (!record_only) insertion_sort_runs(v, n);
+        // a tie = two calls of the merged read at one position: adjacent after the sort
+        bool tie = false;
+        for (long long a = 1; a < n && !tie; a++) tie = (v[a - 1] >> 2) == (v[a] >> 2);
+        if (tie && n > 16) {
+            // more than 16 calls with a tie: the order of the tied calls is std::sort's - replay it from the concatenation order
+            bool done = false;
+            if (!record_only) {
+                for (long long a = 0; a < n; a++) v[a] = M_unsorted[g0 + a];
+                done = std_sort_replay(v, n);
+                if (!done) {                                     // leave the group position-sorted for the host replay's write-back
+                    for (long long a = 0; a < n; a++) v[a] = M_unsorted[g0 + a];
+                    insertion_sort_runs(v, n);
                 }
             }
+            report = !done;
         }
-        if (!done) {
-            unsigned k = atomicAdd(n_tie, 1u);
-            if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
-        }
+    }
+    __syncwarp();
+    if (in_smem && !record_only) for (long long a = lane; a < n; a += 32) M[g0 + a] = v[a];
+    if (lane == 0 && report) {
+        const unsigned k = atomicAdd(n_tie, 1u);
+        if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
     }
 }
 
@@ -685,7 +703,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
             p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
         // multi-alignment merged reads
         LPS_CUDA(ctx, ctx->d_tie_groups.reserve(std::max<size_t>(ctx->d_tie_groups.cap, 4096)));
-        k_sort_multi_groups<<<(n + tb - 1) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
+        k_sort_multi_groups<<<(n + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
                                                           ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu), ctx->d_n_tie.p, 0);
         ctx->stats.kernel_launches += 2;
         if (sync_ties) {
@@ -696,7 +714,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
                 // more tied groups than the list holds: grow it and list them again (the merged reads are sorted by now)
                 LPS_CUDA(ctx, ctx->d_tie_groups.reserve((size_t)h_tie + 1024));
                 LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_tie.p, 0, 4, st));
-                k_sort_multi_groups<<<(n + tb - 1) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
+                k_sort_multi_groups<<<(n + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
                                                                   ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu),
                                                                   ctx->d_n_tie.p, 1);
                 ctx->stats.kernel_launches++;

@@ -30,7 +30,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int SW_CH = 64;        // nodes per staged chunk
 constexpr int SW_RS_MAX = 80;    // lps_vote_row_stride(63)
 constexpr int SW_WARPS = 4;      // segments per CTA
-constexpr int SW_SEG = 512;      // core nodes per segment
+constexpr int SW_SEG = 128;      // core nodes per segment (a warp walks halo + core = ~270 nodes; 64 k nodes are 512 warps, one wave)
 constexpr int SW_HALO_W = 4;     // halo = SW_HALO_W * W nodes
 
 struct SweepArgs {
@@ -175,42 +175,50 @@ __global__ void __launch_bounds__(SW_WARPS * 32) k_sweep_segments(SweepArgs a) {
     sweep_range(a, S, N, max(0, b - a.halo), b, e, p, lane);
 }
 
-// boundary checks + flips (one CTA; thread p checks the boundary in front of segment p)
+// boundary checks + flips (one CTA; thread p checks the boundary in front of segment p; the flips relative to the truth are a scan
+// over the segments, done by one thread on shared memory, a tile of segments at a time)
 __global__ void __launch_bounds__(1024) k_sweep_verify(SweepArgs a) {
+    constexpr int TILE = 4096;
+    __shared__ uint8_t s_rel[TILE], s_anchor[TILE];
     __shared__ int s_ok;
+    __shared__ unsigned s_carry;
     const int N = *a.n_nodes;
-    if (threadIdx.x == 0) s_ok = 1;
+    if (threadIdx.x == 0) { s_ok = 1; s_carry = 0u; }
     __syncthreads();
-    for (int p = 1 + (int)threadIdx.x; p < a.n_seg; p += blockDim.x) {
-        const int b = p * a.seg;
-        int ok = 1, flip = -1;
-        if (b < N - 1 && b - a.halo > 0) {          // a halo that starts at node 0 starts from the true state: nothing to check
-            for (int i = 0; i < a.W; i++) {
-                const int kk = b - a.W + i;
-                if (kk < 0) continue;
-                const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
-                if (h == 0xFFu || ((t ^ h) & 0xBu)) { ok = 0; break; }
-                if (t & 1u) {
-                    const int x = (int)(((t ^ h) >> 2) & 1u);
-                    if (flip < 0) flip = x; else if (flip != x) { ok = 0; break; }
+    for (int p0 = 0; p0 < a.n_seg; p0 += TILE) {
+        const int p1 = min(a.n_seg, p0 + TILE);
+        for (int p = p0 + (int)threadIdx.x; p < p1; p += blockDim.x) {
+            const int b = p * a.seg, e = min(N, b + a.seg);
+            int ok = 1, flip = -1;
+            if (p > 0 && b < N - 1 && b - a.halo > 0) {      // a halo that starts at node 0 starts from the true state: nothing to check
+                for (int i = 0; i < a.W; i++) {
+                    const int kk = b - a.W + i;
+                    if (kk < 0) continue;
+                    const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
+                    if (h == 0xFFu || ((t ^ h) & 0xBu)) { ok = 0; break; }
+                    if (t & 1u) {
+                        const int x = (int)(((t ^ h) >> 2) & 1u);
+                        if (flip < 0) flip = x; else if (flip != x) { ok = 0; break; }
+                    }
                 }
             }
+            s_rel[p - p0] = (uint8_t)(flip > 0 ? 1 : 0);       // relative to segment p - 1
+            s_anchor[p - p0] = (uint8_t)((b < N && a.first_nb[p] < e) ? 1 : 0);   // a block start inside the core re-anchors the orientation
+            if (!ok) s_ok = 0;
         }
-        a.seg_flip[p] = (uint8_t)(flip > 0 ? 1 : 0);     // relative to segment p - 1 for now
-        if (!ok) s_ok = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // flips relative to the truth: a block start inside a segment's core re-anchors the orientation from there on
-        unsigned carry = 0u;                              // flip in force at the end of the previous segment
-        for (int p = 0; p < a.n_seg; p++) {
-            const int b = p * a.seg, e = min(N, b + a.seg);
-            const unsigned F = p == 0 ? 0u : ((unsigned)a.seg_flip[p] ^ carry);
-            a.seg_flip[p] = (uint8_t)F;
-            carry = (b < N && a.first_nb[p] < e) ? 0u : F;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned carry = s_carry;                           // flip in force at the end of the previous segment
+            for (int p = p0; p < p1; p++) {
+                const unsigned F = p == 0 ? 0u : ((unsigned)s_rel[p - p0] ^ carry);
+                a.seg_flip[p] = (uint8_t)F;
+                carry = s_anchor[p - p0] ? 0u : F;
+            }
+            s_carry = carry;
         }
-        *a.all_ok = s_ok;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *a.all_ok = s_ok;
 }
 
 // the exact sequential chain, only when a boundary did not verify

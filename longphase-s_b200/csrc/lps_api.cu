@@ -170,6 +170,8 @@ int lps_ctx_create(int device, lps_ctx **out) {
     for (auto &ev : ctx->user_ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->kev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&ctx->ev_clips, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->stream_side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LPS_E_CUDA; }
     {
         // PQ = (int)(-10*log10(min/(max+min))) (HaplotagStrategy.cpp:287) tabulated with the HOST libm, so that the
         // truncation to int agrees with the reference on the same machine; the kernel only looks it up
@@ -196,6 +198,8 @@ void lps_ctx_destroy(lps_ctx *ctx) {
     for (auto &ev : ctx->user_ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->kev) cudaEventDestroy(ev);
     if (ctx->ev_clips) cudaEventDestroy(ctx->ev_clips);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->stream_side) { cudaStreamSynchronize(ctx->stream_side); cudaStreamDestroy(ctx->stream_side); }
     cudaStreamDestroy(ctx->stream);
     for (auto &cs : ctx->stream_k) if (cs) cudaStreamDestroy(cs);
     if (ctx->stream_up) cudaStreamDestroy(ctx->stream_up);

@@ -140,6 +140,9 @@ struct lps_ctx {
     cudaEvent_t user_ev[4] = {};
     cudaEvent_t kev[6] = {};   // around the hot kernels
     cudaEvent_t ev_clips = nullptr;   // the clip map has reached the pinned staging buffers
+    cudaEvent_t ev_fork = nullptr;    // main stream -> side stream
+    cudaStream_t stream_side = nullptr;   // work that is off the contig's critical path (the clip map: sort, run-length encoding, copy)
+    DevBuf<uint8_t> d_cub_tmp_side;
     std::string err;
     int err_code = 0;
     lps_stats stats = {};
