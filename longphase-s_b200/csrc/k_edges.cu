@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
         // the read) are requested before call t is folded, so the fold never waits on a dependent load chain.  Lane l owns the
         // successors l and 32 + l of a call (W <= 64): one round per call instead of two.
         const int W2 = W > 32 ? W - 32 : 0;
+        const uint32_t t0 = (uint32_t)l0, t1 = (uint32_t)l1;       // 32-bit loop indices: the 64-bit index arithmetic was a fifth of the kernel's instructions
         const uint32_t nm = (uint32_t)n_merged;            // merged entries are indexed with 32 bits (d_M_idx is uint32)
         auto fetch = [&](uint32_t m, uint32_t &ea, uint32_t &gend, uint32_t &e0, uint32_t &e1) {
             ea = M[m]; gend = M_gend[m];
@@ -326,18 +327,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
             e1 = (lane < W2 && i1 < nm) ? M[i1] : 0xffffffffu;
         };
         uint32_t m_cur = 0, m_nxt = 0, ea = 0, gend = 0, e0 = 0xffffffffu, e1 = 0xffffffffu;
-        if (l0 < l1) { m_cur = list[l0]; fetch(m_cur, ea, gend, e0, e1); }
-        if (l0 + 1 < l1) m_nxt = list[l0 + 1];
+        if (t0 < t1) { m_cur = list[t0]; fetch(m_cur, ea, gend, e0, e1); }
+        if (t0 + 1u < t1) m_nxt = list[t0 + 1u];
         unsigned c32 = 0, f32 = 0;                         // per-lane counts of this node (<= 2 per call), widened once at the end
         const float wlo = (float)edge_weight;
         (void)wlo;
-        for (uint64_t t = l0; t < l1; t++) {
+        for (uint32_t t = t0; t < t1; t++) {
             const uint32_t m = m_cur, ea_c = ea, gend_c = gend;
             uint32_t eb0 = e0, eb1 = e1;
-            if (t + 1 < l1) {
+            if (t + 1u < t1) {
                 m_cur = m_nxt;
                 fetch(m_cur, ea, gend, e0, e1);
-                if (t + 2 < l1) m_nxt = list[t + 2];
+                if (t + 2u < t1) m_nxt = list[t + 2u];
             }
             const unsigned al_a = (ea_c >> 1) & 1u, hi_a = ea_c & 1u;
             const bool act0 = lane < W && m + 1u + (uint32_t)lane < gend_c;
@@ -354,16 +355,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
             const bool dense0 = act0 && d0 >= 0 && d0 < W;
             c32 += (unsigned)dense0;
             f32 += (unsigned)(act0 && !dense0);
-            float *cell0 = dense0 ? &acc[d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u))] : nullptr;
+            const int cell0 = d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u));        // offset into the tile (only used when dense0)
             const bool high0 = hi_a && (eb0 & 1u);
             if (!second) {
                 if (!__any_sync(FULL, dup)) {
                     // distinct successors of one read hit distinct cells
-                    if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }   // SubEdge::addSubEdge :40-43, :62-65
+                    if (dense0) { float x = acc[cell0]; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell0] = x; }   // SubEdge::addSubEdge :40-43, :62-65
                 } else {
                     // keep the read's own order
                     for (int l = 0; l < 32; l++) {
-                        if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                        if (lane == l && dense0) { float x = acc[cell0]; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell0] = x; }
                         __syncwarp();
                     }
                 }
@@ -377,19 +378,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
                 const bool dense1 = act1 && d1 >= 0 && d1 < W;
                 c32 += (unsigned)dense1;
                 f32 += (unsigned)(act1 && !dense1);
-                float *cell1 = dense1 ? &acc[d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u))] : nullptr;
+                const int cell1 = d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u));
                 const bool high1 = hi_a && (eb1 & 1u);
                 if (!any_dup) {
-                    if (dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
-                    if (dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
+                    if (dense0) { float x = acc[cell0]; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell0] = x; }
+                    if (dense1) { float x = acc[cell1]; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell1] = x; }
                 } else {
                     // keep the read's own order: successors 0..31, then 32..W-1
                     for (int l = 0; l < 32; l++) {
-                        if (lane == l && dense0) { float x = *cell0; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); *cell0 = x; }
+                        if (lane == l && dense0) { float x = acc[cell0]; x = high0 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell0] = x; }
                         __syncwarp();
                     }
                     for (int l = 0; l < W2; l++) {
-                        if (lane == l && dense1) { float x = *cell1; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); *cell1 = x; }
+                        if (lane == l && dense1) { float x = acc[cell1]; x = high1 ? x + 1.0f : (float)((double)x + edge_weight); acc[cell1] = x; }
                         __syncwarp();
                     }
                 }
