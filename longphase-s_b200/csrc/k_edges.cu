@@ -211,24 +211,37 @@ __device__ __forceinline__ void insertion_sort_runs(uint32_t *v, long long n) {
     }
 }
 
-// One WARP per alignment of the sorted list; only the first alignment of a merged read made of several alignments does anything.
-// The group is copied to shared memory by the whole warp (it is small and the work on it is a dependent chain: in global memory
-// every step waited for L2), lane 0 orders it, the warp writes it back.
-__global__ void __launch_bounds__(SMG_WARPS * 32) k_sort_multi_groups(int n_aln, const uint64_t *__restrict__ keys_sorted,
-                                    const uint64_t *__restrict__ grp_off, uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted,
+// position of every alive alignment in the (name rank, BAM order) list
+__global__ void k_sorted_position(int n, const uint64_t *__restrict__ keys_sorted, int32_t *__restrict__ pos_of_read) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys_sorted[i];
+    if (k != ~0ull) pos_of_read[(uint32_t)k] = i;
+}
+
+// One WARP per read name that owns several alignments of the batch (the groups the host indexed at submit time,
+// lps_host_index_names): its alive alignments are neighbours in the sorted list, so the merged read is M[grp_off[first] ..
+// grp_off[first + alive]).  The group is copied to shared memory by the whole warp (it is small and the work on it is a dependent
+// chain: in global memory every step waited for L2), lane 0 orders it, the warp writes it back.
+__global__ void __launch_bounds__(SMG_WARPS * 32) k_sort_multi_groups(int n_groups, const int32_t *__restrict__ group_off,
+                                    const int32_t *__restrict__ members, const uint32_t *__restrict__ alive_cnt,
+                                    const int32_t *__restrict__ pos_of_read, const uint64_t *__restrict__ grp_off,
+                                    uint32_t *__restrict__ M, uint32_t *__restrict__ M_unsorted,
                                     uint2 *__restrict__ tie_groups, uint32_t tie_cap, unsigned int *__restrict__ n_tie, int record_only) {
     __shared__ uint32_t s_buf[SMG_WARPS][SMG_CAP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wid = (long long)blockIdx.x * SMG_WARPS + wib;
-    if (wid >= n_aln) return;
-    const int i = (int)wid;
-    if (keys_sorted[i] == ~0ull) return;
-    const uint32_t rank = (uint32_t)(keys_sorted[i] >> 32);
-    if (i > 0 && (uint32_t)(keys_sorted[i - 1] >> 32) == rank) return;          // not a group head
-    if (i + 1 >= n_aln || (uint32_t)(keys_sorted[i + 1] >> 32) != rank) return; // single alignment
-    int j = i + 2;
-    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
-    const uint64_t g0 = grp_off[i], g1 = grp_off[j];
+    const int g = blockIdx.x * SMG_WARPS + wib;
+    if (g >= n_groups) return;
+    // first position and number of the group's alive alignments
+    int first = INT_MAX, alive = 0;
+    for (int m = group_off[g] + lane; m < group_off[g + 1]; m += 32) {
+        const int r = members[m];
+        if (alive_cnt[r]) { alive++; first = min(first, pos_of_read[r]); }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { alive += __shfl_xor_sync(FULL, alive, d); first = min(first, __shfl_xor_sync(FULL, first, d)); }
+    if (alive < 2) return;                                                       // a single alignment is sorted already
+    const uint64_t g0 = grp_off[first], g1 = grp_off[first + alive];
     const long long n = (long long)(g1 - g0);
     if (n < 2) return;
     const bool in_smem = n <= SMG_CAP;
@@ -704,9 +717,16 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
             p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
         // multi-alignment merged reads
         LPS_CUDA(ctx, ctx->d_tie_groups.reserve(std::max<size_t>(ctx->d_tie_groups.cap, 4096)));
-        k_sort_multi_groups<<<(n + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
-                                                          ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu), ctx->d_n_tie.p, 0);
-        ctx->stats.kernel_launches += 2;
+        const int n_groups = (int)ctx->h_multi_group_off.size() - 1;
+        if (n_groups > 0) {
+            LPS_CUDA(ctx, ctx->d_pos_of_read.reserve((size_t)n + 1));
+            k_sorted_position<<<(n + tb - 1) / tb, tb, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_pos_of_read.p);
+            k_sort_multi_groups<<<(n_groups + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(
+                n_groups, ctx->d_multi_group_off.p, ctx->d_multi_members.p, ctx->d_alive_cnt.p, ctx->d_pos_of_read.p, ctx->d_grp_off.p, ctx->d_M.p,
+                ctx->d_M_unsorted.p, ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu), ctx->d_n_tie.p, 0);
+            ctx->stats.kernel_launches += 2;
+        }
+        ctx->stats.kernel_launches += 1;
         if (sync_ties) {
             unsigned int h_tie = 0;
             LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, ctx->d_n_tie.p, 4, cudaMemcpyDeviceToHost, st));
@@ -715,9 +735,9 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
                 // more tied groups than the list holds: grow it and list them again (the merged reads are sorted by now)
                 LPS_CUDA(ctx, ctx->d_tie_groups.reserve((size_t)h_tie + 1024));
                 LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_n_tie.p, 0, 4, st));
-                k_sort_multi_groups<<<(n + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_M.p, ctx->d_M_unsorted.p,
-                                                                  ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu),
-                                                                  ctx->d_n_tie.p, 1);
+                k_sort_multi_groups<<<(n_groups + SMG_WARPS - 1) / SMG_WARPS, SMG_WARPS * 32, 0, st>>>(
+                    n_groups, ctx->d_multi_group_off.p, ctx->d_multi_members.p, ctx->d_alive_cnt.p, ctx->d_pos_of_read.p, ctx->d_grp_off.p, ctx->d_M.p,
+                    ctx->d_M_unsorted.p, ctx->d_tie_groups.p, (uint32_t)std::min<size_t>(ctx->d_tie_groups.cap, 0xFFFFFFFFu), ctx->d_n_tie.p, 1);
                 ctx->stats.kernel_launches++;
                 LPS_CUDA(ctx, cudaMemcpyAsync(&h_tie, ctx->d_n_tie.p, 4, cudaMemcpyDeviceToHost, st));
                 LPS_CUDA(ctx, cudaStreamSynchronize(st));

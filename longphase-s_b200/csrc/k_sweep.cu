@@ -187,24 +187,28 @@ __global__ void __launch_bounds__(1024) k_sweep_verify(SweepArgs a) {
     __syncthreads();
     for (int p0 = 0; p0 < a.n_seg; p0 += TILE) {
         const int p1 = min(a.n_seg, p0 + TILE);
-        for (int p = p0 + (int)threadIdx.x; p < p1; p += blockDim.x) {
+        // one warp per boundary, lane i compares the i-th node of the window (W <= 63: two rounds at most)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+        for (int p = p0 + warp; p < p1; p += n_warps) {
             const int b = p * a.seg, e = min(N, b + a.seg);
-            int ok = 1, flip = -1;
-            if (p > 0 && b < N - 1 && b - a.halo > 0) {      // a halo that starts at node 0 starts from the true state: nothing to check
-                for (int i = 0; i < a.W; i++) {
+            bool bad = false;
+            unsigned flip_yes = 0u, flip_no = 0u;               // assigned nodes whose haplotype differs / agrees
+            if (p > 0 && b < N - 1 && b - a.halo > 0) {          // a halo that starts at node 0 starts from the true state: nothing to check
+                for (int i = lane; i < a.W; i += 32) {
                     const int kk = b - a.W + i;
                     if (kk < 0) continue;
                     const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
-                    if (h == 0xFFu || ((t ^ h) & 0xBu)) { ok = 0; break; }
-                    if (t & 1u) {
-                        const int x = (int)(((t ^ h) >> 2) & 1u);
-                        if (flip < 0) flip = x; else if (flip != x) { ok = 0; break; }
-                    }
+                    if (h == 0xFFu || ((t ^ h) & 0xBu)) bad = true;
+                    else if (t & 1u) { if (((t ^ h) >> 2) & 1u) flip_yes = 1u; else flip_no = 1u; }
                 }
             }
-            s_rel[p - p0] = (uint8_t)(flip > 0 ? 1 : 0);       // relative to segment p - 1
-            s_anchor[p - p0] = (uint8_t)((b < N && a.first_nb[p] < e) ? 1 : 0);   // a block start inside the core re-anchors the orientation
-            if (!ok) s_ok = 0;
+            const bool any_bad = __any_sync(0xffffffffu, bad), any_yes = __any_sync(0xffffffffu, flip_yes != 0u),
+                       any_no = __any_sync(0xffffffffu, flip_no != 0u);
+            if (lane == 0) {
+                s_rel[p - p0] = (uint8_t)(any_yes ? 1 : 0);       // relative to segment p - 1
+                s_anchor[p - p0] = (uint8_t)((b < N && a.first_nb[p] < e) ? 1 : 0);   // a block start inside the core re-anchors the orientation
+                if (any_bad || (any_yes && any_no)) s_ok = 0;     // the window must agree up to ONE flip
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {

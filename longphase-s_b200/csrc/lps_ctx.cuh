@@ -181,7 +181,7 @@ struct lps_ctx {
     DevBatch batch;
     std::vector<int32_t> h_name_rank;
     std::vector<int32_t> h_multi_members, h_multi_group_off;   // alignments of names that occur more than once, grouped by name
-    DevBuf<int32_t> d_multi_members, d_multi_group_off, d_multi_kept, d_dead_list;
+    DevBuf<int32_t> d_multi_members, d_multi_group_off, d_multi_kept, d_dead_list, d_pos_of_read;
     DevBuf<uint32_t> d_multi_ncalls;
     uint64_t sum_l_qseq = 0;
     bool have_batch = false;
