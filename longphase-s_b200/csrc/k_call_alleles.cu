@@ -50,6 +50,9 @@ namespace {
 #ifndef LPS_PREFETCH_VREC
 #define LPS_PREFETCH_VREC 1    // variant records of the first phase-2 round requested before phase 1
 #endif
+#ifndef LPS_CLAIM_BATCH
+#define LPS_CLAIM_BATCH 1      // reads claimed per atomic while the work list is far from its end (1 near the end, so the tail stays short)
+#endif
 #ifndef LPS_PAIR_WALK
 #define LPS_PAIR_WALK 1        // phase-2 walk over pairs of ops with the pair table (0: op by op)
 #endif
@@ -1056,8 +1059,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_call_alleles(K1Args a
     t_base = __shfl_sync(FULL, t_base, 0);
     ring_slot[0] = fetch(0, t_base); ring_slot[1] = fetch(1, t_base + 1u); ring_slot[2] = fetch(2, t_base + 2u);
     cp_async_commit();
-    uint32_t claim = 0;
-    if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);     // feeds the ring after the first read; consumed one read later
+    // the claim that feeds the ring is issued one batch ahead of its use: LPS_CLAIM_BATCH reads per atomic while more than a few
+    // batches per warp are left, one read per atomic near the end of the list
+    const uint32_t guided_end = n_items > 4u * LPS_CLAIM_BATCH * gridDim.x * WARPS_PER_CTA ? n_items - 4u * LPS_CLAIM_BATCH * gridDim.x * WARPS_PER_CTA : 0u;
+    uint32_t claim = 0, claim_n = 1, cur_base = 0, cur_left = 0;
+    if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);
     cp_async_wait<0>();
     __syncwarp();
     {
@@ -1075,11 +1081,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_call_alleles(K1Args a
         process_read<MODE>(a, S, s_pair, cur, next, pp, S.cand, CAND_CAP, sl == 0 ? ring_slot[0] : sl == 1 ? ring_slot[1] : ring_slot[2], lane, pc);
         __syncwarp();
         // refill this ring entry with the read claimed one read ago; claim the one after it
-        const uint32_t t = __shfl_sync(FULL, claim, 0);
+        if (cur_left == 0u) {
+            cur_base = __shfl_sync(FULL, claim, 0);
+            cur_left = claim_n;
+            claim_n = (LPS_CLAIM_BATCH > 1 && cur_base < guided_end) ? (uint32_t)LPS_CLAIM_BATCH : 1u;
+            if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, (unsigned long long)claim_n);
+        }
+        const uint32_t t = cur_base;
+        cur_base++; cur_left--;
         const uint32_t ns = fetch(sl, t);
         if (sl == 0) ring_slot[0] = ns; else if (sl == 1) ring_slot[1] = ns; else ring_slot[2] = ns;
         cp_async_commit();
-        if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);
         sl = sn;
         dbg_n++;
     }

@@ -9,6 +9,6 @@ for cfg in "$@"; do
   python - "$cfg" <<'PY'
 import json,sys
 d=json.load(open('/tmp/ab.json'))
-print(sys.argv[1], "k1_ms=%.4f frac=%.3f step_ms=%.3f e2e_ms=%.2f call_alleles=%.3f" % (d["stage_ms"]["k_call_alleles_alone"], d["roofline"]["frac"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["stage_ms"]["call_alleles"]))
+print(sys.argv[1], "k1_ms=%.4f frac=%.3f step_ms=%.3f fold_ms=%.3f" % (d["stage_ms"]["k_call_alleles_alone"], d["roofline"]["frac"], d["ms_per_step"], d["stage_ms"]["k_fold_edges_alone"]))
 PY
 done
