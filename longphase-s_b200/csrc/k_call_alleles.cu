@@ -50,8 +50,8 @@ namespace {
 #ifndef LPS_PREFETCH_VREC
 #define LPS_PREFETCH_VREC 1    // variant records of the first phase-2 round requested before phase 1
 #endif
-#ifndef LPS_CLAIM_BATCH
-#define LPS_CLAIM_BATCH 1      // reads claimed per atomic while the work list is far from its end (1 near the end, so the tail stays short)
+#ifndef LPS_STATIC_SHARE
+#define LPS_STATIC_SHARE 70    // per cent of the work list dealt out statically (item k * warps + warp); the rest is claimed from a global counter
 #endif
 #ifndef LPS_PAIR_WALK
 #define LPS_PAIR_WALK 1        // phase-2 walk over pairs of ops with the pair table (0: op by op)
@@ -1054,16 +1054,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_call_alleles(K1Args a
         } else if (lane == 2) S.desc[k][2].z = 0xFFFFFFFFu;
         return slot;
     };
-    uint32_t t_base = 0;
-    if (lane == 0) t_base = (uint32_t)atomicAdd(&a.counters->next_read.v, 3ull);
-    t_base = __shfl_sync(FULL, t_base, 0);
-    ring_slot[0] = fetch(0, t_base); ring_slot[1] = fetch(1, t_base + 1u); ring_slot[2] = fetch(2, t_base + 2u);
+    // Work distribution.  ~100 k claims on ONE counter saturate its L2 slice (the atomic's round trip grew to a read's duration and
+    // showed up as the largest long-scoreboard stall of the kernel), so the first LPS_STATIC_SHARE per cent of the list - which
+    // starts with the long reads - is dealt out without atomics, item k * warps + warp to every warp, and only the rest, which
+    // evens out the warps' finishing times, is claimed from the counter, one claim ahead of its use.
+    const uint32_t n_warps = gridDim.x * WARPS_PER_CTA, w_global = blockIdx.x * WARPS_PER_CTA + wib;
+    const uint32_t n_static = (uint32_t)(((unsigned long long)n_items * LPS_STATIC_SHARE / 100ull) / n_warps);   // items per warp
+    const uint32_t dyn_base = n_static * n_warps;
+    uint32_t k_static = 0, claim = 0;
+    if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);       // first dynamic item; stays in flight while the static share lasts
+    auto next_item = [&]() -> uint32_t {
+        if (k_static < n_static) return (k_static++) * n_warps + w_global;
+        const uint32_t t = dyn_base + __shfl_sync(FULL, claim, 0);
+        if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);
+        return t;
+    };
+    ring_slot[0] = fetch(0, next_item()); ring_slot[1] = fetch(1, next_item()); ring_slot[2] = fetch(2, next_item());
     cp_async_commit();
-    // the claim that feeds the ring is issued one batch ahead of its use: LPS_CLAIM_BATCH reads per atomic while more than a few
-    // batches per warp are left, one read per atomic near the end of the list
-    const uint32_t guided_end = n_items > 4u * LPS_CLAIM_BATCH * gridDim.x * WARPS_PER_CTA ? n_items - 4u * LPS_CLAIM_BATCH * gridDim.x * WARPS_PER_CTA : 0u;
-    uint32_t claim = 0, claim_n = 1, cur_base = 0, cur_left = 0;
-    if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, 1ull);
     cp_async_wait<0>();
     __syncwarp();
     {
@@ -1081,14 +1088,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_call_alleles(K1Args a
         process_read<MODE>(a, S, s_pair, cur, next, pp, S.cand, CAND_CAP, sl == 0 ? ring_slot[0] : sl == 1 ? ring_slot[1] : ring_slot[2], lane, pc);
         __syncwarp();
         // refill this ring entry with the read claimed one read ago; claim the one after it
-        if (cur_left == 0u) {
-            cur_base = __shfl_sync(FULL, claim, 0);
-            cur_left = claim_n;
-            claim_n = (LPS_CLAIM_BATCH > 1 && cur_base < guided_end) ? (uint32_t)LPS_CLAIM_BATCH : 1u;
-            if (lane == 0) claim = (uint32_t)atomicAdd(&a.counters->next_read.v, (unsigned long long)claim_n);
-        }
-        const uint32_t t = cur_base;
-        cur_base++; cur_left--;
+        const uint32_t t = next_item();
         const uint32_t ns = fetch(sl, t);
         if (sl == 0) ring_slot[0] = ns; else if (sl == 1) ring_slot[1] = ns; else ring_slot[2] = ns;
         cp_async_commit();
