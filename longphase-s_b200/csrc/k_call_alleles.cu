@@ -51,7 +51,7 @@ namespace {
 #define LPS_PREFETCH_VREC 1    // variant records of the first phase-2 round requested before phase 1
 #endif
 #ifndef LPS_STATIC_SHARE
-#define LPS_STATIC_SHARE 70    // per cent of the work list dealt out statically (item k * warps + warp); the rest is claimed from a global counter
+#define LPS_STATIC_SHARE 85    // per cent of the work list dealt out statically (item k * warps + warp); the rest is claimed from a global counter
 #endif
 #ifndef LPS_PAIR_WALK
 #define LPS_PAIR_WALK 1        // phase-2 walk over pairs of ops with the pair table (0: op by op)

@@ -49,7 +49,13 @@ struct alignas(16) SweepSmem {
     uint8_t rows[2][SW_CH * SW_RS_MAX];
     uint16_t meta[2][SW_CH];
     unsigned long long mbar[2];
+    uint8_t flags[SW_SEG + SW_HALO_W * 64];          // decisions of a segment (halo + core), flushed once at its end
 };
+
+// What a voter adds to a successor for every value of a vote byte (5 bits), per (voter haplotype, voter type class): the two float
+// increments and the packed Onelongcase increment.  Type classes: 0 SNP-like (weights 1 / 20, counted by Onelongcase), 1 indel
+// (type 3: same weights, not counted), 2 danger indel (type 4: weight 0.1f).  float4 so that one 128-bit load fetches an entry.
+constexpr int SW_LUT = 32 * 2 * 3;
 
 // everything VariantEdge::findBestEdgePair / edgeConnectResult (:360-417) make of one vote byte, for a voter of haplotype `same`
 __device__ __forceinline__ void vote_of(unsigned info, unsigned same, float w_lo, float w_hi, bool type_ok, float &d1, float &d2, unsigned &dp) {
@@ -64,15 +70,25 @@ __device__ __forceinline__ void vote_of(unsigned info, unsigned same, float w_lo
     dp = ((link != 0u && single) ? 1u : 0u) | ((qual && tA) ? (wi << 8) : 0u) | ((qual && tB) ? (wi << 20) : 0u);
 }
 
+__device__ __forceinline__ void build_vote_lut(float4 *lut) {
+    for (int i = threadIdx.x; i < SW_LUT; i += blockDim.x) {
+        const unsigned info = i & 31u, same = ((i >> 5) & 1u) ? 2u : 1u, cls = (unsigned)i >> 6;
+        float d1, d2; unsigned dp;
+        vote_of(info, same, cls == 2u ? (float)0.1 : 1.f, cls == 2u ? (float)0.1 : 20.f, cls == 0u, d1, d2, dp);
+        lut[i] = make_float4(d1, d2, __uint_as_float(dp), 0.f);
+    }
+}
+
 // the chain over nodes [k_begin, k_end), from an empty state at k_begin; decisions of nodes >= k_core go to flags[], those of the
 // W nodes before k_core to halo_flags[seg]
-__device__ __forceinline__ void sweep_range(const SweepArgs &a, SweepSmem &S, const int N, const int k_begin, const int k_core, const int k_end,
-                                            const int seg, const int lane) {
+__device__ __forceinline__ void sweep_range(const SweepArgs &a, SweepSmem &S, const float4 *__restrict__ lut, const int N, const int k_begin,
+                                            const int k_core, const int k_end, const int seg, const int lane) {
     float w1a = 0.f, w2a = 0.f, w1b = 0.f, w2b = 0.f;
     unsigned pka = 0u, pkb = 0u;
     int last_connect = -1, first_nb = INT_MAX;
     const int W = a.W, RS = a.RS;
     const int k_stop = min(k_end, N - 1);            // the loop of :313 needs a successor
+    const bool staged = seg >= 0 && k_stop - k_begin <= (int)sizeof(S.flags);
     if (k_begin < k_stop) {
         int c = k_begin / SW_CH;
         const int c_last = (k_stop - 1) / SW_CH;
@@ -126,27 +142,21 @@ __device__ __forceinline__ void sweep_range(const SweepArgs &a, SweepSmem &S, co
                     }
                 }
                 if (lane == 0) {
-                    if (k >= k_core) a.flags[k] = (uint8_t)f;
-                    else if (seg >= 0 && k >= k_core - W) a.halo_flags[(size_t)seg * W + (k - (k_core - W))] = (uint8_t)f;
+                    if (staged) S.flags[k - k_begin] = (uint8_t)f;
+                    else if (k >= k_core) a.flags[k] = (uint8_t)f;
                 }
                 if (votes) {
                     const int base = (k + 1) & ~15;
                     const uint8_t *row = S.rows[buf] + (k - k0) * RS;
-                    const unsigned same = hp == 1 ? 1u : 2u;
-                    const float w_lo = type == 4u ? (float)0.1 : 1.f, w_hi = type == 4u ? (float)0.1 : 20.f;
-                    const bool type_ok = type != 3u && type != 4u;
+                    const float4 *__restrict__ L = lut + (((type == 4u ? 2u : type == 3u ? 1u : 0u) << 6) | ((unsigned)(hp - 1) << 5));
                     const int j0 = (lane - base) & 31;
-                    bool slot = (((base + j0) >> 5) & 1) != 0;
-#pragma unroll
-                    for (int t = 0; t < 3; t++) {
-                        const int j = j0 + 32 * t;
-                        if (j < RS) {
-                            float d1, d2; unsigned dp;
-                            vote_of(row[j], same, w_lo, w_hi, type_ok, d1, d2, dp);
-                            if (slot) { w1b += d1; w2b += d2; pkb += dp; } else { w1a += d1; w2a += d2; pka += dp; }
-                        }
-                        slot = !slot;
-                    }
+                    const bool slot = (((base + j0) >> 5) & 1) != 0;           // slot of the node byte j0 votes on; byte j0 + 32 votes on the other slot
+                    float4 c0 = L[row[j0]], c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j0 + 32 < RS) c1 = L[row[j0 + 32]];
+                    if (RS > 64 && j0 + 64 < RS) { const float4 c2 = L[row[j0 + 64]]; c0.x += c2.x; c0.y += c2.y; c0.z = __uint_as_float(__float_as_uint(c0.z) + __float_as_uint(c2.z)); }
+                    const float4 ca = slot ? c1 : c0, cb = slot ? c0 : c1;
+                    w1a += ca.x; w2a += ca.y; pka += __float_as_uint(ca.z);
+                    w1b += cb.x; w2b += cb.y; pkb += __float_as_uint(cb.z);
                     last_connect = k + Lp1;
                 }
             }
@@ -154,11 +164,21 @@ __device__ __forceinline__ void sweep_range(const SweepArgs &a, SweepSmem &S, co
             buf ^= 1;
         }
     }
+    if (staged && k_begin < k_stop) {
+        __syncwarp();
+        for (int k = k_begin + lane; k < k_stop; k += 32) {
+            const uint8_t f = S.flags[k - k_begin];
+            if (k >= k_core) a.flags[k] = f;
+            else if (k >= k_core - W) a.halo_flags[(size_t)seg * W + (k - (k_core - W))] = f;
+        }
+    }
     if (seg >= 0 && lane == 0) a.first_nb[seg] = first_nb;
 }
 
 __global__ void __launch_bounds__(SW_WARPS * 32) k_sweep_segments(SweepArgs a) {
     __shared__ SweepSmem s_all[SW_WARPS];
+    __shared__ float4 s_lut[SW_LUT];
+    build_vote_lut(s_lut);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     SweepSmem &S = s_all[wib];
     if (lane == 0) { mbar_init(smem_u32(&S.mbar[0]), 1u); mbar_init(smem_u32(&S.mbar[1]), 1u); }
@@ -172,7 +192,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) k_sweep_segments(SweepArgs a) {
     if (lane == 0) for (int i = 0; i < a.W; i++) a.halo_flags[(size_t)p * a.W + i] = 0xFFu;
     __syncwarp();
     if (b >= N) { if (lane == 0) a.first_nb[p] = INT_MAX; return; }
-    sweep_range(a, S, N, max(0, b - a.halo), b, e, p, lane);
+    sweep_range(a, S, s_lut, N, max(0, b - a.halo), b, e, p, lane);
 }
 
 // boundary checks + flips (one CTA; thread p checks the boundary in front of segment p; the flips relative to the truth are a scan
@@ -228,13 +248,16 @@ __global__ void __launch_bounds__(1024) k_sweep_verify(SweepArgs a) {
 // the exact sequential chain, only when a boundary did not verify
 __global__ void __launch_bounds__(32) k_sweep_fallback(SweepArgs a) {
     __shared__ SweepSmem S;
+    __shared__ float4 s_lut[SW_LUT];
     if (*a.all_ok) return;
+    build_vote_lut(s_lut);
+    __syncwarp();
     const int lane = threadIdx.x;
     if (lane == 0) { mbar_init(smem_u32(&S.mbar[0]), 1u); mbar_init(smem_u32(&S.mbar[1]), 1u); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     const int N = *a.n_nodes;
-    sweep_range(a, S, N, 0, 0, N, -1, lane);
+    sweep_range(a, S, s_lut, N, 0, 0, N, -1, lane);
     for (int p = lane; p < a.n_seg; p += 32) a.seg_flip[p] = 0;
 }
 
