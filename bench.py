@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--no-other-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])
+    ap.add_argument("--cigar16", action="store_true")    # end-to-end leg: send the 16-bit CIGAR stream instead of the 8-bit wire format
     ap.add_argument("--cigar32", action="store_true")    # end-to-end leg: send BAM's uint32 CIGAR ops instead of the compact 16-bit stream
     ap.add_argument("--allow-unpinned", action="store_true")   # run contigs that have no committed digest (custom shapes); the line says so
     args = ap.parse_args()
@@ -456,8 +457,8 @@ def main():
     # ---- end-to-end leg: pinned host buffers through the C ABI ----
     e2e = None
     if not args.no_e2e:
-        # The host loop packs the CIGAR ops of every record into the compact 16-bit wire format while it appends the record to the
-        # batch (lps_pack_cigar16; include/lps.h).  The big streams are pinned in place (cudaHostRegister), the small ones copied.
+        # The host loop packs the CIGAR ops of every record into the 8-bit wire format while it appends the record to the batch
+        # (lps_pack_cigar8; include/lps.h); the device expands it into the resident 16-bit stream.  The big streams are pinned in place (cudaHostRegister), the small ones copied.
         cudart = torch.cuda.cudart()
         pinned_in_place, ptens, pin_batches = [], [], []
 
@@ -478,12 +479,27 @@ def main():
                 d["cigar"], ptr["cigar"] = pin(c.cigar)
                 b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
                                      **{k: C.cast(ptr[k], ptypes[k]) for k in names + ["cigar"]})
-            else:
+            elif args.cigar16:
                 d["cigar16"], ptr["cigar16"] = pin(pk[0])
                 if len(pk[1]):
                     d["cigar_long_len"], ptr["cigar_long_len"] = pin(pk[1])
                     d["cigar_long_at"], ptr["cigar_long_at"] = pin(pk[2])
                 b = batch_from(c, lambda k, ptr=ptr: ptr.get(k), pk)
+            else:
+                c8, esc16, esc_blk, long_len, long_at = c.pack_cigar8()
+                d["cigar8"], ptr["cigar8"] = pin(c8)
+                d["cigar_esc_blk"], ptr["cigar_esc_blk"] = pin(esc_blk)
+                b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
+                                     **{k: C.cast(ptr[k], ptypes[k]) for k in names})
+                b.cigar8, b.cigar_esc_blk = C.cast(ptr["cigar8"], ffi.u8p), C.cast(ptr["cigar_esc_blk"], ffi.u32p)
+                b.n_cigar_esc, b.n_cigar_long = len(esc16), len(long_len)
+                if len(esc16):
+                    d["cigar_esc16"], ptr["cigar_esc16"] = pin(esc16)
+                    b.cigar_esc16 = C.cast(ptr["cigar_esc16"], ffi.u16p)
+                if len(long_len):
+                    d["cigar_long_len"], ptr["cigar_long_len"] = pin(long_len)
+                    d["cigar_long_at"], ptr["cigar_long_at"] = pin(long_at)
+                    b.cigar_long_len, b.cigar_long_at = C.cast(ptr["cigar_long_len"], ffi.u32p), C.cast(ptr["cigar_long_at"], ffi.u64p)
             ptens.append(d)
             pin_batches.append(b)
         host_bytes = int(sum((t.nbytes if isinstance(t, np.ndarray) else t.numel()) for d in ptens for t in d.values()))
@@ -540,7 +556,9 @@ def main():
                        "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes, "parity_digest_ok": True,
                        "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
                                "CIGAR and per-read records are copied; h2d bytes are the library's own count",
-                       "cigar_wire_format": "uint32 (BAM), narrowed on the device" if args.cigar32 else "16-bit stream (lps_pack_cigar16), used as it arrives"}
+                       "cigar_wire_format": ("uint32 (BAM), narrowed on the device" if args.cigar32 else
+                                             "16-bit stream (lps_pack_cigar16), used as it arrives" if args.cigar16 else
+                                             "8-bit stream (lps_pack_cigar8), expanded into the resident 16-bit stream by k_expand_cigar8")}
     if rank == 0 and world == 1 and not args.no_other_paths:
         # ---- the other dialects of the hot path (BASELINE configs C3 / C4), kernel-resident device time of one call each ----
         other = {}

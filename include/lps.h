@@ -89,6 +89,19 @@ typedef struct {
     const uint32_t *cigar_long_len; /* [n_cigar_long]                                           */
     const uint64_t *cigar_long_at;  /* [n_cigar_long]                                           */
     uint64_t n_cigar_long;
+    /* --- optional wire format of the CIGAR stream in 8 bits per op (lps_batch_submit only) ------------------------------ *
+     * The CIGAR stream is what a batch sends over PCIe once SEQ / QUAL stay on the host, and long-read CIGARs are almost
+     * only short M / I / D ops.  When cigar8 != NULL, cigar[] and cigar16[] are ignored: cigar8[i] is
+     *     0x00..0x7F  M of 1..128 bases      0x80..0xB7  I of 1..56 bases      0xB8..0xEF  D of 1..56 bases
+     *     0xFF        any other op: the next unused entry of cigar_esc16[] (the op in the 16-bit encoding above; it may in
+     *                 turn be a 0xFFF escape into cigar_long_len / cigar_long_at, whose indices are op indices as before)
+     * cigar_esc_blk[k] = number of 0xFF bytes in cigar8[0 .. 256 k), k = 0 .. ceil(cigar_len / 256), so the device can expand
+     * the stream in parallel (k_expand_cigar8 writes the 16-bit stream the kernels read; results cannot differ).
+     * lps_pack_cigar8 produces all of it while the host appends records.                                              */
+    const uint8_t *cigar8;          /* [cigar_len]                                              */
+    const uint16_t *cigar_esc16;    /* [n_cigar_esc]                                            */
+    uint64_t n_cigar_esc;
+    const uint32_t *cigar_esc_blk;  /* [cigar_len / 256 + 2]                                    */
 } lps_read_batch;
 
 /* one allele call: replaces struct Variant (src/shared/Util.h:63-75)                        */
@@ -220,6 +233,13 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b);
  * small (nothing is written past long_cap).  Pure host code; thread-safe on disjoint outputs.                      */
 int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint16_t *out16, uint32_t *long_len,
                      uint64_t *long_at, uint64_t long_cap, uint64_t *n_long);
+/* The 8-bit wire format (lps_read_batch.cigar8): appends n BAM CIGAR ops.  out8[0..n) receives the bytes; ops that need it append
+ * their 16-bit form to esc16[] at slot *n_esc (advanced) and, when 4095 bases or longer, (length, base_index + i) to long_len[] /
+ * long_at[] at slot *n_long (advanced).  esc_blk[] is indexed by ABSOLUTE op index / 256 (the caller allocates
+ * total_ops / 256 + 2 entries for the whole stream and passes the same array to every call); entries up to the block that holds the
+ * last appended op + 1 are kept up to date.  Returns 0 or LPS_E_ARG when a table is too small.  Pure host code.            */
+int lps_pack_cigar8(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint8_t *out8, uint16_t *esc16, uint64_t esc_cap, uint64_t *n_esc,
+                    uint32_t *esc_blk, uint32_t *long_len, uint64_t *long_at, uint64_t long_cap, uint64_t *n_long);
 /* Same, for buffers that already live in device memory (a batch that stays resident across calls): nothing is copied except the
  * name ranks and flags the host needs (to group the alignments of one read name).  The arrays must stay valid until the next
  * submit on this context.  Either cigar (uint32 ops, narrowed into a buffer of the context) or cigar16 (+ its side table).  */

@@ -26,7 +26,8 @@ class LpsReadBatch(C.Structure):
                 ("cigar_off", u64p), ("seq_off", u64p), ("qual_off", u64p), ("flag", u16p), ("mapq", u8p),
                 ("name_rank", i32p), ("cigar", u32p), ("cigar_len", C.c_uint64), ("seq4", u8p),
                 ("seq_bytes", C.c_uint64), ("qual", u8p), ("qual_bytes", C.c_uint64),
-                ("cigar16", u16p), ("cigar_long_len", u32p), ("cigar_long_at", u64p), ("n_cigar_long", C.c_uint64)]
+                ("cigar16", u16p), ("cigar_long_len", u32p), ("cigar_long_at", u64p), ("n_cigar_long", C.c_uint64),
+                ("cigar8", u8p), ("cigar_esc16", u16p), ("n_cigar_esc", C.c_uint64), ("cigar_esc_blk", u32p)]
 
 
 class LpsBgzfBlock(C.Structure):
@@ -193,6 +194,8 @@ SYMBOLS = {
     "lps_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
     "lps_batch_submit_device": (C.c_int, [C.c_void_p, C.POINTER(LpsReadBatch)]),
     "lps_pack_cigar16": (C.c_int, [u32p, C.c_uint64, C.c_uint64, u16p, u32p, u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "lps_pack_cigar8": (C.c_int, [u32p, C.c_uint64, C.c_uint64, u8p, u16p, C.c_uint64, C.POINTER(C.c_uint64), u32p, u32p, u64p, C.c_uint64,
+                                  C.POINTER(C.c_uint64)]),
     "lps_phase_call_alleles": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsCalls)]),
     "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),

@@ -47,6 +47,38 @@ __global__ void k_narrow_cigar32(size_t n, const uint32_t *__restrict__ in, uint
     }
     *reinterpret_cast<uint4 *>(out + i8) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
 }
+// the 8-bit wire format -> the 16-bit stream: one warp per block of 256 ops (8 per lane: one 64-bit load, one 128-bit store); the
+// k-th 0xFF byte of the stream takes esc16[k], k = escapes before the block (host table) + escapes before the op inside the block
+__global__ void k_expand_cigar8(size_t n_ops, const uint8_t *__restrict__ in8, const uint16_t *__restrict__ esc16, const uint32_t *__restrict__ esc_blk,
+                                uint16_t *__restrict__ out) {
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t i8 = warp * 256 + (size_t)lane * 8;
+    if (warp * 256 >= n_ops) return;
+    unsigned long long w = 0x0101010101010101ull * 0u;
+    if (i8 + 8 <= n_ops) w = *reinterpret_cast<const unsigned long long *>(in8 + i8);
+    else for (int j = 0; j < 8; j++) if (i8 + j < n_ops) w |= (unsigned long long)in8[i8 + j] << (8 * j);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) c += (i8 + j < n_ops && ((w >> (8 * j)) & 0xFFull) == 0xFFull) ? 1 : 0;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    size_t e = (size_t)esc_blk[warp] + (size_t)(inc - c);
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t b = (uint32_t)((w >> (8 * j)) & 0xFFull);
+        uint32_t v;
+        if (b < 0x80u) v = ((b + 1u) << 4) | 0u;                       // M
+        else if (b < 0xB8u) v = ((b - 0x80u + 1u) << 4) | 1u;          // I
+        else if (b < 0xF0u) v = ((b - 0xB8u + 1u) << 4) | 2u;          // D
+        else v = (i8 + j < n_ops && b == 0xFFu) ? (uint32_t)esc16[e++] : 1u;
+        h[j] = v;
+    }
+    if (i8 < n_ops) *reinterpret_cast<uint4 *>(out + i8) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+
 __global__ void k_unpack_long_keys(unsigned int n, const unsigned long long *__restrict__ keys, uint64_t *__restrict__ at, uint32_t *__restrict__ len) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { at[i] = keys[i] >> 28; len[i] = (uint32_t)(keys[i] & 0xFFFFFFFull); }
@@ -288,7 +320,31 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_flag, b->flag, n));
     TRY(h2d(ctx, ctx->d_mapq, b->mapq, n));
     TRY(h2d(ctx, ctx->d_name_rank, b->name_rank, n));
-    if (b->cigar16) {
+    if (b->cigar8) {
+        if (b->n_cigar_long && (!b->cigar_long_len || !b->cigar_long_at)) return ctx->fail(LPS_E_ARG, "cigar8 without its long-op table");
+        if (!b->cigar_esc_blk || (b->n_cigar_esc && !b->cigar_esc16)) return ctx->fail(LPS_E_ARG, "cigar8 without its escape tables");
+        const size_t n_blk = (size_t)(b->cigar_len / 256) + 2;
+        if (b->cigar_esc_blk[0] != 0 || b->cigar_esc_blk[(b->cigar_len + 255) / 256] != b->n_cigar_esc)
+            return ctx->fail(LPS_E_ARG, "cigar_esc_blk does not match n_cigar_esc");
+        for (uint64_t i = 0; i < b->n_cigar_long; i++)
+            if (b->cigar_long_at[i] >= b->cigar_len || (b->cigar_long_len[i] >> 28) || (i && b->cigar_long_at[i] <= b->cigar_long_at[i - 1]))
+                return ctx->fail(LPS_E_ARG, "cigar_long_at / cigar_long_len are not a valid side table");
+        TRY(h2d(ctx, ctx->d_cigar8, b->cigar8, (size_t)b->cigar_len, 64));
+        TRY(h2d(ctx, ctx->d_cigar_esc16, b->cigar_esc16, (size_t)b->n_cigar_esc));
+        TRY(h2d(ctx, ctx->d_cigar_esc_blk, b->cigar_esc_blk, n_blk));
+        TRY(h2d(ctx, ctx->d_cigar_long_len, b->cigar_long_len, (size_t)b->n_cigar_long));
+        TRY(h2d(ctx, ctx->d_cigar_long_at, b->cigar_long_at, (size_t)b->n_cigar_long));
+        LPS_CUDA(ctx, ctx->d_cigar16.reserve((size_t)b->cigar_len + 64 + 256));
+        if (b->cigar_len) {
+            const size_t warps = ((size_t)b->cigar_len + 255) / 256;
+            k_expand_cigar8<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>((size_t)b->cigar_len, ctx->d_cigar8.p, ctx->d_cigar_esc16.p,
+                                                                                           ctx->d_cigar_esc_blk.p, ctx->d_cigar16.p);
+            ctx->stats.kernel_launches++;
+            LPS_CUDA(ctx, cudaGetLastError());
+        }
+        ctx->batch.cigar16 = ctx->d_cigar16.p; ctx->batch.long_at = ctx->d_cigar_long_at.p; ctx->batch.long_len = ctx->d_cigar_long_len.p;
+        ctx->batch.n_long = (uint32_t)b->n_cigar_long;
+    } else if (b->cigar16) {
         if (b->n_cigar_long && (!b->cigar_long_len || !b->cigar_long_at)) return ctx->fail(LPS_E_ARG, "cigar16 without its long-op table");
         for (uint64_t i = 0; i < b->n_cigar_long; i++)
             if (b->cigar_long_at[i] >= b->cigar_len || (b->cigar16[b->cigar_long_at[i]] >> 4) != 0xFFFu || (b->cigar_long_len[i] >> 28) ||
@@ -359,6 +415,36 @@ int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uin
         long_len[nl] = w >> 4; long_at[nl] = base_index + i; nl++;
     }
     *n_long = nl;
+    return LPS_OK;
+}
+
+int lps_pack_cigar8(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint8_t *out8, uint16_t *esc16, uint64_t esc_cap, uint64_t *n_esc,
+                    uint32_t *esc_blk, uint32_t *long_len, uint64_t *long_at, uint64_t long_cap, uint64_t *n_long) {
+    if ((n && (!cigar || !out8)) || !n_esc || !n_long || !esc_blk) return LPS_E_ARG;
+    uint64_t ne = *n_esc, nl = *n_long;
+    if (base_index == 0) esc_blk[0] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t at = base_index + i;
+        if ((at & 255u) == 0) esc_blk[at >> 8] = (uint32_t)ne;
+        const uint32_t w = cigar[i], op = w & 15u, len = w >> 4;
+        if (op == 0 && len >= 1 && len <= 128) out8[i] = (uint8_t)(len - 1);
+        else if (op == 1 && len >= 1 && len <= 56) out8[i] = (uint8_t)(0x80u + len - 1);
+        else if (op == 2 && len >= 1 && len <= 56) out8[i] = (uint8_t)(0xB8u + len - 1);
+        else {
+            if (ne >= esc_cap || !esc16) return LPS_E_ARG;
+            out8[i] = 0xFFu;
+            if (len < 0xFFFu) esc16[ne++] = (uint16_t)w;
+            else {
+                if (nl >= long_cap || !long_len || !long_at) return LPS_E_ARG;
+                esc16[ne++] = (uint16_t)(0xFFF0u | op);
+                long_len[nl] = len; long_at[nl] = at; nl++;
+            }
+        }
+    }
+    // the entries a reader of the stream so far needs: the block after the last op (ceil) carries the running total
+    esc_blk[(base_index + n + 255) >> 8] = (uint32_t)ne;
+    esc_blk[((base_index + n) >> 8) + 1] = (uint32_t)ne;
+    *n_esc = ne; *n_long = nl;
     return LPS_OK;
 }
 

@@ -171,6 +171,9 @@ struct lps_ctx {
     DevBuf<lps_bgzf_block> d_bgzf_blocks;
     std::vector<uint8_t> h_bgzf_status;
     DevBuf<uint16_t> d_cigar16;                     // the CIGAR stream in 16 bits per op (what the kernels read)
+    DevBuf<uint8_t> d_cigar8;                       // 8-bit wire format of a submitted batch, expanded into d_cigar16 on arrival
+    DevBuf<uint16_t> d_cigar_esc16;
+    DevBuf<uint32_t> d_cigar_esc_blk;
     DevBuf<unsigned int> d_n_long;                  // escaped ops found while narrowing a uint32 stream on the device
     DevBuf<uint64_t> d_long_keys;                   // ... (op index << 28 | length), sorted into the side table
     DevBuf<uint32_t> d_cigar_long_len;

@@ -246,6 +246,43 @@ class Contig:
             b.cigar_long_at = P(self._c16[2], _ffi.u64p)
         return b
 
+    def pack_cigar8(self):
+        """The 8-bit wire format of the CIGAR stream (include/lps.h, lps_read_batch.cigar8), made by the library's own lps_pack_cigar8
+        as the host loop would while appending records.  Returns (cigar8, esc16, esc_blk, long_len, long_at)."""
+        n = len(self.cigar)
+        op, ln = self.cigar & 15, self.cigar >> 4
+        short = ((op == 0) & (ln >= 1) & (ln <= 128)) | ((op == 1) & (ln >= 1) & (ln <= 56)) | ((op == 2) & (ln >= 1) & (ln <= 56))
+        n_esc_want, n_long_want = int((~short).sum()), int(((~short) & (ln >= 0xFFF)).sum())
+        c8 = np.zeros(max(n, 1), np.uint8)
+        esc16 = np.zeros(max(n_esc_want, 1), np.uint16)
+        esc_blk = np.zeros(n // 256 + 2, np.uint32)
+        long_len, long_at = np.zeros(max(n_long_want, 1), np.uint32), np.zeros(max(n_long_want, 1), np.uint64)
+        n_esc, n_long = C.c_uint64(0), C.c_uint64(0)
+        P = _ffi.ptr
+        rc = _ffi.load_library().lps_pack_cigar8(P(self.cigar, _ffi.u32p), n, 0, P(c8, _ffi.u8p), P(esc16, _ffi.u16p), n_esc_want, C.byref(n_esc),
+                                                 P(esc_blk, _ffi.u32p), P(long_len, _ffi.u32p), P(long_at, _ffi.u64p), n_long_want, C.byref(n_long))
+        if rc != 0 or n_esc.value != n_esc_want or n_long.value != n_long_want:
+            raise RuntimeError(f"lps_pack_cigar8 failed: rc {rc}, {n_esc.value} of {n_esc_want} escapes, {n_long.value} of {n_long_want} long ops")
+        return c8[:n], esc16[:n_esc_want], esc_blk, long_len[:n_long_want], long_at[:n_long_want]
+
+    def batch_struct8(self):
+        """batch_struct() with the CIGAR in the 8-bit wire format; the arrays are kept alive on the object."""
+        self._c8 = self.pack_cigar8()
+        c8, esc16, esc_blk, long_len, long_at = self._c8
+        b = self.batch_struct()
+        P = _ffi.ptr
+        b.cigar = C.cast(None, _ffi.u32p)
+        b.cigar8 = P(c8 if len(c8) else np.zeros(1, np.uint8), _ffi.u8p)
+        b.cigar_esc_blk = P(esc_blk, _ffi.u32p)
+        b.n_cigar_esc = len(esc16)
+        if len(esc16):
+            b.cigar_esc16 = P(esc16, _ffi.u16p)
+        b.n_cigar_long = len(long_len)
+        if len(long_len):
+            b.cigar_long_len = P(long_len, _ffi.u32p)
+            b.cigar_long_at = P(long_at, _ffi.u64p)
+        return b
+
     def name(self, i):
         s = self.names[i * self.NAME_STRIDE:(i + 1) * self.NAME_STRIDE]
         return s[:s.index(b"\0")].decode()

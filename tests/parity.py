@@ -66,6 +66,11 @@ def check_phase(contig, params, ctx=None, verbose=False):
         res3 = ctx.phase_contig(params)
         for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
             assert np.array_equal(res3[k], res[k]), f"cigar16 submit: {k} differs"
+        # ... and the 8-bit wire format (lps_read_batch.cigar8)
+        ctx.submit(contig.batch_struct8())
+        res4 = ctx.phase_contig(params)
+        for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
+            assert np.array_equal(res4[k], res[k]), f"cigar8 submit: {k} differs"
         info = dict(reads=contig.n_reads, variants=contig.n_var, calls=len(orc.calls), nodes=orc.n_nodes,
                     phased=int(m.sum()), contrib=int(orc.n_contrib), lowq_cells=int((orc.weights != np.round(orc.weights)).sum()),
                     stats=ctx.stats())
