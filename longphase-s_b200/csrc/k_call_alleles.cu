@@ -50,6 +50,9 @@ namespace {
 #ifndef LPS_PREFETCH_VREC
 #define LPS_PREFETCH_VREC 1    // variant records of the first phase-2 round requested before phase 1
 #endif
+#ifndef LPS_SPLIT_CHAINS
+#define LPS_SPLIT_CHAINS 1
+#endif
 #ifndef LPS_STATIC_SHARE
 #define LPS_STATIC_SHARE 85    // per cent of the work list dealt out statically (item k * warps + warp); the rest is claimed from a global counter
 #endif
@@ -549,6 +552,20 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
             // advance sums of the lane's two groups of 8 ops: per pair of ops one table word (flags of both op codes) and two
             // dot products of the two 12-bit lengths with them
             unsigned rs = 0, qs = 0, r0 = 0, q0 = 0, acc = 0;
+#if LPS_SPLIT_CHAINS
+            // the two groups of 8 ops accumulate independently: dependent chains of 4 dot products instead of 8
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned x = w[j], y = w[j + 4];
+                const unsigned fx = s_pair[(x & 0xFu) | ((x >> 12) & 0xF0u)], fy = s_pair[(y & 0xFu) | ((y >> 12) & 0xF0u)];
+                // the length fields stay where they are (16 x the length per half word); the sums are scaled back once
+                const unsigned lx = x & 0xFFF0FFF0u, ly = y & 0xFFF0FFF0u;
+                r0 = __dp2a_lo(lx, fx, r0); q0 = __dp2a_hi(lx, fx, q0);
+                rs = __dp2a_lo(ly, fy, rs); qs = __dp2a_hi(ly, fy, qs);
+                acc |= x | y;
+            }
+            rs = (rs + r0) >> 4; qs = (qs + q0) >> 4; r0 >>= 4; q0 >>= 4;
+#else
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const unsigned x = w[j];
@@ -559,6 +576,7 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                 acc |= x;
                 if (j == 3) { r0 = rs; q0 = qs; }
             }
+#endif
             // an escaped length (field == 0xFFF) somewhere in the lane's ops?  (the OR can only err towards "yes")
             const bool esc = ((acc >> 4) & 0xFFFu) == 0xFFFu || (acc >> 20) == 0xFFFu;
             if (__any_sync(FULL, esc)) {

@@ -339,20 +339,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
             e0 = (lane < W && i0 < nm) ? M[i0] : 0xffffffffu;
             e1 = (lane < W2 && i1 < nm) ? M[i1] : 0xffffffffu;
         };
-        uint32_t m_cur = 0, m_nxt = 0, ea = 0, gend = 0, e0 = 0xffffffffu, e1 = 0xffffffffu;
-        if (t0 < t1) { m_cur = list[t0]; fetch(m_cur, ea, gend, e0, e1); }
-        if (t0 + 1u < t1) m_nxt = list[t0 + 1u];
         unsigned c32 = 0, f32 = 0;                         // per-lane counts of this node (<= 2 per call), widened once at the end
         const float wlo = (float)edge_weight;
         (void)wlo;
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t m = m_cur, ea_c = ea, gend_c = gend;
-            uint32_t eb0 = e0, eb1 = e1;
-            if (t + 1u < t1) {
-                m_cur = m_nxt;
-                fetch(m_cur, ea, gend, e0, e1);
-                if (t + 2u < t1) m_nxt = list[t + 2u];
-            }
+        auto fold_call = [&](const uint32_t m, const uint32_t ea_c, const uint32_t gend_c, uint32_t eb0, uint32_t eb1) {
             const unsigned al_a = (ea_c >> 1) & 1u, hi_a = ea_c & 1u;
             const bool act0 = lane < W && m + 1u + (uint32_t)lane < gend_c;
             const bool act1 = lane < W2 && m + 33u + (uint32_t)lane < gend_c;
@@ -409,6 +399,19 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
                 }
             }
             __syncwarp();
+        };
+        // (unrolling by two with two register sets, to save the moves of the hand-over, changed nothing: 0.223 ms either way)
+        uint32_t mA = 0, eaA = 0, gendA = 0, e0A = 0xffffffffu, e1A = 0xffffffffu, mB = 0;
+        if (t0 < t1) { mA = list[t0]; fetch(mA, eaA, gendA, e0A, e1A); }
+        if (t0 + 1u < t1) mB = list[t0 + 1u];
+        for (uint32_t t = t0; t < t1; t++) {
+            const uint32_t m = mA, ea_c = eaA, gend_c = gendA, b0 = e0A, b1 = e1A;
+            if (t + 1u < t1) {
+                mA = mB;
+                fetch(mA, eaA, gendA, e0A, e1A);
+                if (t + 2u < t1) mB = list[t + 2u];
+            }
+            fold_call(m, ea_c, gend_c, b0, b1);
         }
         contrib += c32; far += f32;
     } else {
