@@ -440,9 +440,10 @@ def main():
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r02_k1_traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("reads") == contig0.n_reads:
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        tj = json.load(open(tpath))                     # a list of captured launches; the one of this contig (same read count) counts
+        for e in (tj if isinstance(tj, list) else [tj]):
+            if e.get("reads") == contig0.n_reads:
+                traffic, traffic_src = e["dram_bytes_per_launch"], e["source"]
     achieved = b1 / (k1 * 1e-3) / 1e9 if k1 > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_call_alleles", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": b1, "kernel_ms": k1,
