@@ -481,6 +481,22 @@ typedef struct {
 } lps_somatic_call_result;
 /* Returns LPS_E_DATA where the reference prints "[ERROR](calibrate read HP) ..." / "(statistic all read HP) ..." and exits. */
 int lps_somatic_call(const lps_somatic_call_input *in, lps_somatic_call_result *out);
+/* SomaticVarFilterParams as setFilterParamsWithPurity fills it for a purity (SomaticVarCaller.h:59-104, SomaticVarCaller.cpp:951-1045):
+ * what lps_somatic_call applies, for the header of the calling log (<prefix>_somatic_var.out).                               */
+typedef struct {
+    int32_t tier;                                  /* 1 (purity 0.9-1.0) .. 5 (below 0.3 or out of range)                     */
+    float tumor_purity, nor_vaf_max;
+    int32_t nor_depth_min;
+    float messy_read_ratio;
+    int32_t read_count_min;
+    float hap_consistency_vaf_max;
+    int32_t hap_consistency_read_count_max, hap_consistency_somatic_read_min;
+    float interval_snp_count_vaf_max;
+    int32_t interval_snp_count_read_count_max, interval_snp_count_min;
+    float z_score_max, dense_alt_condition1, dense_alt_condition2;
+    int32_t dense_alt_same_count_min;
+} lps_somatic_filter_params;
+int lps_somatic_filter_params_of(double purity, lps_somatic_filter_params *out);
 
 
 /* ---- timing / accounting ------------------------------------------------------------------ */

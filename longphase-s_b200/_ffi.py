@@ -212,6 +212,7 @@ SYMBOLS = {
     "lps_set_blocking_sync": (C.c_int, [C.c_int, C.c_int]),
     "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
     "lps_somatic_call": (C.c_int, [C.POINTER(LpsSomaticCallInput), C.POINTER(LpsSomaticCallResult)]),
+    "lps_somatic_filter_params_of": (C.c_int, [C.c_double, C.c_void_p]),
     "lps_get_stats": (C.c_int, [C.c_void_p, C.POINTER(LpsStats)]),
     "lps_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "lps_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

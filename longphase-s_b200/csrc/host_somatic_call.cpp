@@ -75,6 +75,21 @@ int judge_somatic_read_hap(int hp1, int hp2, int hp3, int hp4, int n_ps, double 
 
 }  // namespace
 
+int lps_somatic_filter_params_of(double purity, lps_somatic_filter_params *out) {
+    if (!out) return LPS_E_ARG;
+    const int tier = tier_of(purity);
+    const FilterParams p = params_of(tier);
+    out->tier = tier; out->tumor_purity = (float)purity; out->nor_vaf_max = p.norVAF_maxThr; out->nor_depth_min = p.norDepth_minThr;
+    out->messy_read_ratio = p.MessyReadRatioThreshold; out->read_count_min = p.ReadCount_minThr;
+    out->hap_consistency_vaf_max = p.HapConsistency_VAF_maxThr; out->hap_consistency_read_count_max = p.HapConsistency_ReadCount_maxThr;
+    out->hap_consistency_somatic_read_min = p.HapConsistency_somaticRead_minThr;
+    out->interval_snp_count_vaf_max = p.IntervalSnpCount_VAF_maxThr; out->interval_snp_count_read_count_max = p.IntervalSnpCount_ReadCount_maxThr;
+    out->interval_snp_count_min = p.IntervalSnpCount_minThr; out->z_score_max = p.zScore_maxThr;
+    out->dense_alt_condition1 = p.DenseAlt_condition1_thr; out->dense_alt_condition2 = p.DenseAlt_condition2_thr;
+    out->dense_alt_same_count_min = p.DenseAlt_sameCount_minThr;
+    return LPS_OK;
+}
+
 int lps_somatic_call(const lps_somatic_call_input *in, lps_somatic_call_result *out) {
     if (!in || !out || !in->normal || !in->tumor || in->n_tum < 0) return LPS_E_ARG;
     const lps_extract_result &N = *in->normal, &T = *in->tumor;

@@ -10,8 +10,10 @@
 //   SomaticHaplotagChrProcessor::processRead / addAuxiliaryTags   src/somatic_haplotag/SomaticHaplotagProcess.cpp:310-400, 464-472
 // The device judges whole batches (lps_extract_normal / lps_extract_tumor / lps_somatic_tag_reads); purity and calling are the
 // host stages of liblps_b200.so (lps_estimate_purity, lps_somatic_call).
-// Scope notes: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file and --mod-file are
-// parsed but rejected (benchmark tooling and text logs outside the rebuilt hot path).
+//   SomaticVarCaller::writeSomaticVarCallingLog     src/somatic_haplotag/SomaticVarCaller.cpp:1576-1926  (<prefix>_somatic_var.out)
+// Scope notes: --log, --truth-vcf, --truth-bed, --sv-file and --mod-file are parsed but rejected (benchmark tooling and text logs
+// outside the rebuilt hot path); --somatic-calling-log writes <prefix>_somatic_var.out, the file of BASELINE.md's parity
+// gate, and none of the other debugging logs that switch produces in the reference.
 #include "host_common.h"
 
 #include <getopt.h>
@@ -44,7 +46,7 @@ const char *SOM_USAGE =
     "      --output-somatic-vcf            write <prefix>_sc.vcf: the tumor VCF's SNP / indel records, FILTER PASS for called somatic\n"
     "                                      variants and LowQual for the others. default: false.\n"
     "      --cram                          the output file will be in the cram format. default:bam\n"
-    "not available in this build: --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file, --mod-file\n";
+    "not available in this build: --log, --truth-vcf, --truth-bed, --sv-file, --mod-file\n";
 
 enum { S_HELP = 1, S_SUP, S_SV, S_MOD, S_REGION, S_CRAM, S_LOG, S_TUM_SNP, S_TUM_BAM, S_DISABLE_FILTER, S_PURITY, S_OUT_VCF, S_CALL_LOG,
        S_TRUTH_VCF, S_TRUTH_BED, S_BENCH_LOG };
@@ -81,6 +83,7 @@ struct SomOptions {
     bool tag_supplementary = false, estimate_purity = true, enable_filter = true, unsupported = false;
     bool cram = false;
     bool write_sc_vcf = false;  // --output-somatic-vcf: <prefix>_sc.vcf
+    bool write_calling_log = false;   // --somatic-calling-log: <prefix>_somatic_var.out (the other debugging logs of that switch are not written)
     bool purity_only = false;   // the `estimate_purity` sub-command (PurityEstimation.cpp): extract passes + purity, no calling, no tagging
     std::string snp_file, bam, tumor_vcf, tumor_bam, fasta, prefix = "result", region, command = "longphase-s ";
 };
@@ -97,7 +100,7 @@ struct UnionVar {
 // only until its next call)
 struct ExtractCopy {
     bool set = false;
-    std::vector<int32_t> tum_var, pos_base, read_hp_count, somatic_read_hp_count, window_hist, case_read_count, h1, h2, h3, end_pos;
+    std::vector<int32_t> tum_var, pos_base, read_hp_count, somatic_read_hp_count, window_hist, case_read_count, case_count, h1, h2, h3, end_pos;
     std::vector<float> ratios_f;
     std::vector<double> ratios_d;
     std::vector<uint8_t> category, n_ps;
@@ -110,7 +113,7 @@ struct ExtractCopy {
         const size_t nt = (size_t)r.n_tum, nr = (size_t)r.reads.n_reads;
         put(tum_var, r.tum_var, nt); put(pos_base, r.pos_base, nt * LPS_PB_FIELDS); put(read_hp_count, r.read_hp_count, nt * 9);
         put(somatic_read_hp_count, r.somatic_read_hp_count, nt * 9); put(window_hist, r.window_hist, nt * 2 * LPS_WINDOW_BINS);
-        put(case_read_count, r.case_read_count, nt); put(ratios_f, r.ratios_f, nt * LPS_RF_FIELDS); put(ratios_d, r.ratios_d, nt * LPS_RD_FIELDS);
+        put(case_read_count, r.case_read_count, nt); put(case_count, r.case_count, nt * LPS_CASE_FIELDS); put(ratios_f, r.ratios_f, nt * LPS_RF_FIELDS); put(ratios_d, r.ratios_d, nt * LPS_RD_FIELDS);
         put(category, r.reads.category, nr); put(read_hp, r.reads.read_hp, nr); put(h1, r.reads.h1, nr); put(h2, r.reads.h2, nr);
         put(h3, r.reads.h3, nr); put(n_ps, r.reads.n_ps, nr); put(end_pos, r.reads.end_pos, nr);
         put(call_off, r.call_off, r.call_off ? nr + 1 : 0); put(calls, r.calls, r.calls ? (size_t)r.n_calls : 0);
@@ -127,7 +130,7 @@ struct ExtractCopy {
         r.reads.category = ptr(category); r.reads.read_hp = ptr(read_hp); r.reads.h1 = ptr(h1); r.reads.h2 = ptr(h2); r.reads.h3 = ptr(h3);
         r.reads.n_ps = ptr(n_ps); r.reads.end_pos = ptr(end_pos);
         r.somatic_read_hp_count = ptr(somatic_read_hp_count); r.window_hist = ptr(window_hist); r.case_read_count = ptr(case_read_count);
-        r.ratios_f = ptr(ratios_f); r.ratios_d = ptr(ratios_d);
+        r.ratios_f = ptr(ratios_f); r.ratios_d = ptr(ratios_d); r.case_count = ptr(case_count);
         r.n_calls = calls.size(); r.call_off = ptr(call_off); r.calls = ptr(calls);
         return r;
     }
@@ -149,6 +152,10 @@ struct TumorArrays {   // lps_tumor_variants of one contig
 
 struct ContigState {
     ExtractCopy normal, tumor;
+    // per tumor slot, kept for the calling log: lps_somatic_call's products and SomaticData::statisticPurity
+    std::vector<uint8_t> is_somatic, is_filter_out, in_dense, used_for_purity;
+    std::vector<float> mean_alt, z_score;
+    std::vector<int32_t> interval_snp_count, min_distance;
 };
 
 }  // namespace
@@ -207,7 +214,8 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
             case S_PURITY: if (o.purity_only) bad = true; else { lpsh::take(optarg, o.purity); o.estimate_purity = false; } break;
             case S_OUT_VCF: if (o.purity_only) bad = true; else o.write_sc_vcf = true; break;
             case S_CRAM: if (o.purity_only) bad = true; else o.cram = true; break;
-            case S_LOG: case S_SV: case S_MOD: case S_CALL_LOG: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
+            case S_CALL_LOG: o.write_calling_log = true; break;
+            case S_LOG: case S_SV: case S_MOD: case S_TRUTH_VCF: case S_TRUTH_BED: case S_BENCH_LOG:
                 o.unsupported = true; break;
             case S_HELP: std::cout << SOM_USAGE << std::endl; return 2;
             default: bad = true;
@@ -231,7 +239,7 @@ int parse_som_options(int argc, char **argv, SomOptions &o) {
         bad = true;
     }
     if (o.unsupported) {
-        std::cerr << "[ERROR] " << prog << ": --log, --somatic-calling-log, --truth-vcf, --truth-bed, --sv-file and --mod-file "
+        std::cerr << "[ERROR] " << prog << ": --log, --truth-vcf, --truth-bed, --sv-file and --mod-file "
                      "are not available in this build.\n";
         bad = true;
     }
@@ -418,6 +426,105 @@ int write_sc_vcf(lpsh_som &job) {
     return 0;
 }
 
+// SomaticVarCaller::writeSomaticVarCallingLog (SomaticVarCaller.cpp:1576-1926): one row per position called somatic, every column in
+// the reference's own type (float / double / int / bool) so that operator<< prints the same characters
+int write_somatic_var_out(lpsh_som &job) {
+    const SomOptions &o = job.opt;
+    const std::string path = o.prefix + "_somatic_var.out";
+    std::ofstream f(path.c_str());
+    if (!f.is_open()) { std::cerr << "Fail to open write file: " << path << "\n"; exit(1); }
+    std::cerr << "writing somatic variants calling log ... ";
+    std::time_t begin = time(NULL);
+    int total = 0;
+    for (size_t c = 0; c < job.chr_names.size(); c++)
+        for (uint8_t v : job.contig[c].is_somatic) total += v ? 1 : 0;
+    lps_somatic_filter_params fp;
+    lps_somatic_filter_params_of(job.purity, &fp);
+    f << "####################################\n#   Somatic Variants Calling Log   #\n####################################\n";
+    f << "##normalSnpFile:" << o.snp_file << "\n##tumorSnvFile:" << o.tumor_vcf << "\n##bamFile:" << o.bam << "\n##tumorBamFile:" << o.tumor_bam << "\n"
+      << "##resultPrefix:" << o.prefix << "\n##numThreads:" << o.threads << "\n##region:" << o.region << "\n##qualityThreshold:" << o.quality << "\n"
+      << "##percentageThreshold:" << o.percentage << "\n##tagSupplementary:" << o.tag_supplementary << "\n##\n";
+    f << "##======== Filter Parameters =========\n##Enable filter : " << o.enable_filter << "\n##Calling mapping quality :" << o.quality << "\n"
+      << "##Tumor purity : " << fp.tumor_purity << "\n##Normal VAF maximum threshold : " << fp.nor_vaf_max << "\n"
+      << "##Normal depth minimum threshold : " << fp.nor_depth_min << "\n##Messy read ratio threshold : " << fp.messy_read_ratio << "\n"
+      << "##Somatic read count minimum threshold : " << fp.read_count_min << "\n"
+      << "##Haplotag consistency filter VAF threshold : " << fp.hap_consistency_vaf_max << "\n"
+      << "##Haplotag consistency filter read count threshold : " << fp.hap_consistency_read_count_max << "\n"
+      << "##Haplotag consistency somatic read count minimum threshold : " << fp.hap_consistency_somatic_read_min << "\n"
+      << "##Interval SNP count filter threshold : " << fp.interval_snp_count_vaf_max << "\n"
+      << "##Interval SNP count filter read count threshold : " << fp.interval_snp_count_read_count_max << "\n"
+      << "##Interval SNP count minimum threshold : " << fp.interval_snp_count_min << "\n##Z-score maximum threshold : " << fp.z_score_max << "\n"
+      << "##DenseAlt filter condition1 threshold : " << fp.dense_alt_condition1 << "\n##DenseAlt filter condition2 threshold : " << fp.dense_alt_condition2 << "\n"
+      << "##DenseAlt filter minimum same count threshold : " << fp.dense_alt_same_count_min << "\n##==================================== \n##\n"
+      << "##Total Somatic SNPs: " << total << "\n##\n";
+    static const char *COLS[] = {"#CHROM", "POS", "ID", "REF", "ALT", "AltCount", "ReadCount", "NorAltCount", "PureH1-1", "PureH2-1", "PureH3", "MixedHpRead", "UnTag",
+        "PureH1-1ratio", "PureH2-1ratio", "PureH3ratio", "MixedHpReadRatio", "NorVAF", "TumVAF", "NorMpqVAF", "TumMpqVAF", "NorVAF_substract", "TumVAF_substract",
+        "NorDepth", "TumDepth", "Subtract_Depth", "NorDeletionCount", "TumDeletionCount", "NorDeletionRatio", "TumDeletionRatio", "NorMpqReadRatio", "TumMpqReadRatio",
+        "ShannonEntropy", "HomopolymerLength", "H1readCount", "H2readCount", "H1_1readCount", "H2_1readCount", "H3readCount", "GermlineReadHpCount",
+        "GermlineReadHpImbalanceRatio", "SomaticReadHpImbalanceRatio", "BaseGermlineReadHpImbalanceRatio", "PercentageOfGermlineHp", "H1readCountInNorBam",
+        "H2readCountInNorBam", "GermlineReadHpCountInNorBam", "GermlineReadHpImbalanceRatioInNorBam", "PercentageOfGermlineHpInNorBam",
+        "GermlineReadHpImbalanceRatioDifference", "PercentageOfGermlineHpDifference", "SomaticRead_H1-1", "SomaticRead_H2-1", "SomaticRead_H3", "SomaticRead_unTag",
+        "AltMeanCountPerVarRead", "zScore", "IntervalSnpCount", "IntervalMinDistance", "ExistNorSnp", "StatisticPurity", "isFilterOut", "NorNonDelAF", "TumNonDelAF"};
+    for (const char *col : COLS) f << col << "\t";
+    f << "GT\n";
+    enum { HP_UNTAG_ = 0, HP_H1_ = 1, HP_H2_ = 2, HP_H3_ = 3, HP_H1_1_ = 5, HP_H2_1_ = 7 };   // ReadHP (HaplotagType.h:97-108)
+    for (size_t c = 0; c < job.chr_names.size(); c++) {
+        const std::string &chr = job.chr_names[c];
+        const ContigState &S = job.contig[c];
+        const ExtractCopy &N = S.normal, &T = S.tumor;
+        const size_t nt = T.tum_var.size();
+        if (S.is_somatic.size() != nt) continue;
+        size_t k = 0;
+        const auto &vars = job.variants[chr];
+        for (auto it = vars.begin(); it != vars.end(); ++it) {
+            if (!it->second.has_tum) continue;
+            const size_t s = k++;
+            if (s >= nt || !S.is_somatic[s]) continue;
+            const UnionVar &u = it->second;
+            if (u.tum.ref.empty() || u.tum.alt.empty()) {
+                std::cerr << "[ERROR](write tag HP3 log file) => can't find RefBase or AltBase : chr:" << chr << " pos: " << it->first + 1 << " RefBase:" << u.tum.ref << " AltBase:" << u.tum.alt;
+                exit(1);
+            }
+            const int32_t *tb = &T.pos_base[s * LPS_PB_FIELDS], *nb = &N.pos_base[s * LPS_PB_FIELDS];
+            const int32_t *cc = &T.case_count[s * LPS_CASE_FIELDS];
+            const float *tf = &T.ratios_f[s * LPS_RF_FIELDS], *nf = &N.ratios_f[s * LPS_RF_FIELDS];
+            const double *td = &T.ratios_d[s * LPS_RD_FIELDS], *nd = &N.ratios_d[s * LPS_RD_FIELDS];
+            const int32_t *thp = &T.read_hp_count[s * 9], *nhp = &N.read_hp_count[s * 9], *shp = &T.somatic_read_hp_count[s * 9];
+            const int norDepth = nb[LPS_PB_DEPTH], tumDepth = tb[LPS_PB_DEPTH], subtractDepth = tumDepth - norDepth;
+            const float tumVAF = tf[LPS_RF_VAF], tumMpqVAF = tf[LPS_RF_MPQ_VAF], norVAF = nf[LPS_RF_VAF], norMpqVAF = nf[LPS_RF_MPQ_VAF];
+            const float norVAF_substract = (norMpqVAF - norVAF), tumVAF_substract = (tumMpqVAF - tumVAF);
+            const int germlineReadHpCount = thp[HP_H1_] + thp[HP_H2_], germlineReadHpCountInNorBam = nhp[HP_H1_] + nhp[HP_H2_];
+            const double germlineReadHpImbalanceRatioDifference = td[LPS_RD_GERMLINE_IMBALANCE] - nd[LPS_RD_GERMLINE_IMBALANCE];
+            const double percentageOfGermlineHpDifference = td[LPS_RD_PCT_GERMLINE_HP] - nd[LPS_RD_PCT_GERMLINE_HP];
+            double zScore = -1.0;
+            if (S.in_dense[s]) {
+                if (S.z_score[s] < 0.0) { std::cerr << "[ERROR](zScore) => chr: " << chr << " pos: " << it->first + 1 << " zScore: " << S.z_score[s] << std::endl; exit(1); }
+                zScore = S.z_score[s];
+            }
+            const char *gt = u.tum.gt_kind == 3 ? "Homo" : u.tum.gt_kind == 1 ? "Hetero" : u.tum.gt_kind == 2 ? "UnphasedHetero" : "";
+            const double shannonEntropy = 0.0;                       // SomaticData members the reference never assigns
+            const int homopolymerLength = 0;
+            f << chr << " \t" << it->first + 1 << "\t" << "." << "\t" << u.tum.ref << "\t" << u.tum.alt << "\t" << tb[LPS_PB_ALT] << "\t" << T.case_read_count[s] << "\t\t"
+              << nb[LPS_PB_ALT] << "\t" << cc[LPS_CASE_PURE_H1_1] << "\t" << cc[LPS_CASE_PURE_H2_1] << "\t" << cc[LPS_CASE_PURE_H3] << "\t" << cc[LPS_CASE_MIXED] << "\t"
+              << cc[LPS_CASE_UNTAG] << "\t\t" << tf[LPS_RF_PURE_H1_1_RATIO] << "\t" << tf[LPS_RF_PURE_H2_1_RATIO] << "\t" << tf[LPS_RF_PURE_H3_RATIO] << "\t"
+              << tf[LPS_RF_MIXED_RATIO] << "\t\t" << norVAF << "\t" << tumVAF << "\t\t" << norMpqVAF << "\t" << tumMpqVAF << "\t\t" << norVAF_substract << "\t"
+              << tumVAF_substract << "\t\t" << norDepth << "\t" << tumDepth << "\t" << subtractDepth << "\t" << nb[LPS_PB_DEL] << "\t" << tb[LPS_PB_DEL] << "\t"
+              << nf[LPS_RF_DEL_RATIO] << "\t" << tf[LPS_RF_DEL_RATIO] << "\t" << nf[LPS_RF_LOW_MPQ_RATIO] << "\t" << tf[LPS_RF_LOW_MPQ_RATIO] << "\t"
+              << shannonEntropy << "\t" << homopolymerLength << "\t\t" << thp[HP_H1_] << "\t" << thp[HP_H2_] << "\t" << thp[HP_H1_1_] << "\t" << thp[HP_H2_1_] << "\t"
+              << thp[HP_H3_] << "\t" << germlineReadHpCount << "\t" << td[LPS_RD_GERMLINE_IMBALANCE] << "\t" << td[LPS_RD_SOMATIC_IMBALANCE] << "\t"
+              << td[LPS_RD_ALLELIC_IMBALANCE] << "\t" << td[LPS_RD_PCT_GERMLINE_HP] << "\t" << nhp[HP_H1_] << "\t" << nhp[HP_H2_] << "\t" << germlineReadHpCountInNorBam << "\t"
+              << nd[LPS_RD_GERMLINE_IMBALANCE] << "\t" << nd[LPS_RD_PCT_GERMLINE_HP] << "\t" << germlineReadHpImbalanceRatioDifference << "\t"
+              << percentageOfGermlineHpDifference << "\t" << shp[HP_H1_1_] << "\t" << shp[HP_H2_1_] << "\t" << shp[HP_H3_] << "\t" << shp[HP_UNTAG_] << "\t"
+              << S.mean_alt[s] << "\t" << zScore << "\t" << S.interval_snp_count[s] << "\t" << S.min_distance[s] << "\t" << u.has_nor << "\t"
+              << (bool)(S.used_for_purity.size() == nt && S.used_for_purity[s]) << "\t" << (bool)S.is_filter_out[s] << "\t" << nf[LPS_RF_NONDEL_VAF] << "\t"
+              << tf[LPS_RF_NONDEL_VAF] << "\t" << gt << "\n";
+        }
+    }
+    f.close();
+    std::cerr << difftime(time(NULL), begin) << "s\n";
+    return 0;
+}
+
 std::string contig_region(const lpsh_som &job, const std::string &chr) {
     return !job.opt.region.empty() ? job.opt.region : chr + ":1-" + std::to_string(job.chr_length.at(chr));
 }
@@ -542,6 +649,7 @@ int lpsh_som_estimate(lpsh_som *h) {
         std::cerr << "estimating tumor purity ... ";
         std::vector<double> t_imb, n_imb, n_pct;
         std::vector<int32_t> n_h1, n_h2;
+        std::vector<std::pair<size_t, size_t>> where;     // (contig, tumor slot) of every entry handed to the estimator
         for (size_t c = 0; c < nc; c++) {
             const ExtractCopy &N = h->contig[c].normal, &T = h->contig[c].tumor;
             if (N.tum_var.size() != T.tum_var.size()) return lpsh::fail("normal and tumor extract results of " + h->chr_names[c] + " differ in size");
@@ -552,6 +660,7 @@ int lpsh_som_estimate(lpsh_som *h) {
                 n_pct.push_back(N.ratios_d[k * LPS_RD_FIELDS + LPS_RD_PCT_GERMLINE_HP]);
                 n_h1.push_back(N.read_hp_count[k * 9 + 1]);
                 n_h2.push_back(N.read_hp_count[k * 9 + 2]);
+                where.push_back(std::make_pair(c, k));
             }
         }
         lps_purity_input in;
@@ -559,8 +668,12 @@ int lpsh_som_estimate(lpsh_som *h) {
         in.n = (int32_t)t_imb.size();
         in.tumor_germline_imbalance = t_imb.data(); in.normal_germline_imbalance = n_imb.data(); in.normal_pct_germline_hp = n_pct.data();
         in.normal_h1 = n_h1.data(); in.normal_h2 = n_h2.data();
+        std::vector<uint8_t> used(t_imb.size() + 1, 0);
+        in.used = used.data();
         lps_purity_result &r = h->purity_result;
         if (lps_estimate_purity(&in, &r) != 0) return lpsh::fail("lps_estimate_purity failed");
+        for (size_t c = 0; c < nc; c++) h->contig[c].used_for_purity.assign(h->contig[c].tumor.tum_var.size(), 0);
+        for (size_t e = 0; e < where.size(); e++) h->contig[where[e].first].used_for_purity[where[e].second] = used[e];   // markStatisticFlag
         if (r.ok) {
             std::cerr << difftime(time(NULL), t0) << "s\n";
             std::ofstream f((o.prefix + "_purity.out").c_str());   // TumorPurityEstimator::writePurityResult (:375-424)
@@ -637,6 +750,13 @@ int lpsh_som_call(lpsh_som *h) {
         lps_somatic_call_result out;
         memset(&out, 0, sizeof(out));
         out.is_somatic = is_somatic.data(); out.derive_hp = derive.data();
+        ContigState &CS = h->contig[(size_t)c];
+        if (o.write_calling_log) {
+            CS.is_filter_out.assign(nt, 0); CS.in_dense.assign(nt, 0); CS.mean_alt.assign(nt, 0.f); CS.z_score.assign(nt, 0.f);
+            CS.interval_snp_count.assign(nt, 0); CS.min_distance.assign(nt, 0);
+            out.is_filter_out = CS.is_filter_out.data(); out.in_dense_interval = CS.in_dense.data(); out.mean_alt_per_var_read = CS.mean_alt.data();
+            out.z_score = CS.z_score.data(); out.interval_snp_count = CS.interval_snp_count.data(); out.min_distance = CS.min_distance.data();
+        }
         const int rc = nt ? lps_somatic_call(&in, &out) : 0;
         if (rc != 0) {
 #pragma omp critical
@@ -644,10 +764,12 @@ int lpsh_som_call(lpsh_som *h) {
             continue;
         }
         for (size_t k = 0; k < nt; k++) { slot[k]->second.is_somatic = is_somatic[k]; slot[k]->second.derive_hp = derive[k]; }   // getSomaticFlag
+        CS.is_somatic = is_somatic;
 #pragma omp critical
         h->n_somatic += nt ? out.n_somatic : 0;
     }
     std::cerr << difftime(time(NULL), t0) << "s\n";
+    if (!failed && o.write_calling_log) write_somatic_var_out(*h);   // SomaticVarCaller.cpp:877-879
     if (!failed && o.write_sc_vcf) {      // SomaticHaplotagProcess.cpp:77-85
         std::time_t w0 = time(NULL);
         std::cerr << "writing somatic variants to vcf file ... ";

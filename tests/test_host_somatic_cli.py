@@ -193,8 +193,8 @@ def oracle_somatic_through_host(files, extra, cwd, chunk=300, pipelined=False):
         os.chdir(old)
 
 
-SOM_VARIANTS = [["--output-somatic-vcf"], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20"], ["--disableFilter", "-p", "0.7"],
-                ["--region", "chrA:40000-260000", "--tumor-purity", "0.6"]]
+SOM_VARIANTS = [["--output-somatic-vcf", "--somatic-calling-log"], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20", "--somatic-calling-log"],
+                ["--disableFilter", "-p", "0.7"], ["--region", "chrA:40000-260000", "--tumor-purity", "0.6", "--somatic-calling-log"]]
 
 
 @needs_host
@@ -212,6 +212,12 @@ def test_somatic_host_files_match_reference(tmp_path_factory, tmp_path, extra):
         sc = open(tmp_path / "own" / "som_sc.vcf").read()
         assert hc.strip_commandline(sc) == hc.strip_commandline(open(tmp_path / "ref" / "som_sc.vcf").read())
         assert "\tLowQual\t" in sc and "\tPASS\t" in sc and "##longphase_s_version=" in sc
+    if "--somatic-calling-log" in extra:
+        # BASELINE.md's gate file: one row of 65 columns per position called somatic, every number as the reference prints it
+        log = open(tmp_path / "own" / "som_somatic_var.out").read()
+        assert log == open(tmp_path / "ref" / "som_somatic_var.out").read()
+        rows = [l for l in log.splitlines() if l and not l.startswith("#")]
+        assert len(rows) == info["n_somatic"] and all(len(r.split("\t")) >= 65 for r in rows)
     if "--tumor-purity" not in extra:
         assert 0.0 < info["purity"] <= 1.0
         assert open(tmp_path / "own" / "som_purity.out").read() == open(tmp_path / "ref" / "som_purity.out").read()
@@ -320,12 +326,13 @@ def test_somatic_host_rejects_bad_options(capfd):
 @needs_ref
 def test_gpu_cli_somatic_haplotag_matches_reference(tmp_path_factory, tmp_path):
     files = dataset(tmp_path_factory)
-    for k, extra in enumerate([[], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20"]]):
+    for k, extra in enumerate([["--somatic-calling-log"], ["--tumor-purity", "0.35", "--tagSupplementary", "-q", "20", "--somatic-calling-log"]]):
         run_in(str(tmp_path / f"ref{k}"), [hc.REF_BIN] + som_args(files, extra))
         os.makedirs(tmp_path / f"own{k}", exist_ok=True)
         p = subprocess.run([hc.HOST_BIN] + som_args(files, extra), cwd=str(tmp_path / f"own{k}"), env=dict(os.environ, LPS_TAG_CHUNK="2500"),
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert p.returncode == 0, p.stderr[-2000:]
         assert hc.bam_payload(str(tmp_path / f"own{k}" / "som.bam")) == hc.bam_payload(str(tmp_path / f"ref{k}" / "som.bam")), extra
-        if not extra:
+        assert open(tmp_path / f"own{k}" / "som_somatic_var.out").read() == open(tmp_path / f"ref{k}" / "som_somatic_var.out").read(), extra
+        if "--tumor-purity" not in extra:
             assert open(tmp_path / f"own{k}" / "som_purity.out").read() == open(tmp_path / f"ref{k}" / "som_purity.out").read()
