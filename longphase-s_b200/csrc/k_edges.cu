@@ -507,6 +507,158 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges(const int32_t *__rest
     }
 }
 
+// The fold with SIXTEEN lanes per node, two nodes per warp (connect_adjacent <= 48, i.e. at most three rounds of 16 successors per
+// call).  A merged read carries ~18 calls, so a call has ~9 successors on average: with 32 lanes per node two thirds of the lanes
+// idled and the kernel, which is bound by instruction issue, paid a full warp instruction stream per node.  Same order of the float
+// additions as k_fold_edges: calls of a node in name-rank order (one per loop trip), the successors of one call hit distinct cells
+// unless the read has two calls at one position (then in the read's own order, lane by lane).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_fold_edges16(const int32_t *__restrict__ n_nodes_ptr, int W, double edge_weight,
+                                                            const uint64_t *__restrict__ node_off,
+                                                            const uint32_t *__restrict__ list, const uint32_t *__restrict__ M,
+                                                            const uint32_t *__restrict__ M_gend, float *__restrict__ weights,
+                                                            double edge_threshold, uint8_t *__restrict__ vote_info,
+                                                            unsigned long long *__restrict__ counters, const uint64_t *__restrict__ n_merged_ptr,
+                                                            int8_t *__restrict__ last_link, int RS, const int32_t *__restrict__ node_pos,
+                                                            const uint8_t *__restrict__ node_type, int distance, uint16_t *__restrict__ sweep_meta) {
+    extern __shared__ float s_acc[];                       // [WARPS * 2][W*4]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    const int n_nodes = *n_nodes_ptr;
+    const uint32_t nm = (uint32_t)*n_merged_ptr;           // merged entries are indexed with 32 bits (d_M_idx is uint32)
+    const long long first = ((long long)blockIdx.x * WARPS + wib) * 2;
+    if (first >= n_nodes) return;                          // the whole warp
+    const bool valid = first + half < n_nodes;
+    const int a = valid ? (int)(first + half) : 0;
+    float *acc = s_acc + ((size_t)wib * 2 + half) * W * 4;
+    for (int i = hl; i < W * 4; i += 16) acc[i] = 0.0f;
+    __syncwarp();
+    uint32_t t = valid ? (uint32_t)node_off[a] : 0u;
+    const uint32_t t1 = valid ? (uint32_t)node_off[a + 1] : 0u;
+    const unsigned hshift = 16u * (unsigned)half;
+    auto fetch = [&](uint32_t m, uint32_t &ea, uint32_t &gend, uint32_t &e0, uint32_t &e1) {
+        ea = M[m]; gend = M_gend[m];
+        const uint32_t i0 = m + 1u + (uint32_t)hl, i1 = i0 + 16u;
+        e0 = (hl < W && i0 < nm) ? M[i0] : 0xffffffffu;
+        e1 = (16 + hl < W && i1 < nm) ? M[i1] : 0xffffffffu;
+    };
+    auto add = [&](int cell, bool high) {                  // SubEdge::addSubEdge :40-43, :62-65
+        float x = acc[cell];
+        x = high ? x + 1.0f : (float)((double)x + edge_weight);
+        acc[cell] = x;
+    };
+    unsigned c32 = 0, f32 = 0;                             // per-lane counts of this node, widened once at the end
+    uint32_t mA = 0, eaA = 0, gendA = 0, e0A = 0xffffffffu, e1A = 0xffffffffu, mB = 0;
+    bool live = t < t1;
+    if (live) { mA = list[t]; fetch(mA, eaA, gendA, e0A, e1A); }
+    if (t + 1u < t1) mB = list[t + 1u];
+    while (__any_sync(FULL, live)) {
+        const uint32_t m = mA, ea_c = eaA, gend_c = gendA;
+        uint32_t eb0 = e0A, eb1 = e1A;
+        if (live && t + 1u < t1) {                         // the words of the next call are requested before this one is folded
+            mA = mB;
+            fetch(mA, eaA, gendA, e0A, e1A);
+            if (t + 2u < t1) mB = list[t + 2u];
+        }
+        const unsigned al_a = (ea_c >> 1) & 1u, hi_a = ea_c & 1u;
+        const bool act0 = live && hl < W && m + 1u + (uint32_t)hl < gend_c;
+        const bool act1 = live && 16 + hl < W && m + 17u + (uint32_t)hl < gend_c;
+        const bool act2 = live && 32 + hl < W && m + 33u + (uint32_t)hl < gend_c;
+        if (!act0) eb0 = 0xffffffffu;
+        const int nb0 = (int)(eb0 >> 2);
+        // duplicates (two calls of one merged read at the same position) are adjacent in the read's sorted list
+        const uint32_t p0 = __shfl_up_sync(FULL, eb0 >> 2, 1, 16);
+        const bool dup0 = act0 && hl > 0 && p0 == (uint32_t)nb0;
+        const int d0 = nb0 - a - 1;
+        const bool dense0 = act0 && d0 >= 0 && d0 < W;
+        c32 += (unsigned)dense0;
+        f32 += (unsigned)(act0 && !dense0);
+        const int cell0 = d0 * 4 + (int)(al_a * 2u + ((eb0 >> 1) & 1u));
+        const bool high0 = hi_a && (eb0 & 1u);
+        // warp-uniform: does any call of the two reach beyond 16 successors, does any have a duplicate among its first 16?
+        const bool beyond = __any_sync(FULL, act1);
+        const unsigned dupb0 = __ballot_sync(FULL, dup0);
+        if (!beyond && dupb0 == 0u) {
+            if (dense0) add(cell0, high0);
+        } else {
+            if (!act1) eb1 = 0xffffffffu;
+            uint32_t eb2 = 0xffffffffu;
+            if (act2) eb2 = M[m + 33u + (uint32_t)hl];     // successors 33.. of a call: rare, loaded on demand
+            const int nb1 = (int)(eb1 >> 2), nb2 = (int)(eb2 >> 2);
+            const uint32_t p1 = __shfl_up_sync(FULL, eb1 >> 2, 1, 16), l0 = __shfl_sync(FULL, eb0 >> 2, 15, 16);
+            const uint32_t p2 = __shfl_up_sync(FULL, eb2 >> 2, 1, 16), l1 = __shfl_sync(FULL, eb1 >> 2, 15, 16);
+            const bool dup1 = act1 && (hl > 0 ? p1 : l0) == (uint32_t)nb1, dup2 = act2 && (hl > 0 ? p2 : l1) == (uint32_t)nb2;
+            const int d1 = nb1 - a - 1, d2 = nb2 - a - 1;
+            const bool dense1 = act1 && d1 >= 0 && d1 < W, dense2 = act2 && d2 >= 0 && d2 < W;
+            c32 += (unsigned)dense1 + (unsigned)dense2;
+            f32 += (unsigned)(act1 && !dense1) + (unsigned)(act2 && !dense2);
+            const int cell1 = d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u)), cell2 = d2 * 4 + (int)(al_a * 2u + ((eb2 >> 1) & 1u));
+            const bool high1 = hi_a && (eb1 & 1u), high2 = hi_a && (eb2 & 1u);
+            const unsigned dupb = dupb0 | __ballot_sync(FULL, dup1 || dup2);
+            const bool my_dup = ((dupb >> hshift) & 0xFFFFu) != 0u;      // this node's call has a duplicate
+            if (!my_dup) {
+                // distinct successors of one read hit distinct cells
+                if (dense0) add(cell0, high0);
+                if (dense1) add(cell1, high1);
+                if (dense2) add(cell2, high2);
+            }
+            if (dupb != 0u) {
+                // keep the read's own order: successors 0..15, 16..31, 32..
+                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense0) add(cell0, high0); __syncwarp(); }
+                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense1) add(cell1, high1); __syncwarp(); }
+                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense2) add(cell2, high2); __syncwarp(); }
+            }
+        }
+        __syncwarp();
+        if (live) { t++; live = t < t1; }
+    }
+    unsigned long long contrib = c32, far = f32;
+    __syncwarp();
+    if (valid) {
+        float *out = weights + (size_t)a * W * 4;
+        for (int i = hl; i < W * 4; i += 16) out[i] = acc[i];
+    }
+    // epilogue: everything VariantEdge::findBestEdgePair (:166-228) derives from a cell, one byte per successor (see k_fold_edges)
+    int last = -1;
+    const int shift = (a + 1) & 15;
+    if (valid) {
+        for (int j = hl; j < RS; j += 16) {
+            const int d = j - shift;
+            unsigned info = 0;
+            if (d >= 0 && d < W && a + 1 + d < n_nodes) {
+                const float rr = acc[d * 4 + 0], ra = acc[d * 4 + 1], ar = acc[d * 4 + 2], aa = acc[d * 4 + 3];
+                const float para = rr + aa, cross = ar + ra;
+                const double esr = (double)fminf(para, cross) / (double)fmaxf(para, cross);
+                unsigned link = 0;
+                if (rr + aa > ra + ar) link = 1; else if (rr + aa < ra + ar) link = 2;
+                if (esr > edge_threshold) link = 0;
+                info = link;
+                if ((esr <= 0.1 && (rr + aa + ra + ar) >= 1) || ((rr + aa) < 1 && (ra + ar) >= 1) || ((rr + aa) >= 1 && (ra + ar) < 1)) info |= 4u;
+                if ((para + cross) <= 1) info |= 8u;
+                if (esr < 0.2) info |= 16u;
+                if (info & 3u) last = max(last, d);
+            }
+            vote_info[(size_t)a * RS + j] = (uint8_t)info;
+        }
+    }
+#pragma unroll
+    for (int dd = 8; dd; dd >>= 1) last = max(last, __shfl_xor_sync(FULL, last, dd));      // inside the 16 lanes of the node
+    if (valid && hl == 0) {
+        last_link[a] = (int8_t)last;
+        int gap = 0;
+        if (a + 1 < n_nodes) { const int d = node_pos[a + 1] - node_pos[a]; gap = (d < 0 ? -d : d) > distance; }
+        sweep_meta[a] = (uint16_t)((unsigned)node_type[a] | (gap ? 8u : 0u) | ((unsigned)(last + 1) << 8));
+    }
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) {
+        contrib += __shfl_xor_sync(FULL, contrib, dd);
+        far += __shfl_xor_sync(FULL, far, dd);
+    }
+    if (lane == 0) {
+        if (contrib) atomicAdd(&counters[0], contrib);
+        if (far) atomicAdd(&counters[1], far);
+    }
+}
+
 int bits_for(uint32_t n) { int b = 1; while (b < 32 && (1ull << b) < (uint64_t)n + 1) b++; return b; }
 
 }  // namespace
@@ -764,12 +916,22 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
     // 5. the fold (nodes without calls in M - there are none - would simply write an empty row)
     if (NU > 0) {
         constexpr int WARPS = 8;
-        size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
         cudaEventRecord(ctx->kev[2], st);
-        k_fold_edges<WARPS><<<(NU + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
-            ctx->d_n_nodes.p, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
-            p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, d_n_merged, ctx->d_last_link.p, RS, ctx->d_node_pos.p,
-            ctx->d_node_type.p, p->distance, ctx->d_sweep_meta.p);
+        static const bool wide_fold = getenv("LPS_FOLD_WIDE") != nullptr;      // A/B switch: the 32-lanes-per-node kernel
+        if (W <= 48 && !wide_fold) {
+            const size_t smem = (size_t)WARPS * 2 * W * 4 * sizeof(float);
+            const int per_cta = WARPS * 2;
+            k_fold_edges16<WARPS><<<(NU + per_cta - 1) / per_cta, WARPS * 32, smem, st>>>(
+                ctx->d_n_nodes.p, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
+                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, d_n_merged, ctx->d_last_link.p, RS, ctx->d_node_pos.p,
+                ctx->d_node_type.p, p->distance, ctx->d_sweep_meta.p);
+        } else {
+            const size_t smem = (size_t)WARPS * W * 4 * sizeof(float);
+            k_fold_edges<WARPS><<<(NU + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(
+                ctx->d_n_nodes.p, W, p->edge_weight, ctx->d_node_off.p, ctx->d_M_idx_sorted.p, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_weights.p,
+                p->edge_threshold, ctx->d_vote_info.p, (unsigned long long *)ctx->d_edge_counters.p, d_n_merged, ctx->d_last_link.p, RS, ctx->d_node_pos.p,
+                ctx->d_node_type.p, p->distance, ctx->d_sweep_meta.p);
+        }
         cudaEventRecord(ctx->kev[3], st);
         ctx->stats.kernel_launches++;
     }
