@@ -581,31 +581,45 @@ __global__ void __launch_bounds__(WARPS * 32) k_fold_edges16(const int32_t *__re
             if (dense0) add(cell0, high0);
         } else {
             if (!act1) eb1 = 0xffffffffu;
-            uint32_t eb2 = 0xffffffffu;
-            if (act2) eb2 = M[m + 33u + (uint32_t)hl];     // successors 33.. of a call: rare, loaded on demand
-            const int nb1 = (int)(eb1 >> 2), nb2 = (int)(eb2 >> 2);
+            const int nb1 = (int)(eb1 >> 2);
             const uint32_t p1 = __shfl_up_sync(FULL, eb1 >> 2, 1, 16), l0 = __shfl_sync(FULL, eb0 >> 2, 15, 16);
-            const uint32_t p2 = __shfl_up_sync(FULL, eb2 >> 2, 1, 16), l1 = __shfl_sync(FULL, eb1 >> 2, 15, 16);
-            const bool dup1 = act1 && (hl > 0 ? p1 : l0) == (uint32_t)nb1, dup2 = act2 && (hl > 0 ? p2 : l1) == (uint32_t)nb2;
-            const int d1 = nb1 - a - 1, d2 = nb2 - a - 1;
-            const bool dense1 = act1 && d1 >= 0 && d1 < W, dense2 = act2 && d2 >= 0 && d2 < W;
-            c32 += (unsigned)dense1 + (unsigned)dense2;
-            f32 += (unsigned)(act1 && !dense1) + (unsigned)(act2 && !dense2);
-            const int cell1 = d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u)), cell2 = d2 * 4 + (int)(al_a * 2u + ((eb2 >> 1) & 1u));
-            const bool high1 = hi_a && (eb1 & 1u), high2 = hi_a && (eb2 & 1u);
-            const unsigned dupb = dupb0 | __ballot_sync(FULL, dup1 || dup2);
-            const bool my_dup = ((dupb >> hshift) & 0xFFFFu) != 0u;      // this node's call has a duplicate
-            if (!my_dup) {
-                // distinct successors of one read hit distinct cells
+            const bool dup1 = act1 && (hl > 0 ? p1 : l0) == (uint32_t)nb1;
+            const int d1 = nb1 - a - 1;
+            const bool dense1 = act1 && d1 >= 0 && d1 < W;
+            c32 += (unsigned)dense1;
+            f32 += (unsigned)(act1 && !dense1);
+            const int cell1 = d1 * 4 + (int)(al_a * 2u + ((eb1 >> 1) & 1u));
+            const bool high1 = hi_a && (eb1 & 1u);
+            const unsigned dupb1 = dupb0 | __ballot_sync(FULL, dup1);
+            if (!__any_sync(FULL, act2) && dupb1 == 0u) {
+                // 17..32 successors, all distinct: distinct cells
                 if (dense0) add(cell0, high0);
                 if (dense1) add(cell1, high1);
-                if (dense2) add(cell2, high2);
-            }
-            if (dupb != 0u) {
-                // keep the read's own order: successors 0..15, 16..31, 32..
-                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense0) add(cell0, high0); __syncwarp(); }
-                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense1) add(cell1, high1); __syncwarp(); }
-                for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense2) add(cell2, high2); __syncwarp(); }
+            } else {
+                uint32_t eb2 = 0xffffffffu;
+                if (act2) eb2 = M[m + 33u + (uint32_t)hl];     // successors 33.. of a call: rare, loaded on demand
+                const int nb2 = (int)(eb2 >> 2);
+                const uint32_t p2 = __shfl_up_sync(FULL, eb2 >> 2, 1, 16), l1 = __shfl_sync(FULL, eb1 >> 2, 15, 16);
+                const bool dup2 = act2 && (hl > 0 ? p2 : l1) == (uint32_t)nb2;
+                const int d2 = nb2 - a - 1;
+                const bool dense2 = act2 && d2 >= 0 && d2 < W;
+                c32 += (unsigned)dense2;
+                f32 += (unsigned)(act2 && !dense2);
+                const int cell2 = d2 * 4 + (int)(al_a * 2u + ((eb2 >> 1) & 1u));
+                const bool high2 = hi_a && (eb2 & 1u);
+                const unsigned dupb = dupb1 | __ballot_sync(FULL, dup2);
+                const bool my_dup = ((dupb >> hshift) & 0xFFFFu) != 0u;      // this node's call has a duplicate
+                if (!my_dup) {
+                    if (dense0) add(cell0, high0);
+                    if (dense1) add(cell1, high1);
+                    if (dense2) add(cell2, high2);
+                }
+                if (dupb != 0u) {
+                    // keep the read's own order: successors 0..15, 16..31, 32..
+                    for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense0) add(cell0, high0); __syncwarp(); }
+                    for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense1) add(cell1, high1); __syncwarp(); }
+                    for (int l = 0; l < 16; l++) { if (my_dup && hl == l && dense2) add(cell2, high2); __syncwarp(); }
+                }
             }
         }
         __syncwarp();

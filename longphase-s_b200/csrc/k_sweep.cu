@@ -30,7 +30,10 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int SW_CH = 64;        // nodes per staged chunk
 constexpr int SW_RS_MAX = 80;    // lps_vote_row_stride(63)
 constexpr int SW_WARPS = 4;      // segments per CTA
-constexpr int SW_SEG = 128;      // core nodes per segment (a warp walks halo + core = ~270 nodes; 64 k nodes are 512 warps, one wave)
+#ifndef LPS_SW_SEG
+#define LPS_SW_SEG 128
+#endif
+constexpr int SW_SEG = LPS_SW_SEG;      // core nodes per segment (a warp walks halo + core = ~270 nodes; 64 k nodes are 512 warps, one wave)
 constexpr int SW_HALO_W = 4;     // halo = SW_HALO_W * W nodes
 
 struct SweepArgs {
