@@ -12,6 +12,8 @@
 
 namespace {
 
+// (r02: eight lanes per alignment with the votes added in order through shuffles measured 44 - 72 us against 40 us for this
+// one-thread-per-alignment form: the kernel is bound by the integer atomics on the counters of neighbouring alignments' shared variants)
 __global__ void k_read_vote(int n_reads, const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
                             const uint8_t *__restrict__ read_dead, const uint8_t *__restrict__ call_erased,
                             const unsigned long long *__restrict__ var_lastw, const int32_t *__restrict__ ps_sweep,

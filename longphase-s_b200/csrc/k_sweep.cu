@@ -198,61 +198,71 @@ __global__ void __launch_bounds__(SW_WARPS * 32) k_sweep_segments(SweepArgs a) {
     sweep_range(a, S, s_lut, N, max(0, b - a.halo), b, e, p, lane);
 }
 
-// boundary checks + flips (one CTA; thread p checks the boundary in front of segment p; the flips relative to the truth are a scan
-// over the segments, done by one thread on shared memory, a tile of segments at a time)
-__global__ void __launch_bounds__(1024) k_sweep_verify(SweepArgs a) {
-    constexpr int TILE = 4096;
-    __shared__ uint8_t s_rel[TILE], s_anchor[TILE];
-    __shared__ int s_ok;
-    __shared__ unsigned s_carry;
+// boundary checks, one warp per boundary over as many CTAs as it takes (a single CTA took 28 us for 506 boundaries: 16 dependent rounds
+// per warp); the flips relative to the truth are a scan over the segments, done at the start of k_sweep_fallback
+__global__ void __launch_bounds__(256) k_sweep_verify(SweepArgs a) {
+    // one warp per boundary, lane i compares the i-th node of the window (W <= 63: two rounds at most).  The verdict of boundary p
+    // is left in seg_flip[p] as bits: 1 = flipped relative to segment p - 1, 2 = a block start inside the core re-anchors the
+    // orientation, 4 = the window does not agree up to ONE flip.  k_sweep_fallback turns them into the absolute flips.
     const int N = *a.n_nodes;
-    if (threadIdx.x == 0) { s_ok = 1; s_carry = 0u; }
-    __syncthreads();
-    for (int p0 = 0; p0 < a.n_seg; p0 += TILE) {
-        const int p1 = min(a.n_seg, p0 + TILE);
-        // one warp per boundary, lane i compares the i-th node of the window (W <= 63: two rounds at most)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-        for (int p = p0 + warp; p < p1; p += n_warps) {
-            const int b = p * a.seg, e = min(N, b + a.seg);
-            bool bad = false;
-            unsigned flip_yes = 0u, flip_no = 0u;               // assigned nodes whose haplotype differs / agrees
-            if (p > 0 && b < N - 1 && b - a.halo > 0) {          // a halo that starts at node 0 starts from the true state: nothing to check
-                for (int i = lane; i < a.W; i += 32) {
-                    const int kk = b - a.W + i;
-                    if (kk < 0) continue;
-                    const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
-                    if (h == 0xFFu || ((t ^ h) & 0xBu)) bad = true;
-                    else if (t & 1u) { if (((t ^ h) >> 2) & 1u) flip_yes = 1u; else flip_no = 1u; }
-                }
-            }
-            const bool any_bad = __any_sync(0xffffffffu, bad), any_yes = __any_sync(0xffffffffu, flip_yes != 0u),
-                       any_no = __any_sync(0xffffffffu, flip_no != 0u);
-            if (lane == 0) {
-                s_rel[p - p0] = (uint8_t)(any_yes ? 1 : 0);       // relative to segment p - 1
-                s_anchor[p - p0] = (uint8_t)((b < N && a.first_nb[p] < e) ? 1 : 0);   // a block start inside the core re-anchors the orientation
-                if (any_bad || (any_yes && any_no)) s_ok = 0;     // the window must agree up to ONE flip
-            }
+    const int lane = threadIdx.x & 31, p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= a.n_seg) return;
+    const int b = p * a.seg, e = min(N, b + a.seg);
+    bool bad = false;
+    unsigned flip_yes = 0u, flip_no = 0u;               // assigned nodes whose haplotype differs / agrees
+    if (p > 0 && b < N - 1 && b - a.halo > 0) {          // a halo that starts at node 0 starts from the true state: nothing to check
+        for (int i = lane; i < a.W; i += 32) {
+            const int kk = b - a.W + i;
+            if (kk < 0) continue;
+            const unsigned t = a.flags[kk], h = a.halo_flags[(size_t)p * a.W + i];
+            if (h == 0xFFu || ((t ^ h) & 0xBu)) bad = true;
+            else if (t & 1u) { if (((t ^ h) >> 2) & 1u) flip_yes = 1u; else flip_no = 1u; }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned carry = s_carry;                           // flip in force at the end of the previous segment
-            for (int p = p0; p < p1; p++) {
-                const unsigned F = p == 0 ? 0u : ((unsigned)s_rel[p - p0] ^ carry);
-                a.seg_flip[p] = (uint8_t)F;
-                carry = s_anchor[p - p0] ? 0u : F;
-            }
-            s_carry = carry;
-        }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *a.all_ok = s_ok;
+    const bool any_bad = __any_sync(0xffffffffu, bad), any_yes = __any_sync(0xffffffffu, flip_yes != 0u),
+               any_no = __any_sync(0xffffffffu, flip_no != 0u);
+    if (lane == 0)
+        a.seg_flip[p] = (uint8_t)((any_yes ? 1u : 0u) | ((b < N && a.first_nb[p] < e) ? 2u : 0u) | ((any_bad || (any_yes && any_no)) ? 4u : 0u));
 }
 
 // the exact sequential chain, only when a boundary did not verify
-__global__ void __launch_bounds__(32) k_sweep_fallback(SweepArgs a) {
+__global__ void __launch_bounds__(32) k_sweep_fallback(SweepArgs a, int forced) {
     __shared__ SweepSmem S;
     __shared__ float4 s_lut[SW_LUT];
-    if (*a.all_ok) return;
+    __shared__ uint8_t s_pk[4096];
+    if (!forced) {
+        // the scan over the boundaries' verdicts: flip in force inside segment p = its relative flip XOR the flip at the end of p - 1
+        // (a block start inside a core re-anchors the orientation)
+        // carry(p) = XOR of the relative flips of the segments after the last re-anchoring one, up to p: 32 segments per step with ballots
+        const int ln = threadIdx.x;
+        const unsigned below = (1u << ln) - 1u;            // lanes 0 .. ln-1
+        unsigned carry = 0u;
+        int ok = 1;
+        for (int t0 = 0; t0 < a.n_seg; t0 += 4096) {        // a tile of verdicts at a time through shared memory: independent loads
+            const int tn = min(4096, a.n_seg - t0);
+            for (int i = ln; i < tn; i += 32) s_pk[i] = a.seg_flip[t0 + i];
+            __syncwarp();
+            for (int p0 = t0; p0 < t0 + tn; p0 += 32) {
+                const int p = p0 + ln;
+                const unsigned pk = p < t0 + tn ? (unsigned)s_pk[p - t0] : 0u;
+                const unsigned R = __ballot_sync(0xffffffffu, (pk & 1u) != 0u), A = __ballot_sync(0xffffffffu, (pk & 2u) != 0u);
+                if (__any_sync(0xffffffffu, (pk & 4u) != 0u)) ok = 0;
+                const unsigned Ap = A & below;
+                unsigned cprev;                                 // carry at the end of segment p - 1
+                if (Ap) { const int la = 31 - __clz((int)Ap); cprev = (unsigned)__popc(R & below & ~((2u << la) - 1u)) & 1u; }
+                else cprev = ((unsigned)__popc(R & below) & 1u) ^ carry;
+                if (p < t0 + tn) s_pk[p - t0] = (uint8_t)(p == 0 ? 0u : ((pk & 1u) ^ cprev));
+                if (A) { const int la = 31 - __clz((int)A); carry = (unsigned)__popc(R & ~((2u << la) - 1u)) & 1u; }
+                else carry = ((unsigned)__popc(R) & 1u) ^ carry;
+            }
+            __syncwarp();
+            for (int i = ln; i < tn; i += 32) a.seg_flip[t0 + i] = s_pk[i];
+            __syncwarp();
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ln == 0) *a.all_ok = ok;
+        if (ok) return;
+    }
     build_vote_lut(s_lut);
     __syncwarp();
     const int lane = threadIdx.x;
@@ -336,15 +346,16 @@ int lps_launch_sweep(lps_ctx *ctx, const lps_phase_params *p, int n_upper) {
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_flags.p, 0, (size_t)n_upper + 16, st));
     LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_multi.p, 0, (size_t)n_upper + 1, st));
     const char *force = getenv("LPS_SWEEP_SEQUENTIAL");      // A/B and tests: skip the speculation, run the exact chain on one warp
-    if (force && force[0] == '1') {
+    const int forced = (force && force[0] == '1') ? 1 : 0;
+    if (forced) {
         LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_ok.p, 0, 4, st));
         LPS_CUDA(ctx, cudaMemsetAsync(ctx->d_sweep_first_nb.p, 0, 4 * (size_t)a.n_seg, st));
     } else {
         k_sweep_segments<<<(a.n_seg + SW_WARPS - 1) / SW_WARPS, SW_WARPS * 32, 0, st>>>(a);
-        k_sweep_verify<<<1, 1024, 0, st>>>(a);
+        k_sweep_verify<<<(a.n_seg + 7) / 8, 256, 0, st>>>(a);
         ctx->stats.kernel_launches += 2;
     }
-    k_sweep_fallback<<<1, 32, 0, st>>>(a);
+    k_sweep_fallback<<<1, 32, 0, st>>>(a, forced);
     const int tb = 256, gb = (n_upper + tb - 1) / tb;
     k_sweep_block_start<<<gb, tb, 0, st>>>(n_upper, ctx->d_n_nodes.p, ctx->d_sweep_flags.p, ctx->d_sweep_start.p);
     size_t tmp = 0;
