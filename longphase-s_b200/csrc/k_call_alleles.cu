@@ -1224,14 +1224,15 @@ __global__ void k_clip_filter(unsigned long long n, uint32_t *__restrict__ keys,
 __global__ void k_gather_calls(int n_reads, const uint64_t *__restrict__ tmp_start, const uint32_t *__restrict__ ncalls,
                                const uint64_t *__restrict__ call_off, const lps_call *__restrict__ tmp,
                                lps_call *__restrict__ out) {
-    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    // sixteen lanes per read (a read carries ~18 calls)
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    int lane = threadIdx.x & 15;
     if (wid >= n_reads) return;
     uint32_t n = ncalls[wid];
     uint64_t s = tmp_start[wid], d = call_off[wid];
     const uint64_t *src = reinterpret_cast<const uint64_t *>(tmp);
     uint64_t *dst = reinterpret_cast<uint64_t *>(out);
-    for (uint32_t c = lane; c < n; c += 32) dst[d + c] = src[s + c];
+    for (uint32_t c = lane; c < n; c += 16) dst[d + c] = src[s + c];
 }
 
 __global__ void k_widen_u32(int n, const uint32_t *__restrict__ in, uint64_t *__restrict__ out) {
@@ -1497,7 +1498,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     ctx->n_calls = hc.n_calls.v;
     LPS_CUDA(ctx, ctx->d_calls.reserve((size_t)ctx->n_calls + 1));
     if (n > 0) {
-        const long long threads = (long long)n * 32;
+        const long long threads = (long long)n * 16;
         k_gather_calls<<<(unsigned)((threads + tb - 1) / tb), tb, 0, st>>>(n, ctx->d_tmp_start.p, ctx->d_ncalls.p, ctx->d_call_off.p,
                                                                          ctx->d_calls_tmp.p, ctx->d_calls.p);
         ctx->stats.kernel_launches++;

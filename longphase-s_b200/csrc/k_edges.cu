@@ -30,14 +30,15 @@ __global__ void k_mark_nodes(int n_reads, const uint64_t *__restrict__ call_off,
                              const uint8_t *__restrict__ read_dead, const uint8_t *__restrict__ call_erased,
                              const int32_t *__restrict__ name_rank, unsigned long long *__restrict__ var_lastw,
                              uint32_t *__restrict__ alive_cnt, uint64_t *__restrict__ aln_keys) {
-    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (wid >= n_reads) return;
-    int r = (int)wid;
-    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
+    // sixteen lanes per read (a read carries ~18 calls); both reads of a warp stay to the end (full-mask shuffles)
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    int lane = threadIdx.x & 15;
+    const bool present = wid < n_reads;
+    int r = present ? (int)wid : 0;
+    uint64_t c0 = present ? call_off[r] : 0, c1 = present ? call_off[r + 1] : 0;
     int alive = 0;
-    if (!read_dead[r]) {
-        for (uint64_t c = c0 + lane; c < c1; c += 32) {
+    if (present && !read_dead[r]) {
+        for (uint64_t c = c0 + lane; c < c1; c += 16) {
             if (call_erased && call_erased[c]) continue;
             lps_call cl = calls[c];
             unsigned type = cl.quality == -4 ? 3u : (cl.quality == -5 ? 4u : 0u);
@@ -46,8 +47,8 @@ __global__ void k_mark_nodes(int n_reads, const uint64_t *__restrict__ call_off,
         }
     }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) alive += __shfl_xor_sync(FULL, alive, d);
-    if (lane == 0) {
+    for (int d = 8; d; d >>= 1) alive += __shfl_xor_sync(FULL, alive, d);
+    if (present && lane == 0) {
         alive_cnt[r] = (uint32_t)alive;
         aln_keys[r] = alive ? (((uint64_t)(uint32_t)name_rank[r] << 32) | (uint32_t)r) : ~0ull;
     }
@@ -84,24 +85,24 @@ __global__ void k_fill_merged(int n_aln, const uint64_t *__restrict__ keys_sorte
                               const uint64_t *__restrict__ call_off, const lps_call *__restrict__ calls,
                               const uint8_t *__restrict__ call_erased, const int32_t *__restrict__ node_of_var, int base_quality,
                               uint32_t *__restrict__ M, uint32_t *__restrict__ M_gend, uint32_t *__restrict__ node_cnt) {
-    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (wid >= n_aln) return;
-    int i = (int)wid;
-    uint64_t key = keys_sorted[i];
-    if (key == ~0ull) return;                                                   // alignments without an alive call sort to the end
+    // sixteen lanes per alignment (~18 calls each); the two alignments of a warp loop in lockstep (full-mask ballots)
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15, hshift = threadIdx.x & 16;
+    int i = wid < n_aln ? (int)wid : 0;
+    uint64_t key = wid < n_aln ? keys_sorted[i] : ~0ull;
+    const bool live = key != ~0ull;                                             // alignments without an alive call sort to the end
     uint32_t rank = (uint32_t)(key >> 32);
-    int r = (int)(uint32_t)key;
+    int r = live ? (int)(uint32_t)key : 0;
     // end of the merged group: first later alignment with another name
     int j = i + 1;
-    while (j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
-    uint32_t gend = (uint32_t)grp_off[j];
-    uint64_t c0 = call_off[r], c1 = call_off[r + 1];
-    uint64_t w = grp_off[i];
-    for (uint64_t cb = c0; cb < c1; cb += 32) {
+    while (live && j < n_aln && (uint32_t)(keys_sorted[j] >> 32) == rank) j++;
+    uint32_t gend = live ? (uint32_t)grp_off[j] : 0u;
+    uint64_t c0 = live ? call_off[r] : 0, c1 = live ? call_off[r + 1] : 0;
+    uint64_t w = live ? grp_off[i] : 0;
+    for (uint64_t cb = c0; __any_sync(FULL, cb < c1); cb += 16) {
         uint64_t c = cb + lane;
         bool ok = c < c1 && !(call_erased && call_erased[c]);
-        unsigned m = __ballot_sync(FULL, ok);
+        unsigned m = (__ballot_sync(FULL, ok) >> hshift) & 0xFFFFu;             // this alignment's sixteen lanes
         if (ok) {
             lps_call cl = calls[c];
             int q = cl.quality < 0 ? 60 : cl.quality;                       // -4/-5 -> 60 (:820-828)
@@ -840,7 +841,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
 
     // 1. alive calls per read, node marking, alignment keys
     if (n > 0) {
-        k_mark_nodes<<<(unsigned)(((long long)n * 32 + tb - 1) / tb), tb, 0, st>>>(
+        k_mark_nodes<<<(unsigned)(((long long)n * 16 + tb - 1) / tb), tb, 0, st>>>(
             n, ctx->d_call_off.p, ctx->d_calls.p, ctx->d_read_dead.p, erased, ctx->batch.name_rank,
             (unsigned long long *)ctx->d_var_lastw.p, ctx->d_alive_cnt.p, ctx->d_aln_keys.p);
         ctx->stats.kernel_launches++;
@@ -881,7 +882,7 @@ int lps_launch_build_edges(lps_ctx *ctx, const lps_phase_params *p, bool sync_ti
     ctx->stats.kernel_launches += 3;
     const uint64_t *d_n_merged = ctx->d_grp_off.p + n;      // the scan's last element: merged calls
     if (n > 0 && MU > 0) {
-        k_fill_merged<<<(unsigned)(((long long)n * 32 + tb - 1) / tb), tb, 0, st>>>(
+        k_fill_merged<<<(unsigned)(((long long)n * 16 + tb - 1) / tb), tb, 0, st>>>(
             n, ctx->d_aln_keys_sorted.p, ctx->d_grp_off.p, ctx->d_call_off.p, ctx->d_calls.p, erased, ctx->d_node_of_var.p,
             p->base_quality, ctx->d_M.p, ctx->d_M_gend.p, ctx->d_node_cnt.p);
         // multi-alignment merged reads
