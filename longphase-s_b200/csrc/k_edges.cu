@@ -251,13 +251,44 @@ __global__ void __launch_bounds__(SMG_WARPS * 32) k_sort_multi_groups(int n_grou
     if (in_smem) for (long long a = lane; a < n; a += 32) v[a] = M[g0 + a];
     __syncwarp();
     bool report = false;
-    if (lane == 0) {
+    if (in_smem) {
+        // Stable rank sort by position, all lanes: an element's place is the number of smaller keys plus the equal keys in front of
+        // it (= what the insertion sort of the concatenated runs leaves).  One lane's insertion sort took up to 58 us per contig: a
+        // supplementary alignment that maps in front of its primary moves every call past every other one, a shared-memory round trip each.
+        bool tie_l = false;
+        for (long long a = lane; a < n; a += 32) {
+            const uint32_t x = v[a], key = x >> 2;
+            int less = 0, eq_before = 0;
+            for (long long c = 0; c < n; c++) {
+                const uint32_t kc = v[c] >> 2;
+                less += kc < key ? 1 : 0;
+                eq_before += (kc == key && c < a) ? 1 : 0;
+            }
+            if (eq_before) tie_l = true;                       // a tie = two calls of the merged read at one position
+            if (!record_only) M[g0 + less + eq_before] = x;
+        }
+        const bool tie = __any_sync(FULL, tie_l);
+        if (tie && n > 16) {
+            // more than 16 calls with a tie: the order of the tied calls is std::sort's - replay it from the concatenation order
+            int done = 0;
+            if (!record_only) {
+                __syncwarp();
+                for (long long a = lane; a < n; a += 32) v[a] = M_unsorted[g0 + a];
+                __syncwarp();
+                if (lane == 0) done = std_sort_replay(v, n) ? 1 : 0;
+                done = __shfl_sync(FULL, done, 0);
+                __syncwarp();
+                if (done) for (long long a = lane; a < n; a += 32) M[g0 + a] = v[a];
+                // else M keeps the position-sorted order for the host replay's write-back
+            }
+            report = !done;
+        }
+    } else if (lane == 0) {
         if (!record_only) insertion_sort_runs(v, n);
         // a tie = two calls of the merged read at one position: adjacent after the sort
         bool tie = false;
         for (long long a = 1; a < n && !tie; a++) tie = (v[a - 1] >> 2) == (v[a] >> 2);
         if (tie && n > 16) {
-            // more than 16 calls with a tie: the order of the tied calls is std::sort's - replay it from the concatenation order
             bool done = false;
             if (!record_only) {
                 for (long long a = 0; a < n; a++) v[a] = M_unsorted[g0 + a];
@@ -271,7 +302,7 @@ __global__ void __launch_bounds__(SMG_WARPS * 32) k_sort_multi_groups(int n_grou
         }
     }
     __syncwarp();
-    if (in_smem && !record_only) for (long long a = lane; a < n; a += 32) M[g0 + a] = v[a];
+    report = __any_sync(FULL, report);
     if (lane == 0 && report) {
         const unsigned k = atomicAdd(n_tie, 1u);
         if (k < tie_cap) tie_groups[k] = make_uint2((uint32_t)g0, (uint32_t)g1);
