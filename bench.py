@@ -410,7 +410,8 @@ def main():
             ok = ok and wl.phase_digest(r["ps"], r["hap_ref"], r["read_hp"], r["hp_counts"]) == w["digest"]
         return ok, checked
     ok_resident, n_checked = digest_ok(res_resident)
-    if min_over_ranks(1.0 if ok_resident else 0.0) < 1.0:
+    debug_no_gate = os.environ.get("LPS_BENCH_DEBUG_NO_GATE") == "1"     # timing experiments with a deliberately wrong kernel build: the line is marked invalid
+    if min_over_ranks(1.0 if ok_resident else 0.0) < 1.0 and not debug_no_gate:
         raise SystemExit("bench.py: the phase result of a timed contig differs from the committed digest of the CPU checker: no value is reported")
 
     # ---- the kernels timed alone (one context, nothing else on the GPU): rooflines ----
@@ -516,7 +517,7 @@ def main():
         d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
         h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
         ok_e2e, _ = digest_ok(results)
-        if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0:
+        if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0 and not debug_no_gate:
             raise SystemExit("bench.py: the end-to-end leg's result differs from the committed digest: no value is reported")
         e2e = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes)
         for i in range(n_ctg):
@@ -537,7 +538,7 @@ def main():
         "metric": METRIC, "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if args.workload == "genome" else "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
-        "allele_calls_per_s": total_calls / (ms_step * 1e-3), "parity_digest_ok": True, "parity_digests_checked_rank0": n_checked,
+        "allele_calls_per_s": total_calls / (ms_step * 1e-3), "parity_digest_ok": bool(ok_resident), **({"invalid": "LPS_BENCH_DEBUG_NO_GATE=1: a debugging run, not a measurement"} if debug_no_gate else {}), "parity_digests_checked_rank0": n_checked,
         "config": {"workload": workload_text(args, world, n_ctg), "contigs_rank0": n_ctg, "host_threads_per_rank": T_,
                    "reads_total": int(total_reads), "reads_rank0": n_reads_gpu, "largest_rank_share_of_reads": max_reads / total_reads * world,
                    "variants_rank0": int(sum(c.n_var for c in contigs)), "allele_calls_total": int(total_calls),

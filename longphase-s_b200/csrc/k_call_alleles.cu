@@ -503,7 +503,9 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     auto prefetch_base = [&](int qi) {
 #if LPS_PREFETCH_SQ
         asm volatile("prefetch.global.L2 [%0];" ::"l"(seq + (qi >> 1)));
+#ifndef LPS_DEBUG_NO_QUAL
         if (!TAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(qual + qi));
+#endif
 #else
         (void)qi;
 #endif
@@ -976,7 +978,11 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
                 const unsigned code = (byte >> ((~qi & 1) << 2)) & 0xfu;            // bam_seqi
                 const char base = "=ACMGRSVTWYHKDBN"[code];                          // seq_nt16_str
                 const char rb = (char)(vy & 0xFFu), ab = (char)((vy >> 8) & 0xFFu);
+#ifdef LPS_DEBUG_NO_QUAL
+                out.quality = 30;                        // timing experiment only (bench refuses the result): what do the QUAL gathers cost over PCIe?
+#else
                 out.quality = (int16_t)qual[qi];
+#endif
                 out.origin = (int8_t)kind;
                 if (base == rb) { out.allele = 0; valid = true; }
                 else if (base == ab) { out.allele = 1; valid = true; }
