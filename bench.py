@@ -215,6 +215,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sq", action="store_true")            # end-to-end leg: SEQ and QUAL as BAM's two arrays instead of the interleaved rows (lps_read_batch.sq)
+    ap.add_argument("--resident-sq", action="store_true")      # resident leg: the interleaved rows in HBM instead of the two arrays (experiment; the line says so)
     ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])
     ap.add_argument("--cigar16", action="store_true")    # end-to-end leg: send the 16-bit CIGAR stream instead of the 8-bit wire format
     ap.add_argument("--cigar32", action="store_true")    # end-to-end leg: send BAM's uint32 CIGAR ops instead of the compact 16-bit stream
@@ -322,12 +324,21 @@ def main():
 
     dtens, dev_batches = [], []
     for c, pk in zip(contigs, packed):
-        d = {k: dev(getattr(c, k)) for k in names}
+        if args.resident_sq:
+            d = {k: dev(getattr(c, k)) for k in names if k not in ("seq4", "qual", "qual_off", "seq_off")}
+            sq, sq_off = c.pack_sq(threads=min(ncores, 16))
+            d["sq"], d["seq_off"] = dev(sq), dev(sq_off)
+            del sq
+        else:
+            d = {k: dev(getattr(c, k)) for k in names}
         d["cigar16"] = dev(pk[0])
         d["cigar_long_len"] = dev(np.ascontiguousarray(pk[1])) if len(pk[1]) else None
         d["cigar_long_at"] = dev(np.ascontiguousarray(pk[2])) if len(pk[2]) else None
         dtens.append(d)
-        dev_batches.append(batch_from(c, lambda k, d=d: d[k].data_ptr() if d.get(k) is not None else None, pk))
+        b = batch_from(c, lambda k, d=d: d[k].data_ptr() if d.get(k) is not None else None, pk)
+        if args.resident_sq:
+            b.sq, b.sq_bytes, b.seq_bytes, b.qual_bytes = C.cast(d["sq"].data_ptr(), ffi.u8p), d["sq"].numel(), 0, 0
+        dev_batches.append(b)
     resident_bytes = int(sum(t.numel() * t.element_size() for d in dtens for t in d.values() if t is not None))
     n_reads_gpu = int(sum(c.n_reads for c in contigs))
 
@@ -473,10 +484,19 @@ def main():
                     return a, a.ctypes.data
             t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
             return t, t.data_ptr()
+        use_sq = not args.no_sq and not args.cigar32 and not args.cigar16
         for c, pk in zip(contigs, packed):
             d, ptr = {}, {}
             for k in names:
+                if use_sq and k in ("seq4", "qual", "qual_off", "seq_off"):
+                    continue
                 d[k], ptr[k] = pin(getattr(c, k))
+            if use_sq:
+                # the host loop writes a record's bases and qualities as one interleaved row (lps_pack_sq) while it appends the record
+                sq, sq_off = c.pack_sq(threads=min(ncores, 16))
+                d["sq"], ptr["sq"] = pin(sq)
+                d["seq_off"], ptr["seq_off"] = pin(sq_off)
+                del sq
             if args.cigar32:
                 d["cigar"], ptr["cigar"] = pin(c.cigar)
                 b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
@@ -491,8 +511,12 @@ def main():
                 c8, esc16, esc_blk, long_len, long_at = c.pack_cigar8()
                 d["cigar8"], ptr["cigar8"] = pin(c8)
                 d["cigar_esc_blk"], ptr["cigar_esc_blk"] = pin(esc_blk)
-                b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
-                                     **{k: C.cast(ptr[k], ptypes[k]) for k in names})
+                if use_sq:
+                    b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), sq=C.cast(ptr["sq"], ffi.u8p), sq_bytes=len(d["sq"]),
+                                         **{k: C.cast(ptr[k], ptypes[k]) for k in names if k in ptr})
+                else:
+                    b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
+                                         **{k: C.cast(ptr[k], ptypes[k]) for k in names})
                 b.cigar8, b.cigar_esc_blk = C.cast(ptr["cigar8"], ffi.u8p), C.cast(ptr["cigar_esc_blk"], ffi.u32p)
                 b.n_cigar_esc, b.n_cigar_long = len(esc16), len(long_len)
                 if len(esc16):
@@ -519,7 +543,7 @@ def main():
         ok_e2e, _ = digest_ok(results)
         if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0 and not debug_no_gate:
             raise SystemExit("bench.py: the end-to-end leg's result differs from the committed digest: no value is reported")
-        e2e = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes)
+        e2e = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes, use_sq)
         for i in range(n_ctg):
             ctxs[i].submit_device(dev_batches[i])       # nothing refers to the host buffers any more
         for a in pinned_in_place:
@@ -538,7 +562,8 @@ def main():
         "metric": METRIC, "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if args.workload == "genome" else "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
-        "allele_calls_per_s": total_calls / (ms_step * 1e-3), "parity_digest_ok": bool(ok_resident), **({"invalid": "LPS_BENCH_DEBUG_NO_GATE=1: a debugging run, not a measurement"} if debug_no_gate else {}), "parity_digests_checked_rank0": n_checked,
+        "allele_calls_per_s": total_calls / (ms_step * 1e-3), "parity_digest_ok": bool(ok_resident),
+        **({"resident_seq_qual": "interleaved rows (lps_read_batch.sq) in HBM: an experiment, not the default layout"} if args.resident_sq else {}), **({"invalid": "LPS_BENCH_DEBUG_NO_GATE=1: a debugging run, not a measurement"} if debug_no_gate else {}), "parity_digests_checked_rank0": n_checked,
         "config": {"workload": workload_text(args, world, n_ctg), "contigs_rank0": n_ctg, "host_threads_per_rank": T_,
                    "reads_total": int(total_reads), "reads_rank0": n_reads_gpu, "largest_rank_share_of_reads": max_reads / total_reads * world,
                    "variants_rank0": int(sum(c.n_var for c in contigs)), "allele_calls_total": int(total_calls),
@@ -553,11 +578,14 @@ def main():
         "stage_ms": dict(k_call_alleles_alone=k1, k_fold_edges_alone=kf, **stage),
     }
     if e2e is not None:
-        e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes = e2e
+        e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes, use_sq = e2e
         line["e2e"] = {"value": total_reads / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                       "ms_per_step": e2e_ms, "host_buffer_bytes": host_bytes, "parity_digest_ok": True,
+                       "ms_per_step": e2e_ms, "wall_ms_per_step_rank0": e2e_wall_ms, "host_buffer_bytes": host_bytes, "parity_digest_ok": True,
                        "note": "pinned SEQ/QUAL stay on the host; the kernel gathers the sectors it needs over PCIe (zero-copy), "
                                "CIGAR and per-read records are copied; h2d bytes are the library's own count",
+                       "seq_qual_wire_format": ("interleaved rows (lps_pack_sq / lps_read_batch.sq): ten qualities + ten 4-bit bases per 16-byte unit, "
+                                                "one PCIe read request per allele call" if use_sq else
+                                                "BAM's two arrays (seq4, qual): two PCIe read requests per allele call"),
                        "cigar_wire_format": ("uint32 (BAM), narrowed on the device" if args.cigar32 else
                                              "16-bit stream (lps_pack_cigar16), used as it arrives" if args.cigar16 else
                                              "8-bit stream (lps_pack_cigar8), expanded into the resident 16-bit stream by k_expand_cigar8")}

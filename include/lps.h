@@ -102,6 +102,20 @@ typedef struct {
     const uint16_t *cigar_esc16;    /* [n_cigar_esc]                                            */
     uint64_t n_cigar_esc;
     const uint32_t *cigar_esc_blk;  /* [cigar_len / 256 + 2]                                    */
+    /* --- optional wire format of SEQ + QUAL in ONE stream (phase calls only) ------------------------------------------ *
+     * BamParser::get_snp looks at bam_seqi(qstring, i) and bam_get_qual(aln)[i] of the SAME query index i, for ~1 index per
+     * 1000 bases (ParsingBam.cpp:1398-1425).  With seq4[] and qual[] in two arrays every allele call costs two scattered
+     * sectors - two PCIe read requests when the buffers stay in pinned host memory.  When sq != NULL, seq4[] / qual[] /
+     * qual_off[] are ignored (may be NULL) and seq_off[r] is the byte offset of read r in sq[] (a multiple of 16):
+     * the read is a row of 16-byte units, unit u covering query indices 10 u .. 10 u + 9:
+     *     bytes 0..9   bam_get_qual(aln)[10 u + k], k = 0..9            (0 past l_qseq)
+     *     bytes 10..14 bam_get_seq(aln) nibbles of the same ten bases, BAM's packing (even k in the high nibble)
+     *     byte  15     0
+     * so one aligned 16-byte load serves a call.  lps_pack_sq writes a read's row while the host appends the record;
+     * lps_sq_row_bytes gives its length.  Only lps_phase_* accept such a batch (the tag dialects and the window diff read
+     * runs of bases, not single ones: LPS_E_STATE).  Pinned sq stays on the host like pinned seq4 / qual.               */
+    const uint8_t *sq;              /* [sq_bytes]                                               */
+    uint64_t sq_bytes;
 } lps_read_batch;
 
 /* one allele call: replaces struct Variant (src/shared/Util.h:63-75)                        */
@@ -240,9 +254,23 @@ int lps_pack_cigar16(const uint32_t *cigar, uint64_t n, uint64_t base_index, uin
  * last appended op + 1 are kept up to date.  Returns 0 or LPS_E_ARG when a table is too small.  Pure host code.            */
 int lps_pack_cigar8(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint8_t *out8, uint16_t *esc16, uint64_t esc_cap, uint64_t *n_esc,
                     uint32_t *esc_blk, uint32_t *long_len, uint64_t *long_at, uint64_t long_cap, uint64_t *n_long);
+/* The interleaved SEQ + QUAL row of one read (lps_read_batch.sq): 16 * ceil(l_qseq / 10) bytes.                            */
+uint64_t lps_sq_row_bytes(int32_t l_qseq);
+/* Writes that row from bam_get_seq(aln) (4-bit packing) and bam_get_qual(aln); out must hold lps_sq_row_bytes(l_qseq) bytes.
+ * Returns 0 or LPS_E_ARG.  Pure host code; thread-safe on disjoint outputs.                                               */
+int lps_pack_sq(const uint8_t *seq4, const uint8_t *qual, int32_t l_qseq, uint8_t *out);
+/* lps_pack_sq for reads 0 .. n_reads of a batch in the two-array layout: row r is written at sq + sq_off[r] (16-byte aligned
+ * offsets the caller laid out with lps_sq_row_bytes).  Callers may split the reads over threads by passing shifted per-read
+ * arrays (the offsets stay absolute).                                                                                     */
+int lps_pack_sq_batch(int32_t n_reads, const int32_t *l_qseq, const uint64_t *seq_off, const uint64_t *qual_off, const uint8_t *seq4,
+                      const uint8_t *qual, const uint64_t *sq_off, uint8_t *sq);
+/* What the kernel reads from a row for query index qi (the same index arithmetic, compiled for the host): bam_seqi code and
+ * base quality.  For integrators' and this repo's tests.  Returns 0, or LPS_E_ARG for qi outside [0, l_qseq).              */
+int lps_sq_peek(const uint8_t *row, int32_t l_qseq, int32_t qi, uint8_t *seq_code, uint8_t *quality);
 /* Same, for buffers that already live in device memory (a batch that stays resident across calls): nothing is copied except the
  * name ranks and flags the host needs (to group the alignments of one read name).  The arrays must stay valid until the next
- * submit on this context.  Either cigar (uint32 ops, narrowed into a buffer of the context) or cigar16 (+ its side table).  */
+ * submit on this context.  Either cigar (uint32 ops, narrowed into a buffer of the context) or cigar16 (+ its side table);
+ * either seq4 + qual or sq (16-byte aligned).                                                                              */
 int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b_dev);
 
 /* ---- phase -------------------------------------------------------------------------------- */

@@ -27,7 +27,8 @@ class LpsReadBatch(C.Structure):
                 ("name_rank", i32p), ("cigar", u32p), ("cigar_len", C.c_uint64), ("seq4", u8p),
                 ("seq_bytes", C.c_uint64), ("qual", u8p), ("qual_bytes", C.c_uint64),
                 ("cigar16", u16p), ("cigar_long_len", u32p), ("cigar_long_at", u64p), ("n_cigar_long", C.c_uint64),
-                ("cigar8", u8p), ("cigar_esc16", u16p), ("n_cigar_esc", C.c_uint64), ("cigar_esc_blk", u32p)]
+                ("cigar8", u8p), ("cigar_esc16", u16p), ("n_cigar_esc", C.c_uint64), ("cigar_esc_blk", u32p),
+                ("sq", u8p), ("sq_bytes", C.c_uint64)]
 
 
 class LpsBgzfBlock(C.Structure):
@@ -196,6 +197,10 @@ SYMBOLS = {
     "lps_pack_cigar16": (C.c_int, [u32p, C.c_uint64, C.c_uint64, u16p, u32p, u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "lps_pack_cigar8": (C.c_int, [u32p, C.c_uint64, C.c_uint64, u8p, u16p, C.c_uint64, C.POINTER(C.c_uint64), u32p, u32p, u64p, C.c_uint64,
                                   C.POINTER(C.c_uint64)]),
+    "lps_sq_row_bytes": (C.c_uint64, [C.c_int32]),
+    "lps_pack_sq": (C.c_int, [u8p, u8p, C.c_int32, u8p]),
+    "lps_pack_sq_batch": (C.c_int, [C.c_int32, i32p, u64p, u64p, u8p, u8p, u64p, u8p]),
+    "lps_sq_peek": (C.c_int, [u8p, C.c_int32, C.c_int32, u8p, u8p]),
     "lps_phase_call_alleles": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsCalls)]),
     "lps_phase_build_edges": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.c_int, C.POINTER(LpsEdges)]),
     "lps_phase_solve": (C.c_int, [C.c_void_p, C.POINTER(LpsPhaseParams), C.POINTER(LpsPhaseResult)]),

@@ -502,6 +502,10 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
     // as soon as the query index is known, the rest of phase 2 runs while they travel
     auto prefetch_base = [&](int qi) {
 #if LPS_PREFETCH_SQ
+        if (!TAG && a.b.sq) {          // interleaved rows: base and quality share one 16-byte unit
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(seq + (size_t)sq_unit_of((uint32_t)qi) * SQ_UNIT));
+            return;
+        }
         asm volatile("prefetch.global.L2 [%0];" ::"l"(seq + (qi >> 1)));
 #ifndef LPS_DEBUG_NO_QUAL
         if (!TAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(qual + qi));
@@ -974,15 +978,24 @@ __device__ __forceinline__ void process_read(const K1Args &a, WarpScratch &S, co
             } else {
                 ngather++;
                 const int qi = (int)(cd.x & 0x3fffffffu);
-                const unsigned byte = seq[qi >> 1];
-                const unsigned code = (byte >> ((~qi & 1) << 2)) & 0xfu;            // bam_seqi
+                unsigned code, q;
+                if (a.b.sq) {
+                    // one aligned 16-byte load: the unit of ten bases that holds this query index (lps_read_batch.sq)
+                    const uint32_t u = sq_unit_of((uint32_t)qi);
+                    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(seq) + u);
+                    sq_extract(w.x, w.y, w.z, w.w, (uint32_t)qi - u * SQ_BASES, code, q);
+                } else {
+                    const unsigned byte = seq[qi >> 1];
+                    code = (byte >> ((~qi & 1) << 2)) & 0xfu;                        // bam_seqi
+#ifdef LPS_DEBUG_NO_QUAL
+                    q = 30;                              // timing experiment only (bench refuses the result): what do the QUAL gathers cost over PCIe?
+#else
+                    q = qual[qi];
+#endif
+                }
                 const char base = "=ACMGRSVTWYHKDBN"[code];                          // seq_nt16_str
                 const char rb = (char)(vy & 0xFFu), ab = (char)((vy >> 8) & 0xFFu);
-#ifdef LPS_DEBUG_NO_QUAL
-                out.quality = 30;                        // timing experiment only (bench refuses the result): what do the QUAL gathers cost over PCIe?
-#else
-                out.quality = (int16_t)qual[qi];
-#endif
+                out.quality = (int16_t)q;
                 out.origin = (int8_t)kind;
                 if (base == rb) { out.allele = 0; valid = true; }
                 else if (base == ab) { out.allele = 1; valid = true; }
@@ -1210,7 +1223,7 @@ __global__ void __launch_bounds__(256) k_prep_reads(PrepArgs p) {
         const int mid = (lo + hi) >> 1;
         if (p.vpos[mid] < ref_start) lo = mid + 1; else hi = mid;
     }
-    const uint64_t co = p.b.cigar_off[r], so = p.b.seq_off[r], qo = p.b.qual_off[r];
+    const uint64_t co = p.b.cigar_off[r], so = p.b.seq_off[r], qo = p.b.sq ? 0ull : p.b.qual_off[r];
     uint4 *w = p.work + (size_t)slot * 3;
     w[0] = make_uint4((uint32_t)co, (uint32_t)(co >> 32), (uint32_t)so, (uint32_t)(so >> 32));
     w[1] = make_uint4((uint32_t)qo, (uint32_t)(qo >> 32), (uint32_t)ref_start, (uint32_t)lq);
@@ -1293,6 +1306,8 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
     const bool tag = t != nullptr;
     if (mode < 0) mode = tag ? LPS_MODE_GERMLINE : LPS_MODE_PHASE;
     const bool som = mode >= LPS_MODE_EXTRACT_NORMAL;
+    if (ctx->batch.sq && mode != LPS_MODE_PHASE)
+        return ctx->fail(LPS_E_STATE, "a batch with interleaved SEQ + QUAL rows (lps_read_batch.sq) serves the phase calls only");
     const int n = ctx->batch.n_reads;
     const int nv = ctx->var.n;
     cudaStream_t st = ctx->stream;
@@ -1445,7 +1460,7 @@ int lps_launch_call_alleles(lps_ctx *ctx, const lps_phase_params *p, const lps_t
             fprintf(stderr, "k1 mode=%d attempt=%d grid=%d ms=%.4f pool=%llu/%zu calls=%llu clips=%llu overflow_reads=%u aborted=%u\n", mode, attempt, grid,
                     ctx->stats.ms_kernel_call_alleles, hc.tmp_calls.v, ctx->d_calls_tmp.cap, hc.n_calls.v, hc.clips.v, (unsigned)hc.overflow_reads.v, (unsigned)hc.aborted_reads.v);
         // zero-copy accounting: one 32-byte sector of SEQ (phase: and one of QUAL) crosses PCIe per gathered candidate
-        if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers.v * (tag ? 32ull : 64ull);
+        if (ctx->zero_copy) ctx->stats.h2d_bytes += hc.gathers.v * ((tag || ctx->batch.sq) ? 32ull : 64ull);
         if (hc.bad_cigar.v) return ctx->fail(LPS_E_CIGAR, "alignment find unsupported CIGAR operation");
         if (hc.overflow_reads.v > ctx->d_overflow_reads.cap) {
             // more reads overflow the shared candidate buffer than the list holds (dense variants, long reads): grow the list and redo

@@ -153,6 +153,11 @@ int validate_batch(lps_ctx *ctx, const lps_read_batch *b) {
         if (lq < 0) return ctx->fail(LPS_E_ARG, "negative l_qseq");
         if (b->cigar_off[i] > b->cigar_len || (uint64_t)b->n_cigar[i] > b->cigar_len - b->cigar_off[i])
             return ctx->fail(LPS_E_ARG, "cigar_off + n_cigar runs past cigar_len");
+        if (b->sq) {
+            if (lq > 0 && ((b->seq_off[i] & 15u) || b->seq_off[i] > b->sq_bytes || lps_sq_row_bytes((int32_t)lq) > b->sq_bytes - b->seq_off[i]))
+                return ctx->fail(LPS_E_ARG, "seq_off is not a 16-byte aligned row of sq[] that ends within sq_bytes");
+            continue;
+        }
         if (lq > 0 && (b->seq_off[i] > b->seq_bytes || (uint64_t)(lq + 1) / 2 > b->seq_bytes - b->seq_off[i]))
             return ctx->fail(LPS_E_ARG, "seq_off + (l_qseq + 1) / 2 runs past seq_bytes");
         if (lq > 0 && (b->qual_off[i] > b->qual_bytes || (uint64_t)lq > b->qual_bytes - b->qual_off[i]))
@@ -305,7 +310,7 @@ int lps_contig_get_notes(lps_ctx *ctx, lps_variant_notes *out) {
 int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     if (!ctx || !b || b->n_reads < 0) return LPS_E_ARG;
     const size_t n = (size_t)b->n_reads;
-    if (n && (!b->ref_start || !b->l_qseq || !b->n_cigar || !b->cigar_off || !b->seq_off || !b->qual_off || !b->flag || !b->mapq ||
+    if (n && (!b->ref_start || !b->l_qseq || !b->n_cigar || !b->cigar_off || !b->seq_off || (!b->qual_off && !b->sq) || !b->flag || !b->mapq ||
               !b->name_rank))
         return ctx->fail(LPS_E_ARG, "null read array");
     TRY(validate_batch(ctx, b));
@@ -316,7 +321,7 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_n_cigar, b->n_cigar, n));
     TRY(h2d(ctx, ctx->d_cigar_off, b->cigar_off, n));
     TRY(h2d(ctx, ctx->d_seq_off, b->seq_off, n));
-    TRY(h2d(ctx, ctx->d_qual_off, b->qual_off, n));
+    if (!b->sq) TRY(h2d(ctx, ctx->d_qual_off, b->qual_off, n));
     TRY(h2d(ctx, ctx->d_flag, b->flag, n));
     TRY(h2d(ctx, ctx->d_mapq, b->mapq, n));
     TRY(h2d(ctx, ctx->d_name_rank, b->name_rank, n));
@@ -365,7 +370,21 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     // gathers the few sectors it needs straight over PCIe (UVA zero-copy); pageable buffers are copied as before.
     const uint8_t *seq_dev = nullptr, *qual_dev = nullptr;
     bool zero_copy = false;
-    {
+    if (b->sq) {
+        // interleaved SEQ + QUAL rows: one array, one 16-byte unit per allele call; pinned rows stay on the host (they must be
+        // 16-byte aligned there: the kernel loads whole units), pageable rows are copied
+        const char *env = getenv("LPS_ZERO_COPY");
+        cudaPointerAttributes as;
+        if (!(env && env[0] == '0') && b->sq_bytes && cudaPointerGetAttributes(&as, b->sq) == cudaSuccess && as.type == cudaMemoryTypeHost &&
+            as.devicePointer && ((uintptr_t)as.devicePointer & 15u) == 0) {
+            seq_dev = (const uint8_t *)as.devicePointer; zero_copy = true;
+        }
+        cudaGetLastError();
+        if (!zero_copy) {
+            TRY(h2d(ctx, ctx->d_seq4, b->sq, (size_t)b->sq_bytes, 16));
+            seq_dev = ctx->d_seq4.p;
+        }
+    } else {
         const char *env = getenv("LPS_ZERO_COPY");
         cudaPointerAttributes as, aq;
         if (!(env && env[0] == '0') && b->seq_bytes && b->qual_bytes &&
@@ -374,11 +393,11 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
             seq_dev = (const uint8_t *)as.devicePointer; qual_dev = (const uint8_t *)aq.devicePointer; zero_copy = true;
         }
         cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes report an error on old drivers
-    }
-    if (!zero_copy) {
-        TRY(h2d(ctx, ctx->d_seq4, b->seq4, (size_t)b->seq_bytes, 16));
-        TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
-        seq_dev = ctx->d_seq4.p; qual_dev = ctx->d_qual.p;
+        if (!zero_copy) {
+            TRY(h2d(ctx, ctx->d_seq4, b->seq4, (size_t)b->seq_bytes, 16));
+            TRY(h2d(ctx, ctx->d_qual, b->qual, (size_t)b->qual_bytes, 16));
+            seq_dev = ctx->d_seq4.p; qual_dev = ctx->d_qual.p;
+        }
     }
     ctx->zero_copy = zero_copy;
     cudaEventRecord(ctx->ev[1], ctx->stream);
@@ -393,10 +412,11 @@ int lps_batch_submit(lps_ctx *ctx, const lps_read_batch *b) {
     DevBatch &d = ctx->batch;
     d.n_reads = b->n_reads;
     d.ref_start = ctx->d_ref_start.p; d.l_qseq = ctx->d_l_qseq.p; d.n_cigar = ctx->d_n_cigar.p;
-    d.cigar_off = ctx->d_cigar_off.p; d.seq_off = ctx->d_seq_off.p; d.qual_off = ctx->d_qual_off.p;
+    d.cigar_off = ctx->d_cigar_off.p; d.seq_off = ctx->d_seq_off.p; d.qual_off = b->sq ? nullptr : ctx->d_qual_off.p;
     d.flag = ctx->d_flag.p; d.mapq = ctx->d_mapq.p; d.name_rank = ctx->d_name_rank.p;
-    d.cigar_len = b->cigar_len; d.seq4 = seq_dev; d.seq_bytes = b->seq_bytes;
-    d.qual = qual_dev; d.qual_bytes = b->qual_bytes;
+    d.cigar_len = b->cigar_len; d.seq4 = seq_dev; d.seq_bytes = b->sq ? b->sq_bytes : b->seq_bytes;
+    d.qual = qual_dev; d.qual_bytes = b->sq ? 0 : b->qual_bytes;
+    d.sq = b->sq ? 1 : 0;
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.ms_h2d = elapsed(ctx, 0, 1);
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
@@ -448,6 +468,46 @@ int lps_pack_cigar8(const uint32_t *cigar, uint64_t n, uint64_t base_index, uint
     return LPS_OK;
 }
 
+uint64_t lps_sq_row_bytes(int32_t l_qseq) { return l_qseq > 0 ? (uint64_t)SQ_UNIT * (((uint64_t)l_qseq + SQ_BASES - 1) / SQ_BASES) : 0; }
+
+int lps_pack_sq(const uint8_t *seq4, const uint8_t *qual, int32_t l_qseq, uint8_t *out) {
+    if (l_qseq < 0 || (l_qseq > 0 && (!seq4 || !qual || !out))) return LPS_E_ARG;
+    const uint32_t lq = (uint32_t)l_qseq, seq_bytes = (lq + 1) / 2;
+    for (uint32_t at = 0, u = 0; at < lq; at += SQ_BASES, u++) {
+        uint8_t *unit = out + (size_t)u * SQ_UNIT;
+        const uint32_t nb = lq - at < SQ_BASES ? lq - at : SQ_BASES;        // bases of this unit
+        memcpy(unit, qual + at, nb);
+        memset(unit + nb, 0, SQ_UNIT - nb);
+        const uint32_t s0 = at / 2, ns = seq_bytes - s0 < SQ_BASES / 2 ? seq_bytes - s0 : SQ_BASES / 2;   // at is even: unit starts on a byte of seq4
+        memcpy(unit + SQ_BASES, seq4 + s0, ns);
+    }
+    return LPS_OK;
+}
+
+int lps_pack_sq_batch(int32_t n_reads, const int32_t *l_qseq, const uint64_t *seq_off, const uint64_t *qual_off, const uint8_t *seq4,
+                      const uint8_t *qual, const uint64_t *sq_off, uint8_t *sq) {
+    if (n_reads < 0 || (n_reads && (!l_qseq || !seq_off || !qual_off || !sq_off))) return LPS_E_ARG;
+    for (int32_t r = 0; r < n_reads; r++) {
+        if (l_qseq[r] <= 0) continue;
+        if (sq_off[r] & 15u) return LPS_E_ARG;
+        const int rc = lps_pack_sq(seq4 + seq_off[r], qual + qual_off[r], l_qseq[r], sq + sq_off[r]);
+        if (rc != LPS_OK) return rc;
+    }
+    return LPS_OK;
+}
+
+int lps_sq_peek(const uint8_t *row, int32_t l_qseq, int32_t qi, uint8_t *seq_code, uint8_t *quality) {
+    if (!row || qi < 0 || qi >= l_qseq) return LPS_E_ARG;
+    const uint32_t u = sq_unit_of((uint32_t)qi);
+    uint32_t w[4];
+    memcpy(w, row + (size_t)u * SQ_UNIT, SQ_UNIT);                          // little-endian host, like the device
+    unsigned code, q;
+    sq_extract(w[0], w[1], w[2], w[3], (uint32_t)qi - u * SQ_BASES, code, q);
+    if (seq_code) *seq_code = (uint8_t)code;
+    if (quality) *quality = (uint8_t)q;
+    return LPS_OK;
+}
+
 int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     if (!ctx || !b || b->n_reads < 0) return LPS_E_ARG;
     cudaSetDevice(ctx->device);
@@ -457,6 +517,12 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     d.seq_off = b->seq_off; d.qual_off = b->qual_off; d.flag = b->flag; d.mapq = b->mapq; d.name_rank = b->name_rank;
     d.cigar_len = b->cigar_len; d.seq4 = b->seq4; d.seq_bytes = b->seq_bytes;
     d.qual = b->qual; d.qual_bytes = b->qual_bytes;
+    d.sq = 0;
+    if (b->sq) {
+        // interleaved SEQ + QUAL rows used where they lie (phase calls only): the kernel loads whole 16-byte units
+        if (((uintptr_t)b->sq & 15u) != 0) return ctx->fail(LPS_E_ARG, "a device-resident sq stream must be 16-byte aligned");
+        d.seq4 = b->sq; d.seq_bytes = b->sq_bytes; d.qual = nullptr; d.qual_bytes = 0; d.qual_off = nullptr; d.sq = 1;
+    }
     if (b->cigar16) {
         // the 16-bit stream is used where it lies: the bulk copies of k_call_alleles need a 16-byte aligned base
         if (((uintptr_t)b->cigar16 & 15u) != 0) return ctx->fail(LPS_E_ARG, "a device-resident cigar16 stream must be 16-byte aligned");
@@ -474,7 +540,7 @@ int lps_batch_submit_device(lps_ctx *ctx, const lps_read_batch *b) {
     TRY(h2d(ctx, ctx->d_multi_members, ctx->h_multi_members.data(), ctx->h_multi_members.size()));
     TRY(h2d(ctx, ctx->d_multi_group_off, ctx->h_multi_group_off.data(), ctx->h_multi_group_off.size()));
     LPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->sum_l_qseq = b->qual_bytes;
+    ctx->sum_l_qseq = b->sq ? b->sq_bytes / SQ_UNIT * SQ_BASES : b->qual_bytes;   // sizes the call pool (an upper bound; the pool grows on demand)
     ctx->have_batch = true; ctx->have_calls = false; ctx->have_graph = false;
     return LPS_OK;
 }

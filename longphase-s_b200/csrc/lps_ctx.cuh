@@ -79,7 +79,24 @@ struct DevBatch {
     uint64_t seq_bytes = 0;
     const uint8_t *qual = nullptr;
     uint64_t qual_bytes = 0;
+    // SEQ + QUAL interleaved (lps_read_batch.sq): seq4 points at the rows, seq_off[r] is the row of read r, qual / qual_off are unused
+    int sq = 0;
 };
+
+// ---- interleaved SEQ + QUAL rows (include/lps.h, lps_read_batch.sq) -------------------------------------------------------
+// A row is made of 16-byte units of ten bases: bytes 0..9 base qualities, bytes 10..14 the ten 4-bit codes in BAM's packing.
+// The same arithmetic serves the kernel's gather, the host packer and lps_sq_peek.
+constexpr uint32_t SQ_BASES = 10, SQ_UNIT = 16;
+__host__ __device__ __forceinline__ uint32_t sq_unit_of(uint32_t qi) { return qi / SQ_BASES; }
+// w = the unit as four little-endian words, k = qi - 10 * unit
+__host__ __device__ __forceinline__ void sq_extract(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t k, unsigned &code, unsigned &quality) {
+    const uint32_t wq = k < 4u ? w0 : k < 8u ? w1 : w2;
+    quality = (wq >> ((k & 3u) * 8u)) & 0xFFu;
+    const uint32_t sb = 10u + (k >> 1);                       // byte 10..14 holds bases 2 (sb - 10) and 2 (sb - 10) + 1
+    const uint32_t ws = sb < 12u ? w2 : w3;
+    const unsigned byte = (ws >> ((sb & 3u) * 8u)) & 0xFFu;
+    code = (byte >> ((~k & 1u) << 2)) & 0xFu;                 // bam_seqi: even index in the high nibble (unit starts are even)
+}
 
 // device view of the variant table
 struct DevVariants {

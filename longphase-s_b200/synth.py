@@ -283,6 +283,45 @@ class Contig:
             b.cigar_long_at = P(long_at, _ffi.u64p)
         return b
 
+    def pack_sq(self, threads=8):
+        """SEQ + QUAL as interleaved rows (include/lps.h, lps_read_batch.sq), made by the library's own lps_pack_sq_batch as the host
+        loop would while appending records.  Returns (sq, sq_off): the stream and the 16-byte aligned row offset of every read."""
+        lq = np.maximum(self.l_qseq.astype(np.int64), 0)
+        rows = (lq + 9) // 10 * 16
+        sq_off = np.zeros(self.n_reads, np.uint64)
+        if self.n_reads:
+            sq_off[1:] = np.cumsum(rows)[:-1].astype(np.uint64)
+        sq = np.zeros(max(int(rows.sum()), 16), np.uint8)
+        lib, P = _ffi.load_library(), _ffi.ptr
+        l_qseq, seq_off, qual_off = (np.ascontiguousarray(a) for a in (self.l_qseq, self.seq_off, self.qual_off))
+
+        def part(k):
+            r0, r1 = self.n_reads * k // threads, self.n_reads * (k + 1) // threads
+            if r1 > r0:
+                rc = lib.lps_pack_sq_batch(r1 - r0, P(l_qseq[r0:r1], _ffi.i32p), P(seq_off[r0:r1], _ffi.u64p), P(qual_off[r0:r1], _ffi.u64p),
+                                           P(self.seq4, _ffi.u8p), P(self.qual, _ffi.u8p), P(sq_off[r0:r1], _ffi.u64p), P(sq, _ffi.u8p))
+                if rc != 0:
+                    raise RuntimeError(f"lps_pack_sq_batch failed: rc {rc}")
+        if threads > 1 and self.n_reads >= 64:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(part, range(threads)))
+        else:
+            threads = 1
+            part(0)
+        return sq, sq_off
+
+    def batch_struct_sq(self):
+        """batch_struct8() with SEQ + QUAL as interleaved rows (phase calls only); the arrays are kept alive on the object."""
+        self._sq = self.pack_sq()
+        b = self.batch_struct8()
+        P = _ffi.ptr
+        b.seq4, b.qual, b.qual_off = C.cast(None, _ffi.u8p), C.cast(None, _ffi.u8p), C.cast(None, _ffi.u64p)
+        b.seq_bytes = b.qual_bytes = 0
+        b.seq_off = P(self._sq[1], _ffi.u64p)
+        b.sq, b.sq_bytes = P(self._sq[0], _ffi.u8p), len(self._sq[0])
+        return b
+
     def name(self, i):
         s = self.names[i * self.NAME_STRIDE:(i + 1) * self.NAME_STRIDE]
         return s[:s.index(b"\0")].decode()

@@ -71,6 +71,14 @@ def check_phase(contig, params, ctx=None, verbose=False):
         res4 = ctx.phase_contig(params)
         for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
             assert np.array_equal(res4[k], res[k]), f"cigar8 submit: {k} differs"
+        # ... and SEQ + QUAL as interleaved rows (lps_read_batch.sq): the calls themselves (base quality, allele) and the end result
+        ctx.submit(contig.batch_struct_sq())
+        calls5 = ctx.call_alleles(params, want_host=True)
+        assert np.array_equal(calls5["call_off"], calls["call_off"]) and calls5["calls"].tobytes() == calls["calls"].tobytes(), "sq submit: calls differ"
+        assert np.array_equal(calls5["read_status"], calls["read_status"]), "sq submit: read status differs"
+        res5 = ctx.phase_contig(params)
+        for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
+            assert np.array_equal(res5[k], res[k]), f"sq submit: {k} differs"
         info = dict(reads=contig.n_reads, variants=contig.n_var, calls=len(orc.calls), nodes=orc.n_nodes,
                     phased=int(m.sum()), contrib=int(orc.n_contrib), lowq_cells=int((orc.weights != np.round(orc.weights)).sum()),
                     stats=ctx.stats())

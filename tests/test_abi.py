@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     # sizes the C compiler produces for the structs of include/lps.h (LP64)
     assert C.sizeof(ffi.LpsCall) == 8
     assert C.sizeof(ffi.LpsVariants) == 72
-    assert C.sizeof(ffi.LpsReadBatch) == 192
+    assert C.sizeof(ffi.LpsReadBatch) == 208
     assert C.sizeof(ffi.LpsPhaseParams) == 64
     assert ffi.CALL_DTYPE.itemsize == 8
 

@@ -104,10 +104,32 @@ def test_gpu_full_size_properties():
     ctx.submit(batch(pt))                                        # pinned host buffers: SEQ / QUAL gathered over PCIe (zero-copy)
     cc = ctx.call_alleles(p, want_host=True)
     r_c = ctx.phase_contig(p)
-    for x in (b, cc):
+    # SEQ + QUAL as interleaved rows (lps_read_batch.sq): pinned rows gathered over PCIe, then the same rows resident on the device
+    sq, sq_off = c.pack_sq()
+    sq_p, off_p = torch.from_numpy(sq).pin_memory(), torch.from_numpy(sq_off.view(np.int64)).pin_memory()
+    sq_d, off_d = torch.from_numpy(sq).cuda(), torch.from_numpy(sq_off.view(np.int64)).cuda()
+
+    def batch_sq(d, sq_t, off_t):
+        bb = batch(d)
+        bb.seq4, bb.qual, bb.qual_off = C.cast(None, ffi.u8p), C.cast(None, ffi.u8p), C.cast(None, ffi.u64p)
+        bb.seq_bytes = bb.qual_bytes = 0
+        bb.seq_off = C.cast(off_t.data_ptr(), ffi.u64p)
+        bb.sq, bb.sq_bytes = C.cast(sq_t.data_ptr(), ffi.u8p), sq_t.numel()
+        return bb
+    s0 = ctx.stats()["h2d_bytes"]
+    ctx.submit(batch_sq(pt, sq_p, off_p))
+    dd = ctx.call_alleles(p, want_host=True)
+    r_d = ctx.phase_contig(p)
+    moved = ctx.stats()["h2d_bytes"] - s0
+    assert moved < len(c.cigar) * 4 + 64 * c.n_reads + 2 * 40 * a["n_calls"] + (1 << 20), "pinned sq rows were copied instead of gathered"
+    ctx.submit_device(batch_sq(dt, sq_d, off_d))
+    ee = ctx.call_alleles(p, want_host=True)
+    r_e = ctx.phase_contig(p)
+    ctx.submit_device(batch(dt))
+    for x in (b, cc, dd, ee):
         assert np.array_equal(a["call_off"], x["call_off"]) and a["calls"].tobytes() == x["calls"].tobytes()
         assert np.array_equal(a["read_status"], x["read_status"]) and np.array_equal(a["clip_pos"], x["clip_pos"])
-    for x in (r_b, r_c):
+    for x in (r_b, r_c, r_d, r_e):
         for k in ("ps", "hap_ref", "read_hp", "hp_counts"):
             assert np.array_equal(r_a[k], x[k]), k
     off = a["call_off"].astype(np.int64)

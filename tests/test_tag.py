@@ -74,3 +74,19 @@ def test_gpu_tag_requires_phased_variant_table():
     with pytest.raises(host.LpsError):
         ctx.tag_reads(tag_cases.param_sets()["default"])
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_tag_rejects_interleaved_rows():
+    """lps_read_batch.sq serves the phase calls only: the tag dialects read runs of bases and say so instead of reading garbage."""
+    name = next(iter(tag_cases.TAG_CASES))
+    c = tag_cases.get(name, "phase_result")
+    tp = tag_cases.param_sets()["default"]
+    ctx = host.Context(0)
+    check_gpu_tag(c, tp, ctx)                          # context holds the tagged variant table now
+    ctx.submit(c.batch_struct_sq())
+    with pytest.raises(host.LpsError, match="phase calls only"):
+        ctx.tag_reads(tp)
+    ctx.submit(c.batch_struct())
+    assert np.array_equal(ctx.tag_reads(tp, want_calls=False)["hp"], po.OracleTag(c, tp).hp)
+    ctx.close()
