@@ -38,6 +38,34 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "phase_hot_path_reads_per_s"
 
 
+def cpus_of_list(text):
+    out = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            out.update(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_to_gpu_numa(torch, local_rank, want_cores):
+    """Several ranks on one box: keep this rank's host threads on the cores next to its GPU (sysfs local_cpulist of the GPU's PCI
+    function), so that the pages they touch first - the pinned buffers the GPU reads over PCIe - live on that NUMA node.  Only when
+    at least `want_cores` of those cores are in this process's affinity mask; otherwise nothing changes.  Returns what was done."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        local = cpus_of_list(open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read())
+        node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+        mine = os.sched_getaffinity(0)
+        both = mine & local
+        if len(both) >= want_cores and len(both) < len(mine):
+            os.sched_setaffinity(0, both)
+            return "node %s: %d of %d cores" % (node, len(both), len(mine))
+        return "unchanged (node %s, %d local cores among this process's %d)" % (node, len(both), len(mine))
+    except Exception as e:          # no sysfs entry, no permission: the run goes on unbound
+        return "unchanged (%s)" % type(e).__name__
+
+
 def workload_text(args, world, n_contigs_rank0):
     if args.workload == "genome":
         return ("C2 whole-genome shape at %.0f Mb: phase SNP+indel over 24 GRCh38-proportioned contigs (%.1f .. %.1f Mb), %gx ONT-like %g kb reads, "
@@ -216,6 +244,8 @@ def main():
     ap.add_argument("--no-other-paths", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sq", action="store_true")            # end-to-end leg: SEQ and QUAL as BAM's two arrays instead of the interleaved rows (lps_read_batch.sq)
+    ap.add_argument("--no-numa", action="store_true")          # several ranks: do not bind the host threads to the GPU's NUMA node
+    ap.add_argument("--e2e-ab", action="store_true")           # end-to-end leg: time the other SEQ / QUAL wire format as well (reported beside the headline one)
     ap.add_argument("--resident-sq", action="store_true")      # resident leg: the interleaved rows in HBM instead of the two arrays (experiment; the line says so)
     ap.add_argument("--sync", default="auto", choices=["auto", "spin", "block", "yield"])
     ap.add_argument("--cigar16", action="store_true")    # end-to-end leg: send the 16-bit CIGAR stream instead of the 8-bit wire format
@@ -274,6 +304,7 @@ def main():
     blocking = args.sync == "block"
     if blocking or args.sync == "yield":
         ffi.load_library().lps_set_blocking_sync(local_rank, 1 if blocking else 2)
+    numa = bind_to_gpu_numa(torch, local_rank, max(2, ncores // world)) if world > 1 and not args.no_numa else "not applicable"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -468,86 +499,95 @@ def main():
     ctxs[big].submit_device(dev_batches[big])
 
     # ---- end-to-end leg: pinned host buffers through the C ABI ----
-    e2e = None
+    e2e = e2e_other = None
     if not args.no_e2e:
         # The host loop packs the CIGAR ops of every record into the 8-bit wire format while it appends the record to the batch
         # (lps_pack_cigar8; include/lps.h); the device expands it into the resident 16-bit stream.  The big streams are pinned in place (cudaHostRegister), the small ones copied.
         cudart = torch.cuda.cudart()
-        pinned_in_place, ptens, pin_batches = [], [], []
 
-        def pin(a):
-            a = np.ascontiguousarray(a)
-            if a.nbytes >= (1 << 20):
-                rc = cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
-                if int(rc) == 0:
-                    pinned_in_place.append(a)
-                    return a, a.ctypes.data
-            t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
-            return t, t.data_ptr()
-        use_sq = not args.no_sq and not args.cigar32 and not args.cigar16
-        for c, pk in zip(contigs, packed):
-            d, ptr = {}, {}
-            for k in names:
-                if use_sq and k in ("seq4", "qual", "qual_off", "seq_off"):
-                    continue
-                d[k], ptr[k] = pin(getattr(c, k))
-            if use_sq:
-                # the host loop writes a record's bases and qualities as one interleaved row (lps_pack_sq) while it appends the record
-                sq, sq_off = c.pack_sq(threads=min(ncores, 16))
-                d["sq"], ptr["sq"] = pin(sq)
-                d["seq_off"], ptr["seq_off"] = pin(sq_off)
-                del sq
-            if args.cigar32:
-                d["cigar"], ptr["cigar"] = pin(c.cigar)
-                b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
-                                     **{k: C.cast(ptr[k], ptypes[k]) for k in names + ["cigar"]})
-            elif args.cigar16:
-                d["cigar16"], ptr["cigar16"] = pin(pk[0])
-                if len(pk[1]):
-                    d["cigar_long_len"], ptr["cigar_long_len"] = pin(pk[1])
-                    d["cigar_long_at"], ptr["cigar_long_at"] = pin(pk[2])
-                b = batch_from(c, lambda k, ptr=ptr: ptr.get(k), pk)
-            else:
-                c8, esc16, esc_blk, long_len, long_at = c.pack_cigar8()
-                d["cigar8"], ptr["cigar8"] = pin(c8)
-                d["cigar_esc_blk"], ptr["cigar_esc_blk"] = pin(esc_blk)
+        def run_e2e(use_sq):
+            pinned_in_place, ptens, pin_batches = [], [], []
+
+            def pin(a):
+                a = np.ascontiguousarray(a)
+                if a.nbytes >= (1 << 20):
+                    rc = cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+                    if int(rc) == 0:
+                        pinned_in_place.append(a)
+                        return a, a.ctypes.data
+                t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+                return t, t.data_ptr()
+            for c, pk in zip(contigs, packed):
+                d, ptr = {}, {}
+                for k in names:
+                    if use_sq and k in ("seq4", "qual", "qual_off", "seq_off"):
+                        continue
+                    d[k], ptr[k] = pin(getattr(c, k))
                 if use_sq:
-                    b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), sq=C.cast(ptr["sq"], ffi.u8p), sq_bytes=len(d["sq"]),
-                                         **{k: C.cast(ptr[k], ptypes[k]) for k in names if k in ptr})
-                else:
+                    # the host loop writes a record's bases and qualities as one interleaved row (lps_pack_sq) while it appends the record
+                    sq, sq_off = c.pack_sq(threads=min(ncores, 16))
+                    d["sq"], ptr["sq"] = pin(sq)
+                    d["seq_off"], ptr["seq_off"] = pin(sq_off)
+                    del sq
+                    if not args.e2e_ab:
+                        # nothing reads the generator's two host arrays from here on (the resident copy lives in HBM): keeps the
+                        # host footprint at one copy of the bases and qualities
+                        c.seq4, c.qual = c.seq4[:0].copy(), c.qual[:0].copy()
+                if args.cigar32:
+                    d["cigar"], ptr["cigar"] = pin(c.cigar)
                     b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
-                                         **{k: C.cast(ptr[k], ptypes[k]) for k in names})
-                b.cigar8, b.cigar_esc_blk = C.cast(ptr["cigar8"], ffi.u8p), C.cast(ptr["cigar_esc_blk"], ffi.u32p)
-                b.n_cigar_esc, b.n_cigar_long = len(esc16), len(long_len)
-                if len(esc16):
-                    d["cigar_esc16"], ptr["cigar_esc16"] = pin(esc16)
-                    b.cigar_esc16 = C.cast(ptr["cigar_esc16"], ffi.u16p)
-                if len(long_len):
-                    d["cigar_long_len"], ptr["cigar_long_len"] = pin(long_len)
-                    d["cigar_long_at"], ptr["cigar_long_at"] = pin(long_at)
-                    b.cigar_long_len, b.cigar_long_at = C.cast(ptr["cigar_long_len"], ffi.u32p), C.cast(ptr["cigar_long_at"], ffi.u64p)
-            ptens.append(d)
-            pin_batches.append(b)
-        host_bytes = int(sum((t.nbytes if isinstance(t, np.ndarray) else t.numel()) for d in ptens for t in d.values()))
+                                         **{k: C.cast(ptr[k], ptypes[k]) for k in names + ["cigar"]})
+                elif args.cigar16:
+                    d["cigar16"], ptr["cigar16"] = pin(pk[0])
+                    if len(pk[1]):
+                        d["cigar_long_len"], ptr["cigar_long_len"] = pin(pk[1])
+                        d["cigar_long_at"], ptr["cigar_long_at"] = pin(pk[2])
+                    b = batch_from(c, lambda k, ptr=ptr: ptr.get(k), pk)
+                else:
+                    c8, esc16, esc_blk, long_len, long_at = c.pack_cigar8()
+                    d["cigar8"], ptr["cigar8"] = pin(c8)
+                    d["cigar_esc_blk"], ptr["cigar_esc_blk"] = pin(esc_blk)
+                    if use_sq:
+                        b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), sq=C.cast(ptr["sq"], ffi.u8p), sq_bytes=len(d["sq"]),
+                                             **{k: C.cast(ptr[k], ptypes[k]) for k in names if k in ptr})
+                    else:
+                        b = ffi.LpsReadBatch(n_reads=c.n_reads, cigar_len=len(c.cigar), seq_bytes=len(c.seq4), qual_bytes=len(c.qual),
+                                             **{k: C.cast(ptr[k], ptypes[k]) for k in names})
+                    b.cigar8, b.cigar_esc_blk = C.cast(ptr["cigar8"], ffi.u8p), C.cast(ptr["cigar_esc_blk"], ffi.u32p)
+                    b.n_cigar_esc, b.n_cigar_long = len(esc16), len(long_len)
+                    if len(esc16):
+                        d["cigar_esc16"], ptr["cigar_esc16"] = pin(esc16)
+                        b.cigar_esc16 = C.cast(ptr["cigar_esc16"], ffi.u16p)
+                    if len(long_len):
+                        d["cigar_long_len"], ptr["cigar_long_len"] = pin(long_len)
+                        d["cigar_long_at"], ptr["cigar_long_at"] = pin(long_at)
+                        b.cigar_long_len, b.cigar_long_at = C.cast(ptr["cigar_long_len"], ffi.u32p), C.cast(ptr["cigar_long_at"], ffi.u64p)
+                ptens.append(d)
+                pin_batches.append(b)
+            host_bytes = int(sum((t.nbytes if isinstance(t, np.ndarray) else t.numel()) for d in ptens for t in d.values()))
 
-        def step_e2e(i, last):
-            ctxs[i].submit(pin_batches[i])
-            return ctxs[i].phase_contig(params, copy=last)
-        run_threads(step_e2e, min(args.warmup, 2))
-        s2 = [ctx.stats() for ctx in ctxs]
-        e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps, 2)
-        e2e_ms = max_over_ranks(e2e_dev_ms)
-        s3 = [ctx.stats() for ctx in ctxs]
-        d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
-        h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
-        ok_e2e, _ = digest_ok(results)
-        if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0 and not debug_no_gate:
-            raise SystemExit("bench.py: the end-to-end leg's result differs from the committed digest: no value is reported")
-        e2e = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes, use_sq)
-        for i in range(n_ctg):
-            ctxs[i].submit_device(dev_batches[i])       # nothing refers to the host buffers any more
-        for a in pinned_in_place:
-            cudart.cudaHostUnregister(a.ctypes.data)
+            def step_e2e(i, last):
+                ctxs[i].submit(pin_batches[i])
+                return ctxs[i].phase_contig(params, copy=last)
+            run_threads(step_e2e, min(args.warmup, 2))
+            s2 = [ctx.stats() for ctx in ctxs]
+            e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps, 2)
+            e2e_ms = max_over_ranks(e2e_dev_ms)
+            s3 = [ctx.stats() for ctx in ctxs]
+            d2h_step = int(sum(b_["d2h_bytes"] - a_["d2h_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+            h2d_step = int(sum(b_["h2d_bytes"] - a_["h2d_bytes"] for a_, b_ in zip(s2, s3)) / args.steps)
+            ok_e2e, _ = digest_ok(results)
+            if min_over_ranks(1.0 if ok_e2e else 0.0) < 1.0 and not debug_no_gate:
+                raise SystemExit("bench.py: the end-to-end leg's result differs from the committed digest: no value is reported")
+            out = (e2e_ms, e2e_wall_ms, h2d_step, d2h_step, host_bytes, use_sq)
+            for i in range(n_ctg):
+                ctxs[i].submit_device(dev_batches[i])       # nothing refers to the host buffers any more
+            for a in pinned_in_place:
+                cudart.cudaHostUnregister(a.ctypes.data)
+            return out
+        use_sq = not args.no_sq and not args.cigar32 and not args.cigar16
+        e2e = run_e2e(use_sq)
+        e2e_other = run_e2e(not use_sq) if args.e2e_ab and not args.cigar32 and not args.cigar16 else None
 
     if rank == 0:
         clocks = sampler.stop()
@@ -569,7 +609,7 @@ def main():
                    "variants_rank0": int(sum(c.n_var for c in contigs)), "allele_calls_total": int(total_calls),
                    "cigar_ops_per_read": float(np.mean([c.n_cigar.mean() for c in contigs])), "resident_bytes_rank0": resident_bytes,
                    "l2": "inputs (%.1f GB on rank 0) are far larger than the 126 MB L2; no flush needed" % (resident_bytes / 1e9),
-                   "host_sync": "blocking" if blocking else ("yield" if args.sync == "yield" else "spin"), "host_cores": ncores,
+                   "host_sync": "blocking" if blocking else ("yield" if args.sync == "yield" else "spin"), "host_cores": ncores, "numa_bind": numa,
                    "parallelism": "contigs sharded over %d GPU(s) by LPT on read counts, one lps_ctx (stream + scratch) per contig, %d host thread(s) per "
                                   "rank, no collective" % (world, T_),
                    "timing": "CUDA events on every context's stream (the streams the kernels run on), max over contexts and ranks",
@@ -589,6 +629,9 @@ def main():
                        "cigar_wire_format": ("uint32 (BAM), narrowed on the device" if args.cigar32 else
                                              "16-bit stream (lps_pack_cigar16), used as it arrives" if args.cigar16 else
                                              "8-bit stream (lps_pack_cigar8), expanded into the resident 16-bit stream by k_expand_cigar8")}
+    if e2e is not None and e2e_other is not None:
+        line["e2e"]["other_wire_format"] = {"seq_qual": "BAM's two arrays" if e2e[5] else "interleaved rows", "ms_per_step": e2e_other[0],
+                                            "value": total_reads / (e2e_other[0] * 1e-3), "h2d_bytes_per_step": e2e_other[2]}
     if rank == 0 and world == 1 and not args.no_other_paths:
         # ---- the other dialects of the hot path (BASELINE configs C3 / C4), kernel-resident device time of one call each ----
         other = {}

@@ -426,6 +426,8 @@ lpsh_bamw *lpsh_bamw_open(const char *path, int n_contigs, const char **names, c
     return w;
 }
 
+int lpsh_sizeof_read_batch(void) { return (int)sizeof(lps_read_batch); }
+
 int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char *names, int name_stride) {
     if (!w || !b) return -1;
     bam1_t *rec = bam_init1();

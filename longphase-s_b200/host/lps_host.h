@@ -128,6 +128,9 @@ int lpsh_som_main(int argc, char **argv);
 typedef struct lpsh_bamw lpsh_bamw;
 lpsh_bamw *lpsh_bamw_open(const char *path, int n_contigs, const char **names, const int64_t *lens, int threads);
 /* appends the batch (coordinate order) as records of contig `tid`; names = fixed-stride NUL-terminated read names      */
+/* sizeof(lps_read_batch) this library was compiled with: a host built against an older include/lps.h would hand the kernels'
+ * library a shorter struct (tests/test_abi.py compares it with the ctypes mirror and liblps_b200.so's own header hash)      */
+int lpsh_sizeof_read_batch(void);
 int lpsh_bamw_append(lpsh_bamw *w, int tid, const lps_read_batch *b, const char *names, int name_stride);
 int64_t lpsh_decode_only(const char *in_path, int threads);                        /* sam_read1 over the whole file: the I/O floor   */
 int lpsh_to_sam(const char *in_path, const char *fasta, const char *out_path);   /* BAM / CRAM -> SAM text                          */

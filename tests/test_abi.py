@@ -36,6 +36,17 @@ def test_struct_layouts_match_the_header():
     assert ffi.CALL_DTYPE.itemsize == 8
 
 
+def test_host_library_was_built_against_this_header():
+    """liblps_host.so embeds lps_read_batch by value (lpsh_packed): a host library compiled before the struct grew would hand the
+    kernels' library uninitialised trailing fields."""
+    path = os.path.join(ROOT, "longphase-s_b200", "liblps_host.so")
+    if not os.path.exists(path):
+        pytest.skip("the C++ host is not built here")
+    hostlib = C.CDLL(path)
+    assert hasattr(hostlib, "lpsh_sizeof_read_batch"), "stale liblps_host.so: rebuild with make -C longphase-s_b200/host"
+    assert hostlib.lpsh_sizeof_read_batch() == C.sizeof(ffi.LpsReadBatch)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the context cannot be created: the product path must fail loudly."""
     import torch
