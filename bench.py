@@ -47,21 +47,25 @@ def cpus_of_list(text):
     return out
 
 
-def bind_to_gpu_numa(torch, local_rank, want_cores):
+def bind_to_gpu_numa(torch, local_rank, world, cores_per_rank):
     """Several ranks on one box: keep this rank's host threads on the cores next to its GPU (sysfs local_cpulist of the GPU's PCI
     function), so that the pages they touch first - the pinned buffers the GPU reads over PCIe - live on that NUMA node.  Only when
-    at least `want_cores` of those cores are in this process's affinity mask; otherwise nothing changes.  Returns what was done."""
+    those cores, shared with the other ranks whose GPUs sit on the same node, still leave every rank `cores_per_rank` of them;
+    otherwise nothing changes.  Returns what was done."""
     try:
-        pr = torch.cuda.get_device_properties(local_rank)
-        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        local = cpus_of_list(open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read())
-        node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+        def local_cpus(dev):
+            pr = torch.cuda.get_device_properties(dev)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return (cpus_of_list(open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read()),
+                    open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        local, node = local_cpus(local_rank)
+        sharing = sum(1 for d in range(min(world, torch.cuda.device_count())) if local_cpus(d)[0] == local)
         mine = os.sched_getaffinity(0)
         both = mine & local
-        if len(both) >= want_cores and len(both) < len(mine):
+        if len(both) >= max(2, cores_per_rank) * max(1, sharing) and len(both) < len(mine):
             os.sched_setaffinity(0, both)
-            return "node %s: %d of %d cores" % (node, len(both), len(mine))
-        return "unchanged (node %s, %d local cores among this process's %d)" % (node, len(both), len(mine))
+            return "node %s: %d of %d cores, shared by %d rank(s)" % (node, len(both), len(mine), sharing)
+        return "unchanged (node %s, %d local cores among this process's %d, %d rank(s) on the node)" % (node, len(both), len(mine), sharing)
     except Exception as e:          # no sysfs entry, no permission: the run goes on unbound
         return "unchanged (%s)" % type(e).__name__
 
@@ -304,7 +308,7 @@ def main():
     blocking = args.sync == "block"
     if blocking or args.sync == "yield":
         ffi.load_library().lps_set_blocking_sync(local_rank, 1 if blocking else 2)
-    numa = bind_to_gpu_numa(torch, local_rank, max(2, ncores // world)) if world > 1 and not args.no_numa else "not applicable"
+    numa = bind_to_gpu_numa(torch, local_rank, world, ncores // world) if world > 1 and not args.no_numa else "not applicable"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
