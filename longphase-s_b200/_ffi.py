@@ -214,6 +214,9 @@ SYMBOLS = {
     "lps_bgzf_scan": (C.c_int, [u8p, C.c_uint64, C.POINTER(LpsBgzfBlock), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "lps_bgzf_inflate": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(LpsBgzfBlock), C.c_uint64, u8p, C.c_uint64, C.c_int]),
     "lps_bgzf_inflate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "lps_bgzf_deflate_bound": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+    "lps_bgzf_deflate": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.c_uint32, u8p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "lps_bgzf_deflate_block_host": (C.c_int, [u8p, C.c_uint32, u8p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "lps_set_blocking_sync": (C.c_int, [C.c_int, C.c_int]),
     "lps_estimate_purity": (C.c_int, [C.POINTER(LpsPurityInput), C.POINTER(LpsPurityResult)]),
     "lps_somatic_call": (C.c_int, [C.POINTER(LpsSomaticCallInput), C.POINTER(LpsSomaticCallResult)]),

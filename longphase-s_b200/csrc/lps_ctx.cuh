@@ -186,6 +186,8 @@ struct lps_ctx {
     DevBuf<uint32_t> d_n_cigar, d_cigar;
     DevBuf<uint8_t> d_bgzf_in, d_bgzf_out, d_bgzf_status;   // lps_bgzf_inflate
     DevBuf<lps_bgzf_block> d_bgzf_blocks;
+    DevBuf<uint8_t> d_defl_slots, d_defl_out;                // lps_bgzf_deflate: one fixed slot per member, the contiguous stream
+    DevBuf<uint64_t> d_defl_sizes, d_defl_off;
     std::vector<uint8_t> h_bgzf_status;
     DevBuf<uint16_t> d_cigar16;                     // the CIGAR stream in 16 bits per op (what the kernels read)
     DevBuf<uint8_t> d_cigar8;                       // 8-bit wire format of a submitted batch, expanded into d_cigar16 on arrival

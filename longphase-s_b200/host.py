@@ -191,6 +191,17 @@ class Context:
                                               len(blocks), _ffi.ptr(out, _ffi.u8p), out_bytes, int(check_crc)))
         return out[:out_bytes]
 
+    # ---- BGZF (htslib bgzf_write / deflate_block) ----
+    def bgzf_deflate(self, data, block_bytes=0xff00):
+        """Deflates `data` on the device into BGZF members of block_bytes input bytes each (no EOF marker); returns the bytes."""
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        cap = int(self.lib.lps_bgzf_deflate_bound(len(buf), block_bytes))
+        out = np.zeros(max(cap, 1), np.uint8)
+        n = C.c_uint64(0)
+        self._check(self.lib.lps_bgzf_deflate(self.h, _ffi.ptr(buf if len(buf) else np.zeros(1, np.uint8), _ffi.u8p), len(buf), block_bytes,
+                                              _ffi.ptr(out, _ffi.u8p), cap, C.byref(n)))
+        return out[:n.value]
+
     def stats(self):
         s = _ffi.LpsStats()
         self._check(self.lib.lps_get_stats(self.h, C.byref(s)))

@@ -337,7 +337,7 @@ int lpsh_tag_pack(lpsh_tag *h, int i, lpsh_packed *out) {
 static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result *r);
 
 int lpsh_tag_emit(lpsh_tag *h, int i, const lps_tag_result *r) {
-    if (!h || !r || h->chunk_contig != i || !h->io.out) return -1;
+    if (!h || !r || h->chunk_contig != i || !h->io.has_output()) return -1;
     return emit_chunk(h, i, h->chunk, r);
 }
 
@@ -399,7 +399,7 @@ static int emit_chunk(lpsh_tag *h, int i, lpsh::Chunk &ck, const lps_tag_result 
                 h->st_untag++;
             }
         }
-        if (sam_write1(h->io.out, h->io.hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+        if (h->io.write(b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
     }
     ck.clear();
     return 0;
@@ -539,7 +539,7 @@ int lpsh_tag_run(lpsh_tag *h) {
 
 void lpsh_tag_close(lpsh_tag *h) {
     if (!h) return;
-    if (h->io.in || h->io.out) lpsh_tag_end(h);
+    if (h->io.is_open()) lpsh_tag_end(h);
     delete h;
 }
 

@@ -217,6 +217,134 @@ int pack_region_split(const std::string &bam_path, const std::string &fasta, con
 }
 
 // ---- files and region reader of a tagging pass ------------------------------------------------------------------------------------
+// ---- the BAM writer with the deflate on the device ----------------------------------------------------------------------------
+namespace {
+lpsh_deflate_fn g_deflater = nullptr;
+void *g_deflater_user = nullptr;
+const uint8_t BGZF_EOF_MARKER[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // SAM spec 4.1.2
+void put_le32(std::vector<uint8_t> &v, uint32_t x) {
+    const uint8_t b[4] = {(uint8_t)x, (uint8_t)(x >> 8), (uint8_t)(x >> 16), (uint8_t)(x >> 24)};
+    v.insert(v.end(), b, b + 4);
+}
+}  // namespace
+
+bool gpu_deflate_requested(const std::string &out_mode) {
+    const char *e = getenv("LPS_GPU_DEFLATE");
+    return e && e[0] == '1' && e[1] == '\0' && out_mode == "wb";
+}
+
+int DeviceBamWriter::open(const std::string &path, bam_hdr_t *hdr) {
+    fp = fopen(path.c_str(), "wb");
+    if (!fp) return fail("Cannot open output bam file " + path);
+    if (const char *e = getenv("LPS_DEFLATE_BATCH")) {                       // bytes of records per deflate call (tests: small batches)
+        const long long v = atoll(e);
+        if (v >= 0xff00) flush_bytes = (size_t)v / 0xff00 * 0xff00;
+    }
+    // the header as bam_hdr_write lays it out (htslib/sam.c:331-402): magic, text, reference names and lengths
+    const char *text = sam_hdr_str(hdr);
+    const size_t l_text = sam_hdr_length(hdr);
+    if (!text || l_text == SIZE_MAX || l_text > UINT32_MAX) return fail("Cannot write header to output bam file " + path);
+    raw.reserve(flush_bytes + (1u << 20));
+    raw.insert(raw.end(), {'B', 'A', 'M', 1});
+    put_le32(raw, (uint32_t)l_text);
+    raw.insert(raw.end(), text, text + l_text);
+    put_le32(raw, (uint32_t)hdr->n_targets);
+    for (int i = 0; i < hdr->n_targets; i++) {
+        const char *name = hdr->target_name[i];
+        const size_t n = strlen(name) + 1;
+        put_le32(raw, (uint32_t)n);
+        raw.insert(raw.end(), name, name + n);
+        put_le32(raw, hdr->target_len[i]);
+    }
+    return 0;
+}
+
+int DeviceBamWriter::write(const bam1_t *b) {
+    const bam1_core_t &c = b->core;
+    const uint32_t l_name = (uint32_t)c.l_qname - c.l_extranul;
+    if (l_name > 255) return fail("QNAME is longer than 254 characters");
+    if (c.pos > INT32_MAX || c.mpos > INT32_MAX || c.isize < INT32_MIN || c.isize > INT32_MAX) return fail("Positional data is too large for BAM format");
+    const bool long_cigar = c.n_cigar > 0xffff;
+    uint32_t block_len = (uint32_t)b->l_data - c.l_extranul + 32 + (long_cigar ? 16 : 0);
+    put_le32(raw, block_len);
+    put_le32(raw, (uint32_t)c.tid);
+    put_le32(raw, (uint32_t)c.pos);
+    put_le32(raw, (uint32_t)c.bin << 16 | (uint32_t)c.qual << 8 | l_name);
+    put_le32(raw, (uint32_t)c.flag << 16 | (long_cigar ? 2u : (c.n_cigar & 0xffffu)));
+    put_le32(raw, (uint32_t)c.l_qseq);
+    put_le32(raw, (uint32_t)c.mtid);
+    put_le32(raw, (uint32_t)c.mpos);
+    put_le32(raw, (uint32_t)c.isize);
+    raw.insert(raw.end(), b->data, b->data + l_name);                       // the name without the padding NULs bam1_t keeps
+    if (!long_cigar) {
+        raw.insert(raw.end(), b->data + c.l_qname, b->data + b->l_data);
+    } else {
+        // more than 65 535 operations: <l_qseq>S<reference length>N in the CIGAR field, the real operations in a CG:B,I tag (SAM spec 4.2.2)
+        const hts_pos_t rlen = bam_cigar2rlen((int)c.n_cigar, bam_get_cigar(b));
+        if (rlen >= (1 << 28)) return fail("a record with more than 65535 CIGAR operations covers too much reference for BAM");
+        const size_t cigar_st = (size_t)((const uint8_t *)bam_get_cigar(b) - b->data), cigar_en = cigar_st + (size_t)c.n_cigar * 4;
+        put_le32(raw, (uint32_t)c.l_qseq << 4 | BAM_CSOFT_CLIP);
+        put_le32(raw, (uint32_t)rlen << 4 | BAM_CREF_SKIP);
+        raw.insert(raw.end(), b->data + cigar_en, b->data + b->l_data);
+        raw.insert(raw.end(), {'C', 'G', 'B', 'I'});
+        put_le32(raw, c.n_cigar);
+        raw.insert(raw.end(), b->data + cigar_st, b->data + cigar_en);       // little-endian host, like the rest of this file's packing
+    }
+    if (raw.size() >= flush_bytes) return hand_over();
+    return 0;
+}
+
+int DeviceBamWriter::deflate_and_append(const std::vector<uint8_t> &in) {
+    if (in.empty()) return 0;
+    const double t0 = now_ms();
+    const uint64_t cap = lps_bgzf_deflate_bound(in.size(), 0xff00);
+    if (comp.size() < cap) comp.resize((size_t)cap);
+    uint64_t n = 0;
+    int rc;
+    if (g_deflater) {
+        rc = g_deflater(g_deflater_user, in.data(), in.size(), 0xff00, comp.data(), cap, &n);
+        if (rc != 0) return fail("the deflater hook failed");
+    } else {
+        if (!ctx && lps_ctx_create(0, &ctx) != 0) return fail("no usable CUDA device (there is no CPU fallback)");
+        rc = lps_bgzf_deflate(ctx, in.data(), in.size(), 0xff00, comp.data(), cap, &n);
+        if (rc != 0) return fail(std::string("lps_bgzf_deflate: ") + lps_last_error(ctx));
+    }
+    const double t1 = now_ms();
+    if (fwrite(comp.data(), 1, (size_t)n, fp) != (size_t)n) return fail("write output bam file failed");
+    ms_deflate += t1 - t0; ms_file += now_ms() - t1;
+    bytes_in += in.size(); bytes_out += n;
+    return 0;
+}
+
+int DeviceBamWriter::hand_over() {
+    if (flusher_running) { flusher.join(); flusher_running = false; }
+    if (flusher_rc != 0) return -1;
+    // cut at a member boundary so that every call but the last deflates whole 65 280-byte members
+    const size_t whole = raw.size() / 0xff00 * 0xff00;
+    busy_raw.assign(raw.begin(), raw.begin() + (std::ptrdiff_t)whole);
+    raw.erase(raw.begin(), raw.begin() + (std::ptrdiff_t)whole);
+    flusher_running = true;
+    flusher = std::thread([this] { flusher_rc = deflate_and_append(busy_raw); });   // fail() keeps the message for lpsh_last_error
+    return 0;
+}
+
+int DeviceBamWriter::close() {
+    int rc = 0;
+    if (flusher_running) { flusher.join(); flusher_running = false; }
+    if (flusher_rc != 0) rc = -1;
+    if (fp) {
+        if (rc == 0) rc = deflate_and_append(raw);
+        if (rc == 0 && fwrite(BGZF_EOF_MARKER, 1, sizeof(BGZF_EOF_MARKER), fp) != sizeof(BGZF_EOF_MARKER)) rc = fail("write output bam file failed");
+        if (fclose(fp) != 0 && rc == 0) rc = fail("closing the output bam failed");
+        fp = nullptr;
+    }
+    if (ctx) { lps_ctx_destroy(ctx); ctx = nullptr; }
+    if (getenv("LPS_TIMING") || bytes_in)
+        std::cerr << "[timing] device BAM writer: " << bytes_in << " -> " << bytes_out << " bytes, deflate calls " << ms_deflate << " ms, file writes " << ms_file << " ms\n";
+    raw.clear(); raw.shrink_to_fit(); busy_raw.clear(); busy_raw.shrink_to_fit(); comp.clear(); comp.shrink_to_fit();
+    return rc;
+}
+
 int TagBamIO::open(const std::string &bam, const std::string &fasta, const std::string &out_path, const std::string &out_mode, int threads,
                    const std::string &command) {
     bam_path = bam;
@@ -230,6 +358,10 @@ int TagBamIO::open(const std::string &bam, const std::string &fasta, const std::
     idx = sam_index_load(in, bam.c_str());
     if (!idx) return fail("Cannot open index for bam file " + bam);
     if (hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool) != 0) return fail("Cannot set thread pool for input bam file " + bam);
+    if (gpu_deflate_requested(out_mode)) {
+        dev_out = new DeviceBamWriter();
+        return dev_out->open(out_path, hdr);
+    }
     out = hts_open(out_path.c_str(), out_mode.c_str());
     if (!out) return fail("Cannot open output bam file " + out_path);
     hts_set_fai_filename(out, fasta.c_str());
@@ -288,6 +420,7 @@ int TagBamIO::close() {
     if (in) sam_close(in);
     int rc = 0;
     if (out && sam_close(out) < 0) rc = fail("closing the output bam failed");
+    if (dev_out) { if (dev_out->close() != 0) rc = -1; delete dev_out; dev_out = nullptr; }
     idx = nullptr; hdr = nullptr; in = nullptr; out = nullptr;
     if (pool.pool) hts_tpool_destroy(pool.pool);
     pool.pool = NULL;
@@ -392,6 +525,11 @@ void load_sample_vcf(const std::string &path, bool tumor, SampleVcf &out) {
 }
 
 }  // namespace lpsh
+
+extern "C" void lpsh_set_deflater(lpsh_deflate_fn fn, void *user) {
+    lpsh::g_deflater = fn;
+    lpsh::g_deflater_user = user;
+}
 
 extern "C" void lpsh_set_inflater(lpsh_inflate_fn fn, void *user) {
     lpsh::g_inflater = fn;

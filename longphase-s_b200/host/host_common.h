@@ -391,7 +391,33 @@ inline uint8_t category_without_variants(int mapq, int flag, const lps_tag_param
 // The files of a tagging pass (BamFileRAII, src/haplotag/HaplotagParsingBam.cpp:20-82: input with index, output with the @PG line
 // `longphase-s` and the same header, one BGZF thread pool for both) and the region in flight with its chunked record reader
 // (htslib's iterator, or the batched-inflate stream when LPS_GPU_INFLATE=1).  Shared by `haplotag` and `somatic_haplotag`.
+// The tagged-BAM writer with the deflate on the device (the writer side; LPS_GPU_DEFLATE): records are
+// serialised the way bam_write1 lays them out (htslib/sam.c:798-864; SAM spec 4.2, long CIGARs as the CG:B,I convention) into a host
+// buffer; a full buffer is handed to a flusher thread, which has the library deflate it into BGZF members (lps_bgzf_deflate, one
+// dynamic-Huffman block per 65 280 bytes) and appends them to the file while the calling thread goes on tagging.  The file ends
+// with htslib's EOF marker.  The uncompressed stream is byte for byte what htslib would have written; the compressed bytes are not.
+struct DeviceBamWriter {
+    FILE *fp = nullptr;
+    std::vector<uint8_t> raw, busy_raw, comp;
+    size_t flush_bytes = (size_t)4096 * 0xff00;      // ~267 MB of records per device call: 4096 members, one thread each
+    std::thread flusher;
+    bool flusher_running = false;
+    int flusher_rc = 0;
+    lps_ctx *ctx = nullptr;                           // the flusher's own context on device 0 (created on first use)
+    double ms_deflate = 0, ms_file = 0;
+    uint64_t bytes_in = 0, bytes_out = 0;
+    int open(const std::string &path, bam_hdr_t *hdr);
+    int write(const bam1_t *b);
+    int close();                                      // flushes, writes the EOF marker, closes the file; < 0 on any error so far
+  private:
+    int hand_over();                                  // waits for the flusher, then gives it `raw`
+    int deflate_and_append(const std::vector<uint8_t> &in);
+};
+// LPS_GPU_DEFLATE=1 (and a plain "wb" BAM output: no --cram, no LPS_BAM_LEVEL)
+bool gpu_deflate_requested(const std::string &out_mode);
+
 struct TagBamIO {
+    DeviceBamWriter *dev_out = nullptr;                // set instead of `out` when the deflate runs on the device
     samFile *in = nullptr, *out = nullptr;
     bam_hdr_t *hdr = nullptr;
     hts_idx_t *idx = nullptr;
@@ -409,7 +435,10 @@ struct TagBamIO {
     int fill(Chunk &ck, size_t max_records);
     void end_region();
     int close();
-    bool is_open() const { return in != nullptr || out != nullptr; }
+    // sam_write1 on the output, or the device writer
+    int write(bam1_t *b) { return dev_out ? dev_out->write(b) : (sam_write1(out, hdr, b) < 0 ? -1 : 0); }
+    bool has_output() const { return out != nullptr || dev_out != nullptr; }
+    bool is_open() const { return in != nullptr || out != nullptr || dev_out != nullptr; }
 };
 
 // Starts the CUDA driver / context on device 0 in the background (seconds on a box without persistence mode), so that it overlaps

@@ -143,6 +143,12 @@ typedef int (*lpsh_inflate_fn)(void *user, const uint8_t *data, uint64_t n_bytes
                                uint8_t *out, uint64_t out_cap);
 void lpsh_set_inflater(lpsh_inflate_fn fn, void *user);
 
+/* With LPS_GPU_DEFLATE=1 the tagging passes write their BAM through a batched deflater: lps_bgzf_deflate on device 0, or this
+ * hook (tests without a GPU hand in the host-compiled member encoder; the signature is lps_bgzf_deflate's minus the context). */
+typedef int (*lpsh_deflate_fn)(void *user, const uint8_t *in, uint64_t in_len, uint32_t block_bytes, uint8_t *out, uint64_t out_cap,
+                               uint64_t *out_len);
+void lpsh_set_deflater(lpsh_deflate_fn fn, void *user);
+
 const char *lpsh_last_error(void);
 
 #ifdef __cplusplus

@@ -822,7 +822,7 @@ int lpsh_som_tag_pack(lpsh_som *h, int i, lpsh_packed *out, lps_tumor_variants *
 static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result *r);
 
 int lpsh_som_tag_emit(lpsh_som *h, int i, const lps_somatic_tag_result *r) {
-    if (!h || !r || h->chunk_contig != i || !h->io.out) return -1;
+    if (!h || !r || h->chunk_contig != i || !h->io.has_output()) return -1;
     return emit_chunk(h, h->chunk, r);
 }
 
@@ -846,7 +846,7 @@ static int emit_chunk(lpsh_som *h, lpsh::Chunk &ck, const lps_somatic_tag_result
                 bam_aux_append(b, "PQ", 'i', sizeof(int), (uint8_t *)&pq);
             }
         }
-        if (sam_write1(h->io.out, h->io.hdr, b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
+        if (h->io.write(b) < 0) { std::cerr << "[ERROR](BamFileRAII): write output bam file failed" << std::endl; return lpsh::fail("write output bam file failed"); }
     }
     // ReadStatistics arrive reduced over the chunk
     h->st_alignment += r->total_alignment; h->st_supplementary += r->total_supplementary; h->st_secondary += r->total_secondary;
@@ -1004,7 +1004,7 @@ int lpsh_som_run(lpsh_som *h) {
 
 void lpsh_som_close(lpsh_som *h) {
     if (!h) return;
-    if (h->io.in || h->io.out) lpsh_som_tag_end(h);
+    if (h->io.is_open()) lpsh_som_tag_end(h);
     delete h;
 }
 

@@ -481,6 +481,110 @@ def test_haplotag_pipelined_run_matches_reference(tmp_path_factory, tmp_path, ch
     assert open(tmp_path / "own" / "tagged.out").read() == open(tmp_path / "ref" / "tagged.out").read()
 
 
+DEFLATE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64))
+
+
+def host_compiled_deflater(calls):
+    """The hook a box without a GPU hands to lpsh_set_deflater: the member encoder of k_bgzf_deflate compiled for the host
+    (lps_bgzf_deflate_block_host), member by member - what lps_bgzf_deflate's kernel writes, byte for byte (tests/test_bgzf_deflate.py)."""
+    lps = ffi.load_library()
+
+    def deflate(user, src, n, block_bytes, dst, cap, out_len):
+        at, n_out = 0, 0
+        slot = (C.c_uint8 * 65312)()
+        got = C.c_uint32(0)
+        while at < n:
+            m = min(block_bytes, n - at)
+            piece = C.cast(C.addressof(src.contents) + at, ffi.u8p)
+            if lps.lps_bgzf_deflate_block_host(piece, m, C.cast(slot, ffi.u8p), 65312, C.byref(got)) != 0 or n_out + got.value > cap:
+                return -1
+            C.memmove(C.addressof(dst.contents) + n_out, slot, got.value)
+            at += m
+            n_out += got.value
+        out_len[0] = n_out
+        calls.append((int(n), n_out))
+        return 0
+    return DEFLATE_FN(deflate)
+
+
+@needs_host
+@needs_ref
+@pytest.mark.parametrize("chunk", [300, 100000])
+def test_device_bam_writer_writes_the_records_htslib_writes(tmp_path_factory, tmp_path, chunk, monkeypatch):
+    """LPS_GPU_DEFLATE=1: records serialised by the host's own writer and deflated in batches (here by the host-compiled member
+    encoder through lpsh_set_deflater; on the GPU box by lps_bgzf_deflate): the uncompressed stream - header, every record, the
+    EOF marker's empty member - is what the reference binary's htslib wrote, and htslib reads the file back."""
+    files = dataset(tmp_path_factory, "plain")
+    vcf = files.get("phased_vcf")
+    if not vcf:
+        d = os.path.join(files["dir"], "phase_ref")
+        run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont", "--indels"]))
+        vcf = files["phased_vcf"] = os.path.join(d, "out.vcf")
+    extra = ["--tagSupplementary"]
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, vcf, extra))
+    lib = hc.host_lib()
+    lib.lpsh_set_deflater.argtypes = [DEFLATE_FN, C.c_void_p]
+    calls = []
+    cb = host_compiled_deflater(calls)
+    lib.lpsh_set_deflater(cb, None)
+    monkeypatch.setenv("LPS_GPU_DEFLATE", "1")
+    if chunk == 300:
+        monkeypatch.setenv("LPS_DEFLATE_BATCH", str(8 * 65280))          # many batches: the flusher thread works beside the tagging loop
+    try:
+        oracle_tag_pipelined(files, vcf, extra, str(tmp_path / "own"), chunk)
+    finally:
+        lib.lpsh_set_deflater(C.cast(None, DEFLATE_FN), None)
+    own_path, ref_path = str(tmp_path / "own" / "tagged.bam"), str(tmp_path / "ref" / "tagged.bam")
+    assert calls and sum(c[0] for c in calls) == len(hc.bam_payload(ref_path))
+    assert (len(calls) > 10 and all(c[0] % 65280 == 0 for c in calls[:-1])) if chunk == 300 else len(calls) == 1
+    assert hc.bam_payload(own_path) == hc.bam_payload(ref_path)
+    raw = open(own_path, "rb").read()
+    assert raw.endswith(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    # htslib's own reader (sam_read1 with a thread pool) walks the file to its end
+    lib.lpsh_decode_only.restype = C.c_int64
+    lib.lpsh_decode_only.argtypes = [C.c_char_p, C.c_int]
+    n_ref = lib.lpsh_decode_only(ref_path.encode(), 2)
+    assert n_ref > 0 and lib.lpsh_decode_only(own_path.encode(), 2) == n_ref
+
+
+@needs_host
+@needs_ref
+def test_device_bam_writer_long_cigar_record(tmp_path, monkeypatch):
+    """A record with more than 65 535 CIGAR operations: BAM keeps <l_qseq>S<rlen>N in the CIGAR field and the real operations in a
+    CG:B,I tag (SAM spec 4.2.2; bam_write1, htslib/sam.c:836-860).  The device writer must lay it out the same way."""
+    from tests import handmade
+    rng = np.random.default_rng(77)
+    ref = "".join(rng.choice(list("ACGT"), 50_000))
+    variants = []
+    for p in range(500, 49_000, 700):
+        alt = "ACGT"[("ACGT".index(ref[p]) + 1) % 4]
+        variants.append((p, ref[p], alt, p // 700 % 2))
+    R = handmade.read_from_ref
+    big = "".join("1M1I" for _ in range(33_000)) + "500M"                        # 66 001 operations, 33 500 reference bases
+    reads = [R(ref, 100, "3000M", "r_a"), R(ref, 200, big, "r_long"), R(ref, 300, "20S4000M10S", "r_b"), R(ref, 30_000, "6S9000M", "r_c"),
+             R(ref, 40_000, "8000M7S", "r_d")]
+    c = handmade.ManualContig(ref, variants, reads)
+    assert int(c.n_cigar.max()) > 65535
+    os.makedirs(tmp_path / "data")
+    files = hc.write_dataset(str(tmp_path / "data"), [("chrL", c, True)])
+    d = str(tmp_path / "phase_ref")
+    run_in(d, [hc.REF_BIN] + phase_args(files, ["--ont"]))
+    vcf = os.path.join(d, "out.vcf")
+    run_in(str(tmp_path / "ref"), [hc.REF_BIN] + tag_args(files, vcf, []))
+    lib = hc.host_lib()
+    lib.lpsh_set_deflater.argtypes = [DEFLATE_FN, C.c_void_p]
+    calls = []
+    cb = host_compiled_deflater(calls)
+    lib.lpsh_set_deflater(cb, None)
+    monkeypatch.setenv("LPS_GPU_DEFLATE", "1")
+    try:
+        oracle_tag_pipelined(files, vcf, [], str(tmp_path / "own"), 100000)
+    finally:
+        lib.lpsh_set_deflater(C.cast(None, DEFLATE_FN), None)
+    own, want = hc.bam_payload(str(tmp_path / "own" / "tagged.bam")), hc.bam_payload(str(tmp_path / "ref" / "tagged.bam"))
+    assert b"CGBI" in want and own == want
+
+
 @needs_host
 @needs_ref
 def test_bam_level_changes_the_file_not_the_records(tmp_path_factory, tmp_path):
