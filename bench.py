@@ -230,6 +230,51 @@ def bench_bgzf(ctx, host, ffi, torch, ncores, args, mb=1024):
             "cpu_zlib_out_gb_per_s": done / cpu_s / 1e9, "cpu_cores": ncores, "cpu_sample": "%d MB inflated per core, python zlib (libz inflate, GIL released)" % (len(unit) >> 20)}
 
 
+def bench_bgzf_deflate(ctx, ncores, args, peak, mb=256):
+    """SURVEY 8f rank 1, the writer side: deflation of BAM-like bytes into BGZF members (htslib bgzf_write / deflate_block).  Kernel
+    time and the time of the whole call (pageable host buffers in and out), size and speed of zlib on all host cores beside it, and a
+    round trip of the first members through zlib (CRC32 and ISIZE checked by the gzip reader)."""
+    import gzip
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    from tests import bgzf_cases
+    rng = np.random.default_rng(3)
+    tile = bgzf_cases.bam_like(rng, 8 << 20)
+    data = np.frombuffer((tile * (mb // 8 + 1))[:mb << 20], np.uint8).copy()
+    data[::4099] ^= rng.integers(0, 255, len(data[::4099])).astype(np.uint8)      # the tiles are not identical
+    ctx.bgzf_deflate(data[:1 << 20])
+    wall, kern, comp = [], [], None
+    for _ in range(max(1, min(args.steps, 3))):
+        t0 = time.perf_counter()
+        comp = ctx.bgzf_deflate(data)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        kern.append(ctx.stats()["ms_kernel_bgzf"])
+    buf, pos, members = comp.tobytes(), 0, 0
+    while pos < len(buf) and members < 32:
+        pos += int.from_bytes(buf[pos + 16:pos + 18], "little") + 1
+        members += 1
+    if gzip.decompress(buf[:pos]) != data[:members * 65280].tobytes():
+        raise RuntimeError("the deflated members do not inflate to the input")
+    sample = data[:min(len(data), 64 << 20)].tobytes()
+
+    def one(i):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        return len(co.compress(sample[i:i + 65280]) + co.flush()) + 26
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=ncores) as tp:
+        z_bytes = sum(tp.map(one, range(0, len(sample), 65280)))
+    z_s = time.perf_counter() - t0
+    k, w = float(np.mean(kern)), float(np.mean(wall))
+    alg = 2 * len(data) + 2 * len(comp)
+    return {"config": "%d MB of BAM-like bytes, %d members of 65280 bytes, one dynamic-Huffman block of literals each" % (mb, (len(data) + 65279) // 65280),
+            "kernel_ms": k, "in_gb_per_s": len(data) / (k * 1e-3) / 1e9, "call_ms_host_buffers": w, "call_in_gb_per_s": len(data) / (w * 1e-3) / 1e9,
+            "ratio": len(comp) / len(data), "cpu_zlib_level6": {"ratio": z_bytes / len(sample), "in_gb_per_s": len(sample) / z_s / 1e9, "cores": ncores},
+            "roofline": {"bound": "hbm", "kernel": "k_bgzf_deflate", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg), "kernel_ms": k,
+                         "note": "two passes over the input, the slots written once, one copy into the stream; one thread per member: the time is "
+                                 "a member's latency chain through its local-memory tables, not bytes"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -683,6 +728,11 @@ def main():
             other["bgzf_inflate"] = bench_bgzf(ctxs[0], host, ffi, torch, ncores, args)
         except Exception as e:
             other["bgzf_inflate"] = {"error": repr(e)}
+        try:
+            other["bgzf_deflate"] = bench_bgzf_deflate(ctxs[0], ncores, args, peak)
+            line["rooflines"].append(other["bgzf_deflate"]["roofline"])
+        except Exception as e:
+            other["bgzf_deflate"] = {"error": repr(e)}
         line["other_paths"] = other
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

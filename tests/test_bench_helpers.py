@@ -67,3 +67,30 @@ def test_missing_sysfs_is_not_an_error(monkeypatch):
         def get_device_properties(self, d):
             raise RuntimeError("no CUDA")
     assert bench.bind_to_gpu_numa(types.SimpleNamespace(cuda=Broken()), 0, 2, 4).startswith("unchanged")
+
+
+def test_deflate_leg_runs_against_a_stand_in_context():
+    """bench.py's BGZF deflate leg end to end, with the host-compiled member encoder standing in for the device call: the leg's own
+    checks (members inflate to the input, sizes against zlib) and the shape of what it reports."""
+    import ctypes as C
+    import importlib
+
+    import numpy as np
+    bench.entry.load_package()
+    ffi = importlib.import_module("longphase_s_b200._ffi")
+    lib = ffi.load_library()
+
+    class StandIn:
+        def bgzf_deflate(self, data, block_bytes=0xff00):
+            out, slot, n = [], np.zeros(65312, np.uint8), C.c_uint32(0)
+            for i in range(0, len(data), block_bytes):
+                piece = np.ascontiguousarray(data[i:i + block_bytes])
+                assert lib.lps_bgzf_deflate_block_host(ffi.ptr(piece, ffi.u8p), len(piece), ffi.ptr(slot, ffi.u8p), 65312, C.byref(n)) == 0
+                out.append(slot[:n.value].copy())
+            return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+        def stats(self):
+            return {"ms_kernel_bgzf": 2.0}
+    r = bench.bench_bgzf_deflate(StandIn(), 2, types.SimpleNamespace(steps=1), 6534.8, mb=8)
+    assert 0.5 < r["ratio"] < 0.8 and r["ratio"] < 1.1 * r["cpu_zlib_level6"]["ratio"]
+    assert r["roofline"]["kernel"] == "k_bgzf_deflate" and r["roofline"]["algorithmic_bytes_per_launch"] > 2 * (8 << 20)
