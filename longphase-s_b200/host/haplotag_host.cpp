@@ -529,6 +529,7 @@ int lpsh_tag_run(lpsh_tag *h) {
     if (!h) return -1;
     DeviceJudge d;   // no device -> the first chunk fails with "no usable CUDA device"; nothing is ever judged on the host
     lpsh_tag_params(h, &d.tp);
+    h->io.device_pass = true;   // the tagged BAM is deflated on the device as well (LPS_GPU_DEFLATE=0: htslib's writer)
     const int rc = lpsh_tag_run_with(h, device_judge, &d);
     std::cerr << "[timing] judge on the device: context " << d.ms_create << " ms, contig tables " << d.ms_tables << " ms, lps_batch_submit " << d.ms_submit
               << " ms, lps_tag_reads " << d.ms_tag << " ms\n";

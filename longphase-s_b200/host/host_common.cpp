@@ -228,9 +228,11 @@ void put_le32(std::vector<uint8_t> &v, uint32_t x) {
 }
 }  // namespace
 
-bool gpu_deflate_requested(const std::string &out_mode) {
+bool gpu_deflate_requested(const std::string &out_mode, bool device_pass) {
+    if (out_mode != "wb") return false;
     const char *e = getenv("LPS_GPU_DEFLATE");
-    return e && e[0] == '1' && e[1] == '\0' && out_mode == "wb";
+    if (e && e[0] && !e[1]) { if (e[0] == '1') return true; if (e[0] == '0') return false; }
+    return device_pass;
 }
 
 int DeviceBamWriter::open(const std::string &path, bam_hdr_t *hdr) {
@@ -358,7 +360,7 @@ int TagBamIO::open(const std::string &bam, const std::string &fasta, const std::
     idx = sam_index_load(in, bam.c_str());
     if (!idx) return fail("Cannot open index for bam file " + bam);
     if (hts_set_opt(in, HTS_OPT_THREAD_POOL, &pool) != 0) return fail("Cannot set thread pool for input bam file " + bam);
-    if (gpu_deflate_requested(out_mode)) {
+    if (gpu_deflate_requested(out_mode, device_pass)) {
         dev_out = new DeviceBamWriter();
         return dev_out->open(out_path, hdr);
     }

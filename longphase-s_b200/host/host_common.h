@@ -413,11 +413,14 @@ struct DeviceBamWriter {
     int hand_over();                                  // waits for the flusher, then gives it `raw`
     int deflate_and_append(const std::vector<uint8_t> &in);
 };
-// LPS_GPU_DEFLATE=1 (and a plain "wb" BAM output: no --cram, no LPS_BAM_LEVEL)
-bool gpu_deflate_requested(const std::string &out_mode);
+// The device writes plain "wb" BAM output (no --cram, no LPS_BAM_LEVEL) when LPS_GPU_DEFLATE=1, never when it is 0, and otherwise
+// when the device is the judge of the pass as well (`device_pass`: the product binaries; a pass driven by a caller's own judge -
+// the CPU tests - keeps htslib's writer unless asked).
+bool gpu_deflate_requested(const std::string &out_mode, bool device_pass);
 
 struct TagBamIO {
     DeviceBamWriter *dev_out = nullptr;                // set instead of `out` when the deflate runs on the device
+    bool device_pass = false;                          // the pass is judged on the device (lpsh_tag_run / lpsh_som_run)
     samFile *in = nullptr, *out = nullptr;
     bam_hdr_t *hdr = nullptr;
     hts_idx_t *idx = nullptr;

@@ -996,6 +996,7 @@ int lpsh_som_run(lpsh_som *h) {
     d.ctx = ctx;
     d.tp = tp;
     if (rc == 0 && !ctx) { lpsh::fail("no contig to process"); rc = -1; }
+    h->io.device_pass = true;   // the tagged BAM is deflated on the device as well (LPS_GPU_DEFLATE=0: htslib's writer)
     if (rc == 0) rc = lpsh_som_tag_run_with(h, som_device_judge, &d);
     if (rc != 0 && !d.error.empty()) lpsh::fail(d.error);
     if (ctx) lps_ctx_destroy(ctx);

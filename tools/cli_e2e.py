@@ -90,13 +90,13 @@ def main():
         tag_nolog = [w for w in tag if w != "--log"]
         ref2_s, _ = timed([hc.REF_BIN] + tag_nolog, os.path.join(d, "ref_nolog"))
         out["deflate"]["reference_no_log_s"] = round(ref2_s, 3)
-        for name, extra in (("htslib_writer", {}), ("gpu_deflate", {"LPS_GPU_DEFLATE": "1"}), ("gpu_deflate_readers_4", {"LPS_GPU_DEFLATE": "1", "LPS_TAG_READERS": "4"})):
+        for name, extra in (("htslib_writer", {"LPS_GPU_DEFLATE": "0"}), ("gpu_deflate", {"LPS_GPU_DEFLATE": "1"}), ("gpu_deflate_readers_4", {"LPS_GPU_DEFLATE": "1", "LPS_TAG_READERS": "4"})):
             env = dict(os.environ, **extra)
             s_tag, err_t = timed([hc.HOST_BIN] + tag_nolog, os.path.join(d, name), env)
             v = {"haplotag_s": round(s_tag, 3), "bam_bytes": os.path.getsize(os.path.join(d, name, "tagged.bam")),
                  "haplotag_identical": hc.bam_payload(os.path.join(d, name, "tagged.bam")) == hc.bam_payload(os.path.join(d, "ref_nolog", "tagged.bam")),
                  "timing": [ln for ln in err_t.split("\n") if ln.startswith("[timing]")]}
-            if extra:
+            if extra.get("LPS_GPU_DEFLATE") == "1":
                 v["htslib_reads_it"] = int(lib.lpsh_decode_only(os.path.join(d, name, "tagged.bam").encode(), a.threads)) == int(n_dec)
             out["deflate"][name] = v
     out["own_timing_lines"] = [ln for ln in (own_err + tag_err).split("\n") if ln.startswith("[timing]") or ln.startswith("tag read") or ln.startswith("parsing total")]
