@@ -158,3 +158,11 @@ def test_gpu_deflate_matches_the_host_compiled_encoder_and_inflates():
         assert len(ctx.bgzf_deflate(np.zeros(0, np.uint8), 65280)) == 0
     finally:
         ctx.close()
+
+
+def test_member_bytes_are_pinned():
+    """The encoder is deterministic and its choices (tie order of the Huffman merge, header without run-length symbols) are part of
+    what the kernel must reproduce: the member of a fixed input hashes to a committed value."""
+    import hashlib
+    m = member_host(payloads()["bam_like_tail"])
+    assert len(m) == 8482 and hashlib.sha256(m).hexdigest() == "522ba0bf9c02ddcfdfe93f0b0bf6c52b3834f1752c863f16ce6dd39694a082f1"

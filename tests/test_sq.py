@@ -71,3 +71,13 @@ def test_batch_packer_on_a_contig():
     # rows tile the stream without gaps
     rows = np.array([int(lib.lps_sq_row_bytes(int(x))) for x in contig.l_qseq])
     assert np.array_equal(sq_off[1:], np.cumsum(rows)[:-1].astype(np.uint64))
+
+
+def test_wire_format_is_pinned():
+    """The rows of a fixed synthetic contig hash to a committed value: a change of the layout (unit size, byte order of the
+    qualities, nibble packing) has to be made on purpose, in the kernel, the packer and here."""
+    import hashlib
+    contig, _ = cases.get("snp_only")
+    sq, sq_off = contig.pack_sq(threads=1)
+    assert len(sq) == 24242016
+    assert hashlib.sha256(sq.tobytes() + sq_off.tobytes()).hexdigest() == "9d51025d11666b78a55d4c246e7a51c07a95e595a62e73cd119a40d72f589cc7"
