@@ -247,16 +247,16 @@ int DeviceBamWriter::open(const std::string &path, bam_hdr_t *hdr) {
     const size_t l_text = sam_hdr_length(hdr);
     if (!text || l_text == SIZE_MAX || l_text > UINT32_MAX) return fail("Cannot write header to output bam file " + path);
     raw.reserve(flush_bytes + (1u << 20));
-    raw.insert(raw.end(), {'B', 'A', 'M', 1});
-    put_le32(raw, (uint32_t)l_text);
-    raw.insert(raw.end(), text, text + l_text);
-    put_le32(raw, (uint32_t)hdr->n_targets);
+    header.insert(header.end(), {'B', 'A', 'M', 1});
+    put_le32(header, (uint32_t)l_text);
+    header.insert(header.end(), text, text + l_text);
+    put_le32(header, (uint32_t)hdr->n_targets);
     for (int i = 0; i < hdr->n_targets; i++) {
         const char *name = hdr->target_name[i];
         const size_t n = strlen(name) + 1;
-        put_le32(raw, (uint32_t)n);
-        raw.insert(raw.end(), name, name + n);
-        put_le32(raw, hdr->target_len[i]);
+        put_le32(header, (uint32_t)n);
+        header.insert(header.end(), name, name + n);
+        put_le32(header, hdr->target_len[i]);
     }
     return 0;
 }
@@ -297,6 +297,11 @@ int DeviceBamWriter::write(const bam1_t *b) {
 }
 
 int DeviceBamWriter::deflate_and_append(const std::vector<uint8_t> &in) {
+    if (!header_written) {                                    // first call: the header's own members, then the records
+        header_written = true;
+        const int rc = deflate_and_append(header);
+        if (rc != 0) return rc;
+    }
     if (in.empty()) return 0;
     const double t0 = now_ms();
     const uint64_t cap = lps_bgzf_deflate_bound(in.size(), 0xff00);

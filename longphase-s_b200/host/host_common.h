@@ -398,7 +398,8 @@ inline uint8_t category_without_variants(int mapq, int flag, const lps_tag_param
 // with htslib's EOF marker.  The uncompressed stream is byte for byte what htslib would have written; the compressed bytes are not.
 struct DeviceBamWriter {
     FILE *fp = nullptr;
-    std::vector<uint8_t> raw, busy_raw, comp;
+    std::vector<uint8_t> header, raw, busy_raw, comp;   // the BAM header goes into members of its own, as bam_hdr_write's bgzf_flush leaves it
+    bool header_written = false;
     size_t flush_bytes = (size_t)4096 * 0xff00;      // ~267 MB of records per device call: 4096 members, one thread each
     std::thread flusher;
     bool flusher_running = false;
